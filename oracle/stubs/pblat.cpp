@@ -1,0 +1,70 @@
+// Stub `pblat` / `blat` for the oracle harness — TEST INFRASTRUCTURE ONLY.
+//
+// The reference's refinement() (AlignGraph.cpp:2976) shells out to `pblat <db.fa> <query.fa> -noHead <out.psl>
+// -fastMap -threads=8`.  BLAT is not installed in this image, so the harness puts this stand-in on $PATH for BOTH
+// implementations: it reports, for every query, every ungapped placement in a database sequence (either strand)
+// that is seeded by an exact 24-mer and has >= 90 % identity over the full query, as a single-block PSL line.
+// That is enough for the containment test at AlignGraph.cpp:3059 and keeps both sides on identical aligner output.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <fstream>
+#include <set>
+#include <unordered_map>
+
+static void load(const char* path, std::vector<std::string>& names, std::vector<std::string>& seqs) {
+    std::ifstream in(path);
+    if (!in.is_open()) { fprintf(stderr, "stub pblat: cannot open %s\n", path); exit(1); }
+    std::string line;
+    while (std::getline(in, line)) {
+        if (line.empty()) continue;
+        if (line[0] == '>') { names.push_back(line.substr(1)); seqs.emplace_back(); }
+        else if (!seqs.empty()) seqs.back() += line;
+    }
+}
+static std::string rc(const std::string& s) {
+    std::string r(s.rbegin(), s.rend());
+    for (auto& c : r) c = c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : c;
+    return r;
+}
+
+int main(int argc, char** argv) {
+    std::vector<const char*> pos;
+    for (int i = 1; i < argc; i++) if (argv[i][0] != '-') pos.push_back(argv[i]);
+    if (pos.size() < 3) { fprintf(stderr, "usage: pblat db.fa query.fa [-noHead] out.psl\n"); return 1; }
+    std::vector<std::string> tn, ts, qn, qs;
+    load(pos[0], tn, ts);
+    load(pos[1], qn, qs);
+    FILE* out = fopen(pos[2], "w");
+    if (!out) return 1;
+    const size_t K = 24;
+    // index database 24-mers sampled at every position (hash -> list of (target, offset))
+    std::unordered_multimap<std::string, std::pair<int, long>> idx;
+    for (size_t t = 0; t < ts.size(); t++)
+        for (size_t i = 0; i + K <= ts[t].size(); i += 1) idx.emplace(ts[t].substr(i, K), std::make_pair((int)t, (long)i));
+    for (size_t q = 0; q < qs.size(); q++) {
+        for (int strand = 0; strand < 2; strand++) {
+            std::string s = strand ? rc(qs[q]) : qs[q];
+            if (s.size() < K) continue;
+            std::set<std::pair<int, long>> seen;
+            for (size_t off = 0; off + K <= s.size(); off += std::max<size_t>(K, s.size() / 16)) {
+                auto range = idx.equal_range(s.substr(off, K));
+                for (auto it = range.first; it != range.second; ++it) {
+                    int t = it->second.first; long start = it->second.second - (long)off;
+                    if (start < 0 || start + (long)s.size() > (long)ts[t].size()) continue;
+                    if (!seen.insert({t, start}).second) continue;
+                    long match = 0;
+                    for (size_t i = 0; i < s.size(); i++) match += (s[i] == ts[t][start + i]);
+                    if (match * 10 < (long)s.size() * 9) continue;
+                    fprintf(out, "%ld\t%ld\t0\t0\t0\t0\t0\t0\t%c\t%s\t%zu\t0\t%zu\t%s\t%zu\t%ld\t%ld\t1\t%zu,\t0,\t%ld,\n", match,
+                            (long)s.size() - match, strand ? '-' : '+', qn[q].c_str(), s.size(), s.size(), tn[t].c_str(),
+                            ts[t].size(), start, start + (long)s.size(), s.size(), start);
+                }
+            }
+        }
+    }
+    fclose(out);
+    return 0;
+}
