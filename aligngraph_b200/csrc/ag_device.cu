@@ -1,0 +1,820 @@
+// B200 (sm_100a) device pipeline of the AlignGraph hot path: positional de Bruijn graph build (AG:1635-1870, AG:1353-1624),
+// coverage filter (AG:1904-1918) and extension walk (AG:1954-2204).  Integer / indexing work, HBM- and latency-bound: no tensor
+// cores.  See DESIGN.md §3-§5 for the formulation, the HBM layout and the per-kernel algorithmic bytes.
+//
+//   k_prep        1 thread / alignment   resolve left mate, touch range, tile count               (AG:1657-1679)
+//   k_keys        1 thread / alignment   emit (tile, alignment) keys in alignment order
+//   radix sort    stable LSD, 4-bit      bucket alignments by 256-position tile, order preserved
+//   k_nodes       1 CTA / tile, 1 thread / position   ordered first-compatible clustering      (AG:1353-1587)
+//   k_finalize    1 thread / position    position-ordered node table, consensus base, coverage filter (AG:1904-1918, 1944-1952)
+//   k_edges       1 CTA / tile           de-duplicated successor sets                            (AG:1590-1623)
+//   k_uf_*        union-find             independent walk components
+//   k_walk_*      1 thread / component   exact replay of the greedy walk                         (AG:1972-2162)
+//   k_materialize 1 thread / emitted walk  base strings
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include "ag_core.h"
+#include "ag_device.cuh"
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) throw AgError{std::string(#x) + ": " + cudaGetErrorString(e_)}; } while (0)
+
+namespace {
+
+template <class T> struct DBuf {
+    T* p = nullptr; size_t cap = 0;
+    void ensure(size_t n) {
+        if (n <= cap) return;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t nc = n + n / 16 + 256;
+        CK(cudaMalloc((void**)&p, nc * sizeof(T)));
+        cap = nc;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// exclusive scan (u32), out has n + 1 entries (out[n] = total)
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr int SCAN_T = 256, SCAN_I = 8, SCAN_B = SCAN_T * SCAN_I;
+
+__device__ __forceinline__ u32 block_excl_scan(u32 v, u32* smem /* 32 */, u32& total) {
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    u32 x = v;
+    for (int o = 1; o < 32; o <<= 1) { u32 y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) smem[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        u32 w = lane < nw ? smem[lane] : 0, s = w;
+        for (int o = 1; o < 32; o <<= 1) { u32 y = __shfl_up_sync(0xFFFFFFFFu, s, o); if (lane >= o) s += y; }
+        smem[lane] = s - w;  // exclusive warp offsets
+        if (lane == 31) smem[32] = s;
+    }
+    __syncthreads();
+    u32 r = x - v + smem[warp];
+    total = smem[32];
+    __syncthreads();
+    return r;
+}
+
+__global__ void k_scan_sums(const u32* __restrict__ in, u32* __restrict__ sums, size_t n) {
+    __shared__ u32 sm[33];
+    size_t base = (size_t)blockIdx.x * SCAN_B + (size_t)threadIdx.x * SCAN_I;
+    u32 s = 0;
+    for (int i = 0; i < SCAN_I; i++) if (base + i < n) s += in[base + i];
+    u32 total; block_excl_scan(s, sm, total);
+    if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+__global__ void k_scan_apply(const u32* __restrict__ in, u32* __restrict__ out, const u32* __restrict__ offs, size_t n, int write_total) {
+    __shared__ u32 sm[33];
+    size_t base = (size_t)blockIdx.x * SCAN_B + (size_t)threadIdx.x * SCAN_I;
+    u32 v[SCAN_I], s = 0;
+    for (int i = 0; i < SCAN_I; i++) { v[i] = (base + i < n) ? in[base + i] : 0; s += v[i]; }
+    u32 total; u32 ex = block_excl_scan(s, sm, total) + (offs ? offs[blockIdx.x] : 0);
+    for (int i = 0; i < SCAN_I; i++) { if (base + i < n) out[base + i] = ex; ex += v[i]; }
+    if (write_total && blockIdx.x == gridDim.x - 1 && threadIdx.x == SCAN_T - 1) out[n] = ex;
+}
+
+struct Scanner {
+    DBuf<u32> lvl[4];
+    u64* launches = nullptr;
+    void run(const u32* in, u32* out, size_t n, cudaStream_t st, int depth = 0, int write_total = 1) {
+        if (n == 0) { if (write_total) CK(cudaMemsetAsync(out, 0, sizeof(u32), st)); return; }
+        size_t nb = (n + SCAN_B - 1) / SCAN_B;
+        if (nb == 1) { k_scan_apply<<<1, SCAN_T, 0, st>>>(in, out, nullptr, n, write_total); if (launches) ++*launches; return; }
+        if (depth >= 4) throw AgError{"scan depth"};
+        lvl[depth].ensure(nb + 1);
+        k_scan_sums<<<(unsigned)nb, SCAN_T, 0, st>>>(in, lvl[depth].p, n);
+        if (launches) ++*launches;
+        run(lvl[depth].p, lvl[depth].p, nb, st, depth + 1, 0);
+        k_scan_apply<<<(unsigned)nb, SCAN_T, 0, st>>>(in, out, lvl[depth].p, n, write_total);
+        if (launches) ++*launches;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// stable LSD radix sort of (key = tile, val = alignment index), 4 bits per pass
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr int RS_T = 256, RS_I = 8, RS_B = RS_T * RS_I;
+
+__global__ void k_rs_hist(const u32* __restrict__ keys, u32* __restrict__ hist, size_t n, int shift, unsigned nb) {
+    __shared__ u32 h[16];
+    if (threadIdx.x < 16) h[threadIdx.x] = 0;
+    __syncthreads();
+    size_t base = (size_t)blockIdx.x * RS_B;
+    for (int i = threadIdx.x; i < RS_B; i += RS_T) if (base + i < n) atomicAdd(&h[(keys[base + i] >> shift) & 15], 1u);
+    __syncthreads();
+    if (threadIdx.x < 16) hist[(size_t)threadIdx.x * nb + blockIdx.x] = h[threadIdx.x];
+}
+
+__global__ void k_rs_scatter(const u32* __restrict__ keys, const u32* __restrict__ vals, u32* __restrict__ okeys, u32* __restrict__ ovals,
+                             const u32* __restrict__ hist_scanned, size_t n, int shift, unsigned nb) {
+    __shared__ u32 cnt[16 * RS_T];  // [digit][thread]
+    __shared__ u32 sm[33];
+    __shared__ u32 bin_start[17];
+    const int t = threadIdx.x;
+    size_t base = (size_t)blockIdx.x * RS_B + (size_t)t * RS_I;
+    u32 k[RS_I], v[RS_I];
+    for (int d = 0; d < 16; d++) cnt[d * RS_T + t] = 0;
+    for (int i = 0; i < RS_I; i++)
+        if (base + i < n) { k[i] = keys[base + i]; v[i] = vals[base + i]; cnt[((k[i] >> shift) & 15) * RS_T + t]++; }
+    __syncthreads();
+    // exclusive scan of the 4096 counters in (digit, thread) order: thread t owns flat entries [16 t, 16 t + 16)
+    u32 loc[16], s = 0;
+    for (int j = 0; j < 16; j++) { loc[j] = cnt[t * 16 + j]; s += loc[j]; }
+    u32 total; u32 ex = block_excl_scan(s, sm, total);
+    for (int j = 0; j < 16; j++) { cnt[t * 16 + j] = ex; ex += loc[j]; }
+    __syncthreads();
+    if (t < 16) bin_start[t] = cnt[t * RS_T];
+    if (t == 0) bin_start[16] = total;
+    __syncthreads();
+    for (int i = 0; i < RS_I; i++)
+        if (base + i < n) {
+            u32 d = (k[i] >> shift) & 15;
+            u32 r = cnt[d * RS_T + t]++;
+            size_t dst = (size_t)hist_scanned[(size_t)d * nb + blockIdx.x] + (r - bin_start[d]);
+            okeys[dst] = k[i]; ovals[dst] = v[i];
+        }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// device view of one unit
+// ---------------------------------------------------------------------------------------------------------------------------
+struct DevView {
+    ag_reads reads;
+    const unsigned char* ref; u32 n_ref, n_pos;
+    ag_cmtab cmt; const u32* chain_pos; const unsigned char* chain_base;
+    const ag_aln* aln; u32 n_aln; const ag_seg* ext;
+    ag_alnp* alnp; u32* lo; u32* span; u32* ntiles; u32* key_off;
+    u32* keys; u32* vals; u32* tile_cnt; u32* tile_start; u32 n_tiles;
+    ag_nodeb* pool; u32* pool_count; u32 pool_cap;
+    ag_ovfpool ovf;
+    u32* pos_cnt; u32* pos_pool; u32* pos_node;
+    ag_nodem* node_m; ag_nodew* node_w; u32* node_sref; u32* node_pos;
+    u32* eovf_head; u32* eovf_target; u32* eovf_next; u32* eovf_count; u32 eovf_cap;
+    unsigned char* trav; u32* walk_next; u32* parent; u32* cmin; u32* cmax;
+    ag_walk* walks; u32* walk_count; u32 walk_cap;
+    int* err;
+    int k, iv, coverage;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// k_prep / k_keys
+// ---------------------------------------------------------------------------------------------------------------------------
+__global__ void k_prep(DevView d) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.n_aln) return;
+    ag_aln a = d.aln[i];
+    u32 len = d.reads.len[a.pair];
+    ag_prep_out o = ag_prep(a, d.ext, len, (u32)d.k);
+    // every aligned position of either mate must lie inside the unit (the reference indexes genome[0] with them, AG:1369)
+    ag_segv L, R; ag_alnp_segs(o.p, d.ext, L, R);
+    bool bad = false;
+    for (u32 j = 0; j < L.n; j++) { ag_seg s = L.get(j); if (s.dst + s.len > d.n_ref || s.src + s.len > len) bad = true; }
+    for (u32 j = 0; j < R.n; j++) { ag_seg s = R.get(j); if (s.dst + s.len > d.n_ref || s.src + s.len > len) bad = true; }
+    if (bad) { *d.err = 2; o.any = 0; }
+    d.alnp[i] = o.p; d.lo[i] = o.lo; d.span[i] = o.span;
+    d.ntiles[i] = o.any ? ((o.lo + o.span) / AG_TILE - o.lo / AG_TILE + 1) : 0;
+}
+
+__global__ void k_keys(DevView d) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.n_aln) return;
+    u32 n = d.ntiles[i];
+    if (!n) return;
+    u32 off = d.key_off[i], t0 = d.lo[i] / AG_TILE;
+    for (u32 j = 0; j < n; j++) { d.keys[off + j] = t0 + j; d.vals[off + j] = i; atomicAdd(&d.tile_cnt[t0 + j], 1u); }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// k_nodes: one CTA per tile of AG_TILE positions, one thread per position.  The tile's alignments arrive sorted by global
+// alignment index and are staged through shared memory in chunks; a thread tests each against its position and replays the
+// reference's first-compatible clustering in order.
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr int NCHUNK = 128;
+
+__global__ void __launch_bounds__(AG_TILE) k_nodes(DevView d) {
+    __shared__ ag_alnp s_rec[NCHUNK];
+    __shared__ u32 s_lo[NCHUNK], s_span[NCHUNK];
+    __shared__ u32 s_scan[33];
+    __shared__ u32 s_base;
+    const u32 tile = blockIdx.x, q = tile * AG_TILE + threadIdx.x;
+    const bool active = q < d.n_ref;
+    ag_nodelist nl; nl.init();
+    const u32 kb = d.tile_start[tile], ke = d.tile_start[tile + 1];
+    for (u32 c0 = kb; c0 < ke; c0 += NCHUNK) {
+        u32 cn = min((u32)NCHUNK, ke - c0);
+        if (threadIdx.x < cn) {
+            u32 idx = d.vals[c0 + threadIdx.x];
+            s_rec[threadIdx.x] = d.alnp[idx]; s_lo[threadIdx.x] = d.lo[idx]; s_span[threadIdx.x] = d.span[idx];
+        }
+        __syncthreads();
+        if (active)
+            for (u32 a = 0; a < cn; a++) {
+                if (q - s_lo[a] > s_span[a]) continue;
+                const ag_alnp p = s_rec[a];
+                ag_touch t = ag_locate(p, d.ext, q, (u32)d.k);
+                if (!t.kind) continue;
+                int code = -1;
+                if (t.kind == 1 && t.slen) code = d.reads.code(p.left_read, p.len_nseg & 0xFFFFu, t.soff);
+                const u32 sref = p.left_read, sl = t.soff | (t.slen << 16);
+                const bool bump = t.kind == 1;
+                ag_for_candidates(d.cmt, q, t.mate, [&](const ag_nodem& c) { ag_node_touch(nl, d.ovf, c, bump, code, sref, sl, d.iv); });
+            }
+        __syncthreads();
+    }
+    // write the tile's nodes to the pool (tile order in the pool is arbitrary; k_finalize restores position order)
+    u32 total; u32 ex = block_excl_scan(active ? nl.n : 0u, s_scan, total);
+    if (threadIdx.x == 0) {
+        u32 b = total ? atomicAdd(d.pool_count, total) : 0;
+        if (total && b + total > d.pool_cap) { *d.err = 3; b = AG_NONE; }
+        s_base = b;
+    }
+    __syncthreads();
+    if (!active) return;
+    d.pos_cnt[q] = nl.n;
+    if (s_base == AG_NONE) { d.pos_pool[q] = 0; return; }
+    u32 w = s_base + ex;
+    d.pos_pool[q] = w;
+    u32 nloc = nl.n < AG_NODE_CAP ? nl.n : AG_NODE_CAP;
+    for (u32 i = 0; i < nloc; i++) d.pool[w++] = nl.loc[i];
+    if (nl.n > AG_NODE_CAP) for (u32 o = nl.ovf_head; o != AG_NONE; o = d.ovf.next[o]) d.pool[w++] = d.ovf.node[o];
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// k_finalize: position-ordered final table
+// ---------------------------------------------------------------------------------------------------------------------------
+__global__ void k_finalize(DevView d) {
+    u32 q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= d.n_ref) return;
+    u32 n = d.pos_cnt[q];
+    if (!n) return;
+    u32 src = d.pos_pool[q], dst = d.pos_node[q];
+    char refb = (char)d.ref[q];
+    for (u32 i = 0; i < n; i++) {
+        ag_nodeb b = d.pool[src + i];
+        ag_nodem m; m.cid = b.cid; m.coff = b.coff; m.cid0 = b.cid0; m.coff0 = b.coff0; m.moff = b.moff;
+        d.node_m[dst + i] = m;
+        ag_nodew w; w.succ0 = w.succ1 = AG_NONE; w.moff = b.moff;
+        u32 misc = (u32)(unsigned char)ag_consensus(b.cnt, refb);
+        if (b.cid == AG_NONE && (int)b.cov < d.coverage) misc |= AG_NW_FILTERED;  // AG:1912-1915
+        if (b.coff != AG_NONE) misc |= AG_NW_HASCONTIG;                           // AG:2004
+        w.misc = misc;
+        d.node_w[dst + i] = w;
+        d.node_sref[2 * (size_t)(dst + i)] = b.sread; d.node_sref[2 * (size_t)(dst + i) + 1] = b.soff_len;
+        d.node_pos[dst + i] = q;
+        d.trav[dst + i] = (misc & AG_NW_FILTERED) ? 1 : 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// k_edges: same sweep as k_nodes, now against the FINAL table: for every call starting at q resolve the candidates on both
+// sides to their first-compatible nodes and add the edge once  (AG:1590-1623)
+// ---------------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void add_edge(const DevView& d, u32 v, u32 tgt) {
+    ag_nodew* w = &d.node_w[v];
+    if (w->succ0 == tgt || w->succ1 == tgt) return;
+    if (w->succ0 == AG_NONE) { w->succ0 = tgt; return; }
+    if (w->succ1 == AG_NONE) { w->succ1 = tgt; return; }
+    if (w->misc & AG_NW_OVF) { for (u32 o = d.eovf_head[v]; o != AG_NONE; o = d.eovf_next[o]) if (d.eovf_target[o] == tgt) return; }
+    u32 o = atomicAdd(d.eovf_count, 1u);
+    if (o >= d.eovf_cap) { *d.err = 4; return; }
+    d.eovf_target[o] = tgt;
+    d.eovf_next[o] = (w->misc & AG_NW_OVF) ? d.eovf_head[v] : AG_NONE;
+    d.eovf_head[v] = o;
+    w->misc |= AG_NW_OVF;
+}
+
+__global__ void __launch_bounds__(AG_TILE) k_edges(DevView d) {
+    __shared__ ag_alnp s_rec[NCHUNK];
+    __shared__ u32 s_lo[NCHUNK], s_span[NCHUNK];
+    const u32 tile = blockIdx.x, q = tile * AG_TILE + threadIdx.x;
+    const bool active = q < d.n_ref;
+    u32 nb0 = 0, nn0 = 0;
+    if (active) { nb0 = d.pos_node[q]; nn0 = d.pos_node[q + 1] - nb0; }
+    const u32 kb = d.tile_start[tile], ke = d.tile_start[tile + 1];
+    for (u32 c0 = kb; c0 < ke; c0 += NCHUNK) {
+        u32 cn = min((u32)NCHUNK, ke - c0);
+        if (threadIdx.x < cn) {
+            u32 idx = d.vals[c0 + threadIdx.x];
+            s_rec[threadIdx.x] = d.alnp[idx]; s_lo[threadIdx.x] = d.lo[idx]; s_span[threadIdx.x] = d.span[idx];
+        }
+        __syncthreads();
+        if (active && nn0)
+            for (u32 a = 0; a < cn; a++) {
+                if (q - s_lo[a] > s_span[a]) continue;
+                ag_touch t = ag_locate(s_rec[a], d.ext, q, (u32)d.k);
+                if (t.kind != 1) continue;
+                const u32 nb1 = d.pos_node[t.npos], nn1 = d.pos_node[t.npos + 1] - nb1;
+                ag_for_candidates(d.cmt, q, t.mate, [&](const ag_nodem& c) {
+                    u32 ci = ag_first_compatible(d.node_m + nb0, nn0, c, d.iv);
+                    if (ci == AG_NONE) return;
+                    const ag_nodem x = d.node_m[nb0 + ci];
+                    ag_for_candidates(d.cmt, t.npos, t.nmate, [&](const ag_nodem& c2) {
+                        u32 ni = ag_first_compatible(d.node_m + nb1, nn1, c2, d.iv);
+                        if (ni == AG_NONE) return;
+                        if (ag_edge_ok(x, d.node_m[nb1 + ni], d.iv)) add_edge(d, nb0 + ci, nb1 + ni);
+                    });
+                });
+            }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// walk: components (union-find), per-component replay, sequential fallback, materialisation
+// ---------------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 uf_find(u32* parent, u32 x) {
+    for (;;) {
+        u32 p = parent[x];
+        if (p == x) return x;
+        u32 gp = parent[p];
+        if (gp != p) atomicCAS(&parent[x], p, gp);
+        x = p;
+    }
+}
+__device__ __forceinline__ void uf_unite(u32* parent, u32 a, u32 b) {
+    for (;;) {
+        a = uf_find(parent, a); b = uf_find(parent, b);
+        if (a == b) return;
+        if (a > b) { u32 t = a; a = b; b = t; }
+        if (atomicCAS(&parent[b], b, a) == b) return;
+    }
+}
+
+__global__ void k_uf_init(DevView d, u32 n_nodes) {
+    u32 v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_nodes) return;
+    d.parent[v] = v; d.cmin[v] = AG_NONE; d.cmax[v] = 0; d.walk_next[v] = AG_NONE;
+}
+// live successor edges join components (a walk reads the traversed flag of every successor, AG:2022-2032)
+__global__ void k_uf_edges(DevView d, u32 n_nodes) {
+    u32 v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_nodes) return;
+    ag_nodew w = d.node_w[v];
+    if (w.misc & AG_NW_FILTERED) return;
+    if (w.succ0 != AG_NONE && !(d.node_w[w.succ0].misc & AG_NW_FILTERED)) uf_unite(d.parent, v, w.succ0);
+    if (w.succ1 != AG_NONE && !(d.node_w[w.succ1].misc & AG_NW_FILTERED)) uf_unite(d.parent, v, w.succ1);
+    if (w.misc & AG_NW_OVF)
+        for (u32 o = d.eovf_head[v]; o != AG_NONE; o = d.eovf_next[o]) { u32 s = d.eovf_target[o]; if (!(d.node_w[s].misc & AG_NW_FILTERED)) uf_unite(d.parent, v, s); }
+}
+// a contiMer detour from position p inspects every node at the thread's terminal position (AG:2093-2114)
+__global__ void k_uf_chain(DevView d) {
+    u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= d.n_ref) return;
+    u32 c0 = d.cmt.start[p];
+    if (d.cmt.start[p + 1] - c0 != 1) return;
+    ag_cm m = d.cmt.cm[c0];
+    if (m.chain == m.term) return;
+    u32 anchor = AG_NONE;
+    for (u32 x = d.pos_node[p]; x < d.pos_node[p + 1]; x++)
+        if (!(d.node_w[x].misc & AG_NW_FILTERED)) { if (anchor == AG_NONE) anchor = x; else uf_unite(d.parent, anchor, x); }
+    if (anchor == AG_NONE) return;
+    u32 z = d.chain_pos[m.term];
+    if (z >= d.n_ref) return;
+    for (u32 x = d.pos_node[z]; x < d.pos_node[z + 1]; x++) if (!(d.node_w[x].misc & AG_NW_FILTERED)) uf_unite(d.parent, anchor, x);
+}
+__global__ void k_uf_flatten(DevView d, u32 n_nodes) {
+    u32 v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_nodes) return;
+    if (d.node_w[v].misc & AG_NW_FILTERED) return;
+    u32 r = uf_find(d.parent, v);
+    d.parent[v] = r;
+    atomicMin(&d.cmin[r], v); atomicMax(&d.cmax[r], v);
+}
+
+__device__ __forceinline__ ag_walkctx make_ctx(const DevView& d) {
+    ag_walkctx w;
+    w.nw = d.node_w; w.node_pos = d.node_pos; w.pos_node = d.pos_node; w.ovf_head = d.eovf_head; w.ovf_target = d.eovf_target;
+    w.ovf_next = d.eovf_next; w.cmt = d.cmt; w.chain_pos = d.chain_pos; w.trav = d.trav; w.walk_next = d.walk_next;
+    return w;
+}
+__device__ __forceinline__ void push_walk(const DevView& d, ag_walk r) {
+    u32 o = atomicAdd(d.walk_count, 1u);
+    if (o >= d.walk_cap) { *d.err = 5; return; }
+    r.tail_sread = d.node_sref[2 * (size_t)r.last_node]; r.tail_soff_len = d.node_sref[2 * (size_t)r.last_node + 1];
+    d.walks[o] = r;
+}
+
+// one thread per component root: replay the scan (AG:1972-1990) restricted to the component's nodes, in node order
+__global__ void k_walk_components(DevView d, u32 n_nodes) {
+    u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_nodes) return;
+    if (d.node_w[r].misc & AG_NW_FILTERED) return;
+    if (d.parent[r] != r) return;
+    ag_walkctx w = make_ctx(d);
+    u32 hi = d.cmax[r];
+    for (u32 v = d.cmin[r]; v <= hi; v++) {
+        if (d.trav[v] & 1) continue;
+        if (d.parent[v] != r) continue;
+        push_walk(d, ag_walk_from(w, v));
+    }
+}
+
+// exact sequential replay including the 1000-position skip (AG:2194-2202); used only when a >100 kbp contig was emitted
+__global__ void k_walk_sequential(DevView d) {
+    if (blockIdx.x || threadIdx.x) return;
+    ag_walkctx w = make_ctx(d);
+    u32 bso = AG_NONE, beo = AG_NONE, bei = AG_NONE;
+    for (u32 cp = 0; cp < d.n_ref;) {
+        for (u32 v = d.pos_node[cp]; v < d.pos_node[cp + 1]; v++) {
+            if (d.trav[v] & 1) continue;
+            ag_walk r = ag_walk_from(w, v);
+            push_walk(d, r);
+            u32 eoff = r.eoff;
+            if (((r.flags >> 1) & 3) == 0) eoff = eoff + (d.node_sref[2 * (size_t)r.last_node + 1] >> 16) - 1;  // AG:2170
+            bool contained = (bei == 0) && bso <= r.soff && beo >= eoff;     // contain(), AG:1897-1902 (ids are 0 once set)
+            if (!contained) { bso = r.soff; beo = eoff; bei = 0; }
+        }
+        if (beo - bso > 100000u) { if (bei == 0 && cp + 1000 < beo) cp += 1000; else cp++; }
+        else cp++;
+    }
+}
+
+// write the bases of the selected walks (AG:1993-2002): consensus base per node, contig bases along contiMer detours
+__global__ void k_materialize(DevView d, const u32* __restrict__ starts, const u64* __restrict__ offs, u32 n, unsigned char* out) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned char* o = out + offs[i];
+    u32 v = starts[i];
+    while (v != AG_NONE) {
+        *o++ = (unsigned char)(d.node_w[v].misc & 0xFF);
+        if (d.trav[v] & 2) {
+            ag_cm m = d.cmt.cm[d.cmt.start[d.node_pos[v]]];
+            for (u32 e = m.chain + 1; e <= m.term; e++) *o++ = d.chain_base[e];
+        }
+        v = d.walk_next[v];
+    }
+}
+
+__global__ void k_reset_marks(DevView d, u32 n_nodes) {
+    u32 v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_nodes) return;
+    d.trav[v] = (d.node_w[v].misc & AG_NW_FILTERED) ? 1 : 0;
+    d.walk_next[v] = AG_NONE;
+}
+
+__global__ void k_occupancy(DevView d, unsigned char* bits) {
+    u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b * 8 >= d.n_pos) return;
+    unsigned char x = 0;
+    for (u32 j = 0; j < 8; j++) {
+        u32 p = b * 8 + j;
+        if (p >= d.n_pos) break;
+        bool occ = d.cmt.start[p + 1] > d.cmt.start[p];
+        if (p < d.n_ref && d.pos_cnt[p]) occ = true;
+        if (occ) x |= (unsigned char)(1u << j);
+    }
+    bits[b] = x;
+}
+
+struct Timer {
+    cudaEvent_t a, b; cudaStream_t st;
+    Timer(cudaStream_t s) : st(s) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); }
+    float stop() { cudaEventRecord(b, st); cudaEventSynchronize(b); float ms = 0; cudaEventElapsedTime(&ms, a, b); cudaEventDestroy(a); cudaEventDestroy(b); return ms; }
+};
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------------------
+struct AgDevice::Impl {
+    cudaStream_t st = nullptr;
+    // reads
+    DBuf<u32> r_bases, r_nmask; DBuf<uint16_t> r_len; ag_reads reads{}; u64 n_pairs = 0; bool reads_owned = false;
+    // unit inputs
+    DBuf<unsigned char> ref, chain_base; DBuf<u32> cm_start, chain_pos; DBuf<ag_cm> cm; DBuf<ag_aln> aln; DBuf<ag_seg> ext;
+    u32 n_ref = 0, n_pos = 0, n_cm = 0, n_aln = 0;
+    // build products
+    DBuf<ag_alnp> alnp; DBuf<u32> lo, span, ntiles, key_off, keys, vals, keys2, vals2, hist, tile_cnt, tile_start;
+    DBuf<ag_nodeb> pool, ovf_node; DBuf<u32> ovf_next, counters; DBuf<int> err;
+    DBuf<u32> pos_cnt, pos_pool, pos_node;
+    DBuf<ag_nodem> node_m; DBuf<ag_nodew> node_w; DBuf<u32> node_sref, node_pos;
+    DBuf<u32> eovf_head, eovf_target, eovf_next;
+    DBuf<unsigned char> trav; DBuf<u32> walk_next, parent, cmin, cmax; DBuf<ag_walk> walks;
+    DBuf<unsigned char> out_bases, occ; DBuf<u32> sel_start; DBuf<u64> sel_off;
+    Scanner scanner;
+    u32 n_tiles = 0, n_keys = 0, n_nodes = 0;
+    u32 pool_cap = 0, ovf_cap = 0, eovf_cap = 0, walk_cap = 0;
+    DevView view{};
+    // counters layout: [0] pool_count, [1] ovf_count, [2] eovf_count, [3] walk_count
+};
+
+AgDevice::AgDevice(int device) : m_(new Impl), dev_(device) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { delete m_; throw AgError{"no CUDA device: the AlignGraph B200 hot path has no CPU fallback"}; }
+    CK(cudaSetDevice(device));
+    CK(cudaStreamCreateWithFlags(&m_->st, cudaStreamNonBlocking));
+    stream_ = m_->st;
+    m_->scanner.launches = &launches_;
+    m_->counters.ensure(8); m_->err.ensure(1);
+}
+AgDevice::~AgDevice() {
+    cudaSetDevice(dev_);
+    // DBuf members are plain; free what we own
+    Impl& m = *m_;
+    if (m.reads_owned) { m.r_bases.release(); m.r_nmask.release(); m.r_len.release(); }
+    DBuf<unsigned char>* b8[] = {&m.ref, &m.chain_base, &m.trav, &m.out_bases, &m.occ};
+    for (auto* b : b8) b->release();
+    DBuf<u32>* b32[] = {&m.cm_start, &m.chain_pos, &m.lo, &m.span, &m.ntiles, &m.key_off, &m.keys, &m.vals, &m.keys2, &m.vals2, &m.hist, &m.tile_cnt,
+                        &m.tile_start, &m.ovf_next, &m.counters, &m.pos_cnt, &m.pos_pool, &m.pos_node, &m.node_sref, &m.node_pos, &m.eovf_head,
+                        &m.eovf_target, &m.eovf_next, &m.walk_next, &m.parent, &m.cmin, &m.cmax, &m.sel_start};
+    for (auto* b : b32) b->release();
+    for (int i = 0; i < 4; i++) m.scanner.lvl[i].release();
+    m.cm.release(); m.aln.release(); m.ext.release(); m.alnp.release(); m.pool.release(); m.ovf_node.release(); m.err.release();
+    m.node_m.release(); m.node_w.release(); m.walks.release(); m.sel_off.release();
+    if (m.st) cudaStreamDestroy(m.st);
+    delete m_;
+}
+
+void AgDevice::sync() { CK(cudaSetDevice(dev_)); CK(cudaStreamSynchronize(m_->st)); }
+
+void AgDevice::set_reads(const u32* bases, const u32* nmask, const uint16_t* len, u64 n_pairs, u32 stride2, u32 stridem, bool on_device) {
+    CK(cudaSetDevice(dev_));
+    Impl& m = *m_;
+    m.n_pairs = n_pairs;
+    if (on_device) {
+        m.reads.bases = bases; m.reads.nmask = nmask; m.reads.len = len; m.reads_owned = false;
+    } else {
+        Timer tm(m.st);
+        m.r_bases.ensure(2 * n_pairs * stride2 + 1); m.r_nmask.ensure(2 * n_pairs * stridem + 1); m.r_len.ensure(n_pairs + 1);
+        CK(cudaMemcpyAsync(m.r_bases.p, bases, 2 * n_pairs * stride2 * sizeof(u32), cudaMemcpyHostToDevice, m.st));
+        CK(cudaMemcpyAsync(m.r_nmask.p, nmask, 2 * n_pairs * stridem * sizeof(u32), cudaMemcpyHostToDevice, m.st));
+        CK(cudaMemcpyAsync(m.r_len.p, len, n_pairs * sizeof(uint16_t), cudaMemcpyHostToDevice, m.st));
+        m.reads.bases = m.r_bases.p; m.reads.nmask = m.r_nmask.p; m.reads.len = m.r_len.p; m.reads_owned = true;
+        t_.h2d += tm.stop();
+    }
+    m.reads.stride2 = stride2; m.reads.stridem = stridem;
+}
+
+void AgDevice::load_unit(const AgUnitInput& in) {
+    CK(cudaSetDevice(dev_));
+    Impl& m = *m_;
+    Timer tm(m.st);
+    m.n_ref = in.n_ref; m.n_pos = in.n_pos; m.n_cm = in.n_cm; m.n_aln = (u32)in.n_aln;
+    if (in.n_aln >= 0xFFFFFFF0ull) throw AgError{"too many alignments for one unit"};
+    m.ref.ensure(in.n_pos + 1); m.cm_start.ensure((size_t)in.n_pos + 2); m.cm.ensure(in.n_cm + 1); m.chain_pos.ensure(in.n_cm + 1);
+    m.chain_base.ensure(in.n_cm + 1); m.aln.ensure(in.n_aln + 1); m.ext.ensure(in.n_ext + 1);
+    CK(cudaMemcpyAsync(m.ref.p, in.ref, in.n_pos, cudaMemcpyHostToDevice, m.st));
+    CK(cudaMemcpyAsync(m.cm_start.p, in.cm_start, ((size_t)in.n_pos + 1) * sizeof(u32), cudaMemcpyHostToDevice, m.st));
+    if (in.n_cm) {
+        CK(cudaMemcpyAsync(m.cm.p, in.cm, (size_t)in.n_cm * sizeof(ag_cm), cudaMemcpyHostToDevice, m.st));
+        CK(cudaMemcpyAsync(m.chain_pos.p, in.chain_pos, (size_t)in.n_cm * sizeof(u32), cudaMemcpyHostToDevice, m.st));
+        CK(cudaMemcpyAsync(m.chain_base.p, in.chain_base, in.n_cm, cudaMemcpyHostToDevice, m.st));
+    }
+    if (in.n_aln) CK(cudaMemcpyAsync(m.aln.p, in.aln, in.n_aln * sizeof(ag_aln), cudaMemcpyHostToDevice, m.st));
+    if (in.n_ext) CK(cudaMemcpyAsync(m.ext.p, in.ext, in.n_ext * sizeof(ag_seg), cudaMemcpyHostToDevice, m.st));
+    t_.h2d += tm.stop();
+}
+
+void AgDevice::build() {
+    CK(cudaSetDevice(dev_));
+    Impl& m = *m_;
+    cudaStream_t st = m.st;
+    const u32 nA = m.n_aln, n_ref = m.n_ref, n_pos = m.n_pos;
+    m.n_tiles = (n_ref + AG_TILE - 1) / AG_TILE;
+    DevView& d = m.view;
+    d = DevView{};
+    d.reads = m.reads; d.ref = m.ref.p; d.n_ref = n_ref; d.n_pos = n_pos;
+    d.cmt.start = m.cm_start.p; d.cmt.cm = m.cm.p; d.chain_pos = m.chain_pos.p; d.chain_base = m.chain_base.p;
+    d.aln = m.aln.p; d.n_aln = nA; d.ext = m.ext.p; d.k = k_; d.iv = iv_; d.coverage = cov_;
+    m.alnp.ensure(nA + 1); m.lo.ensure(nA + 1); m.span.ensure(nA + 1); m.ntiles.ensure(nA + 1); m.key_off.ensure((size_t)nA + 2);
+    m.tile_cnt.ensure(m.n_tiles + 2); m.tile_start.ensure(m.n_tiles + 2);
+    m.pos_cnt.ensure(n_pos + 2); m.pos_pool.ensure(n_pos + 2); m.pos_node.ensure((size_t)n_pos + 2);
+    d.alnp = m.alnp.p; d.lo = m.lo.p; d.span = m.span.p; d.ntiles = m.ntiles.p; d.key_off = m.key_off.p;
+    d.tile_cnt = m.tile_cnt.p; d.tile_start = m.tile_start.p; d.n_tiles = m.n_tiles;
+    d.pos_cnt = m.pos_cnt.p; d.pos_pool = m.pos_pool.p; d.pos_node = m.pos_node.p;
+    d.err = m.err.p;
+    CK(cudaMemsetAsync(m.err.p, 0, sizeof(int), st));
+    CK(cudaMemsetAsync(m.counters.p, 0, 8 * sizeof(u32), st));
+    CK(cudaMemsetAsync(m.tile_cnt.p, 0, (m.n_tiles + 1) * sizeof(u32), st));
+    CK(cudaMemsetAsync(m.pos_cnt.p, 0, ((size_t)n_pos + 1) * sizeof(u32), st));
+
+    // ---- prep + keys ------------------------------------------------------------------------------------------------
+    {
+        Timer tm(st);
+        if (nA) { k_prep<<<(nA + 255) / 256, 256, 0, st>>>(d); launches_++; }
+        m.scanner.run(m.ntiles.p, m.key_off.p, nA, st);
+        u32 nk = 0;
+        CK(cudaMemcpyAsync(&nk, m.key_off.p + nA, sizeof(u32), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        m.n_keys = nk;
+        m.keys.ensure(nk + 1); m.vals.ensure(nk + 1); m.keys2.ensure(nk + 1); m.vals2.ensure(nk + 1);
+        d.keys = m.keys.p; d.vals = m.vals.p;
+        if (nA) { k_keys<<<(nA + 255) / 256, 256, 0, st>>>(d); launches_++; }
+        m.scanner.run(m.tile_cnt.p, m.tile_start.p, m.n_tiles, st);
+        t_.prep += tm.stop();
+    }
+    // ---- bucket: stable radix sort by tile ---------------------------------------------------------------------------
+    {
+        Timer tm(st);
+        u32 nk = m.n_keys;
+        if (nk) {
+            int bits = 1; while ((1ull << bits) < (u64)m.n_tiles) bits++;
+            unsigned nb = (nk + RS_B - 1) / RS_B;
+            m.hist.ensure((size_t)16 * nb + 2);
+            u32 *ka = m.keys.p, *va = m.vals.p, *kb = m.keys2.p, *vb = m.vals2.p;
+            for (int shift = 0; shift < bits; shift += 4) {
+                k_rs_hist<<<nb, RS_T, 0, st>>>(ka, m.hist.p, nk, shift, nb); launches_++;
+                m.scanner.run(m.hist.p, m.hist.p, (size_t)16 * nb, st, 0, 0);
+                k_rs_scatter<<<nb, RS_T, 0, st>>>(ka, va, kb, vb, m.hist.p, nk, shift, nb); launches_++;
+                std::swap(ka, kb); std::swap(va, vb);
+            }
+            d.keys = ka; d.vals = va;
+        }
+        t_.sort += tm.stop();
+    }
+    // ---- nodes ----------------------------------------------------------------------------------------------------------------
+    {
+        Timer tm(st);
+        if (!m.pool_cap) m.pool_cap = std::max<u32>(1u << 20, 3 * n_ref + (1u << 16));
+        for (;;) {
+            m.pool.ensure(m.pool_cap);
+            m.ovf_cap = std::max<u32>(1u << 18, n_ref / 8);
+            m.ovf_node.ensure(m.ovf_cap); m.ovf_next.ensure(m.ovf_cap);
+            d.pool = m.pool.p; d.pool_count = m.counters.p + 0; d.pool_cap = m.pool_cap;
+            d.ovf.node = m.ovf_node.p; d.ovf.next = m.ovf_next.p; d.ovf.count = m.counters.p + 1; d.ovf.cap = m.ovf_cap; d.ovf.err = m.err.p;
+            if (m.n_tiles) { k_nodes<<<m.n_tiles, AG_TILE, 0, st>>>(d); launches_++; }
+            int err = 0;
+            CK(cudaMemcpyAsync(&err, m.err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (err == 0) break;
+            if (err == 3) {  // node pool too small: grow and redo the sweep
+                m.pool_cap = m.pool_cap * 2;
+                CK(cudaMemsetAsync(m.err.p, 0, sizeof(int), st));
+                CK(cudaMemsetAsync(m.counters.p, 0, 8 * sizeof(u32), st));
+                continue;
+            }
+            if (err == 2) throw AgError{"BOWTIE ALIGNMENT ERROR: alignment outside the unit"};
+            throw AgError{"node overflow pool exhausted"};
+        }
+        t_.nodes += tm.stop();
+    }
+    // ---- finalize -------------------------------------------------------------------------------------------------------------
+    {
+        Timer tm(st);
+        m.scanner.run(m.pos_cnt.p, m.pos_node.p, n_pos, st);
+        u32 nn = 0;
+        CK(cudaMemcpyAsync(&nn, m.pos_node.p + n_pos, sizeof(u32), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        m.n_nodes = nn; t_.n_nodes = nn; t_.n_keys = m.n_keys; t_.n_tiles = m.n_tiles;
+        m.node_m.ensure(nn + 1); m.node_w.ensure(nn + 1); m.node_sref.ensure(2 * (size_t)nn + 2); m.node_pos.ensure(nn + 1);
+        m.trav.ensure(nn + 1); m.eovf_head.ensure(nn + 1);
+        m.eovf_cap = std::max<u32>(1u << 18, nn / 8); m.eovf_target.ensure(m.eovf_cap); m.eovf_next.ensure(m.eovf_cap);
+        d.node_m = m.node_m.p; d.node_w = m.node_w.p; d.node_sref = m.node_sref.p; d.node_pos = m.node_pos.p; d.trav = m.trav.p;
+        d.eovf_head = m.eovf_head.p; d.eovf_target = m.eovf_target.p; d.eovf_next = m.eovf_next.p; d.eovf_count = m.counters.p + 2; d.eovf_cap = m.eovf_cap;
+        if (n_ref) { k_finalize<<<(n_ref + 255) / 256, 256, 0, st>>>(d); launches_++; }
+        t_.finalize += tm.stop();
+    }
+    // ---- edges ----------------------------------------------------------------------------------------------------------------
+    {
+        Timer tm(st);
+        if (m.n_tiles) { k_edges<<<m.n_tiles, AG_TILE, 0, st>>>(d); launches_++; }
+        int err = 0; u32 cnt[4];
+        CK(cudaMemcpyAsync(&err, m.err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(cnt, m.counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (err) throw AgError{"edge overflow pool exhausted"};
+        t_.n_edges_ovf = cnt[2];
+        t_.edges += tm.stop();
+    }
+}
+
+void AgDevice::walk_components() {
+    Impl& m = *m_; cudaStream_t st = m.st; DevView& d = m.view; u32 nn = m.n_nodes;
+    unsigned g = (nn + 255) / 256;
+    {
+        Timer tm(st);
+        k_uf_init<<<g, 256, 0, st>>>(d, nn); launches_++;
+        k_uf_edges<<<g, 256, 0, st>>>(d, nn); launches_++;
+        k_uf_chain<<<(m.n_ref + 255) / 256, 256, 0, st>>>(d); launches_++;
+        k_uf_flatten<<<g, 256, 0, st>>>(d, nn); launches_++;
+        t_.components += tm.stop();
+    }
+    {
+        Timer tm(st);
+        k_walk_components<<<g, 256, 0, st>>>(d, nn); launches_++;
+        t_.walk += tm.stop();
+    }
+}
+
+void AgDevice::walk_sequential() {
+    Impl& m = *m_; cudaStream_t st = m.st; DevView& d = m.view; u32 nn = m.n_nodes;
+    Timer tm(st);
+    // reset marks to the coverage filter state and replay in one thread
+    k_reset_marks<<<(nn + 255) / 256, 256, 0, st>>>(d, nn); launches_++;
+    CK(cudaMemsetAsync(m.counters.p + 3, 0, sizeof(u32), st));
+    k_walk_sequential<<<1, 32, 0, st>>>(d); launches_++;
+    t_.walk += tm.stop();
+    t_.walk_fallback = 1;
+}
+
+void AgDevice::extend(std::vector<ag_walk>& walks) {
+    CK(cudaSetDevice(dev_));
+    Impl& m = *m_; cudaStream_t st = m.st; DevView& d = m.view; u32 nn = m.n_nodes;
+    walks.clear();
+    if (!nn) return;
+    m.walk_next.ensure(nn + 1); m.parent.ensure(nn + 1); m.cmin.ensure(nn + 1); m.cmax.ensure(nn + 1);
+    m.walk_cap = nn; m.walks.ensure(m.walk_cap);
+    d.walk_next = m.walk_next.p; d.parent = m.parent.p; d.cmin = m.cmin.p; d.cmax = m.cmax.p;
+    d.walks = m.walks.p; d.walk_count = m.counters.p + 3; d.walk_cap = m.walk_cap;
+    CK(cudaMemsetAsync(m.counters.p + 3, 0, sizeof(u32), st));
+    walk_components();
+    auto fetch = [&]() {
+        Timer tm(st);
+        u32 nw = 0; int err = 0;
+        CK(cudaMemcpyAsync(&nw, m.counters.p + 3, sizeof(u32), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&err, m.err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (err) throw AgError{"walk record buffer exhausted"};
+        walks.resize(nw);
+        if (nw) CK(cudaMemcpyAsync(walks.data(), m.walks.p, (size_t)nw * sizeof(ag_walk), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        t_.d2h += tm.stop();
+        std::sort(walks.begin(), walks.end(), [](const ag_walk& a, const ag_walk& b) { return a.start_node < b.start_node; });
+    };
+    fetch();
+    // the 1000-position skip of the reference's scan (AG:2194-2202) only matters once a contig longer than 100 kbp has been
+    // emitted; detect that on the emitted sequence and, if so, replay sequentially on the device (exact, slow, rare)
+    {
+        u32 bso = AG_NONE, beo = AG_NONE; bool have = false, trigger = false;
+        for (size_t i = 0; i < walks.size() && !trigger; i++) {
+            const ag_walk& r = walks[i];
+            u32 eoff = r.eoff;
+            if (((r.flags >> 1) & 3) == 0) eoff = eoff + (r.tail_soff_len >> 16) - 1;
+            bool contained = have && bso <= r.soff && beo >= eoff;
+            if (!contained) { bso = r.soff; beo = eoff; have = true; if (beo - bso > 100000u) trigger = true; }
+        }
+        if (trigger) { walk_sequential(); fetch(); }
+    }
+    t_.n_walks = walks.size();
+}
+
+void AgDevice::materialize(const std::vector<ag_walk>& walks, const std::vector<u32>& sel, std::string& bases, std::vector<u64>& offs) {
+    CK(cudaSetDevice(dev_));
+    Impl& m = *m_; cudaStream_t st = m.st; DevView& d = m.view;
+    offs.assign(sel.size() + 1, 0);
+    std::vector<u32> starts(sel.size());
+    for (size_t i = 0; i < sel.size(); i++) { starts[i] = walks[sel[i]].start_node; offs[i + 1] = offs[i] + walks[sel[i]].len; }
+    bases.assign(offs.back(), '\0');
+    if (sel.empty()) return;
+    Timer tm(st);
+    m.sel_start.ensure(sel.size() + 1); m.sel_off.ensure(sel.size() + 1); m.out_bases.ensure(offs.back() + 1);
+    CK(cudaMemcpyAsync(m.sel_start.p, starts.data(), starts.size() * sizeof(u32), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(m.sel_off.p, offs.data(), sel.size() * sizeof(u64), cudaMemcpyHostToDevice, st));
+    k_materialize<<<((u32)sel.size() + 127) / 128, 128, 0, st>>>(d, m.sel_start.p, m.sel_off.p, (u32)sel.size(), m.out_bases.p); launches_++;
+    CK(cudaMemcpyAsync(&bases[0], m.out_bases.p, offs.back(), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    t_.materialize += tm.stop();
+}
+
+void AgDevice::occupancy(std::vector<unsigned char>& bits) {
+    CK(cudaSetDevice(dev_));
+    Impl& m = *m_; cudaStream_t st = m.st;
+    size_t nb = ((size_t)m.n_pos + 7) / 8;
+    bits.assign(nb, 0);
+    if (!nb) return;
+    m.occ.ensure(nb + 1);
+    k_occupancy<<<((u32)nb + 255) / 256, 256, 0, st>>>(m.view, m.occ.p); launches_++;
+    CK(cudaMemcpyAsync(bits.data(), m.occ.p, nb, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+}
+
+void AgDevice::dump_nodes(AgNodeDump& dd) {
+    CK(cudaSetDevice(dev_));
+    Impl& m = *m_; cudaStream_t st = m.st; u32 nn = m.n_nodes, n_pos = m.n_pos;
+    std::vector<u32> pos_cnt(n_pos + 1), pos_pool(n_pos + 1), pos_node(n_pos + 1);
+    CK(cudaMemcpyAsync(pos_cnt.data(), m.pos_cnt.p, (size_t)n_pos * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(pos_pool.data(), m.pos_pool.p, (size_t)n_pos * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(pos_node.data(), m.pos_node.p, ((size_t)n_pos + 1) * 4, cudaMemcpyDeviceToHost, st));
+    u32 cnt[4];
+    CK(cudaMemcpyAsync(cnt, m.counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    std::vector<ag_nodeb> pool(cnt[0]);
+    std::vector<ag_nodew> nw(nn);
+    if (cnt[0]) CK(cudaMemcpyAsync(pool.data(), m.pool.p, (size_t)cnt[0] * sizeof(ag_nodeb), cudaMemcpyDeviceToHost, st));
+    if (nn) CK(cudaMemcpyAsync(nw.data(), m.node_w.p, (size_t)nn * sizeof(ag_nodew), cudaMemcpyDeviceToHost, st));
+    std::vector<u32> eh(nn), et(cnt[2]), en(cnt[2]);
+    if (nn) CK(cudaMemcpyAsync(eh.data(), m.eovf_head.p, (size_t)nn * 4, cudaMemcpyDeviceToHost, st));
+    if (cnt[2]) { CK(cudaMemcpyAsync(et.data(), m.eovf_target.p, (size_t)cnt[2] * 4, cudaMemcpyDeviceToHost, st)); CK(cudaMemcpyAsync(en.data(), m.eovf_next.p, (size_t)cnt[2] * 4, cudaMemcpyDeviceToHost, st)); }
+    CK(cudaStreamSynchronize(st));
+    dd = AgNodeDump();
+    dd.edge_start.push_back(0);
+    for (u32 q = 0; q < m.n_ref; q++)
+        for (u32 i = 0; i < pos_cnt[q]; i++) {
+            const ag_nodeb& b = pool[pos_pool[q] + i];
+            dd.pos.push_back(q); dd.item.push_back(i); dd.cov.push_back(b.cov);
+            for (int j = 0; j < 5; j++) dd.cnt.push_back(b.cnt[j]);
+            dd.cid.push_back(b.cid); dd.coff.push_back(b.coff); dd.cid0.push_back(b.cid0); dd.coff0.push_back(b.coff0); dd.moff.push_back(b.moff);
+            dd.sread.push_back(b.sread); dd.soff_len.push_back(b.soff_len);
+            u32 v = pos_node[q] + i;
+            std::vector<u32> e;
+            if (nw[v].succ0 != AG_NONE) e.push_back(nw[v].succ0);
+            if (nw[v].succ1 != AG_NONE) e.push_back(nw[v].succ1);
+            if (nw[v].misc & AG_NW_OVF) for (u32 o = eh[v]; o != AG_NONE; o = en[o]) e.push_back(et[o]);
+            std::sort(e.begin(), e.end());
+            for (u32 x : e) dd.edge_target.push_back(x);
+            dd.edge_start.push_back((u32)dd.edge_target.size());
+        }
+}

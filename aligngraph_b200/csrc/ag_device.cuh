@@ -1,0 +1,69 @@
+// Host-visible interface of the device pipeline (ag_device.cu).  Internal to the library; the public boundary is the C ABI in
+// include/aligngraph_b200.h.
+#pragma once
+#include "ag_types.h"
+#include <string>
+#include <vector>
+
+struct AgUnitInput {
+    const char* ref;            // unit bases followed by the contig-insertion tail (AG:981-1036), n_pos bytes
+    u32 n_ref, n_pos;
+    const u32* cm_start;        // n_pos + 1
+    const ag_cm* cm; u32 n_cm;
+    const u32* chain_pos;       // n_cm, chain-major
+    const char* chain_base;     // n_cm, chain-major
+    const ag_aln* aln; u64 n_aln;
+    const ag_seg* ext; u64 n_ext;
+};
+
+struct AgNodeDump {  // node table in (position, item) order, for tests
+    std::vector<u32> pos, item, cov, cnt, cid, coff, cid0, coff0, moff, sread, soff_len;
+    std::vector<u32> edge_start;   // CSR over nodes
+    std::vector<u32> edge_target;  // global node index
+};
+
+struct AgTimings {  // milliseconds, CUDA events on the context's stream
+    float h2d = 0, prep = 0, sort = 0, nodes = 0, finalize = 0, edges = 0, components = 0, walk = 0, materialize = 0, d2h = 0;
+    u64 n_nodes = 0, n_edges_ovf = 0, n_walks = 0, n_keys = 0, n_tiles = 0, n_components = 0;
+    int walk_fallback = 0;
+};
+
+class AgDevice {
+public:
+    explicit AgDevice(int device);
+    ~AgDevice();
+    // reads: 2-bit packed + non-ACGT bit plane, fixed stride per read; len per pair.  `on_device` = pointers are device pointers
+    // (the NCCL broadcast target); otherwise they are copied H2D.
+    void set_reads(const u32* bases, const u32* nmask, const uint16_t* len, u64 n_pairs, u32 stride2, u32 stridem, bool on_device);
+    void set_params(int k, int iv, int coverage) { k_ = k; iv_ = iv; cov_ = coverage; }
+    // upload one unit's inputs (H2D, timed)
+    void load_unit(const AgUnitInput& in);
+    // the hot path: prep -> bucket -> nodes -> finalize -> edges  (all device)
+    void build();
+    // coverage filter + walk simulation; fills `walks` (unsorted on return from the device, sorted here by start node)
+    void extend(std::vector<ag_walk>& walks);
+    // materialise the selected walks' base strings (without tails); out[i] gets walks[sel[i]].len bytes
+    void materialize(const std::vector<ag_walk>& walks, const std::vector<u32>& sel, std::string& bases, std::vector<u64>& offs);
+    // occupancy bitmap (any node or contiMer at a position) for the scaffold gap test (AG:2428)
+    void occupancy(std::vector<unsigned char>& bits);
+    void dump_nodes(AgNodeDump& d);
+    void sync();
+    const AgTimings& timings() const { return t_; }
+    void reset_timings() { t_ = AgTimings(); }
+    int device() const { return dev_; }
+    void* stream() const { return stream_; }
+    u64 kernel_launches() const { return launches_; }
+
+private:
+    struct Impl;
+    Impl* m_;
+    int dev_, k_ = 5, iv_ = 50, cov_ = 20;
+    void* stream_ = nullptr;
+    AgTimings t_;
+    u64 launches_ = 0;
+    void walk_components();
+    void walk_sequential();
+};
+
+// thrown on any CUDA failure or capacity error; the C ABI turns it into an error code + ag_last_error()
+struct AgError { std::string msg; };

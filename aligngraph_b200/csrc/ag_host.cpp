@@ -1,0 +1,709 @@
+// Host side of the B200 AlignGraph hot path — see ag_host.h.  Reference citations: AG:line = AlignGraph/AlignGraph.cpp.
+#include "ag_host.h"
+#include <algorithm>
+#include <cstring>
+#include <cstdlib>
+#include <climits>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+namespace {
+
+const int kBatchPairs = 1000000;  // BATCH, AG:37
+const double kReadThreshold = 0.6, kContigThreshold = 0.5, kInitContigThreshold = 0.5;  // AG:28-34
+const long kLargeChunk = 1000000;  // AG:40
+
+struct FileMap {
+    const char* p = nullptr; size_t n = 0; int fd = -1; bool ok = false;
+    explicit FileMap(const std::string& path) {
+        fd = open(path.c_str(), O_RDONLY);
+        if (fd < 0) return;
+        struct stat st;
+        if (fstat(fd, &st) != 0) return;
+        n = (size_t)st.st_size; ok = true;
+        if (n) { void* m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0); if (m == MAP_FAILED) { ok = false; n = 0; } else { p = (const char*)m; madvise(m, n, MADV_SEQUENTIAL); } }
+    }
+    ~FileMap() { if (p) munmap((void*)p, n); if (fd >= 0) close(fd); }
+};
+
+// The reference reads every file with `while(in.good()) { getline(in, buf); if(buf[0] == 0) break; ... }`.  next() hands out
+// exactly the lines that loop sees: an empty line (or the end of a file that ends in '\n') yields n == 0 — the `break`.
+struct Lines {
+    const char* p; const char* end; bool good = true;
+    Lines(const char* b, size_t n) : p(b), end(b + n) {}
+    bool next(const char*& s, size_t& n) {
+        if (!good) return false;
+        if (p == end) { good = false; s = p; n = 0; return true; }
+        const char* e = (const char*)memchr(p, '\n', (size_t)(end - p));
+        s = p;
+        if (e) { n = (size_t)(e - p); p = e + 1; } else { n = (size_t)(end - p); p = end; good = false; }
+        return true;
+    }
+};
+
+int ag_atoi(const char* s, size_t n) {  // atoi() over a bounded field
+    size_t i = 0;
+    while (i < n && (s[i] == ' ' || (s[i] >= '\t' && s[i] <= '\r'))) i++;
+    bool neg = false;
+    if (i < n && (s[i] == '+' || s[i] == '-')) { neg = s[i] == '-'; i++; }
+    unsigned long long v = 0; bool sat = false;
+    for (; i < n && s[i] >= '0' && s[i] <= '9'; i++) { v = v * 10 + (unsigned)(s[i] - '0'); if (v > (unsigned long long)LONG_MAX) sat = true; }
+    long r = sat ? (neg ? LONG_MIN : LONG_MAX) : (neg ? -(long)v : (long)v);
+    return (int)r;
+}
+
+struct Out {  // buffered text sink: a file, or (path empty) an in-memory string
+    FILE* f = nullptr; std::string* mem = nullptr; std::vector<char> buf;
+    explicit Out(const std::string& path) : f(fopen(path.c_str(), "wb")) { if (!f) throw AgHostError{"CANNOT OPEN FILE!"}; buf.reserve(1 << 20); }
+    explicit Out(std::string* m) : mem(m) { m->clear(); }
+    ~Out() { flush(); if (f) fclose(f); }
+    void flush() { if (buf.empty()) return; if (f) fwrite(buf.data(), 1, buf.size(), f); else mem->append(buf.data(), buf.size()); buf.clear(); }
+    void put(const char* s, size_t n) { buf.insert(buf.end(), s, s + n); if (buf.size() > (1u << 20) - 256) flush(); }
+    void put(const std::string& s) { put(s.data(), s.size()); }
+    void ch(char c) { buf.push_back(c); if (buf.size() > (1u << 20)) flush(); }
+    void num(unsigned long v) { char t[24]; int n = snprintf(t, sizeof t, "%lu", v); put(t, (size_t)n); }
+    void inum(long v) { char t[24]; int n = snprintf(t, sizeof t, "%ld", v); put(t, (size_t)n); }
+    void wrap60(const std::string& s) {  // 60 columns, newline after the last base (AG:2179-2184)
+        for (size_t i = 0; i < s.size(); i += 60) { put(s.data() + i, std::min<size_t>(60, s.size() - i)); ch('\n'); }
+    }
+};
+
+inline int absdiff(u32 a, u32 b) { int d = (int)(a - b); return d < 0 ? -d : d; }
+
+void revcomp(std::string& s) {  // AG:854-865
+    std::reverse(s.begin(), s.end());
+    for (char& c : s) c = c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : c;
+}
+
+}  // namespace
+
+// =============================================================================================================================
+// reads
+// =============================================================================================================================
+static inline int base_code(char c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1; }
+
+static void pack_init(AgReads& out, size_t n_reads, u32 maxlen) {
+    out.stride2 = (maxlen + 15) / 16; out.stridem = (maxlen + 31) / 32;
+    if (!out.stride2) out.stride2 = out.stridem = 1;
+    out.bases.assign(n_reads * out.stride2, 0); out.nmask.assign(n_reads * out.stridem, 0);
+    out.n_pairs = n_reads / 2; out.len.assign(out.n_pairs, 0); out.exc.clear();
+}
+static void pack_one(AgReads& out, size_t r, const char* s, size_t n) {
+    u32* b = &out.bases[r * out.stride2]; u32* m = &out.nmask[r * out.stridem];
+    for (size_t i = 0; i < n; i++) {
+        int c = base_code(s[i]);
+        if (c < 0) { m[i >> 5] |= 1u << (i & 31); out.exc.push_back({(u64)r * 65536 + i, s[i]}); }
+        else b[i >> 4] |= (u32)c << ((i & 15) * 2);
+    }
+}
+
+void ag_pack_reads(const std::vector<std::string>& seqs, AgReads& out) {
+    size_t maxlen = 0;
+    for (auto& s : seqs) maxlen = std::max(maxlen, s.size());
+    if (maxlen > 65535) throw AgHostError{"READ TOO LONG"};
+    pack_init(out, seqs.size() & ~(size_t)1, (u32)maxlen);
+    for (size_t r = 0; r + 1 < seqs.size(); r += 2) {
+        if (seqs[r].size() != seqs[r + 1].size()) throw AgHostError{"INCONSISTENT PE FILES!"};
+        out.len[r / 2] = (uint16_t)seqs[r].size();
+        pack_one(out, r, seqs[r].data(), seqs[r].size()); pack_one(out, r + 1, seqs[r + 1].data(), seqs[r + 1].size());
+    }
+}
+
+void ag_parse_reads(const std::string& path, AgReads& out) {
+    FileMap fm(path);
+    if (!fm.ok) throw AgHostError{"CANNOT OPEN FILE!"};
+    // pass 1: record boundaries (a record = '>' line + the sequence lines up to the next '>'), AG:372-396
+    struct Rec { const char* s; size_t n; bool multi; };
+    std::vector<Rec> recs;
+    std::vector<std::string> joined;  // only for multi-line records
+    {
+        Lines ln(fm.p, fm.n); const char* s; size_t n;
+        while (ln.next(s, n)) {
+            if (n == 0 || s[0] == 0) break;
+            if (s[0] == '>') recs.push_back(Rec{nullptr, 0, false});
+            else if (!recs.empty()) {
+                Rec& r = recs.back();
+                if (!r.s) { r.s = s; r.n = n; }
+                else {  // sequence spread over several lines
+                    if (!r.multi) { joined.emplace_back(r.s, r.n); r.multi = true; r.n = joined.size() - 1; }
+                    joined[r.n].append(s, n);
+                }
+            }
+        }
+    }
+    size_t maxlen = 0;
+    for (auto& r : recs) maxlen = std::max(maxlen, r.multi ? joined[r.n].size() : r.n);
+    if (maxlen > 65535) throw AgHostError{"READ TOO LONG"};
+    pack_init(out, recs.size() & ~(size_t)1, (u32)maxlen);
+    for (size_t r = 0; r + 1 < recs.size(); r += 2) {
+        const char* s1 = recs[r].multi ? joined[recs[r].n].data() : recs[r].s; size_t n1 = recs[r].multi ? joined[recs[r].n].size() : recs[r].n;
+        const char* s2 = recs[r + 1].multi ? joined[recs[r + 1].n].data() : recs[r + 1].s; size_t n2 = recs[r + 1].multi ? joined[recs[r + 1].n].size() : recs[r + 1].n;
+        if (n1 != n2) throw AgHostError{"INCONSISTENT PE FILES!"};
+        out.len[r / 2] = (uint16_t)n1;
+        pack_one(out, r, s1, n1); pack_one(out, r + 1, s2, n2);
+    }
+}
+
+char AgReads::at(u32 read, u32 rc, u32 rlen, u32 off) const {
+    u32 i = rc ? rlen - 1 - off : off;
+    if ((nmask[(size_t)read * stridem + (i >> 5)] >> (i & 31)) & 1) {
+        u64 key = (u64)read * 65536 + i;
+        auto it = std::lower_bound(exc.begin(), exc.end(), std::make_pair(key, (char)CHAR_MIN));
+        return it != exc.end() && it->first == key ? it->second : 'N';
+    }
+    u32 c = (bases[(size_t)read * stride2 + (i >> 4)] >> ((i & 15) * 2)) & 3;
+    return "ACGT"[rc ? 3 - c : c];
+}
+
+// =============================================================================================================================
+// unit genome
+// =============================================================================================================================
+void ag_load_genome(const std::string& path, AgUnit& u) {
+    FileMap fm(path);
+    if (!fm.ok) throw AgHostError{"CANNOT OPEN FILE!"};
+    u.ref.clear();
+    Lines ln(fm.p, fm.n); const char* s; size_t n;
+    while (ln.next(s, n)) {
+        if (n == 0 || s[0] == 0) break;
+        if (s[0] == '>') continue;
+        u.ref.append(s, n);
+    }
+    u.n_ref = (u32)u.ref.size();
+}
+
+// =============================================================================================================================
+// contigs: PSL -> position sets -> contiMer threads
+// =============================================================================================================================
+namespace {
+struct Chunk { std::string bases; int id = 0; std::vector<std::vector<u32>> sets; std::vector<int> fr; int outputted = 0; };
+struct PslRec { u32 tid, tstart, tend, tgap, sid, sstart, send, sgap, ssize, fr; std::vector<ag_seg> segs; };
+
+void parse_psl(const char* s, size_t n, PslRec& r) {  // AG:406-522, fields by tab index
+    const char* f[21]; size_t fl[21]; int nf = 0;
+    const char* p = s; const char* end = s + n;
+    while (nf < 21) {
+        const char* e = (const char*)memchr(p, '\t', (size_t)(end - p));
+        f[nf] = p; fl[nf] = e ? (size_t)(e - p) : (size_t)(end - p); nf++;
+        if (!e) break;
+        p = e + 1;
+    }
+    auto fi = [&](int i) { return i < nf ? ag_atoi(f[i], fl[i]) : 0; };
+    r.tid = (u32)fi(13); r.tstart = (u32)fi(15); r.tend = (u32)fi(16); r.tgap = (u32)fi(7);
+    r.sstart = (u32)fi(11); r.send = (u32)fi(12); r.sgap = (u32)fi(5); r.ssize = (u32)fi(10);
+    r.fr = AG_NONE;
+    if (nf > 8 && fl[8] > 0) r.fr = f[8][0] == '+' ? 0u : 1u;
+    r.sid = 0;
+    if (nf > 9) { const char* dot = (const char*)memchr(f[9], '.', fl[9]); r.sid = (u32)ag_atoi(f[9], dot ? (size_t)(dot - f[9]) : fl[9]); }
+    r.segs.clear();
+    auto list = [&](int i, int which) {
+        if (i >= nf) return;
+        const char* q = f[i]; const char* qe = f[i] + fl[i]; size_t k = 0;
+        for (;;) {
+            const char* c = (const char*)memchr(q, ',', (size_t)(qe - q));
+            if (!c) break;
+            u32 v = (u32)ag_atoi(q, (size_t)(c - q));
+            if (which == 0) { ag_seg sg; sg.src = sg.dst = AG_NONE; sg.len = v; r.segs.push_back(sg); }
+            else if (k < r.segs.size()) { if (which == 1) r.segs[k].src = v; else r.segs[k].dst = v; }
+            k++; q = c + 1;
+        }
+    };
+    list(18, 0); list(19, 1); list(20, 2);
+}
+
+// keepPositions (AG:731-748): is the most recent position set of chunk `sid` at least `thr` aligned?
+int keep_set(std::vector<Chunk>& ch, u32 sid, double thr) {
+    if (sid == AG_NONE) return 1;
+    if (ch[sid].sets.empty()) return 1;
+    const std::vector<u32>& last = ch[sid].sets.back();
+    int match = 0;
+    for (u32 v : last) if (v != AG_NONE) match++;
+    return (double)match / last.size() >= thr ? 1 : 0;
+}
+}  // namespace
+
+void ag_thread_contigs(const std::string& contigs_fa, const std::string& psl_path, std::string& initial_text, AgUnit& u) {
+    // ---- chunks (AG:322-359) ----
+    std::vector<Chunk> ch;
+    {
+        FileMap fm(contigs_fa);
+        if (!fm.ok) throw AgHostError{"CANNOT OPEN FILE!"};
+        Lines ln(fm.p, fm.n); const char* s; size_t n;
+        while (ln.next(s, n)) {
+            if (n == 0 || s[0] == 0) break;
+            if (s[0] == '>') {
+                const char* dot = (const char*)memchr(s, '.', n);
+                Chunk c; c.id = dot ? ag_atoi(dot + 1, (size_t)(s + n - dot - 1)) : 0;
+                ch.push_back(std::move(c));
+            } else if (!ch.empty()) ch.back().bases.append(s, n);
+        }
+    }
+    // ---- PSL -> position sets (AG:817-852 with updateContig AG:763-815) ----
+    {
+        FileMap fm(psl_path);
+        if (!fm.ok) throw AgHostError{"CANNOT OPEN FILE!"};
+        Lines ln(fm.p, fm.n); const char* s; size_t n;
+        PslRec r; r.sid = AG_NONE;
+        u32 last_source = AG_NONE;  // sourceIDBak (AG:762); it is -1 on entry (reset at AG:4781 / AG:1241)
+        while (ln.next(s, n)) {
+            if (n == 0 || s[0] == 0) {  // end of file: validate the last set of the LAST PARSED record's chunk (AG:830-836)
+                if (r.sid != AG_NONE && r.sid < ch.size() && keep_set(ch, r.sid, kContigThreshold) == 0) ch[r.sid].sets.pop_back();
+                break;
+            }
+            parse_psl(s, n, r);
+            bool pass = (double)(r.send - r.sstart - r.sgap) / r.ssize >= kInitContigThreshold &&
+                        (double)(r.tend - r.tstart - r.tgap) / (r.tend - r.tstart) >= kInitContigThreshold && r.ssize > 200;
+            if (!pass) continue;
+            if (r.tid == AG_NONE) continue;  // updateContig returns at once (AG:769)
+            if (r.tid != 0 || r.sid >= ch.size()) throw AgHostError{"CONTIG ALIGNMENT ERROR"};
+            Chunk& c = ch[r.sid];
+            auto open_set = [&]() { c.sets.emplace_back(c.bases.size(), AG_NONE); c.fr.push_back((int)r.fr); };
+            if (r.sid != last_source) {
+                if (keep_set(ch, last_source, kContigThreshold) == 0) { ch[last_source].sets.pop_back(); ch[last_source].fr.pop_back(); }
+                open_set();
+                last_source = r.sid;
+            } else {
+                bool clash = false;
+                for (size_t i = 0; i < r.segs.size() && !clash; i++)
+                    for (u32 j = r.segs[i].src; j < r.segs[i].src + r.segs[i].len; j++) {
+                        if (j >= c.bases.size()) throw AgHostError{"CONTIG ALIGNMENT ERROR"};
+                        if (c.sets.back()[j] != AG_NONE) { clash = true; break; }
+                    }
+                if (clash) {
+                    if (keep_set(ch, r.sid, kContigThreshold) == 0) { c.sets.pop_back(); c.fr.pop_back(); }
+                    open_set();
+                }
+            }
+            std::vector<u32>& cur = c.sets.back();
+            for (const ag_seg& sg : r.segs)
+                for (u32 j = 0; j < sg.len; j++) {
+                    if ((size_t)sg.src + j >= cur.size()) throw AgHostError{"CONTIG ALIGNMENT ERROR"};
+                    cur[sg.src + j] = sg.dst + j;
+                }
+        }
+    }
+    // ---- thread every surviving set through the unit (AG:884-1177) ----
+    struct Push { u32 pos, cid, coff; char base; };
+    std::vector<Push> pushes;          // chain-major: one thread after the other, each in walking order
+    std::vector<u32> term_of;          // per push: index of its thread's terminal push
+    std::vector<u32> count(u.n_ref, 0);  // contiMers per position so far (grows with the tail)
+    u.ref.resize(u.n_ref);
+    for (size_t sp = 0; sp < ch.size(); sp++) {
+        Chunk& c = ch[sp];
+        for (size_t pp = 0; pp < c.sets.size(); pp++) {
+            const std::vector<u32>& ps = c.sets[pp];
+            bool skip = false;
+            for (size_t e = 0; e < pp && !skip; e++) if (absdiff(ps[0], c.sets[e][0]) < (int)c.bases.size()) skip = true;  // AG:902-907
+            for (size_t i = 0; !skip && i + 1 < ps.size(); i++)
+                if (ps[i] != AG_NONE) { if (ps[i] >= count.size()) throw AgHostError{"CONTIG ALIGNMENT ERROR"}; if (count[ps[i]] >= 2) skip = true; }  // AG:908-920
+            if (skip) continue;
+            bool flipped = false;
+            if (c.fr[pp] == 1) { revcomp(c.bases); flipped = true; }
+            c.outputted = 1;
+            size_t first_push = pushes.size();
+            auto push = [&](u32 pos, u32 coff, char base) {
+                if (pos >= count.size()) throw AgHostError{"CONTIG ALIGNMENT ERROR"};
+                pushes.push_back(Push{pos, (u32)sp, coff, base}); count[pos]++;
+            };
+            u32 cur = AG_NONE, nxt = AG_NONE;
+            bool have_next = false;
+            size_t i;
+            for (i = 0; i + 1 < ps.size(); i++) {
+                if (ps[i] == AG_NONE) continue;
+                cur = ps[i]; nxt = ps[i + 1]; have_next = nxt != AG_NONE;
+                char base = c.bases[i];
+                if (nxt == AG_NONE) {  // bases inserted relative to the unit: append them behind the unit (SI = 0 => always "large", AG:974-1042)
+                    for (size_t m = i + 2; m < ps.size(); m++) {
+                        if (ps[m] == AG_NONE) continue;
+                        nxt = ps[m]; have_next = true;
+                        push(cur, (u32)i, base);
+                        for (size_t j = i + 1; j < m; j++) {
+                            u.ref.push_back(c.bases[j]); count.push_back(0);
+                            push((u32)u.ref.size() - 1, (u32)j, c.bases[j]);
+                        }
+                        i = m - 1;
+                        break;
+                    }
+                } else push(cur, (u32)i, base);  // ordinary step or deletion (SD = 0 => "large", AG:1075-1118)
+            }
+            if (cur != AG_NONE) {
+                // terminal contiMer carries the UNIT's base (AG:1121-1148)
+                u32 tp = have_next ? nxt : cur;
+                if (tp >= u.ref.size()) throw AgHostError{"CONTIG ALIGNMENT ERROR"};
+                push(tp, (u32)i, u.ref[tp]);
+            }
+            term_of.resize(pushes.size(), 0);
+            for (size_t k = first_push; k < pushes.size(); k++) term_of[k] = (u32)pushes.size() - 1;
+            if (flipped) revcomp(c.bases);
+        }
+    }
+    // ---- CSR by position, push order preserved ----
+    size_t n_pos = u.ref.size();
+    u.cm_start.assign(n_pos + 1, 0);
+    for (const Push& p : pushes) u.cm_start[p.pos + 1]++;
+    for (size_t i = 0; i < n_pos; i++) u.cm_start[i + 1] += u.cm_start[i];
+    u.cm.assign(pushes.size(), ag_cm{});
+    u.chain_pos.resize(pushes.size()); u.chain_base.resize(pushes.size());
+    {
+        std::vector<u32> fill(u.cm_start.begin(), u.cm_start.end() - 1);
+        for (size_t k = 0; k < pushes.size(); k++) {
+            const Push& p = pushes[k];
+            ag_cm m; m.cid = p.cid; m.coff = p.coff; m.chain = (u32)k; m.term = term_of[k];
+            u.cm[fill[p.pos]++] = m;
+            u.chain_pos[k] = p.pos; u.chain_base[k] = p.base;
+        }
+    }
+    // ---- tmp/_initial_contigs.N.fa: original contigs with >= 50 % of their chunks threaded (AG:1179-1216) ----
+    Out out(&initial_text);
+    size_t c = 0, cp = 0;
+    while (c < ch.size()) {
+        size_t e = c; int placed = 0, total = 0; std::string whole;
+        while (e < ch.size() && ch[e].id == ch[c].id) { total++; placed += ch[e].outputted; whole += ch[e].bases; e++; }
+        if ((double)placed / (double)total >= kContigThreshold) { out.ch('>'); out.num(cp); out.ch('\n'); out.wrap60(whole); }
+        cp++; c = e;
+    }
+}
+
+// =============================================================================================================================
+// SAM -> alignments
+// =============================================================================================================================
+namespace {
+struct SamRec { u32 tid, tstart, tend, tgap, sid, sstart, send, sgap, ssize, fr; };
+
+// AG:181-285.  Appends to `segs` (the caller clears — or, on the reference's `continue` paths, does not: AG:1258).
+void parse_sam(const char* s, size_t n, SamRec& r, std::vector<ag_seg>& segs) {
+    const char* f[6]; size_t fl[6]; int nf = 0;
+    const char* p = s; const char* end = s + n;
+    while (nf < 6) {
+        const char* e = (const char*)memchr(p, '\t', (size_t)(end - p));
+        f[nf] = p; fl[nf] = e ? (size_t)(e - p) : (size_t)(end - p); nf++;
+        if (!e) break;
+        p = e + 1;
+    }
+    for (int i = nf; i < 6; i++) { f[i] = end; fl[i] = 0; }
+    r.sid = (u32)ag_atoi(f[0], fl[0]);
+    r.fr = (ag_atoi(f[1], fl[1]) & 0x10) ? 1u : 0u;
+    if (memchr(f[2], '*', fl[2])) { r.tid = r.tstart = r.tend = r.tgap = r.sstart = r.send = r.sgap = r.ssize = AG_NONE; return; }
+    const char* dot = (const char*)memchr(f[2], '.', fl[2]);
+    int pos = ag_atoi(f[3], fl[3]);
+    int ins = 0, del = 0, total = 0, start = 0, end_clip = 0, lead = 1, num = 0;
+    bool have_num = false;
+    for (size_t i = 0; i < fl[5]; i++) {
+        char c = f[5][i];
+        if (c >= '0' && c <= '9') { num = have_num ? num * 10 + (c - '0') : (c - '0'); have_num = true; continue; }
+        int v = have_num ? num : 0;
+        if (c == 'I') { ins += v; total += v; }
+        else if (c == 'D') { del += v; }
+        else if (c == 'M') { ag_seg sg; sg.src = (u32)total; sg.dst = (u32)(pos + total + del - start - ins - 1); sg.len = (u32)v; segs.push_back(sg); total += v; lead = 0; }
+        else if (c == 'S' && lead) { start = v; total += v; lead = 0; }
+        else if (c == 'S') { end_clip = v; total += v; }
+        else if (c != '*') { throw AgHostError{std::string("unknown character: ") + c}; }
+        else continue;  // '*' leaves the digit buffer alone (AG:263-270)
+        have_num = false; num = 0;
+    }
+    r.sstart = (u32)start; r.send = (u32)(total - end_clip); r.sgap = (u32)ins; r.ssize = (u32)total;
+    r.tid = dot ? (u32)ag_atoi(f[2], (size_t)(dot - f[2])) : 0u;
+    r.tstart = (u32)(pos - 1);
+    r.tend = r.tstart + (u32)total + (u32)del - (u32)ins;
+    r.tgap = (u32)del;
+}
+
+// position of read offset 0 in the position set the reference would have built from `segs` (later segments overwrite)
+u32 pos_at0(const std::vector<ag_seg>& segs) {
+    u32 r = AG_NONE;
+    for (const ag_seg& s : segs) if (s.len && s.src == 0) r = s.dst;
+    return r;
+}
+
+// monotone, disjoint, merged segment list equivalent to the position set built from `segs`
+void normalize(const std::vector<ag_seg>& in, u32 rlen, std::vector<ag_seg>& out) {
+    out.clear();
+    bool clean = true;
+    for (const ag_seg& s : in) {
+        if (!s.len) continue;
+        if ((u64)s.src + s.len > rlen) throw AgHostError{"BOWTIE ALIGNMENT ERROR"};  // CIGAR longer than the read: the reference writes out of bounds
+        if (!out.empty()) {
+            ag_seg& b = out.back();
+            if (s.src < b.src + b.len || s.dst < b.dst + b.len) { clean = false; break; }
+            if (s.src == b.src + b.len && s.dst == b.dst + b.len) { b.len += s.len; continue; }
+        }
+        out.push_back(s);
+    }
+    if (clean) return;
+    std::vector<u32> pos(rlen, AG_NONE);
+    for (const ag_seg& s : in) for (u32 j = 0; j < s.len; j++) pos[s.src + j] = s.dst + j;
+    out.clear();
+    for (u32 i = 0; i < rlen; i++) {
+        if (pos[i] == AG_NONE) continue;
+        if (!out.empty() && out.back().src + out.back().len == i && out.back().dst + out.back().len == pos[i]) { out.back().len++; continue; }
+        if (!out.empty() && pos[i] < out.back().dst + out.back().len) throw AgHostError{"BOWTIE ALIGNMENT ERROR"};  // non-monotone: unsupported
+        ag_seg sg; sg.src = i; sg.dst = pos[i]; sg.len = 1; out.push_back(sg);
+    }
+}
+}  // namespace
+
+void ag_parse_sam(const std::string& path, const AgReads& reads, AgUnit& u) {
+    FileMap fm(path);
+    if (!fm.ok) throw AgHostError{"CANNOT OPEN FILE!"};
+    u.aln.clear(); u.ext.clear();
+    if (reads.n_pairs == 0) return;
+    struct Tmp { u32 pair, fr1, fr2, p0; std::vector<ag_seg> s1, s2; };
+    std::vector<Tmp> batch;
+    std::vector<ag_seg> segs1, segs2, n1, n2;
+    long n_pairs = (long)reads.n_pairs;
+    long first = 0, last = std::min<long>(kBatchPairs - 1, n_pairs - 1);
+    Lines ln(fm.p, fm.n); const char* s; size_t n;
+
+    auto flush_batch = [&]() {
+        bool sorted = true;
+        for (size_t i = 1; i < batch.size(); i++) if (batch[i].pair < batch[i - 1].pair) { sorted = false; break; }
+        if (!sorted) std::stable_sort(batch.begin(), batch.end(), [](const Tmp& a, const Tmp& b) { return a.pair < b.pair; });
+        for (size_t i = 0; i < batch.size();) {
+            size_t e = i;
+            while (e < batch.size() && batch[e].pair == batch[i].pair) e++;
+            u32 rlen = reads.len[batch[i].pair];
+            for (size_t pp = i; pp < e; pp++) {
+                bool dup = false;  // AG:1650-1655: compared against EVERY earlier alignment of the pair, skipped ones included
+                for (size_t q = i; q < pp && !dup; q++) if (absdiff(batch[pp].p0, batch[q].p0) < (int)rlen) dup = true;
+                if (dup) continue;
+                Tmp& t = batch[pp];
+                if (!((t.fr1 == 1 && t.fr2 == 0) || (t.fr2 == 1 && t.fr1 == 0))) throw AgHostError{"BOWTIE ALIGNMENT ERROR"};  // AG:1657-1671
+                normalize(t.s1, rlen, n1); normalize(t.s2, rlen, n2);
+                if (n1.empty() || n2.empty() || n1.size() > 255 || n2.size() > 255) throw AgHostError{"BOWTIE ALIGNMENT ERROR"};
+                ag_aln a; a.pair = t.pair; a.pad = 0;
+                a.flags = t.fr1 | (t.fr2 << 1) | ((u32)n1.size() << 8) | ((u32)n2.size() << 16);
+                a.dst1 = n1[0].dst; a.sl1 = n1[0].src | (n1[0].len << 16);
+                a.dst2 = n2[0].dst; a.sl2 = n2[0].src | (n2[0].len << 16);
+                a.ext_idx = (u32)u.ext.size();
+                if (n1.size() > 1) u.ext.insert(u.ext.end(), n1.begin(), n1.end());
+                if (n2.size() > 1) u.ext.insert(u.ext.end(), n2.begin(), n2.end());
+                u.aln.push_back(a);
+            }
+            i = e;
+        }
+        batch.clear();
+    };
+
+    for (;;) {  // one iteration per read batch (AG:1885-1894)
+        bool dropped = false;
+        segs1.clear(); segs2.clear();
+        while (ln.next(s, n)) {
+            if (n == 0 || s[0] == 0) break;
+            if (s[0] == '@') continue;
+            SamRec a, b;
+            parse_sam(s, n, a, segs1);
+            if (!ln.next(s, n) || n == 0 || s[0] == 0) throw AgHostError{"BROKEN BOWTIE FILE"};
+            parse_sam(s, n, b, segs2);
+            if (a.sid < (u32)first) continue;                  // AG:1258 (segment lists are NOT cleared on this path)
+            if (a.sid > (u32)last) { dropped = true; break; }  // AG:1259: this record pair is consumed and lost
+            if (a.tid != AG_NONE && b.tid != AG_NONE &&
+                (double)(a.send - a.sstart - a.sgap) / a.ssize >= kReadThreshold && (double)(a.tend - a.tstart - a.tgap) / (a.tend - a.tstart) >= kReadThreshold &&
+                (double)(b.send - b.sstart - b.sgap) / b.ssize >= kReadThreshold && (double)(b.tend - b.tstart - b.tgap) / (b.tend - b.tstart) >= kReadThreshold) {
+                if (a.tid != 0 || b.tid != 0 || b.sid != a.sid) throw AgHostError{"BROKEN BOWTIE FILE"};
+                Tmp t; t.pair = a.sid; t.fr1 = a.fr; t.fr2 = b.fr; t.p0 = pos_at0(segs1); t.s1 = segs1; t.s2 = segs2;
+                batch.push_back(std::move(t));
+            }
+            segs1.clear(); segs2.clear();
+        }
+        flush_batch();
+        (void)dropped;
+        // the reference starts another batch as long as the read file has more pairs (AG:1889-1894), whatever ended this one
+        if (last >= n_pairs - 1 || !ln.good) break;
+        first = last + 1; last = std::min<long>(first + kBatchPairs - 1, n_pairs - 1);
+    }
+}
+
+// =============================================================================================================================
+// post passes
+// =============================================================================================================================
+void ag_select_emitted(const std::vector<ag_walk>& walks, std::vector<u32>& sel) {
+    sel.clear();
+    bool have = false; u32 bso = 0, beo = 0;
+    for (size_t i = 0; i < walks.size(); i++) {
+        const ag_walk& r = walks[i];
+        u32 eoff = r.eoff;
+        if (((r.flags >> 1) & 3) != 1) eoff = eoff + (r.tail_soff_len >> 16) - 1;  // AG:2164-2173 (u32 wrap when the string is empty)
+        // contain(startIDBak, ..) — the Bak ids are -1 until the first emission, then 0 like every id in a unit (AG:1897-1902)
+        if (have && bso <= r.soff && beo >= eoff) continue;
+        sel.push_back((u32)i);
+        have = true; bso = r.soff; beo = eoff;
+    }
+}
+
+void ag_make_contigs(const std::vector<ag_walk>& walks, const std::vector<u32>& sel, const std::string& bases, const std::vector<u64>& offs,
+                     const AgReads& reads, std::vector<AgContig>& contigs, std::string& pre_text) {
+    Out out(&pre_text);
+    contigs.clear(); contigs.reserve(sel.size());
+    for (size_t i = 0; i < sel.size(); i++) {
+        const ag_walk& r = walks[sel[i]];
+        AgContig c;
+        c.extended = (int)(r.flags & 1);
+        c.sid = 0; c.soff = r.soff; c.eid = 0; c.eoff = r.eoff;
+        c.sid0 = r.soff0 == AG_NONE ? AG_NONE : 0; c.soff0 = r.soff0;
+        c.bases.assign(bases, offs[i], offs[i + 1] - offs[i]);
+        u32 mode = (r.flags >> 1) & 3;
+        if (mode == 1) { c.eid0 = AG_NONE; c.eoff0 = AG_NONE; }  // walk ended on a contiMer (AG:2158-2162)
+        else {
+            c.eid0 = r.eoff0 == AG_NONE ? AG_NONE : 0; c.eoff0 = r.eoff0;
+            u32 slen = r.tail_soff_len >> 16, soff = r.tail_soff_len & 0xFFFFu, read = r.tail_sread >> 1, rc = r.tail_sread & 1;
+            u32 rlen = slen ? reads.len[read >> 1] : 0;
+            for (u32 j = 1; j < slen; j++) c.bases.push_back(reads.at(read, rc, rlen, soff + j));
+            c.eoff = c.eoff + slen - 1; c.eoff0 = c.eoff0 + slen - 1;
+        }
+        out.ch('>'); out.num(i); out.put(", ", 2); out.inum(c.extended); out.put(", ", 2);
+        out.num(c.sid); out.put(", ", 2); out.num(c.soff); out.put(", ", 2); out.num(c.eid); out.put(", ", 2); out.num(c.eoff); out.put(", ", 2);
+        out.num(c.sid0); out.put(", ", 2); out.num(c.soff0); out.put(", ", 2); out.num(c.eid0); out.put(", ", 2); out.num(c.eoff0); out.put(" \n", 2);
+        out.wrap60(c.bases);
+        contigs.push_back(std::move(c));
+    }
+}
+
+static inline int contain(const AgContig& a, const AgContig& b) { return a.sid == b.sid && a.eid == b.eid && a.soff <= b.soff && a.eoff >= b.eoff; }
+
+void ag_dedup_join(std::vector<AgContig>& cs) {
+    int n = (int)cs.size();
+    for (int a = 0; a < n; a++) {  // forward containment (AG:2303-2320)
+        if (cs[a].extended != 1) continue;
+        for (int b = a + 1; b < n; b++) {
+            if (contain(cs[a], cs[b])) cs[b].extended = 2;
+            else if (cs[a].eid != cs[b].sid || cs[a].eoff < cs[b].soff) break;
+        }
+    }
+    for (int a = n - 1; a >= 0; a--) {  // backward containment (AG:2322-2339)
+        if (cs[a].extended != 1) continue;
+        for (int b = a - 1; b >= 0; b--) {
+            if (contain(cs[a], cs[b])) cs[b].extended = 2;
+            else if (cs[b].eid != cs[a].sid || cs[b].eoff < cs[a].soff) break;
+        }
+    }
+    for (int a = 0; a < n; a++) {  // join with the single later contig that starts inside (AG:2342-2378)
+        while (cs[a].extended == 1) {
+            int hits = 0, lastb = -1;
+            for (int b = a + 1; b < n; b++) {
+                if (cs[b].extended == 2) continue;
+                if (cs[a].eoff >= cs[b].soff) { hits++; lastb = b; } else break;
+            }
+            if (hits != 1) break;
+            AgContig& t = cs[lastb];
+            t.extended = 2;
+            u32 from = cs[a].eoff - t.soff + 1;
+            if (from < t.bases.size()) cs[a].bases.append(t.bases, from, std::string::npos);
+            cs[a].eid = t.eid; cs[a].eoff = t.eoff; cs[a].eid0 = t.eid0; cs[a].eoff0 = t.eoff0;
+        }
+    }
+}
+
+static inline int overlap(u32 x1, u32 y1, u32 x2, u32 y2) {  // AG:2388-2394
+    return (x1 <= x2 && x2 <= y1 && y1 <= y2 && (int)y1 - (int)x2 > 0) || (x2 <= x1 && x1 <= y2 && y2 <= y1 && (int)y2 - (int)x1 > 0) ||
+           (x1 <= x2 && x2 <= y2 && y2 <= y1 && (int)y2 - (int)x2 > 0) || (x2 <= x1 && x1 <= y1 && y1 <= y2 && (int)y1 - (int)x1 > 0);
+}
+
+void ag_scaffold(std::vector<AgContig>& cs, const std::string& ref, const std::vector<unsigned char>& occ, std::string& text) {
+    std::vector<std::string> sc;
+    auto occupied = [&](u32 p) { return (size_t)(p >> 3) < occ.size() && ((occ[p >> 3] >> (p & 7)) & 1); };
+    for (u32 cp = 0; cp < cs.size(); cp++) {
+        if (!(cs[cp].sid != AG_NONE && cs[cp].extended == 1)) continue;
+        sc.push_back(cs[cp].bases);
+        cs[cp].sid = AG_NONE;
+        int cont = 1;
+        while (cs[cp].sid0 == cs[cp].eid0 && cont) {
+            cont = 0;
+            for (u32 c0 = cp + 1; c0 < cs.size(); c0++) {
+                const AgContig& a = cs[cp]; AgContig& b = cs[c0];
+                if (!(a.eid0 == b.sid && b.sid == b.eid && overlap(a.soff0, a.eoff0, b.soff, b.eoff) && b.extended == 1)) continue;
+                if (b.soff > a.eoff) {
+                    u32 gap = b.soff - a.eoff - 1; int covered = 0;
+                    for (u32 i = 0; i < gap; i++) if (occupied(a.eoff + i + 1)) covered++;
+                    if ((gap != 0 && (double)covered / gap >= 0.5) || gap == 0) { for (u32 i = 0; i < gap; i++) sc.back().push_back(ref[a.eoff + i + 1]); }
+                    else continue;
+                }
+                sc.back() += b.bases;
+                b.sid = AG_NONE;
+                cp = c0; cont = 1;
+                break;
+            }
+        }
+    }
+    Out out(&text);
+    for (size_t i = 0; i < sc.size(); i++) { out.ch('>'); out.num(i); out.ch('\n'); out.wrap60(sc[i]); }
+}
+
+// =============================================================================================================================
+// input normalisation (--resume re-runs these, AG:4757-4758)
+// =============================================================================================================================
+void ag_formalize_contigs(const std::string& in_path, const std::string& tmp, std::vector<std::string>& contig_ids) {
+    FileMap fm(in_path);
+    if (!fm.ok) throw AgHostError{"CANNOT OPEN FILE!"};
+    std::vector<std::string> seqs, ids;
+    {
+        Lines ln(fm.p, fm.n); const char* s; size_t n;
+        while (ln.next(s, n)) {
+            if (n == 0 || s[0] == 0) break;
+            if (s[0] == '>') { seqs.emplace_back(); ids.emplace_back(s + 1, n - 1); }
+            else if (!seqs.empty()) seqs.back().append(s, n);
+        }
+    }
+    Out out(tmp + "/_contigs.fa"), chaff(tmp + "/_chaff.fa");
+    contig_ids.clear();
+    unsigned long chunk = 0, real = 0;
+    for (size_t c = 0; c < seqs.size(); c++) {
+        const std::string& q = seqs[c];
+        if (q.size() > 200) {
+            auto header = [&]() { out.ch('>'); out.num(chunk++); out.ch('.'); out.num(real); out.ch('\n'); };
+            header();
+            if ((long)q.size() < kLargeChunk) out.wrap60(q);
+            else {
+                long total = 0;
+                for (long i = 0; i < (long)q.size(); i++) {
+                    out.ch(q[i]);
+                    if ((i + 1) % kLargeChunk == 0 && i < (long)q.size() - 1 - 60) { total += kLargeChunk; out.ch('\n'); header(); continue; }
+                    if ((i + 1 - total) % 60 == 0 || i == (long)q.size() - 1) out.ch('\n');
+                }
+            }
+            real++;
+            contig_ids.push_back(ids[c]);
+        } else { chaff.ch('>'); chaff.put(ids[c]); chaff.ch('\n'); chaff.wrap60(q); }
+    }
+}
+
+int ag_formalize_genome(const std::string& in_path, const std::string& tmp, int part, std::vector<std::string>& genome_ids) {
+    FileMap fm(in_path);
+    if (!fm.ok) throw AgHostError{"CANNOT OPEN FILE!"};
+    std::vector<std::string> chr;
+    {
+        Lines ln(fm.p, fm.n); const char* s; size_t n;
+        while (ln.next(s, n)) {
+            if (n == 0 || s[0] == 0) break;
+            if (s[0] == '>') { chr.emplace_back(); genome_ids.emplace_back(s + 1, n - 1); }
+            else if (!chr.empty()) chr.back().append(s, n);
+        }
+    }
+    int unit = 0;
+    Out all(tmp + "/_genome.fa");
+    for (size_t g = 0; g < chr.size(); g++) {
+        const std::string& q = chr[g];
+        Out* out = new Out(tmp + "/_genome." + std::to_string(unit) + ".fa");
+        out->put(">0\n", 3); all.ch('>'); all.num((unsigned long)unit); all.ch('\n');
+        int k = 1; long slice = (long)q.size() / part;
+        for (long i = 0; i < (long)q.size(); i++) {
+            out->ch(q[i]); all.ch(q[i]);
+            bool cut = slice > 0 && ((i + 1) % slice == 0 && k < part);
+            if ((i + 1) % 60 == 0 || i == (long)q.size() - 1 || cut) { out->ch('\n'); all.ch('\n'); }
+            if (i != (long)q.size() - 1 && cut) {
+                delete out; unit++; k++;
+                out = new Out(tmp + "/_genome." + std::to_string(unit) + ".fa");
+                out->put(">0\n", 3); all.ch('>'); all.num((unsigned long)unit); all.ch('\n');
+            }
+        }
+        delete out; unit++;
+    }
+    return unit;
+}
+
+void ag_write_file(const std::string& path, const std::string& text) {
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) throw AgHostError{"CANNOT OPEN FILE!"};
+    if (!text.empty()) fwrite(text.data(), 1, text.size(), f);
+    fclose(f);
+}

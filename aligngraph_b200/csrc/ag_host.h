@@ -1,0 +1,56 @@
+// Host side of the B200 AlignGraph hot path: the text <-> packed-array boundary of the reference's tmp/ file contract
+//  and the order-dependent FASTA post-passes.  Everything here is cheap, sequential text / interval logic; the
+// graph build and the walk run on the device (ag_device.cu).
+#pragma once
+#include "ag_types.h"
+#include <string>
+#include <vector>
+#include <cstdio>
+
+struct AgHostError { std::string msg; };  // message the CLI prints on stdout before exit(-1), as the reference does
+
+// ---- reads (tmp/_reads.fa, AG:361-404) -----------------------------------------------------------------------------------
+struct AgReads {
+    std::vector<u32> bases, nmask;   // 2 bits / base, 16 per word; 1 bit / base, 32 per word; fixed stride per read
+    std::vector<uint16_t> len;       // per pair
+    std::vector<std::pair<u64, char>> exc;  // (read * 65536 + offset, original character) for every non-ACGT character, sorted
+    u64 n_pairs = 0;
+    u32 stride2 = 0, stridem = 0;
+    char at(u32 read, u32 rc, u32 rlen, u32 off) const;  // character of the oriented read (AG:854-865 leaves non-ACGT unchanged)
+};
+void ag_parse_reads(const std::string& path, AgReads& out);
+// pack in-memory reads (one string per read, mates interleaved) — used by the synthetic bench and tests
+void ag_pack_reads(const std::vector<std::string>& seqs, AgReads& out);
+
+// ---- one unit -----------------------------------------------------------------------------------------------------------------
+struct AgUnit {
+    std::string ref;                 // unit bases + contig-insertion tail
+    u32 n_ref = 0;
+    std::vector<u32> cm_start;       // CSR over positions (ref.size() + 1)
+    std::vector<ag_cm> cm;
+    std::vector<u32> chain_pos;      // chain-major
+    std::string chain_base;
+    std::vector<ag_aln> aln;
+    std::vector<ag_seg> ext;
+};
+void ag_load_genome(const std::string& path, AgUnit& u);                                         // AG:287-320
+// contig chunks + PSL -> contiMer table + the text of tmp/_initial_contigs.N.fa                       // AG:1219-1231
+void ag_thread_contigs(const std::string& contigs_fa, const std::string& psl, std::string& initial_text, AgUnit& u);
+// SAM -> surviving alignments in processing order                                                 // AG:1233-1277, 1644-1656, 1872-1895
+void ag_parse_sam(const std::string& path, const AgReads& reads, AgUnit& u);
+
+// ---- post passes --------------------------------------------------------------------------------------------------------------------
+struct AgContig { int extended; u32 sid, soff, eid, eoff, sid0, soff0, eid0, eoff0; std::string bases; };
+// emission filter of extdContigs1 (AG:2176-2189): indices of the walks that are written to _pre_extended_contigs
+void ag_select_emitted(const std::vector<ag_walk>& walks, std::vector<u32>& sel);
+// assemble emitted contigs (bases from the device + s[1..] tails from the reads) + the text of tmp/_pre_extended_contigs.N.fa
+void ag_make_contigs(const std::vector<ag_walk>& walks, const std::vector<u32>& sel, const std::string& bases, const std::vector<u64>& offs,
+                     const AgReads& reads, std::vector<AgContig>& contigs, std::string& pre_text);
+void ag_dedup_join(std::vector<AgContig>& contigs);                                               // AG:2296-2380
+// AG:2396-2464; occ = bitmap "position holds a node or a contiMer"
+void ag_scaffold(std::vector<AgContig>& contigs, const std::string& ref, const std::vector<unsigned char>& occ, std::string& text);
+
+// ---- input normalisation re-run by --resume (AG:3228-3345, AG:3347-3418) ----------------------------------------------------
+void ag_formalize_contigs(const std::string& in_path, const std::string& tmp, std::vector<std::string>& contig_ids);
+int ag_formalize_genome(const std::string& in_path, const std::string& tmp, int part, std::vector<std::string>& genome_ids);
+void ag_write_file(const std::string& path, const std::string& text);

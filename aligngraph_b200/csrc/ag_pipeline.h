@@ -1,0 +1,92 @@
+// One unit (chromosome or --part slice) through the hot path: the five calls of the reference's loop body (AG:4768-4776)
+// expressed over an Engine.  The product instantiates it with AgDevice (CUDA, ag_device.cu); the CPU test-suite instantiates
+// it with a host emulation of the same per-thread code (tests/emul) to check the formulation without a GPU.
+#pragma once
+#include "ag_host.h"
+#include "ag_device.cuh"
+#include <chrono>
+
+struct AgUnitResult {
+    std::string initial_text, pre_text, ext_text;  // tmp/_initial_contigs.N.fa, _pre_extended_contigs.N.fa, _extended_contigs.N.fa
+    double t_parse = 0, t_device = 0, t_post = 0;  // wall seconds: host parsing / device section incl. copies / host post passes
+    u64 n_aln = 0, n_walks = 0, n_emitted = 0;
+};
+
+inline AgUnitInput ag_unit_input(const AgUnit& u) {
+    AgUnitInput in;
+    in.ref = u.ref.data(); in.n_ref = u.n_ref; in.n_pos = (u32)u.ref.size();
+    in.cm_start = u.cm_start.data(); in.cm = u.cm.data(); in.n_cm = (u32)u.cm.size();
+    in.chain_pos = u.chain_pos.data(); in.chain_base = u.chain_base.data();
+    in.aln = u.aln.data(); in.n_aln = u.aln.size(); in.ext = u.ext.data(); in.n_ext = u.ext.size();
+    return in;
+}
+
+// loadGenome + loadContigAlignment + the parsing half of loadReadAlignment (AG:4768-4772)
+inline void ag_prepare_unit(const AgReads& reads, const std::string& tmp, int unit, AgUnit& u, std::string& initial_text) {
+    std::string n = std::to_string(unit);
+    ag_load_genome(tmp + "/_genome." + n + ".fa", u);
+    ag_thread_contigs(tmp + "/_contigs.fa", tmp + "/_contigs_genome." + n + ".psl", initial_text, u);
+    ag_parse_sam(tmp + "/_reads_genome." + n + ".bowtie", reads, u);
+}
+
+// graph build + extendContigs + scaffoldContigs on prepared arrays
+template <class Engine> void ag_process_unit(Engine& eng, const AgReads& reads, const AgUnit& u, AgUnitResult& r) {
+    auto t0 = std::chrono::steady_clock::now();
+    eng.load_unit(ag_unit_input(u));
+    eng.build();
+    std::vector<ag_walk> walks;
+    eng.extend(walks);
+    std::vector<u32> sel;
+    ag_select_emitted(walks, sel);
+    std::string bases; std::vector<u64> offs;
+    eng.materialize(walks, sel, bases, offs);
+    std::vector<unsigned char> occ;
+    eng.occupancy(occ);
+    auto t1 = std::chrono::steady_clock::now();
+    std::vector<AgContig> contigs;
+    ag_make_contigs(walks, sel, bases, offs, reads, contigs, r.pre_text);
+    ag_dedup_join(contigs);
+    ag_scaffold(contigs, u.ref, occ, r.ext_text);
+    auto t2 = std::chrono::steady_clock::now();
+    r.t_device += std::chrono::duration<double>(t1 - t0).count();
+    r.t_post += std::chrono::duration<double>(t2 - t1).count();
+    r.n_aln = u.aln.size(); r.n_walks = walks.size(); r.n_emitted = sel.size();
+}
+
+template <class Engine> void ag_run_unit_files(Engine& eng, const AgReads& reads, const std::string& tmp, int unit, AgUnitResult& r, bool write = true) {
+    auto t0 = std::chrono::steady_clock::now();
+    AgUnit u;
+    ag_prepare_unit(reads, tmp, unit, u, r.initial_text);
+    r.t_parse += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    ag_process_unit(eng, reads, u, r);
+    if (write) {
+        std::string n = std::to_string(unit);
+        ag_write_file(tmp + "/_initial_contigs." + n + ".fa", r.initial_text);
+        ag_write_file(tmp + "/_pre_extended_contigs." + n + ".fa", r.pre_text);
+        ag_write_file(tmp + "/_extended_contigs." + n + ".fa", r.ext_text);
+    }
+}
+
+// Node table as text, one line per node in (position, item) order — the format of the oracle's --dump-nodes, for node-level
+// parity tests:  pos item cov A C G T N cid coff cid0 coff0 mid moff [s] succPos:succItem ...
+inline void ag_format_node_dump(const AgNodeDump& d, const AgReads& reads, std::string& text) {
+    text.clear();
+    char buf[256];
+    // global node index -> (pos, item)
+    for (size_t v = 0; v < d.pos.size(); v++) {
+        u32 moff = d.moff[v];
+        int n = snprintf(buf, sizeof buf, "%u %u %u %u %u %u %u %u %u %u %u %u %u %u [", d.pos[v], d.item[v], d.cov[v], d.cnt[5 * v], d.cnt[5 * v + 1], d.cnt[5 * v + 2],
+                         d.cnt[5 * v + 3], d.cnt[5 * v + 4], d.cid[v], d.coff[v], d.cid0[v], d.coff0[v], moff == AG_NONE ? AG_NONE : 0u, moff);
+        text.append(buf, (size_t)n);
+        u32 slen = d.soff_len[v] >> 16, soff = d.soff_len[v] & 0xFFFFu, read = d.sread[v] >> 1, rc = d.sread[v] & 1;
+        u32 rlen = slen ? reads.len[read >> 1] : 0;
+        for (u32 j = 0; j < slen; j++) text.push_back(reads.at(read, rc, rlen, soff + j));
+        text.push_back(']');
+        for (u32 e = d.edge_start[v]; e < d.edge_start[v + 1]; e++) {
+            u32 t = d.edge_target[e];
+            n = snprintf(buf, sizeof buf, " %u:%u", d.pos[t], d.item[t]);
+            text.append(buf, (size_t)n);
+        }
+        text.push_back('\n');
+    }
+}

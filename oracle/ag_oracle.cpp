@@ -427,7 +427,7 @@ static void countBase(const std::string& s, Node& n) {  // AG:1340-1351
     switch (s[0]) { case 'A': n.a++; break; case 'C': n.c++; break; case 'G': n.g++; break; case 'T': n.t++; break; default: n.n++; }
 }
 
-static long g_events = 0;
+static long g_events = 0, g_walks = 0, g_walk_bases = 0, g_walk_max = 0, g_chain_steps = 0, g_emitted = 0, g_emitted_bases = 0;
 
 // One side of updateKMer (AG:1362-1477 for the node at P with bump=true, AG:1480-1587 for the node at nextP with
 // bump=false): enumerate candidates = contiMers at P x contiMers at the mate position, first-compatible lookup, create
@@ -568,7 +568,7 @@ static void walk(int coverage, int unit) {  // AG:1954-2204
             int mode = 1;                            // kMerTag
             std::string tail;
             while ((mode == 1 && G[p].nodes[it].traversed == 0) || mode == 0) {
-                if (mode == 0) c.bases += G[p].cm[it].base;
+                if (mode == 0) { c.bases += G[p].cm[it].base; g_chain_steps++; }
                 else { char b = consensus(G[p].nodes[it]); c.bases += (b != 'X') ? b : G[p].base; }
                 if ((mode == 1 && G[p].nodes[it].coff != NONE) || mode == 0) c.extended = 1;
                 if (mode == 1) {
@@ -607,7 +607,9 @@ static void walk(int coverage, int unit) {  // AG:1954-2204
                 c.eoff = (u32)(c.eoff + tail.size() - 1);      // size_t arithmetic truncated to u32 (AG:2170-2171)
                 c.eoff0 = (u32)(c.eoff0 + tail.size() - 1);
             }
+            g_walks++; g_walk_bases += (long)c.bases.size(); if ((long)c.bases.size() > g_walk_max) g_walk_max = (long)c.bases.size();
             if (!contain(bsi, bso, bei, beo, c.sid, c.soff, c.eid, c.eoff)) {
+                g_emitted++; g_emitted_bases += (long)c.bases.size();
                 out << ">" << seq++ << ", " << c.extended << ", " << c.sid << ", " << c.soff << ", " << c.eid << ", " << c.eoff << ", "
                     << c.sid0 << ", " << c.soff0 << ", " << c.eid0 << ", " << c.eoff0 << " \n";
                 wrap60(out, c.bases);
@@ -757,7 +759,8 @@ int main(int argc, char** argv) {
         size_t nn = 0, ne = 0; for (auto& s : G) { nn += s.nodes.size(); for (auto& n : s.nodes) ne += n.next.size(); }
         fprintf(stderr, "oracle unit %d: bp=%zu nodes=%zu edges=%zu events=%ld  contigs %.3fs reads %.3fs extend %.3fs\n", unit, G.size(), nn, ne, g_events,
                 std::chrono::duration<double>(t1 - t0).count(), std::chrono::duration<double>(t2 - t1).count(), std::chrono::duration<double>(t3 - t2).count());
-        contigs.clear(); G.clear(); lastSource = NONE; g_events = 0;
+        fprintf(stderr, "  walks=%ld walk_bases=%ld max_walk=%ld chain_steps=%ld emitted=%ld emitted_bases=%ld\n", g_walks, g_walk_bases, g_walk_max, g_chain_steps, g_emitted, g_emitted_bases);
+        contigs.clear(); G.clear(); lastSource = NONE; g_events = 0; g_walks = g_walk_bases = g_walk_max = g_chain_steps = g_emitted = g_emitted_bases = 0;
     }
     return 0;
 }

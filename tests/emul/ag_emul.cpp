@@ -1,0 +1,288 @@
+// ag_emul — HOST EMULATION of the device pipeline, for the CPU test-suite only.
+//
+// *** TEST INFRASTRUCTURE.  Never built into, linked with or loaded by the product. ***
+// There is no GPU in the development container, so the per-thread logic of the CUDA kernels lives in
+// aligngraph_b200/csrc/ag_core.h as host+device functions; this program drives exactly those functions with plain loops
+// (one "thread" per unit position / alignment / component, in the same order the kernels guarantee) so that the position-parallel
+// formulation — touch fusion, first-compatible-on-final-table edges, component-parallel walk — is checked against the oracle
+// and the reference on CPU.  The CUDA kernels themselves (sort, scans, pools, launches) are covered by the `-m gpu` tests.
+#include "../../aligngraph_b200/csrc/ag_core.h"
+#include "../../aligngraph_b200/csrc/ag_pipeline.h"
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <unistd.h>
+
+class AgEmul {
+public:
+    int k = 5, iv = 50, cov = 20;
+    AgUnitInput in{};
+    ag_reads rd{};
+    // products
+    std::vector<ag_alnp> alnp; std::vector<u32> lo, span;
+    std::vector<std::vector<u32>> tiles;
+    std::vector<u32> pos_node, node_pos, node_sref, eovf_head, eovf_target, eovf_next, walk_next, parent;
+    std::vector<ag_nodeb> nodeb;  // final order
+    std::vector<ag_nodem> node_m; std::vector<ag_nodew> node_w; std::vector<unsigned char> trav;
+    std::vector<ag_nodeb> ovf_node; std::vector<u32> ovf_next; u32 ovf_count = 0; int err = 0;
+    u32 n_nodes = 0;
+    bool fallback_used = false;
+
+    void set_reads(const AgReads& r) { rd.bases = r.bases.data(); rd.nmask = r.nmask.data(); rd.len = r.len.data(); rd.stride2 = r.stride2; rd.stridem = r.stridem; }
+    void load_unit(const AgUnitInput& i) { in = i; }
+
+    ag_cmtab cmt() const { ag_cmtab t; t.start = in.cm_start; t.cm = in.cm; return t; }
+
+    void build() {
+        const u32 nA = (u32)in.n_aln, n_ref = in.n_ref, n_pos = in.n_pos;
+        alnp.resize(nA); lo.resize(nA); span.resize(nA);
+        u32 n_tiles = (n_ref + AG_TILE - 1) / AG_TILE;
+        tiles.assign(n_tiles, {});
+        for (u32 i = 0; i < nA; i++) {  // k_prep + k_keys + sort
+            ag_prep_out o = ag_prep(in.aln[i], in.ext, rd.len[in.aln[i].pair], (u32)k);
+            alnp[i] = o.p; lo[i] = o.lo; span[i] = o.span;
+            if (!o.any) continue;
+            if (o.lo + o.span >= n_ref) throw AgHostError{"BOWTIE ALIGNMENT ERROR"};
+            for (u32 t = o.lo / AG_TILE; t <= (o.lo + o.span) / AG_TILE; t++) tiles[t].push_back(i);
+        }
+        ovf_node.assign(1 << 16, ag_nodeb{}); ovf_next.assign(1 << 16, 0); ovf_count = 0;
+        ag_ovfpool pool; pool.node = ovf_node.data(); pool.next = ovf_next.data(); pool.count = &ovf_count; pool.cap = (u32)ovf_node.size(); pool.err = &err;
+        ag_cmtab ct = cmt();
+        pos_node.assign((size_t)n_pos + 1, 0);
+        nodeb.clear();
+        for (u32 q = 0; q < n_ref; q++) {  // k_nodes
+            ag_nodelist nl; nl.init();
+            for (u32 idx : tiles[q / AG_TILE]) {
+                if (q - lo[idx] > span[idx]) continue;
+                const ag_alnp& p = alnp[idx];
+                ag_touch t = ag_locate(p, in.ext, q, (u32)k);
+                if (!t.kind) continue;
+                int code = -1;
+                if (t.kind == 1 && t.slen) code = rd.code(p.left_read, p.len_nseg & 0xFFFFu, t.soff);
+                u32 sl = t.soff | (t.slen << 16);
+                bool bump = t.kind == 1;
+                ag_for_candidates(ct, q, t.mate, [&](const ag_nodem& c) { ag_node_touch(nl, pool, c, bump, code, p.left_read, sl, iv); });
+            }
+            if (err) throw AgHostError{"emul: overflow pool exhausted"};
+            pos_node[q] = (u32)nodeb.size();
+            u32 nloc = nl.n < AG_NODE_CAP ? nl.n : AG_NODE_CAP;
+            for (u32 i = 0; i < nloc; i++) nodeb.push_back(nl.loc[i]);
+            if (nl.n > AG_NODE_CAP) for (u32 o = nl.ovf_head; o != AG_NONE; o = ovf_next[o]) nodeb.push_back(ovf_node[o]);
+        }
+        for (u32 q = n_ref; q <= n_pos; q++) pos_node[q] = (u32)nodeb.size();
+        n_nodes = (u32)nodeb.size();
+        // k_finalize
+        node_m.resize(n_nodes); node_w.resize(n_nodes); node_sref.resize(2 * (size_t)n_nodes); node_pos.resize(n_nodes); trav.resize(n_nodes);
+        eovf_head.assign(n_nodes, AG_NONE); eovf_target.clear(); eovf_next.clear();
+        for (u32 q = 0; q < n_ref; q++)
+            for (u32 v = pos_node[q]; v < pos_node[q + 1]; v++) {
+                const ag_nodeb& b = nodeb[v];
+                ag_nodem m; m.cid = b.cid; m.coff = b.coff; m.cid0 = b.cid0; m.coff0 = b.coff0; m.moff = b.moff; node_m[v] = m;
+                ag_nodew w; w.succ0 = w.succ1 = AG_NONE; w.moff = b.moff;
+                u32 misc = (u32)(unsigned char)ag_consensus(b.cnt, in.ref[q]);
+                if (b.cid == AG_NONE && (int)b.cov < cov) misc |= AG_NW_FILTERED;
+                if (b.coff != AG_NONE) misc |= AG_NW_HASCONTIG;
+                w.misc = misc; node_w[v] = w;
+                node_sref[2 * (size_t)v] = b.sread; node_sref[2 * (size_t)v + 1] = b.soff_len; node_pos[v] = q;
+                trav[v] = (misc & AG_NW_FILTERED) ? 1 : 0;
+            }
+        // k_edges
+        for (u32 q = 0; q < n_ref; q++) {
+            u32 nb0 = pos_node[q], nn0 = pos_node[q + 1] - nb0;
+            if (!nn0) continue;
+            for (u32 idx : tiles[q / AG_TILE]) {
+                if (q - lo[idx] > span[idx]) continue;
+                ag_touch t = ag_locate(alnp[idx], in.ext, q, (u32)k);
+                if (t.kind != 1) continue;
+                u32 nb1 = pos_node[t.npos], nn1 = pos_node[t.npos + 1] - nb1;
+                ag_for_candidates(ct, q, t.mate, [&](const ag_nodem& c) {
+                    u32 ci = ag_first_compatible(node_m.data() + nb0, nn0, c, iv);
+                    if (ci == AG_NONE) return;
+                    const ag_nodem x = node_m[nb0 + ci];
+                    ag_for_candidates(ct, t.npos, t.nmate, [&](const ag_nodem& c2) {
+                        u32 ni = ag_first_compatible(node_m.data() + nb1, nn1, c2, iv);
+                        if (ni == AG_NONE) return;
+                        if (ag_edge_ok(x, node_m[nb1 + ni], iv)) add_edge(nb0 + ci, nb1 + ni);
+                    });
+                });
+            }
+        }
+    }
+
+    void add_edge(u32 v, u32 tgt) {
+        ag_nodew& w = node_w[v];
+        if (w.succ0 == tgt || w.succ1 == tgt) return;
+        if (w.succ0 == AG_NONE) { w.succ0 = tgt; return; }
+        if (w.succ1 == AG_NONE) { w.succ1 = tgt; return; }
+        if (w.misc & AG_NW_OVF) for (u32 o = eovf_head[v]; o != AG_NONE; o = eovf_next[o]) if (eovf_target[o] == tgt) return;
+        eovf_target.push_back(tgt); eovf_next.push_back((w.misc & AG_NW_OVF) ? eovf_head[v] : AG_NONE);
+        eovf_head[v] = (u32)eovf_target.size() - 1; w.misc |= AG_NW_OVF;
+    }
+
+    ag_walkctx ctx() {
+        ag_walkctx w; w.nw = node_w.data(); w.node_pos = node_pos.data(); w.pos_node = pos_node.data(); w.ovf_head = eovf_head.data();
+        w.ovf_target = eovf_target.data(); w.ovf_next = eovf_next.data(); w.cmt = cmt(); w.chain_pos = in.chain_pos; w.trav = trav.data(); w.walk_next = walk_next.data();
+        return w;
+    }
+    u32 find(u32 x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; }
+    void unite(u32 a, u32 b) { a = find(a); b = find(b); if (a == b) return; if (a > b) std::swap(a, b); parent[b] = a; }
+    bool live(u32 v) const { return !(node_w[v].misc & AG_NW_FILTERED); }
+    void fill_tail(ag_walk& r) { r.tail_sread = node_sref[2 * (size_t)r.last_node]; r.tail_soff_len = node_sref[2 * (size_t)r.last_node + 1]; }
+
+    void extend(std::vector<ag_walk>& walks) {
+        walks.clear();
+        walk_next.assign(n_nodes, AG_NONE); parent.resize(n_nodes);
+        std::iota(parent.begin(), parent.end(), 0u);
+        ag_cmtab ct = cmt();
+        for (u32 v = 0; v < n_nodes; v++) {  // k_uf_edges
+            if (!live(v)) continue;
+            const ag_nodew& w = node_w[v];
+            if (w.succ0 != AG_NONE && live(w.succ0)) unite(v, w.succ0);
+            if (w.succ1 != AG_NONE && live(w.succ1)) unite(v, w.succ1);
+            if (w.misc & AG_NW_OVF) for (u32 o = eovf_head[v]; o != AG_NONE; o = eovf_next[o]) if (live(eovf_target[o])) unite(v, eovf_target[o]);
+        }
+        for (u32 p = 0; p < in.n_ref; p++) {  // k_uf_chain
+            u32 c0 = ct.start[p];
+            if (ct.start[p + 1] - c0 != 1) continue;
+            ag_cm m = ct.cm[c0];
+            if (m.chain == m.term) continue;
+            u32 anchor = AG_NONE;
+            for (u32 x = pos_node[p]; x < pos_node[p + 1]; x++) if (live(x)) { if (anchor == AG_NONE) anchor = x; else unite(anchor, x); }
+            if (anchor == AG_NONE) continue;
+            u32 z = in.chain_pos[m.term];
+            for (u32 x = pos_node[z]; x < pos_node[z + 1]; x++) if (live(x)) unite(anchor, x);
+        }
+        std::vector<u32> cmin(n_nodes, AG_NONE), cmax(n_nodes, 0);
+        for (u32 v = 0; v < n_nodes; v++) if (live(v)) { u32 r = find(v); parent[v] = r; cmin[r] = std::min(cmin[r], v); cmax[r] = std::max(cmax[r], v); }
+        ag_walkctx w = ctx();
+        // components are replayed from the LAST root to the first to make sure nothing depends on cross-component order
+        for (u32 r = n_nodes; r-- > 0;) {
+            if (!live(r) || parent[r] != r) continue;
+            for (u32 v = cmin[r]; v <= cmax[r]; v++) {
+                if (trav[v] & 1) continue;
+                if (parent[v] != r) continue;
+                ag_walk x = ag_walk_from(w, v); fill_tail(x); walks.push_back(x);
+            }
+        }
+        std::sort(walks.begin(), walks.end(), [](const ag_walk& a, const ag_walk& b) { return a.start_node < b.start_node; });
+        // skip-rule trigger (AG:2194-2202)
+        u32 bso = 0, beo = 0; bool have = false, trigger = false;
+        for (const ag_walk& r : walks) {
+            u32 eoff = r.eoff;
+            if (((r.flags >> 1) & 3) != 1) eoff = eoff + (r.tail_soff_len >> 16) - 1;
+            if (have && bso <= r.soff && beo >= eoff) continue;
+            bso = r.soff; beo = eoff; have = true;
+            if (beo - bso > 100000u) { trigger = true; break; }
+        }
+        if (trigger || getenv("AG_EMUL_FORCE_SEQUENTIAL")) {
+            fallback_used = true;
+            walks.clear();
+            for (u32 v = 0; v < n_nodes; v++) { trav[v] = live(v) ? 0 : 1; walk_next[v] = AG_NONE; }
+            u32 sbo = AG_NONE, seo = AG_NONE, sei = AG_NONE;
+            for (u32 cp = 0; cp < in.n_ref;) {
+                for (u32 v = pos_node[cp]; v < pos_node[cp + 1]; v++) {
+                    if (trav[v] & 1) continue;
+                    ag_walk x = ag_walk_from(w, v); fill_tail(x); walks.push_back(x);
+                    u32 eoff = x.eoff;
+                    if (((x.flags >> 1) & 3) != 1) eoff = eoff + (x.tail_soff_len >> 16) - 1;
+                    bool contained = (sei == 0) && sbo <= x.soff && seo >= eoff;
+                    if (!contained) { sbo = x.soff; seo = eoff; sei = 0; }
+                }
+                if (seo - sbo > 100000u) { if (sei == 0 && cp + 1000 < seo) cp += 1000; else cp++; }
+                else cp++;
+            }
+        }
+    }
+
+    void materialize(const std::vector<ag_walk>& walks, const std::vector<u32>& sel, std::string& bases, std::vector<u64>& offs) {
+        offs.assign(sel.size() + 1, 0);
+        for (size_t i = 0; i < sel.size(); i++) offs[i + 1] = offs[i] + walks[sel[i]].len;
+        bases.assign(offs.back(), '\0');
+        ag_cmtab ct = cmt();
+        for (size_t i = 0; i < sel.size(); i++) {
+            size_t o = offs[i];
+            for (u32 v = walks[sel[i]].start_node; v != AG_NONE; v = walk_next[v]) {
+                bases[o++] = (char)(node_w[v].misc & 0xFF);
+                if (trav[v] & 2) { ag_cm m = ct.cm[ct.start[node_pos[v]]]; for (u32 e = m.chain + 1; e <= m.term; e++) bases[o++] = in.chain_base[e]; }
+            }
+            if (o != offs[i + 1]) throw AgHostError{"emul: walk length mismatch"};
+        }
+    }
+
+    void occupancy(std::vector<unsigned char>& bits) {
+        bits.assign(((size_t)in.n_pos + 7) / 8, 0);
+        for (u32 p = 0; p < in.n_pos; p++) {
+            bool occ = in.cm_start[p + 1] > in.cm_start[p];
+            if (p < in.n_ref && pos_node[p + 1] > pos_node[p]) occ = true;
+            if (occ) bits[p >> 3] |= (unsigned char)(1u << (p & 7));
+        }
+    }
+
+    void dump_nodes(AgNodeDump& d) {
+        d = AgNodeDump(); d.edge_start.push_back(0);
+        for (u32 v = 0; v < n_nodes; v++) {
+            const ag_nodeb& b = nodeb[v];
+            d.pos.push_back(node_pos[v]); d.item.push_back(v - pos_node[node_pos[v]]); d.cov.push_back(b.cov);
+            for (int j = 0; j < 5; j++) d.cnt.push_back(b.cnt[j]);
+            d.cid.push_back(b.cid); d.coff.push_back(b.coff); d.cid0.push_back(b.cid0); d.coff0.push_back(b.coff0); d.moff.push_back(b.moff);
+            d.sread.push_back(b.sread); d.soff_len.push_back(b.soff_len);
+            std::vector<u32> e;
+            if (node_w[v].succ0 != AG_NONE) e.push_back(node_w[v].succ0);
+            if (node_w[v].succ1 != AG_NONE) e.push_back(node_w[v].succ1);
+            if (node_w[v].misc & AG_NW_OVF) for (u32 o = eovf_head[v]; o != AG_NONE; o = eovf_next[o]) e.push_back(eovf_target[o]);
+            std::sort(e.begin(), e.end());
+            for (u32 x : e) d.edge_target.push_back(x);
+            d.edge_start.push_back((u32)d.edge_target.size());
+        }
+    }
+};
+
+int main(int argc, char** argv) {
+    std::string dir = ".";
+    int dump = 0, first = 0, last = -1;
+    for (int i = 1; i < argc; i++) {
+        std::string a = argv[i];
+        if (a == "--dir") dir = argv[++i];
+        else if (a == "--dump-nodes") dump = 1;
+        else if (a == "--first") first = atoi(argv[++i]);
+        else if (a == "--last") last = atoi(argv[++i]);
+        else { fprintf(stderr, "ag_emul: unknown option %s\n", a.c_str()); return 2; }
+    }
+    try {
+        if (chdir(dir.c_str()) != 0) throw AgHostError{"CANNOT OPEN FILE!"};
+        int k = 5, iv = 50, cov = 20, part = 1;
+        std::string contigFile, genomeFile;
+        {
+            FILE* f = fopen("tmp/_command.txt", "r");
+            if (!f) throw AgHostError{"CANNOT OPEN FILE!"};
+            char line[4096]; std::vector<std::string> tok;
+            while (fgets(line, sizeof line, f)) { std::string s(line); while (!s.empty() && (s.back() == '\n' || s.back() == '\r')) s.pop_back(); tok.push_back(s); }
+            fclose(f);
+            for (size_t i = 0; i + 1 < tok.size(); i++) {
+                if (tok[i] == "--kMer") k = atoi(tok[i + 1].c_str());
+                else if (tok[i] == "--insertVariation") iv = atoi(tok[i + 1].c_str());
+                else if (tok[i] == "--coverage") cov = atoi(tok[i + 1].c_str());
+                else if (tok[i] == "--part") part = atoi(tok[i + 1].c_str());
+                else if (tok[i] == "--contig") contigFile = tok[i + 1];
+                else if (tok[i] == "--genome") genomeFile = tok[i + 1];
+            }
+        }
+        std::vector<std::string> cids, gids;
+        ag_formalize_contigs(contigFile, "tmp", cids);
+        int units = ag_formalize_genome(genomeFile, "tmp", part, gids);
+        if (last < 0 || last >= units) last = units - 1;
+        AgReads reads;
+        ag_parse_reads("tmp/_reads.fa", reads);
+        AgEmul eng; eng.k = k; eng.iv = iv; eng.cov = cov; eng.set_reads(reads);
+        for (int unit = first; unit <= last; unit++) {
+            AgUnitResult r;
+            ag_run_unit_files(eng, reads, "tmp", unit, r);
+            fprintf(stderr, "emul unit %d: aln=%lu nodes=%u walks=%lu emitted=%lu%s\n", unit, (unsigned long)r.n_aln, eng.n_nodes, (unsigned long)r.n_walks, (unsigned long)r.n_emitted,
+                    eng.fallback_used ? " (sequential walk)" : "");
+            if (dump) { AgNodeDump d; eng.dump_nodes(d); std::string text; ag_format_node_dump(d, reads, text); ag_write_file("tmp/_nodes." + std::to_string(unit) + ".txt", text); }
+        }
+    } catch (const AgHostError& e) { printf("%s\n", e.msg.c_str()); return 255; }
+    catch (const AgError& e) { printf("%s\n", e.msg.c_str()); return 255; }
+    return 0;
+}
