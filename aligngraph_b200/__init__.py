@@ -1,0 +1,184 @@
+"""aligngraph_b200 — B200-native drop-in for AlignGraph's per-chromosome graph-build + contig-extension path.
+
+Python is only the test / benchmark harness: this module is a thin ctypes binding of the C ABI declared in
+``include/aligngraph_b200.h`` (the product is the shared library + the ``AlignGraph`` CLI).  There is no CPU fallback: if the
+CUDA library is missing or no GPU is present, construction of a :class:`Context` raises.
+
+Method names mirror the reference's loop body (AlignGraph.cpp:4768-4776): ``run_unit`` = loadGenome + loadContigAlignment +
+loadReadAlignment + extendContigs + scaffoldContigs for one unit, on the reference's own tmp/ files.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libaligngraph_b200.so")
+HEADER_PATH = os.path.join(_HERE, "..", "include", "aligngraph_b200.h")
+
+
+class AlignGraphError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    _fields_ = [("k", C.c_int), ("insert_variation", C.c_int), ("coverage", C.c_int), ("device", C.c_int)]
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("ms_h2d", "ms_prep", "ms_sort", "ms_nodes", "ms_finalize", "ms_edges", "ms_components",
+                                         "ms_walk", "ms_materialize", "ms_d2h")] + \
+               [(n, C.c_double) for n in ("s_parse", "s_device_section", "s_post")] + \
+               [(n, C.c_uint64) for n in ("n_aln", "n_nodes", "n_walks", "n_emitted", "n_keys", "n_tiles", "kernel_launches",
+                                          "h2d_bytes", "d2h_bytes")] + \
+               [("walk_fallback", C.c_int)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class UnitView(C.Structure):
+    _fields_ = [("ref", C.c_void_p), ("n_ref", C.c_uint32), ("n_tail", C.c_uint32), ("cm_start", C.c_void_p), ("cm", C.c_void_p),
+                ("n_cm", C.c_uint32), ("chain_pos", C.c_void_p), ("chain_base", C.c_void_p), ("aln", C.c_void_p), ("n_aln", C.c_uint64),
+                ("ext", C.c_void_p), ("n_ext", C.c_uint64)]
+
+
+_lib = None
+
+
+def load_library(path=None):
+    """Load the CUDA shared library.  Raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise AlignGraphError(f"{path} not found: build it with `python -m aligngraph_b200.build` (there is no CPU fallback)")
+    lib = C.CDLL(path)
+    vp, cp, i32, u32, u64 = C.c_void_p, C.c_char_p, C.c_int, C.c_uint32, C.c_uint64
+    sig = {
+        "ag_create": (i32, [C.POINTER(Params), C.POINTER(vp)]),
+        "ag_destroy": (None, [vp]),
+        "ag_last_error": (cp, [vp]),
+        "ag_create_error": (cp, []),
+        "ag_set_reads": (i32, [vp, vp, vp, vp, u64, u32, u32]),
+        "ag_set_reads_device": (i32, [vp, vp, vp, vp, u64, u32, u32]),
+        "ag_set_read_exceptions": (i32, [vp, vp, vp, u64]),
+        "ag_load_reads_fasta": (i32, [vp, cp]),
+        "ag_get_reads": (i32, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(u64), C.POINTER(u32), C.POINTER(u32)]),
+        "ag_begin_unit": (i32, [vp, i32, vp, u32]),
+        "ag_set_contimers": (i32, [vp, vp, vp, u32, vp, vp, vp, u32]),
+        "ag_add_alignments": (i32, [vp, vp, u64, vp, u64]),
+        "ag_build": (i32, [vp]),
+        "ag_extend": (i32, [vp]),
+        "ag_get_text": (i32, [vp, i32, C.POINTER(vp), C.POINTER(u64)]),
+        "ag_prepare_unit_files": (i32, [vp, cp, i32]),
+        "ag_write_unit_files": (i32, [vp, cp, i32]),
+        "ag_run_unit_files": (i32, [vp, cp, i32]),
+        "ag_get_unit": (i32, [vp, C.POINTER(UnitView)]),
+        "ag_get_stats": (i32, [vp, C.POINTER(Stats)]),
+        "ag_reset_stats": (i32, [vp]),
+        "ag_dump_nodes_text": (i32, [vp, C.POINTER(vp), C.POINTER(u64)]),
+        "ag_cuda_stream": (vp, [vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    lib._ag_signatures = sig
+    if path == LIB_PATH:
+        _lib = lib
+    return lib
+
+
+class Context:
+    """One GPU context (``ag_ctx``).  ``k`` / ``insert_variation`` / ``coverage`` are --kMer / --insertVariation / --coverage."""
+
+    def __init__(self, k=5, insert_variation=50, coverage=20, device=0):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        p = Params(k, insert_variation, coverage, device)
+        rc = self._lib.ag_create(C.byref(p), C.byref(self._h))
+        if rc != 0:
+            raise AlignGraphError("ag_create: " + self._lib.ag_create_error().decode())
+        self._keep = []
+
+    def close(self):
+        if self._h:
+            self._lib.ag_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise AlignGraphError(f"{what}: {self._lib.ag_last_error(self._h).decode()}")
+
+    # ---- reads ---------------------------------------------------------------------------------------------------------
+    def load_reads_fasta(self, path):
+        self._ck(self._lib.ag_load_reads_fasta(self._h, os.fsencode(path)), "ag_load_reads_fasta")
+
+    def get_reads(self):
+        """(bases_ptr, nmask_ptr, len_ptr, n_pairs, stride2, stridem) of the packed host copy."""
+        b, m, l = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        n, s2, sm = C.c_uint64(), C.c_uint32(), C.c_uint32()
+        self._ck(self._lib.ag_get_reads(self._h, C.byref(b), C.byref(m), C.byref(l), C.byref(n), C.byref(s2), C.byref(sm)), "ag_get_reads")
+        return b.value, m.value, l.value, n.value, s2.value, sm.value
+
+    def set_reads(self, bases_ptr, nmask_ptr, len_ptr, n_pairs, stride2, stridem, on_device=False):
+        fn = self._lib.ag_set_reads_device if on_device else self._lib.ag_set_reads
+        self._ck(fn(self._h, bases_ptr, nmask_ptr, len_ptr, n_pairs, stride2, stridem), "ag_set_reads")
+
+    # ---- file level (the reference's loop body) ---------------------------------------------------------------------------
+    def run_unit(self, tmp_dir, unit):
+        self._ck(self._lib.ag_run_unit_files(self._h, os.fsencode(tmp_dir), unit), "ag_run_unit_files")
+
+    def prepare_unit(self, tmp_dir, unit):
+        self._ck(self._lib.ag_prepare_unit_files(self._h, os.fsencode(tmp_dir), unit), "ag_prepare_unit_files")
+
+    def write_unit(self, tmp_dir, unit):
+        self._ck(self._lib.ag_write_unit_files(self._h, os.fsencode(tmp_dir), unit), "ag_write_unit_files")
+
+    # ---- array level ----------------------------------------------------------------------------------------------------------
+    def get_unit(self):
+        v = UnitView()
+        self._ck(self._lib.ag_get_unit(self._h, C.byref(v)), "ag_get_unit")
+        return v
+
+    def begin_unit(self, unit, ref_ptr, n_ref):
+        self._ck(self._lib.ag_begin_unit(self._h, unit, ref_ptr, n_ref), "ag_begin_unit")
+
+    def set_contimers(self, cm_start, cm, n_cm, chain_pos, chain_base, tail_ptr, n_tail):
+        self._ck(self._lib.ag_set_contimers(self._h, cm_start, cm, n_cm, chain_pos, chain_base, tail_ptr, n_tail), "ag_set_contimers")
+
+    def add_alignments(self, aln, n, ext, n_ext):
+        self._ck(self._lib.ag_add_alignments(self._h, aln, n, ext, n_ext), "ag_add_alignments")
+
+    def build(self):
+        self._ck(self._lib.ag_build(self._h), "ag_build")
+
+    def extend(self):
+        self._ck(self._lib.ag_extend(self._h), "ag_extend")
+
+    def text(self, which):
+        p, n = C.c_void_p(), C.c_uint64()
+        self._ck(self._lib.ag_get_text(self._h, which, C.byref(p), C.byref(n)), "ag_get_text")
+        return C.string_at(p.value, n.value) if n.value else b""
+
+    # ---- introspection ----------------------------------------------------------------------------------------------------------
+    def stats(self):
+        s = Stats()
+        self._ck(self._lib.ag_get_stats(self._h, C.byref(s)), "ag_get_stats")
+        return s.as_dict()
+
+    def reset_stats(self):
+        self._ck(self._lib.ag_reset_stats(self._h), "ag_reset_stats")
+
+    def dump_nodes_text(self):
+        p, n = C.c_void_p(), C.c_uint64()
+        self._ck(self._lib.ag_dump_nodes_text(self._h, C.byref(p), C.byref(n)), "ag_dump_nodes_text")
+        return C.string_at(p.value, n.value) if n.value else b""
+
+    def cuda_stream(self):
+        return self._lib.ag_cuda_stream(self._h)

@@ -1,0 +1,219 @@
+// C ABI of the B200 AlignGraph hot path (include/aligngraph_b200.h).  Thin: owns the context, stages host arrays, turns
+// exceptions into error codes.  All graph work happens in AgDevice (ag_device.cu).
+#include "../../include/aligngraph_b200.h"
+#include "ag_pipeline.h"
+#include <cstring>
+#include <new>
+
+static_assert(sizeof(ag_aln_c) == sizeof(ag_aln) && sizeof(ag_seg_c) == sizeof(ag_seg) && sizeof(ag_cm_c) == sizeof(ag_cm), "ABI structs mirror the internal layouts");
+
+struct ag_ctx {
+    AgDevice* dev = nullptr;
+    ag_params params{};
+    AgReads reads;
+    bool have_reads = false;
+    AgUnit unit;
+    int unit_id = -1;
+    AgUnitResult res;
+    std::string err, dump;
+    double s_parse = 0, s_device = 0, s_post = 0;
+    u64 n_aln = 0, n_walks = 0, n_emitted = 0;
+};
+
+static std::string g_create_error;
+
+template <class F> static int guard(ag_ctx* ctx, F f) {
+    try { f(); return 0; }
+    catch (const AgHostError& e) { if (ctx) ctx->err = e.msg; return 1; }
+    catch (const AgError& e) { if (ctx) ctx->err = e.msg; return 2; }
+    catch (const std::bad_alloc&) { if (ctx) ctx->err = "out of host memory"; return 3; }
+    catch (...) { if (ctx) ctx->err = "unknown error"; return 4; }
+}
+
+extern "C" {
+
+int ag_create(const ag_params* params, ag_ctx** out) {
+    if (!params || !out) { g_create_error = "null argument"; return 1; }
+    ag_ctx* c = new (std::nothrow) ag_ctx;
+    if (!c) { g_create_error = "out of host memory"; return 3; }
+    c->params = *params;
+    try { c->dev = new AgDevice(params->device); c->dev->set_params(params->k, params->insert_variation, params->coverage); }
+    catch (const AgError& e) { g_create_error = e.msg; delete c; return 2; }
+    *out = c;
+    return 0;
+}
+void ag_destroy(ag_ctx* ctx) { if (!ctx) return; delete ctx->dev; delete ctx; }
+const char* ag_last_error(const ag_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+const char* ag_create_error(void) { return g_create_error.c_str(); }
+
+int ag_set_reads(ag_ctx* ctx, const uint32_t* bases2, const uint32_t* nmask, const uint16_t* pair_len, uint64_t n_pairs, uint32_t stride2, uint32_t stridem) {
+    return guard(ctx, [&] {
+        AgReads& r = ctx->reads;
+        r.n_pairs = n_pairs; r.stride2 = stride2; r.stridem = stridem;
+        r.bases.assign(bases2, bases2 + 2 * n_pairs * stride2); r.nmask.assign(nmask, nmask + 2 * n_pairs * stridem); r.len.assign(pair_len, pair_len + n_pairs);
+        r.exc.clear();
+        ctx->dev->set_reads(bases2, nmask, pair_len, n_pairs, stride2, stridem, false);
+        ctx->have_reads = true;
+    });
+}
+int ag_set_reads_device(ag_ctx* ctx, const uint32_t* d_bases2, const uint32_t* d_nmask, const uint16_t* d_pair_len, uint64_t n_pairs, uint32_t stride2, uint32_t stridem) {
+    return guard(ctx, [&] {
+        AgReads& r = ctx->reads;
+        r.n_pairs = n_pairs; r.stride2 = stride2; r.stridem = stridem;
+        r.bases.resize(2 * n_pairs * stride2); r.nmask.resize(2 * n_pairs * stridem); r.len.resize(n_pairs); r.exc.clear();
+        ctx->dev->set_reads(d_bases2, d_nmask, d_pair_len, n_pairs, stride2, stridem, true);
+        ctx->dev->copy_reads_to_host(r.bases.data(), r.nmask.data(), r.len.data());
+        ctx->have_reads = true;
+    });
+}
+int ag_set_read_exceptions(ag_ctx* ctx, const uint64_t* keys, const char* chars, uint64_t n) {
+    return guard(ctx, [&] { ctx->reads.exc.clear(); for (uint64_t i = 0; i < n; i++) ctx->reads.exc.push_back({keys[i], chars[i]}); });
+}
+int ag_load_reads_fasta(ag_ctx* ctx, const char* path) {
+    return guard(ctx, [&] {
+        auto t0 = std::chrono::steady_clock::now();
+        ag_parse_reads(path, ctx->reads);
+        ctx->s_parse += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        const AgReads& r = ctx->reads;
+        ctx->dev->set_reads(r.bases.data(), r.nmask.data(), r.len.data(), r.n_pairs, r.stride2, r.stridem, false);
+        ctx->have_reads = true;
+    });
+}
+int ag_get_reads(ag_ctx* ctx, const uint32_t** bases2, const uint32_t** nmask, const uint16_t** pair_len, uint64_t* n_pairs, uint32_t* stride2, uint32_t* stridem) {
+    return guard(ctx, [&] {
+        const AgReads& r = ctx->reads;
+        *bases2 = r.bases.data(); *nmask = r.nmask.data(); *pair_len = r.len.data(); *n_pairs = r.n_pairs; *stride2 = r.stride2; *stridem = r.stridem;
+    });
+}
+
+int ag_begin_unit(ag_ctx* ctx, int unit_id, const char* ref_bases, uint32_t n_ref) {
+    return guard(ctx, [&] {
+        ctx->unit = AgUnit(); ctx->res = AgUnitResult(); ctx->unit_id = unit_id;
+        ctx->unit.ref.assign(ref_bases, n_ref); ctx->unit.n_ref = n_ref;
+        ctx->unit.cm_start.assign((size_t)n_ref + 1, 0);
+    });
+}
+int ag_set_contimers(ag_ctx* ctx, const uint32_t* cm_start, const ag_cm_c* cm, uint32_t n_cm, const uint32_t* chain_pos, const char* chain_base,
+                     const char* tail_bases, uint32_t n_tail) {
+    return guard(ctx, [&] {
+        AgUnit& u = ctx->unit;
+        u.ref.resize(u.n_ref);
+        if (n_tail) u.ref.append(tail_bases, n_tail);
+        u.cm_start.assign(cm_start, cm_start + u.ref.size() + 1);
+        u.cm.assign((const ag_cm*)cm, (const ag_cm*)cm + n_cm);
+        u.chain_pos.assign(chain_pos, chain_pos + n_cm); u.chain_base.assign(chain_base, n_cm);
+    });
+}
+int ag_add_alignments(ag_ctx* ctx, const ag_aln_c* aln, uint64_t n, const ag_seg_c* ext, uint64_t n_ext) {
+    return guard(ctx, [&] {
+        AgUnit& u = ctx->unit;
+        u32 base = (u32)u.ext.size();
+        size_t a0 = u.aln.size();
+        u.aln.insert(u.aln.end(), (const ag_aln*)aln, (const ag_aln*)aln + n);
+        if (base) for (size_t i = a0; i < u.aln.size(); i++) u.aln[i].ext_idx += base;
+        u.ext.insert(u.ext.end(), (const ag_seg*)ext, (const ag_seg*)ext + n_ext);
+    });
+}
+
+int ag_build(ag_ctx* ctx) {
+    return guard(ctx, [&] {
+        if (!ctx->have_reads) throw AgHostError{"reads not set"};
+        auto t0 = std::chrono::steady_clock::now();
+        ctx->dev->load_unit(ag_unit_input(ctx->unit));
+        ctx->dev->build();
+        ctx->s_device += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        ctx->n_aln += ctx->unit.aln.size();
+    });
+}
+
+// extension half of ag_process_unit (kept separate so that ag_build can be timed / inspected on its own)
+int ag_extend(ag_ctx* ctx) {
+    return guard(ctx, [&] {
+        auto t0 = std::chrono::steady_clock::now();
+        AgDevice& eng = *ctx->dev;
+        std::vector<ag_walk> walks;
+        eng.extend(walks);
+        std::vector<u32> sel;
+        ag_select_emitted(walks, sel);
+        std::string bases; std::vector<u64> offs;
+        eng.materialize(walks, sel, bases, offs);
+        std::vector<unsigned char> occ;
+        eng.occupancy(occ);
+        auto t1 = std::chrono::steady_clock::now();
+        std::vector<AgContig> contigs;
+        ag_make_contigs(walks, sel, bases, offs, ctx->reads, contigs, ctx->res.pre_text);
+        ag_dedup_join(contigs);
+        ag_scaffold(contigs, ctx->unit.ref, occ, ctx->res.ext_text);
+        auto t2 = std::chrono::steady_clock::now();
+        ctx->s_device += std::chrono::duration<double>(t1 - t0).count();
+        ctx->s_post += std::chrono::duration<double>(t2 - t1).count();
+        ctx->n_walks += walks.size(); ctx->n_emitted += sel.size();
+    });
+}
+
+int ag_get_text(ag_ctx* ctx, int which, const char** text, uint64_t* len) {
+    return guard(ctx, [&] {
+        const std::string& s = which == 0 ? ctx->res.initial_text : which == 1 ? ctx->res.pre_text : ctx->res.ext_text;
+        *text = s.data(); *len = s.size();
+    });
+}
+
+int ag_prepare_unit_files(ag_ctx* ctx, const char* tmp_dir, int unit_id) {
+    return guard(ctx, [&] {
+        if (!ctx->have_reads) throw AgHostError{"reads not set"};
+        auto t0 = std::chrono::steady_clock::now();
+        ctx->unit = AgUnit(); ctx->res = AgUnitResult(); ctx->unit_id = unit_id;
+        ag_prepare_unit(ctx->reads, tmp_dir, unit_id, ctx->unit, ctx->res.initial_text);
+        ctx->s_parse += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    });
+}
+int ag_write_unit_files(ag_ctx* ctx, const char* tmp_dir, int unit_id) {
+    return guard(ctx, [&] {
+        std::string n = std::to_string(unit_id), tmp = tmp_dir;
+        ag_write_file(tmp + "/_initial_contigs." + n + ".fa", ctx->res.initial_text);
+        ag_write_file(tmp + "/_pre_extended_contigs." + n + ".fa", ctx->res.pre_text);
+        ag_write_file(tmp + "/_extended_contigs." + n + ".fa", ctx->res.ext_text);
+    });
+}
+int ag_run_unit_files(ag_ctx* ctx, const char* tmp_dir, int unit_id) {
+    int rc = ag_prepare_unit_files(ctx, tmp_dir, unit_id);
+    if (!rc) rc = ag_build(ctx);
+    if (!rc) rc = ag_extend(ctx);
+    if (!rc) rc = ag_write_unit_files(ctx, tmp_dir, unit_id);
+    return rc;
+}
+
+int ag_get_unit(ag_ctx* ctx, ag_unit_view* out) {
+    return guard(ctx, [&] {
+        const AgUnit& u = ctx->unit;
+        out->ref = u.ref.data(); out->n_ref = u.n_ref; out->n_tail = (uint32_t)u.ref.size() - u.n_ref;
+        out->cm_start = u.cm_start.data(); out->cm = (const ag_cm_c*)u.cm.data(); out->n_cm = (uint32_t)u.cm.size();
+        out->chain_pos = u.chain_pos.data(); out->chain_base = u.chain_base.data();
+        out->aln = (const ag_aln_c*)u.aln.data(); out->n_aln = u.aln.size(); out->ext = (const ag_seg_c*)u.ext.data(); out->n_ext = u.ext.size();
+    });
+}
+
+int ag_get_stats(ag_ctx* ctx, ag_stats* o) {
+    return guard(ctx, [&] {
+        const AgTimings& t = ctx->dev->timings();
+        memset(o, 0, sizeof *o);
+        o->ms_h2d = t.h2d; o->ms_prep = t.prep; o->ms_sort = t.sort; o->ms_nodes = t.nodes; o->ms_finalize = t.finalize; o->ms_edges = t.edges;
+        o->ms_components = t.components; o->ms_walk = t.walk; o->ms_materialize = t.materialize; o->ms_d2h = t.d2h;
+        o->s_parse = ctx->s_parse; o->s_device_section = ctx->s_device; o->s_post = ctx->s_post;
+        o->n_aln = ctx->n_aln; o->n_nodes = t.n_nodes; o->n_walks = ctx->n_walks; o->n_emitted = ctx->n_emitted; o->n_keys = t.n_keys; o->n_tiles = t.n_tiles;
+        o->kernel_launches = ctx->dev->kernel_launches(); o->h2d_bytes = t.h2d_bytes; o->d2h_bytes = t.d2h_bytes; o->walk_fallback = t.walk_fallback;
+    });
+}
+int ag_reset_stats(ag_ctx* ctx) {
+    return guard(ctx, [&] { ctx->dev->reset_timings(); ctx->s_parse = ctx->s_device = ctx->s_post = 0; ctx->n_aln = ctx->n_walks = ctx->n_emitted = 0; });
+}
+int ag_dump_nodes_text(ag_ctx* ctx, const char** text, uint64_t* len) {
+    return guard(ctx, [&] {
+        AgNodeDump d; ctx->dev->dump_nodes(d);
+        ag_format_node_dump(d, ctx->reads, ctx->dump);
+        *text = ctx->dump.data(); *len = ctx->dump.size();
+    });
+}
+void* ag_cuda_stream(ag_ctx* ctx) { return ctx ? ctx->dev->stream() : nullptr; }
+
+}  // extern "C"

@@ -544,8 +544,18 @@ void AgDevice::set_reads(const u32* bases, const u32* nmask, const uint16_t* len
         CK(cudaMemcpyAsync(m.r_len.p, len, n_pairs * sizeof(uint16_t), cudaMemcpyHostToDevice, m.st));
         m.reads.bases = m.r_bases.p; m.reads.nmask = m.r_nmask.p; m.reads.len = m.r_len.p; m.reads_owned = true;
         t_.h2d += tm.stop();
+        t_.h2d_bytes += 2 * n_pairs * (stride2 + stridem) * sizeof(u32) + n_pairs * sizeof(uint16_t);
     }
     m.reads.stride2 = stride2; m.reads.stridem = stridem;
+}
+
+void AgDevice::copy_reads_to_host(u32* bases, u32* nmask, uint16_t* len) {
+    CK(cudaSetDevice(dev_));
+    Impl& m = *m_;
+    CK(cudaMemcpyAsync(bases, m.reads.bases, 2 * m.n_pairs * m.reads.stride2 * sizeof(u32), cudaMemcpyDeviceToHost, m.st));
+    CK(cudaMemcpyAsync(nmask, m.reads.nmask, 2 * m.n_pairs * m.reads.stridem * sizeof(u32), cudaMemcpyDeviceToHost, m.st));
+    CK(cudaMemcpyAsync(len, m.reads.len, m.n_pairs * sizeof(uint16_t), cudaMemcpyDeviceToHost, m.st));
+    CK(cudaStreamSynchronize(m.st));
 }
 
 void AgDevice::load_unit(const AgUnitInput& in) {
@@ -566,6 +576,7 @@ void AgDevice::load_unit(const AgUnitInput& in) {
     if (in.n_aln) CK(cudaMemcpyAsync(m.aln.p, in.aln, in.n_aln * sizeof(ag_aln), cudaMemcpyHostToDevice, m.st));
     if (in.n_ext) CK(cudaMemcpyAsync(m.ext.p, in.ext, in.n_ext * sizeof(ag_seg), cudaMemcpyHostToDevice, m.st));
     t_.h2d += tm.stop();
+    t_.h2d_bytes += in.n_pos + ((size_t)in.n_pos + 1) * 4 + (size_t)in.n_cm * (sizeof(ag_cm) + 5) + in.n_aln * sizeof(ag_aln) + in.n_ext * sizeof(ag_seg);
 }
 
 void AgDevice::build() {
@@ -732,6 +743,7 @@ void AgDevice::extend(std::vector<ag_walk>& walks) {
         if (nw) CK(cudaMemcpyAsync(walks.data(), m.walks.p, (size_t)nw * sizeof(ag_walk), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         t_.d2h += tm.stop();
+        t_.d2h_bytes += (size_t)nw * sizeof(ag_walk);
         std::sort(walks.begin(), walks.end(), [](const ag_walk& a, const ag_walk& b) { return a.start_node < b.start_node; });
     };
     fetch();
@@ -767,6 +779,7 @@ void AgDevice::materialize(const std::vector<ag_walk>& walks, const std::vector<
     CK(cudaMemcpyAsync(&bases[0], m.out_bases.p, offs.back(), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     t_.materialize += tm.stop();
+    t_.h2d_bytes += sel.size() * 12; t_.d2h_bytes += offs.back();
 }
 
 void AgDevice::occupancy(std::vector<unsigned char>& bits) {
@@ -779,6 +792,7 @@ void AgDevice::occupancy(std::vector<unsigned char>& bits) {
     k_occupancy<<<((u32)nb + 255) / 256, 256, 0, st>>>(m.view, m.occ.p); launches_++;
     CK(cudaMemcpyAsync(bits.data(), m.occ.p, nb, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    t_.d2h_bytes += nb;
 }
 
 void AgDevice::dump_nodes(AgNodeDump& dd) {

@@ -25,6 +25,7 @@ struct AgNodeDump {  // node table in (position, item) order, for tests
 struct AgTimings {  // milliseconds, CUDA events on the context's stream
     float h2d = 0, prep = 0, sort = 0, nodes = 0, finalize = 0, edges = 0, components = 0, walk = 0, materialize = 0, d2h = 0;
     u64 n_nodes = 0, n_edges_ovf = 0, n_walks = 0, n_keys = 0, n_tiles = 0, n_components = 0;
+    u64 h2d_bytes = 0, d2h_bytes = 0;
     int walk_fallback = 0;
 };
 
@@ -35,6 +36,7 @@ public:
     // reads: 2-bit packed + non-ACGT bit plane, fixed stride per read; len per pair.  `on_device` = pointers are device pointers
     // (the NCCL broadcast target); otherwise they are copied H2D.
     void set_reads(const u32* bases, const u32* nmask, const uint16_t* len, u64 n_pairs, u32 stride2, u32 stridem, bool on_device);
+    void copy_reads_to_host(u32* bases, u32* nmask, uint16_t* len);
     void set_params(int k, int iv, int coverage) { k_ = k; iv_ = iv; cov_ = coverage; }
     // upload one unit's inputs (H2D, timed)
     void load_unit(const AgUnitInput& in);

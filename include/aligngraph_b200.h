@@ -1,0 +1,117 @@
+/* aligngraph_b200 — C ABI of the B200-native AlignGraph hot path.
+ *
+ * The reference (baoe/AlignGraph, AlignGraph/AlignGraph.cpp, cited "AG:line") has no plugin or FFI interface; its boundary for
+ * this path is the five calls of the per-chromosome loop body (AG:4768-4776) and the tmp/ files they read and write:
+ *
+ *     loadGenome(genome, N)                       AG:287      tmp/_genome.N.fa
+ *     loadContigAlignment(genome, N)              AG:1219     tmp/_contigs.fa, tmp/_contigs_genome.N.psl  -> tmp/_initial_contigs.N.fa
+ *     loadReadAlignment(genome, k, iv, N, mrl)    AG:1872     tmp/_reads.fa, tmp/_reads_genome.N.bowtie
+ *     extendContigs(genome, coverage, k, N)       AG:2382     -> tmp/_pre_extended_contigs.N.fa
+ *     scaffoldContigs(genome, N)                  AG:2396     -> tmp/_extended_contigs.N.fa
+ *
+ * This library replaces them at two levels:
+ *   (1) file level  — ag_run_unit_files() is a drop-in for the five calls together (same files in, same files out);
+ *   (2) array level — the same work on packed host buffers (what a host that has already parsed its text would hand over):
+ *       ag_set_reads / ag_begin_unit / ag_set_contimers / ag_add_alignments / ag_build / ag_extend / ag_get_text.
+ * All graph construction, pruning and walking runs in CUDA kernels on one B200 per context; there is NO CPU fallback —
+ * ag_create() fails when no CUDA device is present.
+ *
+ * Conventions: plain pointers and sizes, no C++ types; the caller owns every input buffer (they may be freed after the call
+ * returns); the context owns device memory and the returned text buffers (valid until the next call on the context).  Every
+ * function returns 0 on success; otherwise ag_last_error() holds the message the reference would print before exit(-1)
+ * (e.g. "CANNOT OPEN FILE!", "BOWTIE ALIGNMENT ERROR", "BROKEN BOWTIE FILE").  One context per GPU; calls on different
+ * contexts are thread-safe, calls on one context are not (the reference's loop is single-threaded and not re-entrant either).
+ */
+#ifndef ALIGNGRAPH_B200_H
+#define ALIGNGRAPH_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ag_ctx ag_ctx;
+
+typedef struct ag_params {
+    int k;                /* --kMer            (AG:4701 default 5)  */
+    int insert_variation; /* --insertVariation (AG:4701 default 50) */
+    int coverage;         /* --coverage        (AG:4701 default 20) */
+    int device;           /* CUDA device ordinal */
+} ag_params;
+
+/* One M segment of a CIGAR: read offsets [src, src+len) lie on unit positions [dst, dst+len)   (Segment, AG:44-49) */
+typedef struct ag_seg_c { uint32_t src, dst, len; } ag_seg_c;
+
+/* One read-pair alignment that passed the load-time filters (AG:1261, AG:1650-1655), 32 bytes.
+ * flags: bit0 mate 1 reverse (FLAG&0x10), bit1 mate 2 reverse, bits 8-15 number of M segments of mate 1, bits 16-23 of mate 2.
+ * dstX / slX: first segment of mate X (dst ; src | len<<16).  A mate with more than one segment has ALL its segments in the ext
+ * array: mate 1's at ext[ext_idx], mate 2's right after (or at ext_idx when mate 1 has a single segment). */
+typedef struct ag_aln_c { uint32_t pair, flags, dst1, sl1, dst2, sl2, ext_idx, pad; } ag_aln_c;
+
+/* contiMer (ContiMer, AG:51-62) in position-CSR order; `chain` indexes the chain-major arrays (the next contiMer of the same
+ * contig thread is chain+1), `term` is the chain index of the thread's terminal contiMer (nextID == -1). */
+typedef struct ag_cm_c { uint32_t cid, coff, chain, term; } ag_cm_c;
+
+typedef struct ag_stats {
+    /* device milliseconds (CUDA events on the context's stream), accumulated since ag_reset_stats */
+    float ms_h2d, ms_prep, ms_sort, ms_nodes, ms_finalize, ms_edges, ms_components, ms_walk, ms_materialize, ms_d2h;
+    /* host wall seconds */
+    double s_parse, s_device_section, s_post;
+    uint64_t n_aln, n_nodes, n_walks, n_emitted, n_keys, n_tiles, kernel_launches, h2d_bytes, d2h_bytes;
+    int walk_fallback; /* 1 when the exact sequential replay (AG:2194-2202 skip rule) had to be used */
+} ag_stats;
+
+int ag_create(const ag_params* params, ag_ctx** out);
+void ag_destroy(ag_ctx* ctx);
+const char* ag_last_error(const ag_ctx* ctx);
+/* message of the last failed ag_create (no context exists then) */
+const char* ag_create_error(void);
+
+/* ---- reads: once per run, shared by all units (the reference re-reads tmp/_reads.fa for every unit, AG:1880) ------------
+ * bases2: 2 bits/base (A0 C1 G2 T3), 16 bases per word, `stride2` words per read; nmask: 1 bit/base marking characters other
+ * than upper-case ACGT (counted as N, AG:1349), `stridem` words per read; reads 2p and 2p+1 are the mates of pair p and have
+ * pair_len[p] bases each (AG:3454). */
+int ag_set_reads(ag_ctx* ctx, const uint32_t* bases2, const uint32_t* nmask, const uint16_t* pair_len, uint64_t n_pairs, uint32_t stride2, uint32_t stridem);
+/* same layout, buffers already in device memory of this context's GPU (target of the NCCL broadcast) */
+int ag_set_reads_device(ag_ctx* ctx, const uint32_t* d_bases2, const uint32_t* d_nmask, const uint16_t* d_pair_len, uint64_t n_pairs, uint32_t stride2, uint32_t stridem);
+/* original characters of the masked bases (only needed to print them in contig tails, AG:2167): keys = read*65536 + offset, sorted */
+int ag_set_read_exceptions(ag_ctx* ctx, const uint64_t* keys, const char* chars, uint64_t n);
+/* parse tmp/_reads.fa (AG:361-404) and upload */
+int ag_load_reads_fasta(ag_ctx* ctx, const char* path);
+/* packed host copy held by the context (after ag_load_reads_fasta) — lets a launcher broadcast it */
+int ag_get_reads(ag_ctx* ctx, const uint32_t** bases2, const uint32_t** nmask, const uint16_t** pair_len, uint64_t* n_pairs, uint32_t* stride2, uint32_t* stridem);
+
+/* ---- array level -------------------------------------------------------------------------------------------------------------- */
+int ag_begin_unit(ag_ctx* ctx, int unit_id, const char* ref_bases, uint32_t n_ref);                       /* loadGenome, AG:287 */
+int ag_set_contimers(ag_ctx* ctx, const uint32_t* cm_start /* n_ref+n_tail+1 */, const ag_cm_c* cm, uint32_t n_cm,
+                     const uint32_t* chain_pos, const char* chain_base, const char* tail_bases, uint32_t n_tail); /* result of loadContigAlignment, AG:1219 */
+int ag_add_alignments(ag_ctx* ctx, const ag_aln_c* aln, uint64_t n, const ag_seg_c* ext, uint64_t n_ext); /* parsing half of loadReadAlignment, AG:1872 */
+int ag_build(ag_ctx* ctx);   /* graph half of loadReadAlignment: updateGenomeWithRead / updateKMer, AG:1635-1870, AG:1353-1624 */
+int ag_extend(ag_ctx* ctx);  /* extendContigs + scaffoldContigs, AG:2382, AG:2396 */
+/* which: 0 = tmp/_initial_contigs.N.fa (file level only), 1 = tmp/_pre_extended_contigs.N.fa, 2 = tmp/_extended_contigs.N.fa */
+int ag_get_text(ag_ctx* ctx, int which, const char** text, uint64_t* len);
+
+/* ---- file level ------------------------------------------------------------------------------------------------------------------- */
+/* host half only: parse the unit's files into the staged arrays (then ag_build / ag_extend / ag_write_unit_files) */
+int ag_prepare_unit_files(ag_ctx* ctx, const char* tmp_dir, int unit_id);
+int ag_write_unit_files(ag_ctx* ctx, const char* tmp_dir, int unit_id);
+/* the five calls of AG:4768-4776 for unit N */
+int ag_run_unit_files(ag_ctx* ctx, const char* tmp_dir, int unit_id);
+/* staged arrays of the current unit (valid until the next ag_begin_unit / ag_prepare_unit_files) */
+typedef struct ag_unit_view {
+    const char* ref; uint32_t n_ref, n_tail;
+    const uint32_t* cm_start; const ag_cm_c* cm; uint32_t n_cm; const uint32_t* chain_pos; const char* chain_base;
+    const ag_aln_c* aln; uint64_t n_aln; const ag_seg_c* ext; uint64_t n_ext;
+} ag_unit_view;
+int ag_get_unit(ag_ctx* ctx, ag_unit_view* out);
+
+/* ---- introspection ------------------------------------------------------------------------------------------------------------------- */
+int ag_get_stats(ag_ctx* ctx, ag_stats* out);
+int ag_reset_stats(ag_ctx* ctx);
+/* node table after ag_build as text, one node per line (tests): pos item cov A C G T N cid coff cid0 coff0 mid moff [s] pos:item... */
+int ag_dump_nodes_text(ag_ctx* ctx, const char** text, uint64_t* len);
+void* ag_cuda_stream(ag_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

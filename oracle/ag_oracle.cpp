@@ -708,7 +708,7 @@ static void dumpNodes(int unit) {
 
 int main(int argc, char** argv) {
     std::string dir = ".", contigFile, genomeFile;
-    int k = 5, iv = 50, cov = 20, part = 1, first = 0, last = -1, dump = 0, prepare = 1;
+    int k = 5, iv = 50, cov = 20, part = 1, first = 0, last = -1, dump = 0, prepare = 1, prepare_only = 0;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         if (a == "--dir") dir = argv[++i];
@@ -717,6 +717,7 @@ int main(int argc, char** argv) {
         else if (a == "--last") last = atoi(argv[++i]);
         else if (a == "--dump-nodes") dump = 1;
         else if (a == "--no-prepare") prepare = 0;
+        else if (a == "--prepare-only") prepare_only = 1;
         else { fprintf(stderr, "ag_oracle: unknown option %s\n", a.c_str()); return 2; }
     }
     if (chdir(dir.c_str()) != 0) die("CANNOT OPEN FILE!");
@@ -738,6 +739,7 @@ int main(int argc, char** argv) {
     int units;
     if (prepare) { formalizeContigs(contigFile); units = formalizeGenome(genomeFile, part); }
     else { units = 0; while (access(("tmp/_genome." + std::to_string(units) + ".fa").c_str(), R_OK) == 0) units++; }
+    if (prepare_only) return 0;
     if (last < 0 || last >= units) last = units - 1;
     for (int unit = first; unit <= last; unit++) {
         auto t0 = std::chrono::steady_clock::now();

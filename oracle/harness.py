@@ -1,0 +1,147 @@
+"""Test / benchmark harness around the oracle — TEST INFRASTRUCTURE, never imported by the product package.
+
+Builds (g++) and runs: the synthetic generator (tools/agsynth.cpp), the CPU restatement (oracle/ag_oracle.cpp), the stub aligner,
+the host emulation of the kernels (tests/emul) and — only where /root/reference exists (the development container) — the
+unmodified reference into oracle/_ref/.
+"""
+import os
+import shutil
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE = os.path.join(ROOT, "oracle")
+BIN = os.path.join(ORACLE, "_bin")
+REF = os.path.join(ORACLE, "_ref")
+EMUL = os.path.join(ROOT, "tests", "emul", "_bin", "ag_emul")
+REF_SRC = "/root/reference/AlignGraph/AlignGraph.cpp"
+
+
+def _run(cmd, **kw):
+    return subprocess.run(cmd, check=True, **kw)
+
+
+def _stale(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.exists(s) and os.path.getmtime(s) > t for s in sources)
+
+
+def build_tools(with_ref=True, with_emul=True):
+    """Compile the checker binaries (idempotent).  Building the checker is not using it."""
+    cxx = os.environ.get("CXX", "g++")
+    os.makedirs(os.path.join(BIN, "stubs"), exist_ok=True)
+    jobs = [
+        (os.path.join(BIN, "ag_oracle"), [os.path.join(ORACLE, "ag_oracle.cpp")]),
+        (os.path.join(BIN, "agsynth"), [os.path.join(ROOT, "tools", "agsynth.cpp")]),
+        (os.path.join(BIN, "stubs", "pblat"), [os.path.join(ORACLE, "stubs", "pblat.cpp")]),
+    ]
+    for out, srcs in jobs:
+        if _stale(out, srcs):
+            _run([cxx, "-O2", "-std=c++17", "-o", out] + srcs)
+    blat = os.path.join(BIN, "stubs", "blat")
+    if _stale(blat, [os.path.join(BIN, "stubs", "pblat")]):
+        shutil.copy(os.path.join(BIN, "stubs", "pblat"), blat)
+    if with_emul:
+        csrc = os.path.join(ROOT, "aligngraph_b200", "csrc")
+        srcs = [os.path.join(ROOT, "tests", "emul", "ag_emul.cpp"), os.path.join(csrc, "ag_host.cpp")]
+        deps = srcs + [os.path.join(csrc, f) for f in ("ag_core.h", "ag_types.h", "ag_pipeline.h", "ag_host.h", "ag_device.cuh")]
+        if _stale(EMUL, deps):
+            os.makedirs(os.path.dirname(EMUL), exist_ok=True)
+            _run([cxx, "-O2", "-std=c++17", "-o", EMUL] + srcs)
+    if with_ref and os.path.exists(REF_SRC):
+        os.makedirs(REF, exist_ok=True)
+        for name, flags in (("AlignGraph", []), ("AlignGraph_O2", ["-O2"])):
+            out = os.path.join(REF, name)
+            if _stale(out, [REF_SRC]):
+                _run([cxx, "-w"] + flags + ["-o", out, REF_SRC, "-lpthread"])
+
+
+def have_reference():
+    return os.path.exists(os.path.join(REF, "AlignGraph_O2"))
+
+
+def synth(out_dir, **params):
+    """Generate a synthetic work directory.  params map to agsynth options (underscores -> dashes)."""
+    cmd = [os.path.join(BIN, "agsynth"), "--out", out_dir]
+    for k, v in params.items():
+        cmd += ["--" + k.replace("_", "-"), str(v)]
+    _run(cmd)
+    meta = {}
+    with open(os.path.join(out_dir, "synth_meta.txt")) as f:
+        for line in f:
+            k, v = line.split()
+            meta[k] = int(v)
+    return meta
+
+
+def read_command(work_dir):
+    """--kMer / --insertVariation / --coverage / --part as the reference reloads them on --resume (AlignGraph.cpp:4752)."""
+    p = {"kMer": 5, "insertVariation": 50, "coverage": 20, "part": 1}
+    with open(os.path.join(work_dir, "tmp", "_command.txt")) as f:
+        tok = [l.rstrip("\n") for l in f]
+    for i, t in enumerate(tok[:-1]):
+        if t.startswith("--") and t[2:] in p:
+            p[t[2:]] = int(tok[i + 1])
+        if t in ("--contig", "--genome"):
+            p[t[2:]] = tok[i + 1]
+    return p
+
+
+def run_oracle(work_dir, dump_nodes=False, prepare=True, first=None, last=None, capture=True):
+    cmd = [os.path.join(BIN, "ag_oracle"), "--dir", work_dir]
+    if dump_nodes:
+        cmd.append("--dump-nodes")
+    if not prepare:
+        cmd.append("--no-prepare")
+    if first is not None:
+        cmd += ["--first", str(first)]
+    if last is not None:
+        cmd += ["--last", str(last)]
+    r = subprocess.run(cmd, check=True, capture_output=capture, text=True)
+    return r.stderr if capture else ""
+
+
+def run_emul(work_dir, dump_nodes=False, env=None):
+    cmd = [EMUL, "--dir", work_dir]
+    if dump_nodes:
+        cmd.append("--dump-nodes")
+    e = dict(os.environ)
+    if env:
+        e.update(env)
+    return subprocess.run(cmd, check=True, capture_output=True, text=True, env=e).stderr
+
+
+def run_reference(work_dir, optimized=True, timeout=3600):
+    """Unmodified reference through its --resume door (AlignGraph.cpp:4748-4760) with the stub aligner on PATH.
+    Returns (exit_code, stdout).  The reference segfaults in refinement() for --part > 1 AFTER writing the hot-path files."""
+    exe = os.path.join(REF, "AlignGraph_O2" if optimized else "AlignGraph")
+    env = dict(os.environ)
+    env["PATH"] = os.path.join(BIN, "stubs") + os.pathsep + env["PATH"]
+    with open(os.path.join(work_dir, "tmp", "_checkpoint.txt"), "w") as f:
+        f.write("0\n")
+    r = subprocess.run([exe, "--resume"], cwd=work_dir, env=env, capture_output=True, text=True, timeout=timeout)
+    return r.returncode, r.stdout
+
+
+def prepare_tmp(work_dir):
+    """Write tmp/_contigs.fa and tmp/_genome.N.fa (what --resume regenerates, AlignGraph.cpp:4757-4758) via the oracle."""
+    _run([os.path.join(BIN, "ag_oracle"), "--dir", work_dir, "--prepare-only"])
+
+
+UNIT_FILES = ("_initial_contigs.{}.fa", "_pre_extended_contigs.{}.fa", "_extended_contigs.{}.fa")
+
+
+def unit_outputs(work_dir, unit):
+    out = []
+    for pat in UNIT_FILES:
+        with open(os.path.join(work_dir, "tmp", pat.format(unit)), "rb") as f:
+            out.append(f.read())
+    return out
+
+
+def n_units(work_dir):
+    n = 0
+    while os.path.exists(os.path.join(work_dir, "tmp", f"_genome.{n}.fa")):
+        n += 1
+    return n

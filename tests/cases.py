@@ -1,0 +1,20 @@
+"""Synthetic cases shared by the test-suite, the golden-fixture script and the smoke test (agsynth options)."""
+
+# Small cases whose REAL-reference outputs are committed under tests/golden/<name>/ (made by tests/golden/make_golden.py).
+GOLDEN = {
+    "plain": dict(genome_bp=30000, coverage=50, contig_len=4000, contig_gap=600, seed=11),
+    "mix": dict(genome_bp=30000, coverage=40, indel=0.004, softclip=0.3, multi=0.2, unaligned=0.02, lowqual=0.03, n_rate=0.003,
+                read_err=0.005, header=1, contig_len=3000, contig_gap=400, seed=12),
+    "k7_150_2chr": dict(genome_bp=40000, chroms=2, coverage=40, readlen=150, kmer=7, indel=0.002, softclip=0.2, contig_len=5000, seed=13),
+    "part2": dict(genome_bp=30000, part=2, coverage=30, indel=0.001, insert_sd=80, cov=10, seed=14),
+}
+
+# Larger / nastier cases checked live against the oracle (and the reference where it is available).
+LIVE = {
+    "a1": dict(genome_bp=100000, coverage=40, indel=0.002, softclip=0.2, multi=0.1, unaligned=0.02, n_rate=0.002, read_err=0.005, header=1,
+               contig_len=5000, seed=1),
+    "a4": dict(genome_bp=60000, coverage=60, indel=0.01, softclip=0.5, multi=0.5, seed=4, kmer=3, readlen=60, insert_mean=300, contig_len=2000),
+    "deep": dict(genome_bp=20000, coverage=400, insert_sd=120, contig_len=3000, seed=5, cov=30),
+    "lowcov": dict(genome_bp=50000, coverage=8, seed=6, cov=3, contig_len=8000),
+    "nocontigs": dict(genome_bp=30000, coverage=50, seed=7, contig_len=150, contig_gap=5000),
+}

@@ -1,0 +1,36 @@
+"""Regenerate tests/golden/*: outputs of the UNMODIFIED reference (oracle/_ref, built from /root/reference by `make -C oracle ref`)
+on the deterministic synthetic cases in tests/cases.py.  Run in the development container (the reference is absent elsewhere):
+
+    python tests/golden/make_golden.py
+"""
+import os
+import shutil
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from oracle import harness  # noqa: E402
+import cases  # noqa: E402
+
+harness.build_tools()
+assert harness.have_reference(), "the reference is not available here"
+for name, params in cases.GOLDEN.items():
+    work = tempfile.mkdtemp(prefix="ag_golden_")
+    harness.synth(work, **params)
+    rc, out = harness.run_reference(work, optimized=False)  # the README build line (-O0) is the parity oracle
+    dst = os.path.join(ROOT, "tests", "golden", name)
+    shutil.rmtree(dst, ignore_errors=True)
+    os.makedirs(dst)
+    n = harness.n_units(work)
+    for u in range(n):
+        for pat in harness.UNIT_FILES:
+            shutil.copy(os.path.join(work, "tmp", pat.format(u)), dst)
+    for extra in ("extendedContigs.fa", "remainingContigs.fa"):
+        if rc == 0 and os.path.exists(os.path.join(work, extra)):
+            shutil.copy(os.path.join(work, extra), dst)
+    with open(os.path.join(dst, "README.txt"), "w") as f:
+        f.write(f"reference exit code {rc}; units {n}; agsynth params {params}\n")
+    print(name, "units", n, "reference exit", rc)
+    shutil.rmtree(work)

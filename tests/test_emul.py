@@ -1,0 +1,41 @@
+"""Host emulation of the CUDA kernels' per-thread logic (tests/emul, built from aligngraph_b200/csrc/ag_core.h) against the oracle:
+checks the position-parallel formulation (touch fusion, edges from the final table, component-parallel walk), the host parsers and
+the post passes on CPU.  The kernels themselves are exercised by the -m gpu tests."""
+import os
+import shutil
+
+import pytest
+
+import cases
+from conftest import compare_with_golden
+
+
+@pytest.mark.parametrize("name", sorted(cases.GOLDEN))
+def test_emulation_matches_golden(harness, workdir, name):
+    harness.synth(workdir, **cases.GOLDEN[name])
+    harness.run_emul(workdir)
+    compare_with_golden(harness, workdir, name)
+
+
+@pytest.mark.parametrize("name", sorted(cases.LIVE))
+def test_emulation_matches_oracle_nodes_and_files(harness, workdir, name):
+    emu = os.path.join(workdir, "emu")
+    ora = os.path.join(workdir, "ora")
+    harness.synth(emu, **cases.LIVE[name])
+    shutil.copytree(emu, ora)
+    harness.run_oracle(ora, dump_nodes=True)
+    harness.run_emul(emu, dump_nodes=True)
+    n = harness.n_units(ora)
+    for u in range(n):
+        assert harness.unit_outputs(emu, u) == harness.unit_outputs(ora, u)
+        a = open(os.path.join(emu, "tmp", f"_nodes.{u}.txt"), "rb").read()
+        b = open(os.path.join(ora, "tmp", f"_nodes.{u}.txt"), "rb").read()
+        assert a == b, "node tables differ"
+
+
+def test_emulation_sequential_walk_path(harness, workdir):
+    """The exact sequential replay used when the reference's 1000-position skip (AlignGraph.cpp:2194-2202) applies."""
+    harness.synth(workdir, **cases.GOLDEN["mix"])
+    log = harness.run_emul(workdir, env={"AG_EMUL_FORCE_SEQUENTIAL": "1"})
+    assert "sequential walk" in log
+    compare_with_golden(harness, workdir, "mix")

@@ -1,0 +1,105 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the oracle and the committed reference outputs."""
+import os
+import shutil
+
+import pytest
+
+import cases
+from conftest import compare_with_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ag():
+    import aligngraph_b200 as m
+    m.load_library()
+    return m
+
+
+def run_cuda(ag, harness, work, dump=False):
+    p = harness.read_command(work)
+    harness.prepare_tmp(work)  # tmp/_contigs.fa, tmp/_genome.N.fa — input normalisation, outside the hot path
+    ctx = ag.Context(k=p["kMer"], insert_variation=p["insertVariation"], coverage=p["coverage"])
+    ctx.load_reads_fasta(os.path.join(work, "tmp", "_reads.fa"))
+    dumps = []
+    for u in range(harness.n_units(work)):
+        ctx.prepare_unit(os.path.join(work, "tmp"), u)
+        ctx.build()
+        if dump:
+            dumps.append(ctx.dump_nodes_text())
+        ctx.extend()
+        ctx.write_unit(os.path.join(work, "tmp"), u)
+    st = ctx.stats()
+    ctx.close()
+    return st, dumps
+
+
+@pytest.mark.parametrize("name", sorted(cases.GOLDEN))
+def test_cuda_matches_reference_golden(ag, harness, workdir, name):
+    harness.synth(workdir, **cases.GOLDEN[name])
+    st, _ = run_cuda(ag, harness, workdir)
+    assert st["kernel_launches"] > 0
+    compare_with_golden(harness, workdir, name)
+
+
+@pytest.mark.parametrize("name", sorted(cases.LIVE))
+def test_cuda_matches_oracle_nodes_and_files(ag, harness, workdir, name):
+    gpu = os.path.join(workdir, "gpu")
+    ora = os.path.join(workdir, "ora")
+    harness.synth(gpu, **cases.LIVE[name])
+    shutil.copytree(gpu, ora)
+    harness.run_oracle(ora, dump_nodes=True)
+    st, dumps = run_cuda(ag, harness, gpu, dump=True)
+    for u in range(harness.n_units(ora)):
+        want = open(os.path.join(ora, "tmp", f"_nodes.{u}.txt"), "rb").read()
+        assert dumps[u] == want, "node table differs from the oracle"
+        assert harness.unit_outputs(gpu, u) == harness.unit_outputs(ora, u)
+
+
+def test_run_unit_files_is_the_five_calls(ag, harness, workdir):
+    """ag_run_unit_files == loadGenome..scaffoldContigs on the reference's tmp/ contract."""
+    harness.synth(workdir, **cases.GOLDEN["plain"])
+    harness.prepare_tmp(workdir)
+    ctx = ag.Context()
+    ctx.load_reads_fasta(os.path.join(workdir, "tmp", "_reads.fa"))
+    ctx.run_unit(os.path.join(workdir, "tmp"), 0)
+    compare_with_golden(harness, workdir, "plain")
+
+
+def test_array_level_equals_file_level(ag, harness, workdir):
+    """Feeding the staged packed arrays back through ag_begin_unit / ag_set_contimers / ag_add_alignments gives the same FASTA."""
+    harness.synth(workdir, **cases.GOLDEN["mix"])
+    harness.prepare_tmp(workdir)
+    p = harness.read_command(workdir)
+    a = ag.Context(k=p["kMer"], insert_variation=p["insertVariation"], coverage=p["coverage"])
+    a.load_reads_fasta(os.path.join(workdir, "tmp", "_reads.fa"))
+    a.prepare_unit(os.path.join(workdir, "tmp"), 0)
+    v = a.get_unit()
+    b = ag.Context(k=p["kMer"], insert_variation=p["insertVariation"], coverage=p["coverage"])
+    b.load_reads_fasta(os.path.join(workdir, "tmp", "_reads.fa"))
+    b.begin_unit(0, v.ref, v.n_ref)
+    b.set_contimers(v.cm_start, v.cm, v.n_cm, v.chain_pos, v.chain_base, v.ref + v.n_ref, v.n_tail)
+    b.add_alignments(v.aln, v.n_aln, v.ext, v.n_ext)
+    b.build(); b.extend()
+    a.build(); a.extend()
+    assert a.text(1) == b.text(1) and a.text(2) == b.text(2) and len(a.text(1)) > 0
+    g = os.path.join(os.path.dirname(__file__), "golden", "mix")
+    assert b.text(1) == open(os.path.join(g, "_pre_extended_contigs.0.fa"), "rb").read()
+    assert b.text(2) == open(os.path.join(g, "_extended_contigs.0.fa"), "rb").read()
+
+
+def test_full_size_properties(ag, harness, workdir):
+    """A larger unit (crosses many tiles; several hundred thousand alignments): size-independent properties — the device build is
+    deterministic across runs, every emitted contig is non-empty ACGTN text, headers are strictly ordered by start position."""
+    harness.synth(workdir, genome_bp=1000000, coverage=50, seed=99)
+    outs = []
+    for rep in range(2):
+        st, _ = run_cuda(ag, harness, workdir)
+        outs.append(harness.unit_outputs(workdir, 0))
+    assert outs[0] == outs[1]
+    pre = outs[0][1].decode().splitlines()
+    starts = [int(l.split(", ")[3]) for l in pre if l.startswith(">")]
+    assert starts == sorted(starts) and len(starts) > 100
+    assert all(set(l) <= set("ACGTN") for l in pre if not l.startswith(">"))
+    assert st["n_nodes"] > 1000000

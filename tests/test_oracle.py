@@ -1,0 +1,34 @@
+"""The CPU restatement (oracle/ag_oracle.cpp) is pinned against the real reference: committed golden outputs everywhere, a live
+run of the unmodified reference where /root/reference has been compiled into oracle/_ref (the development container)."""
+import os
+import shutil
+
+import pytest
+
+import cases
+from conftest import compare_with_golden
+
+
+@pytest.mark.parametrize("name", sorted(cases.GOLDEN))
+def test_oracle_matches_reference_golden(harness, workdir, name):
+    harness.synth(workdir, **cases.GOLDEN[name])
+    harness.run_oracle(workdir)
+    compare_with_golden(harness, workdir, name)
+
+
+@pytest.mark.parametrize("name", ["a1", "a4", "deep"])
+def test_oracle_matches_live_reference(harness, workdir, name):
+    if not harness.have_reference():
+        pytest.skip("reference not built here (oracle/_ref absent)")
+    ref = os.path.join(workdir, "ref")
+    ora = os.path.join(workdir, "ora")
+    harness.synth(ref, **cases.LIVE[name])
+    shutil.copytree(ref, ora)
+    harness.run_reference(ref)
+    harness.run_oracle(ora)
+    n = harness.n_units(ref)
+    assert n == harness.n_units(ora) and n > 0
+    for u in range(n):
+        assert harness.unit_outputs(ref, u) == harness.unit_outputs(ora, u)
+    for f in ("_contigs.fa", "_genome.0.fa"):
+        assert open(os.path.join(ref, "tmp", f), "rb").read() == open(os.path.join(ora, "tmp", f), "rb").read()
