@@ -78,6 +78,12 @@ def load_library(path=None):
         "ag_reset_stats": (i32, [vp]),
         "ag_dump_nodes_text": (i32, [vp, C.POINTER(vp), C.POINTER(u64)]),
         "ag_cuda_stream": (vp, [vp]),
+        "ag_invalidate_device_inputs": (i32, [vp]),
+        "ag_reupload_reads": (i32, [vp]),
+        "ag_pin_staged": (i32, [vp]),
+        "ag_formalize_inputs": (i32, [vp, cp, cp, cp, i32, C.POINTER(i32)]),
+        "ag_timer_start": (i32, [vp]),
+        "ag_timer_stop": (i32, [vp, C.POINTER(C.c_float)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -179,6 +185,29 @@ class Context:
         p, n = C.c_void_p(), C.c_uint64()
         self._ck(self._lib.ag_dump_nodes_text(self._h, C.byref(p), C.byref(n)), "ag_dump_nodes_text")
         return C.string_at(p.value, n.value) if n.value else b""
+
+    def invalidate_device_inputs(self):
+        self._ck(self._lib.ag_invalidate_device_inputs(self._h), "ag_invalidate_device_inputs")
+
+    def reupload_reads(self):
+        self._ck(self._lib.ag_reupload_reads(self._h), "ag_reupload_reads")
+
+    def pin_staged(self):
+        self._ck(self._lib.ag_pin_staged(self._h), "ag_pin_staged")
+
+    def formalize_inputs(self, contig_fa, genome_fa, tmp_dir, part=1):
+        n = C.c_int()
+        self._ck(self._lib.ag_formalize_inputs(self._h, os.fsencode(contig_fa), os.fsencode(genome_fa), os.fsencode(tmp_dir), part, C.byref(n)),
+                 "ag_formalize_inputs")
+        return n.value
+
+    def timer_start(self):
+        self._ck(self._lib.ag_timer_start(self._h), "ag_timer_start")
+
+    def timer_stop(self):
+        ms = C.c_float()
+        self._ck(self._lib.ag_timer_stop(self._h, C.byref(ms)), "ag_timer_stop")
+        return ms.value
 
     def cuda_stream(self):
         return self._lib.ag_cuda_stream(self._h)

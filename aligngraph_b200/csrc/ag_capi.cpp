@@ -14,6 +14,7 @@ struct ag_ctx {
     bool have_reads = false;
     AgUnit unit;
     int unit_id = -1;
+    bool uploaded = false;  // the staged unit arrays are resident on the device
     AgUnitResult res;
     std::string err, dump;
     double s_parse = 0, s_device = 0, s_post = 0;
@@ -42,12 +43,13 @@ int ag_create(const ag_params* params, ag_ctx** out) {
     *out = c;
     return 0;
 }
-void ag_destroy(ag_ctx* ctx) { if (!ctx) return; delete ctx->dev; delete ctx; }
+void ag_destroy(ag_ctx* ctx) { if (!ctx) return; if (ctx->dev) ctx->dev->unpin_all(); delete ctx->dev; delete ctx; }
 const char* ag_last_error(const ag_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 const char* ag_create_error(void) { return g_create_error.c_str(); }
 
 int ag_set_reads(ag_ctx* ctx, const uint32_t* bases2, const uint32_t* nmask, const uint16_t* pair_len, uint64_t n_pairs, uint32_t stride2, uint32_t stridem) {
     return guard(ctx, [&] {
+        ctx->dev->unpin_all();
         AgReads& r = ctx->reads;
         r.n_pairs = n_pairs; r.stride2 = stride2; r.stridem = stridem;
         r.bases.assign(bases2, bases2 + 2 * n_pairs * stride2); r.nmask.assign(nmask, nmask + 2 * n_pairs * stridem); r.len.assign(pair_len, pair_len + n_pairs);
@@ -58,6 +60,7 @@ int ag_set_reads(ag_ctx* ctx, const uint32_t* bases2, const uint32_t* nmask, con
 }
 int ag_set_reads_device(ag_ctx* ctx, const uint32_t* d_bases2, const uint32_t* d_nmask, const uint16_t* d_pair_len, uint64_t n_pairs, uint32_t stride2, uint32_t stridem) {
     return guard(ctx, [&] {
+        ctx->dev->unpin_all();
         AgReads& r = ctx->reads;
         r.n_pairs = n_pairs; r.stride2 = stride2; r.stridem = stridem;
         r.bases.resize(2 * n_pairs * stride2); r.nmask.resize(2 * n_pairs * stridem); r.len.resize(n_pairs); r.exc.clear();
@@ -71,6 +74,7 @@ int ag_set_read_exceptions(ag_ctx* ctx, const uint64_t* keys, const char* chars,
 }
 int ag_load_reads_fasta(ag_ctx* ctx, const char* path) {
     return guard(ctx, [&] {
+        ctx->dev->unpin_all();
         auto t0 = std::chrono::steady_clock::now();
         ag_parse_reads(path, ctx->reads);
         ctx->s_parse += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -88,7 +92,7 @@ int ag_get_reads(ag_ctx* ctx, const uint32_t** bases2, const uint32_t** nmask, c
 
 int ag_begin_unit(ag_ctx* ctx, int unit_id, const char* ref_bases, uint32_t n_ref) {
     return guard(ctx, [&] {
-        ctx->unit = AgUnit(); ctx->res = AgUnitResult(); ctx->unit_id = unit_id;
+        ctx->dev->unpin_all(); ctx->unit = AgUnit(); ctx->res = AgUnitResult(); ctx->unit_id = unit_id; ctx->uploaded = false;
         ctx->unit.ref.assign(ref_bases, n_ref); ctx->unit.n_ref = n_ref;
         ctx->unit.cm_start.assign((size_t)n_ref + 1, 0);
     });
@@ -96,7 +100,8 @@ int ag_begin_unit(ag_ctx* ctx, int unit_id, const char* ref_bases, uint32_t n_re
 int ag_set_contimers(ag_ctx* ctx, const uint32_t* cm_start, const ag_cm_c* cm, uint32_t n_cm, const uint32_t* chain_pos, const char* chain_base,
                      const char* tail_bases, uint32_t n_tail) {
     return guard(ctx, [&] {
-        AgUnit& u = ctx->unit;
+        ctx->dev->unpin_all();
+        AgUnit& u = ctx->unit; ctx->uploaded = false;
         u.ref.resize(u.n_ref);
         if (n_tail) u.ref.append(tail_bases, n_tail);
         u.cm_start.assign(cm_start, cm_start + u.ref.size() + 1);
@@ -106,7 +111,8 @@ int ag_set_contimers(ag_ctx* ctx, const uint32_t* cm_start, const ag_cm_c* cm, u
 }
 int ag_add_alignments(ag_ctx* ctx, const ag_aln_c* aln, uint64_t n, const ag_seg_c* ext, uint64_t n_ext) {
     return guard(ctx, [&] {
-        AgUnit& u = ctx->unit;
+        ctx->dev->unpin_all();
+        AgUnit& u = ctx->unit; ctx->uploaded = false;
         u32 base = (u32)u.ext.size();
         size_t a0 = u.aln.size();
         u.aln.insert(u.aln.end(), (const ag_aln*)aln, (const ag_aln*)aln + n);
@@ -119,7 +125,7 @@ int ag_build(ag_ctx* ctx) {
     return guard(ctx, [&] {
         if (!ctx->have_reads) throw AgHostError{"reads not set"};
         auto t0 = std::chrono::steady_clock::now();
-        ctx->dev->load_unit(ag_unit_input(ctx->unit));
+        if (!ctx->uploaded) { ctx->dev->load_unit(ag_unit_input(ctx->unit)); ctx->uploaded = true; }
         ctx->dev->build();
         ctx->s_device += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         ctx->n_aln += ctx->unit.aln.size();
@@ -162,7 +168,7 @@ int ag_prepare_unit_files(ag_ctx* ctx, const char* tmp_dir, int unit_id) {
     return guard(ctx, [&] {
         if (!ctx->have_reads) throw AgHostError{"reads not set"};
         auto t0 = std::chrono::steady_clock::now();
-        ctx->unit = AgUnit(); ctx->res = AgUnitResult(); ctx->unit_id = unit_id;
+        ctx->dev->unpin_all(); ctx->unit = AgUnit(); ctx->res = AgUnitResult(); ctx->unit_id = unit_id; ctx->uploaded = false;
         ag_prepare_unit(ctx->reads, tmp_dir, unit_id, ctx->unit, ctx->res.initial_text);
         ctx->s_parse += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     });
@@ -215,5 +221,31 @@ int ag_dump_nodes_text(ag_ctx* ctx, const char** text, uint64_t* len) {
     });
 }
 void* ag_cuda_stream(ag_ctx* ctx) { return ctx ? ctx->dev->stream() : nullptr; }
+int ag_invalidate_device_inputs(ag_ctx* ctx) { return guard(ctx, [&] { ctx->uploaded = false; }); }
+int ag_reupload_reads(ag_ctx* ctx) {
+    return guard(ctx, [&] {
+        const AgReads& r = ctx->reads;
+        ctx->dev->set_reads(r.bases.data(), r.nmask.data(), r.len.data(), r.n_pairs, r.stride2, r.stridem, false);
+    });
+}
+int ag_formalize_inputs(ag_ctx* ctx, const char* contig_fa, const char* genome_fa, const char* tmp_dir, int part, int* n_units) {
+    return guard(ctx, [&] {
+        std::vector<std::string> cids, gids;
+        ag_formalize_contigs(contig_fa, tmp_dir, cids);
+        *n_units = ag_formalize_genome(genome_fa, tmp_dir, part, gids);
+    });
+}
+int ag_pin_staged(ag_ctx* ctx) {
+    return guard(ctx, [&] {
+        AgDevice& d = *ctx->dev; const AgReads& r = ctx->reads; const AgUnit& u = ctx->unit;
+        d.unpin_all();
+        d.pin(r.bases.data(), r.bases.size() * 4); d.pin(r.nmask.data(), r.nmask.size() * 4); d.pin(r.len.data(), r.len.size() * 2);
+        d.pin(u.ref.data(), u.ref.size()); d.pin(u.cm_start.data(), u.cm_start.size() * 4); d.pin(u.cm.data(), u.cm.size() * sizeof(ag_cm));
+        d.pin(u.chain_pos.data(), u.chain_pos.size() * 4); d.pin(u.chain_base.data(), u.chain_base.size());
+        d.pin(u.aln.data(), u.aln.size() * sizeof(ag_aln)); d.pin(u.ext.data(), u.ext.size() * sizeof(ag_seg));
+    });
+}
+int ag_timer_start(ag_ctx* ctx) { return guard(ctx, [&] { ctx->dev->timer_start(); }); }
+int ag_timer_stop(ag_ctx* ctx, float* ms) { return guard(ctx, [&] { *ms = ctx->dev->timer_stop(); }); }
 
 }  // extern "C"

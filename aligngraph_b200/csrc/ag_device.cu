@@ -528,6 +528,31 @@ AgDevice::~AgDevice() {
     delete m_;
 }
 
+void AgDevice::pin(const void* p, size_t bytes) {
+    if (!p || !bytes) return;
+    CK(cudaSetDevice(dev_));
+    if (cudaHostRegister((void*)p, bytes, cudaHostRegisterDefault) == cudaSuccess) pinned_.push_back((void*)p);
+    else cudaGetLastError();
+}
+void AgDevice::unpin_all() {
+    if (pinned_.empty()) return;
+    cudaSetDevice(dev_);
+    for (void* p : pinned_) cudaHostUnregister(p);
+    pinned_.clear();
+}
+void AgDevice::timer_start() {
+    CK(cudaSetDevice(dev_));
+    if (!ev0_) { cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b)); ev0_ = a; ev1_ = b; }
+    CK(cudaStreamSynchronize(m_->st));
+    CK(cudaEventRecord((cudaEvent_t)ev0_, m_->st));
+}
+float AgDevice::timer_stop() {
+    CK(cudaSetDevice(dev_));
+    CK(cudaEventRecord((cudaEvent_t)ev1_, m_->st));
+    CK(cudaEventSynchronize((cudaEvent_t)ev1_));
+    float ms = 0; CK(cudaEventElapsedTime(&ms, (cudaEvent_t)ev0_, (cudaEvent_t)ev1_));
+    return ms;
+}
 void AgDevice::sync() { CK(cudaSetDevice(dev_)); CK(cudaStreamSynchronize(m_->st)); }
 
 void AgDevice::set_reads(const u32* bases, const u32* nmask, const uint16_t* len, u64 n_pairs, u32 stride2, u32 stridem, bool on_device) {

@@ -50,8 +50,12 @@ public:
     void occupancy(std::vector<unsigned char>& bits);
     void dump_nodes(AgNodeDump& d);
     void sync();
+    void pin(const void* p, size_t bytes);
+    void unpin_all();
+    void timer_start();
+    float timer_stop();
     const AgTimings& timings() const { return t_; }
-    void reset_timings() { t_ = AgTimings(); }
+    void reset_timings() { t_ = AgTimings(); launches_ = 0; }
     int device() const { return dev_; }
     void* stream() const { return stream_; }
     u64 kernel_launches() const { return launches_; }
@@ -63,6 +67,8 @@ private:
     void* stream_ = nullptr;
     AgTimings t_;
     u64 launches_ = 0;
+    void *ev0_ = nullptr, *ev1_ = nullptr;
+    std::vector<void*> pinned_;
     void walk_components();
     void walk_sequential();
 };

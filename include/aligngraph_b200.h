@@ -110,6 +110,19 @@ int ag_reset_stats(ag_ctx* ctx);
 /* node table after ag_build as text, one node per line (tests): pos item cov A C G T N cid coff cid0 coff0 mid moff [s] pos:item... */
 int ag_dump_nodes_text(ag_ctx* ctx, const char** text, uint64_t* len);
 void* ag_cuda_stream(ag_ctx* ctx);
+/* ---- benchmark support ---------------------------------------------------------------------------------------------------------
+ * ag_build() uploads the staged unit arrays only when they changed since the last upload; ag_invalidate_device_inputs() forces the
+ * next ag_build() to copy them again (end-to-end timing), ag_reupload_reads() repeats the reads' host->device copy.
+ * ag_timer_start/stop bracket a region with CUDA events on the context's stream. */
+int ag_invalidate_device_inputs(ag_ctx* ctx);
+int ag_reupload_reads(ag_ctx* ctx);
+/* page-lock the staged host arrays (reads + current unit) so that the copies above run from pinned memory */
+int ag_pin_staged(ag_ctx* ctx);
+/* input normalisation that --resume re-runs (formalizeInput(contigs) + formalizeGenome, AG:4757-4758): writes tmp/_contigs.fa,
+ * tmp/_chaff.fa, tmp/_genome.fa and tmp/_genome.N.fa; returns the number of units */
+int ag_formalize_inputs(ag_ctx* ctx, const char* contig_fa, const char* genome_fa, const char* tmp_dir, int part, int* n_units);
+int ag_timer_start(ag_ctx* ctx);
+int ag_timer_stop(ag_ctx* ctx, float* ms);
 
 #ifdef __cplusplus
 }

@@ -7,6 +7,7 @@ unmodified reference into oracle/_ref/.
 import os
 import shutil
 import subprocess
+import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE = os.path.join(ROOT, "oracle")
@@ -14,6 +15,8 @@ BIN = os.path.join(ORACLE, "_bin")
 REF = os.path.join(ORACLE, "_ref")
 EMUL = os.path.join(ROOT, "tests", "emul", "_bin", "ag_emul")
 REF_SRC = "/root/reference/AlignGraph/AlignGraph.cpp"
+sys.path.insert(0, ROOT)
+from tools import synth as _synth  # noqa: E402
 
 
 def _run(cmd, **kw):
@@ -30,10 +33,10 @@ def _stale(target, sources):
 def build_tools(with_ref=True, with_emul=True):
     """Compile the checker binaries (idempotent).  Building the checker is not using it."""
     cxx = os.environ.get("CXX", "g++")
+    _synth.build()
     os.makedirs(os.path.join(BIN, "stubs"), exist_ok=True)
     jobs = [
         (os.path.join(BIN, "ag_oracle"), [os.path.join(ORACLE, "ag_oracle.cpp")]),
-        (os.path.join(BIN, "agsynth"), [os.path.join(ROOT, "tools", "agsynth.cpp")]),
         (os.path.join(BIN, "stubs", "pblat"), [os.path.join(ORACLE, "stubs", "pblat.cpp")]),
     ]
     for out, srcs in jobs:
@@ -62,17 +65,7 @@ def have_reference():
 
 
 def synth(out_dir, **params):
-    """Generate a synthetic work directory.  params map to agsynth options (underscores -> dashes)."""
-    cmd = [os.path.join(BIN, "agsynth"), "--out", out_dir]
-    for k, v in params.items():
-        cmd += ["--" + k.replace("_", "-"), str(v)]
-    _run(cmd)
-    meta = {}
-    with open(os.path.join(out_dir, "synth_meta.txt")) as f:
-        for line in f:
-            k, v = line.split()
-            meta[k] = int(v)
-    return meta
+    return _synth.synth(out_dir, **params)
 
 
 def read_command(work_dir):
