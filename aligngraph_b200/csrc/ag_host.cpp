@@ -707,3 +707,212 @@ void ag_write_file(const std::string& path, const std::string& text) {
     if (!text.empty()) fwrite(text.data(), 1, text.size(), f);
     fclose(f);
 }
+
+// =============================================================================================================================
+// CLI-side phases outside the hot path (kept byte-compatible with the reference so that the binary is a drop-in)
+// =============================================================================================================================
+int ag_max_read_length(const std::string& path) {  // AG:3197-3226
+    FileMap fm(path);
+    if (!fm.ok) throw AgHostError{"CANNOT OPEN FILE!"};
+    int mx = 0, len = 0;
+    Lines ln(fm.p, fm.n); const char* s; size_t n;
+    while (ln.next(s, n)) {
+        if (n == 0 || s[0] == 0) break;
+        if (s[0] == '>') { if (len > mx) mx = len; len = 0; continue; }
+        len += (int)n;
+    }
+    if (len > mx) mx = len;
+    return mx;
+}
+
+// AG:3420-3518: rename pairs to integers, truncate both mates to the shorter one, write the interleaved and the two split files
+long ag_formalize_reads(const std::string& in1, const std::string& in2, const std::string& tmp) {
+    FileMap f1(in1), f2(in2);
+    if (!f1.ok || !f2.ok) throw AgHostError{"CANNOT OPEN FILE!"};
+    Out out(tmp + "/_reads.fa"), out1(tmp + "/_reads_1.fa"), out2(tmp + "/_reads_2.fa");
+    Lines l1(f1.p, f1.n), l2(f2.p, f2.n);
+    std::string r1, r2;
+    unsigned long id = 0;
+    auto emit = [&]() {
+        if (r1.empty() || r2.empty()) return;
+        size_t sz = std::min(r1.size(), r2.size());
+        for (Out* o : {&out, &out1}) { o->ch('>'); o->num(id); o->ch('\n'); o->put(r1.data(), sz); o->ch('\n'); }
+        for (Out* o : {&out, &out2}) { o->ch('>'); o->num(id); o->ch('\n'); o->put(r2.data(), sz); o->ch('\n'); }
+        id++;
+    };
+    for (;;) {
+        const char *s1 = nullptr, *s2 = nullptr; size_t n1 = 0, n2 = 0;
+        bool g1 = l1.next(s1, n1), g2 = l2.next(s2, n2);
+        if (!g1 || !g2) break;  // while(in1.good() && in2.good())
+        bool e1 = n1 == 0 || s1[0] == 0, e2 = n2 == 0 || s2[0] == 0;
+        if (e1 && e2) break;
+        if (e1 != e2) throw AgHostError{"INCONSISTENT PE FILES!"};
+        if (s1[0] == '>' && s2[0] == '>') { emit(); r1.clear(); r2.clear(); }
+        else if (s1[0] != '>' && s2[0] != '>') { r1.append(s1, n1); r2.append(s2, n2); }
+        else throw AgHostError{"INCONSISTENT PE FILES!"};
+    }
+    emit();
+    return (long)id;
+}
+
+// AG:3545-3579 (+ parseBT AG:3520-3543): split the whole-genome SAM by the integer RNAME
+void ag_distribute_alignments(const std::string& tmp, int units) {
+    FileMap fm(tmp + "/_reads_genome.bowtie");
+    if (!fm.ok) throw AgHostError{"CANNOT OPEN FILE!"};
+    std::vector<Out*> outs;
+    for (int u = 0; u < units; u++) outs.push_back(new Out(tmp + "/_reads_genome." + std::to_string(u) + ".bowtie"));
+    Lines ln(fm.p, fm.n); const char* s; size_t n;
+    while (ln.next(s, n)) {
+        if (n && s[0] == '@') continue;
+        if (n == 0 || s[0] == 0) break;
+        const char* end = s + n; const char* p = s; int tab = 0;
+        while (p < end && tab < 2) { if (*p == '\t') tab++; p++; }
+        const char* q = p;
+        while (q < end && *q != '\t') q++;
+        int target = memchr(p, '*', (size_t)(q - p)) ? -1 : ag_atoi(p, std::min<size_t>((size_t)(q - p), 9));
+        if (target >= 0 && target < units) { outs[target]->put(s, n); outs[target]->ch('\n'); }
+    }
+    for (Out* o : outs) delete o;
+}
+
+// AG:3751-3819
+double ag_check_ratio(const std::string& tmp, int units) {
+    long n_reads = 0;
+    {
+        FileMap fm(tmp + "/_reads_1.fa");
+        if (!fm.ok) throw AgHostError{"CANNOT OPEN FILE!"};
+        for (size_t i = 0; i < fm.n; i++) if (fm.p[i] == '>' && (i == 0 || fm.p[i - 1] == '\n')) n_reads++;
+    }
+    std::vector<char> hit((size_t)n_reads, 0);
+    std::vector<ag_seg> s1, s2;
+    for (int u = 0; u < units; u++) {
+        FileMap fm(tmp + "/_reads_genome." + std::to_string(u) + ".bowtie");
+        if (!fm.ok) throw AgHostError{"CANNOT OPEN FILE!"};
+        Lines ln(fm.p, fm.n); const char* s; size_t n;
+        while (ln.next(s, n)) {
+            if (n == 0 || s[0] == 0) break;
+            if (s[0] == '@') continue;
+            SamRec a, b;
+            parse_sam(s, n, a, s1);
+            if (!ln.next(s, n) || n == 0 || s[0] == 0) throw AgHostError{"BROKEN BOWTIE FILE"};
+            parse_sam(s, n, b, s2);
+            if (a.tid != AG_NONE && b.tid != AG_NONE &&
+                (double)(a.send - a.sstart - a.sgap) / a.ssize >= kReadThreshold && (double)(a.tend - a.tstart - a.tgap) / (a.tend - a.tstart) >= kReadThreshold &&
+                (double)(b.send - b.sstart - b.sgap) / b.ssize >= kReadThreshold && (double)(b.tend - b.tstart - b.tgap) / (b.tend - b.tstart) >= kReadThreshold)
+                if ((long)a.sid < n_reads) hit[a.sid] = 1;
+        }
+    }
+    long aligned = 0;
+    for (char c : hit) aligned += c;
+    return aligned == 0 ? 0.0 : (double)aligned / (double)n_reads;
+}
+
+// AG:2864-3195.  `blat` runs the aligner for unit i (database tmp/_extended_contigs.i.fa, query tmp/_short_initial_contigs.i.fa,
+// output tmp/_short_initial_contigs_extended_contigs.i.psl) and returns false when both pblat and blat failed.
+void ag_refinement(const std::string& tmp, int units, const std::vector<std::string>& genome_ids, const std::vector<std::string>& contig_ids,
+                   int unique_extension, const std::string& ext_path, const std::string& rmn_path, bool (*blat)(int unit, void* user), void* user,
+                   bool write_test_files) {
+    const size_t kSmallChunk = 20000;  // SMALL_CHUNK, AG:41
+    auto load_fasta = [](const std::string& path, std::vector<std::string>& names, std::vector<std::string>& seqs) {
+        FileMap fm(path);
+        if (!fm.ok) return false;
+        Lines ln(fm.p, fm.n); const char* s; size_t n;
+        while (ln.next(s, n)) {
+            if (n == 0 || s[0] == 0) break;
+            if (s[0] == '>') { names.emplace_back(s + 1, n - 1); seqs.emplace_back(); }
+            else if (!seqs.empty()) seqs.back().append(s, n);
+        }
+        return true;
+    };
+    for (int i = 0; i < units; i++) {  // truncate the initial contigs to 20 kbp for the aligner (AG:2891-2953)
+        std::vector<std::string> names, seqs;
+        if (!load_fasta(tmp + "/_initial_contigs." + std::to_string(i) + ".fa", names, seqs)) throw AgHostError{"CANNOT OPEN FILE!"};
+        Out o(tmp + "/_short_initial_contigs." + std::to_string(i) + ".fa");
+        for (size_t j = 0; j < seqs.size(); j++) {
+            int num = ag_atoi(names[j].data(), names[j].size());
+            o.ch('>'); o.inum(num);
+            if (seqs[j].size() > kSmallChunk) { o.ch('.'); o.num(seqs[j].size()); o.ch('\n'); o.wrap60(seqs[j].substr(0, kSmallChunk)); }
+            else { o.ch('\n'); o.wrap60(seqs[j]); }
+        }
+    }
+    for (int i = 0; i < units; i++) if (!blat(i, user)) throw AgHostError{"BLAT CALL FAILED!"};
+    // original contigs regrouped from the chunks (AG:2985-3014)
+    std::vector<std::string> init;
+    {
+        FileMap fm(tmp + "/_contigs.fa");
+        if (!fm.ok) { printf("CANNOT OPEN FILE!\n"); return; }
+        Lines ln(fm.p, fm.n); const char* s; size_t n; int prev = -1;
+        while (ln.next(s, n)) {
+            if (n == 0 || s[0] == 0) break;
+            if (s[0] == '>') {
+                const char* dot = (const char*)memchr(s, '.', n);
+                int id = dot ? ag_atoi(dot + 1, (size_t)(s + n - dot - 1)) : 0;
+                if (id != prev) { init.emplace_back(); prev = id; }
+            } else if (!init.empty()) init.back().append(s, n);
+        }
+    }
+    std::vector<int> init_tags(init.size(), 0);
+    std::vector<std::vector<int>> extd_init_map;  // NOT reset between units in the reference (AG:2877, AG:3035)
+    Out e(ext_path), r(rmn_path);
+    Out* test_in = write_test_files ? new Out(std::string("in.fa")) : nullptr;
+    Out* test_ex = write_test_files ? new Out(std::string("ex.fa")) : nullptr;
+    unsigned long seq_id = 0;
+    for (int i = 0; i < units; i++) {
+        std::vector<std::string> names, extd;
+        if (!load_fasta(tmp + "/_extended_contigs." + std::to_string(i) + ".fa", names, extd)) { printf("CANNOT OPEN FILE!\n"); return; }
+        std::vector<int> extd_tags(extd.size(), 0);
+        for (size_t j = 0; j < extd.size(); j++) extd_init_map.emplace_back();
+        int target_bak = -1;
+        FileMap fm(tmp + "/_short_initial_contigs_extended_contigs." + std::to_string(i) + ".psl");
+        if (!fm.ok) { printf("CANNOT OPEN FILE!\n"); return; }
+        Lines ln(fm.p, fm.n); const char* s; size_t n;
+        PslRec p;
+        while (ln.next(s, n)) {
+            if (n == 0 || s[0] == 0) break;
+            parse_psl(s, n, p);
+            // parseBLAT's return value and targetSize (AG:501-521)
+            const char* f = s; int tab = 0; const char* fe = s + n; const char* q9 = nullptr; size_t l9 = 0; u32 tsize = 0;
+            for (const char* c = s; c <= fe; c++) {
+                if (c == fe || *c == '\t') { if (tab == 9) { q9 = f; l9 = (size_t)(c - f); } if (tab == 14) tsize = (u32)ag_atoi(f, (size_t)(c - f)); tab++; f = c + 1; }
+            }
+            u32 real_size = p.ssize;
+            if (q9) { const char* dot = (const char*)memchr(q9, '.', l9); if (dot) real_size = (u32)ag_atoi(dot + 1, (size_t)(q9 + l9 - dot - 1)); }
+            if (!((double)(p.send - p.sstart - p.sgap) / p.ssize >= 0.8 && (double)(p.tend - p.tstart - p.tgap) / (double)(p.tend - p.tstart) >= 0.8 &&
+                  tsize > real_size + 100 && real_size > tsize / 100)) continue;
+            if (p.tid >= extd_tags.size() || p.sid >= init_tags.size()) continue;  // the reference would index out of bounds
+            if (unique_extension == 1) {
+                if (init_tags[p.sid] > 0 && target_bak != -1) {
+                    if (extd_tags[target_bak] < extd_tags[p.tid]) {
+                        extd_tags[target_bak] = 0;
+                        if (!extd_init_map[target_bak].empty()) extd_init_map[target_bak].pop_back();
+                        extd_tags[p.tid] = (int)tsize; init_tags[p.sid] = 1; extd_init_map[p.tid].push_back((int)p.sid);
+                    }
+                } else { extd_tags[p.tid] = (int)tsize; init_tags[p.sid] = 1; extd_init_map[p.tid].push_back((int)p.sid); }
+                target_bak = (int)p.tid;
+            } else { extd_tags[p.tid] = 1; init_tags[p.sid] = 1; extd_init_map[p.tid].push_back((int)p.sid); }
+        }
+        for (size_t j = 0; j < extd_tags.size(); j++) {
+            if (extd_tags[j] <= 0) continue;
+            // genomeIds[i] with i = unit index (AG:3102); with --part > 1 the reference reads past the vector —
+            // we stay in bounds and name the last chromosome instead of crashing
+            const std::string& gid = genome_ids.empty() ? std::string() : genome_ids[std::min<size_t>((size_t)i, genome_ids.size() - 1)];
+            e.put(">AlignGraph", 11); e.num(seq_id); e.put(" @ ", 3); e.put(gid); e.put(" : ", 3);
+            for (int c : extd_init_map[j]) { if ((size_t)c < contig_ids.size()) e.put(contig_ids[(size_t)c]); e.put(" ; ", 3); }
+            e.ch('\n');
+            if (test_ex) { test_ex->ch('>'); test_ex->inum(i); test_ex->put(": ", 2); test_ex->num(seq_id); test_ex->ch('\n'); test_ex->wrap60(extd[j]); }
+            seq_id++;
+            e.wrap60(extd[j]);
+        }
+    }
+    for (size_t i = 0; i < init_tags.size(); i++) {
+        if (init_tags[i] != 0) continue;
+        r.ch('>'); if (i < contig_ids.size()) r.put(contig_ids[i]); r.ch('\n'); r.wrap60(init[i]);
+    }
+    {
+        FileMap fm(tmp + "/_chaff.fa");
+        if (!fm.ok) { printf("CANNOT OPEN FILE!\n"); }
+        else { Lines ln(fm.p, fm.n); const char* s; size_t n; while (ln.next(s, n)) { if (n == 0 || s[0] == 0) break; r.put(s, n); r.ch('\n'); } }
+    }
+    if (test_in) for (size_t i = 0; i < init_tags.size(); i++) if (init_tags[i] == 1) { test_in->ch('>'); test_in->num(i); test_in->ch('\n'); test_in->wrap60(init[i]); }
+    delete test_in; delete test_ex;
+}

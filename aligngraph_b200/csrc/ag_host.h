@@ -54,3 +54,12 @@ void ag_scaffold(std::vector<AgContig>& contigs, const std::string& ref, const s
 void ag_formalize_contigs(const std::string& in_path, const std::string& tmp, std::vector<std::string>& contig_ids);
 int ag_formalize_genome(const std::string& in_path, const std::string& tmp, int part, std::vector<std::string>& genome_ids);
 void ag_write_file(const std::string& path, const std::string& text);
+
+// ---- CLI phases outside the hot path (drop-in compatibility) ----------------------------------------------------------------
+int ag_max_read_length(const std::string& path);                                                        // AG:3197
+long ag_formalize_reads(const std::string& in1, const std::string& in2, const std::string& tmp);        // AG:3420
+void ag_distribute_alignments(const std::string& tmp, int units);                                       // AG:3545
+double ag_check_ratio(const std::string& tmp, int units);                                               // AG:3751
+void ag_refinement(const std::string& tmp, int units, const std::vector<std::string>& genome_ids, const std::vector<std::string>& contig_ids,
+                   int unique_extension, const std::string& ext_path, const std::string& rmn_path, bool (*blat)(int unit, void* user), void* user,
+                   bool write_test_files);                                                              // AG:2864

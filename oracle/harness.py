@@ -42,6 +42,11 @@ def build_tools(with_ref=True, with_emul=True):
     for out, srcs in jobs:
         if _stale(out, srcs):
             _run([cxx, "-O2", "-std=c++17", "-o", out] + srcs)
+    for script in ("bowtie2", "bowtie2-build"):
+        dst = os.path.join(BIN, "stubs", script)
+        if _stale(dst, [os.path.join(ORACLE, "stubs", script)]):
+            shutil.copy(os.path.join(ORACLE, "stubs", script), dst)
+            os.chmod(dst, 0o755)
     blat = os.path.join(BIN, "stubs", "blat")
     if _stale(blat, [os.path.join(BIN, "stubs", "pblat")]):
         shutil.copy(os.path.join(BIN, "stubs", "pblat"), blat)
@@ -54,6 +59,11 @@ def build_tools(with_ref=True, with_emul=True):
             _run([cxx, "-O2", "-std=c++17", "-o", EMUL] + srcs)
     if with_ref and os.path.exists(REF_SRC):
         os.makedirs(REF, exist_ok=True)
+        # the binary the reference ships next to its source: the only build that survives a FRESH run here — task0/task1 have no
+        # return statement (AlignGraph.cpp:3613, 3656), which g++ 13 turns into a trap; --resume never calls them
+        shipped = os.path.join(os.path.dirname(REF_SRC), "AlignGraph")
+        if os.path.exists(shipped) and _stale(os.path.join(REF, "AlignGraph_shipped"), [shipped]):
+            shutil.copy(shipped, os.path.join(REF, "AlignGraph_shipped"))
         for name, flags in (("AlignGraph", []), ("AlignGraph_O2", ["-O2"])):
             out = os.path.join(REF, name)
             if _stale(out, [REF_SRC]):
@@ -114,6 +124,40 @@ def run_reference(work_dir, optimized=True, timeout=3600):
     with open(os.path.join(work_dir, "tmp", "_checkpoint.txt"), "w") as f:
         f.write("0\n")
     r = subprocess.run([exe, "--resume"], cwd=work_dir, env=env, capture_output=True, text=True, timeout=timeout)
+    return r.returncode, r.stdout
+
+
+def stub_env():
+    env = dict(os.environ)
+    env["PATH"] = os.path.join(BIN, "stubs") + os.pathsep + env["PATH"]
+    return env
+
+
+def fresh_args(work_dir):
+    """argv of a fresh (non --resume) run equivalent to the generator's tmp/_command.txt."""
+    with open(os.path.join(work_dir, "tmp", "_command.txt")) as f:
+        return [l.rstrip("\n") for l in f if l.strip()]
+
+
+def prepare_fresh(work_dir):
+    """Turn a generated work directory into the starting point of a FRESH run: keep only the four user inputs plus the truth SAM the
+    stub bowtie2 replays (all units concatenated in unit order; distributeAlignments, AlignGraph.cpp:3545, splits it again)."""
+    tmp = os.path.join(work_dir, "tmp")
+    n = 0
+    parts = []
+    while os.path.exists(os.path.join(tmp, f"_reads_genome.{n}.bowtie")):
+        parts.append(open(os.path.join(tmp, f"_reads_genome.{n}.bowtie"), "rb").read())
+        n += 1
+    args = fresh_args(work_dir)
+    shutil.rmtree(tmp)
+    os.makedirs(tmp)
+    with open(os.path.join(tmp, "_truth.sam"), "wb") as f:
+        f.write(b"".join(parts))
+    return args
+
+
+def run_fresh(exe, work_dir, args, timeout=3600):
+    r = subprocess.run([exe] + args, cwd=work_dir, env=stub_env(), capture_output=True, text=True, timeout=timeout)
     return r.returncode, r.stdout
 
 

@@ -34,3 +34,24 @@ for name, params in cases.GOLDEN.items():
         f.write(f"reference exit code {rc}; units {n}; agsynth params {params}\n")
     print(name, "units", n, "reference exit", rc)
     shutil.rmtree(work)
+
+# a FRESH run (no --resume) of the reference AS SHIPPED (prebuilt binary; a g++-13 build traps in task0/task1) with the stub aligners: exercises formalizeInput for reads, distributeAlignments,
+# the aligner command lines and refinement; final FASTA only
+for name in ("plain", "two_chr"):
+    work = tempfile.mkdtemp(prefix="ag_golden_")
+    harness.synth(work, **cases.GOLDEN[name])
+    args = harness.prepare_fresh(work)
+    rc, out = harness.run_fresh(os.path.join(harness.REF, "AlignGraph_shipped"), work, args)
+    dst = os.path.join(ROOT, "tests", "golden", name + "_fresh")
+    shutil.rmtree(dst, ignore_errors=True)
+    os.makedirs(dst)
+    for extra in ("extendedContigs.fa", "remainingContigs.fa"):
+        shutil.copy(os.path.join(work, extra), dst)
+    n = harness.n_units(work)
+    for u in range(n):
+        for pat in harness.UNIT_FILES:
+            shutil.copy(os.path.join(work, "tmp", pat.format(u)), dst)
+    with open(os.path.join(dst, "README.txt"), "w") as f:
+        f.write(f"fresh run (stub bowtie2/pblat), reference exit code {rc}; stdout tail: {out[-200:]!r}\n")
+    print(name + "_fresh", "reference exit", rc, "ext bytes", os.path.getsize(os.path.join(dst, "extendedContigs.fa")))
+    shutil.rmtree(work)

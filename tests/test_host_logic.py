@@ -1,0 +1,75 @@
+"""Host-side logic on CPU: unit scheduling across ranks (world_size 2, gloo), packed-read round trip, batch-boundary quirk."""
+import os
+import subprocess
+import sys
+import textwrap
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_unit_partition_two_ranks_gloo(tmp_path):
+    """bench.py / the CLI farm unit u to rank u mod world; every unit is owned exactly once and the packed read buffer
+    broadcast from rank 0 arrives bit-identical (gloo stands in for NCCL on CPU)."""
+    script = tmp_path / "w.py"
+    script.write_text(textwrap.dedent("""
+        import os, sys, torch, torch.distributed as dist
+        sys.path.insert(0, %r)
+        dist.init_process_group("gloo")
+        rank, world = dist.get_rank(), dist.get_world_size()
+        units = 5
+        mine = [u for u in range(units) if u %% world == rank]
+        got = [None] * world
+        dist.all_gather_object(got, mine)
+        flat = sorted(u for g in got for u in g)
+        assert flat == list(range(units)), flat
+        # one broadcast of the packed read buffer from rank 0
+        g = torch.Generator().manual_seed(7)
+        buf = torch.randint(-2**31, 2**31 - 1, (4096,), dtype=torch.int32, generator=g) if rank == 0 else torch.empty(4096, dtype=torch.int32)
+        ref = torch.randint(-2**31, 2**31 - 1, (4096,), dtype=torch.int32, generator=torch.Generator().manual_seed(7))
+        dist.broadcast(buf, src=0)
+        assert torch.equal(buf, ref)
+        # max-over-ranks timing reduction used by bench.py
+        t = torch.tensor([float(rank + 1)], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        assert t.item() == float(world)
+        dist.destroy_process_group()
+        print("ok", rank)
+    """ % ROOT))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29531", str(script)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("ok") == 2
+
+
+def test_batch_boundary_drops_one_record(harness, workdir):
+    """AlignGraph.cpp:1259 consumes and loses the first record pair beyond each 1,000,000-pair batch.  A SAM whose read ids start at
+    999,998 crosses the boundary: the emulation (product host parser) and the oracle must agree on what survives."""
+    import shutil
+    import cases
+    base = os.path.join(workdir, "a")
+    harness.synth(base, genome_bp=20000, coverage=40, seed=21, contig_len=3000)
+    tmp = os.path.join(base, "tmp")
+    shift = 999_900
+    # renumber: prepend `shift` dummy unaligned pairs of the same read length to the read file, shift the SAM ids
+    reads = open(os.path.join(tmp, "_reads.fa")).read().split("\n")
+    rl = len(reads[1])
+    with open(os.path.join(tmp, "_reads.fa"), "w") as f:
+        for i in range(shift):
+            f.write(f">{i}\n{'A' * rl}\n>{i}\n{'C' * rl}\n")
+        for i in range(0, len(reads) - 1, 2):
+            pid = int(reads[i][1:]) + shift
+            f.write(f">{pid}\n{reads[i + 1]}\n")
+    sam = open(os.path.join(tmp, "_reads_genome.0.bowtie")).read().split("\n")
+    with open(os.path.join(tmp, "_reads_genome.0.bowtie"), "w") as f:
+        for line in sam:
+            if not line:
+                continue
+            fields = line.split("\t")
+            fields[0] = str(int(fields[0]) + shift)
+            f.write("\t".join(fields) + "\n")
+    other = os.path.join(workdir, "b")
+    shutil.copytree(base, other)
+    harness.run_oracle(base)
+    harness.run_emul(other)
+    assert harness.unit_outputs(base, 0) == harness.unit_outputs(other, 0)
+    # and the boundary matters: dropping is visible in the oracle's event count vs. an unshifted run is not asserted here, only parity
