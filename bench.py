@@ -228,13 +228,12 @@ def b200_arm(args):
             meta[0] = (npairs, s2, sm)
         dist.broadcast_object_list(meta, src=0)
         npairs, s2, sm = meta[0]
-        shapes = [(2 * npairs * s2, torch.int32), (2 * npairs * sm, torch.int32), (npairs, torch.int16)]
+        nbytes_each = [2 * npairs * s2 * 4, 2 * npairs * sm * 4, npairs * 2]  # byte buffers: NCCL has no 16-bit integer type
         if rank == 0:
-            host = [np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ct)), shape=(cnt,)) for p, (cnt, _), ct in
-                    zip((b, m, l), shapes, (ctypes.c_int32, ctypes.c_int32, ctypes.c_int16))]
+            host = [np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint8)), shape=(cnt,)) for p, cnt in zip((b, m, l), nbytes_each)]
             dev = [torch.from_numpy(h).cuda() for h in host]
         else:
-            dev = [torch.empty(cnt, dtype=dt, device="cuda") for cnt, dt in shapes]
+            dev = [torch.empty(cnt, dtype=torch.uint8, device="cuda") for cnt in nbytes_each]
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
