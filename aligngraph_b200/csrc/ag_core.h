@@ -175,6 +175,43 @@ AG_HD ag_touch ag_locate(const ag_alnp& p, const ag_seg* ext, u32 q, u32 k) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
+// fast path: both mates are a single M segment (every CIGAR of the form [S]M[S]) — by far the common case.  All touch arithmetic
+// collapses to adds and unsigned range checks in unit-position space; computed once per (tile, alignment) when the tile's chunk is
+// staged in shared memory.
+// ---------------------------------------------------------------------------------------------------------------------------
+struct ag_fast {
+    u32 lo, span;        // touched positions [lo, lo + span]; for a simple alignment span == number of calls
+    u32 lsrc_len;        // left-mate read offset of position lo | read length << 16
+    u32 mlo, mlen;       // the right mate covers positions q with (q - mlo) < mlen ...
+    u32 mdelta;          // ... where the mate position is q + mdelta            (all modulo 2^32, like the reference's unsigned math)
+    u32 read;            // (read index << 1) | rc of the left mate
+    u32 simple;          // 1: fast path valid; 0: use ag_locate on the prepared record
+};
+
+AG_HD ag_fast ag_fast_prep(const ag_alnp& p, u32 lo, u32 span) {
+    ag_fast f;
+    f.lo = lo; f.span = span; f.read = p.left_read;
+    u32 len = p.len_nseg & 0xFFFFu;
+    f.simple = (((p.len_nseg >> 16) & 0xFF) == 1 && ((p.len_nseg >> 24) & 0xFF) == 1) ? 1u : 0u;
+    u32 lsrc = p.l_sl & 0xFFFFu, rsrc = p.r_sl & 0xFFFFu;
+    f.lsrc_len = lsrc | (len << 16);
+    f.mlo = lo + rsrc - lsrc; f.mlen = p.r_sl >> 16; f.mdelta = p.r_dst - f.mlo;
+    return f;
+}
+
+// touch of a simple alignment at position q; requires q - f.lo <= f.span
+AG_HD ag_touch ag_fast_touch(const ag_fast& f, u32 q, u32 k) {
+    ag_touch t;
+    u32 d = q - f.lo, len = f.lsrc_len >> 16, a = (f.lsrc_len & 0xFFFFu) + d;
+    t.kind = d < f.span ? 1 : 2;
+    t.soff = a; t.slen = t.kind == 1 ? k : ag_min_u32(k, len - a);
+    t.mate = (q - f.mlo < f.mlen) ? q + f.mdelta : AG_NONE;
+    t.npos = q + 1; t.nsoff = a + 1; t.nslen = ag_min_u32(k, len - (a + 1));
+    t.nmate = (q + 1 - f.mlo < f.mlen) ? q + 1 + f.mdelta : AG_NONE;
+    return t;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
 // reads: 2 bits per base (A0 C1 G2 T3), 16 bases per u32, fixed stride per read; 1-bit plane marks non-ACGT characters
 // ---------------------------------------------------------------------------------------------------------------------------
 struct ag_reads {
@@ -212,6 +249,17 @@ struct ag_cmtab {
     AG_HD u32 count(u32 pos) const { return start[pos + 1] - start[pos]; }
 };
 
+// cm1[pos] = (cid, coff) of the only contiMer at pos; (NONE, NONE) when there is none; (AG_CM_MANY, count) when there are several
+// (then the CSR has to be walked).  One 8-byte load per mate lookup instead of three dependent ones.
+#define AG_CM_MANY 0xFFFFFFFEu
+struct ag_cm1 { u32 cid, coff; };
+AG_HD ag_cm1 ag_make_cm1(const ag_cmtab& t, u32 pos) {
+    u32 a = t.start[pos], n = t.start[pos + 1] - a;
+    ag_cm1 r;
+    if (n == 0) { r.cid = r.coff = AG_NONE; } else if (n == 1) { r.cid = t.cm[a].cid; r.coff = t.cm[a].coff; } else { r.cid = AG_CM_MANY; r.coff = n; }
+    return r;
+}
+
 // Enumerate the candidates of a touch at `pos` with mate position `mate` in the reference's order: contiMers at pos (outer) x
 // contiMers at the mate position (inner); an empty side contributes one "-1" entry (AG:1369-1477).
 template <class F> AG_HD void ag_for_candidates(const ag_cmtab& t, u32 pos, u32 mate, F f) {
@@ -234,40 +282,55 @@ template <class F> AG_HD void ag_for_candidates(const ag_cmtab& t, u32 pos, u32 
 #define AG_NODE_CAP 6
 struct ag_ovfpool { ag_nodeb* node; u32* next; u32* count; u32 cap; int* err; };
 
-struct ag_nodelist {
-    ag_nodeb loc[AG_NODE_CAP];
-    u32 n, ovf_head, ovf_tail;
-    AG_HD void init() { n = 0; ovf_head = ovf_tail = AG_NONE; }
-};
-
 AG_HD bool ag_compat_b(const ag_nodem& c, const ag_nodeb& y, int iv) {
     ag_nodem m; m.cid = y.cid; m.coff = y.coff; m.cid0 = y.cid0; m.coff0 = y.coff0; m.moff = y.moff;
     return ag_compatible(c, m, iv);
 }
 
-// One candidate of one touch: first-compatible lookup, bump or create  (AG:1375-1389 / AG:1493-1506)
-AG_HD void ag_node_touch(ag_nodelist& nl, const ag_ovfpool& pool, const ag_nodem& c, bool bump, int code, u32 sread, u32 soff_len, int iv) {
-    ag_nodeb* hit = 0;
-    u32 nloc = nl.n < AG_NODE_CAP ? nl.n : AG_NODE_CAP;
-    for (u32 i = 0; i < nloc; i++) if (ag_compat_b(c, nl.loc[i], iv)) { hit = &nl.loc[i]; break; }
-    if (!hit && nl.n > AG_NODE_CAP)
-        for (u32 o = nl.ovf_head; o != AG_NONE; o = pool.next[o]) if (ag_compat_b(c, pool.node[o], iv)) { hit = &pool.node[o]; break; }
-    if (!hit) {
-        if (nl.n < AG_NODE_CAP) hit = &nl.loc[nl.n];
-        else {
-            u32 o = AG_ATOMIC_ADD(pool.count, 1u);
-            if (o >= pool.cap) { *pool.err = 1; return; }
-            pool.next[o] = AG_NONE;
-            if (nl.ovf_tail == AG_NONE) nl.ovf_head = o; else pool.next[nl.ovf_tail] = o;
-            nl.ovf_tail = o;
-            hit = &pool.node[o];
-        }
-        nl.n++;
-        hit->cid = c.cid; hit->coff = c.coff; hit->cid0 = c.cid0; hit->coff0 = c.coff0; hit->moff = c.moff;
-        hit->cov = 0; hit->cnt[0] = hit->cnt[1] = hit->cnt[2] = hit->cnt[3] = hit->cnt[4] = 0;
-        hit->sread = sread; hit->soff_len = soff_len;
+// Strided view of a position's node list: field f of node i lives at base[f * fstride + i * nstride].  On the device the first
+// `cap` nodes of every position sit in shared memory as [field][node][thread] (conflict-free); the host emulation / generic code
+// uses the same accessors over an array of ag_nodeb (fstride 1, nstride 13).  Nodes beyond `cap` go to a global overflow pool.
+struct ag_nview {
+    u32* base; u32 fstride, nstride, cap;
+    u32 n, ovf_head, ovf_tail;
+    AG_HD void init(u32* b, u32 fs, u32 ns, u32 c) { base = b; fstride = fs; nstride = ns; cap = c; n = 0; ovf_head = ovf_tail = AG_NONE; }
+    AG_HD u32& f(u32 field, u32 i) const { return base[field * fstride + i * nstride]; }
+    AG_HD ag_nodem match(u32 i) const { ag_nodem m; m.cid = f(0, i); m.coff = f(1, i); m.cid0 = f(2, i); m.coff0 = f(3, i); m.moff = f(4, i); return m; }
+    AG_HD ag_nodeb get(u32 i) const {
+        ag_nodeb b; b.cid = f(0, i); b.coff = f(1, i); b.cid0 = f(2, i); b.coff0 = f(3, i); b.moff = f(4, i); b.cov = f(5, i);
+        for (u32 j = 0; j < 5; j++) b.cnt[j] = f(6 + j, i);
+        b.sread = f(11, i); b.soff_len = f(12, i);
+        return b;
     }
-    if (bump) { hit->cov++; if (code >= 0) hit->cnt[code]++; }
+};
+
+// One candidate of one touch: first-compatible lookup, bump or create  (AG:1375-1389 / AG:1493-1506)
+AG_HD void ag_node_touch_v(ag_nview& nl, const ag_ovfpool& pool, const ag_nodem& c, bool bump, int code, u32 sread, u32 soff_len, int iv) {
+    u32 nloc = nl.n < nl.cap ? nl.n : nl.cap;
+    for (u32 i = 0; i < nloc; i++)
+        if (ag_compatible(c, nl.match(i), iv)) { if (bump) { nl.f(5, i)++; if (code >= 0) nl.f(6 + (u32)code, i)++; } return; }
+    if (nl.n > nl.cap)
+        for (u32 o = nl.ovf_head; o != AG_NONE; o = pool.next[o])
+            if (ag_compat_b(c, pool.node[o], iv)) { if (bump) { pool.node[o].cov++; if (code >= 0) pool.node[o].cnt[code]++; } return; }
+    if (nl.n < nl.cap) {
+        u32 i = nl.n;
+        nl.f(0, i) = c.cid; nl.f(1, i) = c.coff; nl.f(2, i) = c.cid0; nl.f(3, i) = c.coff0; nl.f(4, i) = c.moff;
+        nl.f(5, i) = bump ? 1u : 0u;
+        for (u32 j = 0; j < 5; j++) nl.f(6 + j, i) = (bump && code == (int)j) ? 1u : 0u;
+        nl.f(11, i) = sread; nl.f(12, i) = soff_len;
+    } else {
+        u32 o = AG_ATOMIC_ADD(pool.count, 1u);
+        if (o >= pool.cap) { *pool.err = 1; return; }
+        pool.next[o] = AG_NONE;
+        if (nl.ovf_tail == AG_NONE) nl.ovf_head = o; else pool.next[nl.ovf_tail] = o;
+        nl.ovf_tail = o;
+        ag_nodeb* h = &pool.node[o];
+        h->cid = c.cid; h->coff = c.coff; h->cid0 = c.cid0; h->coff0 = c.coff0; h->moff = c.moff;
+        h->cov = bump ? 1u : 0u;
+        for (u32 j = 0; j < 5; j++) h->cnt[j] = (bump && code == (int)j) ? 1u : 0u;
+        h->sread = sread; h->soff_len = soff_len;
+    }
+    nl.n++;
 }
 
 // first node of a FINAL list compatible with candidate c
@@ -291,7 +354,7 @@ AG_HD char ag_consensus(const u32* cnt, char refbase) {
 // extension walk (AG:1954-2204) on the final table
 // ---------------------------------------------------------------------------------------------------------------------------
 struct ag_walkctx {
-    const ag_nodew* nw;       // per node
+    ag_nodew* nw;             // per node; misc carries the traversed / detour marks
     const u32* node_pos;      // node -> unit position
     const u32* pos_node;      // CSR position -> first node index (n_pos + 1)
     const u32* ovf_head;      // per node: head of overflow successor list (valid when misc & AG_NW_OVF)
@@ -299,52 +362,59 @@ struct ag_walkctx {
     const u32* ovf_next;
     ag_cmtab cmt;
     const u32* chain_pos;     // chain-major: unit position of every contiMer
-    unsigned char* trav;      // per node: bit0 traversed, bit1 "left through a contiMer detour"
     u32* walk_next;           // per node: next node of the walk that marked it, or NONE
 };
 
-// count the untraversed successors of node v; returns the count, `pick` = the last one seen (AG:2020-2032)
-AG_HD u32 ag_live_succ(const ag_walkctx& w, u32 v, u32& pick) {
-    const ag_nodew nd = w.nw[v];
+// untraversed successors of node v (record `nd` already loaded): count, `pick` = the last one seen, `prec` = its record (AG:2020-2032)
+AG_HD u32 ag_live_succ(const ag_walkctx& w, u32 v, const ag_nodew& nd, u32& pick, ag_nodew& prec) {
     u32 cnt = 0; pick = AG_NONE;
-    if (nd.succ0 != AG_NONE && !(w.trav[nd.succ0] & 1)) { cnt++; pick = nd.succ0; }
-    if (nd.succ1 != AG_NONE && !(w.trav[nd.succ1] & 1)) { cnt++; pick = nd.succ1; }
+    ag_nodew s0, s1;
+    if (nd.succ0 != AG_NONE) s0 = w.nw[nd.succ0];
+    if (nd.succ1 != AG_NONE) s1 = w.nw[nd.succ1];
+    if (nd.succ0 != AG_NONE && !(s0.misc & AG_NW_TRAV)) { cnt++; pick = nd.succ0; prec = s0; }
+    if (nd.succ1 != AG_NONE && !(s1.misc & AG_NW_TRAV)) { cnt++; pick = nd.succ1; prec = s1; }
     if (nd.misc & AG_NW_OVF)
-        for (u32 o = w.ovf_head[v]; o != AG_NONE; o = w.ovf_next[o]) { u32 s = w.ovf_target[o]; if (!(w.trav[s] & 1)) { cnt++; pick = s; } }
+        for (u32 o = w.ovf_head[v]; o != AG_NONE; o = w.ovf_next[o]) {
+            u32 s = w.ovf_target[o]; ag_nodew r = w.nw[s];
+            if (!(r.misc & AG_NW_TRAV)) { cnt++; pick = s; prec = r; }
+        }
     return cnt;
 }
 
-// Simulate the walk that starts at untraversed node `start`.  Marks nodes, records the path in walk_next / trav bit1.
+// Simulate the walk that starts at untraversed node `start`.  Marks nodes, records the path in walk_next / the detour bit.
 AG_HD ag_walk ag_walk_from(const ag_walkctx& w, u32 start) {
     ag_walk r;
-    r.start_node = start; r.soff = w.node_pos[start]; r.soff0 = w.nw[start].moff;
+    ag_nodew cur = w.nw[start];
+    r.start_node = start; r.soff = w.node_pos[start]; r.soff0 = cur.moff;
     u32 v = start, len = 0, ext = 0;
     for (;;) {
         // kMerTag == 1 step on an untraversed node (AG:1997-2060)
         len++;
-        if (w.nw[v].misc & AG_NW_HASCONTIG) ext = 1;
-        w.trav[v] = 1;
-        u32 pick, cnt = ag_live_succ(w, v, pick);
-        if (cnt == 1) { w.walk_next[v] = pick; v = pick; continue; }
+        if (cur.misc & AG_NW_HASCONTIG) ext = 1;
+        cur.misc |= AG_NW_TRAV;
+        w.nw[v].misc = cur.misc;
+        u32 pick; ag_nodew prec;
+        u32 cnt = ag_live_succ(w, v, cur, pick, prec);
+        if (cnt == 1) { w.walk_next[v] = pick; v = pick; cur = prec; continue; }
         u32 p = w.node_pos[v];
         u32 c0 = w.cmt.start[p];
         if (w.cmt.start[p + 1] - c0 == 1 && w.cmt.cm[c0].chain != w.cmt.cm[c0].term) {
             // switch to the contiMer thread (AG:2047-2057), run to its terminal (AG:2064-2072), try to re-enter (AG:2093-2136)
             ag_cm m = w.cmt.cm[c0];
             len += m.term - m.chain; ext = 1;
-            w.trav[v] = 3;
+            w.nw[v].misc = cur.misc | AG_NW_DETOUR;
             u32 z = w.chain_pos[m.term];
-            u32 live = 0, item = AG_NONE;
-            for (u32 x = w.pos_node[z]; x < w.pos_node[z + 1]; x++) if (!(w.trav[x] & 1)) { live++; item = x; }
-            u32 pick2 = AG_NONE, cnt2 = 0;
-            if (live == 1) cnt2 = ag_live_succ(w, item, pick2);
-            if (cnt2 == 1) { w.walk_next[v] = pick2; v = pick2; continue; }
+            u32 live = 0, item = AG_NONE; ag_nodew irec;
+            for (u32 x = w.pos_node[z]; x < w.pos_node[z + 1]; x++) { ag_nodew xr = w.nw[x]; if (!(xr.misc & AG_NW_TRAV)) { live++; item = x; irec = xr; } }
+            u32 pick2 = AG_NONE, cnt2 = 0; ag_nodew prec2;
+            if (live == 1) cnt2 = ag_live_succ(w, item, irec, pick2, prec2);
+            if (cnt2 == 1) { w.walk_next[v] = pick2; v = pick2; cur = prec2; continue; }
             w.walk_next[v] = AG_NONE;
             r.eoff = z; r.eoff0 = AG_NONE; r.flags = ext | (1u << 1);  // kMerTag -2
             break;
         }
         w.walk_next[v] = AG_NONE;
-        r.eoff = p; r.eoff0 = w.nw[v].moff; r.flags = ext | (0u << 1);  // kMerTag -1
+        r.eoff = p; r.eoff0 = cur.moff; r.flags = ext | (0u << 1);  // kMerTag -1
         break;
     }
     r.len = len; r.last_node = v;

@@ -145,7 +145,7 @@ __global__ void k_rs_scatter(const u32* __restrict__ keys, const u32* __restrict
 struct DevView {
     ag_reads reads;
     const unsigned char* ref; u32 n_ref, n_pos;
-    ag_cmtab cmt; const u32* chain_pos; const unsigned char* chain_base;
+    ag_cmtab cmt; const ag_cm1* cm1; const u32* chain_pos; const unsigned char* chain_base;
     const ag_aln* aln; u32 n_aln; const ag_seg* ext;
     ag_alnp* alnp; u32* lo; u32* span; u32* ntiles; u32* key_off;
     u32* keys; u32* vals; u32* tile_cnt; u32* tile_start; u32 n_tiles;
@@ -154,8 +154,8 @@ struct DevView {
     u32* pos_cnt; u32* pos_pool; u32* pos_node;
     ag_nodem* node_m; ag_nodew* node_w; u32* node_sref; u32* node_pos;
     u32* eovf_head; u32* eovf_target; u32* eovf_next; u32* eovf_count; u32 eovf_cap;
-    unsigned char* trav; u32* walk_next; u32* parent; u32* cmin; u32* cmax;
-    ag_walk* walks; u32* walk_count; u32 walk_cap;
+    u32* walk_next; u32* parent; u32* cmin; u32* cmax;
+    ag_walk* walks; ag_walk* walks_sorted; u32* walk_count; u32 walk_cap;
     int* err;
     int k, iv, coverage;
 };
@@ -189,40 +189,75 @@ __global__ void k_keys(DevView d) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
+// k_cm1: per-position summary of the contiMer table (one 8-byte load per lookup in the sweeps)
+// ---------------------------------------------------------------------------------------------------------------------------
+__global__ void k_cm1(DevView d, ag_cm1* out) {
+    u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= d.n_pos) return;
+    out[p] = ag_make_cm1(d.cmt, p);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
 // k_nodes: one CTA per tile of AG_TILE positions, one thread per position.  The tile's alignments arrive sorted by global
-// alignment index and are staged through shared memory in chunks; a thread tests each against its position and replays the
-// reference's first-compatible clustering in order.
+// alignment order; they are staged through shared memory in chunks (touch arithmetic pre-reduced to ag_fast once per tile and
+// alignment), each warp keeps only the entries that overlap its 32 positions (ballot), and every thread replays the reference's
+// first-compatible clustering on a node list held in shared memory ([field][node][thread], conflict-free).
 // ---------------------------------------------------------------------------------------------------------------------------
 constexpr int NCHUNK = 128;
+constexpr int NODE_SCAP = 4;                                   // nodes per position kept in shared memory; more spill to the pool
+constexpr int NODES_SMEM = 13 * NODE_SCAP * AG_TILE * 4;       // bytes of dynamic shared memory
+
+// one candidate when both sides have at most one contiMer (the common case), else the reference's nested enumeration
+template <class F> __device__ __forceinline__ void for_candidates_fast(const DevView& d, u32 q, const ag_cm1& ca, u32 mate, F f) {
+    ag_cm1 cb; cb.cid = cb.coff = AG_NONE;
+    if (mate != AG_NONE) cb = d.cm1[mate];
+    if (ca.cid != AG_CM_MANY && cb.cid != AG_CM_MANY) {
+        ag_nodem c; c.cid = ca.cid; c.coff = ca.coff; c.cid0 = cb.cid; c.coff0 = cb.coff; c.moff = mate;
+        f(c);
+    } else ag_for_candidates(d.cmt, q, mate, f);
+}
 
 __global__ void __launch_bounds__(AG_TILE) k_nodes(DevView d) {
-    __shared__ ag_alnp s_rec[NCHUNK];
-    __shared__ u32 s_lo[NCHUNK], s_span[NCHUNK];
+    extern __shared__ u32 s_nodes[];
+    __shared__ ag_fast s_f[NCHUNK];
+    __shared__ u32 s_idx[NCHUNK];
     __shared__ u32 s_scan[33];
     __shared__ u32 s_base;
-    const u32 tile = blockIdx.x, q = tile * AG_TILE + threadIdx.x;
+    const u32 tile = blockIdx.x, q = tile * AG_TILE + threadIdx.x, lane = threadIdx.x & 31;
     const bool active = q < d.n_ref;
-    ag_nodelist nl; nl.init();
+    const u32 wq0 = tile * AG_TILE + (threadIdx.x & ~31u);     // first position of this warp
+    ag_nview nl; nl.init(s_nodes + threadIdx.x, NODE_SCAP * AG_TILE, AG_TILE, NODE_SCAP);
+    ag_cm1 ca; ca.cid = ca.coff = AG_NONE;
+    if (active) ca = d.cm1[q];
     const u32 kb = d.tile_start[tile], ke = d.tile_start[tile + 1];
     for (u32 c0 = kb; c0 < ke; c0 += NCHUNK) {
-        u32 cn = min((u32)NCHUNK, ke - c0);
+        const u32 cn = min((u32)NCHUNK, ke - c0);
         if (threadIdx.x < cn) {
             u32 idx = d.vals[c0 + threadIdx.x];
-            s_rec[threadIdx.x] = d.alnp[idx]; s_lo[threadIdx.x] = d.lo[idx]; s_span[threadIdx.x] = d.span[idx];
+            s_idx[threadIdx.x] = idx;
+            s_f[threadIdx.x] = ag_fast_prep(d.alnp[idx], d.lo[idx], d.span[idx]);
         }
         __syncthreads();
-        if (active)
-            for (u32 a = 0; a < cn; a++) {
-                if (q - s_lo[a] > s_span[a]) continue;
-                const ag_alnp p = s_rec[a];
-                ag_touch t = ag_locate(p, d.ext, q, (u32)d.k);
-                if (!t.kind) continue;
+        for (u32 r0 = 0; r0 < cn; r0 += 32) {
+            // which of these 32 entries touch any of the warp's 32 positions?
+            bool ov = false;
+            if (r0 + lane < cn) { u32 lo = s_f[r0 + lane].lo; ov = lo <= wq0 + 31 && lo + s_f[r0 + lane].span >= wq0; }
+            u32 mask = __ballot_sync(0xFFFFFFFFu, ov);
+            while (mask) {
+                const u32 a = r0 + (u32)__ffs((int)mask) - 1;
+                mask &= mask - 1;
+                const ag_fast f = s_f[a];
+                if (!active || q - f.lo > f.span) continue;
+                ag_touch t;
+                if (f.simple) t = ag_fast_touch(f, q, (u32)d.k);
+                else { t = ag_locate(d.alnp[s_idx[a]], d.ext, q, (u32)d.k); if (!t.kind) continue; }
                 int code = -1;
-                if (t.kind == 1 && t.slen) code = d.reads.code(p.left_read, p.len_nseg & 0xFFFFu, t.soff);
-                const u32 sref = p.left_read, sl = t.soff | (t.slen << 16);
+                if (t.kind == 1 && t.slen) code = d.reads.code(f.read, f.lsrc_len >> 16, t.soff);
+                const u32 sl = t.soff | (t.slen << 16);
                 const bool bump = t.kind == 1;
-                ag_for_candidates(d.cmt, q, t.mate, [&](const ag_nodem& c) { ag_node_touch(nl, d.ovf, c, bump, code, sref, sl, d.iv); });
+                for_candidates_fast(d, q, ca, t.mate, [&](const ag_nodem& c) { ag_node_touch_v(nl, d.ovf, c, bump, code, f.read, sl, d.iv); });
             }
+        }
         __syncthreads();
     }
     // write the tile's nodes to the pool (tile order in the pool is arbitrary; k_finalize restores position order)
@@ -238,9 +273,9 @@ __global__ void __launch_bounds__(AG_TILE) k_nodes(DevView d) {
     if (s_base == AG_NONE) { d.pos_pool[q] = 0; return; }
     u32 w = s_base + ex;
     d.pos_pool[q] = w;
-    u32 nloc = nl.n < AG_NODE_CAP ? nl.n : AG_NODE_CAP;
-    for (u32 i = 0; i < nloc; i++) d.pool[w++] = nl.loc[i];
-    if (nl.n > AG_NODE_CAP) for (u32 o = nl.ovf_head; o != AG_NONE; o = d.ovf.next[o]) d.pool[w++] = d.ovf.node[o];
+    u32 nloc = nl.n < NODE_SCAP ? nl.n : NODE_SCAP;
+    for (u32 i = 0; i < nloc; i++) d.pool[w++] = nl.get(i);
+    if (nl.n > NODE_SCAP) for (u32 o = nl.ovf_head; o != AG_NONE; o = d.ovf.next[o]) d.pool[w++] = d.ovf.node[o];
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -259,13 +294,12 @@ __global__ void k_finalize(DevView d) {
         d.node_m[dst + i] = m;
         ag_nodew w; w.succ0 = w.succ1 = AG_NONE; w.moff = b.moff;
         u32 misc = (u32)(unsigned char)ag_consensus(b.cnt, refb);
-        if (b.cid == AG_NONE && (int)b.cov < d.coverage) misc |= AG_NW_FILTERED;  // AG:1912-1915
+        if (b.cid == AG_NONE && (int)b.cov < d.coverage) misc |= AG_NW_FILTERED | AG_NW_TRAV;  // AG:1912-1915
         if (b.coff != AG_NONE) misc |= AG_NW_HASCONTIG;                           // AG:2004
         w.misc = misc;
         d.node_w[dst + i] = w;
         d.node_sref[2 * (size_t)(dst + i)] = b.sread; d.node_sref[2 * (size_t)(dst + i) + 1] = b.soff_len;
         d.node_pos[dst + i] = q;
-        d.trav[dst + i] = (misc & AG_NW_FILTERED) ? 1 : 0;
     }
 }
 
@@ -288,37 +322,54 @@ __device__ __forceinline__ void add_edge(const DevView& d, u32 v, u32 tgt) {
 }
 
 __global__ void __launch_bounds__(AG_TILE) k_edges(DevView d) {
-    __shared__ ag_alnp s_rec[NCHUNK];
-    __shared__ u32 s_lo[NCHUNK], s_span[NCHUNK];
-    const u32 tile = blockIdx.x, q = tile * AG_TILE + threadIdx.x;
-    const bool active = q < d.n_ref;
+    __shared__ ag_fast s_f[NCHUNK];
+    __shared__ u32 s_idx[NCHUNK];
+    const u32 tile = blockIdx.x, q = tile * AG_TILE + threadIdx.x, lane = threadIdx.x & 31;
+    const u32 wq0 = tile * AG_TILE + (threadIdx.x & ~31u);
     u32 nb0 = 0, nn0 = 0;
-    if (active) { nb0 = d.pos_node[q]; nn0 = d.pos_node[q + 1] - nb0; }
+    if (q < d.n_ref) { nb0 = d.pos_node[q]; nn0 = d.pos_node[q + 1] - nb0; }
+    const bool active = nn0 != 0;
+    ag_cm1 ca; ca.cid = ca.coff = AG_NONE;
+    ag_cm1 ca1 = ca;
+    if (active) { ca = d.cm1[q]; ca1 = d.cm1[q + 1]; }  // q + 1 <= n_ref < n_pos + 1 entries... guarded below
+    u32 last_v = AG_NONE, last_t = AG_NONE;               // the previous edge: most touches repeat it
     const u32 kb = d.tile_start[tile], ke = d.tile_start[tile + 1];
     for (u32 c0 = kb; c0 < ke; c0 += NCHUNK) {
-        u32 cn = min((u32)NCHUNK, ke - c0);
+        const u32 cn = min((u32)NCHUNK, ke - c0);
         if (threadIdx.x < cn) {
             u32 idx = d.vals[c0 + threadIdx.x];
-            s_rec[threadIdx.x] = d.alnp[idx]; s_lo[threadIdx.x] = d.lo[idx]; s_span[threadIdx.x] = d.span[idx];
+            s_idx[threadIdx.x] = idx;
+            s_f[threadIdx.x] = ag_fast_prep(d.alnp[idx], d.lo[idx], d.span[idx]);
         }
         __syncthreads();
-        if (active && nn0)
-            for (u32 a = 0; a < cn; a++) {
-                if (q - s_lo[a] > s_span[a]) continue;
-                ag_touch t = ag_locate(s_rec[a], d.ext, q, (u32)d.k);
-                if (t.kind != 1) continue;
+        for (u32 r0 = 0; r0 < cn; r0 += 32) {
+            bool ov = false;
+            if (r0 + lane < cn) { u32 lo = s_f[r0 + lane].lo; ov = lo <= wq0 + 31 && lo + s_f[r0 + lane].span >= wq0; }
+            u32 mask = __ballot_sync(0xFFFFFFFFu, ov);
+            while (mask) {
+                const u32 a = r0 + (u32)__ffs((int)mask) - 1;
+                mask &= mask - 1;
+                const ag_fast f = s_f[a];
+                if (!active || q - f.lo >= f.span + (f.simple ? 0u : 1u)) continue;   // simple: calls start at lo .. lo+span-1 only
+                ag_touch t;
+                if (f.simple) t = ag_fast_touch(f, q, (u32)d.k);
+                else { t = ag_locate(d.alnp[s_idx[a]], d.ext, q, (u32)d.k); if (t.kind != 1) continue; }
                 const u32 nb1 = d.pos_node[t.npos], nn1 = d.pos_node[t.npos + 1] - nb1;
-                ag_for_candidates(d.cmt, q, t.mate, [&](const ag_nodem& c) {
+                const ag_cm1 cn1 = (t.npos == q + 1) ? ca1 : d.cm1[t.npos];
+                for_candidates_fast(d, q, ca, t.mate, [&](const ag_nodem& c) {
                     u32 ci = ag_first_compatible(d.node_m + nb0, nn0, c, d.iv);
                     if (ci == AG_NONE) return;
                     const ag_nodem x = d.node_m[nb0 + ci];
-                    ag_for_candidates(d.cmt, t.npos, t.nmate, [&](const ag_nodem& c2) {
+                    for_candidates_fast(d, t.npos, cn1, t.nmate, [&](const ag_nodem& c2) {
                         u32 ni = ag_first_compatible(d.node_m + nb1, nn1, c2, d.iv);
                         if (ni == AG_NONE) return;
+                        if (nb0 + ci == last_v && nb1 + ni == last_t) return;
                         if (ag_edge_ok(x, d.node_m[nb1 + ni], d.iv)) add_edge(d, nb0 + ci, nb1 + ni);
+                        last_v = nb0 + ci; last_t = nb1 + ni;
                     });
                 });
             }
+        }
         __syncthreads();
     }
 }
@@ -388,7 +439,7 @@ __global__ void k_uf_flatten(DevView d, u32 n_nodes) {
 __device__ __forceinline__ ag_walkctx make_ctx(const DevView& d) {
     ag_walkctx w;
     w.nw = d.node_w; w.node_pos = d.node_pos; w.pos_node = d.pos_node; w.ovf_head = d.eovf_head; w.ovf_target = d.eovf_target;
-    w.ovf_next = d.eovf_next; w.cmt = d.cmt; w.chain_pos = d.chain_pos; w.trav = d.trav; w.walk_next = d.walk_next;
+    w.ovf_next = d.eovf_next; w.cmt = d.cmt; w.chain_pos = d.chain_pos; w.walk_next = d.walk_next;
     return w;
 }
 __device__ __forceinline__ void push_walk(const DevView& d, ag_walk r) {
@@ -407,10 +458,20 @@ __global__ void k_walk_components(DevView d, u32 n_nodes) {
     ag_walkctx w = make_ctx(d);
     u32 hi = d.cmax[r];
     for (u32 v = d.cmin[r]; v <= hi; v++) {
-        if (d.trav[v] & 1) continue;
+        if (d.node_w[v].misc & AG_NW_TRAV) continue;
         if (d.parent[v] != r) continue;
         push_walk(d, ag_walk_from(w, v));
     }
+}
+
+// put the walk records in scan order (= by start node): flag the start nodes, exclusive scan, scatter
+__global__ void k_walk_flag(DevView d, u32 nw, u32* flag) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nw) flag[d.walks[i].start_node] = 1;
+}
+__global__ void k_walk_scatter(DevView d, u32 nw, const u32* rank) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nw) { ag_walk r = d.walks[i]; d.walks_sorted[rank[r.start_node]] = r; }
 }
 
 // exact sequential replay including the 1000-position skip (AG:2194-2202); used only when a >100 kbp contig was emitted
@@ -420,7 +481,7 @@ __global__ void k_walk_sequential(DevView d) {
     u32 bso = AG_NONE, beo = AG_NONE, bei = AG_NONE;
     for (u32 cp = 0; cp < d.n_ref;) {
         for (u32 v = d.pos_node[cp]; v < d.pos_node[cp + 1]; v++) {
-            if (d.trav[v] & 1) continue;
+            if (d.node_w[v].misc & AG_NW_TRAV) continue;
             ag_walk r = ag_walk_from(w, v);
             push_walk(d, r);
             u32 eoff = r.eoff;
@@ -441,7 +502,7 @@ __global__ void k_materialize(DevView d, const u32* __restrict__ starts, const u
     u32 v = starts[i];
     while (v != AG_NONE) {
         *o++ = (unsigned char)(d.node_w[v].misc & 0xFF);
-        if (d.trav[v] & 2) {
+        if (d.node_w[v].misc & AG_NW_DETOUR) {
             ag_cm m = d.cmt.cm[d.cmt.start[d.node_pos[v]]];
             for (u32 e = m.chain + 1; e <= m.term; e++) *o++ = d.chain_base[e];
         }
@@ -452,7 +513,8 @@ __global__ void k_materialize(DevView d, const u32* __restrict__ starts, const u
 __global__ void k_reset_marks(DevView d, u32 n_nodes) {
     u32 v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n_nodes) return;
-    d.trav[v] = (d.node_w[v].misc & AG_NW_FILTERED) ? 1 : 0;
+    u32 m = d.node_w[v].misc & ~(AG_NW_TRAV | AG_NW_DETOUR);
+    d.node_w[v].misc = (m & AG_NW_FILTERED) ? (m | AG_NW_TRAV) : m;
     d.walk_next[v] = AG_NONE;
 }
 
@@ -492,7 +554,7 @@ struct AgDevice::Impl {
     DBuf<u32> pos_cnt, pos_pool, pos_node;
     DBuf<ag_nodem> node_m; DBuf<ag_nodew> node_w; DBuf<u32> node_sref, node_pos;
     DBuf<u32> eovf_head, eovf_target, eovf_next;
-    DBuf<unsigned char> trav; DBuf<u32> walk_next, parent, cmin, cmax; DBuf<ag_walk> walks;
+    DBuf<u32> walk_next, parent, cmin, cmax; DBuf<ag_walk> walks, walks2; DBuf<ag_cm1> cm1;
     DBuf<unsigned char> out_bases, occ; DBuf<u32> sel_start; DBuf<u64> sel_off;
     Scanner scanner;
     u32 n_tiles = 0, n_keys = 0, n_nodes = 0;
@@ -515,7 +577,7 @@ AgDevice::~AgDevice() {
     // DBuf members are plain; free what we own
     Impl& m = *m_;
     if (m.reads_owned) { m.r_bases.release(); m.r_nmask.release(); m.r_len.release(); }
-    DBuf<unsigned char>* b8[] = {&m.ref, &m.chain_base, &m.trav, &m.out_bases, &m.occ};
+    DBuf<unsigned char>* b8[] = {&m.ref, &m.chain_base, &m.out_bases, &m.occ};
     for (auto* b : b8) b->release();
     DBuf<u32>* b32[] = {&m.cm_start, &m.chain_pos, &m.lo, &m.span, &m.ntiles, &m.key_off, &m.keys, &m.vals, &m.keys2, &m.vals2, &m.hist, &m.tile_cnt,
                         &m.tile_start, &m.ovf_next, &m.counters, &m.pos_cnt, &m.pos_pool, &m.pos_node, &m.node_sref, &m.node_pos, &m.eovf_head,
@@ -523,7 +585,7 @@ AgDevice::~AgDevice() {
     for (auto* b : b32) b->release();
     for (int i = 0; i < 4; i++) m.scanner.lvl[i].release();
     m.cm.release(); m.aln.release(); m.ext.release(); m.alnp.release(); m.pool.release(); m.ovf_node.release(); m.err.release();
-    m.node_m.release(); m.node_w.release(); m.walks.release(); m.sel_off.release();
+    m.node_m.release(); m.node_w.release(); m.walks.release(); m.walks2.release(); m.cm1.release(); m.sel_off.release();
     if (m.st) cudaStreamDestroy(m.st);
     delete m_;
 }
@@ -627,6 +689,11 @@ void AgDevice::build() {
     CK(cudaMemsetAsync(m.tile_cnt.p, 0, (m.n_tiles + 1) * sizeof(u32), st));
     CK(cudaMemsetAsync(m.pos_cnt.p, 0, ((size_t)n_pos + 1) * sizeof(u32), st));
 
+    m.cm1.ensure((size_t)n_pos + 2); d.cm1 = m.cm1.p;
+    if (n_pos) { k_cm1<<<(n_pos + 255) / 256, 256, 0, st>>>(d, m.cm1.p); launches_++; }
+    static bool attr_done = false;
+    if (!attr_done) { CK(cudaFuncSetAttribute(k_nodes, cudaFuncAttributeMaxDynamicSharedMemorySize, NODES_SMEM)); attr_done = true; }
+
     // ---- prep + keys ------------------------------------------------------------------------------------------------
     {
         Timer tm(st);
@@ -671,7 +738,7 @@ void AgDevice::build() {
             m.ovf_node.ensure(m.ovf_cap); m.ovf_next.ensure(m.ovf_cap);
             d.pool = m.pool.p; d.pool_count = m.counters.p + 0; d.pool_cap = m.pool_cap;
             d.ovf.node = m.ovf_node.p; d.ovf.next = m.ovf_next.p; d.ovf.count = m.counters.p + 1; d.ovf.cap = m.ovf_cap; d.ovf.err = m.err.p;
-            if (m.n_tiles) { k_nodes<<<m.n_tiles, AG_TILE, 0, st>>>(d); launches_++; }
+            if (m.n_tiles) { k_nodes<<<m.n_tiles, AG_TILE, NODES_SMEM, st>>>(d); launches_++; }
             int err = 0;
             CK(cudaMemcpyAsync(&err, m.err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
@@ -696,9 +763,9 @@ void AgDevice::build() {
         CK(cudaStreamSynchronize(st));
         m.n_nodes = nn; t_.n_nodes = nn; t_.n_keys = m.n_keys; t_.n_tiles = m.n_tiles;
         m.node_m.ensure(nn + 1); m.node_w.ensure(nn + 1); m.node_sref.ensure(2 * (size_t)nn + 2); m.node_pos.ensure(nn + 1);
-        m.trav.ensure(nn + 1); m.eovf_head.ensure(nn + 1);
+        m.eovf_head.ensure(nn + 1);
         m.eovf_cap = std::max<u32>(1u << 18, nn / 8); m.eovf_target.ensure(m.eovf_cap); m.eovf_next.ensure(m.eovf_cap);
-        d.node_m = m.node_m.p; d.node_w = m.node_w.p; d.node_sref = m.node_sref.p; d.node_pos = m.node_pos.p; d.trav = m.trav.p;
+        d.node_m = m.node_m.p; d.node_w = m.node_w.p; d.node_sref = m.node_sref.p; d.node_pos = m.node_pos.p;
         d.eovf_head = m.eovf_head.p; d.eovf_target = m.eovf_target.p; d.eovf_next = m.eovf_next.p; d.eovf_count = m.counters.p + 2; d.eovf_cap = m.eovf_cap;
         if (n_ref) { k_finalize<<<(n_ref + 255) / 256, 256, 0, st>>>(d); launches_++; }
         t_.finalize += tm.stop();
@@ -752,9 +819,9 @@ void AgDevice::extend(std::vector<ag_walk>& walks) {
     walks.clear();
     if (!nn) return;
     m.walk_next.ensure(nn + 1); m.parent.ensure(nn + 1); m.cmin.ensure(nn + 1); m.cmax.ensure(nn + 1);
-    m.walk_cap = nn; m.walks.ensure(m.walk_cap);
+    m.walk_cap = nn; m.walks.ensure(m.walk_cap); m.walks2.ensure(m.walk_cap); m.cmin.ensure((size_t)nn + 2);
     d.walk_next = m.walk_next.p; d.parent = m.parent.p; d.cmin = m.cmin.p; d.cmax = m.cmax.p;
-    d.walks = m.walks.p; d.walk_count = m.counters.p + 3; d.walk_cap = m.walk_cap;
+    d.walks = m.walks.p; d.walks_sorted = m.walks2.p; d.walk_count = m.counters.p + 3; d.walk_cap = m.walk_cap;
     CK(cudaMemsetAsync(m.counters.p + 3, 0, sizeof(u32), st));
     walk_components();
     auto fetch = [&]() {
@@ -765,11 +832,16 @@ void AgDevice::extend(std::vector<ag_walk>& walks) {
         CK(cudaStreamSynchronize(st));
         if (err) throw AgError{"walk record buffer exhausted"};
         walks.resize(nw);
-        if (nw) CK(cudaMemcpyAsync(walks.data(), m.walks.p, (size_t)nw * sizeof(ag_walk), cudaMemcpyDeviceToHost, st));
+        if (nw) {  // records into scan order on the device (the component threads append them in arbitrary order)
+            CK(cudaMemsetAsync(m.parent.p, 0, (size_t)nn * sizeof(u32), st));
+            k_walk_flag<<<(nw + 255) / 256, 256, 0, st>>>(d, nw, m.parent.p); launches_++;
+            m.scanner.run(m.parent.p, m.cmin.p, nn, st);
+            k_walk_scatter<<<(nw + 255) / 256, 256, 0, st>>>(d, nw, m.cmin.p); launches_++;
+            CK(cudaMemcpyAsync(walks.data(), m.walks2.p, (size_t)nw * sizeof(ag_walk), cudaMemcpyDeviceToHost, st));
+        }
         CK(cudaStreamSynchronize(st));
         t_.d2h += tm.stop();
         t_.d2h_bytes += (size_t)nw * sizeof(ag_walk);
-        std::sort(walks.begin(), walks.end(), [](const ag_walk& a, const ag_walk& b) { return a.start_node < b.start_node; });
     };
     fetch();
     // the 1000-position skip of the reference's scan (AG:2194-2202) only matters once a contig longer than 100 kbp has been

@@ -63,8 +63,8 @@ struct Out {  // buffered text sink: a file, or (path empty) an in-memory string
     void put(const char* s, size_t n) { buf.insert(buf.end(), s, s + n); if (buf.size() > (1u << 20) - 256) flush(); }
     void put(const std::string& s) { put(s.data(), s.size()); }
     void ch(char c) { buf.push_back(c); if (buf.size() > (1u << 20)) flush(); }
-    void num(unsigned long v) { char t[24]; int n = snprintf(t, sizeof t, "%lu", v); put(t, (size_t)n); }
-    void inum(long v) { char t[24]; int n = snprintf(t, sizeof t, "%ld", v); put(t, (size_t)n); }
+    void num(unsigned long v) { char t[24]; int i = 24; do { t[--i] = (char)('0' + v % 10); v /= 10; } while (v); put(t + i, (size_t)(24 - i)); }
+    void inum(long v) { if (v < 0) { ch('-'); num((unsigned long)(-(v + 1)) + 1); } else num((unsigned long)v); }
     void wrap60(const std::string& s) {  // 60 columns, newline after the last base (AG:2179-2184)
         for (size_t i = 0; i < s.size(); i += 60) { put(s.data() + i, std::min<size_t>(60, s.size() - i)); ch('\n'); }
     }

@@ -61,14 +61,16 @@ struct ag_nodeb {
 };
 
 // final node record used by the edge sweep and the walk (position-ordered)
-struct ag_nodew {
+struct alignas(16) ag_nodew {
     u32 succ0, succ1;  // first two successors (global node index) or NONE
     u32 moff;          // chromosomeOffset0
-    u32 misc;          // bits 0-7 consensus base char; bit 8 filtered (AG:1912-1915); bit 9 contigOffset != -1; bit 10 has overflow edges
+    u32 misc;          // bits 0-7 consensus base char; bit 8 filtered (AG:1912-1915); bit 9 contigOffset != -1; bit 10 has overflow edges; bits 11-12 walk marks
 };
 #define AG_NW_FILTERED 0x100u
 #define AG_NW_HASCONTIG 0x200u
 #define AG_NW_OVF 0x400u
+#define AG_NW_TRAV 0x800u    /* traversed (AG:2013); set from the start on coverage-filtered nodes */
+#define AG_NW_DETOUR 0x1000u /* the walk left this node through a contiMer thread */
 
 struct ag_nodem { u32 cid, coff, cid0, coff0, moff; };  // match fields of a final node
 

@@ -17,5 +17,8 @@ LIVE = {
     "a4": dict(genome_bp=60000, coverage=60, indel=0.01, softclip=0.5, multi=0.5, seed=4, kmer=3, readlen=60, insert_mean=300, contig_len=2000),
     "deep": dict(genome_bp=20000, coverage=400, insert_sd=120, contig_len=3000, seed=5, cov=30),
     "lowcov": dict(genome_bp=50000, coverage=8, seed=6, cov=3, contig_len=8000),
+    # BASELINE configs[3] / [4] shapes at test size: 8 chromosomes 2x150 k=7; 2 chromosomes --part 4 (8 units)
+    "c4_shape": dict(genome_bp=400000, chroms=8, coverage=50, readlen=150, kmer=7, insert_mean=500, insert_sd=50, seed=31),
+    "c5_shape": dict(genome_bp=200000, chroms=2, part=4, coverage=50, readlen=150, kmer=7, seed=32, indel=0.001),
     "nocontigs": dict(genome_bp=30000, coverage=50, seed=7, contig_len=150, contig_gap=5000),
 }

@@ -24,7 +24,7 @@ public:
     std::vector<std::vector<u32>> tiles;
     std::vector<u32> pos_node, node_pos, node_sref, eovf_head, eovf_target, eovf_next, walk_next, parent;
     std::vector<ag_nodeb> nodeb;  // final order
-    std::vector<ag_nodem> node_m; std::vector<ag_nodew> node_w; std::vector<unsigned char> trav;
+    std::vector<ag_nodem> node_m; std::vector<ag_nodew> node_w; std::vector<ag_cm1> cm1;
     std::vector<ag_nodeb> ovf_node; std::vector<u32> ovf_next; u32 ovf_count = 0; int err = 0;
     u32 n_nodes = 0;
     bool fallback_used = false;
@@ -33,6 +33,15 @@ public:
     void load_unit(const AgUnitInput& i) { in = i; }
 
     ag_cmtab cmt() const { ag_cmtab t; t.start = in.cm_start; t.cm = in.cm; return t; }
+    // same single-candidate shortcut as the kernels' for_candidates_fast
+    template <class F> void for_candidates_fast(u32 q, const ag_cm1& ca, u32 mate, F f) {
+        ag_cm1 cb; cb.cid = cb.coff = AG_NONE;
+        if (mate != AG_NONE) cb = cm1[mate];
+        if (ca.cid != AG_CM_MANY && cb.cid != AG_CM_MANY && !force_generic) {
+            ag_nodem c; c.cid = ca.cid; c.coff = ca.coff; c.cid0 = cb.cid; c.coff0 = cb.coff; c.moff = mate; f(c);
+        } else ag_for_candidates(cmt(), q, mate, f);
+    }
+    bool force_generic = getenv("AG_EMUL_FORCE_GENERIC") != nullptr;
 
     void build() {
         const u32 nA = (u32)in.n_aln, n_ref = in.n_ref, n_pos = in.n_pos;
@@ -51,29 +60,34 @@ public:
         ag_cmtab ct = cmt();
         pos_node.assign((size_t)n_pos + 1, 0);
         nodeb.clear();
+        cm1.resize((size_t)n_pos + 1);
+        for (u32 p = 0; p < n_pos; p++) cm1[p] = ag_make_cm1(ct, p);
         for (u32 q = 0; q < n_ref; q++) {  // k_nodes
-            ag_nodelist nl; nl.init();
+            ag_nodeb loc[AG_NODE_CAP];
+            ag_nview nl; nl.init((u32*)loc, 1, 13, AG_NODE_CAP);
+            const ag_cm1 ca = cm1[q];
             for (u32 idx : tiles[q / AG_TILE]) {
-                if (q - lo[idx] > span[idx]) continue;
-                const ag_alnp& p = alnp[idx];
-                ag_touch t = ag_locate(p, in.ext, q, (u32)k);
-                if (!t.kind) continue;
+                const ag_fast f = ag_fast_prep(alnp[idx], lo[idx], span[idx]);
+                if (q - f.lo > f.span) continue;
+                ag_touch t;
+                if (f.simple && !force_generic) t = ag_fast_touch(f, q, (u32)k);
+                else { t = ag_locate(alnp[idx], in.ext, q, (u32)k); if (!t.kind) continue; }
                 int code = -1;
-                if (t.kind == 1 && t.slen) code = rd.code(p.left_read, p.len_nseg & 0xFFFFu, t.soff);
+                if (t.kind == 1 && t.slen) code = rd.code(f.read, f.lsrc_len >> 16, t.soff);
                 u32 sl = t.soff | (t.slen << 16);
                 bool bump = t.kind == 1;
-                ag_for_candidates(ct, q, t.mate, [&](const ag_nodem& c) { ag_node_touch(nl, pool, c, bump, code, p.left_read, sl, iv); });
+                for_candidates_fast(q, ca, t.mate, [&](const ag_nodem& c) { ag_node_touch_v(nl, pool, c, bump, code, f.read, sl, iv); });
             }
             if (err) throw AgHostError{"emul: overflow pool exhausted"};
             pos_node[q] = (u32)nodeb.size();
             u32 nloc = nl.n < AG_NODE_CAP ? nl.n : AG_NODE_CAP;
-            for (u32 i = 0; i < nloc; i++) nodeb.push_back(nl.loc[i]);
+            for (u32 i = 0; i < nloc; i++) nodeb.push_back(nl.get(i));
             if (nl.n > AG_NODE_CAP) for (u32 o = nl.ovf_head; o != AG_NONE; o = ovf_next[o]) nodeb.push_back(ovf_node[o]);
         }
         for (u32 q = n_ref; q <= n_pos; q++) pos_node[q] = (u32)nodeb.size();
         n_nodes = (u32)nodeb.size();
         // k_finalize
-        node_m.resize(n_nodes); node_w.resize(n_nodes); node_sref.resize(2 * (size_t)n_nodes); node_pos.resize(n_nodes); trav.resize(n_nodes);
+        node_m.resize(n_nodes); node_w.resize(n_nodes); node_sref.resize(2 * (size_t)n_nodes); node_pos.resize(n_nodes);
         eovf_head.assign(n_nodes, AG_NONE); eovf_target.clear(); eovf_next.clear();
         for (u32 q = 0; q < n_ref; q++)
             for (u32 v = pos_node[q]; v < pos_node[q + 1]; v++) {
@@ -81,29 +95,36 @@ public:
                 ag_nodem m; m.cid = b.cid; m.coff = b.coff; m.cid0 = b.cid0; m.coff0 = b.coff0; m.moff = b.moff; node_m[v] = m;
                 ag_nodew w; w.succ0 = w.succ1 = AG_NONE; w.moff = b.moff;
                 u32 misc = (u32)(unsigned char)ag_consensus(b.cnt, in.ref[q]);
-                if (b.cid == AG_NONE && (int)b.cov < cov) misc |= AG_NW_FILTERED;
+                if (b.cid == AG_NONE && (int)b.cov < cov) misc |= AG_NW_FILTERED | AG_NW_TRAV;
                 if (b.coff != AG_NONE) misc |= AG_NW_HASCONTIG;
                 w.misc = misc; node_w[v] = w;
                 node_sref[2 * (size_t)v] = b.sread; node_sref[2 * (size_t)v + 1] = b.soff_len; node_pos[v] = q;
-                trav[v] = (misc & AG_NW_FILTERED) ? 1 : 0;
             }
         // k_edges
         for (u32 q = 0; q < n_ref; q++) {
             u32 nb0 = pos_node[q], nn0 = pos_node[q + 1] - nb0;
             if (!nn0) continue;
+            const ag_cm1 ca = cm1[q];
+            u32 last_v = AG_NONE, last_t = AG_NONE;
             for (u32 idx : tiles[q / AG_TILE]) {
-                if (q - lo[idx] > span[idx]) continue;
-                ag_touch t = ag_locate(alnp[idx], in.ext, q, (u32)k);
-                if (t.kind != 1) continue;
+                const ag_fast f = ag_fast_prep(alnp[idx], lo[idx], span[idx]);
+                bool simple = f.simple && !force_generic;
+                if (q - f.lo >= f.span + (simple ? 0u : 1u)) continue;
+                ag_touch t;
+                if (simple) t = ag_fast_touch(f, q, (u32)k);
+                else { t = ag_locate(alnp[idx], in.ext, q, (u32)k); if (t.kind != 1) continue; }
                 u32 nb1 = pos_node[t.npos], nn1 = pos_node[t.npos + 1] - nb1;
-                ag_for_candidates(ct, q, t.mate, [&](const ag_nodem& c) {
+                const ag_cm1 cn1 = cm1[t.npos];
+                for_candidates_fast(q, ca, t.mate, [&](const ag_nodem& c) {
                     u32 ci = ag_first_compatible(node_m.data() + nb0, nn0, c, iv);
                     if (ci == AG_NONE) return;
                     const ag_nodem x = node_m[nb0 + ci];
-                    ag_for_candidates(ct, t.npos, t.nmate, [&](const ag_nodem& c2) {
+                    for_candidates_fast(t.npos, cn1, t.nmate, [&](const ag_nodem& c2) {
                         u32 ni = ag_first_compatible(node_m.data() + nb1, nn1, c2, iv);
                         if (ni == AG_NONE) return;
+                        if (nb0 + ci == last_v && nb1 + ni == last_t) return;
                         if (ag_edge_ok(x, node_m[nb1 + ni], iv)) add_edge(nb0 + ci, nb1 + ni);
+                        last_v = nb0 + ci; last_t = nb1 + ni;
                     });
                 });
             }
@@ -122,7 +143,7 @@ public:
 
     ag_walkctx ctx() {
         ag_walkctx w; w.nw = node_w.data(); w.node_pos = node_pos.data(); w.pos_node = pos_node.data(); w.ovf_head = eovf_head.data();
-        w.ovf_target = eovf_target.data(); w.ovf_next = eovf_next.data(); w.cmt = cmt(); w.chain_pos = in.chain_pos; w.trav = trav.data(); w.walk_next = walk_next.data();
+        w.ovf_target = eovf_target.data(); w.ovf_next = eovf_next.data(); w.cmt = cmt(); w.chain_pos = in.chain_pos; w.walk_next = walk_next.data();
         return w;
     }
     u32 find(u32 x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; }
@@ -160,7 +181,7 @@ public:
         for (u32 r = n_nodes; r-- > 0;) {
             if (!live(r) || parent[r] != r) continue;
             for (u32 v = cmin[r]; v <= cmax[r]; v++) {
-                if (trav[v] & 1) continue;
+                if (node_w[v].misc & AG_NW_TRAV) continue;
                 if (parent[v] != r) continue;
                 ag_walk x = ag_walk_from(w, v); fill_tail(x); walks.push_back(x);
             }
@@ -178,11 +199,11 @@ public:
         if (trigger || getenv("AG_EMUL_FORCE_SEQUENTIAL")) {
             fallback_used = true;
             walks.clear();
-            for (u32 v = 0; v < n_nodes; v++) { trav[v] = live(v) ? 0 : 1; walk_next[v] = AG_NONE; }
+            for (u32 v = 0; v < n_nodes; v++) { u32 m = node_w[v].misc & ~(AG_NW_TRAV | AG_NW_DETOUR); node_w[v].misc = live(v) ? m : (m | AG_NW_TRAV); walk_next[v] = AG_NONE; }
             u32 sbo = AG_NONE, seo = AG_NONE, sei = AG_NONE;
             for (u32 cp = 0; cp < in.n_ref;) {
                 for (u32 v = pos_node[cp]; v < pos_node[cp + 1]; v++) {
-                    if (trav[v] & 1) continue;
+                    if (node_w[v].misc & AG_NW_TRAV) continue;
                     ag_walk x = ag_walk_from(w, v); fill_tail(x); walks.push_back(x);
                     u32 eoff = x.eoff;
                     if (((x.flags >> 1) & 3) != 1) eoff = eoff + (x.tail_soff_len >> 16) - 1;
@@ -204,7 +225,7 @@ public:
             size_t o = offs[i];
             for (u32 v = walks[sel[i]].start_node; v != AG_NONE; v = walk_next[v]) {
                 bases[o++] = (char)(node_w[v].misc & 0xFF);
-                if (trav[v] & 2) { ag_cm m = ct.cm[ct.start[node_pos[v]]]; for (u32 e = m.chain + 1; e <= m.term; e++) bases[o++] = in.chain_base[e]; }
+                if (node_w[v].misc & AG_NW_DETOUR) { ag_cm m = ct.cm[ct.start[node_pos[v]]]; for (u32 e = m.chain + 1; e <= m.term; e++) bases[o++] = in.chain_base[e]; }
             }
             if (o != offs[i + 1]) throw AgHostError{"emul: walk length mismatch"};
         }

@@ -39,3 +39,10 @@ def test_emulation_sequential_walk_path(harness, workdir):
     log = harness.run_emul(workdir, env={"AG_EMUL_FORCE_SEQUENTIAL": "1"})
     assert "sequential walk" in log
     compare_with_golden(harness, workdir, "mix")
+
+
+def test_emulation_generic_path_only(harness, workdir):
+    """Same result when every alignment goes through the general multi-segment locator / nested candidate enumeration."""
+    harness.synth(workdir, **cases.GOLDEN["mix"])
+    harness.run_emul(workdir, env={"AG_EMUL_FORCE_GENERIC": "1"})
+    compare_with_golden(harness, workdir, "mix")
