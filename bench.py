@@ -180,7 +180,10 @@ def b200_arm(args):
     import torch
     import torch.distributed as dist
     import aligngraph_b200 as ag
+    from aligngraph_b200 import build as _build
     from tools import synth
+    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+        _build.build()  # no-op when the in-tree library is newer than its sources
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus and world > 1:

@@ -12,6 +12,9 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # never test a stale library: rebuild (mtime check) before anything imports it
+    from aligngraph_b200 import build
+    build.build()
 
 
 @pytest.fixture(scope="session")
