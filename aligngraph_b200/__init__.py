@@ -25,7 +25,7 @@ class Params(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("ms_h2d", "ms_prep", "ms_sort", "ms_nodes", "ms_finalize", "ms_edges", "ms_components",
-                                         "ms_walk", "ms_materialize", "ms_d2h")] + \
+                                         "ms_chains", "ms_walk", "ms_materialize", "ms_d2h")] + \
                [(n, C.c_double) for n in ("s_parse", "s_device_section", "s_post")] + \
                [(n, C.c_uint64) for n in ("n_aln", "n_nodes", "n_walks", "n_emitted", "n_keys", "n_tiles", "kernel_launches",
                                           "h2d_bytes", "d2h_bytes")] + \

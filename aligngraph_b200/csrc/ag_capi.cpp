@@ -204,7 +204,7 @@ int ag_get_stats(ag_ctx* ctx, ag_stats* o) {
         const AgTimings& t = ctx->dev->timings();
         memset(o, 0, sizeof *o);
         o->ms_h2d = t.h2d; o->ms_prep = t.prep; o->ms_sort = t.sort; o->ms_nodes = t.nodes; o->ms_finalize = t.finalize; o->ms_edges = t.edges;
-        o->ms_components = t.components; o->ms_walk = t.walk; o->ms_materialize = t.materialize; o->ms_d2h = t.d2h;
+        o->ms_components = t.components; o->ms_chains = t.chains; o->ms_walk = t.walk; o->ms_materialize = t.materialize; o->ms_d2h = t.d2h;
         o->s_parse = ctx->s_parse; o->s_device_section = ctx->s_device; o->s_post = ctx->s_post;
         o->n_aln = ctx->n_aln; o->n_nodes = t.n_nodes; o->n_walks = ctx->n_walks; o->n_emitted = ctx->n_emitted; o->n_keys = t.n_keys; o->n_tiles = t.n_tiles;
         o->kernel_launches = ctx->dev->kernel_launches(); o->h2d_bytes = t.h2d_bytes; o->d2h_bytes = t.d2h_bytes; o->walk_fallback = t.walk_fallback;

@@ -363,6 +363,7 @@ struct ag_walkctx {
     ag_cmtab cmt;
     const u32* chain_pos;     // chain-major: unit position of every contiMer
     u32* walk_next;           // per node: next node of the walk that marked it, or NONE
+    const ag_chain* chain;    // forced-link chains; null = step node by node (exact sequential replay)
 };
 
 // untraversed successors of node v (record `nd` already loaded): count, `pick` = the last one seen, `prec` = its record (AG:2020-2032)
@@ -381,6 +382,22 @@ AG_HD u32 ag_live_succ(const ag_walkctx& w, u32 v, const ag_nodew& nd, u32& pick
     return cnt;
 }
 
+// Forced link u -> w: w is u's only live successor, u is w's only live predecessor, and neither sits on a position
+// that holds a terminal contiMer (where a detour can inspect nodes and jump past them, AG:2093-2136).  Then w is marked exactly
+// when u is, by the same walk, so chains of forced links can be contracted.
+AG_HD u32 ag_forced_succ(const ag_nodew* nw, const u32* ovf_head, const u32* ovf_target, const u32* ovf_next, const u32* indeg, const unsigned char* pos_term,
+                         const u32* node_pos, u32 u) {
+    const ag_nodew nd = nw[u];
+    if (nd.misc & AG_NW_FILTERED) return AG_NONE;
+    if (pos_term[node_pos[u]]) return AG_NONE;
+    u32 cnt = 0, w = AG_NONE;
+    if (nd.succ0 != AG_NONE && !(nw[nd.succ0].misc & AG_NW_FILTERED)) { cnt++; w = nd.succ0; }
+    if (nd.succ1 != AG_NONE && !(nw[nd.succ1].misc & AG_NW_FILTERED)) { cnt++; w = nd.succ1; }
+    if (nd.misc & AG_NW_OVF) for (u32 o = ovf_head[u]; o != AG_NONE; o = ovf_next[o]) if (!(nw[ovf_target[o]].misc & AG_NW_FILTERED)) { cnt++; w = ovf_target[o]; }
+    if (cnt != 1 || indeg[w] != 1 || pos_term[node_pos[w]]) return AG_NONE;
+    return w;
+}
+
 // Simulate the walk that starts at untraversed node `start`.  Marks nodes, records the path in walk_next / the detour bit.
 AG_HD ag_walk ag_walk_from(const ag_walkctx& w, u32 start) {
     ag_walk r;
@@ -393,6 +410,10 @@ AG_HD ag_walk ag_walk_from(const ag_walkctx& w, u32 start) {
         if (cur.misc & AG_NW_HASCONTIG) ext = 1;
         cur.misc |= AG_NW_TRAV;
         w.nw[v].misc = cur.misc;
+        if (w.chain) {  // a chain of forced links is marked as one: jump to its tail (interior nodes are never inspected by anyone else)
+            ag_chain c = w.chain[v];
+            if (c.tail != v) { len += c.len - 1; ext |= c.flg; v = c.tail; cur = w.nw[v]; }
+        }
         u32 pick; ag_nodew prec;
         u32 cnt = ag_live_succ(w, v, cur, pick, prec);
         if (cnt == 1) { w.walk_next[v] = pick; v = pick; cur = prec; continue; }

@@ -155,6 +155,7 @@ struct DevView {
     ag_nodem* node_m; ag_nodew* node_w; u32* node_sref; u32* node_pos;
     u32* eovf_head; u32* eovf_target; u32* eovf_next; u32* eovf_count; u32 eovf_cap;
     u32* walk_next; u32* parent; u32* cmin; u32* cmax;
+    unsigned char* pos_term; u32* indeg; u32* fnext; ag_chain* chain_a; ag_chain* chain_b; const ag_chain* chain; int* changed;
     ag_walk* walks; ag_walk* walks_sorted; u32* walk_count; u32 walk_cap;
     int* err;
     int k, iv, coverage;
@@ -191,10 +192,13 @@ __global__ void k_keys(DevView d) {
 // ---------------------------------------------------------------------------------------------------------------------------
 // k_cm1: per-position summary of the contiMer table (one 8-byte load per lookup in the sweeps)
 // ---------------------------------------------------------------------------------------------------------------------------
-__global__ void k_cm1(DevView d, ag_cm1* out) {
+__global__ void k_cm1(DevView d, ag_cm1* out, unsigned char* pos_term) {
     u32 p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= d.n_pos) return;
     out[p] = ag_make_cm1(d.cmt, p);
+    unsigned char t = 0;
+    for (u32 e = d.cmt.start[p]; e < d.cmt.start[p + 1]; e++) if (d.cmt.cm[e].chain == d.cmt.cm[e].term) t = 1;
+    pos_term[p] = t;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -439,7 +443,7 @@ __global__ void k_uf_flatten(DevView d, u32 n_nodes) {
 __device__ __forceinline__ ag_walkctx make_ctx(const DevView& d) {
     ag_walkctx w;
     w.nw = d.node_w; w.node_pos = d.node_pos; w.pos_node = d.pos_node; w.ovf_head = d.eovf_head; w.ovf_target = d.eovf_target;
-    w.ovf_next = d.eovf_next; w.cmt = d.cmt; w.chain_pos = d.chain_pos; w.walk_next = d.walk_next;
+    w.ovf_next = d.eovf_next; w.cmt = d.cmt; w.chain_pos = d.chain_pos; w.walk_next = d.walk_next; w.chain = d.chain;
     return w;
 }
 __device__ __forceinline__ void push_walk(const DevView& d, ag_walk r) {
@@ -447,6 +451,37 @@ __device__ __forceinline__ void push_walk(const DevView& d, ag_walk r) {
     if (o >= d.walk_cap) { *d.err = 5; return; }
     r.tail_sread = d.node_sref[2 * (size_t)r.last_node]; r.tail_soff_len = d.node_sref[2 * (size_t)r.last_node + 1];
     d.walks[o] = r;
+}
+
+// ---- forced-link chains: in-degrees, links, list ranking (Wyllie pointer jumping, double-buffered) ------------------------------
+__global__ void k_indeg(DevView d, u32 n_nodes) {
+    u32 v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_nodes) return;
+    ag_nodew w = d.node_w[v];
+    if (w.misc & AG_NW_FILTERED) return;
+    if (w.succ0 != AG_NONE && !(d.node_w[w.succ0].misc & AG_NW_FILTERED)) atomicAdd(&d.indeg[w.succ0], 1u);
+    if (w.succ1 != AG_NONE && !(d.node_w[w.succ1].misc & AG_NW_FILTERED)) atomicAdd(&d.indeg[w.succ1], 1u);
+    if (w.misc & AG_NW_OVF) for (u32 o = d.eovf_head[v]; o != AG_NONE; o = d.eovf_next[o]) { u32 s = d.eovf_target[o]; if (!(d.node_w[s].misc & AG_NW_FILTERED)) atomicAdd(&d.indeg[s], 1u); }
+}
+__global__ void k_links(DevView d, u32 n_nodes) {
+    u32 v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_nodes) return;
+    u32 w = ag_forced_succ(d.node_w, d.eovf_head, d.eovf_target, d.eovf_next, d.indeg, d.pos_term, d.node_pos, v);
+    d.fnext[v] = w;
+    if (w != AG_NONE) atomicOr(&d.node_w[w].misc, AG_NW_INTERIOR);
+    ag_chain c; c.jump = w; c.tail = v; c.len = 1; c.flg = (d.node_w[v].misc & AG_NW_HASCONTIG) ? 1u : 0u;
+    d.chain_a[v] = c;
+}
+__global__ void k_rank(const ag_chain* __restrict__ in, ag_chain* __restrict__ out, u32 n_nodes, int* changed) {
+    u32 v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_nodes) return;
+    ag_chain c = in[v];
+    if (c.jump != AG_NONE) {
+        ag_chain j = in[c.jump];
+        c.len += j.len; c.flg |= j.flg; c.tail = j.tail; c.jump = j.jump;
+        if (c.jump != AG_NONE) *changed = 1;
+    }
+    out[v] = c;
 }
 
 // one thread per component root: replay the scan (AG:1972-1990) restricted to the component's nodes, in node order
@@ -458,7 +493,7 @@ __global__ void k_walk_components(DevView d, u32 n_nodes) {
     ag_walkctx w = make_ctx(d);
     u32 hi = d.cmax[r];
     for (u32 v = d.cmin[r]; v <= hi; v++) {
-        if (d.node_w[v].misc & AG_NW_TRAV) continue;
+        if (d.node_w[v].misc & (AG_NW_TRAV | AG_NW_INTERIOR)) continue;
         if (d.parent[v] != r) continue;
         push_walk(d, ag_walk_from(w, v));
     }
@@ -495,7 +530,7 @@ __global__ void k_walk_sequential(DevView d) {
 }
 
 // write the bases of the selected walks (AG:1993-2002): consensus base per node, contig bases along contiMer detours
-__global__ void k_materialize(DevView d, const u32* __restrict__ starts, const u64* __restrict__ offs, u32 n, unsigned char* out) {
+__global__ void k_materialize(DevView d, const u32* __restrict__ starts, const u64* __restrict__ offs, u32 n, unsigned char* out, int use_chains) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     unsigned char* o = out + offs[i];
@@ -506,14 +541,15 @@ __global__ void k_materialize(DevView d, const u32* __restrict__ starts, const u
             ag_cm m = d.cmt.cm[d.cmt.start[d.node_pos[v]]];
             for (u32 e = m.chain + 1; e <= m.term; e++) *o++ = d.chain_base[e];
         }
-        v = d.walk_next[v];
+        u32 f = use_chains ? d.fnext[v] : AG_NONE;
+        v = f != AG_NONE ? f : d.walk_next[v];
     }
 }
 
 __global__ void k_reset_marks(DevView d, u32 n_nodes) {
     u32 v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n_nodes) return;
-    u32 m = d.node_w[v].misc & ~(AG_NW_TRAV | AG_NW_DETOUR);
+    u32 m = d.node_w[v].misc & ~(AG_NW_TRAV | AG_NW_DETOUR | AG_NW_INTERIOR);
     d.node_w[v].misc = (m & AG_NW_FILTERED) ? (m | AG_NW_TRAV) : m;
     d.walk_next[v] = AG_NONE;
 }
@@ -554,7 +590,7 @@ struct AgDevice::Impl {
     DBuf<u32> pos_cnt, pos_pool, pos_node;
     DBuf<ag_nodem> node_m; DBuf<ag_nodew> node_w; DBuf<u32> node_sref, node_pos;
     DBuf<u32> eovf_head, eovf_target, eovf_next;
-    DBuf<u32> walk_next, parent, cmin, cmax; DBuf<ag_walk> walks, walks2; DBuf<ag_cm1> cm1;
+    DBuf<u32> walk_next, parent, cmin, cmax; DBuf<ag_walk> walks, walks2; DBuf<ag_cm1> cm1; DBuf<unsigned char> pos_term; DBuf<u32> indeg, fnext; DBuf<ag_chain> chain_a, chain_b; DBuf<int> changed;
     DBuf<unsigned char> out_bases, occ; DBuf<u32> sel_start; DBuf<u64> sel_off;
     Scanner scanner;
     u32 n_tiles = 0, n_keys = 0, n_nodes = 0;
@@ -585,7 +621,7 @@ AgDevice::~AgDevice() {
     for (auto* b : b32) b->release();
     for (int i = 0; i < 4; i++) m.scanner.lvl[i].release();
     m.cm.release(); m.aln.release(); m.ext.release(); m.alnp.release(); m.pool.release(); m.ovf_node.release(); m.err.release();
-    m.node_m.release(); m.node_w.release(); m.walks.release(); m.walks2.release(); m.cm1.release(); m.sel_off.release();
+    m.node_m.release(); m.node_w.release(); m.walks.release(); m.walks2.release(); m.cm1.release(); m.pos_term.release(); m.indeg.release(); m.fnext.release(); m.chain_a.release(); m.chain_b.release(); m.changed.release(); m.sel_off.release();
     if (m.st) cudaStreamDestroy(m.st);
     delete m_;
 }
@@ -689,8 +725,8 @@ void AgDevice::build() {
     CK(cudaMemsetAsync(m.tile_cnt.p, 0, (m.n_tiles + 1) * sizeof(u32), st));
     CK(cudaMemsetAsync(m.pos_cnt.p, 0, ((size_t)n_pos + 1) * sizeof(u32), st));
 
-    m.cm1.ensure((size_t)n_pos + 2); d.cm1 = m.cm1.p;
-    if (n_pos) { k_cm1<<<(n_pos + 255) / 256, 256, 0, st>>>(d, m.cm1.p); launches_++; }
+    m.cm1.ensure((size_t)n_pos + 2); d.cm1 = m.cm1.p; m.pos_term.ensure((size_t)n_pos + 2); d.pos_term = m.pos_term.p;
+    if (n_pos) { k_cm1<<<(n_pos + 255) / 256, 256, 0, st>>>(d, m.cm1.p, m.pos_term.p); launches_++; }
     static bool attr_done = false;
     if (!attr_done) { CK(cudaFuncSetAttribute(k_nodes, cudaFuncAttributeMaxDynamicSharedMemorySize, NODES_SMEM)); attr_done = true; }
 
@@ -795,11 +831,34 @@ void AgDevice::walk_components() {
         k_uf_flatten<<<g, 256, 0, st>>>(d, nn); launches_++;
         t_.components += tm.stop();
     }
+    {   // forced-link chains
+        Timer tm(st);
+        m.indeg.ensure(nn + 1); m.fnext.ensure(nn + 1); m.chain_a.ensure(nn + 1); m.chain_b.ensure(nn + 1); m.changed.ensure(1);
+        d.indeg = m.indeg.p; d.fnext = m.fnext.p; d.chain_a = m.chain_a.p; d.chain_b = m.chain_b.p; d.changed = m.changed.p;
+        CK(cudaMemsetAsync(m.indeg.p, 0, (size_t)nn * sizeof(u32), st));
+        k_indeg<<<g, 256, 0, st>>>(d, nn); launches_++;
+        k_links<<<g, 256, 0, st>>>(d, nn); launches_++;
+        ag_chain *a = m.chain_a.p, *b = m.chain_b.p;
+        for (int round = 0; round < 32; round++) {
+            CK(cudaMemsetAsync(m.changed.p, 0, sizeof(int), st));
+            k_rank<<<g, 256, 0, st>>>(a, b, nn, m.changed.p); launches_++;
+            std::swap(a, b);
+            if (round >= 7) {  // chains shorter than 2^8 are done by now; afterwards ask the device
+                int ch = 0;
+                CK(cudaMemcpyAsync(&ch, m.changed.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                if (!ch) break;
+            }
+        }
+        d.chain = a;
+        t_.chains += tm.stop();
+    }
     {
         Timer tm(st);
         k_walk_components<<<g, 256, 0, st>>>(d, nn); launches_++;
         t_.walk += tm.stop();
     }
+    chains_valid_ = true;
 }
 
 void AgDevice::walk_sequential() {
@@ -807,6 +866,7 @@ void AgDevice::walk_sequential() {
     Timer tm(st);
     // reset marks to the coverage filter state and replay in one thread
     k_reset_marks<<<(nn + 255) / 256, 256, 0, st>>>(d, nn); launches_++;
+    d.chain = nullptr; chains_valid_ = false;
     CK(cudaMemsetAsync(m.counters.p + 3, 0, sizeof(u32), st));
     k_walk_sequential<<<1, 32, 0, st>>>(d); launches_++;
     t_.walk += tm.stop();
@@ -872,7 +932,7 @@ void AgDevice::materialize(const std::vector<ag_walk>& walks, const std::vector<
     m.sel_start.ensure(sel.size() + 1); m.sel_off.ensure(sel.size() + 1); m.out_bases.ensure(offs.back() + 1);
     CK(cudaMemcpyAsync(m.sel_start.p, starts.data(), starts.size() * sizeof(u32), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(m.sel_off.p, offs.data(), sel.size() * sizeof(u64), cudaMemcpyHostToDevice, st));
-    k_materialize<<<((u32)sel.size() + 127) / 128, 128, 0, st>>>(d, m.sel_start.p, m.sel_off.p, (u32)sel.size(), m.out_bases.p); launches_++;
+    k_materialize<<<((u32)sel.size() + 127) / 128, 128, 0, st>>>(d, m.sel_start.p, m.sel_off.p, (u32)sel.size(), m.out_bases.p, chains_valid_ ? 1 : 0); launches_++;
     CK(cudaMemcpyAsync(&bases[0], m.out_bases.p, offs.back(), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     t_.materialize += tm.stop();

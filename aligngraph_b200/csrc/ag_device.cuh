@@ -23,7 +23,7 @@ struct AgNodeDump {  // node table in (position, item) order, for tests
 };
 
 struct AgTimings {  // milliseconds, CUDA events on the context's stream
-    float h2d = 0, prep = 0, sort = 0, nodes = 0, finalize = 0, edges = 0, components = 0, walk = 0, materialize = 0, d2h = 0;
+    float h2d = 0, prep = 0, sort = 0, nodes = 0, finalize = 0, edges = 0, components = 0, chains = 0, walk = 0, materialize = 0, d2h = 0;
     u64 n_nodes = 0, n_edges_ovf = 0, n_walks = 0, n_keys = 0, n_tiles = 0, n_components = 0;
     u64 h2d_bytes = 0, d2h_bytes = 0;
     int walk_fallback = 0;
@@ -69,6 +69,7 @@ private:
     u64 launches_ = 0;
     void *ev0_ = nullptr, *ev1_ = nullptr;
     std::vector<void*> pinned_;
+    bool chains_valid_ = false;
     void walk_components();
     void walk_sequential();
 };

@@ -271,8 +271,8 @@ int main(int argc, char* argv[]) {
         if (getenv("AG_STATS")) {
             for (size_t g = 0; g < ctxs.size(); g++) {
                 ag_stats s; ag_get_stats(ctxs[g], &s);
-                fprintf(stderr, "[ag] gpu %d: parse %.3f s, device section %.3f s, post %.3f s; kernels ms: prep %.2f sort %.2f nodes %.2f finalize %.2f edges %.2f cc %.2f walk %.2f mat %.2f; launches %lu\n",
-                        devices[g], s.s_parse, s.s_device_section, s.s_post, s.ms_prep, s.ms_sort, s.ms_nodes, s.ms_finalize, s.ms_edges, s.ms_components, s.ms_walk,
+                fprintf(stderr, "[ag] gpu %d: parse %.3f s, device section %.3f s, post %.3f s; kernels ms: prep %.2f sort %.2f nodes %.2f finalize %.2f edges %.2f cc %.2f chains %.2f walk %.2f mat %.2f; launches %lu\n",
+                        devices[g], s.s_parse, s.s_device_section, s.s_post, s.ms_prep, s.ms_sort, s.ms_nodes, s.ms_finalize, s.ms_edges, s.ms_components, s.ms_chains, s.ms_walk,
                         s.ms_materialize, (unsigned long)s.kernel_launches);
             }
         }

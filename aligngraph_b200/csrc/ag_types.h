@@ -71,6 +71,7 @@ struct alignas(16) ag_nodew {
 #define AG_NW_OVF 0x400u
 #define AG_NW_TRAV 0x800u    /* traversed (AG:2013); set from the start on coverage-filtered nodes */
 #define AG_NW_DETOUR 0x1000u /* the walk left this node through a contiMer thread */
+#define AG_NW_INTERIOR 0x2000u /* entered only through its unique live predecessor (forced link): never starts a walk */
 
 struct ag_nodem { u32 cid, coff, cid0, coff0, moff; };  // match fields of a final node
 
@@ -87,6 +88,9 @@ struct ag_walk {
     u32 tail_sread;  // founder string of last_node: (read index << 1) | rc
     u32 tail_soff_len;  // offset | len<<16
 };
+
+// forced-link chain record after list ranking: from this node to the tail of its chain
+struct alignas(16) ag_chain { u32 jump, tail, len, flg; };
 
 struct ag_params_dev {
     int k, iv, coverage;

@@ -53,7 +53,7 @@ typedef struct ag_cm_c { uint32_t cid, coff, chain, term; } ag_cm_c;
 
 typedef struct ag_stats {
     /* device milliseconds (CUDA events on the context's stream), accumulated since ag_reset_stats */
-    float ms_h2d, ms_prep, ms_sort, ms_nodes, ms_finalize, ms_edges, ms_components, ms_walk, ms_materialize, ms_d2h;
+    float ms_h2d, ms_prep, ms_sort, ms_nodes, ms_finalize, ms_edges, ms_components, ms_chains, ms_walk, ms_materialize, ms_d2h;
     /* host wall seconds */
     double s_parse, s_device_section, s_post;
     uint64_t n_aln, n_nodes, n_walks, n_emitted, n_keys, n_tiles, kernel_launches, h2d_bytes, d2h_bytes;

@@ -25,9 +25,11 @@ public:
     std::vector<u32> pos_node, node_pos, node_sref, eovf_head, eovf_target, eovf_next, walk_next, parent;
     std::vector<ag_nodeb> nodeb;  // final order
     std::vector<ag_nodem> node_m; std::vector<ag_nodew> node_w; std::vector<ag_cm1> cm1;
+    std::vector<unsigned char> pos_term; std::vector<u32> indeg, fnext; std::vector<ag_chain> chain; bool use_chains = false;
     std::vector<ag_nodeb> ovf_node; std::vector<u32> ovf_next; u32 ovf_count = 0; int err = 0;
     u32 n_nodes = 0;
     bool fallback_used = false;
+    u32 n_live = 0, n_heads = 0, max_chain = 0;
 
     void set_reads(const AgReads& r) { rd.bases = r.bases.data(); rd.nmask = r.nmask.data(); rd.len = r.len.data(); rd.stride2 = r.stride2; rd.stridem = r.stridem; }
     void load_unit(const AgUnitInput& i) { in = i; }
@@ -143,7 +145,7 @@ public:
 
     ag_walkctx ctx() {
         ag_walkctx w; w.nw = node_w.data(); w.node_pos = node_pos.data(); w.pos_node = pos_node.data(); w.ovf_head = eovf_head.data();
-        w.ovf_target = eovf_target.data(); w.ovf_next = eovf_next.data(); w.cmt = cmt(); w.chain_pos = in.chain_pos; w.walk_next = walk_next.data();
+        w.ovf_target = eovf_target.data(); w.ovf_next = eovf_next.data(); w.cmt = cmt(); w.chain_pos = in.chain_pos; w.walk_next = walk_next.data(); w.chain = use_chains ? chain.data() : nullptr;
         return w;
     }
     u32 find(u32 x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; }
@@ -176,12 +178,38 @@ public:
         }
         std::vector<u32> cmin(n_nodes, AG_NONE), cmax(n_nodes, 0);
         for (u32 v = 0; v < n_nodes; v++) if (live(v)) { u32 r = find(v); parent[v] = r; cmin[r] = std::min(cmin[r], v); cmax[r] = std::max(cmax[r], v); }
+        // forced-link chains (k_indeg, k_links, list ranking)
+        pos_term.assign((size_t)in.n_pos + 1, 0);
+        for (u32 p = 0; p < in.n_pos; p++) for (u32 e = ct.start[p]; e < ct.start[p + 1]; e++) if (ct.cm[e].chain == ct.cm[e].term) pos_term[p] = 1;
+        indeg.assign(n_nodes, 0); fnext.assign(n_nodes, AG_NONE); chain.assign(n_nodes, ag_chain{});
+        for (u32 v = 0; v < n_nodes; v++) {
+            if (!live(v)) continue;
+            const ag_nodew& x = node_w[v];
+            if (x.succ0 != AG_NONE && live(x.succ0)) indeg[x.succ0]++;
+            if (x.succ1 != AG_NONE && live(x.succ1)) indeg[x.succ1]++;
+            if (x.misc & AG_NW_OVF) for (u32 o = eovf_head[v]; o != AG_NONE; o = eovf_next[o]) if (live(eovf_target[o])) indeg[eovf_target[o]]++;
+        }
+        for (u32 v = 0; v < n_nodes; v++) {
+            fnext[v] = ag_forced_succ(node_w.data(), eovf_head.data(), eovf_target.data(), eovf_next.data(), indeg.data(), pos_term.data(), node_pos.data(), v);
+            if (fnext[v] != AG_NONE) node_w[fnext[v]].misc |= AG_NW_INTERIOR;
+        }
+        for (u32 v = n_nodes; v-- > 0;) {  // forced links point to higher node indices (positions increase), so one backward pass ranks every chain
+            ag_chain c; c.jump = AG_NONE; c.tail = v; c.len = 1; c.flg = (node_w[v].misc & AG_NW_HASCONTIG) ? 1u : 0u;
+            if (fnext[v] != AG_NONE) {
+                if (fnext[v] <= v) throw AgHostError{"emul: forced link does not point forward"};
+                const ag_chain& j = chain[fnext[v]]; c.tail = j.tail; c.len += j.len; c.flg |= j.flg;
+            }
+            chain[v] = c;
+        }
+        use_chains = !getenv("AG_EMUL_NO_CHAINS");
+        n_live = n_heads = 0; max_chain = 0;
+        for (u32 v = 0; v < n_nodes; v++) if (live(v)) { n_live++; if (!(node_w[v].misc & AG_NW_INTERIOR)) { n_heads++; max_chain = std::max(max_chain, chain[v].len); } }
         ag_walkctx w = ctx();
         // components are replayed from the LAST root to the first to make sure nothing depends on cross-component order
         for (u32 r = n_nodes; r-- > 0;) {
             if (!live(r) || parent[r] != r) continue;
             for (u32 v = cmin[r]; v <= cmax[r]; v++) {
-                if (node_w[v].misc & AG_NW_TRAV) continue;
+                if (node_w[v].misc & (AG_NW_TRAV | (use_chains ? AG_NW_INTERIOR : 0u))) continue;
                 if (parent[v] != r) continue;
                 ag_walk x = ag_walk_from(w, v); fill_tail(x); walks.push_back(x);
             }
@@ -197,9 +225,9 @@ public:
             if (beo - bso > 100000u) { trigger = true; break; }
         }
         if (trigger || getenv("AG_EMUL_FORCE_SEQUENTIAL")) {
-            fallback_used = true;
+            fallback_used = true; use_chains = false; w = ctx();
             walks.clear();
-            for (u32 v = 0; v < n_nodes; v++) { u32 m = node_w[v].misc & ~(AG_NW_TRAV | AG_NW_DETOUR); node_w[v].misc = live(v) ? m : (m | AG_NW_TRAV); walk_next[v] = AG_NONE; }
+            for (u32 v = 0; v < n_nodes; v++) { u32 m = node_w[v].misc & ~(AG_NW_TRAV | AG_NW_DETOUR | AG_NW_INTERIOR); node_w[v].misc = live(v) ? m : (m | AG_NW_TRAV); walk_next[v] = AG_NONE; }
             u32 sbo = AG_NONE, seo = AG_NONE, sei = AG_NONE;
             for (u32 cp = 0; cp < in.n_ref;) {
                 for (u32 v = pos_node[cp]; v < pos_node[cp + 1]; v++) {
@@ -223,7 +251,7 @@ public:
         ag_cmtab ct = cmt();
         for (size_t i = 0; i < sel.size(); i++) {
             size_t o = offs[i];
-            for (u32 v = walks[sel[i]].start_node; v != AG_NONE; v = walk_next[v]) {
+            for (u32 v = walks[sel[i]].start_node; v != AG_NONE; v = (use_chains && fnext[v] != AG_NONE) ? fnext[v] : walk_next[v]) {
                 bases[o++] = (char)(node_w[v].misc & 0xFF);
                 if (node_w[v].misc & AG_NW_DETOUR) { ag_cm m = ct.cm[ct.start[node_pos[v]]]; for (u32 e = m.chain + 1; e <= m.term; e++) bases[o++] = in.chain_base[e]; }
             }
@@ -299,7 +327,7 @@ int main(int argc, char** argv) {
         for (int unit = first; unit <= last; unit++) {
             AgUnitResult r;
             ag_run_unit_files(eng, reads, "tmp", unit, r);
-            fprintf(stderr, "emul unit %d: aln=%lu nodes=%u walks=%lu emitted=%lu%s\n", unit, (unsigned long)r.n_aln, eng.n_nodes, (unsigned long)r.n_walks, (unsigned long)r.n_emitted,
+            fprintf(stderr, "emul unit %d: aln=%lu nodes=%u live=%u chain_heads=%u max_chain=%u walks=%lu emitted=%lu%s\n", unit, (unsigned long)r.n_aln, eng.n_nodes, eng.n_live, eng.n_heads, eng.max_chain, (unsigned long)r.n_walks, (unsigned long)r.n_emitted,
                     eng.fallback_used ? " (sequential walk)" : "");
             if (dump) { AgNodeDump d; eng.dump_nodes(d); std::string text; ag_format_node_dump(d, reads, text); ag_write_file("tmp/_nodes." + std::to_string(unit) + ".txt", text); }
         }
