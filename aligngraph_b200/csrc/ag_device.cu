@@ -155,6 +155,7 @@ struct DevView {
     ag_nodem* node_m; ag_nodew* node_w; u32* node_sref; u32* node_pos;
     u32* eovf_head; u32* eovf_target; u32* eovf_next; u32* eovf_count; u32 eovf_cap;
     u32* walk_next; u32* parent; u32* cmin; u32* cmax;
+    u32* cand_rank; u32* cand_node; u32* cand_label;
     unsigned char* pos_term; u32* indeg; u32* fnext; ag_chain* chain_a; ag_chain* chain_b; const ag_chain* chain; int* changed;
     ag_walk* walks; ag_walk* walks_sorted; u32* walk_count; u32 walk_cap;
     int* err;
@@ -208,7 +209,7 @@ __global__ void k_cm1(DevView d, ag_cm1* out, unsigned char* pos_term) {
 // first-compatible clustering on a node list held in shared memory ([field][node][thread], conflict-free).
 // ---------------------------------------------------------------------------------------------------------------------------
 constexpr int NCHUNK = 128;
-constexpr int NODE_SCAP = 4;                                   // nodes per position kept in shared memory; more spill to the pool
+constexpr int NODE_SCAP = 3;                                   // nodes per position kept in shared memory; more spill to the pool
 constexpr int NODES_SMEM = 13 * NODE_SCAP * AG_TILE * 4;       // bytes of dynamic shared memory
 
 // one candidate when both sides have at most one contiMer (the common case), else the reference's nested enumeration
@@ -484,7 +485,21 @@ __global__ void k_rank(const ag_chain* __restrict__ in, ag_chain* __restrict__ o
     out[v] = c;
 }
 
-// one thread per component root: replay the scan (AG:1972-1990) restricted to the component's nodes, in node order
+// walk starts can only be live nodes that are not chain-interior: compact them (in node order) so that a component's replay does not
+// have to step over every node of its range
+__global__ void k_cand_flag(DevView d, u32 n_nodes, u32* flag) {
+    u32 v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_nodes) return;
+    flag[v] = (d.node_w[v].misc & (AG_NW_FILTERED | AG_NW_INTERIOR)) ? 0u : 1u;
+}
+__global__ void k_cand_scatter(DevView d, u32 n_nodes, const u32* flag) {
+    u32 v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_nodes || !flag[v]) return;
+    u32 i = d.cand_rank[v];
+    d.cand_node[i] = v; d.cand_label[i] = d.parent[v];
+}
+
+// one thread per component root: replay the scan (AG:1972-1990) restricted to the component's start candidates, in node order
 __global__ void k_walk_components(DevView d, u32 n_nodes) {
     u32 r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_nodes) return;
@@ -492,9 +507,11 @@ __global__ void k_walk_components(DevView d, u32 n_nodes) {
     if (d.parent[r] != r) return;
     ag_walkctx w = make_ctx(d);
     u32 hi = d.cmax[r];
-    for (u32 v = d.cmin[r]; v <= hi; v++) {
-        if (d.node_w[v].misc & (AG_NW_TRAV | AG_NW_INTERIOR)) continue;
-        if (d.parent[v] != r) continue;
+    u32 i1 = d.cand_rank[hi + 1];
+    for (u32 i = d.cand_rank[d.cmin[r]]; i < i1; i++) {
+        if (d.cand_label[i] != r) continue;
+        u32 v = d.cand_node[i];
+        if (d.node_w[v].misc & AG_NW_TRAV) continue;
         push_walk(d, ag_walk_from(w, v));
     }
 }
@@ -546,6 +563,44 @@ __global__ void k_materialize(DevView d, const u32* __restrict__ starts, const u
     }
 }
 
+// materialisation in two steps when chains are valid: (1) one thread per emitted walk hops from chain head to chain head and emits
+// work items, (2) one thread per chain item writes that chain's consensus bases, one warp per detour item copies the contig bases
+struct MatItem { u32 a, n; u64 off; };  // chain item: a = head node, n = nodes; detour item: a = first chain-major index, n = bases
+__global__ void k_mat_items(DevView d, const u32* __restrict__ starts, const u64* __restrict__ offs, u32 n, MatItem* chains, MatItem* detours, u32* counts, u32 cap) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u64 off = offs[i];
+    u32 v = starts[i];
+    while (v != AG_NONE) {
+        ag_chain c = d.chain[v];
+        u32 o = atomicAdd(&counts[0], 1u);
+        if (o < cap) { MatItem it; it.a = v; it.n = c.len; it.off = off; chains[o] = it; } else *d.err = 6;
+        off += c.len;
+        u32 t = c.tail;
+        if (d.node_w[t].misc & AG_NW_DETOUR) {
+            ag_cm m = d.cmt.cm[d.cmt.start[d.node_pos[t]]];
+            u32 o2 = atomicAdd(&counts[1], 1u);
+            if (o2 < cap) { MatItem it; it.a = m.chain + 1; it.n = m.term - m.chain; it.off = off; detours[o2] = it; } else *d.err = 6;
+            off += m.term - m.chain;
+        }
+        v = d.walk_next[t];
+    }
+}
+__global__ void k_mat_chains(DevView d, const MatItem* __restrict__ items, const u32* counts, unsigned char* out) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= counts[0]) return;
+    MatItem it = items[i];
+    unsigned char* o = out + it.off;
+    u32 v = it.a;
+    for (u32 j = 0; j < it.n; j++) { *o++ = (unsigned char)(d.node_w[v].misc & 0xFF); v = d.fnext[v]; }
+}
+__global__ void k_mat_detours(DevView d, const MatItem* __restrict__ items, const u32* counts, unsigned char* out) {
+    u32 w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= counts[1]) return;
+    MatItem it = items[w];
+    for (u32 j = lane; j < it.n; j += 32) out[it.off + j] = d.chain_base[it.a + j];
+}
+
 __global__ void k_reset_marks(DevView d, u32 n_nodes) {
     u32 v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n_nodes) return;
@@ -590,7 +645,7 @@ struct AgDevice::Impl {
     DBuf<u32> pos_cnt, pos_pool, pos_node;
     DBuf<ag_nodem> node_m; DBuf<ag_nodew> node_w; DBuf<u32> node_sref, node_pos;
     DBuf<u32> eovf_head, eovf_target, eovf_next;
-    DBuf<u32> walk_next, parent, cmin, cmax; DBuf<ag_walk> walks, walks2; DBuf<ag_cm1> cm1; DBuf<unsigned char> pos_term; DBuf<u32> indeg, fnext; DBuf<ag_chain> chain_a, chain_b; DBuf<int> changed;
+    DBuf<u32> walk_next, parent, cmin, cmax; DBuf<ag_walk> walks, walks2; DBuf<ag_cm1> cm1; DBuf<MatItem> mat_chains, mat_detours; u32 n_cand = 0; DBuf<unsigned char> pos_term; DBuf<u32> indeg, fnext, cand_rank, cand_node, cand_label; DBuf<ag_chain> chain_a, chain_b; DBuf<int> changed;
     DBuf<unsigned char> out_bases, occ; DBuf<u32> sel_start; DBuf<u64> sel_off;
     Scanner scanner;
     u32 n_tiles = 0, n_keys = 0, n_nodes = 0;
@@ -621,7 +676,7 @@ AgDevice::~AgDevice() {
     for (auto* b : b32) b->release();
     for (int i = 0; i < 4; i++) m.scanner.lvl[i].release();
     m.cm.release(); m.aln.release(); m.ext.release(); m.alnp.release(); m.pool.release(); m.ovf_node.release(); m.err.release();
-    m.node_m.release(); m.node_w.release(); m.walks.release(); m.walks2.release(); m.cm1.release(); m.pos_term.release(); m.indeg.release(); m.fnext.release(); m.chain_a.release(); m.chain_b.release(); m.changed.release(); m.sel_off.release();
+    m.node_m.release(); m.node_w.release(); m.walks.release(); m.walks2.release(); m.cm1.release(); m.mat_chains.release(); m.mat_detours.release(); m.pos_term.release(); m.cand_rank.release(); m.cand_node.release(); m.cand_label.release(); m.indeg.release(); m.fnext.release(); m.chain_a.release(); m.chain_b.release(); m.changed.release(); m.sel_off.release();
     if (m.st) cudaStreamDestroy(m.st);
     delete m_;
 }
@@ -851,6 +906,13 @@ void AgDevice::walk_components() {
             }
         }
         d.chain = a;
+        // start candidates
+        m.cand_rank.ensure((size_t)nn + 2); m.cand_node.ensure(nn + 1); m.cand_label.ensure(nn + 1);
+        d.cand_rank = m.cand_rank.p; d.cand_node = m.cand_node.p; d.cand_label = m.cand_label.p;
+        k_cand_flag<<<g, 256, 0, st>>>(d, nn, m.indeg.p); launches_++;
+        m.scanner.run(m.indeg.p, m.cand_rank.p, nn, st);
+        k_cand_scatter<<<g, 256, 0, st>>>(d, nn, m.indeg.p); launches_++;
+        CK(cudaMemcpyAsync(&m.n_cand, m.cand_rank.p + nn, sizeof(u32), cudaMemcpyDeviceToHost, st));
         t_.chains += tm.stop();
     }
     {
@@ -932,9 +994,21 @@ void AgDevice::materialize(const std::vector<ag_walk>& walks, const std::vector<
     m.sel_start.ensure(sel.size() + 1); m.sel_off.ensure(sel.size() + 1); m.out_bases.ensure(offs.back() + 1);
     CK(cudaMemcpyAsync(m.sel_start.p, starts.data(), starts.size() * sizeof(u32), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(m.sel_off.p, offs.data(), sel.size() * sizeof(u64), cudaMemcpyHostToDevice, st));
-    k_materialize<<<((u32)sel.size() + 127) / 128, 128, 0, st>>>(d, m.sel_start.p, m.sel_off.p, (u32)sel.size(), m.out_bases.p, chains_valid_ ? 1 : 0); launches_++;
+    if (chains_valid_) {
+        u32 cap = m.n_cand + 1;
+        m.mat_chains.ensure(cap); m.mat_detours.ensure(cap);
+        CK(cudaMemsetAsync(m.counters.p + 4, 0, 2 * sizeof(u32), st));
+        k_mat_items<<<((u32)sel.size() + 127) / 128, 128, 0, st>>>(d, m.sel_start.p, m.sel_off.p, (u32)sel.size(), m.mat_chains.p, m.mat_detours.p, m.counters.p + 4, cap); launches_++;
+        k_mat_chains<<<(cap + 127) / 128, 128, 0, st>>>(d, m.mat_chains.p, m.counters.p + 4, m.out_bases.p); launches_++;
+        k_mat_detours<<<(cap + 3) / 4, 128, 0, st>>>(d, m.mat_detours.p, m.counters.p + 4, m.out_bases.p); launches_++;
+    } else {
+        k_materialize<<<((u32)sel.size() + 127) / 128, 128, 0, st>>>(d, m.sel_start.p, m.sel_off.p, (u32)sel.size(), m.out_bases.p, 0); launches_++;
+    }
     CK(cudaMemcpyAsync(&bases[0], m.out_bases.p, offs.back(), cudaMemcpyDeviceToHost, st));
+    int err = 0;
+    CK(cudaMemcpyAsync(&err, m.err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    if (err) throw AgError{"materialise item buffer exhausted"};
     t_.materialize += tm.stop();
     t_.h2d_bytes += sel.size() * 12; t_.d2h_bytes += offs.back();
 }

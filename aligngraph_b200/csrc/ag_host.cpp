@@ -54,20 +54,26 @@ int ag_atoi(const char* s, size_t n) {  // atoi() over a bounded field
     return (int)r;
 }
 
-struct Out {  // buffered text sink: a file, or (path empty) an in-memory string
-    FILE* f = nullptr; std::string* mem = nullptr; std::vector<char> buf;
-    explicit Out(const std::string& path) : f(fopen(path.c_str(), "wb")) { if (!f) throw AgHostError{"CANNOT OPEN FILE!"}; buf.reserve(1 << 20); }
-    explicit Out(std::string* m) : mem(m) { m->clear(); }
-    ~Out() { flush(); if (f) fclose(f); }
-    void flush() { if (buf.empty()) return; if (f) fwrite(buf.data(), 1, buf.size(), f); else mem->append(buf.data(), buf.size()); buf.clear(); }
-    void put(const char* s, size_t n) { buf.insert(buf.end(), s, s + n); if (buf.size() > (1u << 20) - 256) flush(); }
+struct Out {  // buffered text sink: a file, or an in-memory string (written in place, no intermediate copy)
+    FILE* f = nullptr; std::string own; std::string* b;
+    explicit Out(const std::string& path) : f(fopen(path.c_str(), "wb")), b(&own) { if (!f) throw AgHostError{"CANNOT OPEN FILE!"}; own.reserve(1 << 21); }
+    explicit Out(std::string* m) : b(m) { m->clear(); }
+    ~Out() { if (f) { flush(); fclose(f); } }
+    void flush() { if (f && !b->empty()) { fwrite(b->data(), 1, b->size(), f); b->clear(); } }
+    void maybe_flush() { if (f && b->size() > (1u << 20)) flush(); }
+    void put(const char* s, size_t n) { b->append(s, n); maybe_flush(); }
     void put(const std::string& s) { put(s.data(), s.size()); }
-    void ch(char c) { buf.push_back(c); if (buf.size() > (1u << 20)) flush(); }
-    void num(unsigned long v) { char t[24]; int i = 24; do { t[--i] = (char)('0' + v % 10); v /= 10; } while (v); put(t + i, (size_t)(24 - i)); }
+    void ch(char c) { b->push_back(c); }
+    void num(unsigned long v) { char t[24]; int i = 24; do { t[--i] = (char)('0' + v % 10); v /= 10; } while (v); b->append(t + i, (size_t)(24 - i)); }
     void inum(long v) { if (v < 0) { ch('-'); num((unsigned long)(-(v + 1)) + 1); } else num((unsigned long)v); }
-    void wrap60(const std::string& s) {  // 60 columns, newline after the last base (AG:2179-2184)
-        for (size_t i = 0; i < s.size(); i += 60) { put(s.data() + i, std::min<size_t>(60, s.size() - i)); ch('\n'); }
+    void wrap60(const char* s, size_t n) {  // 60 columns, newline after the last base (AG:2179-2184)
+        size_t old = b->size(), lines = (n + 59) / 60;
+        b->resize(old + n + lines);
+        char* p = &(*b)[old];
+        for (size_t i = 0; i < n; i += 60) { size_t m = std::min<size_t>(60, n - i); memcpy(p, s + i, m); p += m; *p++ = '\n'; }
+        maybe_flush();
     }
+    void wrap60(const std::string& s) { wrap60(s.data(), s.size()); }
 };
 
 inline int absdiff(u32 a, u32 b) { int d = (int)(a - b); return d < 0 ? -d : d; }
@@ -602,6 +608,10 @@ static inline int overlap(u32 x1, u32 y1, u32 x2, u32 y2) {  // AG:2388-2394
 void ag_scaffold(std::vector<AgContig>& cs, const std::string& ref, const std::vector<unsigned char>& occ, std::string& text) {
     std::vector<std::string> sc;
     auto occupied = [&](u32 p) { return (size_t)(p >> 3) < occ.size() && ((occ[p >> 3] >> (p & 7)) & 1); };
+    // the reference scans EVERY later contig for a chaining partner (quadratic); only contigs with extended == 1 can ever satisfy the
+    // test and `extended` does not change here, so scanning that sub-list in the same order is equivalent
+    std::vector<u32> ext1;
+    for (u32 i = 0; i < cs.size(); i++) if (cs[i].extended == 1) ext1.push_back(i);
     for (u32 cp = 0; cp < cs.size(); cp++) {
         if (!(cs[cp].sid != AG_NONE && cs[cp].extended == 1)) continue;
         sc.push_back(cs[cp].bases);
@@ -609,7 +619,8 @@ void ag_scaffold(std::vector<AgContig>& cs, const std::string& ref, const std::v
         int cont = 1;
         while (cs[cp].sid0 == cs[cp].eid0 && cont) {
             cont = 0;
-            for (u32 c0 = cp + 1; c0 < cs.size(); c0++) {
+            for (size_t e = (size_t)(std::upper_bound(ext1.begin(), ext1.end(), cp) - ext1.begin()); e < ext1.size(); e++) {
+                const u32 c0 = ext1[e];
                 const AgContig& a = cs[cp]; AgContig& b = cs[c0];
                 if (!(a.eid0 == b.sid && b.sid == b.eid && overlap(a.soff0, a.eoff0, b.soff, b.eoff) && b.extended == 1)) continue;
                 if (b.soff > a.eoff) {

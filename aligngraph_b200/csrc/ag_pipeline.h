@@ -5,6 +5,8 @@
 #include "ag_host.h"
 #include "ag_device.cuh"
 #include <chrono>
+#include <cstdlib>
+#include <cstdio>
 
 struct AgUnitResult {
     std::string initial_text, pre_text, ext_text;  // tmp/_initial_contigs.N.fa, _pre_extended_contigs.N.fa, _extended_contigs.N.fa
@@ -45,9 +47,13 @@ template <class Engine> void ag_process_unit(Engine& eng, const AgReads& reads, 
     auto t1 = std::chrono::steady_clock::now();
     std::vector<AgContig> contigs;
     ag_make_contigs(walks, sel, bases, offs, reads, contigs, r.pre_text);
+    auto t1a = std::chrono::steady_clock::now();
     ag_dedup_join(contigs);
+    auto t1b = std::chrono::steady_clock::now();
     ag_scaffold(contigs, u.ref, occ, r.ext_text);
     auto t2 = std::chrono::steady_clock::now();
+    if (getenv("AG_POST_TIMING")) fprintf(stderr, "[post] select+make %.2f ms, dedup_join %.2f ms, scaffold %.2f ms\n", std::chrono::duration<double>(t1a - t1).count() * 1e3,
+                                          std::chrono::duration<double>(t1b - t1a).count() * 1e3, std::chrono::duration<double>(t2 - t1b).count() * 1e3);
     r.t_device += std::chrono::duration<double>(t1 - t0).count();
     r.t_post += std::chrono::duration<double>(t2 - t1).count();
     r.n_aln = u.aln.size(); r.n_walks = walks.size(); r.n_emitted = sel.size();
