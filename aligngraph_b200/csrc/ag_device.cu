@@ -405,40 +405,32 @@ __global__ void k_uf_init(DevView d, u32 n_nodes) {
     if (v >= n_nodes) return;
     d.parent[v] = v; d.cmin[v] = AG_NONE; d.cmax[v] = 0; d.walk_next[v] = AG_NONE;
 }
-// live successor edges join components (a walk reads the traversed flag of every successor, AG:2022-2032)
-__global__ void k_uf_edges(DevView d, u32 n_nodes) {
-    u32 v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= n_nodes) return;
-    ag_nodew w = d.node_w[v];
-    if (w.misc & AG_NW_FILTERED) return;
-    if (w.succ0 != AG_NONE && !(d.node_w[w.succ0].misc & AG_NW_FILTERED)) uf_unite(d.parent, v, w.succ0);
-    if (w.succ1 != AG_NONE && !(d.node_w[w.succ1].misc & AG_NW_FILTERED)) uf_unite(d.parent, v, w.succ1);
+// Components over chain TAILS.  Only a chain's tail has live successors outside its chain and only a tail can
+// leave through a contiMer detour (interior nodes always see exactly one untraversed successor), so the relations a walk can follow are:
+// tail -> chains of its live successors (AG:2022-2032) and tail -> chains of the live nodes at its detour's terminal position
+// (AG:2093-2114).  One thread per start candidate (= chain head), ~1/66 of the nodes.
+__global__ void k_uf_tails(DevView d, u32 n_cand) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cand) return;
+    const u32 t = d.chain[d.cand_node[i]].tail;
+    const ag_nodew w = d.node_w[t];
+    if (w.succ0 != AG_NONE && !(d.node_w[w.succ0].misc & AG_NW_FILTERED)) uf_unite(d.parent, t, d.chain[w.succ0].tail);
+    if (w.succ1 != AG_NONE && !(d.node_w[w.succ1].misc & AG_NW_FILTERED)) uf_unite(d.parent, t, d.chain[w.succ1].tail);
     if (w.misc & AG_NW_OVF)
-        for (u32 o = d.eovf_head[v]; o != AG_NONE; o = d.eovf_next[o]) { u32 s = d.eovf_target[o]; if (!(d.node_w[s].misc & AG_NW_FILTERED)) uf_unite(d.parent, v, s); }
-}
-// a contiMer detour from position p inspects every node at the thread's terminal position (AG:2093-2114)
-__global__ void k_uf_chain(DevView d) {
-    u32 p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= d.n_ref) return;
-    u32 c0 = d.cmt.start[p];
+        for (u32 o = d.eovf_head[t]; o != AG_NONE; o = d.eovf_next[o]) { u32 s = d.eovf_target[o]; if (!(d.node_w[s].misc & AG_NW_FILTERED)) uf_unite(d.parent, t, d.chain[s].tail); }
+    const u32 p = d.node_pos[t], c0 = d.cmt.start[p];
     if (d.cmt.start[p + 1] - c0 != 1) return;
-    ag_cm m = d.cmt.cm[c0];
+    const ag_cm m = d.cmt.cm[c0];
     if (m.chain == m.term) return;
-    u32 anchor = AG_NONE;
-    for (u32 x = d.pos_node[p]; x < d.pos_node[p + 1]; x++)
-        if (!(d.node_w[x].misc & AG_NW_FILTERED)) { if (anchor == AG_NONE) anchor = x; else uf_unite(d.parent, anchor, x); }
-    if (anchor == AG_NONE) return;
-    u32 z = d.chain_pos[m.term];
-    if (z >= d.n_ref) return;
-    for (u32 x = d.pos_node[z]; x < d.pos_node[z + 1]; x++) if (!(d.node_w[x].misc & AG_NW_FILTERED)) uf_unite(d.parent, anchor, x);
+    const u32 z = d.chain_pos[m.term];
+    for (u32 x = d.pos_node[z]; x < d.pos_node[z + 1]; x++) if (!(d.node_w[x].misc & AG_NW_FILTERED)) uf_unite(d.parent, t, d.chain[x].tail);
 }
-__global__ void k_uf_flatten(DevView d, u32 n_nodes) {
-    u32 v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= n_nodes) return;
-    if (d.node_w[v].misc & AG_NW_FILTERED) return;
-    u32 r = uf_find(d.parent, v);
-    d.parent[v] = r;
-    atomicMin(&d.cmin[r], v); atomicMax(&d.cmax[r], v);
+__global__ void k_uf_flatten(DevView d, u32 n_cand) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cand) return;
+    u32 r = uf_find(d.parent, d.chain[d.cand_node[i]].tail);
+    d.cand_label[i] = r;
+    atomicMin(&d.cmin[r], i); atomicMax(&d.cmax[r], i);
 }
 
 __device__ __forceinline__ ag_walkctx make_ctx(const DevView& d) {
@@ -485,6 +477,27 @@ __global__ void k_rank(const ag_chain* __restrict__ in, ag_chain* __restrict__ o
     out[v] = c;
 }
 
+// list ranking, step 1: pointer jumping inside blocks of 1024 consecutive nodes in shared memory.  Forced links point to higher node
+// indices and chains are short-range (the next node is the next position), so almost every chain is finished here; what remains are
+// links that leave the block, resolved by a few global k_rank rounds.
+__global__ void __launch_bounds__(1024) k_rank_local(ag_chain* recs, u32 n_nodes) {
+    __shared__ ag_chain sa[1024], sb[1024];
+    const u32 b0 = blockIdx.x * 1024u, v = b0 + threadIdx.x;
+    ag_chain c; c.jump = AG_NONE; c.tail = v; c.len = 0; c.flg = 0;
+    if (v < n_nodes) c = recs[v];
+    sa[threadIdx.x] = c;
+    __syncthreads();
+    ag_chain *src = sa, *dst = sb;
+    for (int r = 0; r < 10; r++) {
+        c = src[threadIdx.x];
+        if (c.jump != AG_NONE && c.jump - b0 < 1024u) { ag_chain j = src[c.jump - b0]; c.len += j.len; c.flg |= j.flg; c.tail = j.tail; c.jump = j.jump; }
+        dst[threadIdx.x] = c;
+        __syncthreads();
+        ag_chain* t = src; src = dst; dst = t;
+    }
+    if (v < n_nodes) recs[v] = src[threadIdx.x];
+}
+
 // walk starts can only be live nodes that are not chain-interior: compact them (in node order) so that a component's replay does not
 // have to step over every node of its range
 __global__ void k_cand_flag(DevView d, u32 n_nodes, u32* flag) {
@@ -496,19 +509,19 @@ __global__ void k_cand_scatter(DevView d, u32 n_nodes, const u32* flag) {
     u32 v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n_nodes || !flag[v]) return;
     u32 i = d.cand_rank[v];
-    d.cand_node[i] = v; d.cand_label[i] = d.parent[v];
+    d.cand_node[i] = v;
 }
 
-// one thread per component root: replay the scan (AG:1972-1990) restricted to the component's start candidates, in node order
-__global__ void k_walk_components(DevView d, u32 n_nodes) {
-    u32 r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_nodes) return;
-    if (d.node_w[r].misc & AG_NW_FILTERED) return;
+// one thread per component (the candidate whose chain tail is the union-find root): replay the scan (AG:1972-1990) over the
+// component's start candidates, in node order
+__global__ void k_walk_components(DevView d, u32 n_cand) {
+    u32 i0 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i0 >= n_cand) return;
+    const u32 r = d.chain[d.cand_node[i0]].tail;
     if (d.parent[r] != r) return;
     ag_walkctx w = make_ctx(d);
-    u32 hi = d.cmax[r];
-    u32 i1 = d.cand_rank[hi + 1];
-    for (u32 i = d.cand_rank[d.cmin[r]]; i < i1; i++) {
+    const u32 hi = d.cmax[r];
+    for (u32 i = d.cmin[r]; i <= hi; i++) {
         if (d.cand_label[i] != r) continue;
         u32 v = d.cand_node[i];
         if (d.node_w[v].misc & AG_NW_TRAV) continue;
@@ -878,27 +891,21 @@ void AgDevice::build() {
 void AgDevice::walk_components() {
     Impl& m = *m_; cudaStream_t st = m.st; DevView& d = m.view; u32 nn = m.n_nodes;
     unsigned g = (nn + 255) / 256;
-    {
-        Timer tm(st);
-        k_uf_init<<<g, 256, 0, st>>>(d, nn); launches_++;
-        k_uf_edges<<<g, 256, 0, st>>>(d, nn); launches_++;
-        k_uf_chain<<<(m.n_ref + 255) / 256, 256, 0, st>>>(d); launches_++;
-        k_uf_flatten<<<g, 256, 0, st>>>(d, nn); launches_++;
-        t_.components += tm.stop();
-    }
     {   // forced-link chains
         Timer tm(st);
         m.indeg.ensure(nn + 1); m.fnext.ensure(nn + 1); m.chain_a.ensure(nn + 1); m.chain_b.ensure(nn + 1); m.changed.ensure(1);
         d.indeg = m.indeg.p; d.fnext = m.fnext.p; d.chain_a = m.chain_a.p; d.chain_b = m.chain_b.p; d.changed = m.changed.p;
         CK(cudaMemsetAsync(m.indeg.p, 0, (size_t)nn * sizeof(u32), st));
+        k_uf_init<<<g, 256, 0, st>>>(d, nn); launches_++;
         k_indeg<<<g, 256, 0, st>>>(d, nn); launches_++;
         k_links<<<g, 256, 0, st>>>(d, nn); launches_++;
         ag_chain *a = m.chain_a.p, *b = m.chain_b.p;
-        for (int round = 0; round < 32; round++) {
+        k_rank_local<<<(nn + 1023) / 1024, 1024, 0, st>>>(a, nn); launches_++;
+        for (int round = 0; round < 32; round++) {  // links that leave a 1024-node block: log2(blocks spanned) + 1 global rounds
             CK(cudaMemsetAsync(m.changed.p, 0, sizeof(int), st));
             k_rank<<<g, 256, 0, st>>>(a, b, nn, m.changed.p); launches_++;
             std::swap(a, b);
-            if (round >= 7) {  // chains shorter than 2^8 are done by now; afterwards ask the device
+            if (round >= 1) {
                 int ch = 0;
                 CK(cudaMemcpyAsync(&ch, m.changed.p, sizeof(int), cudaMemcpyDeviceToHost, st));
                 CK(cudaStreamSynchronize(st));
@@ -906,18 +913,29 @@ void AgDevice::walk_components() {
             }
         }
         d.chain = a;
-        // start candidates
+        // start candidates = chain heads, compacted in node order
         m.cand_rank.ensure((size_t)nn + 2); m.cand_node.ensure(nn + 1); m.cand_label.ensure(nn + 1);
         d.cand_rank = m.cand_rank.p; d.cand_node = m.cand_node.p; d.cand_label = m.cand_label.p;
         k_cand_flag<<<g, 256, 0, st>>>(d, nn, m.indeg.p); launches_++;
         m.scanner.run(m.indeg.p, m.cand_rank.p, nn, st);
         k_cand_scatter<<<g, 256, 0, st>>>(d, nn, m.indeg.p); launches_++;
         CK(cudaMemcpyAsync(&m.n_cand, m.cand_rank.p + nn, sizeof(u32), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
         t_.chains += tm.stop();
+    }
+    const u32 nc = m.n_cand;
+    t_.n_components = nc;
+    if (!nc) { chains_valid_ = true; return; }
+    unsigned gc = (nc + 255) / 256;
+    {
+        Timer tm(st);
+        k_uf_tails<<<gc, 256, 0, st>>>(d, nc); launches_++;
+        k_uf_flatten<<<gc, 256, 0, st>>>(d, nc); launches_++;
+        t_.components += tm.stop();
     }
     {
         Timer tm(st);
-        k_walk_components<<<g, 256, 0, st>>>(d, nn); launches_++;
+        k_walk_components<<<gc, 256, 0, st>>>(d, nc); launches_++;
         t_.walk += tm.stop();
     }
     chains_valid_ = true;

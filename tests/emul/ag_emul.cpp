@@ -158,26 +158,6 @@ public:
         walk_next.assign(n_nodes, AG_NONE); parent.resize(n_nodes);
         std::iota(parent.begin(), parent.end(), 0u);
         ag_cmtab ct = cmt();
-        for (u32 v = 0; v < n_nodes; v++) {  // k_uf_edges
-            if (!live(v)) continue;
-            const ag_nodew& w = node_w[v];
-            if (w.succ0 != AG_NONE && live(w.succ0)) unite(v, w.succ0);
-            if (w.succ1 != AG_NONE && live(w.succ1)) unite(v, w.succ1);
-            if (w.misc & AG_NW_OVF) for (u32 o = eovf_head[v]; o != AG_NONE; o = eovf_next[o]) if (live(eovf_target[o])) unite(v, eovf_target[o]);
-        }
-        for (u32 p = 0; p < in.n_ref; p++) {  // k_uf_chain
-            u32 c0 = ct.start[p];
-            if (ct.start[p + 1] - c0 != 1) continue;
-            ag_cm m = ct.cm[c0];
-            if (m.chain == m.term) continue;
-            u32 anchor = AG_NONE;
-            for (u32 x = pos_node[p]; x < pos_node[p + 1]; x++) if (live(x)) { if (anchor == AG_NONE) anchor = x; else unite(anchor, x); }
-            if (anchor == AG_NONE) continue;
-            u32 z = in.chain_pos[m.term];
-            for (u32 x = pos_node[z]; x < pos_node[z + 1]; x++) if (live(x)) unite(anchor, x);
-        }
-        std::vector<u32> cmin(n_nodes, AG_NONE), cmax(n_nodes, 0);
-        for (u32 v = 0; v < n_nodes; v++) if (live(v)) { u32 r = find(v); parent[v] = r; cmin[r] = std::min(cmin[r], v); cmax[r] = std::max(cmax[r], v); }
         // forced-link chains (k_indeg, k_links, list ranking)
         pos_term.assign((size_t)in.n_pos + 1, 0);
         for (u32 p = 0; p < in.n_pos; p++) for (u32 e = ct.start[p]; e < ct.start[p + 1]; e++) if (ct.cm[e].chain == ct.cm[e].term) pos_term[p] = 1;
@@ -201,16 +181,37 @@ public:
             }
             chain[v] = c;
         }
-        use_chains = !getenv("AG_EMUL_NO_CHAINS");
-        n_live = n_heads = 0; max_chain = 0;
-        for (u32 v = 0; v < n_nodes; v++) if (live(v)) { n_live++; if (!(node_w[v].misc & AG_NW_INTERIOR)) { n_heads++; max_chain = std::max(max_chain, chain[v].len); } }
+        use_chains = true;
+        // start candidates = chain heads in node order (k_cand_*)
+        std::vector<u32> cand;
+        n_live = 0; max_chain = 0;
+        for (u32 v = 0; v < n_nodes; v++) if (live(v)) { n_live++; if (!(node_w[v].misc & AG_NW_INTERIOR)) { cand.push_back(v); max_chain = std::max(max_chain, chain[v].len); } }
+        n_heads = (u32)cand.size();
+        // components over chain tails (k_uf_tails, k_uf_flatten)
+        for (u32 h : cand) {
+            const u32 t = chain[h].tail;
+            const ag_nodew& x = node_w[t];
+            if (x.succ0 != AG_NONE && live(x.succ0)) unite(t, chain[x.succ0].tail);
+            if (x.succ1 != AG_NONE && live(x.succ1)) unite(t, chain[x.succ1].tail);
+            if (x.misc & AG_NW_OVF) for (u32 o = eovf_head[t]; o != AG_NONE; o = eovf_next[o]) if (live(eovf_target[o])) unite(t, chain[eovf_target[o]].tail);
+            u32 p = node_pos[t], c0 = ct.start[p];
+            if (ct.start[p + 1] - c0 != 1) continue;
+            ag_cm m = ct.cm[c0];
+            if (m.chain == m.term) continue;
+            u32 z = in.chain_pos[m.term];
+            for (u32 y = pos_node[z]; y < pos_node[z + 1]; y++) if (live(y)) unite(t, chain[y].tail);
+        }
+        std::vector<u32> label(cand.size()), cmin(n_nodes, AG_NONE), cmax(n_nodes, 0);
+        for (u32 i = 0; i < cand.size(); i++) { u32 r = find(chain[cand[i]].tail); label[i] = r; cmin[r] = std::min(cmin[r], i); cmax[r] = std::max(cmax[r], i); }
         ag_walkctx w = ctx();
-        // components are replayed from the LAST root to the first to make sure nothing depends on cross-component order
-        for (u32 r = n_nodes; r-- > 0;) {
-            if (!live(r) || parent[r] != r) continue;
-            for (u32 v = cmin[r]; v <= cmax[r]; v++) {
-                if (node_w[v].misc & (AG_NW_TRAV | (use_chains ? AG_NW_INTERIOR : 0u))) continue;
-                if (parent[v] != r) continue;
+        // components are replayed from the LAST candidate's root to the first to make sure nothing depends on cross-component order
+        for (u32 i0 = (u32)cand.size(); i0-- > 0;) {
+            const u32 r = chain[cand[i0]].tail;
+            if (find(r) != r) continue;
+            for (u32 i = cmin[r]; i <= cmax[r]; i++) {
+                if (label[i] != r) continue;
+                u32 v = cand[i];
+                if (node_w[v].misc & AG_NW_TRAV) continue;
                 ag_walk x = ag_walk_from(w, v); fill_tail(x); walks.push_back(x);
             }
         }
