@@ -160,6 +160,7 @@ struct DevView {
     ag_walk* walks; ag_walk* walks_sorted; u32* walk_count; u32 walk_cap;
     int* err;
     int k, iv, coverage;
+    u32 rw;  // words per staged read (stride2 + stridem) when the tile sweeps keep the chunk's reads in shared memory, else 0
 };
 
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -210,7 +211,8 @@ __global__ void k_cm1(DevView d, ag_cm1* out, unsigned char* pos_term) {
 // ---------------------------------------------------------------------------------------------------------------------------
 constexpr int NCHUNK = 128;
 constexpr int NODE_SCAP = 3;                                   // nodes per position kept in shared memory; more spill to the pool
-constexpr int NODES_SMEM = 13 * NODE_SCAP * AG_TILE * 4;       // bytes of dynamic shared memory
+constexpr int NODES_SMEM = 13 * NODE_SCAP * AG_TILE * 4;       // bytes of dynamic shared memory for the node lists
+constexpr int READ_WORDS_MAX = 24;                             // stage reads of up to 256 bases (16 + 8 words) per chunk entry
 
 // one candidate when both sides have at most one contiMer (the common case), else the reference's nested enumeration
 template <class F> __device__ __forceinline__ void for_candidates_fast(const DevView& d, u32 q, const ag_cm1& ca, u32 mate, F f) {
@@ -224,6 +226,7 @@ template <class F> __device__ __forceinline__ void for_candidates_fast(const Dev
 
 __global__ void __launch_bounds__(AG_TILE) k_nodes(DevView d) {
     extern __shared__ u32 s_nodes[];
+    u32* const s_reads = s_nodes + 13 * NODE_SCAP * AG_TILE;   // [NCHUNK][rw] raw words of every chunk entry's left mate (bases, then mask)
     __shared__ ag_fast s_f[NCHUNK];
     __shared__ u32 s_idx[NCHUNK];
     __shared__ u32 s_scan[33];
@@ -243,6 +246,14 @@ __global__ void __launch_bounds__(AG_TILE) k_nodes(DevView d) {
             s_f[threadIdx.x] = ag_fast_prep(d.alnp[idx], d.lo[idx], d.span[idx]);
         }
         __syncthreads();
+        if (d.rw) {  // stage the left mates' packed bases + non-ACGT plane: two dependent global loads per touch become shared-memory reads
+            const u32 s2 = d.reads.stride2;
+            for (u32 w = threadIdx.x; w < cn * d.rw; w += AG_TILE) {
+                const u32 e = w / d.rw, j = w - e * d.rw, read = s_f[e].read >> 1;
+                s_reads[w] = j < s2 ? d.reads.bases[(u64)read * s2 + j] : d.reads.nmask[(u64)read * d.reads.stridem + (j - s2)];
+            }
+            __syncthreads();
+        }
         for (u32 r0 = 0; r0 < cn; r0 += 32) {
             // which of these 32 entries touch any of the warp's 32 positions?
             bool ov = false;
@@ -257,7 +268,14 @@ __global__ void __launch_bounds__(AG_TILE) k_nodes(DevView d) {
                 if (f.simple) t = ag_fast_touch(f, q, (u32)d.k);
                 else { t = ag_locate(d.alnp[s_idx[a]], d.ext, q, (u32)d.k); if (!t.kind) continue; }
                 int code = -1;
-                if (t.kind == 1 && t.slen) code = d.reads.code(f.read, f.lsrc_len >> 16, t.soff);
+                if (t.kind == 1 && t.slen) {
+                    if (d.rw) {
+                        const u32 rc = f.read & 1, len = f.lsrc_len >> 16, i = rc ? len - 1 - t.soff : t.soff;
+                        const u32* rd = s_reads + a * d.rw;
+                        if ((rd[d.reads.stride2 + (i >> 5)] >> (i & 31)) & 1) code = 4;
+                        else { u32 c = (rd[i >> 4] >> ((i & 15) * 2)) & 3; code = rc ? 3 - (int)c : (int)c; }
+                    } else code = d.reads.code(f.read, f.lsrc_len >> 16, t.soff);
+                }
                 const u32 sl = t.soff | (t.slen << 16);
                 const bool bump = t.kind == 1;
                 for_candidates_fast(d, q, ca, t.mate, [&](const ag_nodem& c) { ag_node_touch_v(nl, d.ovf, c, bump, code, f.read, sl, d.iv); });
@@ -796,7 +814,8 @@ void AgDevice::build() {
     m.cm1.ensure((size_t)n_pos + 2); d.cm1 = m.cm1.p; m.pos_term.ensure((size_t)n_pos + 2); d.pos_term = m.pos_term.p;
     if (n_pos) { k_cm1<<<(n_pos + 255) / 256, 256, 0, st>>>(d, m.cm1.p, m.pos_term.p); launches_++; }
     static bool attr_done = false;
-    if (!attr_done) { CK(cudaFuncSetAttribute(k_nodes, cudaFuncAttributeMaxDynamicSharedMemorySize, NODES_SMEM)); attr_done = true; }
+    if (!attr_done) { CK(cudaFuncSetAttribute(k_nodes, cudaFuncAttributeMaxDynamicSharedMemorySize, NODES_SMEM + NCHUNK * READ_WORDS_MAX * 4)); attr_done = true; }
+    d.rw = (m.reads.stride2 + m.reads.stridem <= (u32)READ_WORDS_MAX) ? m.reads.stride2 + m.reads.stridem : 0;
 
     // ---- prep + keys ------------------------------------------------------------------------------------------------
     {
@@ -842,7 +861,7 @@ void AgDevice::build() {
             m.ovf_node.ensure(m.ovf_cap); m.ovf_next.ensure(m.ovf_cap);
             d.pool = m.pool.p; d.pool_count = m.counters.p + 0; d.pool_cap = m.pool_cap;
             d.ovf.node = m.ovf_node.p; d.ovf.next = m.ovf_next.p; d.ovf.count = m.counters.p + 1; d.ovf.cap = m.ovf_cap; d.ovf.err = m.err.p;
-            if (m.n_tiles) { k_nodes<<<m.n_tiles, AG_TILE, NODES_SMEM, st>>>(d); launches_++; }
+            if (m.n_tiles) { k_nodes<<<m.n_tiles, AG_TILE, NODES_SMEM + NCHUNK * d.rw * 4, st>>>(d); launches_++; }
             int err = 0;
             CK(cudaMemcpyAsync(&err, m.err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));

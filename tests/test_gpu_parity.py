@@ -103,3 +103,16 @@ def test_full_size_properties(ag, harness, workdir):
     assert starts == sorted(starts) and len(starts) > 100
     assert all(set(l) <= set("ACGTN") for l in pre if not l.startswith(">"))
     assert st["n_nodes"] > 1000000
+
+
+def test_baseline_config1_full_size_against_oracle(ag, harness, workdir):
+    """BASELINE.json configs[1] at FULL size (4.6 Mbp unit, 1.15 M pairs 2x100 at 50x, k=5, coverage=20 — crosses the 1,000,000-pair
+    batch boundary of AlignGraph.cpp:1259): every per-unit output byte-identical to the CPU restatement."""
+    gpu = os.path.join(workdir, "gpu")
+    ora = os.path.join(workdir, "ora")
+    harness.synth(gpu, genome_bp=4600000, coverage=50, readlen=100, insert_mean=500, insert_sd=50, kmer=5, cov=20, seed=20260927)
+    shutil.copytree(gpu, ora)
+    harness.run_oracle(ora)
+    st, _ = run_cuda(ag, harness, gpu)
+    assert harness.unit_outputs(gpu, 0) == harness.unit_outputs(ora, 0)
+    assert st["n_aln"] > 1_100_000 and st["walk_fallback"] == 0
