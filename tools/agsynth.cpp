@@ -59,6 +59,7 @@ struct Params {
     int dist_low = 0, dist_high = 1500;
     int header = 0;            // write @SQ header lines into the SAM
     int misasm = 0;
+    int user_reads = 1;        // 0: skip reads_1.fa / reads_2.fa (only a fresh run needs them) to save disk on the big configs
 };
 
 static const char ACGT[5] = "ACGT";
@@ -149,6 +150,7 @@ int main(int argc, char** argv) {
         else if (a == "--ivar") p.ivar = atoi(val());
         else if (a == "--header") p.header = atoi(val());
         else if (a == "--misasm") p.misasm = atoi(val());
+        else if (a == "--user-reads") p.user_reads = atoi(val());
         else { fprintf(stderr, "agsynth: unknown option %s\n", a.c_str()); return 2; }
     }
     mkdir(p.out.c_str(), 0755);
@@ -275,8 +277,8 @@ int main(int argc, char** argv) {
             bool fwd_is_1 = rng.below(2) == 0;
             const std::string& s1 = fwd_is_1 ? fwd : rev;
             const std::string& s2 = fwd_is_1 ? rev : fwd;
-            for (Out* o : {&r1, &rall}) { o->putc_('>'); o->num(pair_id); o->putc_('\n'); o->put(s1); o->putc_('\n'); }
-            for (Out* o : {&r2, &rall}) { o->putc_('>'); o->num(pair_id); o->putc_('\n'); o->put(s2); o->putc_('\n'); }
+            for (Out* o : {&r1, &rall}) { if (o != &rall && !p.user_reads) continue; o->putc_('>'); o->num(pair_id); o->putc_('\n'); o->put(s1); o->putc_('\n'); }
+            for (Out* o : {&r2, &rall}) { if (o != &rall && !p.user_reads) continue; o->putc_('>'); o->num(pair_id); o->putc_('\n'); o->put(s2); o->putc_('\n'); }
 
             int c5f = 0, c3f = 0, c5r = 0, c3r = 0;
             if (p.softclip > 0 && rng.uni() < p.softclip) { c5f = (int)rng.below(12); c3f = (int)rng.below(12); }
