@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libaligngraph_b200.so")
 CLI = os.path.join(HERE, "bin", "AlignGraph")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function,-pthread"]
 
 
 def _newer(target, sources):

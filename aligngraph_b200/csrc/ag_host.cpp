@@ -8,6 +8,8 @@
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#include <thread>
+#include <atomic>
 
 namespace {
 
@@ -117,9 +119,86 @@ void ag_pack_reads(const std::vector<std::string>& seqs, AgReads& out) {
     }
 }
 
+static size_t parallel_min_bytes() {  // files smaller than this are parsed sequentially (AG_PARSE_PARALLEL_MIN overrides, for tests)
+    if (const char* e = getenv("AG_PARSE_PARALLEL_MIN")) return (size_t)atol(e);
+    return (size_t)1 << 22;
+}
+static int host_threads() {
+    if (const char* e = getenv("AG_THREADS")) { int n = atoi(e); if (n > 0) return n; }
+    unsigned h = std::thread::hardware_concurrency();
+    return (int)std::min<unsigned>(h ? h : 1, 32);
+}
+
+// Fast path for the file formalizeInput writes (AG:3455-3471): strictly alternating ">id" / one sequence line.  Chunks of the mapped
+// file are scanned and packed by several threads; anything irregular (multi-line record, empty line, odd record count, unequal mates)
+// returns false and the sequential parser below — the literal semantics — takes over.
+static bool parse_reads_parallel(const char* p, size_t n, AgReads& out) {
+    const int T = host_threads();
+    if (T <= 1 || n < parallel_min_bytes()) return false;
+    if (n == 0 || p[0] != '>' || p[n - 1] != '\n' || memmem(p, n, "\n\n", 2)) return false;
+    std::vector<size_t> cut((size_t)T + 1, n);
+    cut[0] = 0;
+    for (int t = 1; t < T; t++) {  // chunk starts: the next '>' that begins a line
+        size_t o = n / T * t;
+        const char* q = p + o;
+        for (;;) { q = (const char*)memchr(q, '>', (size_t)(p + n - q)); if (!q) break; if (q[-1] == '\n') break; q++; }
+        cut[t] = q ? (size_t)(q - p) : n;
+    }
+    for (int t = 1; t <= T; t++) if (cut[t] < cut[t - 1]) cut[t] = cut[t - 1];
+    std::vector<size_t> nrec((size_t)T, 0), maxlen((size_t)T, 0);
+    std::vector<char> bad((size_t)T, 0);
+    auto scan = [&](int t) {
+        const char* q = p + cut[t]; const char* e = p + cut[t + 1];
+        size_t cnt = 0, mx = 0;
+        while (q < e) {
+            if (*q != '>') { bad[t] = 1; return; }
+            const char* h = (const char*)memchr(q, '\n', (size_t)(e - q));
+            if (!h || h + 1 >= e) { bad[t] = 1; return; }
+            const char* sq = h + 1;
+            if (*sq == '>') { bad[t] = 1; return; }
+            const char* l = (const char*)memchr(sq, '\n', (size_t)(e - sq));
+            if (!l) { bad[t] = 1; return; }
+            mx = std::max(mx, (size_t)(l - sq)); cnt++;
+            q = l + 1;
+        }
+        nrec[t] = cnt; maxlen[t] = mx;
+    };
+    { std::vector<std::thread> th; for (int t = 0; t < T; t++) th.emplace_back(scan, t); for (auto& x : th) x.join(); }
+    size_t total = 0, mx = 0;
+    std::vector<size_t> base((size_t)T + 1, 0);
+    for (int t = 0; t < T; t++) { if (bad[t]) return false; base[t] = total; total += nrec[t]; mx = std::max(mx, maxlen[t]); }
+    if (total & 1 || mx > 65535) return false;
+    pack_init(out, total, (u32)mx);
+    std::vector<std::vector<std::pair<u64, char>>> exc((size_t)T);
+    std::vector<uint16_t> rlen(total);
+    auto pack = [&](int t) {
+        const char* q = p + cut[t]; const char* e = p + cut[t + 1];
+        size_t r = base[t];
+        u32* B = out.bases.data(); u32* M = out.nmask.data();
+        while (q < e) {
+            const char* sq = (const char*)memchr(q, '\n', (size_t)(e - q)) + 1;
+            const char* l = (const char*)memchr(sq, '\n', (size_t)(e - sq));
+            size_t len = (size_t)(l - sq);
+            u32* b = B + r * out.stride2; u32* m = M + r * out.stridem;
+            for (size_t i = 0; i < len; i++) {
+                int c = base_code(sq[i]);
+                if (c < 0) { m[i >> 5] |= 1u << (i & 31); exc[t].push_back({(u64)r * 65536 + i, sq[i]}); }
+                else b[i >> 4] |= (u32)c << ((i & 15) * 2);
+            }
+            rlen[r] = (uint16_t)len;
+            r++; q = l + 1;
+        }
+    };
+    { std::vector<std::thread> th; for (int t = 0; t < T; t++) th.emplace_back(pack, t); for (auto& x : th) x.join(); }
+    for (size_t i = 0; i + 1 < total; i += 2) { if (rlen[i] != rlen[i + 1]) throw AgHostError{"INCONSISTENT PE FILES!"}; out.len[i / 2] = rlen[i]; }
+    for (int t = 0; t < T; t++) out.exc.insert(out.exc.end(), exc[t].begin(), exc[t].end());
+    return true;
+}
+
 void ag_parse_reads(const std::string& path, AgReads& out) {
     FileMap fm(path);
     if (!fm.ok) throw AgHostError{"CANNOT OPEN FILE!"};
+    if (parse_reads_parallel(fm.p, fm.n, out)) return;
     // pass 1: record boundaries (a record = '>' line + the sequence lines up to the next '>'), AG:372-396
     struct Rec { const char* s; size_t n; bool multi; };
     std::vector<Rec> recs;
@@ -449,11 +528,137 @@ void normalize(const std::vector<ag_seg>& in, u32 rlen, std::vector<ag_seg>& out
 }
 }  // namespace
 
+// Parallel front half of ag_parse_sam for well-formed files ('@' lines only at the top, record pairs on consecutive lines, read ids
+// non-decreasing, no parse errors): threads turn text into per-pair records; the order-dependent part (1,000,000-pair batches and the
+// dropped record AG:1259, duplicate rule AG:1650-1655, strand check AG:1657-1671) then runs sequentially over those records exactly
+// as in the sequential parser.  Returns false (nothing changed) when the file is not of that form — the sequential parser decides.
+namespace {
+struct PRec { u32 sid; u32 flags; u32 p0; u32 seg_off; uint16_t n1, n2; };  // flags: bit0 fr1, bit1 fr2, bit2 passes AG:1261
+}
+static bool parse_sam_parallel(const char* p, size_t n, const AgReads& reads, AgUnit& u) {
+    const int T = host_threads();
+    if (T <= 1 || n < parallel_min_bytes()) return false;
+    size_t body = 0;
+    while (body < n && p[body] == '@') { const char* l = (const char*)memchr(p + body, '\n', n - body); if (!l) return false; body = (size_t)(l - p) + 1; }
+    if (body >= n || p[n - 1] != '\n' || memmem(p + body, n - body, "\n\n", 2) || p[body] == '\n') return false;
+    // chunk boundaries on line starts; parity fixed after counting lines
+    std::vector<size_t> cut((size_t)T + 1, n);
+    cut[0] = body;
+    for (int t = 1; t < T; t++) {
+        size_t o = body + (n - body) / T * t;
+        const char* l = (const char*)memchr(p + o, '\n', n - o);
+        cut[t] = l ? (size_t)(l - p) + 1 : n;
+    }
+    for (int t = 1; t <= T; t++) if (cut[t] < cut[t - 1]) cut[t] = cut[t - 1];
+    std::vector<size_t> nlines((size_t)T, 0);
+    {
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; t++) th.emplace_back([&, t]() { size_t c = 0; const char* q = p + cut[t]; const char* e = p + cut[t + 1]; while (q < e) { q = (const char*)memchr(q, '\n', (size_t)(e - q)) + 1; c++; } nlines[t] = c; });
+        for (auto& x : th) x.join();
+    }
+    size_t lines = 0;
+    for (int t = 0; t < T; t++) {   // a chunk must start on the first line of a pair
+        if (lines & 1) { const char* l = (const char*)memchr(p + cut[t], '\n', n - cut[t]); size_t nc = l ? (size_t)(l - p) + 1 : n; if (cut[t] < cut[t + 1]) { nlines[t]--; nlines[t - 1]++; lines++; } cut[t] = std::min(nc, cut[t + 1]); }
+        lines += nlines[t];
+    }
+    if (lines & 1) return false;  // BROKEN BOWTIE FILE territory: let the sequential parser report it
+    std::vector<std::vector<PRec>> recs((size_t)T);
+    std::vector<std::vector<ag_seg>> segs((size_t)T);
+    std::vector<char> bad((size_t)T, 0);
+    auto work = [&](int t) {
+        const char* q = p + cut[t]; const char* e = p + cut[t + 1];
+        std::vector<ag_seg> s1, s2, n1, n2;
+        recs[t].reserve((size_t)(e - q) / 140 + 16);
+        try {
+            while (q < e) {
+                const char* l1 = (const char*)memchr(q, '\n', (size_t)(e - q));
+                if (!l1 || l1 + 1 >= e) { bad[t] = 1; return; }
+                const char* l2 = (const char*)memchr(l1 + 1, '\n', (size_t)(e - l1 - 1));
+                if (!l2 || *q == '@') { bad[t] = 1; return; }
+                SamRec a, b;
+                s1.clear(); s2.clear();
+                parse_sam(q, (size_t)(l1 - q), a, s1);
+                parse_sam(l1 + 1, (size_t)(l2 - l1 - 1), b, s2);
+                PRec r; r.sid = a.sid; r.flags = a.fr | (b.fr << 1); r.p0 = pos_at0(s1); r.seg_off = (u32)segs[t].size(); r.n1 = r.n2 = 0;
+                bool pass = a.tid != AG_NONE && b.tid != AG_NONE &&
+                    (double)(a.send - a.sstart - a.sgap) / a.ssize >= kReadThreshold && (double)(a.tend - a.tstart - a.tgap) / (a.tend - a.tstart) >= kReadThreshold &&
+                    (double)(b.send - b.sstart - b.sgap) / b.ssize >= kReadThreshold && (double)(b.tend - b.tstart - b.tgap) / (b.tend - b.tstart) >= kReadThreshold;
+                if (pass) {
+                    if (a.tid != 0 || b.tid != 0 || b.sid != a.sid || a.sid >= reads.n_pairs) { bad[t] = 1; return; }
+                    u32 rlen = reads.len[a.sid];
+                    normalize(s1, rlen, n1); normalize(s2, rlen, n2);
+                    if (n1.empty() || n2.empty() || n1.size() > 255 || n2.size() > 255) { bad[t] = 1; return; }
+                    r.flags |= 4; r.n1 = (uint16_t)n1.size(); r.n2 = (uint16_t)n2.size();
+                    segs[t].insert(segs[t].end(), n1.begin(), n1.end()); segs[t].insert(segs[t].end(), n2.begin(), n2.end());
+                }
+                recs[t].push_back(r);
+                q = l2 + 1;
+            }
+        } catch (const AgHostError&) { bad[t] = 1; }
+    };
+    { std::vector<std::thread> th; for (int t = 0; t < T; t++) th.emplace_back(work, t); for (auto& x : th) x.join(); }
+    for (int t = 0; t < T; t++) if (bad[t]) return false;
+    u32 prev = 0; bool first_rec = true;
+    for (int t = 0; t < T; t++) for (const PRec& r : recs[t]) { if (!first_rec && r.sid < prev) return false; prev = r.sid; first_rec = false; }
+    // ---- sequential, order-dependent half (same logic as the sequential parser on already-parsed records) ----
+    u.aln.clear(); u.ext.clear();
+    const long n_pairs = (long)reads.n_pairs;
+    long first = 0, last = std::min<long>(kBatchPairs - 1, n_pairs - 1);
+    struct Grp { int t; size_t i; };
+    std::vector<Grp> group;   // surviving records of the current pair, in file order
+    auto flush_group = [&]() {
+        if (group.empty()) return;
+        const u32 rlen = reads.len[recs[group[0].t][group[0].i].sid];
+        for (size_t pp = 0; pp < group.size(); pp++) {
+            const PRec& r = recs[group[pp].t][group[pp].i];
+            bool dup = false;
+            for (size_t q = 0; q < pp && !dup; q++) { const PRec& o = recs[group[q].t][group[q].i]; if (absdiff(r.p0, o.p0) < (int)rlen) dup = true; }
+            if (dup) continue;
+            u32 fr1 = r.flags & 1, fr2 = (r.flags >> 1) & 1;
+            if (!((fr1 == 1 && fr2 == 0) || (fr2 == 1 && fr1 == 0))) throw AgHostError{"BOWTIE ALIGNMENT ERROR"};
+            const ag_seg* sg = segs[group[pp].t].data() + r.seg_off;
+            ag_aln a; a.pair = r.sid; a.pad = 0;
+            a.flags = fr1 | (fr2 << 1) | ((u32)r.n1 << 8) | ((u32)r.n2 << 16);
+            a.dst1 = sg[0].dst; a.sl1 = sg[0].src | (sg[0].len << 16);
+            a.dst2 = sg[r.n1].dst; a.sl2 = sg[r.n1].src | (sg[r.n1].len << 16);
+            a.ext_idx = (u32)u.ext.size();
+            if (r.n1 > 1) u.ext.insert(u.ext.end(), sg, sg + r.n1);
+            if (r.n2 > 1) u.ext.insert(u.ext.end(), sg + r.n1, sg + r.n1 + r.n2);
+            u.aln.push_back(a);
+        }
+        group.clear();
+    };
+    bool done = false;
+    u32 cur_pair = AG_NONE;
+    for (int t = 0; t < T && !done; t++)
+        for (size_t i = 0; i < recs[t].size(); i++) {
+            const PRec& r = recs[t][i];
+            // ids are non-decreasing and `first` only grows, so `r.sid < first` (AG:1258) cannot happen for a record that was not dropped
+            while ((long)r.sid > last) {   // AG:1259: this record is consumed and lost; the next batch starts with the following record
+                flush_group(); cur_pair = AG_NONE;
+                if (last >= n_pairs - 1) { done = true; break; }
+                first = last + 1; last = std::min<long>(first + kBatchPairs - 1, n_pairs - 1);
+                goto next_record;
+            }
+            if (done) break;
+            if ((long)r.sid < first) goto next_record;
+            if (r.flags & 4) {
+                if (r.sid != cur_pair) { flush_group(); cur_pair = r.sid; }
+                group.push_back(Grp{t, i});
+            }
+        next_record:;
+        }
+    flush_group();
+    return true;
+}
+
 void ag_parse_sam(const std::string& path, const AgReads& reads, AgUnit& u) {
     FileMap fm(path);
     if (!fm.ok) throw AgHostError{"CANNOT OPEN FILE!"};
     u.aln.clear(); u.ext.clear();
     if (reads.n_pairs == 0) return;
+    if (parse_sam_parallel(fm.p, fm.n, reads, u)) return;
+    u.aln.clear(); u.ext.clear();
     struct Tmp { u32 pair, fr1, fr2, p0; std::vector<ag_seg> s1, s2; };
     std::vector<Tmp> batch;
     std::vector<ag_seg> segs1, segs2, n1, n2;

@@ -56,7 +56,7 @@ def build_tools(with_ref=True, with_emul=True):
         deps = srcs + [os.path.join(csrc, f) for f in ("ag_core.h", "ag_types.h", "ag_pipeline.h", "ag_host.h", "ag_device.cuh")]
         if _stale(EMUL, deps):
             os.makedirs(os.path.dirname(EMUL), exist_ok=True)
-            _run([cxx, "-O2", "-std=c++17", "-o", EMUL] + srcs)
+            _run([cxx, "-O2", "-std=c++17", "-pthread", "-o", EMUL] + srcs)
     if with_ref and os.path.exists(REF_SRC):
         os.makedirs(REF, exist_ok=True)
         # the binary the reference ships next to its source: the only build that survives a FRESH run here — task0/task1 have no

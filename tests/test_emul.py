@@ -46,3 +46,12 @@ def test_emulation_generic_path_only(harness, workdir):
     harness.synth(workdir, **cases.GOLDEN["mix"])
     harness.run_emul(workdir, env={"AG_EMUL_FORCE_GENERIC": "1"})
     compare_with_golden(harness, workdir, "mix")
+
+
+@pytest.mark.parametrize("name", ["mix", "two_chr", "k7_150_2chr"])
+def test_parallel_text_parsers_match_golden(harness, workdir, name):
+    """The multi-threaded read / SAM parsers (used for large files) forced onto the small golden cases: '@' header, -k records,
+    unaligned records, soft clips, indels."""
+    harness.synth(workdir, **cases.GOLDEN[name])
+    harness.run_emul(workdir, env={"AG_PARSE_PARALLEL_MIN": "0", "AG_THREADS": "5"})
+    compare_with_golden(harness, workdir, name)
