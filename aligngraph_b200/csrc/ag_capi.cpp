@@ -52,7 +52,7 @@ int ag_set_reads(ag_ctx* ctx, const uint32_t* bases2, const uint32_t* nmask, con
         ctx->dev->unpin_all();
         AgReads& r = ctx->reads;
         r.n_pairs = n_pairs; r.stride2 = stride2; r.stridem = stridem;
-        r.bases.assign(bases2, bases2 + 2 * n_pairs * stride2); r.nmask.assign(nmask, nmask + 2 * n_pairs * stridem); r.len.assign(pair_len, pair_len + n_pairs);
+        r.bases.assign((const u32*)bases2, (const u32*)bases2 + 2 * n_pairs * stride2); r.nmask.assign((const u32*)nmask, (const u32*)nmask + 2 * n_pairs * stridem); r.len.assign(pair_len, pair_len + n_pairs);
         r.exc.clear();
         ctx->dev->set_reads(bases2, nmask, pair_len, n_pairs, stride2, stridem, false);
         ctx->have_reads = true;

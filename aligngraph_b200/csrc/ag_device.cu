@@ -344,7 +344,7 @@ __device__ __forceinline__ void add_edge(const DevView& d, u32 v, u32 tgt) {
     w->misc |= AG_NW_OVF;
 }
 
-__global__ void __launch_bounds__(AG_TILE) k_edges(DevView d) {
+__global__ void __launch_bounds__(AG_TILE, 5) k_edges(DevView d) {
     __shared__ ag_fast s_f[NCHUNK];
     __shared__ u32 s_idx[NCHUNK];
     const u32 tile = blockIdx.x, q = tile * AG_TILE + threadIdx.x, lane = threadIdx.x & 31;
@@ -632,6 +632,19 @@ __global__ void k_mat_detours(DevView d, const MatItem* __restrict__ items, cons
     for (u32 j = lane; j < it.n; j += 32) out[it.off + j] = d.chain_base[it.a + j];
 }
 
+// s[1..] of the last node of every selected walk that ended in the k-mer graph (AG:2164-2168); characters outside ACGT come out as 'N'
+// here and are restored on the host from the reads' exception list
+__global__ void k_mat_tails(DevView d, const u32* __restrict__ tails /* per walk: sread, soff_len, loop length */, const u64* __restrict__ offs, u32 n, unsigned char* out) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u32 sread = tails[3 * i], sl = tails[3 * i + 1], len = tails[3 * i + 2];
+    const u32 slen = sl >> 16, soff = sl & 0xFFFFu;
+    if (slen < 2) return;
+    const u32 rlen = d.reads.len[sread >> 2];
+    unsigned char* o = out + offs[i] + len;
+    for (u32 j = 1; j < slen; j++) { int c = d.reads.code(sread, rlen, soff + j); *o++ = (unsigned char)"ACGTN"[c]; }
+}
+
 __global__ void k_reset_marks(DevView d, u32 n_nodes) {
     u32 v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n_nodes) return;
@@ -677,7 +690,7 @@ struct AgDevice::Impl {
     DBuf<ag_nodem> node_m; DBuf<ag_nodew> node_w; DBuf<u32> node_sref, node_pos;
     DBuf<u32> eovf_head, eovf_target, eovf_next;
     DBuf<u32> walk_next, parent, cmin, cmax; DBuf<ag_walk> walks, walks2; DBuf<ag_cm1> cm1; DBuf<MatItem> mat_chains, mat_detours; u32 n_cand = 0; DBuf<unsigned char> pos_term; DBuf<u32> indeg, fnext, cand_rank, cand_node, cand_label; DBuf<ag_chain> chain_a, chain_b; DBuf<int> changed;
-    DBuf<unsigned char> out_bases, occ; DBuf<u32> sel_start; DBuf<u64> sel_off;
+    DBuf<unsigned char> out_bases, occ; DBuf<u32> sel_start, sel_tails; DBuf<u64> sel_off;
     Scanner scanner;
     u32 n_tiles = 0, n_keys = 0, n_nodes = 0;
     u32 pool_cap = 0, ovf_cap = 0, eovf_cap = 0, walk_cap = 0;
@@ -703,7 +716,7 @@ AgDevice::~AgDevice() {
     for (auto* b : b8) b->release();
     DBuf<u32>* b32[] = {&m.cm_start, &m.chain_pos, &m.lo, &m.span, &m.ntiles, &m.key_off, &m.keys, &m.vals, &m.keys2, &m.vals2, &m.hist, &m.tile_cnt,
                         &m.tile_start, &m.ovf_next, &m.counters, &m.pos_cnt, &m.pos_pool, &m.pos_node, &m.node_sref, &m.node_pos, &m.eovf_head,
-                        &m.eovf_target, &m.eovf_next, &m.walk_next, &m.parent, &m.cmin, &m.cmax, &m.sel_start};
+                        &m.eovf_target, &m.eovf_next, &m.walk_next, &m.parent, &m.cmin, &m.cmax, &m.sel_start, &m.sel_tails};
     for (auto* b : b32) b->release();
     for (int i = 0; i < 4; i++) m.scanner.lvl[i].release();
     m.cm.release(); m.aln.release(); m.ext.release(); m.alnp.release(); m.pool.release(); m.ovf_node.release(); m.err.release();
@@ -1024,11 +1037,18 @@ void AgDevice::materialize(const std::vector<ag_walk>& walks, const std::vector<
     Impl& m = *m_; cudaStream_t st = m.st; DevView& d = m.view;
     offs.assign(sel.size() + 1, 0);
     std::vector<u32> starts(sel.size());
-    for (size_t i = 0; i < sel.size(); i++) { starts[i] = walks[sel[i]].start_node; offs[i + 1] = offs[i] + walks[sel[i]].len; }
+    std::vector<u32> tails(3 * sel.size());
+    for (size_t i = 0; i < sel.size(); i++) {
+        const ag_walk& r = walks[sel[i]];
+        u32 tl = ag_walk_tail_len(r);
+        starts[i] = r.start_node; offs[i + 1] = offs[i] + r.len + tl;
+        tails[3 * i] = r.tail_sread; tails[3 * i + 1] = tl ? r.tail_soff_len : 0; tails[3 * i + 2] = r.len;
+    }
     bases.assign(offs.back(), '\0');
     if (sel.empty()) return;
     Timer tm(st);
-    m.sel_start.ensure(sel.size() + 1); m.sel_off.ensure(sel.size() + 1); m.out_bases.ensure(offs.back() + 1);
+    m.sel_start.ensure(sel.size() + 1); m.sel_off.ensure(sel.size() + 1); m.out_bases.ensure(offs.back() + 1); m.sel_tails.ensure(3 * sel.size() + 1);
+    CK(cudaMemcpyAsync(m.sel_tails.p, tails.data(), tails.size() * sizeof(u32), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(m.sel_start.p, starts.data(), starts.size() * sizeof(u32), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(m.sel_off.p, offs.data(), sel.size() * sizeof(u64), cudaMemcpyHostToDevice, st));
     if (chains_valid_) {
@@ -1041,6 +1061,7 @@ void AgDevice::materialize(const std::vector<ag_walk>& walks, const std::vector<
     } else {
         k_materialize<<<((u32)sel.size() + 127) / 128, 128, 0, st>>>(d, m.sel_start.p, m.sel_off.p, (u32)sel.size(), m.out_bases.p, 0); launches_++;
     }
+    k_mat_tails<<<((u32)sel.size() + 127) / 128, 128, 0, st>>>(d, m.sel_tails.p, m.sel_off.p, (u32)sel.size(), m.out_bases.p); launches_++;
     CK(cudaMemcpyAsync(&bases[0], m.out_bases.p, offs.back(), cudaMemcpyDeviceToHost, st));
     int err = 0;
     CK(cudaMemcpyAsync(&err, m.err.p, sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -9,6 +9,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 #include <thread>
+#include <mutex>
 #include <atomic>
 
 namespace {
@@ -95,7 +96,7 @@ static inline int base_code(char c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 
 static void pack_init(AgReads& out, size_t n_reads, u32 maxlen) {
     out.stride2 = (maxlen + 15) / 16; out.stridem = (maxlen + 31) / 32;
     if (!out.stride2) out.stride2 = out.stridem = 1;
-    out.bases.assign(n_reads * out.stride2, 0); out.nmask.assign(n_reads * out.stridem, 0);
+    out.bases.assign_zero(n_reads * out.stride2); out.nmask.assign_zero(n_reads * out.stridem);
     out.n_pairs = n_reads / 2; out.len.assign(out.n_pairs, 0); out.exc.clear();
 }
 static void pack_one(AgReads& out, size_t r, const char* s, size_t n) {
@@ -308,22 +309,39 @@ int keep_set(std::vector<Chunk>& ch, u32 sid, double thr) {
 }
 }  // namespace
 
-void ag_thread_contigs(const std::string& contigs_fa, const std::string& psl_path, std::string& initial_text, AgUnit& u) {
-    // ---- chunks (AG:322-359) ----
-    std::vector<Chunk> ch;
-    {
+// tmp/_contigs.fa is the same for every unit (the reference re-reads it per chromosome, AG:1225-1228): parse it once per file version
+namespace {
+struct ChunkCache { std::string path; long size = -1, mtime = -1, mtime_ns = -1; std::vector<std::pair<int, std::string>> chunks; };
+std::mutex g_chunk_mu;
+ChunkCache g_chunk_cache;
+}
+static void load_chunks(const std::string& contigs_fa, std::vector<Chunk>& ch) {
+    std::lock_guard<std::mutex> lk(g_chunk_mu);
+    struct stat st;
+    if (stat(contigs_fa.c_str(), &st) != 0) throw AgHostError{"CANNOT OPEN FILE!"};
+    ChunkCache& c = g_chunk_cache;
+    if (c.path != contigs_fa || c.size != (long)st.st_size || c.mtime != (long)st.st_mtim.tv_sec || c.mtime_ns != (long)st.st_mtim.tv_nsec) {
         FileMap fm(contigs_fa);
         if (!fm.ok) throw AgHostError{"CANNOT OPEN FILE!"};
+        c.chunks.clear();
         Lines ln(fm.p, fm.n); const char* s; size_t n;
-        while (ln.next(s, n)) {
+        while (ln.next(s, n)) {   // AG:322-359
             if (n == 0 || s[0] == 0) break;
             if (s[0] == '>') {
                 const char* dot = (const char*)memchr(s, '.', n);
-                Chunk c; c.id = dot ? ag_atoi(dot + 1, (size_t)(s + n - dot - 1)) : 0;
-                ch.push_back(std::move(c));
-            } else if (!ch.empty()) ch.back().bases.append(s, n);
+                c.chunks.emplace_back(dot ? ag_atoi(dot + 1, (size_t)(s + n - dot - 1)) : 0, std::string());
+            } else if (!c.chunks.empty()) c.chunks.back().second.append(s, n);
         }
+        c.path = contigs_fa; c.size = (long)st.st_size; c.mtime = (long)st.st_mtim.tv_sec; c.mtime_ns = (long)st.st_mtim.tv_nsec;
     }
+    ch.resize(c.chunks.size());
+    for (size_t i = 0; i < ch.size(); i++) { ch[i].id = c.chunks[i].first; ch[i].bases = c.chunks[i].second; }
+}
+
+void ag_thread_contigs(const std::string& contigs_fa, const std::string& psl_path, std::string& initial_text, AgUnit& u) {
+    // ---- chunks (AG:322-359) ----
+    std::vector<Chunk> ch;
+    load_chunks(contigs_fa, ch);
     // ---- PSL -> position sets (AG:817-852 with updateContig AG:763-815) ----
     {
         FileMap fm(psl_path);
@@ -742,31 +760,35 @@ void ag_select_emitted(const std::vector<ag_walk>& walks, std::vector<u32>& sel)
     }
 }
 
-void ag_make_contigs(const std::vector<ag_walk>& walks, const std::vector<u32>& sel, const std::string& bases, const std::vector<u64>& offs,
+void ag_make_contigs(const std::vector<ag_walk>& walks, const std::vector<u32>& sel, std::string& bases, const std::vector<u64>& offs,
                      const AgReads& reads, std::vector<AgContig>& contigs, std::string& pre_text) {
     Out out(&pre_text);
-    contigs.clear(); contigs.reserve(sel.size());
+    out.b->reserve(bases.size() + bases.size() / 60 + sel.size() * 96 + 64);
+    contigs.clear(); contigs.resize(sel.size());
+    const bool patch = !reads.exc.empty();
     for (size_t i = 0; i < sel.size(); i++) {
         const ag_walk& r = walks[sel[i]];
-        AgContig c;
+        AgContig& c = contigs[i];
         c.extended = (int)(r.flags & 1);
         c.sid = 0; c.soff = r.soff; c.eid = 0; c.eoff = r.eoff;
         c.sid0 = r.soff0 == AG_NONE ? AG_NONE : 0; c.soff0 = r.soff0;
-        c.bases.assign(bases, offs[i], offs[i + 1] - offs[i]);
+        c.p = bases.data() + offs[i]; c.n = (size_t)(offs[i + 1] - offs[i]);
         u32 mode = (r.flags >> 1) & 3;
         if (mode == 1) { c.eid0 = AG_NONE; c.eoff0 = AG_NONE; }  // walk ended on a contiMer (AG:2158-2162)
         else {
             c.eid0 = r.eoff0 == AG_NONE ? AG_NONE : 0; c.eoff0 = r.eoff0;
             u32 slen = r.tail_soff_len >> 16, soff = r.tail_soff_len & 0xFFFFu, read = r.tail_sread >> 1, rc = r.tail_sread & 1;
-            u32 rlen = slen ? reads.len[read >> 1] : 0;
-            for (u32 j = 1; j < slen; j++) c.bases.push_back(reads.at(read, rc, rlen, soff + j));
-            c.eoff = c.eoff + slen - 1; c.eoff0 = c.eoff0 + slen - 1;
+            if (patch && slen > 1) {  // the device wrote 'N' for every masked base; put the original characters back (AG:2167 copies s verbatim)
+                u32 rlen = reads.len[read >> 1];
+                char* t = &bases[offs[i] + r.len];
+                for (u32 j = 1; j < slen; j++) t[j - 1] = reads.at(read, rc, rlen, soff + j);
+            }
+            c.eoff = c.eoff + slen - 1; c.eoff0 = c.eoff0 + slen - 1;   // size_t arithmetic truncated to u32 (AG:2170-2171)
         }
         out.ch('>'); out.num(i); out.put(", ", 2); out.inum(c.extended); out.put(", ", 2);
         out.num(c.sid); out.put(", ", 2); out.num(c.soff); out.put(", ", 2); out.num(c.eid); out.put(", ", 2); out.num(c.eoff); out.put(", ", 2);
         out.num(c.sid0); out.put(", ", 2); out.num(c.soff0); out.put(", ", 2); out.num(c.eid0); out.put(", ", 2); out.num(c.eoff0); out.put(" \n", 2);
-        out.wrap60(c.bases);
-        contigs.push_back(std::move(c));
+        out.wrap60(c.p, c.n);
     }
 }
 
@@ -799,7 +821,10 @@ void ag_dedup_join(std::vector<AgContig>& cs) {
             AgContig& t = cs[lastb];
             t.extended = 2;
             u32 from = cs[a].eoff - t.soff + 1;
-            if (from < t.bases.size()) cs[a].bases.append(t.bases, from, std::string::npos);
+            if (from < t.size()) {
+                if (cs[a].own.empty()) cs[a].own.assign(cs[a].p, cs[a].n);
+                cs[a].own.append(t.data() + from, t.size() - from);
+            }
             cs[a].eid = t.eid; cs[a].eoff = t.eoff; cs[a].eid0 = t.eid0; cs[a].eoff0 = t.eoff0;
         }
     }
@@ -819,7 +844,7 @@ void ag_scaffold(std::vector<AgContig>& cs, const std::string& ref, const std::v
     for (u32 i = 0; i < cs.size(); i++) if (cs[i].extended == 1) ext1.push_back(i);
     for (u32 cp = 0; cp < cs.size(); cp++) {
         if (!(cs[cp].sid != AG_NONE && cs[cp].extended == 1)) continue;
-        sc.push_back(cs[cp].bases);
+        sc.emplace_back(cs[cp].data(), cs[cp].size());
         cs[cp].sid = AG_NONE;
         int cont = 1;
         while (cs[cp].sid0 == cs[cp].eid0 && cont) {
@@ -834,7 +859,7 @@ void ag_scaffold(std::vector<AgContig>& cs, const std::string& ref, const std::v
                     if ((gap != 0 && (double)covered / gap >= 0.5) || gap == 0) { for (u32 i = 0; i < gap; i++) sc.back().push_back(ref[a.eoff + i + 1]); }
                     else continue;
                 }
-                sc.back() += b.bases;
+                sc.back().append(b.data(), b.size());
                 b.sid = AG_NONE;
                 cp = c0; cont = 1;
                 break;

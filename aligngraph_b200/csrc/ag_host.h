@@ -6,12 +6,30 @@
 #include <string>
 #include <vector>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 
-struct AgHostError { std::string msg; };  // message the CLI prints on stdout before exit(-1), as the reference does
+struct AgHostError { std::string msg; };
+
+// Zero-initialised growable array backed by calloc: large blocks come from fresh (already zero) pages that are first touched by whoever
+// writes them — the parallel packers — instead of being memset by one thread as std::vector would do.
+template <class T> struct AgZVec {
+    T* p = nullptr; size_t n = 0;
+    AgZVec() {}
+    AgZVec(const AgZVec& o) { assign(o.p, o.p + o.n); }
+    AgZVec& operator=(const AgZVec& o) { if (this != &o) assign(o.p, o.p + o.n); return *this; }
+    ~AgZVec() { free(p); }
+    void assign_zero(size_t count) { free(p); p = count ? (T*)calloc(count, sizeof(T)) : nullptr; n = count; if (count && !p) throw AgHostError{"out of host memory"}; }
+    void assign(const T* b, const T* e) { assign_zero((size_t)(e - b)); if (n) memcpy(p, b, n * sizeof(T)); }
+    void resize(size_t count) { assign_zero(count); }
+    T* data() { return p; } const T* data() const { return p; }
+    size_t size() const { return n; }
+    T& operator[](size_t i) { return p[i]; } const T& operator[](size_t i) const { return p[i]; }
+};  // message the CLI prints on stdout before exit(-1), as the reference does
 
 // ---- reads (tmp/_reads.fa, AG:361-404) -----------------------------------------------------------------------------------
 struct AgReads {
-    std::vector<u32> bases, nmask;   // 2 bits / base, 16 per word; 1 bit / base, 32 per word; fixed stride per read
+    AgZVec<u32> bases, nmask;        // 2 bits / base, 16 per word; 1 bit / base, 32 per word; fixed stride per read
     std::vector<uint16_t> len;       // per pair
     std::vector<std::pair<u64, char>> exc;  // (read * 65536 + offset, original character) for every non-ACGT character, sorted
     u64 n_pairs = 0;
@@ -40,11 +58,18 @@ void ag_thread_contigs(const std::string& contigs_fa, const std::string& psl, st
 void ag_parse_sam(const std::string& path, const AgReads& reads, AgUnit& u);
 
 // ---- post passes --------------------------------------------------------------------------------------------------------------------
-struct AgContig { int extended; u32 sid, soff, eid, eoff, sid0, soff0, eid0, eoff0; std::string bases; };
+struct AgContig {
+    int extended; u32 sid, soff, eid, eoff, sid0, soff0, eid0, eoff0;
+    const char* p = nullptr; size_t n = 0;  // bases: a view into the materialised buffer ...
+    std::string own;                        // ... or an owned string once the contig has been joined with another (AG:2368-2370)
+    const char* data() const { return own.empty() ? p : own.data(); }
+    size_t size() const { return own.empty() ? n : own.size(); }
+};
 // emission filter of extdContigs1 (AG:2176-2189): indices of the walks that are written to _pre_extended_contigs
 void ag_select_emitted(const std::vector<ag_walk>& walks, std::vector<u32>& sel);
-// assemble emitted contigs (bases from the device + s[1..] tails from the reads) + the text of tmp/_pre_extended_contigs.N.fa
-void ag_make_contigs(const std::vector<ag_walk>& walks, const std::vector<u32>& sel, const std::string& bases, const std::vector<u64>& offs,
+// emitted contigs as views into `bases` (loop bases + s[1..] tail per walk, written by the device; characters outside ACGT are
+// restored here from the reads' exception list) + the text of tmp/_pre_extended_contigs.N.fa
+void ag_make_contigs(const std::vector<ag_walk>& walks, const std::vector<u32>& sel, std::string& bases, const std::vector<u64>& offs,
                      const AgReads& reads, std::vector<AgContig>& contigs, std::string& pre_text);
 void ag_dedup_join(std::vector<AgContig>& contigs);                                               // AG:2296-2380
 // AG:2396-2464; occ = bitmap "position holds a node or a contiMer"

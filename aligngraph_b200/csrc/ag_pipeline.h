@@ -26,9 +26,15 @@ inline AgUnitInput ag_unit_input(const AgUnit& u) {
 // loadGenome + loadContigAlignment + the parsing half of loadReadAlignment (AG:4768-4772)
 inline void ag_prepare_unit(const AgReads& reads, const std::string& tmp, int unit, AgUnit& u, std::string& initial_text) {
     std::string n = std::to_string(unit);
+    auto t0 = std::chrono::steady_clock::now();
     ag_load_genome(tmp + "/_genome." + n + ".fa", u);
+    auto t1 = std::chrono::steady_clock::now();
     ag_thread_contigs(tmp + "/_contigs.fa", tmp + "/_contigs_genome." + n + ".psl", initial_text, u);
+    auto t2 = std::chrono::steady_clock::now();
     ag_parse_sam(tmp + "/_reads_genome." + n + ".bowtie", reads, u);
+    auto t3 = std::chrono::steady_clock::now();
+    if (getenv("AG_POST_TIMING")) fprintf(stderr, "[parse] genome %.1f ms, contigs %.1f ms, sam %.1f ms\n", std::chrono::duration<double>(t1 - t0).count() * 1e3,
+                                          std::chrono::duration<double>(t2 - t1).count() * 1e3, std::chrono::duration<double>(t3 - t2).count() * 1e3);
 }
 
 // graph build + extendContigs + scaffoldContigs on prepared arrays

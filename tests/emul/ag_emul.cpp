@@ -247,7 +247,7 @@ public:
 
     void materialize(const std::vector<ag_walk>& walks, const std::vector<u32>& sel, std::string& bases, std::vector<u64>& offs) {
         offs.assign(sel.size() + 1, 0);
-        for (size_t i = 0; i < sel.size(); i++) offs[i + 1] = offs[i] + walks[sel[i]].len;
+        for (size_t i = 0; i < sel.size(); i++) offs[i + 1] = offs[i] + walks[sel[i]].len + ag_walk_tail_len(walks[sel[i]]);
         bases.assign(offs.back(), '\0');
         ag_cmtab ct = cmt();
         for (size_t i = 0; i < sel.size(); i++) {
@@ -255,6 +255,11 @@ public:
             for (u32 v = walks[sel[i]].start_node; v != AG_NONE; v = (use_chains && fnext[v] != AG_NONE) ? fnext[v] : walk_next[v]) {
                 bases[o++] = (char)(node_w[v].misc & 0xFF);
                 if (node_w[v].misc & AG_NW_DETOUR) { ag_cm m = ct.cm[ct.start[node_pos[v]]]; for (u32 e = m.chain + 1; e <= m.term; e++) bases[o++] = in.chain_base[e]; }
+            }
+            {   // k_mat_tails
+                const ag_walk& r = walks[sel[i]];
+                u32 tl = ag_walk_tail_len(r), slen = r.tail_soff_len >> 16, soff = r.tail_soff_len & 0xFFFFu;
+                if (tl) { u32 rlen = rd.len[r.tail_sread >> 2]; for (u32 j = 1; j < slen; j++) bases[o++] = "ACGTN"[rd.code(r.tail_sread, rlen, soff + j)]; }
             }
             if (o != offs[i + 1]) throw AgHostError{"emul: walk length mismatch"};
         }
