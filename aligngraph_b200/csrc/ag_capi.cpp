@@ -2,6 +2,7 @@
 // exceptions into error codes.  All graph work happens in AgDevice (ag_device.cu).
 #include "../../include/aligngraph_b200.h"
 #include "ag_pipeline.h"
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -35,6 +36,7 @@ extern "C" {
 
 int ag_create(const ag_params* params, ag_ctx** out) {
     if (!params || !out) { g_create_error = "null argument"; return 1; }
+    ag_tune_malloc();
     ag_ctx* c = new (std::nothrow) ag_ctx;
     if (!c) { g_create_error = "out of host memory"; return 3; }
     c->params = *params;

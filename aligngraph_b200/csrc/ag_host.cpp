@@ -8,6 +8,7 @@
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#include <malloc.h>
 #include <thread>
 #include <mutex>
 #include <atomic>
@@ -1156,4 +1157,16 @@ void ag_refinement(const std::string& tmp, int units, const std::vector<std::str
     }
     if (test_in) for (size_t i = 0; i < init_tags.size(); i++) if (init_tags[i] == 1) { test_in->ch('>'); test_in->num(i); test_in->ch('\n'); test_in->wrap60(init[i]); }
     delete test_in; delete test_ex;
+}
+
+// The host side stages hundreds of MB per unit in vectors.  By default glibc serves such blocks with mmap and returns them on free, so
+// every unit pays the page faults (and the kernel's page zeroing) again; keeping them on the heap makes the second and later units run
+// on warm memory.  Opt out with AG_NO_MALLOPT=1.
+void ag_tune_malloc() {
+    static bool done = false;
+    if (done || getenv("AG_NO_MALLOPT")) return;
+    done = true;
+    mallopt(M_MMAP_MAX, 0);
+    mallopt(M_TRIM_THRESHOLD, 0x7FFFFFFF);
+    mallopt(M_TOP_PAD, 64 << 20);
 }

@@ -79,6 +79,8 @@ void ag_scaffold(std::vector<AgContig>& contigs, const std::string& ref, const s
 void ag_formalize_contigs(const std::string& in_path, const std::string& tmp, std::vector<std::string>& contig_ids);
 int ag_formalize_genome(const std::string& in_path, const std::string& tmp, int part, std::vector<std::string>& genome_ids);
 void ag_write_file(const std::string& path, const std::string& text);
+// glibc tuning for the staging buffers (see ag_host.cpp); no-op when AG_NO_MALLOPT is set
+void ag_tune_malloc();
 
 // ---- CLI phases outside the hot path (drop-in compatibility) ----------------------------------------------------------------
 int ag_max_read_length(const std::string& path);                                                        // AG:3197

@@ -304,6 +304,7 @@ int main(int argc, char** argv) {
         else if (a == "--last") last = atoi(argv[++i]);
         else { fprintf(stderr, "ag_emul: unknown option %s\n", a.c_str()); return 2; }
     }
+    ag_tune_malloc();
     try {
         if (chdir(dir.c_str()) != 0) throw AgHostError{"CANNOT OPEN FILE!"};
         int k = 5, iv = 50, cov = 20, part = 1;
