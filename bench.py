@@ -314,6 +314,11 @@ def b200_arm(args):
         achieved = alg / nodes_ms / 1e6
         pairs = UNIT_BP * 50 // 200
         k1_equiv = pairs * (2 * ((L + 3) // 4) + 32 + 16 * (L - SHAPE["kmer"])) / ((st["ms_prep"] + st["ms_sort"] + st["ms_nodes"]) / K) / 1e6
+        traffic = None
+        try:   # DRAM bytes of one k_nodes launch from the committed `ncu --set full` capture of this same workload (profiles/README.md)
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["traffic"]
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": round(mbp * K / (ms / 1000), 3), "unit": "Mbp/s", "n_gpus": n, "steps": K, "warmup": max(args.warmup, 3),
             "ms_per_step": round(ms / K, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
@@ -323,7 +328,7 @@ def b200_arm(args):
             "gpu_launches": int(st["kernel_launches"]),
             "clocks": clock_info,
             "roofline": {"bound": "hbm", "kernel": "k_nodes", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                         "traffic": None, "alg_bytes_per_launch": int(alg), "ms_per_launch": round(nodes_ms, 4),
+                         "traffic": traffic, "alg_bytes_per_launch": int(alg), "ms_per_launch": round(nodes_ms, 4),
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                          "survey_k1_equiv_gbs": round(k1_equiv, 1)},
             "device_ms_per_step": {k[3:]: round(st[k] / K, 4) for k in st if k.startswith("ms_")},
