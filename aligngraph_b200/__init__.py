@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libaligngraph_b200.so")
+LIB_PATH = os.environ.get("AG_LIB_PATH") or os.path.join(_HERE, "libaligngraph_b200.so")  # AG_LIB_PATH: tuning variants only
 HEADER_PATH = os.path.join(_HERE, "..", "include", "aligngraph_b200.h")
 
 

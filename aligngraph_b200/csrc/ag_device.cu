@@ -209,8 +209,20 @@ __global__ void k_cm1(DevView d, ag_cm1* out, unsigned char* pos_term) {
 // alignment), each warp keeps only the entries that overlap its 32 positions (ballot), and every thread replays the reference's
 // first-compatible clustering on a node list held in shared memory ([field][node][thread], conflict-free).
 // ---------------------------------------------------------------------------------------------------------------------------
-constexpr int NCHUNK = 128;
-constexpr int NODE_SCAP = 3;                                   // nodes per position kept in shared memory; more spill to the pool
+#ifndef AG_NCHUNK
+#define AG_NCHUNK 128
+#endif
+#ifndef AG_NODE_SCAP
+#define AG_NODE_SCAP 3
+#endif
+#ifndef AG_NODES_MINB
+#define AG_NODES_MINB 5
+#endif
+#ifndef AG_EDGES_MINB
+#define AG_EDGES_MINB 5
+#endif
+constexpr int NCHUNK = AG_NCHUNK;
+constexpr int NODE_SCAP = AG_NODE_SCAP;                                   // nodes per position kept in shared memory; more spill to the pool
 constexpr int NODES_SMEM = 13 * NODE_SCAP * AG_TILE * 4;       // bytes of dynamic shared memory for the node lists
 constexpr int READ_WORDS_MAX = 24;                             // stage reads of up to 256 bases (16 + 8 words) per chunk entry
 
@@ -224,7 +236,7 @@ template <class F> __device__ __forceinline__ void for_candidates_fast(const Dev
     } else ag_for_candidates(d.cmt, q, mate, f);
 }
 
-__global__ void __launch_bounds__(AG_TILE) k_nodes(DevView d) {
+__global__ void __launch_bounds__(AG_TILE, AG_NODES_MINB) k_nodes(DevView d) {
     extern __shared__ u32 s_nodes[];
     u32* const s_reads = s_nodes + 13 * NODE_SCAP * AG_TILE;   // [NCHUNK][rw] raw words of every chunk entry's left mate (bases, then mask)
     __shared__ ag_fast s_f[NCHUNK];
@@ -344,7 +356,7 @@ __device__ __forceinline__ void add_edge(const DevView& d, u32 v, u32 tgt) {
     w->misc |= AG_NW_OVF;
 }
 
-__global__ void __launch_bounds__(AG_TILE, 5) k_edges(DevView d) {
+__global__ void __launch_bounds__(AG_TILE, AG_EDGES_MINB) k_edges(DevView d) {
     __shared__ ag_fast s_f[NCHUNK];
     __shared__ u32 s_idx[NCHUNK];
     const u32 tile = blockIdx.x, q = tile * AG_TILE + threadIdx.x, lane = threadIdx.x & 31;
