@@ -213,15 +213,19 @@ __global__ void k_cm1(DevView d, ag_cm1* out, unsigned char* pos_term) {
 #define AG_NCHUNK 128
 #endif
 #ifndef AG_NODE_SCAP
-#define AG_NODE_SCAP 3
+#define AG_NODE_SCAP 2
 #endif
 #ifndef AG_NODES_MINB
-#define AG_NODES_MINB 5
+#define AG_NODES_MINB 6
 #endif
 #ifndef AG_EDGES_MINB
 #define AG_EDGES_MINB 5
 #endif
-constexpr int NCHUNK = AG_NCHUNK;
+#ifndef AG_NCHUNK_NODES
+#define AG_NCHUNK_NODES 64
+#endif
+constexpr int NCHUNK = AG_NCHUNK;            // chunk of tile alignments staged per round in k_edges
+constexpr int NCHUNK_N = AG_NCHUNK_NODES;    // ... in k_nodes (smaller: its shared memory also holds the node lists and the reads)
 constexpr int NODE_SCAP = AG_NODE_SCAP;                                   // nodes per position kept in shared memory; more spill to the pool
 constexpr int NODES_SMEM = 13 * NODE_SCAP * AG_TILE * 4;       // bytes of dynamic shared memory for the node lists
 constexpr int READ_WORDS_MAX = 24;                             // stage reads of up to 256 bases (16 + 8 words) per chunk entry
@@ -238,9 +242,9 @@ template <class F> __device__ __forceinline__ void for_candidates_fast(const Dev
 
 __global__ void __launch_bounds__(AG_TILE, AG_NODES_MINB) k_nodes(DevView d) {
     extern __shared__ u32 s_nodes[];
-    u32* const s_reads = s_nodes + 13 * NODE_SCAP * AG_TILE;   // [NCHUNK][rw] raw words of every chunk entry's left mate (bases, then mask)
-    __shared__ ag_fast s_f[NCHUNK];
-    __shared__ u32 s_idx[NCHUNK];
+    u32* const s_reads = s_nodes + 13 * NODE_SCAP * AG_TILE;   // [NCHUNK_N][rw] raw words of every chunk entry's left mate (bases, then mask)
+    __shared__ ag_fast s_f[NCHUNK_N];
+    __shared__ u32 s_idx[NCHUNK_N];
     __shared__ u32 s_scan[33];
     __shared__ u32 s_base;
     const u32 tile = blockIdx.x, q = tile * AG_TILE + threadIdx.x, lane = threadIdx.x & 31;
@@ -250,8 +254,8 @@ __global__ void __launch_bounds__(AG_TILE, AG_NODES_MINB) k_nodes(DevView d) {
     ag_cm1 ca; ca.cid = ca.coff = AG_NONE;
     if (active) ca = d.cm1[q];
     const u32 kb = d.tile_start[tile], ke = d.tile_start[tile + 1];
-    for (u32 c0 = kb; c0 < ke; c0 += NCHUNK) {
-        const u32 cn = min((u32)NCHUNK, ke - c0);
+    for (u32 c0 = kb; c0 < ke; c0 += NCHUNK_N) {
+        const u32 cn = min((u32)NCHUNK_N, ke - c0);
         if (threadIdx.x < cn) {
             u32 idx = d.vals[c0 + threadIdx.x];
             s_idx[threadIdx.x] = idx;
@@ -839,7 +843,7 @@ void AgDevice::build() {
     m.cm1.ensure((size_t)n_pos + 2); d.cm1 = m.cm1.p; m.pos_term.ensure((size_t)n_pos + 2); d.pos_term = m.pos_term.p;
     if (n_pos) { k_cm1<<<(n_pos + 255) / 256, 256, 0, st>>>(d, m.cm1.p, m.pos_term.p); launches_++; }
     static bool attr_done = false;
-    if (!attr_done) { CK(cudaFuncSetAttribute(k_nodes, cudaFuncAttributeMaxDynamicSharedMemorySize, NODES_SMEM + NCHUNK * READ_WORDS_MAX * 4)); attr_done = true; }
+    if (!attr_done) { CK(cudaFuncSetAttribute(k_nodes, cudaFuncAttributeMaxDynamicSharedMemorySize, NODES_SMEM + NCHUNK_N * READ_WORDS_MAX * 4)); attr_done = true; }
     d.rw = (m.reads.stride2 + m.reads.stridem <= (u32)READ_WORDS_MAX) ? m.reads.stride2 + m.reads.stridem : 0;
 
     // ---- prep + keys ------------------------------------------------------------------------------------------------
@@ -886,7 +890,7 @@ void AgDevice::build() {
             m.ovf_node.ensure(m.ovf_cap); m.ovf_next.ensure(m.ovf_cap);
             d.pool = m.pool.p; d.pool_count = m.counters.p + 0; d.pool_cap = m.pool_cap;
             d.ovf.node = m.ovf_node.p; d.ovf.next = m.ovf_next.p; d.ovf.count = m.counters.p + 1; d.ovf.cap = m.ovf_cap; d.ovf.err = m.err.p;
-            if (m.n_tiles) { k_nodes<<<m.n_tiles, AG_TILE, NODES_SMEM + NCHUNK * d.rw * 4, st>>>(d); launches_++; }
+            if (m.n_tiles) { k_nodes<<<m.n_tiles, AG_TILE, NODES_SMEM + NCHUNK_N * d.rw * 4, st>>>(d); launches_++; }
             int err = 0;
             CK(cudaMemcpyAsync(&err, m.err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
