@@ -363,7 +363,10 @@ struct ag_walkctx {
     ag_cmtab cmt;
     const u32* chain_pos;     // chain-major: unit position of every contiMer
     u32* walk_next;           // per node: next node of the walk that marked it, or NONE
-    const ag_chain* chain;    // forced-link chains; null = step node by node (exact sequential replay)
+    const ag_chain* chain;    // forced-link chains
+    // exact sequential replay (skip rule, AG:2194-2202): a chain can be entered at an interior node, so marks are kept as a marked SUFFIX
+    // per chain, indexed by the chain's tail: msuf = nodes marked at the tail end, mnode = first marked node
+    u32* msuf; u32* mnode; const u32* fprev;
 };
 
 // untraversed successors of node v (record `nd` already loaded): count, `pick` = the last one seen, `prec` = its record (AG:2020-2032)
@@ -412,7 +415,7 @@ AG_HD ag_walk ag_walk_from(const ag_walkctx& w, u32 start) {
         w.nw[v].misc = cur.misc;
         if (w.chain) {  // a chain of forced links is marked as one: jump to its tail (interior nodes are never inspected by anyone else)
             ag_chain c = w.chain[v];
-            if (c.tail != v) { len += c.len - 1; ext |= c.flg; v = c.tail; cur = w.nw[v]; }
+            if (c.tail != v) { len += c.len - 1; if (c.flg) ext = 1; v = c.tail; cur = w.nw[v]; }
         }
         u32 pick; ag_nodew prec;
         u32 cnt = ag_live_succ(w, v, cur, pick, prec);
@@ -439,5 +442,61 @@ AG_HD ag_walk ag_walk_from(const ag_walkctx& w, u32 start) {
         break;
     }
     r.len = len; r.last_node = v;
+    return r;
+}
+
+// ---- exact sequential replay with chains ----------------------------------------------------------------------------------
+// With the 1000-position skip (AG:2194-2202) the scan can start a walk INSIDE a chain (its head was skipped), so a chain is no longer
+// all-or-nothing; but walks only run forward, so the marked nodes of a chain always form a suffix.  traversed(x) <=> x is filtered or
+// lies in the marked suffix of its chain.
+AG_HD bool ag_seq_trav(const ag_walkctx& w, u32 x) {
+    if (w.nw[x].misc & AG_NW_FILTERED) return true;
+    const ag_chain c = w.chain[x];
+    return c.len <= w.msuf[c.tail];
+}
+AG_HD u32 ag_seq_live_succ(const ag_walkctx& w, u32 v, const ag_nodew& nd, u32& pick) {
+    u32 cnt = 0; pick = AG_NONE;
+    if (nd.succ0 != AG_NONE && !ag_seq_trav(w, nd.succ0)) { cnt++; pick = nd.succ0; }
+    if (nd.succ1 != AG_NONE && !ag_seq_trav(w, nd.succ1)) { cnt++; pick = nd.succ1; }
+    if (nd.misc & AG_NW_OVF) for (u32 o = w.ovf_head[v]; o != AG_NONE; o = w.ovf_next[o]) { u32 s = w.ovf_target[o]; if (!ag_seq_trav(w, s)) { cnt++; pick = s; } }
+    return cnt;
+}
+AG_HD ag_walk ag_walk_from_seq(const ag_walkctx& w, u32 start) {
+    ag_walk r;
+    r.start_node = start; r.soff = w.node_pos[start]; r.soff0 = w.nw[start].moff;
+    u32 v = start, len = 0, ext = 0, stop = start;
+    for (;;) {
+        const ag_chain c = w.chain[v];
+        const u32 t = c.tail, ms = w.msuf[t], old_m = w.mnode[t];
+        const u32 sufflg = ms ? w.chain[old_m].flg : 0;
+        len += c.len - ms;
+        if (c.flg - sufflg) ext = 1;
+        w.msuf[t] = c.len; w.mnode[t] = v;                  // the chain is now marked from v to its tail
+        stop = ms ? w.fprev[old_m] : t;                     // last node this walk marks in the chain
+        const ag_nodew sn = w.nw[stop];
+        u32 pick = AG_NONE, cnt = 0;
+        if (!ms) cnt = ag_seq_live_succ(w, stop, sn, pick); // otherwise stop's only live successor is the (traversed) old suffix start
+        if (cnt == 1) { w.nw[stop].misc = sn.misc | AG_NW_STOP; w.walk_next[stop] = pick; v = pick; continue; }
+        const u32 p = w.node_pos[stop], c0 = w.cmt.start[p];
+        if (w.cmt.start[p + 1] - c0 == 1 && w.cmt.cm[c0].chain != w.cmt.cm[c0].term) {
+            const ag_cm m = w.cmt.cm[c0];
+            len += m.term - m.chain; ext = 1;
+            w.nw[stop].misc = sn.misc | AG_NW_STOP | AG_NW_DETOUR;
+            const u32 z = w.chain_pos[m.term];
+            u32 live = 0, item = AG_NONE;
+            for (u32 x = w.pos_node[z]; x < w.pos_node[z + 1]; x++) if (!ag_seq_trav(w, x)) { live++; item = x; }
+            u32 pick2 = AG_NONE, cnt2 = 0;
+            if (live == 1) cnt2 = ag_seq_live_succ(w, item, w.nw[item], pick2);
+            if (cnt2 == 1) { w.walk_next[stop] = pick2; v = pick2; continue; }
+            w.walk_next[stop] = AG_NONE;
+            r.eoff = z; r.eoff0 = AG_NONE; r.flags = ext | (1u << 1);
+            break;
+        }
+        w.nw[stop].misc = sn.misc | AG_NW_STOP;
+        w.walk_next[stop] = AG_NONE;
+        r.eoff = p; r.eoff0 = sn.moff; r.flags = ext | (0u << 1);
+        break;
+    }
+    r.len = len; r.last_node = stop;
     return r;
 }

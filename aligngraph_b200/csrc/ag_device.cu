@@ -156,7 +156,7 @@ struct DevView {
     u32* eovf_head; u32* eovf_target; u32* eovf_next; u32* eovf_count; u32 eovf_cap;
     u32* walk_next; u32* parent; u32* cmin; u32* cmax;
     u32* cand_rank; u32* cand_node; u32* cand_label;
-    unsigned char* pos_term; u32* indeg; u32* fnext; ag_chain* chain_a; ag_chain* chain_b; const ag_chain* chain; int* changed;
+    unsigned char* pos_term; u32* indeg; u32* fnext; u32* fprev; u32* msuf; u32* mnode; ag_chain* chain_a; ag_chain* chain_b; const ag_chain* chain; int* changed;
     ag_walk* walks; ag_walk* walks_sorted; u32* walk_count; u32 walk_cap;
     int* err;
     int k, iv, coverage;
@@ -437,7 +437,7 @@ __device__ __forceinline__ void uf_unite(u32* parent, u32 a, u32 b) {
 __global__ void k_uf_init(DevView d, u32 n_nodes) {
     u32 v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n_nodes) return;
-    d.parent[v] = v; d.cmin[v] = AG_NONE; d.cmax[v] = 0; d.walk_next[v] = AG_NONE;
+    d.parent[v] = v; d.cmin[v] = AG_NONE; d.cmax[v] = 0; d.walk_next[v] = AG_NONE; d.fprev[v] = AG_NONE;
 }
 // Components over chain TAILS.  Only a chain's tail has live successors outside its chain and only a tail can
 // leave through a contiMer detour (interior nodes always see exactly one untraversed successor), so the relations a walk can follow are:
@@ -470,7 +470,7 @@ __global__ void k_uf_flatten(DevView d, u32 n_cand) {
 __device__ __forceinline__ ag_walkctx make_ctx(const DevView& d) {
     ag_walkctx w;
     w.nw = d.node_w; w.node_pos = d.node_pos; w.pos_node = d.pos_node; w.ovf_head = d.eovf_head; w.ovf_target = d.eovf_target;
-    w.ovf_next = d.eovf_next; w.cmt = d.cmt; w.chain_pos = d.chain_pos; w.walk_next = d.walk_next; w.chain = d.chain;
+    w.ovf_next = d.eovf_next; w.cmt = d.cmt; w.chain_pos = d.chain_pos; w.walk_next = d.walk_next; w.chain = d.chain; w.msuf = d.msuf; w.mnode = d.mnode; w.fprev = d.fprev;
     return w;
 }
 __device__ __forceinline__ void push_walk(const DevView& d, ag_walk r) {
@@ -495,7 +495,7 @@ __global__ void k_links(DevView d, u32 n_nodes) {
     if (v >= n_nodes) return;
     u32 w = ag_forced_succ(d.node_w, d.eovf_head, d.eovf_target, d.eovf_next, d.indeg, d.pos_term, d.node_pos, v);
     d.fnext[v] = w;
-    if (w != AG_NONE) atomicOr(&d.node_w[w].misc, AG_NW_INTERIOR);
+    if (w != AG_NONE) { atomicOr(&d.node_w[w].misc, AG_NW_INTERIOR); d.fprev[w] = v; }
     ag_chain c; c.jump = w; c.tail = v; c.len = 1; c.flg = (d.node_w[v].misc & AG_NW_HASCONTIG) ? 1u : 0u;
     d.chain_a[v] = c;
 }
@@ -505,7 +505,7 @@ __global__ void k_rank(const ag_chain* __restrict__ in, ag_chain* __restrict__ o
     ag_chain c = in[v];
     if (c.jump != AG_NONE) {
         ag_chain j = in[c.jump];
-        c.len += j.len; c.flg |= j.flg; c.tail = j.tail; c.jump = j.jump;
+        c.len += j.len; c.flg += j.flg; c.tail = j.tail; c.jump = j.jump;
         if (c.jump != AG_NONE) *changed = 1;
     }
     out[v] = c;
@@ -524,7 +524,7 @@ __global__ void __launch_bounds__(1024) k_rank_local(ag_chain* recs, u32 n_nodes
     ag_chain *src = sa, *dst = sb;
     for (int r = 0; r < 10; r++) {
         c = src[threadIdx.x];
-        if (c.jump != AG_NONE && c.jump - b0 < 1024u) { ag_chain j = src[c.jump - b0]; c.len += j.len; c.flg |= j.flg; c.tail = j.tail; c.jump = j.jump; }
+        if (c.jump != AG_NONE && c.jump - b0 < 1024u) { ag_chain j = src[c.jump - b0]; c.len += j.len; c.flg += j.flg; c.tail = j.tail; c.jump = j.jump; }
         dst[threadIdx.x] = c;
         __syncthreads();
         ag_chain* t = src; src = dst; dst = t;
@@ -580,11 +580,11 @@ __global__ void k_walk_sequential(DevView d) {
     u32 bso = AG_NONE, beo = AG_NONE, bei = AG_NONE;
     for (u32 cp = 0; cp < d.n_ref;) {
         for (u32 v = d.pos_node[cp]; v < d.pos_node[cp + 1]; v++) {
-            if (d.node_w[v].misc & AG_NW_TRAV) continue;
-            ag_walk r = ag_walk_from(w, v);
+            if (ag_seq_trav(w, v)) continue;
+            ag_walk r = ag_walk_from_seq(w, v);
             push_walk(d, r);
             u32 eoff = r.eoff;
-            if (((r.flags >> 1) & 3) == 0) eoff = eoff + (d.node_sref[2 * (size_t)r.last_node + 1] >> 16) - 1;  // AG:2170
+            if (((r.flags >> 1) & 3) != 1) eoff = eoff + (d.node_sref[2 * (size_t)r.last_node + 1] >> 16) - 1;  // AG:2170
             bool contained = (bei == 0) && bso <= r.soff && beo >= eoff;     // contain(), AG:1897-1902 (ids are 0 once set)
             if (!contained) { bso = r.soff; beo = eoff; bei = 0; }
         }
@@ -593,20 +593,21 @@ __global__ void k_walk_sequential(DevView d) {
     }
 }
 
-// write the bases of the selected walks (AG:1993-2002): consensus base per node, contig bases along contiMer detours
-__global__ void k_materialize(DevView d, const u32* __restrict__ starts, const u64* __restrict__ offs, u32 n, unsigned char* out, int use_chains) {
+// sequential replay: thread per walk; inside a chain follow the forced links until the node where the walk left it (STOP)
+__global__ void k_materialize_seq(DevView d, const u32* __restrict__ starts, const u64* __restrict__ offs, u32 n, unsigned char* out) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     unsigned char* o = out + offs[i];
     u32 v = starts[i];
     while (v != AG_NONE) {
-        *o++ = (unsigned char)(d.node_w[v].misc & 0xFF);
-        if (d.node_w[v].misc & AG_NW_DETOUR) {
+        const u32 misc = d.node_w[v].misc;
+        *o++ = (unsigned char)(misc & 0xFF);
+        if (!(misc & AG_NW_STOP)) { v = d.fnext[v]; continue; }
+        if (misc & AG_NW_DETOUR) {
             ag_cm m = d.cmt.cm[d.cmt.start[d.node_pos[v]]];
             for (u32 e = m.chain + 1; e <= m.term; e++) *o++ = d.chain_base[e];
         }
-        u32 f = use_chains ? d.fnext[v] : AG_NONE;
-        v = f != AG_NONE ? f : d.walk_next[v];
+        v = d.walk_next[v];
     }
 }
 
@@ -664,9 +665,9 @@ __global__ void k_mat_tails(DevView d, const u32* __restrict__ tails /* per walk
 __global__ void k_reset_marks(DevView d, u32 n_nodes) {
     u32 v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n_nodes) return;
-    u32 m = d.node_w[v].misc & ~(AG_NW_TRAV | AG_NW_DETOUR | AG_NW_INTERIOR);
+    u32 m = d.node_w[v].misc & ~(AG_NW_TRAV | AG_NW_DETOUR | AG_NW_STOP);
     d.node_w[v].misc = (m & AG_NW_FILTERED) ? (m | AG_NW_TRAV) : m;
-    d.walk_next[v] = AG_NONE;
+    d.walk_next[v] = AG_NONE; d.msuf[v] = 0; d.mnode[v] = AG_NONE;
 }
 
 __global__ void k_occupancy(DevView d, unsigned char* bits) {
@@ -705,7 +706,7 @@ struct AgDevice::Impl {
     DBuf<u32> pos_cnt, pos_pool, pos_node;
     DBuf<ag_nodem> node_m; DBuf<ag_nodew> node_w; DBuf<u32> node_sref, node_pos;
     DBuf<u32> eovf_head, eovf_target, eovf_next;
-    DBuf<u32> walk_next, parent, cmin, cmax; DBuf<ag_walk> walks, walks2; DBuf<ag_cm1> cm1; DBuf<MatItem> mat_chains, mat_detours; u32 n_cand = 0; DBuf<unsigned char> pos_term; DBuf<u32> indeg, fnext, cand_rank, cand_node, cand_label; DBuf<ag_chain> chain_a, chain_b; DBuf<int> changed;
+    DBuf<u32> walk_next, parent, cmin, cmax; DBuf<ag_walk> walks, walks2; DBuf<ag_cm1> cm1; DBuf<MatItem> mat_chains, mat_detours; u32 n_cand = 0; DBuf<unsigned char> pos_term; DBuf<u32> indeg, fnext, fprev, msuf, mnode, cand_rank, cand_node, cand_label; DBuf<ag_chain> chain_a, chain_b; DBuf<int> changed;
     DBuf<unsigned char> out_bases, occ; DBuf<u32> sel_start, sel_tails; DBuf<u64> sel_off;
     Scanner scanner;
     u32 n_tiles = 0, n_keys = 0, n_nodes = 0;
@@ -736,7 +737,7 @@ AgDevice::~AgDevice() {
     for (auto* b : b32) b->release();
     for (int i = 0; i < 4; i++) m.scanner.lvl[i].release();
     m.cm.release(); m.aln.release(); m.ext.release(); m.alnp.release(); m.pool.release(); m.ovf_node.release(); m.err.release();
-    m.node_m.release(); m.node_w.release(); m.walks.release(); m.walks2.release(); m.cm1.release(); m.mat_chains.release(); m.mat_detours.release(); m.pos_term.release(); m.cand_rank.release(); m.cand_node.release(); m.cand_label.release(); m.indeg.release(); m.fnext.release(); m.chain_a.release(); m.chain_b.release(); m.changed.release(); m.sel_off.release();
+    m.node_m.release(); m.node_w.release(); m.walks.release(); m.walks2.release(); m.cm1.release(); m.mat_chains.release(); m.mat_detours.release(); m.pos_term.release(); m.cand_rank.release(); m.cand_node.release(); m.cand_label.release(); m.fprev.release(); m.msuf.release(); m.mnode.release(); m.indeg.release(); m.fnext.release(); m.chain_a.release(); m.chain_b.release(); m.changed.release(); m.sel_off.release();
     if (m.st) cudaStreamDestroy(m.st);
     delete m_;
 }
@@ -886,7 +887,7 @@ void AgDevice::build() {
         if (!m.pool_cap) m.pool_cap = std::max<u32>(1u << 20, 3 * n_ref + (1u << 16));
         for (;;) {
             m.pool.ensure(m.pool_cap);
-            m.ovf_cap = std::max<u32>(1u << 18, n_ref / 8);
+            if (!m.ovf_cap) m.ovf_cap = std::max<u32>(1u << 18, n_ref / 8);
             m.ovf_node.ensure(m.ovf_cap); m.ovf_next.ensure(m.ovf_cap);
             d.pool = m.pool.p; d.pool_count = m.counters.p + 0; d.pool_cap = m.pool_cap;
             d.ovf.node = m.ovf_node.p; d.ovf.next = m.ovf_next.p; d.ovf.count = m.counters.p + 1; d.ovf.cap = m.ovf_cap; d.ovf.err = m.err.p;
@@ -902,6 +903,12 @@ void AgDevice::build() {
                 continue;
             }
             if (err == 2) throw AgError{"BOWTIE ALIGNMENT ERROR: alignment outside the unit"};
+            if (err == 1 && m.ovf_cap < (1u << 30)) {  // overflow pool (nodes beyond the shared-memory slots) too small: grow and redo the sweep
+                m.ovf_cap *= 4;
+                CK(cudaMemsetAsync(m.err.p, 0, sizeof(int), st));
+                CK(cudaMemsetAsync(m.counters.p, 0, 8 * sizeof(u32), st));
+                continue;
+            }
             throw AgError{"node overflow pool exhausted"};
         }
         t_.nodes += tm.stop();
@@ -941,7 +948,7 @@ void AgDevice::walk_components() {
     unsigned g = (nn + 255) / 256;
     {   // forced-link chains
         Timer tm(st);
-        m.indeg.ensure(nn + 1); m.fnext.ensure(nn + 1); m.chain_a.ensure(nn + 1); m.chain_b.ensure(nn + 1); m.changed.ensure(1);
+        m.indeg.ensure(nn + 1); m.fnext.ensure(nn + 1); m.fprev.ensure(nn + 1); d.fprev = m.fprev.p; m.chain_a.ensure(nn + 1); m.chain_b.ensure(nn + 1); m.changed.ensure(1);
         d.indeg = m.indeg.p; d.fnext = m.fnext.p; d.chain_a = m.chain_a.p; d.chain_b = m.chain_b.p; d.changed = m.changed.p;
         CK(cudaMemsetAsync(m.indeg.p, 0, (size_t)nn * sizeof(u32), st));
         k_uf_init<<<g, 256, 0, st>>>(d, nn); launches_++;
@@ -993,8 +1000,9 @@ void AgDevice::walk_sequential() {
     Impl& m = *m_; cudaStream_t st = m.st; DevView& d = m.view; u32 nn = m.n_nodes;
     Timer tm(st);
     // reset marks to the coverage filter state and replay in one thread
+    m.msuf.ensure(nn + 1); m.mnode.ensure(nn + 1); d.msuf = m.msuf.p; d.mnode = m.mnode.p;
     k_reset_marks<<<(nn + 255) / 256, 256, 0, st>>>(d, nn); launches_++;
-    d.chain = nullptr; chains_valid_ = false;
+    chains_valid_ = false;  // chains stay valid as data; materialisation switches to the STOP-bit rule
     CK(cudaMemsetAsync(m.counters.p + 3, 0, sizeof(u32), st));
     k_walk_sequential<<<1, 32, 0, st>>>(d); launches_++;
     t_.walk += tm.stop();
@@ -1075,7 +1083,7 @@ void AgDevice::materialize(const std::vector<ag_walk>& walks, const std::vector<
         k_mat_chains<<<(cap + 127) / 128, 128, 0, st>>>(d, m.mat_chains.p, m.counters.p + 4, m.out_bases.p); launches_++;
         k_mat_detours<<<(cap + 3) / 4, 128, 0, st>>>(d, m.mat_detours.p, m.counters.p + 4, m.out_bases.p); launches_++;
     } else {
-        k_materialize<<<((u32)sel.size() + 127) / 128, 128, 0, st>>>(d, m.sel_start.p, m.sel_off.p, (u32)sel.size(), m.out_bases.p, 0); launches_++;
+        k_materialize_seq<<<((u32)sel.size() + 127) / 128, 128, 0, st>>>(d, m.sel_start.p, m.sel_off.p, (u32)sel.size(), m.out_bases.p); launches_++;
     }
     k_mat_tails<<<((u32)sel.size() + 127) / 128, 128, 0, st>>>(d, m.sel_tails.p, m.sel_off.p, (u32)sel.size(), m.out_bases.p); launches_++;
     CK(cudaMemcpyAsync(&bases[0], m.out_bases.p, offs.back(), cudaMemcpyDeviceToHost, st));

@@ -71,6 +71,7 @@ struct alignas(16) ag_nodew {
 #define AG_NW_OVF 0x400u
 #define AG_NW_TRAV 0x800u    /* traversed (AG:2013); set from the start on coverage-filtered nodes */
 #define AG_NW_DETOUR 0x1000u /* the walk left this node through a contiMer thread */
+#define AG_NW_STOP 0x4000u    /* sequential replay: the walk that marked this node left the chain here (follow walk_next, not fnext) */
 #define AG_NW_INTERIOR 0x2000u /* entered only through its unique live predecessor (forced link): never starts a walk */
 
 struct ag_nodem { u32 cid, coff, cid0, coff0, moff; };  // match fields of a final node
@@ -90,7 +91,7 @@ struct ag_walk {
 };
 
 // forced-link chain record after list ranking: from this node to the tail of its chain
-struct alignas(16) ag_chain { u32 jump, tail, len, flg; };
+struct alignas(16) ag_chain { u32 jump, tail, len, flg; };  // flg = NUMBER of nodes with contigOffset != -1 from here to the tail
 
 // bases a walk contributes to its contig: the loop's bases plus s[1..] of the last node when it ended in the k-mer graph (AG:2164-2168)
 AG_HD u32 ag_walk_tail_len(const ag_walk& r) { u32 slen = r.tail_soff_len >> 16; return (((r.flags >> 1) & 3) != 1 && slen > 1) ? slen - 1 : 0; }

@@ -20,5 +20,7 @@ LIVE = {
     # BASELINE configs[3] / [4] shapes at test size: 8 chromosomes 2x150 k=7; 2 chromosomes --part 4 (8 units)
     "c4_shape": dict(genome_bp=400000, chroms=8, coverage=50, readlen=150, kmer=7, insert_mean=500, insert_sd=50, seed=31),
     "c5_shape": dict(genome_bp=200000, chroms=2, part=4, coverage=50, readlen=150, kmer=7, seed=32, indel=0.001),
+    # a 160 kbp contig: the walk emits a > 100 kbp contig, which switches on the reference's 1000-position scan skip (AlignGraph.cpp:2194-2202)
+    "longcontig": dict(genome_bp=500000, coverage=40, contig_len=160000, contig_gap=3000, seed=41),
     "nocontigs": dict(genome_bp=30000, coverage=50, seed=7, contig_len=150, contig_gap=5000),
 }

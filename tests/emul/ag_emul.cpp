@@ -25,7 +25,7 @@ public:
     std::vector<u32> pos_node, node_pos, node_sref, eovf_head, eovf_target, eovf_next, walk_next, parent;
     std::vector<ag_nodeb> nodeb;  // final order
     std::vector<ag_nodem> node_m; std::vector<ag_nodew> node_w; std::vector<ag_cm1> cm1;
-    std::vector<unsigned char> pos_term; std::vector<u32> indeg, fnext; std::vector<ag_chain> chain; bool use_chains = false;
+    std::vector<unsigned char> pos_term; std::vector<u32> indeg, fnext, fprev, msuf, mnode; std::vector<ag_chain> chain; bool use_chains = false;
     std::vector<ag_nodeb> ovf_node; std::vector<u32> ovf_next; u32 ovf_count = 0; int err = 0;
     u32 n_nodes = 0;
     bool fallback_used = false;
@@ -145,7 +145,7 @@ public:
 
     ag_walkctx ctx() {
         ag_walkctx w; w.nw = node_w.data(); w.node_pos = node_pos.data(); w.pos_node = pos_node.data(); w.ovf_head = eovf_head.data();
-        w.ovf_target = eovf_target.data(); w.ovf_next = eovf_next.data(); w.cmt = cmt(); w.chain_pos = in.chain_pos; w.walk_next = walk_next.data(); w.chain = use_chains ? chain.data() : nullptr;
+        w.ovf_target = eovf_target.data(); w.ovf_next = eovf_next.data(); w.cmt = cmt(); w.chain_pos = in.chain_pos; w.walk_next = walk_next.data(); w.chain = chain.data(); w.msuf = msuf.data(); w.mnode = mnode.data(); w.fprev = fprev.data();
         return w;
     }
     u32 find(u32 x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; }
@@ -161,7 +161,7 @@ public:
         // forced-link chains (k_indeg, k_links, list ranking)
         pos_term.assign((size_t)in.n_pos + 1, 0);
         for (u32 p = 0; p < in.n_pos; p++) for (u32 e = ct.start[p]; e < ct.start[p + 1]; e++) if (ct.cm[e].chain == ct.cm[e].term) pos_term[p] = 1;
-        indeg.assign(n_nodes, 0); fnext.assign(n_nodes, AG_NONE); chain.assign(n_nodes, ag_chain{});
+        indeg.assign(n_nodes, 0); fnext.assign(n_nodes, AG_NONE); fprev.assign(n_nodes, AG_NONE); msuf.assign(n_nodes, 0); mnode.assign(n_nodes, AG_NONE); chain.assign(n_nodes, ag_chain{});
         for (u32 v = 0; v < n_nodes; v++) {
             if (!live(v)) continue;
             const ag_nodew& x = node_w[v];
@@ -171,13 +171,13 @@ public:
         }
         for (u32 v = 0; v < n_nodes; v++) {
             fnext[v] = ag_forced_succ(node_w.data(), eovf_head.data(), eovf_target.data(), eovf_next.data(), indeg.data(), pos_term.data(), node_pos.data(), v);
-            if (fnext[v] != AG_NONE) node_w[fnext[v]].misc |= AG_NW_INTERIOR;
+            if (fnext[v] != AG_NONE) { node_w[fnext[v]].misc |= AG_NW_INTERIOR; fprev[fnext[v]] = v; }
         }
         for (u32 v = n_nodes; v-- > 0;) {  // forced links point to higher node indices (positions increase), so one backward pass ranks every chain
             ag_chain c; c.jump = AG_NONE; c.tail = v; c.len = 1; c.flg = (node_w[v].misc & AG_NW_HASCONTIG) ? 1u : 0u;
             if (fnext[v] != AG_NONE) {
                 if (fnext[v] <= v) throw AgHostError{"emul: forced link does not point forward"};
-                const ag_chain& j = chain[fnext[v]]; c.tail = j.tail; c.len += j.len; c.flg |= j.flg;
+                const ag_chain& j = chain[fnext[v]]; c.tail = j.tail; c.len += j.len; c.flg += j.flg;
             }
             chain[v] = c;
         }
@@ -226,14 +226,15 @@ public:
             if (beo - bso > 100000u) { trigger = true; break; }
         }
         if (trigger || getenv("AG_EMUL_FORCE_SEQUENTIAL")) {
-            fallback_used = true; use_chains = false; w = ctx();
+            fallback_used = true; use_chains = false;
             walks.clear();
-            for (u32 v = 0; v < n_nodes; v++) { u32 m = node_w[v].misc & ~(AG_NW_TRAV | AG_NW_DETOUR | AG_NW_INTERIOR); node_w[v].misc = live(v) ? m : (m | AG_NW_TRAV); walk_next[v] = AG_NONE; }
+            for (u32 v = 0; v < n_nodes; v++) { u32 m = node_w[v].misc & ~(AG_NW_TRAV | AG_NW_DETOUR | AG_NW_STOP); node_w[v].misc = live(v) ? m : (m | AG_NW_TRAV); walk_next[v] = AG_NONE; msuf[v] = 0; mnode[v] = AG_NONE; }
+            w = ctx();
             u32 sbo = AG_NONE, seo = AG_NONE, sei = AG_NONE;
-            for (u32 cp = 0; cp < in.n_ref;) {
+            for (u32 cp = 0; cp < in.n_ref;) {   // k_walk_sequential
                 for (u32 v = pos_node[cp]; v < pos_node[cp + 1]; v++) {
-                    if (node_w[v].misc & AG_NW_TRAV) continue;
-                    ag_walk x = ag_walk_from(w, v); fill_tail(x); walks.push_back(x);
+                    if (ag_seq_trav(w, v)) continue;
+                    ag_walk x = ag_walk_from_seq(w, v); fill_tail(x); walks.push_back(x);
                     u32 eoff = x.eoff;
                     if (((x.flags >> 1) & 3) != 1) eoff = eoff + (x.tail_soff_len >> 16) - 1;
                     bool contained = (sei == 0) && sbo <= x.soff && seo >= eoff;
@@ -252,9 +253,11 @@ public:
         ag_cmtab ct = cmt();
         for (size_t i = 0; i < sel.size(); i++) {
             size_t o = offs[i];
-            for (u32 v = walks[sel[i]].start_node; v != AG_NONE; v = (use_chains && fnext[v] != AG_NONE) ? fnext[v] : walk_next[v]) {
+            for (u32 v = walks[sel[i]].start_node; v != AG_NONE;) {
                 bases[o++] = (char)(node_w[v].misc & 0xFF);
+                if (!use_chains && !(node_w[v].misc & AG_NW_STOP)) { v = fnext[v]; continue; }   // k_materialize_seq
                 if (node_w[v].misc & AG_NW_DETOUR) { ag_cm m = ct.cm[ct.start[node_pos[v]]]; for (u32 e = m.chain + 1; e <= m.term; e++) bases[o++] = in.chain_base[e]; }
+                v = (use_chains && fnext[v] != AG_NONE) ? fnext[v] : walk_next[v];
             }
             {   // k_mat_tails
                 const ag_walk& r = walks[sel[i]];

@@ -24,10 +24,12 @@ def test_emulation_matches_oracle_nodes_and_files(harness, workdir, name):
     harness.synth(emu, **cases.LIVE[name])
     shutil.copytree(emu, ora)
     harness.run_oracle(ora, dump_nodes=True)
-    harness.run_emul(emu, dump_nodes=True)
+    log = harness.run_emul(emu, dump_nodes=True)
     n = harness.n_units(ora)
     for u in range(n):
         assert harness.unit_outputs(emu, u) == harness.unit_outputs(ora, u)
+        if name == "longcontig":
+            assert "sequential walk" in log
         a = open(os.path.join(emu, "tmp", f"_nodes.{u}.txt"), "rb").read()
         b = open(os.path.join(ora, "tmp", f"_nodes.{u}.txt"), "rb").read()
         assert a == b, "node tables differ"
