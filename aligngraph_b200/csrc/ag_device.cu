@@ -22,6 +22,19 @@
 
 namespace {
 
+struct PinnedBuf {  // page-locked host staging buffer for device->host results
+    char* p = nullptr; size_t cap = 0;
+    void ensure(size_t n) {
+        if (n <= cap) return;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t nc = n + n / 8 + 4096;
+        CK(cudaHostAlloc((void**)&p, nc, cudaHostAllocDefault));
+        cap = nc;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
 template <class T> struct DBuf {
     T* p = nullptr; size_t cap = 0;
     void ensure(size_t n) {
@@ -708,6 +721,7 @@ struct AgDevice::Impl {
     DBuf<u32> eovf_head, eovf_target, eovf_next;
     DBuf<u32> walk_next, parent, cmin, cmax; DBuf<ag_walk> walks, walks2; DBuf<ag_cm1> cm1; DBuf<MatItem> mat_chains, mat_detours; u32 n_cand = 0; DBuf<unsigned char> pos_term; DBuf<u32> indeg, fnext, fprev, msuf, mnode, cand_rank, cand_node, cand_label; DBuf<ag_chain> chain_a, chain_b; DBuf<int> changed;
     DBuf<unsigned char> out_bases, occ; DBuf<u32> sel_start, sel_tails; DBuf<u64> sel_off;
+    PinnedBuf h_walks, h_bases, h_occ;
     Scanner scanner;
     u32 n_tiles = 0, n_keys = 0, n_nodes = 0;
     u32 pool_cap = 0, ovf_cap = 0, eovf_cap = 0, walk_cap = 0;
@@ -738,6 +752,7 @@ AgDevice::~AgDevice() {
     for (int i = 0; i < 4; i++) m.scanner.lvl[i].release();
     m.cm.release(); m.aln.release(); m.ext.release(); m.alnp.release(); m.pool.release(); m.ovf_node.release(); m.err.release();
     m.node_m.release(); m.node_w.release(); m.walks.release(); m.walks2.release(); m.cm1.release(); m.mat_chains.release(); m.mat_detours.release(); m.pos_term.release(); m.cand_rank.release(); m.cand_node.release(); m.cand_label.release(); m.fprev.release(); m.msuf.release(); m.mnode.release(); m.indeg.release(); m.fnext.release(); m.chain_a.release(); m.chain_b.release(); m.changed.release(); m.sel_off.release();
+    m.h_walks.release(); m.h_bases.release(); m.h_occ.release();
     if (m.st) cudaStreamDestroy(m.st);
     delete m_;
 }
@@ -1033,9 +1048,11 @@ void AgDevice::extend(std::vector<ag_walk>& walks) {
             k_walk_flag<<<(nw + 255) / 256, 256, 0, st>>>(d, nw, m.parent.p); launches_++;
             m.scanner.run(m.parent.p, m.cmin.p, nn, st);
             k_walk_scatter<<<(nw + 255) / 256, 256, 0, st>>>(d, nw, m.cmin.p); launches_++;
-            CK(cudaMemcpyAsync(walks.data(), m.walks2.p, (size_t)nw * sizeof(ag_walk), cudaMemcpyDeviceToHost, st));
+            m.h_walks.ensure((size_t)nw * sizeof(ag_walk));
+            CK(cudaMemcpyAsync(m.h_walks.p, m.walks2.p, (size_t)nw * sizeof(ag_walk), cudaMemcpyDeviceToHost, st));
         }
         CK(cudaStreamSynchronize(st));
+        if (nw) memcpy(walks.data(), m.h_walks.p, (size_t)nw * sizeof(ag_walk));
         t_.d2h += tm.stop();
         t_.d2h_bytes += (size_t)nw * sizeof(ag_walk);
     };
@@ -1086,11 +1103,13 @@ void AgDevice::materialize(const std::vector<ag_walk>& walks, const std::vector<
         k_materialize_seq<<<((u32)sel.size() + 127) / 128, 128, 0, st>>>(d, m.sel_start.p, m.sel_off.p, (u32)sel.size(), m.out_bases.p); launches_++;
     }
     k_mat_tails<<<((u32)sel.size() + 127) / 128, 128, 0, st>>>(d, m.sel_tails.p, m.sel_off.p, (u32)sel.size(), m.out_bases.p); launches_++;
-    CK(cudaMemcpyAsync(&bases[0], m.out_bases.p, offs.back(), cudaMemcpyDeviceToHost, st));
+    m.h_bases.ensure(offs.back());
+    CK(cudaMemcpyAsync(m.h_bases.p, m.out_bases.p, offs.back(), cudaMemcpyDeviceToHost, st));
     int err = 0;
     CK(cudaMemcpyAsync(&err, m.err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (err) throw AgError{"materialise item buffer exhausted"};
+    memcpy(&bases[0], m.h_bases.p, offs.back());
     t_.materialize += tm.stop();
     t_.h2d_bytes += sel.size() * 12; t_.d2h_bytes += offs.back();
 }
@@ -1103,8 +1122,10 @@ void AgDevice::occupancy(std::vector<unsigned char>& bits) {
     if (!nb) return;
     m.occ.ensure(nb + 1);
     k_occupancy<<<((u32)nb + 255) / 256, 256, 0, st>>>(m.view, m.occ.p); launches_++;
-    CK(cudaMemcpyAsync(bits.data(), m.occ.p, nb, cudaMemcpyDeviceToHost, st));
+    m.h_occ.ensure(nb);
+    CK(cudaMemcpyAsync(m.h_occ.p, m.occ.p, nb, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    memcpy(bits.data(), m.h_occ.p, nb);
     t_.d2h_bytes += nb;
 }
 

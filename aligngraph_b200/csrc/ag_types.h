@@ -96,6 +96,3 @@ struct alignas(16) ag_chain { u32 jump, tail, len, flg; };  // flg = NUMBER of n
 // bases a walk contributes to its contig: the loop's bases plus s[1..] of the last node when it ended in the k-mer graph (AG:2164-2168)
 AG_HD u32 ag_walk_tail_len(const ag_walk& r) { u32 slen = r.tail_soff_len >> 16; return (((r.flags >> 1) & 3) != 1 && slen > 1) ? slen - 1 : 0; }
 
-struct ag_params_dev {
-    int k, iv, coverage;
-};
