@@ -858,8 +858,7 @@ void AgDevice::build() {
 
     m.cm1.ensure((size_t)n_pos + 2); d.cm1 = m.cm1.p; m.pos_term.ensure((size_t)n_pos + 2); d.pos_term = m.pos_term.p;
     if (n_pos) { k_cm1<<<(n_pos + 255) / 256, 256, 0, st>>>(d, m.cm1.p, m.pos_term.p); launches_++; }
-    static bool attr_done = false;
-    if (!attr_done) { CK(cudaFuncSetAttribute(k_nodes, cudaFuncAttributeMaxDynamicSharedMemorySize, NODES_SMEM + NCHUNK_N * READ_WORDS_MAX * 4)); attr_done = true; }
+    if (!attr_done_) { CK(cudaFuncSetAttribute(k_nodes, cudaFuncAttributeMaxDynamicSharedMemorySize, NODES_SMEM + NCHUNK_N * READ_WORDS_MAX * 4)); attr_done_ = true; }  // per device
     d.rw = (m.reads.stride2 + m.reads.stridem <= (u32)READ_WORDS_MAX) ? m.reads.stride2 + m.reads.stridem : 0;
 
     // ---- prep + keys ------------------------------------------------------------------------------------------------

@@ -69,7 +69,7 @@ private:
     u64 launches_ = 0;
     void *ev0_ = nullptr, *ev1_ = nullptr;
     std::vector<void*> pinned_;
-    bool chains_valid_ = false;
+    bool chains_valid_ = false, attr_done_ = false;
     void walk_components();
     void walk_sequential();
 };
