@@ -9,7 +9,9 @@
 #include <sys/stat.h>
 #include <unistd.h>
 #include <malloc.h>
+#include <sys/resource.h>
 #include <thread>
+#include <chrono>
 #include <mutex>
 #include <atomic>
 
@@ -341,8 +343,11 @@ static void load_chunks(const std::string& contigs_fa, std::vector<Chunk>& ch) {
 
 void ag_thread_contigs(const std::string& contigs_fa, const std::string& psl_path, std::string& initial_text, AgUnit& u) {
     // ---- chunks (AG:322-359) ----
+    auto T0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) { if (getenv("AG_POST_TIMING")) { auto t = std::chrono::steady_clock::now(); struct rusage ru; getrusage(RUSAGE_SELF, &ru); fprintf(stderr, "  [contigs] %s %.1f ms (minflt %ld, stime %.0f ms)\n", what, std::chrono::duration<double>(t - T0).count() * 1e3, ru.ru_minflt, ru.ru_stime.tv_sec * 1e3 + ru.ru_stime.tv_usec / 1e3); T0 = t; } };
     std::vector<Chunk> ch;
     load_chunks(contigs_fa, ch);
+    lap("chunks");
     // ---- PSL -> position sets (AG:817-852 with updateContig AG:763-815) ----
     {
         FileMap fm(psl_path);
@@ -387,11 +392,13 @@ void ag_thread_contigs(const std::string& contigs_fa, const std::string& psl_pat
                 }
         }
     }
+    lap("psl+sets");
     // ---- thread every surviving set through the unit (AG:884-1177) ----
     struct Push { u32 pos, cid, coff; char base; };
     std::vector<Push> pushes;          // chain-major: one thread after the other, each in walking order
     std::vector<u32> term_of;          // per push: index of its thread's terminal push
     std::vector<u32> count(u.n_ref, 0);  // contiMers per position so far (grows with the tail)
+    { size_t cap = 0; for (const Chunk& c : ch) for (const auto& st : c.sets) cap += st.size() + 1; pushes.reserve(cap); term_of.reserve(cap); }
     u.ref.resize(u.n_ref);
     for (size_t sp = 0; sp < ch.size(); sp++) {
         Chunk& c = ch[sp];
@@ -442,6 +449,7 @@ void ag_thread_contigs(const std::string& contigs_fa, const std::string& psl_pat
             if (flipped) revcomp(c.bases);
         }
     }
+    lap("threading");
     // ---- CSR by position, push order preserved ----
     size_t n_pos = u.ref.size();
     u.cm_start.assign(n_pos + 1, 0);
@@ -458,6 +466,7 @@ void ag_thread_contigs(const std::string& contigs_fa, const std::string& psl_pat
             u.chain_pos[k] = p.pos; u.chain_base[k] = p.base;
         }
     }
+    lap("csr");
     // ---- tmp/_initial_contigs.N.fa: original contigs with >= 50 % of their chunks threaded (AG:1179-1216) ----
     Out out(&initial_text);
     size_t c = 0, cp = 0;
@@ -467,6 +476,7 @@ void ag_thread_contigs(const std::string& contigs_fa, const std::string& psl_pat
         if ((double)placed / (double)total >= kContigThreshold) { out.ch('>'); out.num(cp); out.ch('\n'); out.wrap60(whole); }
         cp++; c = e;
     }
+    lap("initial_text");
 }
 
 // =============================================================================================================================
@@ -621,6 +631,7 @@ static bool parse_sam_parallel(const char* p, size_t n, const AgReads& reads, Ag
     for (int t = 0; t < T; t++) for (const PRec& r : recs[t]) { if (!first_rec && r.sid < prev) return false; prev = r.sid; first_rec = false; }
     // ---- sequential, order-dependent half (same logic as the sequential parser on already-parsed records) ----
     u.aln.clear(); u.ext.clear();
+    { size_t nr = 0, ns = 0; for (int t = 0; t < T; t++) { nr += recs[t].size(); ns += segs[t].size(); } u.aln.reserve(nr); u.ext.reserve(ns / 8 + 16); }
     const long n_pairs = (long)reads.n_pairs;
     long first = 0, last = std::min<long>(kBatchPairs - 1, n_pairs - 1);
     struct Grp { int t; size_t i; };
