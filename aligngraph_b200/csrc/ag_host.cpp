@@ -139,7 +139,7 @@ static int host_threads() {
 static bool parse_reads_parallel(const char* p, size_t n, AgReads& out) {
     const int T = host_threads();
     if (T <= 1 || n < parallel_min_bytes()) return false;
-    if (n == 0 || p[0] != '>' || p[n - 1] != '\n' || memmem(p, n, "\n\n", 2)) return false;
+    if (n == 0 || p[0] != '>' || p[n - 1] != '\n') return false;  // (empty lines are caught by the parallel scan below)
     std::vector<size_t> cut((size_t)T + 1, n);
     cut[0] = 0;
     for (int t = 1; t < T; t++) {  // chunk starts: the next '>' that begins a line
@@ -162,6 +162,7 @@ static bool parse_reads_parallel(const char* p, size_t n, AgReads& out) {
             if (*sq == '>') { bad[t] = 1; return; }
             const char* l = (const char*)memchr(sq, '\n', (size_t)(e - sq));
             if (!l) { bad[t] = 1; return; }
+            if (l == sq) { bad[t] = 1; return; }   // an empty line ends the file for the reference (AG:375): leave it to the sequential parser
             mx = std::max(mx, (size_t)(l - sq)); cnt++;
             q = l + 1;
         }
@@ -566,10 +567,12 @@ struct PRec { u32 sid; u32 flags; u32 p0; u32 seg_off; uint16_t n1, n2; };  // f
 }
 static bool parse_sam_parallel(const char* p, size_t n, const AgReads& reads, AgUnit& u) {
     const int T = host_threads();
+    auto T0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) { if (getenv("AG_POST_TIMING")) { auto t = std::chrono::steady_clock::now(); fprintf(stderr, "  [sam] %s %.1f ms\n", what, std::chrono::duration<double>(t - T0).count() * 1e3); T0 = t; } };
     if (T <= 1 || n < parallel_min_bytes()) return false;
     size_t body = 0;
     while (body < n && p[body] == '@') { const char* l = (const char*)memchr(p + body, '\n', n - body); if (!l) return false; body = (size_t)(l - p) + 1; }
-    if (body >= n || p[n - 1] != '\n' || memmem(p + body, n - body, "\n\n", 2) || p[body] == '\n') return false;
+    if (body >= n || p[n - 1] != '\n' || p[body] == '\n') return false;
     // chunk boundaries on line starts; parity fixed after counting lines
     std::vector<size_t> cut((size_t)T + 1, n);
     cut[0] = body;
@@ -580,17 +583,23 @@ static bool parse_sam_parallel(const char* p, size_t n, const AgReads& reads, Ag
     }
     for (int t = 1; t <= T; t++) if (cut[t] < cut[t - 1]) cut[t] = cut[t - 1];
     std::vector<size_t> nlines((size_t)T, 0);
+    std::vector<char> empty_line((size_t)T, 0);
     {
         std::vector<std::thread> th;
-        for (int t = 0; t < T; t++) th.emplace_back([&, t]() { size_t c = 0; const char* q = p + cut[t]; const char* e = p + cut[t + 1]; while (q < e) { q = (const char*)memchr(q, '\n', (size_t)(e - q)) + 1; c++; } nlines[t] = c; });
+        for (int t = 0; t < T; t++) th.emplace_back([&, t]() {
+            size_t c = 0; const char* q = p + cut[t]; const char* e = p + cut[t + 1];
+            while (q < e) { const char* l = (const char*)memchr(q, '\n', (size_t)(e - q)); if (l == q) empty_line[t] = 1; q = l + 1; c++; }
+            nlines[t] = c; });
         for (auto& x : th) x.join();
     }
+    for (int t = 0; t < T; t++) if (empty_line[t]) return false;  // an empty line ends the file for the reference (AG:1247): sequential parser
     size_t lines = 0;
     for (int t = 0; t < T; t++) {   // a chunk must start on the first line of a pair
         if (lines & 1) { const char* l = (const char*)memchr(p + cut[t], '\n', n - cut[t]); size_t nc = l ? (size_t)(l - p) + 1 : n; if (cut[t] < cut[t + 1]) { nlines[t]--; nlines[t - 1]++; lines++; } cut[t] = std::min(nc, cut[t + 1]); }
         lines += nlines[t];
     }
     if (lines & 1) return false;  // BROKEN BOWTIE FILE territory: let the sequential parser report it
+    lap("line count");
     std::vector<std::vector<PRec>> recs((size_t)T);
     std::vector<std::vector<ag_seg>> segs((size_t)T);
     std::vector<char> bad((size_t)T, 0);
@@ -627,6 +636,7 @@ static bool parse_sam_parallel(const char* p, size_t n, const AgReads& reads, Ag
     };
     { std::vector<std::thread> th; for (int t = 0; t < T; t++) th.emplace_back(work, t); for (auto& x : th) x.join(); }
     for (int t = 0; t < T; t++) if (bad[t]) return false;
+    lap("parse threads");
     u32 prev = 0; bool first_rec = true;
     for (int t = 0; t < T; t++) for (const PRec& r : recs[t]) { if (!first_rec && r.sid < prev) return false; prev = r.sid; first_rec = false; }
     // ---- sequential, order-dependent half (same logic as the sequential parser on already-parsed records) ----
@@ -679,6 +689,7 @@ static bool parse_sam_parallel(const char* p, size_t n, const AgReads& reads, Ag
         next_record:;
         }
     flush_group();
+    lap("merge");
     return true;
 }
 

@@ -73,3 +73,20 @@ def test_batch_boundary_drops_one_record(harness, workdir):
     harness.run_emul(other)
     assert harness.unit_outputs(base, 0) == harness.unit_outputs(other, 0)
     # and the boundary matters: dropping is visible in the oracle's event count vs. an unshifted run is not asserted here, only parity
+
+
+def test_empty_line_truncates_like_the_reference(harness, workdir):
+    """`if(buf[0] == 0) break;` (AlignGraph.cpp:1247, :375): an empty line ends the SAM / the read file.  The multi-threaded parsers must
+    hand such files to the sequential path; product host code (via the emulation) == oracle."""
+    import shutil
+    base = os.path.join(workdir, "a")
+    harness.synth(base, genome_bp=20000, coverage=40, seed=22, contig_len=3000)
+    sam = os.path.join(base, "tmp", "_reads_genome.0.bowtie")
+    lines = open(sam).read().split("\n")
+    cut = (len(lines) // 2) & ~1
+    open(sam, "w").write("\n".join(lines[:cut]) + "\n\n" + "\n".join(lines[cut:]))
+    other = os.path.join(workdir, "b")
+    shutil.copytree(base, other)
+    harness.run_oracle(base)
+    harness.run_emul(other, env={"AG_PARSE_PARALLEL_MIN": "0", "AG_THREADS": "4"})
+    assert harness.unit_outputs(base, 0) == harness.unit_outputs(other, 0)
