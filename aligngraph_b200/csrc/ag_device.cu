@@ -373,35 +373,18 @@ __device__ __forceinline__ void add_edge(const DevView& d, u32 v, u32 tgt) {
     w->misc |= AG_NW_OVF;
 }
 
-// Per chunk: (1) every lane resolves ITS position's touch of each overlapping alignment to an item of its final node list and parks it in
-// shared memory; the touch at q+1 of the same alignment is exactly the successor side of the call that starts at q, so (2) a lane
-// reads its successor's item from its right-hand neighbour instead of evaluating a second first-compatible scan.  The position right
-// after the tile (halo) is resolved by the first `cn` threads, one alignment each.  Anything irregular — multi-segment alignments,
-// several contiMers on either side, more than 253 nodes — takes the direct two-sided evaluation.
 __global__ void __launch_bounds__(AG_TILE, AG_EDGES_MINB) k_edges(DevView d) {
     __shared__ ag_fast s_f[NCHUNK];
     __shared__ u32 s_idx[NCHUNK];
-    __shared__ unsigned char s_item[NCHUNK * AG_TILE];
-    __shared__ unsigned char s_halo[NCHUNK];
-    const u32 tile = blockIdx.x, q0 = tile * AG_TILE, q = q0 + threadIdx.x, lane = threadIdx.x & 31;
-    const u32 wq0 = q0 + (threadIdx.x & ~31u), qh = q0 + AG_TILE;
+    const u32 tile = blockIdx.x, q = tile * AG_TILE + threadIdx.x, lane = threadIdx.x & 31;
+    const u32 wq0 = tile * AG_TILE + (threadIdx.x & ~31u);
     u32 nb0 = 0, nn0 = 0;
     if (q < d.n_ref) { nb0 = d.pos_node[q]; nn0 = d.pos_node[q + 1] - nb0; }
     const bool active = nn0 != 0;
     ag_cm1 ca; ca.cid = ca.coff = AG_NONE;
-    if (active) ca = d.cm1[q];
-    const u32 nb1c = (q < d.n_ref) ? d.pos_node[q + 1] : 0;   // first node of position q + 1
+    ag_cm1 ca1 = ca;
+    if (active) { ca = d.cm1[q]; ca1 = d.cm1[q + 1]; }  // q + 1 <= n_ref < n_pos + 1 entries... guarded below
     u32 last_v = AG_NONE, last_t = AG_NONE;               // the previous edge: most touches repeat it
-    // item of the touch an alignment makes at position pos (own list [nb, nb+nn)), or 254 = needs the general path, 255 = none
-    auto resolve = [&](const ag_fast& f, u32 pos, const ag_cm1& cpos, u32 nb, u32 nn) -> unsigned char {
-        if (!f.simple || cpos.cid == AG_CM_MANY) return 254;
-        u32 mate = (pos - f.mlo < f.mlen) ? pos + f.mdelta : AG_NONE;
-        ag_cm1 cb; cb.cid = cb.coff = AG_NONE;
-        if (mate != AG_NONE) { cb = d.cm1[mate]; if (cb.cid == AG_CM_MANY) return 254; }
-        ag_nodem c; c.cid = cpos.cid; c.coff = cpos.coff; c.cid0 = cb.cid; c.coff0 = cb.coff; c.moff = mate;
-        u32 it = ag_first_compatible(d.node_m + nb, nn, c, d.iv);
-        return it < 254 ? (unsigned char)it : (unsigned char)254;
-    };
     const u32 kb = d.tile_start[tile], ke = d.tile_start[tile + 1];
     for (u32 c0 = kb; c0 < ke; c0 += NCHUNK) {
         const u32 cn = min((u32)NCHUNK, ke - c0);
@@ -411,27 +394,6 @@ __global__ void __launch_bounds__(AG_TILE, AG_EDGES_MINB) k_edges(DevView d) {
             s_f[threadIdx.x] = ag_fast_prep(d.alnp[idx], d.lo[idx], d.span[idx]);
         }
         __syncthreads();
-        // ---- (1) own items ----
-        for (u32 r0 = 0; r0 < cn; r0 += 32) {
-            bool ov = false;
-            if (r0 + lane < cn) { u32 lo = s_f[r0 + lane].lo; ov = lo <= wq0 + 31 && lo + s_f[r0 + lane].span >= wq0; }
-            u32 mask = __ballot_sync(0xFFFFFFFFu, ov);
-            while (mask) {
-                const u32 a = r0 + (u32)__ffs((int)mask) - 1;
-                mask &= mask - 1;
-                const ag_fast f = s_f[a];
-                if (!active || q - f.lo > f.span) continue;
-                s_item[a * AG_TILE + threadIdx.x] = resolve(f, q, ca, nb0, nn0);
-            }
-        }
-        if (threadIdx.x < cn) {   // halo: the position right after the tile, one alignment per thread
-            const ag_fast f = s_f[threadIdx.x];
-            unsigned char h = 255;
-            if (qh < d.n_ref && qh - f.lo <= f.span) { u32 nb = d.pos_node[qh], nn = d.pos_node[qh + 1] - nb; h = nn ? resolve(f, qh, d.cm1[qh], nb, nn) : (unsigned char)254; }
-            s_halo[threadIdx.x] = h;
-        }
-        __syncthreads();
-        // ---- (2) edges ----
         for (u32 r0 = 0; r0 < cn; r0 += 32) {
             bool ov = false;
             if (r0 + lane < cn) { u32 lo = s_f[r0 + lane].lo; ov = lo <= wq0 + 31 && lo + s_f[r0 + lane].span >= wq0; }
@@ -441,23 +403,11 @@ __global__ void __launch_bounds__(AG_TILE, AG_EDGES_MINB) k_edges(DevView d) {
                 mask &= mask - 1;
                 const ag_fast f = s_f[a];
                 if (!active || q - f.lo >= f.span + (f.simple ? 0u : 1u)) continue;   // simple: calls start at lo .. lo+span-1 only
-                if (f.simple) {
-                    const unsigned char ci = s_item[a * AG_TILE + threadIdx.x];
-                    const unsigned char ni = threadIdx.x == AG_TILE - 1 ? s_halo[a] : s_item[a * AG_TILE + threadIdx.x + 1];
-                    if (ci < 254 && ni < 254) {
-                        const u32 v = nb0 + ci, t = nb1c + ni;
-                        if (v == last_v && t == last_t) continue;
-                        if (ag_edge_ok(d.node_m[v], d.node_m[t], d.iv)) add_edge(d, v, t);
-                        last_v = v; last_t = t;
-                        continue;
-                    }
-                }
-                // general path: resolve both sides with the reference's nested candidate enumeration
                 ag_touch t;
                 if (f.simple) t = ag_fast_touch(f, q, (u32)d.k);
                 else { t = ag_locate(d.alnp[s_idx[a]], d.ext, q, (u32)d.k); if (t.kind != 1) continue; }
                 const u32 nb1 = d.pos_node[t.npos], nn1 = d.pos_node[t.npos + 1] - nb1;
-                const ag_cm1 cn1 = d.cm1[t.npos];
+                const ag_cm1 cn1 = (t.npos == q + 1) ? ca1 : d.cm1[t.npos];
                 for_candidates_fast(d, q, ca, t.mate, [&](const ag_nodem& c) {
                     u32 ci = ag_first_compatible(d.node_m + nb0, nn0, c, d.iv);
                     if (ci == AG_NONE) return;
