@@ -29,7 +29,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 UNIT_BP = 4_600_000          # configs[1]: E. coli-sized unit
-SAMPLE_BP = 460_000          # CPU legs: 1/10 of a unit, same shape (~6 s per pass on one core)
+SAMPLE_BP = 1_150_000        # CPU legs: 1/4 of a unit, same shape (~6 s per pass on one host core of the GPU box)
 SHAPE = dict(coverage=50, readlen=100, insert_mean=500, insert_sd=50, kmer=5, cov=20, contig_len=10000, contig_gap=1000, snp=0.01)
 SEED = 20260925 + 2
 METRIC = "graph-build+extend Mbp/s"
@@ -116,7 +116,7 @@ def reference_arm(args):
             "ms_per_step": round(1000 * worst / args.steps, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
             "data": "synthetic", "config": workload_config(n, sample=True),
             "cpu_baseline": {"value": round(value, 5), "unit": "Mbp/s", "cores": cores, "kind": kind,
-                             "sample": f"{n} unit(s) of {SAMPLE_BP} bp (1/10 of the {UNIT_BP} bp unit, same shape), one process per unit; hot path = span "
+                             "sample": f"{n} unit(s) of {SAMPLE_BP} bp (1/4 of the {UNIT_BP} bp unit, same shape), one process per unit; hot path = span "
                                        f"of the reference's progress lines (loadGenome..scaffoldContigs), text parsing included as in the reference"},
             "e2e": {"value": round(value, 5), "unit": "Mbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": round(wall, 2),
@@ -273,7 +273,6 @@ def b200_arm(args):
         step()
     ms = ctx.timer_stop()
     st = ctx.stats()
-    clock_info = clocks.stop() if clocks else None
     barrier()
     # ---- timed: end to end through the array-level C ABI from pinned host buffers -------------------------------------------------
     ctx.reset_stats()
@@ -285,6 +284,7 @@ def b200_arm(args):
         step()
     ms_e2e = ctx.timer_stop()
     st_e2e = ctx.stats()
+    clock_info = clocks.stop() if clocks else None   # sampled every 100 ms across both timed regions
     barrier()
     assert ctx.text(1) == check_pre and len(check_pre) > 0
     # ---- file level (text in, text out), for reference: one pass --------------------------------------------------------------------
@@ -347,7 +347,7 @@ def b200_arm(args):
                 dirs = make_samples(sdir, 1)
                 s, kind = cpu_pass(dirs)
                 line["cpu_baseline"] = {"value": round(SAMPLE_BP / 1e6 / s, 5), "unit": "Mbp/s", "cores": 1, "kind": kind,
-                                        "sample": f"one {SAMPLE_BP} bp unit (1/10 of the workload unit, same shape), hot path of the reference's CPU "
+                                        "sample": f"one {SAMPLE_BP} bp unit (1/4 of the workload unit, same shape), hot path of the reference's CPU "
                                                   f"implementation timed once: {s:.2f} s"}
                 shutil.rmtree(sdir, ignore_errors=True)
             except Exception as e:  # the CPU leg must never take the GPU number down with it
@@ -364,7 +364,7 @@ def b200_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
