@@ -57,3 +57,18 @@ def test_parallel_text_parsers_match_golden(harness, workdir, name):
     harness.synth(workdir, **cases.GOLDEN[name])
     harness.run_emul(workdir, env={"AG_PARSE_PARALLEL_MIN": "0", "AG_THREADS": "5"})
     compare_with_golden(harness, workdir, name)
+
+
+import edge_cases
+
+
+@pytest.mark.parametrize("kind", edge_cases.KINDS)
+def test_emulation_edge_cases(harness, workdir, kind):
+    emu = os.path.join(workdir, "emu")
+    ora = os.path.join(workdir, "ora")
+    edge_cases.make(harness, emu, kind)
+    shutil.copytree(emu, ora)
+    harness.run_oracle(ora, dump_nodes=True)
+    harness.run_emul(emu, dump_nodes=True)
+    assert harness.unit_outputs(emu, 0) == harness.unit_outputs(ora, 0)
+    assert open(os.path.join(emu, "tmp", "_nodes.0.txt"), "rb").read() == open(os.path.join(ora, "tmp", "_nodes.0.txt"), "rb").read()

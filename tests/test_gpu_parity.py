@@ -118,3 +118,18 @@ def test_baseline_config1_full_size_against_oracle(ag, harness, workdir):
     st, _ = run_cuda(ag, harness, gpu)
     assert harness.unit_outputs(gpu, 0) == harness.unit_outputs(ora, 0)
     assert st["n_aln"] > 1_100_000 and st["walk_fallback"] == 0
+
+
+import edge_cases
+
+
+@pytest.mark.parametrize("kind", edge_cases.KINDS)
+def test_cuda_edge_cases(ag, harness, workdir, kind):
+    gpu = os.path.join(workdir, "gpu")
+    ora = os.path.join(workdir, "ora")
+    edge_cases.make(harness, gpu, kind)
+    shutil.copytree(gpu, ora)
+    harness.run_oracle(ora, dump_nodes=True)
+    st, dumps = run_cuda(ag, harness, gpu, dump=True)
+    assert dumps[0] == open(os.path.join(ora, "tmp", "_nodes.0.txt"), "rb").read()
+    assert harness.unit_outputs(gpu, 0) == harness.unit_outputs(ora, 0)

@@ -32,3 +32,22 @@ def test_oracle_matches_live_reference(harness, workdir, name):
         assert harness.unit_outputs(ref, u) == harness.unit_outputs(ora, u)
     for f in ("_contigs.fa", "_genome.0.fa"):
         assert open(os.path.join(ref, "tmp", f), "rb").read() == open(os.path.join(ora, "tmp", f), "rb").read()
+
+
+import edge_cases
+
+
+@pytest.mark.parametrize("kind", edge_cases.KINDS)
+def test_oracle_edge_cases_match_live_reference(harness, workdir, kind):
+    """Empty SAM / PSL, only unaligned records, k = read length, coverage 0 / huge, all-N and lower-case reads: the restatement
+    follows the real reference on each of them (README -O0 build)."""
+    if not harness.have_reference():
+        pytest.skip("reference not built here (oracle/_ref absent)")
+    ref = os.path.join(workdir, "ref")
+    ora = os.path.join(workdir, "ora")
+    edge_cases.make(harness, ref, kind)
+    shutil.copytree(ref, ora)
+    rc, _ = harness.run_reference(ref, optimized=False)
+    assert rc == 0
+    harness.run_oracle(ora)
+    assert harness.unit_outputs(ref, 0) == harness.unit_outputs(ora, 0)
