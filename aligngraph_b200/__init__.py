@@ -73,6 +73,7 @@ def load_library(path=None):
         "ag_prepare_unit_files": (i32, [vp, cp, i32]),
         "ag_write_unit_files": (i32, [vp, cp, i32]),
         "ag_run_unit_files": (i32, [vp, cp, i32]),
+        "ag_run_units_files": (i32, [C.POINTER(vp), i32, cp, i32, i32, i32, vp, vp]),
         "ag_get_unit": (i32, [vp, C.POINTER(UnitView)]),
         "ag_get_stats": (i32, [vp, C.POINTER(Stats)]),
         "ag_reset_stats": (i32, [vp]),
@@ -139,6 +140,12 @@ class Context:
     # ---- file level (the reference's loop body) ---------------------------------------------------------------------------
     def run_unit(self, tmp_dir, unit):
         self._ck(self._lib.ag_run_unit_files(self._h, os.fsencode(tmp_dir), unit), "ag_run_unit_files")
+
+    def run_units(self, tmp_dir, first, n, prefetch=4):
+        """Units [first, first+n) with the host parsing pipelined ahead of the GPU (ag_run_units_files, this context only)."""
+        arr = (C.c_void_p * 1)(self._h)
+        rc = self._lib.ag_run_units_files(arr, 1, os.fsencode(tmp_dir), first, n, prefetch, None, None)
+        self._ck(rc, "ag_run_units_files")
 
     def prepare_unit(self, tmp_dir, unit):
         self._ck(self._lib.ag_prepare_unit_files(self._h, os.fsencode(tmp_dir), unit), "ag_prepare_unit_files")

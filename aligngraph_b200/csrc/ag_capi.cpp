@@ -5,6 +5,12 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <thread>
+#include <mutex>
+#include <condition_variable>
+#include <map>
+#include <atomic>
+#include <memory>
 
 static_assert(sizeof(ag_aln_c) == sizeof(ag_aln) && sizeof(ag_seg_c) == sizeof(ag_seg) && sizeof(ag_cm_c) == sizeof(ag_cm), "ABI structs mirror the internal layouts");
 
@@ -189,6 +195,71 @@ int ag_run_unit_files(ag_ctx* ctx, const char* tmp_dir, int unit_id) {
     if (!rc) rc = ag_extend(ctx);
     if (!rc) rc = ag_write_unit_files(ctx, tmp_dir, unit_id);
     return rc;
+}
+
+// Several units through the file-level path with the host half pipelined: `prefetch` threads parse units ahead (SAM / PSL / FASTA ->
+// packed arrays) while one worker thread per context uploads, builds, extends and writes.  Units are handed out in order; outputs do
+// not depend on the number of contexts or on timing (units are independent, AG:4779-4781).  `done` is called (serialised) after every
+// unit with its return code; the first failing unit's code is returned.
+int ag_run_units_files(ag_ctx** ctxs, int n_ctx, const char* tmp_dir, int first_unit, int n_units, int prefetch,
+                       void (*done)(int unit, int rc, const char* error, void* user), void* user) {
+    if (!ctxs || n_ctx <= 0 || n_units < 0) return 1;
+    if (n_units == 0) return 0;
+    for (int i = 0; i < n_ctx; i++) if (!ctxs[i] || !ctxs[i]->have_reads) { if (ctxs[i]) ctxs[i]->err = "reads not set"; return 1; }
+    struct Prepared { AgUnit unit; std::string initial_text, error; double s_parse = 0; };
+    std::mutex mu; std::condition_variable cv;
+    std::map<int, std::unique_ptr<Prepared>> ready;
+    std::atomic<int> next_prepare(first_unit), next_run(first_unit);
+    int consumed = first_unit;   // units [first_unit, consumed) have been taken by workers (bounds the look-ahead)
+    const int last = first_unit + n_units;
+    if (prefetch < 1) prefetch = 1;
+    const std::string tmp = tmp_dir;
+    const AgReads& reads = ctxs[0]->reads;
+    auto preparer = [&]() {
+        for (;;) {
+            int u = next_prepare.fetch_add(1);
+            if (u >= last) return;
+            { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return u < consumed + prefetch + n_ctx; }); }
+            auto p = std::make_unique<Prepared>();
+            auto t0 = std::chrono::steady_clock::now();
+            try { ag_prepare_unit(reads, tmp, u, p->unit, p->initial_text); }
+            catch (const AgHostError& e) { p->error = e.msg; }
+            catch (const std::bad_alloc&) { p->error = "out of host memory"; }
+            p->s_parse = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            { std::lock_guard<std::mutex> lk(mu); ready[u] = std::move(p); }
+            cv.notify_all();
+        }
+    };
+    int first_rc = 0;
+    auto worker = [&](ag_ctx* ctx) {
+        for (;;) {
+            int u = next_run.fetch_add(1);
+            if (u >= last) return;
+            std::unique_ptr<Prepared> p;
+            { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return ready.count(u) != 0; }); p = std::move(ready[u]); ready.erase(u); if (u + 1 > consumed) consumed = u + 1; }
+            cv.notify_all();
+            int rc = 0;
+            if (!p->error.empty()) { ctx->err = p->error; rc = 1; }
+            else {
+                ctx->dev->unpin_all();
+                ctx->unit = std::move(p->unit); ctx->res = AgUnitResult(); ctx->res.initial_text = std::move(p->initial_text);
+                ctx->unit_id = u; ctx->uploaded = false; ctx->s_parse += p->s_parse;
+                rc = ag_build(ctx);
+                if (!rc) rc = ag_extend(ctx);
+                if (!rc) rc = ag_write_unit_files(ctx, tmp_dir, u);
+            }
+            std::lock_guard<std::mutex> lk(mu);
+            if (rc && !first_rc) first_rc = rc;
+            if (done) done(u, rc, rc ? ctx->err.c_str() : "", user);
+        }
+    };
+    std::vector<std::thread> th;
+    int n_prep = std::min(prefetch, n_units);
+    for (int i = 0; i < n_prep; i++) th.emplace_back(preparer);
+    for (int i = 1; i < n_ctx; i++) th.emplace_back(worker, ctxs[i]);
+    worker(ctxs[0]);
+    for (auto& t : th) t.join();
+    return first_rc;
 }
 
 int ag_get_unit(ag_ctx* ctx, ag_unit_view* out) {

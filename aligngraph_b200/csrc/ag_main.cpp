@@ -236,38 +236,32 @@ int main(int argc, char* argv[]) {
             ag_get_reads(ctxs[0], &b, &m, &l, &n, &s2, &sm);
             if (ag_set_reads(ctxs[g], b, m, l, n, s2, sm) != 0) die(ag_last_error(ctxs[g]));
         }
-        std::atomic<int> next(cp);
         std::vector<string> errors((size_t)units);
         std::vector<char> done((size_t)units, 0);
-        std::mutex mu;
         int printed = cp;
-        auto flush_progress = [&]() {  // progress lines and checkpoints strictly in unit order, as the reference emits them
-            while (printed < units && done[(size_t)printed]) {
-                if (!errors[(size_t)printed].empty()) die(errors[(size_t)printed]);
-                cout << endl << "CHROMOSOME " << printed << ": " << endl;
+        struct Progress { std::vector<string>* errors; std::vector<char>* done; int* printed; int units; std::ofstream* wcp; } pg{&errors, &done, &printed, units, &wcp};
+        auto flush_progress = [](Progress& g) {  // progress lines and checkpoints strictly in unit order, as the reference emits them
+            while (*g.printed < g.units && (*g.done)[(size_t)*g.printed]) {
+                if (!(*g.errors)[(size_t)*g.printed].empty()) die((*g.errors)[(size_t)*g.printed]);
+                cout << endl << "CHROMOSOME " << *g.printed << ": " << endl;
                 cout << "(1) Chromosome loaded" << endl << "(2) Contig alignment loaded" << endl << "(3) Read alignment loaded" << endl
                      << "(4) Contigs extended" << endl << "(5) Contigs scaffolded" << endl;
                 if (system("ps euf >> mem.txt")) {}
-                wcp << printed + 1 << endl;
-                printed++;
+                *g.wcp << *g.printed + 1 << endl;
+                (*g.printed)++;
             }
         };
-        auto worker = [&](ag_ctx* c) {
-            for (;;) {
-                int u = next.fetch_add(1);
-                if (u >= units) break;
-                int rc = ag_run_unit_files(c, "tmp", u);
-                std::lock_guard<std::mutex> lk(mu);
-                if (rc != 0) errors[(size_t)u] = ag_last_error(c);
-                done[(size_t)u] = 1;
-                flush_progress();
-            }
+        static void (*flush_fn)(Progress&) = flush_progress;
+        auto on_done = [](int unit, int rc, const char* error, void* user) {   // serialised by the library
+            Progress& g = *(Progress*)user;
+            if (rc != 0) (*g.errors)[(size_t)unit] = error && *error ? error : "UNKNOWN ERROR";
+            (*g.done)[(size_t)unit] = 1;
+            flush_fn(g);
         };
-        std::vector<std::thread> th;
-        for (size_t g = 1; g < ctxs.size(); g++) th.emplace_back(worker, ctxs[g]);
-        worker(ctxs[0]);
-        for (auto& t : th) t.join();
-        { std::lock_guard<std::mutex> lk(mu); flush_progress(); }
+        int prefetch = 4;
+        if (const char* e = getenv("AG_PREFETCH")) prefetch = atoi(e);
+        ag_run_units_files(ctxs.data(), (int)ctxs.size(), "tmp", cp, units - cp, prefetch, on_done, &pg);
+        flush_progress(pg);
         if (getenv("AG_STATS")) {
             for (size_t g = 0; g < ctxs.size(); g++) {
                 ag_stats s; ag_get_stats(ctxs[g], &s);

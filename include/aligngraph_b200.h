@@ -96,6 +96,10 @@ int ag_prepare_unit_files(ag_ctx* ctx, const char* tmp_dir, int unit_id);
 int ag_write_unit_files(ag_ctx* ctx, const char* tmp_dir, int unit_id);
 /* the five calls of AG:4768-4776 for unit N */
 int ag_run_unit_files(ag_ctx* ctx, const char* tmp_dir, int unit_id);
+/* units [first_unit, first_unit + n_units) through ag_run_unit_files, one worker per context (one context per GPU), with `prefetch` host
+ * threads parsing units ahead of the GPUs.  `done` (may be NULL) is called after every unit, serialised, possibly out of unit order. */
+int ag_run_units_files(ag_ctx** ctxs, int n_ctx, const char* tmp_dir, int first_unit, int n_units, int prefetch,
+                       void (*done)(int unit, int rc, const char* error, void* user), void* user);
 /* staged arrays of the current unit (valid until the next ag_begin_unit / ag_prepare_unit_files) */
 typedef struct ag_unit_view {
     const char* ref; uint32_t n_ref, n_tail;

@@ -133,3 +133,16 @@ def test_cuda_edge_cases(ag, harness, workdir, kind):
     st, dumps = run_cuda(ag, harness, gpu, dump=True)
     assert dumps[0] == open(os.path.join(ora, "tmp", "_nodes.0.txt"), "rb").read()
     assert harness.unit_outputs(gpu, 0) == harness.unit_outputs(ora, 0)
+
+
+@pytest.mark.parametrize("name", ["two_chr", "k7_150_2chr", "part2"])
+def test_pipelined_multi_unit_entry_point(ag, harness, workdir, name):
+    """ag_run_units_files: host parsing of later units overlaps the GPU work of earlier ones; same files as the reference."""
+    harness.synth(workdir, **cases.GOLDEN[name])
+    harness.prepare_tmp(workdir)
+    p = harness.read_command(workdir)
+    ctx = ag.Context(k=p["kMer"], insert_variation=p["insertVariation"], coverage=p["coverage"])
+    ctx.load_reads_fasta(os.path.join(workdir, "tmp", "_reads.fa"))
+    ctx.run_units(os.path.join(workdir, "tmp"), 0, harness.n_units(workdir), prefetch=3)
+    ctx.close()
+    compare_with_golden(harness, workdir, name)

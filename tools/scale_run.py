@@ -43,6 +43,8 @@ def main():
     ap.add_argument("--json", default=None)
     ap.add_argument("--oracle-unit", type=int, default=None)
     ap.add_argument("--keep", action="store_true")
+    ap.add_argument("--serial", action="store_true", help="one ag_run_unit_files call per unit, no prefetch")
+    ap.add_argument("--prefetch", type=int, default=8)
     ap.add_argument("--ref-slice-bp", type=int, default=2_500_000)
     args = ap.parse_args()
     from tools import synth
@@ -75,9 +77,14 @@ def main():
         ctx.load_reads_fasta(os.path.join(tmp, "_reads.fa"))
         res["reads_parse_s"] = round(time.perf_counter() - t0, 2)
         per_unit = []
-        for u in range(units):
+        if args.serial:
+            for u in range(units):
+                t0 = time.perf_counter()
+                ctx.run_unit(tmp, u)
+                per_unit.append(round(time.perf_counter() - t0, 3))
+        else:   # host parsing of the next units pipelined ahead of the GPU (ag_run_units_files)
             t0 = time.perf_counter()
-            ctx.run_unit(tmp, u)
+            ctx.run_units(tmp, 0, units, prefetch=args.prefetch)
             per_unit.append(round(time.perf_counter() - t0, 3))
         t_hot = time.perf_counter() - t_hot0
         st = ctx.stats()
