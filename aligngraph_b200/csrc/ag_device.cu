@@ -307,6 +307,15 @@ __global__ void __launch_bounds__(AG_TILE, AG_NODES_MINB) k_nodes(DevView d) {
                 }
                 const u32 sl = t.soff | (t.slen << 16);
                 const bool bump = t.kind == 1;
+                if (ca.cid != AG_CM_MANY) {   // one contiMer (or none) at q: single candidate per mate entry, contig clause always true
+                    ag_cm1 cb; cb.cid = cb.coff = AG_NONE;
+                    if (t.mate != AG_NONE) cb = d.cm1[t.mate];
+                    if (cb.cid != AG_CM_MANY) {
+                        ag_nodem c; c.cid = ca.cid; c.coff = ca.coff; c.cid0 = cb.cid; c.coff0 = cb.coff; c.moff = t.mate;
+                        ag_node_touch_single(nl, d.ovf, c, bump, code, f.read, sl, d.iv);
+                        continue;
+                    }
+                }
                 for_candidates_fast(d, q, ca, t.mate, [&](const ag_nodem& c) { ag_node_touch_v(nl, d.ovf, c, bump, code, f.read, sl, d.iv); });
             }
         }
@@ -994,6 +1003,9 @@ void AgDevice::walk_components() {
     }
     const u32 nc = m.n_cand;
     t_.n_components = nc;
+    // every walk starts at a chain head, so the candidate count bounds the number of walk records
+    m.walk_cap = nc + 1; m.walks.ensure(m.walk_cap); m.walks2.ensure(m.walk_cap);
+    d.walks = m.walks.p; d.walks_sorted = m.walks2.p; d.walk_cap = m.walk_cap;
     if (!nc) { chains_valid_ = true; return; }
     unsigned gc = (nc + 255) / 256;
     {
@@ -1015,6 +1027,9 @@ void AgDevice::walk_sequential() {
     Timer tm(st);
     // reset marks to the coverage filter state and replay in one thread
     m.msuf.ensure(nn + 1); m.mnode.ensure(nn + 1); d.msuf = m.msuf.p; d.mnode = m.mnode.p;
+    // with the skip rule a walk may start inside a chain: any live node can be a start
+    m.walk_cap = nn + 1; m.walks.ensure(m.walk_cap); m.walks2.ensure(m.walk_cap);
+    d.walks = m.walks.p; d.walks_sorted = m.walks2.p; d.walk_cap = m.walk_cap;
     k_reset_marks<<<(nn + 255) / 256, 256, 0, st>>>(d, nn); launches_++;
     chains_valid_ = false;  // chains stay valid as data; materialisation switches to the STOP-bit rule
     CK(cudaMemsetAsync(m.counters.p + 3, 0, sizeof(u32), st));
@@ -1029,9 +1044,9 @@ void AgDevice::extend(std::vector<ag_walk>& walks) {
     walks.clear();
     if (!nn) return;
     m.walk_next.ensure(nn + 1); m.parent.ensure(nn + 1); m.cmin.ensure(nn + 1); m.cmax.ensure(nn + 1);
-    m.walk_cap = nn; m.walks.ensure(m.walk_cap); m.walks2.ensure(m.walk_cap); m.cmin.ensure((size_t)nn + 2);
+    m.cmin.ensure((size_t)nn + 2);
     d.walk_next = m.walk_next.p; d.parent = m.parent.p; d.cmin = m.cmin.p; d.cmax = m.cmax.p;
-    d.walks = m.walks.p; d.walks_sorted = m.walks2.p; d.walk_count = m.counters.p + 3; d.walk_cap = m.walk_cap;
+    d.walk_count = m.counters.p + 3;
     CK(cudaMemsetAsync(m.counters.p + 3, 0, sizeof(u32), st));
     walk_components();
     auto fetch = [&]() {
