@@ -333,27 +333,6 @@ AG_HD void ag_node_touch_v(ag_nview& nl, const ag_ovfpool& pool, const ag_nodem&
     nl.n++;
 }
 
-// Same, for a position whose contiMer summary is a single entry (or none): every candidate and therefore every node of the position
-// carries the same (contigID, contigOffset), so the first clause of compatible() (AG:1296-1299) is always true and only the mate-side
-// clauses are evaluated.
-AG_HD void ag_node_touch_single(ag_nview& nl, const ag_ovfpool& pool, const ag_nodem& c, bool bump, int code, u32 sread, u32 soff_len, int iv) {
-    u32 nloc = nl.n < nl.cap ? nl.n : nl.cap;
-    const int lim = 2 * iv + 5 * AG_EP;
-    for (u32 i = 0; i < nloc; i++) {
-        const u32 ycid0 = nl.f(2, i), ymoff = nl.f(4, i);
-        bool c2 = c.cid0 == AG_NONE || ycid0 == AG_NONE || c.cid0 != ycid0 || ag_absdiff(c.coff0, nl.f(3, i)) <= lim;
-        bool c3 = c.moff == AG_NONE || ymoff == AG_NONE || ag_absdiff(c.moff, ymoff) <= lim;
-        if (c2 && c3) { if (bump) { nl.f(5, i)++; if (code >= 0) nl.f(6 + (u32)code, i)++; } return; }
-    }
-    if (nl.n >= nl.cap) { ag_node_touch_v(nl, pool, c, bump, code, sread, soff_len, iv); return; }   // overflow nodes: general path (re-scans the first ones, same result)
-    u32 i = nl.n;
-    nl.f(0, i) = c.cid; nl.f(1, i) = c.coff; nl.f(2, i) = c.cid0; nl.f(3, i) = c.coff0; nl.f(4, i) = c.moff;
-    nl.f(5, i) = bump ? 1u : 0u;
-    for (u32 j = 0; j < 5; j++) nl.f(6 + j, i) = (bump && code == (int)j) ? 1u : 0u;
-    nl.f(11, i) = sread; nl.f(12, i) = soff_len;
-    nl.n++;
-}
-
 // first node of a FINAL list compatible with candidate c
 AG_HD u32 ag_first_compatible(const ag_nodem* nodes, u32 n, const ag_nodem& c, int iv) {
     for (u32 i = 0; i < n; i++) if (ag_compatible(c, nodes[i], iv)) return i;

@@ -307,15 +307,6 @@ __global__ void __launch_bounds__(AG_TILE, AG_NODES_MINB) k_nodes(DevView d) {
                 }
                 const u32 sl = t.soff | (t.slen << 16);
                 const bool bump = t.kind == 1;
-                if (ca.cid != AG_CM_MANY) {   // one contiMer (or none) at q: single candidate per mate entry, contig clause always true
-                    ag_cm1 cb; cb.cid = cb.coff = AG_NONE;
-                    if (t.mate != AG_NONE) cb = d.cm1[t.mate];
-                    if (cb.cid != AG_CM_MANY) {
-                        ag_nodem c; c.cid = ca.cid; c.coff = ca.coff; c.cid0 = cb.cid; c.coff0 = cb.coff; c.moff = t.mate;
-                        ag_node_touch_single(nl, d.ovf, c, bump, code, f.read, sl, d.iv);
-                        continue;
-                    }
-                }
                 for_candidates_fast(d, q, ca, t.mate, [&](const ag_nodem& c) { ag_node_touch_v(nl, d.ovf, c, bump, code, f.read, sl, d.iv); });
             }
         }

@@ -78,15 +78,6 @@ public:
                 if (t.kind == 1 && t.slen) code = rd.code(f.read, f.lsrc_len >> 16, t.soff);
                 u32 sl = t.soff | (t.slen << 16);
                 bool bump = t.kind == 1;
-                if (ca.cid != AG_CM_MANY && !force_generic) {   // same shortcut as k_nodes
-                    ag_cm1 cb; cb.cid = cb.coff = AG_NONE;
-                    if (t.mate != AG_NONE) cb = cm1[t.mate];
-                    if (cb.cid != AG_CM_MANY) {
-                        ag_nodem c; c.cid = ca.cid; c.coff = ca.coff; c.cid0 = cb.cid; c.coff0 = cb.coff; c.moff = t.mate;
-                        ag_node_touch_single(nl, pool, c, bump, code, f.read, sl, iv);
-                        continue;
-                    }
-                }
                 for_candidates_fast(q, ca, t.mate, [&](const ag_nodem& c) { ag_node_touch_v(nl, pool, c, bump, code, f.read, sl, iv); });
             }
             if (err) throw AgHostError{"emul: overflow pool exhausted"};
