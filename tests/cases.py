@@ -22,5 +22,7 @@ LIVE = {
     "c5_shape": dict(genome_bp=200000, chroms=2, part=4, coverage=50, readlen=150, kmer=7, seed=32, indel=0.001),
     # a 160 kbp contig: the walk emits a > 100 kbp contig, which switches on the reference's 1000-position scan skip (AlignGraph.cpp:2194-2202)
     "longcontig": dict(genome_bp=500000, coverage=40, contig_len=160000, contig_gap=3000, seed=41),
+    # contigs longer than LARGE_CHUNK = 1,000,000 bp are cut into chunks (AlignGraph.cpp:3277-3293); 1.28 Mbp walks, skip rule active
+    "bigchunk": dict(genome_bp=3000000, coverage=12, contig_len=1300000, contig_gap=20000, seed=51, cov=4),
     "nocontigs": dict(genome_bp=30000, coverage=50, seed=7, contig_len=150, contig_gap=5000),
 }

@@ -56,7 +56,7 @@ def test_cuda_matches_oracle_nodes_and_files(ag, harness, workdir, name):
         assert dumps[u] == want, "node table differs from the oracle"
         assert harness.unit_outputs(gpu, u) == harness.unit_outputs(ora, u)
     # the > 100 kbp contig case must have gone through the exact sequential replay (skip rule), the others must not
-    assert st["walk_fallback"] == (1 if name == "longcontig" else 0)
+    assert st["walk_fallback"] == (1 if name in ("longcontig", "bigchunk") else 0)
 
 
 def test_run_unit_files_is_the_five_calls(ag, harness, workdir):

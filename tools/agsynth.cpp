@@ -166,7 +166,7 @@ int main(int argc, char** argv) {
     r2.open(p.out + "/reads_2.fa");
     rall.open(p.out + "/tmp/_reads.fa");
 
-    long pair_id = 0, contig_idx = 0, unit_base = 0;
+    long pair_id = 0, contig_idx = 0, chunk_idx = 0, unit_base = 0;
     long n_units = 0;
     for (int c = 0; c < p.chroms; c++) {
         // ---- reference chromosome and diverged target -------------------------------------------------
@@ -226,17 +226,31 @@ int main(int argc, char** argv) {
             std::string seq = tgt.substr(a, b - a);
             bool rc = (contig_idx & 1);
             write_fasta(contigs_fa, "ctg" + std::to_string(contig_idx), rc ? revcomp(seq) : seq);
-            int u = unit_of(t2r[a]);
-            if (unit_of(t2r[b - 1]) == u) {
-                // PSL blocks = maximal runs mapped to consecutive reference positions
+            // formalizeInput cuts contigs of >= 1,000,000 bp into chunks named "chunk.contig" (AlignGraph.cpp:3277-3293); BLAT then reports
+            // one record per chunk, in chunk coordinates
+            const long n = b - a;
+            std::vector<std::pair<long, long>> chunks;   // [s, e) in FILE coordinates (the file holds the reverse complement when rc)
+            if (n < 1000000) chunks.push_back({0, n});
+            else { long cs = 0; for (long cpp = 0; cpp < n; cpp++) if ((cpp + 1) % 1000000 == 0 && cpp < n - 1 - 60) { chunks.push_back({cs, cpp + 1}); cs = cpp + 1; } chunks.push_back({cs, n}); }
+            for (auto& chk : chunks) {
+                long ta = rc ? a + (n - chk.second) : a + chk.first, tb = rc ? a + (n - chk.first) : a + chk.second;   // target interval of the chunk
+                long fa = ta, fb = tb;
+                while (fa < fb && t2r[fa] < 0) fa++;
+                while (fb > fa && t2r[fb - 1] < 0) fb--;
+                long this_chunk = chunk_idx++;
+                if (fb - fa < 1) continue;
+                int u = unit_of(t2r[fa]);
+                if (unit_of(t2r[fb - 1]) != u) continue;
+                // PSL blocks = maximal runs mapped to consecutive reference positions (query offsets relative to the chunk, on the
+                // strand the chunk aligns with)
                 std::vector<long> bs, qs, ts;
                 long qins = 0, nqins = 0, tins = 0, ntins = 0, matches = 0;
-                long i = a;
-                while (i < b) {
+                long i = fa;
+                while (i < fb) {
                     if (t2r[i] < 0) { i++; continue; }
                     long j = i;
-                    while (j + 1 < b && t2r[j + 1] == t2r[j] + 1) j++;
-                    bs.push_back(j - i + 1); qs.push_back(i - a); ts.push_back(t2r[i] - ustart[u]);
+                    while (j + 1 < fb && t2r[j + 1] == t2r[j] + 1) j++;
+                    bs.push_back(j - i + 1); qs.push_back(i - ta); ts.push_back(t2r[i] - ustart[u]);
                     matches += j - i + 1;
                     i = j + 1;
                 }
@@ -246,10 +260,10 @@ int main(int argc, char** argv) {
                     if (tg > 0) { ntins++; tins += tg; }
                 }
                 Out& o = psl[u];
-                long qsize = b - a;
+                long qsize = tb - ta;
                 o.num(matches); o.put("\t0\t0\t0\t"); o.num(nqins); o.putc_('\t'); o.num(qins); o.putc_('\t');
                 o.num(ntins); o.putc_('\t'); o.num(tins); o.putc_('\t'); o.putc_(rc ? '-' : '+'); o.putc_('\t');
-                o.num(contig_idx); o.putc_('.'); o.num(contig_idx); o.putc_('\t'); o.num(qsize); o.put("\t0\t"); o.num(qsize);
+                o.num(this_chunk); o.putc_('.'); o.num(contig_idx); o.putc_('\t'); o.num(qsize); o.putc_('\t'); o.num(qs.front()); o.putc_('\t'); o.num(qs.back() + bs.back());
                 o.put("\t0\t"); o.num(unit_end(u) - ustart[u]); o.putc_('\t'); o.num(ts.front()); o.putc_('\t');
                 o.num(ts.back() + bs.back()); o.putc_('\t'); o.num((long)bs.size()); o.putc_('\t');
                 for (long v : bs) { o.num(v); o.putc_(','); } o.putc_('\t');
