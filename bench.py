@@ -121,7 +121,7 @@ def reference_arm(args):
             "e2e": {"value": round(value, 5), "unit": "Mbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": round(wall, 2),
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     finally:
         shutil.rmtree(base, ignore_errors=True)
 
@@ -352,7 +352,7 @@ def b200_arm(args):
                 shutil.rmtree(sdir, ignore_errors=True)
             except Exception as e:  # the CPU leg must never take the GPU number down with it
                 line["cpu_baseline"] = {"value": None, "unit": "Mbp/s", "cores": 1, "kind": "port", "sample": f"failed: {e}"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     barrier()
     ctx.close()
     if rank == 0:
@@ -361,7 +361,24 @@ def b200_arm(args):
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The one JSON line goes to the real stdout; everything else any library prints to fd 1 (NCCL's version banner, ...) was diverted to
+    stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)   # C-level and Python-level stdout -> stderr from here on
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
