@@ -193,6 +193,15 @@ def b200_arm(args):
         raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
+        # one process per GPU: give every rank its own block of host cores (post passes and staging are memory-bound host work;
+        # unbound ranks pile up on one NUMA node)
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = len(cores) // world
+            if per >= 2:
+                os.sched_setaffinity(0, set(cores[local * per:(local + 1) * per]))
+        except (AttributeError, OSError):
+            pass
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
