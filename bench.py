@@ -196,10 +196,29 @@ def b200_arm(args):
         # one process per GPU: give every rank its own block of host cores (post passes and staging are memory-bound host work;
         # unbound ranks pile up on one NUMA node)
         try:
-            cores = sorted(os.sched_getaffinity(0))
-            per = len(cores) // world
-            if per >= 2:
-                os.sched_setaffinity(0, set(cores[local * per:(local + 1) * per]))
+            allowed = sorted(os.sched_getaffinity(0))
+            mine = None
+            try:   # cores local to this GPU (NVML), shared evenly by the ranks whose GPUs sit on the same NUMA node
+                import pynvml
+                pynvml.nvmlInit()
+                words = (max(allowed) // 64) + 1
+                aff = []
+                for g in range(world):
+                    mask = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(g), words)
+                    aff.append(tuple(c for c in allowed if (mask[c // 64] >> (c % 64)) & 1))
+                peers = [g for g in range(world) if aff[g] == aff[local]]
+                if aff[local] and len(aff[local]) // len(peers) >= 2:
+                    per = len(aff[local]) // len(peers)
+                    i = peers.index(local)
+                    mine = aff[local][i * per:(i + 1) * per]
+            except Exception:
+                mine = None
+            if mine is None:
+                per = len(allowed) // world
+                if per >= 2:
+                    mine = allowed[local * per:(local + 1) * per]
+            if mine:
+                os.sched_setaffinity(0, set(mine))
         except (AttributeError, OSError):
             pass
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
