@@ -77,6 +77,7 @@ def load_library(path=None):
         "ag_get_unit": (i32, [vp, C.POINTER(UnitView)]),
         "ag_get_stats": (i32, [vp, C.POINTER(Stats)]),
         "ag_reset_stats": (i32, [vp]),
+        "ag_keep_node_counts": (i32, [vp, i32]),
         "ag_dump_nodes_text": (i32, [vp, C.POINTER(vp), C.POINTER(u64)]),
         "ag_cuda_stream": (vp, [vp]),
         "ag_invalidate_device_inputs": (i32, [vp]),
@@ -187,6 +188,10 @@ class Context:
 
     def reset_stats(self):
         self._ck(self._lib.ag_reset_stats(self._h), "ag_reset_stats")
+
+    def keep_node_counts(self, on=True):
+        """Keep coverage / base counters per node after the build (needed by dump_nodes_text; tests only)."""
+        self._ck(self._lib.ag_keep_node_counts(self._h, 1 if on else 0), "ag_keep_node_counts")
 
     def dump_nodes_text(self):
         p, n = C.c_void_p(), C.c_uint64()

@@ -286,6 +286,10 @@ int ag_get_stats(ag_ctx* ctx, ag_stats* o) {
 int ag_reset_stats(ag_ctx* ctx) {
     return guard(ctx, [&] { ctx->dev->reset_timings(); ctx->s_parse = ctx->s_device = ctx->s_post = 0; ctx->n_aln = ctx->n_walks = ctx->n_emitted = 0; });
 }
+int ag_keep_node_counts(ag_ctx* ctx, int on) {
+    return guard(ctx, [&] { ctx->dev->set_keep_counts(on != 0); });
+}
+
 int ag_dump_nodes_text(ag_ctx* ctx, const char** text, uint64_t* len) {
     return guard(ctx, [&] {
         AgNodeDump d; ctx->dev->dump_nodes(d);

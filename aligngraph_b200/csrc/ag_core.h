@@ -32,7 +32,19 @@ template <class T> static inline T ag_host_cas(T* p, T c, T v) { T o = *p; if (o
 #define AG_ATOMIC_CAS(p, c, v) ag_host_cas((p), (c), (v))
 #endif
 
-#define AG_TILE 256  // unit positions per tile (= threads per CTA of the node / edge sweeps)
+// Tile geometry of the node / edge sweeps: a CTA of AG_TILE threads = 8 warps; a warp owns AG_WPOS = 31 consecutive unit positions
+// (lanes 0-30) and its lane 31 replays the NEXT position as a halo, so that the item an alignment resolves to at q + 1 reaches the
+// lane of q by one shuffle (the edge of the call that starts at q, AG:1590-1623, is then known inside the node sweep).  A tile owns
+// AG_TPOS positions and additionally needs every alignment that touches its halo position.
+#define AG_TILE 256
+#define AG_WPOS 31
+#define AG_TPOS (8 * AG_WPOS)
+AG_HD void ag_tile_range(u32 lo, u32 hi, u32 n_tiles, u32& t0, u32& t1) {  // tiles that must see an alignment touching [lo, hi]
+    t0 = lo ? (lo - 1) / AG_TPOS : 0u;
+    t1 = hi / AG_TPOS;
+    if (t1 >= n_tiles) t1 = n_tiles - 1;
+    if (t0 > t1) t0 = t1;
+}
 
 AG_HD int ag_absdiff(u32 a, u32 b) {  // abs((int)(a - b)) on unsigned operands, as the reference writes it (AG:1296)
     int d = (int)(a - b);
@@ -185,8 +197,10 @@ struct ag_fast {
     u32 mlo, mlen;       // the right mate covers positions q with (q - mlo) < mlen ...
     u32 mdelta;          // ... where the mate position is q + mdelta            (all modulo 2^32, like the reference's unsigned math)
     u32 read;            // (read index << 1) | rc of the left mate
-    u32 simple;          // 1: fast path valid; 0: use ag_locate on the prepared record
+    u32 simple;          // 0: use ag_locate on the prepared record; bit 0: fast path valid; bit 1 (AG_FAST_CLEAN): every position the alignment
+                         // touches — on the left mate and at the mate positions — holds at most one contiMer, so every touch has one candidate
 };
+#define AG_FAST_CLEAN 2u
 
 AG_HD ag_fast ag_fast_prep(const ag_alnp& p, u32 lo, u32 span) {
     ag_fast f;
@@ -197,6 +211,20 @@ AG_HD ag_fast ag_fast_prep(const ag_alnp& p, u32 lo, u32 span) {
     f.lsrc_len = lsrc | (len << 16);
     f.mlo = lo + rsrc - lsrc; f.mlen = p.r_sl >> 16; f.mdelta = p.r_dst - f.mlo;
     return f;
+}
+
+// many_prefix[p] = number of positions < p holding several contiMers (exclusive scan, n_pos + 1 entries)
+AG_HD bool ag_fast_is_clean(const ag_fast& f, const ag_alnp& p, const u32* many_prefix) {
+    if (!f.simple) return false;
+    if (many_prefix[f.lo + f.span + 1] != many_prefix[f.lo]) return false;
+    // right mate: the touch at q looks at r_dst + (q - mlo) for q in [lo, lo + span] with 0 <= q - mlo < mlen
+    const long long mlo = (long long)f.lo + (long long)(p.r_sl & 0xFFFFu) - (long long)(p.l_sl & 0xFFFFu);
+    const long long qa = (long long)f.lo > mlo ? (long long)f.lo : mlo;
+    const long long qe = (long long)f.lo + f.span, me = mlo + (long long)f.mlen - 1;
+    const long long qb = qe < me ? qe : me;
+    if (qa > qb) return true;
+    const u32 a = p.r_dst + (u32)(qa - mlo), b = p.r_dst + (u32)(qb - mlo);
+    return many_prefix[b + 1] == many_prefix[a];
 }
 
 // touch of a simple alignment at position q; requires q - f.lo <= f.span
@@ -236,11 +264,6 @@ AG_HD bool ag_compatible(const ag_nodem& x, const ag_nodem& y, int iv) {  // AG:
     bool c3 = x.moff == AG_NONE || y.moff == AG_NONE || ag_absdiff(x.moff, y.moff) <= 2 * iv + 5 * AG_EP;
     return c1 && c2 && c3;
 }
-AG_HD bool ag_edge_ok(const ag_nodem& x, const ag_nodem& y, int iv) {  // AG:1600-1615
-    bool c1 = y.cid == AG_NONE || x.cid == AG_NONE || y.cid != x.cid || ag_absdiff(y.coff, x.coff) <= 5 * AG_EP;
-    bool c2 = y.cid0 == AG_NONE || x.cid0 == AG_NONE || y.cid0 != x.cid0 || ag_absdiff(y.coff0, x.coff0) <= 2 * iv + 5 * AG_EP;
-    return c1 && c2;
-}
 
 // contiMers by position (static during the read phase)
 struct ag_cmtab {
@@ -279,64 +302,172 @@ template <class F> AG_HD void ag_for_candidates(const ag_cmtab& t, u32 pos, u32 
 // ---------------------------------------------------------------------------------------------------------------------------
 // node list of one position while it is being built
 // ---------------------------------------------------------------------------------------------------------------------------
-#define AG_NODE_CAP 6
+// The first AG_NODE_SCAP nodes of a position live in "slots" (shared memory on the device, [field][slot][thread], conflict-free);
+// further nodes — and ALL nodes of the rare positions that hold several contiMers — are full ag_nodeb records chained through a
+// global overflow pool.  A slot does not store contigID / contigOffset: on a position with at most one contiMer every candidate
+// carries the same pair (the position's), so clause 1 of compatible() (AG:1296-1299) is identically true there.
+#ifndef AG_NODE_SCAP
+#define AG_NODE_SCAP 2
+#endif
+enum { AG_F_CID0 = 0, AG_F_COFF0 = 1, AG_F_MOFF = 2, AG_F_COV = 3, AG_F_CNT = 4, AG_F_SREAD = 9, AG_F_SL = 10, AG_F_SUCC = 11, AG_NF = 12 };
+struct ag_slots {
+    u32* base; u32 fstride, nstride;
+    AG_HD u32& f(u32 field, u32 i) const { return base[field * fstride + i * nstride]; }
+};
+struct ag_plist { u32 n, ovf_head, ovf_tail; };  // n counts slot nodes + pool nodes
 struct ag_ovfpool { ag_nodeb* node; u32* next; u32* count; u32 cap; int* err; };
 
 AG_HD bool ag_compat_b(const ag_nodem& c, const ag_nodeb& y, int iv) {
     ag_nodem m; m.cid = y.cid; m.coff = y.coff; m.cid0 = y.cid0; m.coff0 = y.coff0; m.moff = y.moff;
     return ag_compatible(c, m, iv);
 }
-
-// Strided view of a position's node list: field f of node i lives at base[f * fstride + i * nstride].  On the device the first
-// `cap` nodes of every position sit in shared memory as [field][node][thread] (conflict-free); the host emulation / generic code
-// uses the same accessors over an array of ag_nodeb (fstride 1, nstride 13).  Nodes beyond `cap` go to a global overflow pool.
-struct ag_nview {
-    u32* base; u32 fstride, nstride, cap;
-    u32 n, ovf_head, ovf_tail;
-    AG_HD void init(u32* b, u32 fs, u32 ns, u32 c) { base = b; fstride = fs; nstride = ns; cap = c; n = 0; ovf_head = ovf_tail = AG_NONE; }
-    AG_HD u32& f(u32 field, u32 i) const { return base[field * fstride + i * nstride]; }
-    AG_HD ag_nodem match(u32 i) const { ag_nodem m; m.cid = f(0, i); m.coff = f(1, i); m.cid0 = f(2, i); m.coff0 = f(3, i); m.moff = f(4, i); return m; }
-    AG_HD ag_nodeb get(u32 i) const {
-        ag_nodeb b; b.cid = f(0, i); b.coff = f(1, i); b.cid0 = f(2, i); b.coff0 = f(3, i); b.moff = f(4, i); b.cov = f(5, i);
-        for (u32 j = 0; j < 5; j++) b.cnt[j] = f(6 + j, i);
-        b.sread = f(11, i); b.soff_len = f(12, i);
-        return b;
-    }
-};
-
-// One candidate of one touch: first-compatible lookup, bump or create  (AG:1375-1389 / AG:1493-1506)
-AG_HD void ag_node_touch_v(ag_nview& nl, const ag_ovfpool& pool, const ag_nodem& c, bool bump, int code, u32 sread, u32 soff_len, int iv) {
-    u32 nloc = nl.n < nl.cap ? nl.n : nl.cap;
-    for (u32 i = 0; i < nloc; i++)
-        if (ag_compatible(c, nl.match(i), iv)) { if (bump) { nl.f(5, i)++; if (code >= 0) nl.f(6 + (u32)code, i)++; } return; }
-    if (nl.n > nl.cap)
-        for (u32 o = nl.ovf_head; o != AG_NONE; o = pool.next[o])
-            if (ag_compat_b(c, pool.node[o], iv)) { if (bump) { pool.node[o].cov++; if (code >= 0) pool.node[o].cnt[code]++; } return; }
-    if (nl.n < nl.cap) {
-        u32 i = nl.n;
-        nl.f(0, i) = c.cid; nl.f(1, i) = c.coff; nl.f(2, i) = c.cid0; nl.f(3, i) = c.coff0; nl.f(4, i) = c.moff;
-        nl.f(5, i) = bump ? 1u : 0u;
-        for (u32 j = 0; j < 5; j++) nl.f(6 + j, i) = (bump && code == (int)j) ? 1u : 0u;
-        nl.f(11, i) = sread; nl.f(12, i) = soff_len;
-    } else {
-        u32 o = AG_ATOMIC_ADD(pool.count, 1u);
-        if (o >= pool.cap) { *pool.err = 1; return; }
-        pool.next[o] = AG_NONE;
-        if (nl.ovf_tail == AG_NONE) nl.ovf_head = o; else pool.next[nl.ovf_tail] = o;
-        nl.ovf_tail = o;
-        ag_nodeb* h = &pool.node[o];
-        h->cid = c.cid; h->coff = c.coff; h->cid0 = c.cid0; h->coff0 = c.coff0; h->moff = c.moff;
-        h->cov = bump ? 1u : 0u;
-        for (u32 j = 0; j < 5; j++) h->cnt[j] = (bump && code == (int)j) ? 1u : 0u;
-        h->sread = sread; h->soff_len = soff_len;
-    }
-    nl.n++;
+// clauses 2 and 3 of compatible() (AG:1300-1310) on scalars
+AG_HD bool ag_compat23(u32 cid0, u32 coff0, u32 moff, u32 ycid0, u32 ycoff0, u32 ymoff, int iv) {
+    bool c2 = cid0 == AG_NONE || ycid0 == AG_NONE || cid0 != ycid0 || ag_absdiff(coff0, ycoff0) <= 2 * iv + 5 * AG_EP;
+    bool c3 = moff == AG_NONE || ymoff == AG_NONE || ag_absdiff(moff, ymoff) <= 2 * iv + 5 * AG_EP;
+    return c2 && c3;
 }
 
-// first node of a FINAL list compatible with candidate c
-AG_HD u32 ag_first_compatible(const ag_nodem* nodes, u32 n, const ag_nodem& c, int iv) {
-    for (u32 i = 0; i < n; i++) if (ag_compatible(c, nodes[i], iv)) return i;
+// append a full record to the position's pool chain; returns the pool slot (NONE when the pool is exhausted: err is set and the
+// whole sweep is repeated with a larger pool)
+AG_HD u32 ag_pool_new(ag_plist& pl, const ag_ovfpool& pool, const ag_nodem& c, bool bump, int code, u32 sread, u32 soff_len) {
+    u32 o = AG_ATOMIC_ADD(pool.count, 1u);
+    if (o >= pool.cap) { *pool.err = 1; return AG_NONE; }
+    pool.next[o] = AG_NONE;
+    if (pl.ovf_tail == AG_NONE) pl.ovf_head = o; else pool.next[pl.ovf_tail] = o;
+    pl.ovf_tail = o;
+    ag_nodeb* h = &pool.node[o];
+    h->cid = c.cid; h->coff = c.coff; h->cid0 = c.cid0; h->coff0 = c.coff0; h->moff = c.moff;
+    h->cov = bump ? 1u : 0u;
+    for (u32 j = 0; j < 5; j++) h->cnt[j] = (bump && code == (int)j) ? 1u : 0u;
+    h->sread = sread; h->soff_len = soff_len; h->succ = 0;
+    return o;
+}
+
+// One candidate of one touch on a slot-mode position: first-compatible lookup, bump or create (AG:1375-1389 / AG:1493-1506).
+// Returns the item index (stable: lists only grow at the tail); oslot = pool slot of the item, NONE when it sits in a slot.
+AG_HD u32 ag_touch_slots(ag_plist& pl, const ag_slots& sv, const ag_ovfpool& pool, const ag_nodem& c, bool bump, int code, u32 sread, u32 soff_len, int iv, u32& oslot) {
+    oslot = AG_NONE;
+    const u32 nloc = pl.n < (u32)AG_NODE_SCAP ? pl.n : (u32)AG_NODE_SCAP;
+    for (u32 i = 0; i < nloc; i++)
+        if (ag_compat23(c.cid0, c.coff0, c.moff, sv.f(AG_F_CID0, i), sv.f(AG_F_COFF0, i), sv.f(AG_F_MOFF, i), iv)) {
+            if (bump) { sv.f(AG_F_COV, i)++; if (code >= 0) sv.f(AG_F_CNT + (u32)code, i)++; }
+            return i;
+        }
+    if (pl.n > (u32)AG_NODE_SCAP) {
+        u32 i = AG_NODE_SCAP;
+        for (u32 o = pl.ovf_head; o != AG_NONE; o = pool.next[o], i++) {
+            ag_nodeb* h = &pool.node[o];
+            if (ag_compat23(c.cid0, c.coff0, c.moff, h->cid0, h->coff0, h->moff, iv)) { if (bump) { h->cov++; if (code >= 0) h->cnt[code]++; } oslot = o; return i; }
+        }
+    }
+    const u32 i = pl.n;
+    if (i < (u32)AG_NODE_SCAP) {
+        sv.f(AG_F_CID0, i) = c.cid0; sv.f(AG_F_COFF0, i) = c.coff0; sv.f(AG_F_MOFF, i) = c.moff;
+        sv.f(AG_F_COV, i) = bump ? 1u : 0u;
+        for (u32 j = 0; j < 5; j++) sv.f(AG_F_CNT + j, i) = (bump && code == (int)j) ? 1u : 0u;
+        sv.f(AG_F_SREAD, i) = sread; sv.f(AG_F_SL, i) = soff_len; sv.f(AG_F_SUCC, i) = 0;
+    } else {
+        oslot = ag_pool_new(pl, pool, c, bump, code, sread, soff_len);
+        if (oslot == AG_NONE) return i;
+    }
+    pl.n = i + 1;
+    return i;
+}
+
+// the same on a position that holds several contiMers: every node is a pool record and all three clauses are evaluated
+AG_HD u32 ag_touch_pool(ag_plist& pl, const ag_ovfpool& pool, const ag_nodem& c, bool bump, int code, u32 sread, u32 soff_len, int iv, u32& oslot) {
+    u32 i = 0;
+    for (u32 o = pl.ovf_head; o != AG_NONE; o = pool.next[o], i++)
+        if (ag_compat_b(c, pool.node[o], iv)) { ag_nodeb* h = &pool.node[o]; if (bump) { h->cov++; if (code >= 0) h->cnt[code]++; } oslot = o; return i; }
+    oslot = ag_pool_new(pl, pool, c, bump, code, sread, soff_len);
+    if (oslot != AG_NONE) pl.n = i + 1;
+    return i;
+}
+
+// record "the call that bumped (item, oslot) continues on item `nb` of the next position"
+AG_HD void ag_note_succ(const ag_slots& sv, const ag_ovfpool& pool, u32 item, u32 oslot, u32 nb) {
+    if (oslot == AG_NONE) sv.f(AG_F_SUCC, item) |= 1u << nb; else pool.node[oslot].succ |= 1u << nb;
+}
+
+// What one lane (= one unit position q) does with one alignment of its tile during the node sweep.
+//   want: a call starts at q (kind-1 touch), so an edge to the alignment's item at the call's successor position is due;
+//   sh:   the item this lane resolved, offered to the lane on its left as that successor item — only for CLEAN alignments (successor
+//         position = q + 1, i.e. the next lane, and exactly one candidate per touch); NONE otherwise.
+// An edge that cannot be settled through (want, sh of the right neighbour) flags the tile for the generic edge sweep: flag 1 when the
+// alignment is not clean (the generic sweep then handles exactly the non-clean alignments of the tile), flag 2 when a clean alignment
+// met an item index >= 32 (the generic sweep then redoes every call of the tile; edges are de-duplicated).
+struct ag_lane_out { u32 sh, item, oslot; bool want; };
+
+// rare cases (several contiMers on either side, multi-segment CIGARs, gap chains): the reference's nested candidate enumeration
+// (AG:1369-1477).  Out of line and by value so that the hot path keeps its list state in registers.
+struct ag_gen_ret { ag_plist pl; bool want; };
+template <class CodeF>
+AG_HD_COLD ag_gen_ret ag_lane_generic(ag_plist pl, const ag_slots sv, const ag_ovfpool pool, const ag_cmtab cmt, const ag_cm1 ca, const ag_touch t, u32 q, u32 sread, int iv,
+                                      CodeF codef) {
+    int code = -1;
+    if (t.kind == 1 && t.slen) code = codef(t.soff);
+    const u32 sl = t.soff | (t.slen << 16);
+    const bool bump = t.kind == 1;
+    const bool slots = ca.cid != AG_CM_MANY;
+    ag_for_candidates(cmt, q, t.mate, [&](const ag_nodem& c) {
+        u32 o;
+        if (slots) ag_touch_slots(pl, sv, pool, c, bump, code, sread, sl, iv, o);
+        else ag_touch_pool(pl, pool, c, bump, code, sread, sl, iv, o);
+    });
+    ag_gen_ret r; r.pl = pl; r.want = bump;
+    return r;
+}
+
+AG_HD_COLD ag_touch ag_locate_cold(const ag_alnp* ap, const ag_seg* ext, u32 q, u32 k) { return ag_locate(*ap, ext, q, k); }
+AG_HD u32 ag_fast_mate(const ag_fast& f, u32 q) { return (q - f.mlo < f.mlen) ? q + f.mdelta : AG_NONE; }
+
+// the common case: simple alignment (one M segment per mate), at most one contiMer at q (ca) and at the mate position (cb)
+template <class CodeF>
+AG_HD void ag_lane_fast(ag_lane_out& out, ag_plist& pl, const ag_slots& sv, const ag_ovfpool& pool, const ag_cm1& ca, const ag_cm1& cb, const ag_fast& f, u32 q, u32 mate,
+                        u32 k, int iv, CodeF codef) {
+    const u32 d = q - f.lo, len = f.lsrc_len >> 16, a = (f.lsrc_len & 0xFFFFu) + d;
+    const bool bump = d < f.span;                             // a call starts here (kind 1); else the stand-alone k2 of the last call
+    const u32 slen = bump ? k : ag_min_u32(k, len - a);
+    int code = -1;
+    if (bump && slen) code = codef(a);
+    ag_nodem c; c.cid = ca.cid; c.coff = ca.coff; c.cid0 = cb.cid; c.coff0 = cb.coff; c.moff = mate;
+    out.item = ag_touch_slots(pl, sv, pool, c, bump, code, f.read, a | (slen << 16), iv, out.oslot);
+    out.sh = out.item; out.want = bump;
+}
+
+// everything one lane does with one tile alignment whose touch range contains q (q - f.lo <= f.span)
+template <class CodeF>
+AG_HD void ag_lane_touch(ag_lane_out& out, ag_plist& pl, const ag_slots& sv, const ag_ovfpool& pool, const ag_cmtab& cmt, const ag_cm1* cm1, const ag_cm1& ca, const ag_fast& f,
+                         const ag_alnp* ap, const ag_seg* ext, u32 q, u32 k, int iv, bool force_generic, CodeF codef) {
+    out.sh = AG_NONE; out.item = 0; out.oslot = AG_NONE; out.want = false;
+    if ((f.simple & AG_FAST_CLEAN) && !force_generic) {   // one candidate by construction: neither ca nor cb can be AG_CM_MANY
+        const u32 mate = ag_fast_mate(f, q);
+        ag_cm1 cb; cb.cid = cb.coff = AG_NONE;
+        if (mate != AG_NONE) cb = cm1[mate];
+        ag_lane_fast(out, pl, sv, pool, ca, cb, f, q, mate, k, iv, codef);
+        return;
+    }
+    ag_touch t;
+    if (f.simple && !force_generic) t = ag_fast_touch(f, q, k);
+    else { t = ag_locate_cold(ap, ext, q, k); if (!t.kind) return; }
+    const ag_gen_ret r = ag_lane_generic(pl, sv, pool, cmt, ca, t, q, f.read, iv, codef);
+    pl = r.pl; out.want = r.want;
+}
+
+// first node of the FINAL list [nb, nb + n) compatible with candidate c
+AG_HD u32 ag_first_compatible(const ag_nodec* nc, const ag_nodew* nw, u32 nb, u32 n, const ag_nodem& c, int iv) {
+    for (u32 i = 0; i < n; i++) {
+        const ag_nodec y = nc[nb + i];
+        ag_nodem m; m.cid = y.cid; m.coff = y.coff; m.cid0 = y.cid0; m.coff0 = y.coff0; m.moff = nw[nb + i].moff;
+        if (ag_compatible(c, m, iv)) return i;
+    }
     return AG_NONE;
+}
+AG_HD bool ag_edge_ok_c(const ag_nodec& x, const ag_nodec& y, int iv) {  // AG:1600-1615
+    bool c1 = y.cid == AG_NONE || x.cid == AG_NONE || y.cid != x.cid || ag_absdiff(y.coff, x.coff) <= 5 * AG_EP;
+    bool c2 = y.cid0 == AG_NONE || x.cid0 == AG_NONE || y.cid0 != x.cid0 || ag_absdiff(y.coff0, x.coff0) <= 2 * iv + 5 * AG_EP;
+    return c1 && c2;
 }
 
 // consensus base of a node (AG:1944-1952 + AG:1997-2001)
@@ -348,6 +479,14 @@ AG_HD char ag_consensus(const u32* cnt, char refbase) {
     if (g >= a && g >= c && g >= t && g >= n) return 'G';
     if (t >= a && t >= c && t >= g && t >= n) return 'T';
     return 'N';
+}
+
+// misc word of a final node: consensus base, coverage filter (AG:1912-1915), contigOffset != -1 (AG:2004)
+AG_HD u32 ag_node_misc(u32 cid, u32 coff, u32 cov, const u32* cnt, char refbase, int coverage) {
+    u32 misc = (u32)(unsigned char)ag_consensus(cnt, refbase);
+    if (cid == AG_NONE && (int)cov < coverage) misc |= AG_NW_FILTERED | AG_NW_TRAV;
+    if (coff != AG_NONE) misc |= AG_NW_HASCONTIG;
+    return misc;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------

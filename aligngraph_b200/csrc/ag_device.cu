@@ -158,14 +158,14 @@ __global__ void k_rs_scatter(const u32* __restrict__ keys, const u32* __restrict
 struct DevView {
     ag_reads reads;
     const unsigned char* ref; u32 n_ref, n_pos;
-    ag_cmtab cmt; const ag_cm1* cm1; const u32* chain_pos; const unsigned char* chain_base;
+    ag_cmtab cmt; const ag_cm1* cm1; const u32* many_prefix; const u32* chain_pos; const unsigned char* chain_base;
     const ag_aln* aln; u32 n_aln; const ag_seg* ext;
-    ag_alnp* alnp; u32* lo; u32* span; u32* ntiles; u32* key_off;
+    ag_alnp* alnp; ag_fast* fast; u32* ntiles; u32* key_off;
     u32* keys; u32* vals; u32* tile_cnt; u32* tile_start; u32 n_tiles;
-    ag_nodeb* pool; u32* pool_count; u32 pool_cap;
     ag_ovfpool ovf;
-    u32* pos_cnt; u32* pos_pool; u32* pos_node;
-    ag_nodem* node_m; ag_nodew* node_w; u32* node_sref; u32* node_pos;
+    u32* ticket; unsigned long long* tile_state; u32* tile_flag; u32* n_nodes_out; u32 node_cap;
+    u32* pos_node;
+    ag_nodec* node_c; ag_nodew* node_w; u32* node_sref; u32* node_pos; u32* node_cc;
     u32* eovf_head; u32* eovf_target; u32* eovf_next; u32* eovf_count; u32 eovf_cap;
     u32* walk_next; u32* parent; u32* cmin; u32* cmax;
     u32* cand_rank; u32* cand_node; u32* cand_label;
@@ -190,9 +190,14 @@ __global__ void k_prep(DevView d) {
     bool bad = false;
     for (u32 j = 0; j < L.n; j++) { ag_seg s = L.get(j); if (s.dst + s.len > d.n_ref || s.src + s.len > len) bad = true; }
     for (u32 j = 0; j < R.n; j++) { ag_seg s = R.get(j); if (s.dst + s.len > d.n_ref || s.src + s.len > len) bad = true; }
+    if (o.any && o.lo + o.span >= d.n_ref) bad = true;
     if (bad) { *d.err = 2; o.any = 0; }
-    d.alnp[i] = o.p; d.lo[i] = o.lo; d.span[i] = o.span;
-    d.ntiles[i] = o.any ? ((o.lo + o.span) / AG_TILE - o.lo / AG_TILE + 1) : 0;
+    ag_fast f = ag_fast_prep(o.p, o.lo, o.span);
+    if (o.any && ag_fast_is_clean(f, o.p, d.many_prefix)) f.simple |= AG_FAST_CLEAN;
+    d.alnp[i] = o.p; d.fast[i] = f;
+    u32 nt = 0;
+    if (o.any) { u32 t0, t1; ag_tile_range(o.lo, o.lo + o.span, d.n_tiles, t0, t1); nt = t1 - t0 + 1; }
+    d.ntiles[i] = nt;
 }
 
 __global__ void k_keys(DevView d) {
@@ -200,33 +205,41 @@ __global__ void k_keys(DevView d) {
     if (i >= d.n_aln) return;
     u32 n = d.ntiles[i];
     if (!n) return;
-    u32 off = d.key_off[i], t0 = d.lo[i] / AG_TILE;
+    const ag_fast f = d.fast[i];
+    u32 t0, t1; ag_tile_range(f.lo, f.lo + f.span, d.n_tiles, t0, t1);
+    u32 off = d.key_off[i];
     for (u32 j = 0; j < n; j++) { d.keys[off + j] = t0 + j; d.vals[off + j] = i; atomicAdd(&d.tile_cnt[t0 + j], 1u); }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
 // k_cm1: per-position summary of the contiMer table (one 8-byte load per lookup in the sweeps)
 // ---------------------------------------------------------------------------------------------------------------------------
-__global__ void k_cm1(DevView d, ag_cm1* out, unsigned char* pos_term) {
+__global__ void k_cm1(DevView d, ag_cm1* out, unsigned char* pos_term, u32* many) {
     u32 p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= d.n_pos) return;
-    out[p] = ag_make_cm1(d.cmt, p);
+    const ag_cm1 c = ag_make_cm1(d.cmt, p);
+    out[p] = c; many[p] = c.cid == AG_CM_MANY ? 1u : 0u;
     unsigned char t = 0;
     for (u32 e = d.cmt.start[p]; e < d.cmt.start[p + 1]; e++) if (d.cmt.cm[e].chain == d.cmt.cm[e].term) t = 1;
     pos_term[p] = t;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
-// k_nodes: one CTA per tile of AG_TILE positions, one thread per position.  The tile's alignments arrive sorted by global
-// alignment order; they are staged through shared memory in chunks (touch arithmetic pre-reduced to ag_fast once per tile and
-// alignment), each warp keeps only the entries that overlap its 32 positions (ballot), and every thread replays the reference's
-// first-compatible clustering on a node list held in shared memory ([field][node][thread], conflict-free).
+// k_build: the node sweep, with the edges of the common case settled in the same pass.
+//   * one CTA per tile (handed out by ticket), 8 warps x (31 owned positions + 1 halo lane), one thread per position;
+//   * the tile's alignments arrive sorted by global alignment order and are staged through shared memory in chunks (touch
+//     arithmetic pre-reduced to ag_fast by k_prep, the left mates' packed bases next to them); each warp keeps only the entries that
+//     overlap its 32 positions (ballot) and every thread replays the reference's first-compatible clustering on a node list held in
+//     shared memory ([field][slot][thread], conflict-free);
+//   * the item a touch resolves to never moves (lists grow at the tail), and the call that starts at q continues at q + 1 with the item
+//     the NEXT lane resolves for the same alignment in the same iteration: one shuffle yields the edge (AG:1590-1623), kept as a bit per
+//     successor item until the final node indices exist (k_succ).  Calls that cannot be settled this way (multi-segment CIGARs, several
+//     contiMers on a side, item >= 32) flag the tile for the generic edge sweep k_edges;
+//   * the tiles' node counts are chained by a decoupled look-back, so nodes are written straight into their final, position-ordered
+//     records — no intermediate pool, no second pass.
 // ---------------------------------------------------------------------------------------------------------------------------
 #ifndef AG_NCHUNK
 #define AG_NCHUNK 128
-#endif
-#ifndef AG_NODE_SCAP
-#define AG_NODE_SCAP 2
 #endif
 #ifndef AG_NODES_MINB
 #define AG_NODES_MINB 6
@@ -238,47 +251,52 @@ __global__ void k_cm1(DevView d, ag_cm1* out, unsigned char* pos_term) {
 #define AG_NCHUNK_NODES 64
 #endif
 constexpr int NCHUNK = AG_NCHUNK;            // chunk of tile alignments staged per round in k_edges
-constexpr int NCHUNK_N = AG_NCHUNK_NODES;    // ... in k_nodes (smaller: its shared memory also holds the node lists and the reads)
-constexpr int NODE_SCAP = AG_NODE_SCAP;                                   // nodes per position kept in shared memory; more spill to the pool
-constexpr int NODES_SMEM = 13 * NODE_SCAP * AG_TILE * 4;       // bytes of dynamic shared memory for the node lists
-constexpr int READ_WORDS_MAX = 24;                             // stage reads of up to 256 bases (16 + 8 words) per chunk entry
+constexpr int NCHUNK_N = AG_NCHUNK_NODES;    // ... in k_build (smaller: its shared memory also holds the node lists and the reads)
+constexpr int NODE_SCAP = AG_NODE_SCAP;                         // nodes per position kept in shared memory; more spill to the pool
+constexpr int NODES_SMEM = AG_NF * NODE_SCAP * AG_TILE * 4;     // bytes of dynamic shared memory for the node lists
+constexpr int READ_WORDS_MAX = 24;                              // stage reads of up to 256 bases (16 + 8 words) per chunk entry
+constexpr unsigned long long ST_AGG = 1ull << 62, ST_INC = 2ull << 62, ST_VAL = (1ull << 62) - 1;
 
-// one candidate when both sides have at most one contiMer (the common case), else the reference's nested enumeration
-template <class F> __device__ __forceinline__ void for_candidates_fast(const DevView& d, u32 q, const ag_cm1& ca, u32 mate, F f) {
-    ag_cm1 cb; cb.cid = cb.coff = AG_NONE;
-    if (mate != AG_NONE) cb = d.cm1[mate];
-    if (ca.cid != AG_CM_MANY && cb.cid != AG_CM_MANY) {
-        ag_nodem c; c.cid = ca.cid; c.coff = ca.coff; c.cid0 = cb.cid; c.coff0 = cb.coff; c.moff = mate;
-        f(c);
-    } else ag_for_candidates(d.cmt, q, mate, f);
+__device__ __forceinline__ void emit_node(const DevView& d, u32 v, u32 q, char refb, u32 cid, u32 coff, u32 cid0, u32 coff0, u32 moff, u32 cov, const u32* cnt,
+                                          u32 sread, u32 sl, u32 succ) {
+    ag_nodec c; c.cid = cid; c.coff = coff; c.cid0 = cid0; c.coff0 = coff0;
+    d.node_c[v] = c;
+    ag_nodew w; w.succ0 = succ; w.succ1 = AG_NONE; w.moff = moff; w.misc = ag_node_misc(cid, coff, cov, cnt, refb, d.coverage);  // succ0 holds the item mask until k_succ
+    d.node_w[v] = w;
+    *reinterpret_cast<uint2*>(d.node_sref + 2 * (size_t)v) = make_uint2(sread, sl);
+    d.node_pos[v] = q;
+    if (d.node_cc) { u32* o = d.node_cc + 6 * (size_t)v; o[0] = cov; for (int j = 0; j < 5; j++) o[1 + j] = cnt[j]; }
 }
 
-__global__ void __launch_bounds__(AG_TILE, AG_NODES_MINB) k_nodes(DevView d) {
+__global__ void __launch_bounds__(AG_TILE, AG_NODES_MINB) k_build(DevView d) {
     extern __shared__ u32 s_nodes[];
-    u32* const s_reads = s_nodes + 13 * NODE_SCAP * AG_TILE;   // [NCHUNK_N][rw] raw words of every chunk entry's left mate (bases, then mask)
+    u32* const s_reads = s_nodes + AG_NF * NODE_SCAP * AG_TILE;   // [NCHUNK_N][rw] raw words of every chunk entry's left mate (bases, then mask)
     __shared__ ag_fast s_f[NCHUNK_N];
     __shared__ u32 s_idx[NCHUNK_N];
     __shared__ u32 s_scan[33];
-    __shared__ u32 s_base;
-    const u32 tile = blockIdx.x, q = tile * AG_TILE + threadIdx.x, lane = threadIdx.x & 31;
-    const bool active = q < d.n_ref;
-    const u32 wq0 = tile * AG_TILE + (threadIdx.x & ~31u);     // first position of this warp
-    ag_nview nl; nl.init(s_nodes + threadIdx.x, NODE_SCAP * AG_TILE, AG_TILE, NODE_SCAP);
+    __shared__ u32 s_base, s_tile, s_flag, s_total;
+    if (threadIdx.x == 0) { s_tile = atomicAdd(d.ticket, 1u); s_flag = 0; }
+    __syncthreads();
+    const u32 tile = s_tile, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 wq0 = tile * AG_TPOS + warp * AG_WPOS, q = wq0 + lane;   // lane 31 = halo: first position of the next warp / tile
+    const bool active = q < d.n_ref, owner = active && lane < AG_WPOS;
+    ag_slots sv; sv.base = s_nodes + threadIdx.x; sv.fstride = NODE_SCAP * AG_TILE; sv.nstride = AG_TILE;
+    ag_plist pl; pl.n = 0; pl.ovf_head = pl.ovf_tail = AG_NONE;
     ag_cm1 ca; ca.cid = ca.coff = AG_NONE;
     if (active) ca = d.cm1[q];
+    const u32 rw = d.rw, s2 = d.reads.stride2;
     const u32 kb = d.tile_start[tile], ke = d.tile_start[tile + 1];
     for (u32 c0 = kb; c0 < ke; c0 += NCHUNK_N) {
         const u32 cn = min((u32)NCHUNK_N, ke - c0);
         if (threadIdx.x < cn) {
-            u32 idx = d.vals[c0 + threadIdx.x];
+            const u32 idx = d.vals[c0 + threadIdx.x];
             s_idx[threadIdx.x] = idx;
-            s_f[threadIdx.x] = ag_fast_prep(d.alnp[idx], d.lo[idx], d.span[idx]);
+            s_f[threadIdx.x] = d.fast[idx];
         }
         __syncthreads();
-        if (d.rw) {  // stage the left mates' packed bases + non-ACGT plane: two dependent global loads per touch become shared-memory reads
-            const u32 s2 = d.reads.stride2;
-            for (u32 w = threadIdx.x; w < cn * d.rw; w += AG_TILE) {
-                const u32 e = w / d.rw, j = w - e * d.rw, read = s_f[e].read >> 1;
+        if (rw) {  // stage the left mates' packed bases + non-ACGT plane: two dependent global loads per touch become shared-memory reads
+            for (u32 w = threadIdx.x; w < cn * rw; w += AG_TILE) {
+                const u32 e = w / rw, j = w - e * rw, read = s_f[e].read >> 1;
                 s_reads[w] = j < s2 ? d.reads.bases[(u64)read * s2 + j] : d.reads.nmask[(u64)read * d.reads.stridem + (j - s2)];
             }
             __syncthreads();
@@ -286,78 +304,116 @@ __global__ void __launch_bounds__(AG_TILE, AG_NODES_MINB) k_nodes(DevView d) {
         for (u32 r0 = 0; r0 < cn; r0 += 32) {
             // which of these 32 entries touch any of the warp's 32 positions?
             bool ov = false;
-            if (r0 + lane < cn) { u32 lo = s_f[r0 + lane].lo; ov = lo <= wq0 + 31 && lo + s_f[r0 + lane].span >= wq0; }
+            if (r0 + lane < cn) { const u32 lo = s_f[r0 + lane].lo; ov = lo <= wq0 + 31 && lo + s_f[r0 + lane].span >= wq0; }
             u32 mask = __ballot_sync(0xFFFFFFFFu, ov);
             while (mask) {
                 const u32 a = r0 + (u32)__ffs((int)mask) - 1;
                 mask &= mask - 1;
                 const ag_fast f = s_f[a];
-                if (!active || q - f.lo > f.span) continue;
-                ag_touch t;
-                if (f.simple) t = ag_fast_touch(f, q, (u32)d.k);
-                else { t = ag_locate(d.alnp[s_idx[a]], d.ext, q, (u32)d.k); if (!t.kind) continue; }
-                int code = -1;
-                if (t.kind == 1 && t.slen) {
-                    if (d.rw) {
-                        const u32 rc = f.read & 1, len = f.lsrc_len >> 16, i = rc ? len - 1 - t.soff : t.soff;
-                        const u32* rd = s_reads + a * d.rw;
-                        if ((rd[d.reads.stride2 + (i >> 5)] >> (i & 31)) & 1) code = 4;
-                        else { u32 c = (rd[i >> 4] >> ((i & 15) * 2)) & 3; code = rc ? 3 - (int)c : (int)c; }
-                    } else code = d.reads.code(f.read, f.lsrc_len >> 16, t.soff);
+                ag_lane_out out; out.sh = AG_NONE; out.item = 0; out.oslot = AG_NONE; out.want = false;
+                if (active && q - f.lo <= f.span) {
+                    const u32* rd = s_reads + a * rw;
+                    const ag_reads reads = d.reads;
+                    const u32 fread = f.read, flen = f.lsrc_len >> 16;
+                    auto codef = [=](u32 soff) -> int {
+                        if (!rw) return reads.code(fread, flen, soff);
+                        const u32 rc = fread & 1, i = rc ? flen - 1 - soff : soff;
+                        if ((rd[s2 + (i >> 5)] >> (i & 31)) & 1) return 4;
+                        const u32 c = (rd[i >> 4] >> ((i & 15) * 2)) & 3;
+                        return rc ? 3 - (int)c : (int)c;
+                    };
+                    ag_lane_touch(out, pl, sv, d.ovf, d.cmt, d.cm1, ca, f, d.alnp + s_idx[a], d.ext, q, (u32)d.k, d.iv, false, codef);
                 }
-                const u32 sl = t.soff | (t.slen << 16);
-                const bool bump = t.kind == 1;
-                for_candidates_fast(d, q, ca, t.mate, [&](const ag_nodem& c) { ag_node_touch_v(nl, d.ovf, c, bump, code, f.read, sl, d.iv); });
+                // the call that starts at q continues on the item the next lane resolved for this alignment
+                const u32 nb = __shfl_down_sync(0xFFFFFFFFu, out.sh, 1);
+                if (out.want && lane < AG_WPOS) {
+                    if (out.sh != AG_NONE && nb < 32u) ag_note_succ(sv, d.ovf, out.item, out.oslot, nb);
+                    else if (out.sh == AG_NONE) atomicOr(&s_flag, 1u);   // not a clean alignment
+                    else atomicOr(&s_flag, 2u);                          // successor item index does not fit the mask
+                }
             }
         }
         __syncthreads();
     }
-    // write the tile's nodes to the pool (tile order in the pool is arbitrary; k_finalize restores position order)
-    u32 total; u32 ex = block_excl_scan(active ? nl.n : 0u, s_scan, total);
+    // ---- the tile's first node index: decoupled look-back over the tiles' node counts (every predecessor has started: tickets) ----
+    u32 total; const u32 ex = block_excl_scan(owner ? pl.n : 0u, s_scan, total);
     if (threadIdx.x == 0) {
-        u32 b = total ? atomicAdd(d.pool_count, total) : 0;
-        if (total && b + total > d.pool_cap) { *d.err = 3; b = AG_NONE; }
-        s_base = b;
+        volatile unsigned long long* st = d.tile_state;
+        unsigned long long excl = 0;
+        if (tile == 0) st[0] = ST_INC | total;
+        else {
+            st[tile] = ST_AGG | total;
+            for (u32 t = tile; t-- > 0;) {
+                unsigned long long x;
+                do { x = st[t]; } while ((x >> 62) == 0);
+                excl += x & ST_VAL;
+                if ((x >> 62) == 2) break;
+            }
+            st[tile] = ST_INC | (excl + total);
+        }
+        u32 b = (u32)excl;
+        if (excl + total > d.node_cap) { *d.err = 3; b = AG_NONE; }
+        s_base = b; s_total = (u32)(excl + total);
+        if (s_flag) d.tile_flag[tile] = s_flag;
+        if (tile == d.n_tiles - 1) *d.n_nodes_out = (u32)(excl + total);
     }
     __syncthreads();
-    if (!active) return;
-    d.pos_cnt[q] = nl.n;
-    if (s_base == AG_NONE) { d.pos_pool[q] = 0; return; }
-    u32 w = s_base + ex;
-    d.pos_pool[q] = w;
-    u32 nloc = nl.n < NODE_SCAP ? nl.n : NODE_SCAP;
-    for (u32 i = 0; i < nloc; i++) d.pool[w++] = nl.get(i);
-    if (nl.n > NODE_SCAP) for (u32 o = nl.ovf_head; o != AG_NONE; o = d.ovf.next[o]) d.pool[w++] = d.ovf.node[o];
-}
-
-// ---------------------------------------------------------------------------------------------------------------------------
-// k_finalize: position-ordered final table
-// ---------------------------------------------------------------------------------------------------------------------------
-__global__ void k_finalize(DevView d) {
-    u32 q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= d.n_ref) return;
-    u32 n = d.pos_cnt[q];
-    if (!n) return;
-    u32 src = d.pos_pool[q], dst = d.pos_node[q];
-    char refb = (char)d.ref[q];
-    for (u32 i = 0; i < n; i++) {
-        ag_nodeb b = d.pool[src + i];
-        ag_nodem m; m.cid = b.cid; m.coff = b.coff; m.cid0 = b.cid0; m.coff0 = b.coff0; m.moff = b.moff;
-        d.node_m[dst + i] = m;
-        ag_nodew w; w.succ0 = w.succ1 = AG_NONE; w.moff = b.moff;
-        u32 misc = (u32)(unsigned char)ag_consensus(b.cnt, refb);
-        if (b.cid == AG_NONE && (int)b.cov < d.coverage) misc |= AG_NW_FILTERED | AG_NW_TRAV;  // AG:1912-1915
-        if (b.coff != AG_NONE) misc |= AG_NW_HASCONTIG;                           // AG:2004
-        w.misc = misc;
-        d.node_w[dst + i] = w;
-        d.node_sref[2 * (size_t)(dst + i)] = b.sread; d.node_sref[2 * (size_t)(dst + i) + 1] = b.soff_len;
-        d.node_pos[dst + i] = q;
+    if (tile == d.n_tiles - 1)  // CSR tail: the contig-insertion positions behind the unit hold no nodes
+        for (u32 p = d.n_ref + threadIdx.x; p <= d.n_pos; p += AG_TILE) d.pos_node[p] = s_total;
+    if (!owner) return;
+    if (s_base == AG_NONE) { d.pos_node[q] = 0; return; }
+    u32 v = s_base + ex;
+    d.pos_node[q] = v;
+    if (!pl.n) return;
+    const char refb = (char)d.ref[q];
+    if (ca.cid != AG_CM_MANY) {
+        const u32 nloc = pl.n < (u32)NODE_SCAP ? pl.n : (u32)NODE_SCAP;
+        for (u32 i = 0; i < nloc; i++, v++) {
+            u32 cnt[5];
+            for (u32 j = 0; j < 5; j++) cnt[j] = sv.f(AG_F_CNT + j, i);
+            emit_node(d, v, q, refb, ca.cid, ca.coff, sv.f(AG_F_CID0, i), sv.f(AG_F_COFF0, i), sv.f(AG_F_MOFF, i), sv.f(AG_F_COV, i), cnt, sv.f(AG_F_SREAD, i), sv.f(AG_F_SL, i),
+                      sv.f(AG_F_SUCC, i));
+        }
+    }
+    for (u32 o = pl.ovf_head; o != AG_NONE; o = d.ovf.next[o], v++) {
+        const ag_nodeb b = d.ovf.node[o];
+        emit_node(d, v, q, refb, b.cid, b.coff, b.cid0, b.coff0, b.moff, b.cov, b.cnt, b.sread, b.soff_len, b.succ);
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
-// k_edges: same sweep as k_nodes, now against the FINAL table: for every call starting at q resolve the candidates on both
-// sides to their first-compatible nodes and add the edge once  (AG:1590-1623)
+// k_succ: successor-item bits -> successor node indices, subject to the contig-consistency predicate of AG:1600-1615
+// ---------------------------------------------------------------------------------------------------------------------------
+__global__ void k_succ(DevView d, u32 n_nodes) {
+    const u32 v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_nodes) return;
+    ag_nodew w = d.node_w[v];
+    u32 mask = w.succ0, head = AG_NONE;
+    w.succ0 = AG_NONE;
+    if (mask) {
+        const u32 b1 = d.pos_node[d.node_pos[v] + 1];
+        const ag_nodec x = d.node_c[v];
+        while (mask) {
+            const u32 t = b1 + (u32)__ffs((int)mask) - 1;
+            mask &= mask - 1;
+            if (!ag_edge_ok_c(x, d.node_c[t], d.iv)) continue;
+            if (w.succ0 == AG_NONE) w.succ0 = t;
+            else if (w.succ1 == AG_NONE) w.succ1 = t;
+            else {
+                const u32 o = atomicAdd(d.eovf_count, 1u);
+                if (o >= d.eovf_cap) { *d.err = 4; break; }
+                d.eovf_target[o] = t; d.eovf_next[o] = head; head = o;
+                w.misc |= AG_NW_OVF;
+            }
+        }
+    }
+    if (head != AG_NONE) d.eovf_head[v] = head;
+    d.node_w[v] = w;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// k_edges: generic edge sweep over the tiles k_build flagged, against the FINAL table: for every call starting at q resolve the
+// candidates on both sides to their first-compatible nodes and add the edge once  (AG:1590-1623)
 // ---------------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void add_edge(const DevView& d, u32 v, u32 tgt) {
     ag_nodew* w = &d.node_w[v];
@@ -373,30 +429,43 @@ __device__ __forceinline__ void add_edge(const DevView& d, u32 v, u32 tgt) {
     w->misc |= AG_NW_OVF;
 }
 
+// one candidate when both sides have at most one contiMer (the common case), else the reference's nested enumeration
+template <class F> __device__ __forceinline__ void for_candidates_fast(const DevView& d, u32 q, const ag_cm1& ca, u32 mate, F f) {
+    ag_cm1 cb; cb.cid = cb.coff = AG_NONE;
+    if (mate != AG_NONE) cb = d.cm1[mate];
+    if (ca.cid != AG_CM_MANY && cb.cid != AG_CM_MANY) {
+        ag_nodem c; c.cid = ca.cid; c.coff = ca.coff; c.cid0 = cb.cid; c.coff0 = cb.coff; c.moff = mate;
+        f(c);
+    } else ag_for_candidates(d.cmt, q, mate, f);
+}
+
 __global__ void __launch_bounds__(AG_TILE, AG_EDGES_MINB) k_edges(DevView d) {
     __shared__ ag_fast s_f[NCHUNK];
     __shared__ u32 s_idx[NCHUNK];
-    const u32 tile = blockIdx.x, q = tile * AG_TILE + threadIdx.x, lane = threadIdx.x & 31;
-    const u32 wq0 = tile * AG_TILE + (threadIdx.x & ~31u);
+    const u32 tile = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 tflag = d.tile_flag[tile];
+    if (!tflag) return;
+    const bool all = (tflag & 2u) != 0;                   // else: only the alignments that are not clean
+    const u32 wq0 = tile * AG_TPOS + warp * AG_WPOS, q = wq0 + lane;
     u32 nb0 = 0, nn0 = 0;
-    if (q < d.n_ref) { nb0 = d.pos_node[q]; nn0 = d.pos_node[q + 1] - nb0; }
+    if (q < d.n_ref && lane < AG_WPOS) { nb0 = d.pos_node[q]; nn0 = d.pos_node[q + 1] - nb0; }
     const bool active = nn0 != 0;
     ag_cm1 ca; ca.cid = ca.coff = AG_NONE;
     ag_cm1 ca1 = ca;
-    if (active) { ca = d.cm1[q]; ca1 = d.cm1[q + 1]; }  // q + 1 <= n_ref < n_pos + 1 entries... guarded below
+    if (active) { ca = d.cm1[q]; ca1 = d.cm1[q + 1]; }
     u32 last_v = AG_NONE, last_t = AG_NONE;               // the previous edge: most touches repeat it
     const u32 kb = d.tile_start[tile], ke = d.tile_start[tile + 1];
     for (u32 c0 = kb; c0 < ke; c0 += NCHUNK) {
         const u32 cn = min((u32)NCHUNK, ke - c0);
         if (threadIdx.x < cn) {
-            u32 idx = d.vals[c0 + threadIdx.x];
+            const u32 idx = d.vals[c0 + threadIdx.x];
             s_idx[threadIdx.x] = idx;
-            s_f[threadIdx.x] = ag_fast_prep(d.alnp[idx], d.lo[idx], d.span[idx]);
+            s_f[threadIdx.x] = d.fast[idx];
         }
         __syncthreads();
         for (u32 r0 = 0; r0 < cn; r0 += 32) {
             bool ov = false;
-            if (r0 + lane < cn) { u32 lo = s_f[r0 + lane].lo; ov = lo <= wq0 + 31 && lo + s_f[r0 + lane].span >= wq0; }
+            if (r0 + lane < cn) { const u32 lo = s_f[r0 + lane].lo; ov = lo <= wq0 + 30 && lo + s_f[r0 + lane].span >= wq0 && (all || !(s_f[r0 + lane].simple & AG_FAST_CLEAN)); }
             u32 mask = __ballot_sync(0xFFFFFFFFu, ov);
             while (mask) {
                 const u32 a = r0 + (u32)__ffs((int)mask) - 1;
@@ -409,14 +478,14 @@ __global__ void __launch_bounds__(AG_TILE, AG_EDGES_MINB) k_edges(DevView d) {
                 const u32 nb1 = d.pos_node[t.npos], nn1 = d.pos_node[t.npos + 1] - nb1;
                 const ag_cm1 cn1 = (t.npos == q + 1) ? ca1 : d.cm1[t.npos];
                 for_candidates_fast(d, q, ca, t.mate, [&](const ag_nodem& c) {
-                    u32 ci = ag_first_compatible(d.node_m + nb0, nn0, c, d.iv);
+                    const u32 ci = ag_first_compatible(d.node_c, d.node_w, nb0, nn0, c, d.iv);
                     if (ci == AG_NONE) return;
-                    const ag_nodem x = d.node_m[nb0 + ci];
+                    const ag_nodec x = d.node_c[nb0 + ci];
                     for_candidates_fast(d, t.npos, cn1, t.nmate, [&](const ag_nodem& c2) {
-                        u32 ni = ag_first_compatible(d.node_m + nb1, nn1, c2, d.iv);
+                        const u32 ni = ag_first_compatible(d.node_c, d.node_w, nb1, nn1, c2, d.iv);
                         if (ni == AG_NONE) return;
                         if (nb0 + ci == last_v && nb1 + ni == last_t) return;
-                        if (ag_edge_ok(x, d.node_m[nb1 + ni], d.iv)) add_edge(d, nb0 + ci, nb1 + ni);
+                        if (ag_edge_ok_c(x, d.node_c[nb1 + ni], d.iv)) add_edge(d, nb0 + ci, nb1 + ni);
                         last_v = nb0 + ci; last_t = nb1 + ni;
                     });
                 });
@@ -691,7 +760,7 @@ __global__ void k_occupancy(DevView d, unsigned char* bits) {
         u32 p = b * 8 + j;
         if (p >= d.n_pos) break;
         bool occ = d.cmt.start[p + 1] > d.cmt.start[p];
-        if (p < d.n_ref && d.pos_cnt[p]) occ = true;
+        if (p < d.n_ref && d.pos_node[p + 1] > d.pos_node[p]) occ = true;
         if (occ) x |= (unsigned char)(1u << j);
     }
     bits[b] = x;
@@ -714,19 +783,20 @@ struct AgDevice::Impl {
     DBuf<unsigned char> ref, chain_base; DBuf<u32> cm_start, chain_pos; DBuf<ag_cm> cm; DBuf<ag_aln> aln; DBuf<ag_seg> ext;
     u32 n_ref = 0, n_pos = 0, n_cm = 0, n_aln = 0;
     // build products
-    DBuf<ag_alnp> alnp; DBuf<u32> lo, span, ntiles, key_off, keys, vals, keys2, vals2, hist, tile_cnt, tile_start;
-    DBuf<ag_nodeb> pool, ovf_node; DBuf<u32> ovf_next, counters; DBuf<int> err;
-    DBuf<u32> pos_cnt, pos_pool, pos_node;
-    DBuf<ag_nodem> node_m; DBuf<ag_nodew> node_w; DBuf<u32> node_sref, node_pos;
+    DBuf<ag_alnp> alnp; DBuf<ag_fast> fast; DBuf<u32> ntiles, key_off, keys, vals, keys2, vals2, hist, tile_cnt, tile_start, tile_flag, many, many_prefix;
+    DBuf<unsigned long long> tile_state;
+    DBuf<ag_nodeb> ovf_node; DBuf<u32> ovf_next, counters; DBuf<int> err;
+    DBuf<u32> pos_node;
+    DBuf<ag_nodec> node_c; DBuf<ag_nodew> node_w; DBuf<u32> node_sref, node_pos, node_cc;
     DBuf<u32> eovf_head, eovf_target, eovf_next;
     DBuf<u32> walk_next, parent, cmin, cmax; DBuf<ag_walk> walks, walks2; DBuf<ag_cm1> cm1; DBuf<MatItem> mat_chains, mat_detours; u32 n_cand = 0; DBuf<unsigned char> pos_term; DBuf<u32> indeg, fnext, fprev, msuf, mnode, cand_rank, cand_node, cand_label; DBuf<ag_chain> chain_a, chain_b; DBuf<int> changed;
     DBuf<unsigned char> out_bases, occ; DBuf<u32> sel_start, sel_tails; DBuf<u64> sel_off;
     PinnedBuf h_walks, h_bases, h_occ;
     Scanner scanner;
     u32 n_tiles = 0, n_keys = 0, n_nodes = 0;
-    u32 pool_cap = 0, ovf_cap = 0, eovf_cap = 0, walk_cap = 0;
+    u32 node_cap = 0, ovf_cap = 0, eovf_cap = 0, walk_cap = 0;
     DevView view{};
-    // counters layout: [0] pool_count, [1] ovf_count, [2] eovf_count, [3] walk_count
+    // counters layout: [0] n_nodes, [1] ovf_count, [2] eovf_count, [3] walk_count, [4,5] materialise items, [6] tile ticket
 };
 
 AgDevice::AgDevice(int device) : m_(new Impl), dev_(device) {
@@ -745,13 +815,13 @@ AgDevice::~AgDevice() {
     if (m.reads_owned) { m.r_bases.release(); m.r_nmask.release(); m.r_len.release(); }
     DBuf<unsigned char>* b8[] = {&m.ref, &m.chain_base, &m.out_bases, &m.occ};
     for (auto* b : b8) b->release();
-    DBuf<u32>* b32[] = {&m.cm_start, &m.chain_pos, &m.lo, &m.span, &m.ntiles, &m.key_off, &m.keys, &m.vals, &m.keys2, &m.vals2, &m.hist, &m.tile_cnt,
-                        &m.tile_start, &m.ovf_next, &m.counters, &m.pos_cnt, &m.pos_pool, &m.pos_node, &m.node_sref, &m.node_pos, &m.eovf_head,
+    DBuf<u32>* b32[] = {&m.cm_start, &m.chain_pos, &m.ntiles, &m.key_off, &m.keys, &m.vals, &m.keys2, &m.vals2, &m.hist, &m.tile_cnt,
+                        &m.tile_start, &m.tile_flag, &m.many, &m.many_prefix, &m.ovf_next, &m.counters, &m.pos_node, &m.node_sref, &m.node_pos, &m.node_cc, &m.eovf_head,
                         &m.eovf_target, &m.eovf_next, &m.walk_next, &m.parent, &m.cmin, &m.cmax, &m.sel_start, &m.sel_tails};
     for (auto* b : b32) b->release();
     for (int i = 0; i < 4; i++) m.scanner.lvl[i].release();
-    m.cm.release(); m.aln.release(); m.ext.release(); m.alnp.release(); m.pool.release(); m.ovf_node.release(); m.err.release();
-    m.node_m.release(); m.node_w.release(); m.walks.release(); m.walks2.release(); m.cm1.release(); m.mat_chains.release(); m.mat_detours.release(); m.pos_term.release(); m.cand_rank.release(); m.cand_node.release(); m.cand_label.release(); m.fprev.release(); m.msuf.release(); m.mnode.release(); m.indeg.release(); m.fnext.release(); m.chain_a.release(); m.chain_b.release(); m.changed.release(); m.sel_off.release();
+    m.cm.release(); m.aln.release(); m.ext.release(); m.alnp.release(); m.fast.release(); m.tile_state.release(); m.ovf_node.release(); m.err.release();
+    m.node_c.release(); m.node_w.release(); m.walks.release(); m.walks2.release(); m.cm1.release(); m.mat_chains.release(); m.mat_detours.release(); m.pos_term.release(); m.cand_rank.release(); m.cand_node.release(); m.cand_label.release(); m.fprev.release(); m.msuf.release(); m.mnode.release(); m.indeg.release(); m.fnext.release(); m.chain_a.release(); m.chain_b.release(); m.changed.release(); m.sel_off.release();
     m.h_walks.release(); m.h_bases.release(); m.h_occ.release();
     if (m.st) cudaStreamDestroy(m.st);
     delete m_;
@@ -838,27 +908,29 @@ void AgDevice::build() {
     Impl& m = *m_;
     cudaStream_t st = m.st;
     const u32 nA = m.n_aln, n_ref = m.n_ref, n_pos = m.n_pos;
-    m.n_tiles = (n_ref + AG_TILE - 1) / AG_TILE;
+    m.n_tiles = (n_ref + AG_TPOS - 1) / AG_TPOS;
     DevView& d = m.view;
     d = DevView{};
     d.reads = m.reads; d.ref = m.ref.p; d.n_ref = n_ref; d.n_pos = n_pos;
     d.cmt.start = m.cm_start.p; d.cmt.cm = m.cm.p; d.chain_pos = m.chain_pos.p; d.chain_base = m.chain_base.p;
     d.aln = m.aln.p; d.n_aln = nA; d.ext = m.ext.p; d.k = k_; d.iv = iv_; d.coverage = cov_;
-    m.alnp.ensure(nA + 1); m.lo.ensure(nA + 1); m.span.ensure(nA + 1); m.ntiles.ensure(nA + 1); m.key_off.ensure((size_t)nA + 2);
-    m.tile_cnt.ensure(m.n_tiles + 2); m.tile_start.ensure(m.n_tiles + 2);
-    m.pos_cnt.ensure(n_pos + 2); m.pos_pool.ensure(n_pos + 2); m.pos_node.ensure((size_t)n_pos + 2);
-    d.alnp = m.alnp.p; d.lo = m.lo.p; d.span = m.span.p; d.ntiles = m.ntiles.p; d.key_off = m.key_off.p;
-    d.tile_cnt = m.tile_cnt.p; d.tile_start = m.tile_start.p; d.n_tiles = m.n_tiles;
-    d.pos_cnt = m.pos_cnt.p; d.pos_pool = m.pos_pool.p; d.pos_node = m.pos_node.p;
+    m.alnp.ensure(nA + 1); m.fast.ensure(nA + 1); m.ntiles.ensure(nA + 1); m.key_off.ensure((size_t)nA + 2);
+    m.tile_cnt.ensure(m.n_tiles + 2); m.tile_start.ensure(m.n_tiles + 2); m.tile_flag.ensure(m.n_tiles + 2); m.tile_state.ensure(m.n_tiles + 2);
+    m.pos_node.ensure((size_t)n_pos + 2);
+    d.alnp = m.alnp.p; d.fast = m.fast.p; d.ntiles = m.ntiles.p; d.key_off = m.key_off.p;
+    d.tile_cnt = m.tile_cnt.p; d.tile_start = m.tile_start.p; d.n_tiles = m.n_tiles; d.tile_flag = m.tile_flag.p; d.tile_state = m.tile_state.p;
+    d.pos_node = m.pos_node.p;
     d.err = m.err.p;
     CK(cudaMemsetAsync(m.err.p, 0, sizeof(int), st));
     CK(cudaMemsetAsync(m.counters.p, 0, 8 * sizeof(u32), st));
     CK(cudaMemsetAsync(m.tile_cnt.p, 0, (m.n_tiles + 1) * sizeof(u32), st));
-    CK(cudaMemsetAsync(m.pos_cnt.p, 0, ((size_t)n_pos + 1) * sizeof(u32), st));
+    CK(cudaMemsetAsync(m.pos_node.p, 0, ((size_t)n_pos + 1) * sizeof(u32), st));
 
     m.cm1.ensure((size_t)n_pos + 2); d.cm1 = m.cm1.p; m.pos_term.ensure((size_t)n_pos + 2); d.pos_term = m.pos_term.p;
-    if (n_pos) { k_cm1<<<(n_pos + 255) / 256, 256, 0, st>>>(d, m.cm1.p, m.pos_term.p); launches_++; }
-    if (!attr_done_) { CK(cudaFuncSetAttribute(k_nodes, cudaFuncAttributeMaxDynamicSharedMemorySize, NODES_SMEM + NCHUNK_N * READ_WORDS_MAX * 4)); attr_done_ = true; }  // per device
+    m.many.ensure((size_t)n_pos + 2); m.many_prefix.ensure((size_t)n_pos + 2); d.many_prefix = m.many_prefix.p;
+    if (n_pos) { k_cm1<<<(n_pos + 255) / 256, 256, 0, st>>>(d, m.cm1.p, m.pos_term.p, m.many.p); launches_++; }
+    m.scanner.run(m.many.p, m.many_prefix.p, n_pos, st);
+    if (!attr_done_) { CK(cudaFuncSetAttribute(k_build, cudaFuncAttributeMaxDynamicSharedMemorySize, NODES_SMEM + NCHUNK_N * READ_WORDS_MAX * 4)); attr_done_ = true; }  // per device
     d.rw = (m.reads.stride2 + m.reads.stridem <= (u32)READ_WORDS_MAX) ? m.reads.stride2 + m.reads.stridem : 0;
 
     // ---- prep + keys ------------------------------------------------------------------------------------------------
@@ -895,58 +967,50 @@ void AgDevice::build() {
         }
         t_.sort += tm.stop();
     }
-    // ---- nodes ----------------------------------------------------------------------------------------------------------------
+    // ---- nodes (+ the common-case edges as successor-item bits) -------------------------------------------------------------------
+    u32 nn = 0;
     {
         Timer tm(st);
-        if (!m.pool_cap) m.pool_cap = std::max<u32>(1u << 20, 3 * n_ref + (1u << 16));
+        if (!m.node_cap) m.node_cap = std::max<u32>(1u << 20, 3 * n_ref + (1u << 16));
         for (;;) {
-            m.pool.ensure(m.pool_cap);
+            m.node_c.ensure((size_t)m.node_cap + 1); m.node_w.ensure((size_t)m.node_cap + 1); m.node_sref.ensure(2 * (size_t)m.node_cap + 2); m.node_pos.ensure((size_t)m.node_cap + 1);
+            if (keep_counts_) m.node_cc.ensure(6 * (size_t)m.node_cap + 6);
             if (!m.ovf_cap) m.ovf_cap = std::max<u32>(1u << 18, n_ref / 8);
             m.ovf_node.ensure(m.ovf_cap); m.ovf_next.ensure(m.ovf_cap);
-            d.pool = m.pool.p; d.pool_count = m.counters.p + 0; d.pool_cap = m.pool_cap;
+            d.node_c = m.node_c.p; d.node_w = m.node_w.p; d.node_sref = m.node_sref.p; d.node_pos = m.node_pos.p; d.node_cc = keep_counts_ ? m.node_cc.p : nullptr;
+            d.node_cap = m.node_cap; d.n_nodes_out = m.counters.p + 0; d.ticket = m.counters.p + 6;
             d.ovf.node = m.ovf_node.p; d.ovf.next = m.ovf_next.p; d.ovf.count = m.counters.p + 1; d.ovf.cap = m.ovf_cap; d.ovf.err = m.err.p;
-            if (m.n_tiles) { k_nodes<<<m.n_tiles, AG_TILE, NODES_SMEM + NCHUNK_N * d.rw * 4, st>>>(d); launches_++; }
+            CK(cudaMemsetAsync(m.tile_state.p, 0, ((size_t)m.n_tiles + 1) * sizeof(unsigned long long), st));
+            CK(cudaMemsetAsync(m.tile_flag.p, 0, ((size_t)m.n_tiles + 1) * sizeof(u32), st));
+            if (m.n_tiles) { k_build<<<m.n_tiles, AG_TILE, NODES_SMEM + NCHUNK_N * d.rw * 4, st>>>(d); launches_++; }
             int err = 0;
             CK(cudaMemcpyAsync(&err, m.err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(&nn, m.counters.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             if (err == 0) break;
-            if (err == 3) {  // node pool too small: grow and redo the sweep
-                m.pool_cap = m.pool_cap * 2;
-                CK(cudaMemsetAsync(m.err.p, 0, sizeof(int), st));
-                CK(cudaMemsetAsync(m.counters.p, 0, 8 * sizeof(u32), st));
-                continue;
-            }
             if (err == 2) throw AgError{"BOWTIE ALIGNMENT ERROR: alignment outside the unit"};
-            if (err == 1 && m.ovf_cap < (1u << 30)) {  // overflow pool (nodes beyond the shared-memory slots) too small: grow and redo the sweep
-                m.ovf_cap *= 4;
-                CK(cudaMemsetAsync(m.err.p, 0, sizeof(int), st));
-                CK(cudaMemsetAsync(m.counters.p, 0, 8 * sizeof(u32), st));
-                continue;
-            }
-            throw AgError{"node overflow pool exhausted"};
+            if (err == 3 && m.node_cap < (1u << 31)) m.node_cap = m.node_cap * 2;           // node table too small: grow and redo the sweep
+            else if (err == 1 && m.ovf_cap < (1u << 30)) m.ovf_cap *= 4;                    // overflow pool (nodes beyond the shared-memory slots) too small
+            else throw AgError{"node table exhausted"};
+            CK(cudaMemsetAsync(m.err.p, 0, sizeof(int), st));
+            CK(cudaMemsetAsync(m.counters.p, 0, 8 * sizeof(u32), st));
         }
         t_.nodes += tm.stop();
     }
-    // ---- finalize -------------------------------------------------------------------------------------------------------------
+    m.n_nodes = nn; t_.n_nodes = nn; t_.n_keys = m.n_keys; t_.n_tiles = m.n_tiles;
+    // ---- successor bits -> successor indices --------------------------------------------------------------------------------------
     {
         Timer tm(st);
-        m.scanner.run(m.pos_cnt.p, m.pos_node.p, n_pos, st);
-        u32 nn = 0;
-        CK(cudaMemcpyAsync(&nn, m.pos_node.p + n_pos, sizeof(u32), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        m.n_nodes = nn; t_.n_nodes = nn; t_.n_keys = m.n_keys; t_.n_tiles = m.n_tiles;
-        m.node_m.ensure(nn + 1); m.node_w.ensure(nn + 1); m.node_sref.ensure(2 * (size_t)nn + 2); m.node_pos.ensure(nn + 1);
         m.eovf_head.ensure(nn + 1);
         m.eovf_cap = std::max<u32>(1u << 18, nn / 8); m.eovf_target.ensure(m.eovf_cap); m.eovf_next.ensure(m.eovf_cap);
-        d.node_m = m.node_m.p; d.node_w = m.node_w.p; d.node_sref = m.node_sref.p; d.node_pos = m.node_pos.p;
         d.eovf_head = m.eovf_head.p; d.eovf_target = m.eovf_target.p; d.eovf_next = m.eovf_next.p; d.eovf_count = m.counters.p + 2; d.eovf_cap = m.eovf_cap;
-        if (n_ref) { k_finalize<<<(n_ref + 255) / 256, 256, 0, st>>>(d); launches_++; }
+        if (nn) { k_succ<<<(nn + 255) / 256, 256, 0, st>>>(d, nn); launches_++; }
         t_.finalize += tm.stop();
     }
-    // ---- edges ----------------------------------------------------------------------------------------------------------------
+    // ---- generic edge sweep over the flagged tiles ----------------------------------------------------------------------------------
     {
         Timer tm(st);
-        if (m.n_tiles) { k_edges<<<m.n_tiles, AG_TILE, 0, st>>>(d); launches_++; }
+        if (m.n_tiles && nn) { k_edges<<<m.n_tiles, AG_TILE, 0, st>>>(d); launches_++; }
         int err = 0; u32 cnt[4];
         CK(cudaMemcpyAsync(&err, m.err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(cnt, m.counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, st));
@@ -1137,37 +1201,39 @@ void AgDevice::occupancy(std::vector<unsigned char>& bits) {
 void AgDevice::dump_nodes(AgNodeDump& dd) {
     CK(cudaSetDevice(dev_));
     Impl& m = *m_; cudaStream_t st = m.st; u32 nn = m.n_nodes, n_pos = m.n_pos;
-    std::vector<u32> pos_cnt(n_pos + 1), pos_pool(n_pos + 1), pos_node(n_pos + 1);
-    CK(cudaMemcpyAsync(pos_cnt.data(), m.pos_cnt.p, (size_t)n_pos * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(pos_pool.data(), m.pos_pool.p, (size_t)n_pos * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(pos_node.data(), m.pos_node.p, ((size_t)n_pos + 1) * 4, cudaMemcpyDeviceToHost, st));
+    if (!keep_counts_ || !m.view.node_cc) throw AgError{"node dump needs the per-node counters: set option keep_counts before building"};
+    std::vector<u32> pos_node((size_t)n_pos + 1), cc(6 * (size_t)nn), sref(2 * (size_t)nn), npos(nn);
+    std::vector<ag_nodec> nc(nn);
+    std::vector<ag_nodew> nw(nn);
     u32 cnt[4];
     CK(cudaMemcpyAsync(cnt, m.counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(pos_node.data(), m.pos_node.p, ((size_t)n_pos + 1) * 4, cudaMemcpyDeviceToHost, st));
+    if (nn) {
+        CK(cudaMemcpyAsync(cc.data(), m.node_cc.p, (size_t)nn * 24, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(sref.data(), m.node_sref.p, (size_t)nn * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(npos.data(), m.node_pos.p, (size_t)nn * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(nc.data(), m.node_c.p, (size_t)nn * sizeof(ag_nodec), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(nw.data(), m.node_w.p, (size_t)nn * sizeof(ag_nodew), cudaMemcpyDeviceToHost, st));
+    }
     CK(cudaStreamSynchronize(st));
-    std::vector<ag_nodeb> pool(cnt[0]);
-    std::vector<ag_nodew> nw(nn);
-    if (cnt[0]) CK(cudaMemcpyAsync(pool.data(), m.pool.p, (size_t)cnt[0] * sizeof(ag_nodeb), cudaMemcpyDeviceToHost, st));
-    if (nn) CK(cudaMemcpyAsync(nw.data(), m.node_w.p, (size_t)nn * sizeof(ag_nodew), cudaMemcpyDeviceToHost, st));
     std::vector<u32> eh(nn), et(cnt[2]), en(cnt[2]);
     if (nn) CK(cudaMemcpyAsync(eh.data(), m.eovf_head.p, (size_t)nn * 4, cudaMemcpyDeviceToHost, st));
     if (cnt[2]) { CK(cudaMemcpyAsync(et.data(), m.eovf_target.p, (size_t)cnt[2] * 4, cudaMemcpyDeviceToHost, st)); CK(cudaMemcpyAsync(en.data(), m.eovf_next.p, (size_t)cnt[2] * 4, cudaMemcpyDeviceToHost, st)); }
     CK(cudaStreamSynchronize(st));
     dd = AgNodeDump();
     dd.edge_start.push_back(0);
-    for (u32 q = 0; q < m.n_ref; q++)
-        for (u32 i = 0; i < pos_cnt[q]; i++) {
-            const ag_nodeb& b = pool[pos_pool[q] + i];
-            dd.pos.push_back(q); dd.item.push_back(i); dd.cov.push_back(b.cov);
-            for (int j = 0; j < 5; j++) dd.cnt.push_back(b.cnt[j]);
-            dd.cid.push_back(b.cid); dd.coff.push_back(b.coff); dd.cid0.push_back(b.cid0); dd.coff0.push_back(b.coff0); dd.moff.push_back(b.moff);
-            dd.sread.push_back(b.sread); dd.soff_len.push_back(b.soff_len);
-            u32 v = pos_node[q] + i;
-            std::vector<u32> e;
-            if (nw[v].succ0 != AG_NONE) e.push_back(nw[v].succ0);
-            if (nw[v].succ1 != AG_NONE) e.push_back(nw[v].succ1);
-            if (nw[v].misc & AG_NW_OVF) for (u32 o = eh[v]; o != AG_NONE; o = en[o]) e.push_back(et[o]);
-            std::sort(e.begin(), e.end());
-            for (u32 x : e) dd.edge_target.push_back(x);
-            dd.edge_start.push_back((u32)dd.edge_target.size());
-        }
+    for (u32 v = 0; v < nn; v++) {
+        const u32 q = npos[v];
+        dd.pos.push_back(q); dd.item.push_back(v - pos_node[q]); dd.cov.push_back(cc[6 * (size_t)v]);
+        for (int j = 0; j < 5; j++) dd.cnt.push_back(cc[6 * (size_t)v + 1 + j]);
+        dd.cid.push_back(nc[v].cid); dd.coff.push_back(nc[v].coff); dd.cid0.push_back(nc[v].cid0); dd.coff0.push_back(nc[v].coff0); dd.moff.push_back(nw[v].moff);
+        dd.sread.push_back(sref[2 * (size_t)v]); dd.soff_len.push_back(sref[2 * (size_t)v + 1]);
+        std::vector<u32> e;
+        if (nw[v].succ0 != AG_NONE) e.push_back(nw[v].succ0);
+        if (nw[v].succ1 != AG_NONE) e.push_back(nw[v].succ1);
+        if (nw[v].misc & AG_NW_OVF) for (u32 o = eh[v]; o != AG_NONE; o = en[o]) e.push_back(et[o]);
+        std::sort(e.begin(), e.end());
+        for (u32 x : e) dd.edge_target.push_back(x);
+        dd.edge_start.push_back((u32)dd.edge_target.size());
+    }
 }

@@ -38,9 +38,11 @@ public:
     void set_reads(const u32* bases, const u32* nmask, const uint16_t* len, u64 n_pairs, u32 stride2, u32 stridem, bool on_device);
     void copy_reads_to_host(u32* bases, u32* nmask, uint16_t* len);
     void set_params(int k, int iv, int coverage) { k_ = k; iv_ = iv; cov_ = coverage; }
+    // keep coverage + base counters per node after the build (24 B per node; only the node dump of the tests needs them)
+    void set_keep_counts(bool on) { keep_counts_ = on; }
     // upload one unit's inputs (H2D, timed)
     void load_unit(const AgUnitInput& in);
-    // the hot path: prep -> bucket -> nodes -> finalize -> edges  (all device)
+    // the hot path: prep -> bucket -> nodes (+ common-case edges) -> successor lists -> generic edges on flagged tiles  (all device)
     void build();
     // coverage filter + walk simulation; fills `walks` (unsorted on return from the device, sorted here by start node)
     void extend(std::vector<ag_walk>& walks);
@@ -69,7 +71,7 @@ private:
     u64 launches_ = 0;
     void *ev0_ = nullptr, *ev1_ = nullptr;
     std::vector<void*> pinned_;
-    bool chains_valid_ = false, attr_done_ = false;
+    bool chains_valid_ = false, attr_done_ = false, keep_counts_ = false;
     void walk_components();
     void walk_sequential();
 };

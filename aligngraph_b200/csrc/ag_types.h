@@ -9,8 +9,10 @@
 
 #ifdef __CUDACC__
 #define AG_HD __host__ __device__ __forceinline__
+#define AG_HD_COLD __host__ __device__ __noinline__  /* rare paths: kept out of line so the hot loops stay small */
 #else
 #define AG_HD inline
+#define AG_HD_COLD inline
 #endif
 
 typedef uint32_t u32;
@@ -58,6 +60,7 @@ struct ag_nodeb {
     u32 cnt[5];                        // A C G T N   (AG:1340-1351)
     u32 sread;                         // founder k-mer string: (read index << 1) | rc
     u32 soff_len;                      // offset | len<<16  (len 0 = empty string)
+    u32 succ;                          // bit j: an edge to item j of the next position was seen during the sweep
 };
 
 // final node record used by the edge sweep and the walk (position-ordered)
@@ -74,7 +77,9 @@ struct alignas(16) ag_nodew {
 #define AG_NW_STOP 0x4000u    /* sequential replay: the walk that marked this node left the chain here (follow walk_next, not fnext) */
 #define AG_NW_INTERIOR 0x2000u /* entered only through its unique live predecessor (forced link): never starts a walk */
 
-struct ag_nodem { u32 cid, coff, cid0, coff0, moff; };  // match fields of a final node
+struct ag_nodem { u32 cid, coff, cid0, coff0, moff; };  // match fields of a candidate / node (AG:1293-1312)
+// contig-side match fields of a final node, one 16-byte record (the fifth match field, chromosomeOffset0, is ag_nodew::moff)
+struct alignas(16) ag_nodec { u32 cid, coff, cid0, coff0; };
 
 // per-walk record (one per live node that starts a walk in AG:1976-1990), compacted in scan order
 struct ag_walk {

@@ -111,7 +111,9 @@ int ag_get_unit(ag_ctx* ctx, ag_unit_view* out);
 /* ---- introspection ------------------------------------------------------------------------------------------------------------------- */
 int ag_get_stats(ag_ctx* ctx, ag_stats* out);
 int ag_reset_stats(ag_ctx* ctx);
-/* node table after ag_build as text, one node per line (tests): pos item cov A C G T N cid coff cid0 coff0 mid moff [s] pos:item... */
+/* node table after ag_build as text, one node per line (tests): pos item cov A C G T N cid coff cid0 coff0 mid moff [s] pos:item...
+ * The per-node coverage / base counters are only kept when ag_keep_node_counts(ctx, 1) was called before ag_build (24 B per node). */
+int ag_keep_node_counts(ag_ctx* ctx, int on);
 int ag_dump_nodes_text(ag_ctx* ctx, const char** text, uint64_t* len);
 void* ag_cuda_stream(ag_ctx* ctx);
 /* ---- benchmark support ---------------------------------------------------------------------------------------------------------

@@ -24,5 +24,11 @@ LIVE = {
     "longcontig": dict(genome_bp=500000, coverage=40, contig_len=160000, contig_gap=3000, seed=41),
     # contigs longer than LARGE_CHUNK = 1,000,000 bp are cut into chunks (AlignGraph.cpp:3277-3293); 1.28 Mbp walks, skip rule active
     "bigchunk": dict(genome_bp=3000000, coverage=12, contig_len=1300000, contig_gap=20000, seed=51, cov=4),
+    # overlapping contig tiles: positions holding two contiMers (several candidates per touch, AlignGraph.cpp:1369-1477; nodes of such
+    # positions live in the overflow pool; every edge around them goes through the generic edge sweep)
+    "overlap": dict(genome_bp=60000, coverage=40, indel=0.002, softclip=0.2, multi=0.1, contig_len=3000, contig_gap=-1200, seed=61),
+    # very wide insert distribution at 1200x: up to 75 nodes per position, i.e. successor items beyond the 32-bit item mask of the node
+    # sweep (tiles flagged for the full generic edge sweep), long overflow chains
+    "manyitems": dict(genome_bp=16000, coverage=1200, insert_mean=5000, insert_sd=2500, contig_len=3000, seed=62, cov=3),
     "nocontigs": dict(genome_bp=30000, coverage=50, seed=7, contig_len=150, contig_gap=5000),
 }

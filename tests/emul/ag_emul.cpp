@@ -20,16 +20,17 @@ public:
     AgUnitInput in{};
     ag_reads rd{};
     // products
-    std::vector<ag_alnp> alnp; std::vector<u32> lo, span;
+    std::vector<ag_alnp> alnp; std::vector<ag_fast> fast;
     std::vector<std::vector<u32>> tiles;
     std::vector<u32> pos_node, node_pos, node_sref, eovf_head, eovf_target, eovf_next, walk_next, parent;
     std::vector<ag_nodeb> nodeb;  // final order
-    std::vector<ag_nodem> node_m; std::vector<ag_nodew> node_w; std::vector<ag_cm1> cm1;
+    std::vector<ag_nodec> node_c; std::vector<ag_nodew> node_w; std::vector<ag_cm1> cm1;
     std::vector<unsigned char> pos_term; std::vector<u32> indeg, fnext, fprev, msuf, mnode; std::vector<ag_chain> chain; bool use_chains = false;
     std::vector<ag_nodeb> ovf_node; std::vector<u32> ovf_next; u32 ovf_count = 0; int err = 0;
     u32 n_nodes = 0;
     bool fallback_used = false;
-    u32 n_live = 0, n_heads = 0, max_chain = 0;
+    u32 n_live = 0, n_heads = 0, max_chain = 0, n_flagged = 0, n_flag2 = 0, n_tiles_total = 0, n_many = 0, max_items = 0;
+    bool force_all_edges = getenv("AG_EMUL_ALL_EDGES") != nullptr;   // run the generic edge sweep on every tile (must change nothing)
 
     void set_reads(const AgReads& r) { rd.bases = r.bases.data(); rd.nmask = r.nmask.data(); rd.len = r.len.data(); rd.stride2 = r.stride2; rd.stridem = r.stridem; }
     void load_unit(const AgUnitInput& i) { in = i; }
@@ -45,92 +46,147 @@ public:
     }
     bool force_generic = getenv("AG_EMUL_FORCE_GENERIC") != nullptr;
 
-    void build() {
+    void build() {   // like AgDevice::build: grow the overflow pool and redo the sweep when it runs out
+        for (size_t cap = 1 << 18;; cap *= 4) { err = 0; if (build_once(cap)) return; if (cap > ((size_t)1 << 26)) throw AgHostError{"emul: overflow pool exhausted"}; }
+    }
+    bool build_once(size_t pool_cap) {
         const u32 nA = (u32)in.n_aln, n_ref = in.n_ref, n_pos = in.n_pos;
-        alnp.resize(nA); lo.resize(nA); span.resize(nA);
-        u32 n_tiles = (n_ref + AG_TILE - 1) / AG_TILE;
+        alnp.resize(nA); fast.resize(nA);
+        const u32 n_tiles = (n_ref + AG_TPOS - 1) / AG_TPOS;
         tiles.assign(n_tiles, {});
+        ag_cmtab ct = cmt();
+        cm1.resize((size_t)n_pos + 1);
+        std::vector<u32> many_prefix((size_t)n_pos + 1, 0);
+        for (u32 p = 0; p < n_pos; p++) { cm1[p] = ag_make_cm1(ct, p); many_prefix[p + 1] = many_prefix[p] + (cm1[p].cid == AG_CM_MANY ? 1u : 0u); }
         for (u32 i = 0; i < nA; i++) {  // k_prep + k_keys + sort
             ag_prep_out o = ag_prep(in.aln[i], in.ext, rd.len[in.aln[i].pair], (u32)k);
-            alnp[i] = o.p; lo[i] = o.lo; span[i] = o.span;
+            alnp[i] = o.p; fast[i] = ag_fast_prep(o.p, o.lo, o.span);
             if (!o.any) continue;
             if (o.lo + o.span >= n_ref) throw AgHostError{"BOWTIE ALIGNMENT ERROR"};
-            for (u32 t = o.lo / AG_TILE; t <= (o.lo + o.span) / AG_TILE; t++) tiles[t].push_back(i);
+            if (ag_fast_is_clean(fast[i], o.p, many_prefix.data())) fast[i].simple |= AG_FAST_CLEAN;
+            u32 t0, t1; ag_tile_range(o.lo, o.lo + o.span, n_tiles, t0, t1);
+            for (u32 t = t0; t <= t1; t++) tiles[t].push_back(i);
         }
-        ovf_node.assign(1 << 16, ag_nodeb{}); ovf_next.assign(1 << 16, 0); ovf_count = 0;
+        ovf_node.assign(pool_cap, ag_nodeb{}); ovf_next.assign(pool_cap, 0); ovf_count = 0;
         ag_ovfpool pool; pool.node = ovf_node.data(); pool.next = ovf_next.data(); pool.count = &ovf_count; pool.cap = (u32)ovf_node.size(); pool.err = &err;
-        ag_cmtab ct = cmt();
         pos_node.assign((size_t)n_pos + 1, 0);
         nodeb.clear();
-        cm1.resize((size_t)n_pos + 1);
-        for (u32 p = 0; p < n_pos; p++) cm1[p] = ag_make_cm1(ct, p);
-        for (u32 q = 0; q < n_ref; q++) {  // k_nodes
-            ag_nodeb loc[AG_NODE_CAP];
-            ag_nview nl; nl.init((u32*)loc, 1, 13, AG_NODE_CAP);
-            const ag_cm1 ca = cm1[q];
-            for (u32 idx : tiles[q / AG_TILE]) {
-                const ag_fast f = ag_fast_prep(alnp[idx], lo[idx], span[idx]);
-                if (q - f.lo > f.span) continue;
-                ag_touch t;
-                if (f.simple && !force_generic) t = ag_fast_touch(f, q, (u32)k);
-                else { t = ag_locate(alnp[idx], in.ext, q, (u32)k); if (!t.kind) continue; }
-                int code = -1;
-                if (t.kind == 1 && t.slen) code = rd.code(f.read, f.lsrc_len >> 16, t.soff);
-                u32 sl = t.soff | (t.slen << 16);
-                bool bump = t.kind == 1;
-                for_candidates_fast(q, ca, t.mate, [&](const ag_nodem& c) { ag_node_touch_v(nl, pool, c, bump, code, f.read, sl, iv); });
+        std::vector<unsigned char> tile_flag(n_tiles, 0);
+        // k_build: tile by tile, warp by warp; a warp's 32 lanes (31 owned positions + the halo) see every tile alignment together,
+        // the successor item travels from lane + 1 to lane (the kernel's shuffle)
+        for (u32 tile = 0; tile < n_tiles; tile++)
+            for (u32 warp = 0; warp < 8; warp++) {
+                const u32 wq0 = tile * AG_TPOS + warp * AG_WPOS;
+                u32 slot_mem[32][AG_NF * AG_NODE_SCAP];
+                ag_slots sv[32]; ag_plist pl[32]; ag_cm1 ca[32];
+                for (u32 l = 0; l < 32; l++) {
+                    sv[l].base = slot_mem[l]; sv[l].fstride = AG_NODE_SCAP; sv[l].nstride = 1;
+                    pl[l].n = 0; pl[l].ovf_head = pl[l].ovf_tail = AG_NONE;
+                    ca[l].cid = ca[l].coff = AG_NONE;
+                    if (wq0 + l < n_ref) ca[l] = cm1[wq0 + l];
+                }
+                for (u32 idx : tiles[tile]) {
+                    const ag_fast f = fast[idx];
+                    if (!(f.lo <= wq0 + 31 && f.lo + f.span >= wq0)) continue;
+                    ag_lane_out out[32];
+                    for (u32 l = 0; l < 32; l++) {
+                        const u32 q = wq0 + l;
+                        out[l].sh = AG_NONE; out[l].item = 0; out[l].oslot = AG_NONE; out[l].want = false;
+                        if (q < n_ref && q - f.lo <= f.span) {
+                            auto codef = [&](u32 soff) -> int { return rd.code(f.read, f.lsrc_len >> 16, soff); };
+                            ag_lane_touch(out[l], pl[l], sv[l], pool, ct, cm1.data(), ca[l], f, &alnp[idx], in.ext, q, (u32)k, iv, force_generic, codef);
+                        }
+                    }
+                    for (u32 l = 0; l < AG_WPOS; l++) {
+                        if (!out[l].want) continue;
+                        const u32 nb = out[l + 1].sh;
+                        if (out[l].sh != AG_NONE && nb < 32u) ag_note_succ(sv[l], pool, out[l].item, out[l].oslot, nb);
+                        else tile_flag[tile] |= (out[l].sh == AG_NONE) ? 1 : 2;
+                    }
+                }
+                if (err) return false;
+                for (u32 l = 0; l < AG_WPOS; l++) {  // write-out in position order (the kernel's look-back gives the same indices)
+                    const u32 q = wq0 + l;
+                    if (q >= n_ref) break;
+                    pos_node[q] = (u32)nodeb.size();
+                    if (ca[l].cid != AG_CM_MANY) {
+                        const u32 nloc = pl[l].n < (u32)AG_NODE_SCAP ? pl[l].n : (u32)AG_NODE_SCAP;
+                        for (u32 i = 0; i < nloc; i++) {
+                            ag_nodeb b; b.cid = ca[l].cid; b.coff = ca[l].coff; b.cid0 = sv[l].f(AG_F_CID0, i); b.coff0 = sv[l].f(AG_F_COFF0, i); b.moff = sv[l].f(AG_F_MOFF, i);
+                            b.cov = sv[l].f(AG_F_COV, i);
+                            for (u32 j = 0; j < 5; j++) b.cnt[j] = sv[l].f(AG_F_CNT + j, i);
+                            b.sread = sv[l].f(AG_F_SREAD, i); b.soff_len = sv[l].f(AG_F_SL, i); b.succ = sv[l].f(AG_F_SUCC, i);
+                            nodeb.push_back(b);
+                        }
+                    }
+                    for (u32 o = pl[l].ovf_head; o != AG_NONE; o = ovf_next[o]) nodeb.push_back(ovf_node[o]);
+                    if ((u32)nodeb.size() - pos_node[q] != pl[l].n) throw AgHostError{"emul: node list length mismatch"};
+                }
             }
-            if (err) throw AgHostError{"emul: overflow pool exhausted"};
-            pos_node[q] = (u32)nodeb.size();
-            u32 nloc = nl.n < AG_NODE_CAP ? nl.n : AG_NODE_CAP;
-            for (u32 i = 0; i < nloc; i++) nodeb.push_back(nl.get(i));
-            if (nl.n > AG_NODE_CAP) for (u32 o = nl.ovf_head; o != AG_NONE; o = ovf_next[o]) nodeb.push_back(ovf_node[o]);
-        }
         for (u32 q = n_ref; q <= n_pos; q++) pos_node[q] = (u32)nodeb.size();
         n_nodes = (u32)nodeb.size();
-        // k_finalize
-        node_m.resize(n_nodes); node_w.resize(n_nodes); node_sref.resize(2 * (size_t)n_nodes); node_pos.resize(n_nodes);
+        n_many = many_prefix[n_pos]; max_items = 0; n_flag2 = 0;
+        for (u32 q = 0; q < n_ref; q++) max_items = std::max(max_items, pos_node[q + 1] - pos_node[q]);
+        for (u32 t = 0; t < n_tiles; t++) if (tile_flag[t] & 2) n_flag2++;
+        // emit_node
+        node_c.resize(n_nodes); node_w.resize(n_nodes); node_sref.resize(2 * (size_t)n_nodes); node_pos.resize(n_nodes);
         eovf_head.assign(n_nodes, AG_NONE); eovf_target.clear(); eovf_next.clear();
         for (u32 q = 0; q < n_ref; q++)
             for (u32 v = pos_node[q]; v < pos_node[q + 1]; v++) {
                 const ag_nodeb& b = nodeb[v];
-                ag_nodem m; m.cid = b.cid; m.coff = b.coff; m.cid0 = b.cid0; m.coff0 = b.coff0; m.moff = b.moff; node_m[v] = m;
+                ag_nodec c; c.cid = b.cid; c.coff = b.coff; c.cid0 = b.cid0; c.coff0 = b.coff0; node_c[v] = c;
                 ag_nodew w; w.succ0 = w.succ1 = AG_NONE; w.moff = b.moff;
-                u32 misc = (u32)(unsigned char)ag_consensus(b.cnt, in.ref[q]);
-                if (b.cid == AG_NONE && (int)b.cov < cov) misc |= AG_NW_FILTERED | AG_NW_TRAV;
-                if (b.coff != AG_NONE) misc |= AG_NW_HASCONTIG;
-                w.misc = misc; node_w[v] = w;
+                w.misc = ag_node_misc(b.cid, b.coff, b.cov, b.cnt, in.ref[q], cov); node_w[v] = w;
                 node_sref[2 * (size_t)v] = b.sread; node_sref[2 * (size_t)v + 1] = b.soff_len; node_pos[v] = q;
             }
-        // k_edges
-        for (u32 q = 0; q < n_ref; q++) {
-            u32 nb0 = pos_node[q], nn0 = pos_node[q + 1] - nb0;
-            if (!nn0) continue;
-            const ag_cm1 ca = cm1[q];
-            u32 last_v = AG_NONE, last_t = AG_NONE;
-            for (u32 idx : tiles[q / AG_TILE]) {
-                const ag_fast f = ag_fast_prep(alnp[idx], lo[idx], span[idx]);
-                bool simple = f.simple && !force_generic;
-                if (q - f.lo >= f.span + (simple ? 0u : 1u)) continue;
-                ag_touch t;
-                if (simple) t = ag_fast_touch(f, q, (u32)k);
-                else { t = ag_locate(alnp[idx], in.ext, q, (u32)k); if (t.kind != 1) continue; }
-                u32 nb1 = pos_node[t.npos], nn1 = pos_node[t.npos + 1] - nb1;
-                const ag_cm1 cn1 = cm1[t.npos];
-                for_candidates_fast(q, ca, t.mate, [&](const ag_nodem& c) {
-                    u32 ci = ag_first_compatible(node_m.data() + nb0, nn0, c, iv);
-                    if (ci == AG_NONE) return;
-                    const ag_nodem x = node_m[nb0 + ci];
-                    for_candidates_fast(t.npos, cn1, t.nmate, [&](const ag_nodem& c2) {
-                        u32 ni = ag_first_compatible(node_m.data() + nb1, nn1, c2, iv);
-                        if (ni == AG_NONE) return;
-                        if (nb0 + ci == last_v && nb1 + ni == last_t) return;
-                        if (ag_edge_ok(x, node_m[nb1 + ni], iv)) add_edge(nb0 + ci, nb1 + ni);
-                        last_v = nb0 + ci; last_t = nb1 + ni;
-                    });
-                });
+        // k_succ
+        for (u32 v = 0; v < n_nodes; v++) {
+            u32 mask = nodeb[v].succ;
+            if (!mask) continue;
+            const u32 b1 = pos_node[node_pos[v] + 1];
+            for (u32 j = 0; j < 32; j++) if ((mask >> j) & 1) {
+                if (b1 + j >= pos_node[node_pos[v] + 2]) throw AgHostError{"emul: successor item out of range"};
+                if (ag_edge_ok_c(node_c[v], node_c[b1 + j], iv)) add_edge(v, b1 + j);
             }
         }
+        // k_edges on the flagged tiles
+        n_flagged = 0;
+        for (u32 tile = 0; tile < n_tiles; tile++) {
+            if (!tile_flag[tile] && !force_all_edges) continue;
+            n_flagged++;
+            const bool all = (tile_flag[tile] & 2) || force_all_edges;
+            for (u32 q = tile * AG_TPOS; q < (tile + 1) * AG_TPOS && q < n_ref; q++) {
+                u32 nb0 = pos_node[q], nn0 = pos_node[q + 1] - nb0;
+                if (!nn0) continue;
+                const ag_cm1 ca = cm1[q];
+                u32 last_v = AG_NONE, last_t = AG_NONE;
+                for (u32 idx : tiles[tile]) {
+                    const ag_fast f = fast[idx];
+                    if (!all && (f.simple & AG_FAST_CLEAN) && !force_generic) continue;   // settled inside the node sweep
+                    bool simple = f.simple && !force_generic;
+                    if (q - f.lo >= f.span + (simple ? 0u : 1u)) continue;
+                    ag_touch t;
+                    if (simple) t = ag_fast_touch(f, q, (u32)k);
+                    else { t = ag_locate(alnp[idx], in.ext, q, (u32)k); if (t.kind != 1) continue; }
+                    u32 nb1 = pos_node[t.npos], nn1 = pos_node[t.npos + 1] - nb1;
+                    const ag_cm1 cn1 = cm1[t.npos];
+                    for_candidates_fast(q, ca, t.mate, [&](const ag_nodem& c) {
+                        u32 ci = ag_first_compatible(node_c.data(), node_w.data(), nb0, nn0, c, iv);
+                        if (ci == AG_NONE) return;
+                        const ag_nodec x = node_c[nb0 + ci];
+                        for_candidates_fast(t.npos, cn1, t.nmate, [&](const ag_nodem& c2) {
+                            u32 ni = ag_first_compatible(node_c.data(), node_w.data(), nb1, nn1, c2, iv);
+                            if (ni == AG_NONE) return;
+                            if (nb0 + ci == last_v && nb1 + ni == last_t) return;
+                            if (ag_edge_ok_c(x, node_c[nb1 + ni], iv)) add_edge(nb0 + ci, nb1 + ni);
+                            last_v = nb0 + ci; last_t = nb1 + ni;
+                        });
+                    });
+                }
+            }
+        }
+        n_tiles_total = n_tiles;
+        return true;
     }
 
     void add_edge(u32 v, u32 tgt) {
@@ -337,7 +393,7 @@ int main(int argc, char** argv) {
         for (int unit = first; unit <= last; unit++) {
             AgUnitResult r;
             ag_run_unit_files(eng, reads, "tmp", unit, r);
-            fprintf(stderr, "emul unit %d: aln=%lu nodes=%u live=%u chain_heads=%u max_chain=%u walks=%lu emitted=%lu%s\n", unit, (unsigned long)r.n_aln, eng.n_nodes, eng.n_live, eng.n_heads, eng.max_chain, (unsigned long)r.n_walks, (unsigned long)r.n_emitted,
+            fprintf(stderr, "emul unit %d: aln=%lu nodes=%u live=%u chain_heads=%u max_chain=%u flagged_tiles=%u/%u flag2_tiles=%u many_pos=%u max_items=%u walks=%lu emitted=%lu%s\n", unit, (unsigned long)r.n_aln, eng.n_nodes, eng.n_live, eng.n_heads, eng.max_chain, eng.n_flagged, eng.n_tiles_total, eng.n_flag2, eng.n_many, eng.max_items, (unsigned long)r.n_walks, (unsigned long)r.n_emitted,
                     eng.fallback_used ? " (sequential walk)" : "");
             if (dump) { AgNodeDump d; eng.dump_nodes(d); std::string text; ag_format_node_dump(d, reads, text); ag_write_file("tmp/_nodes." + std::to_string(unit) + ".txt", text); }
         }

@@ -50,6 +50,26 @@ def test_emulation_generic_path_only(harness, workdir):
     compare_with_golden(harness, workdir, "mix")
 
 
+def test_emulation_generic_edge_sweep_everywhere(harness, workdir):
+    """Edges settled inside the node sweep (successor-item bits) and edges from the generic sweep agree: running the generic sweep on
+    every tile, for every alignment, must change nothing."""
+    emu = os.path.join(workdir, "emu")
+    ora = os.path.join(workdir, "ora")
+    harness.synth(emu, **cases.GOLDEN["mix"])
+    shutil.copytree(emu, ora)
+    harness.run_oracle(ora, dump_nodes=True)
+    harness.run_emul(emu, dump_nodes=True, env={"AG_EMUL_ALL_EDGES": "1"})
+    assert open(os.path.join(emu, "tmp", "_nodes.0.txt"), "rb").read() == open(os.path.join(ora, "tmp", "_nodes.0.txt"), "rb").read()
+
+
+def test_emulation_clean_input_needs_no_generic_edge_sweep(harness, workdir):
+    """All-M CIGARs and non-overlapping contigs: every edge is settled inside the node sweep, no tile is flagged."""
+    harness.synth(workdir, **cases.GOLDEN["plain"])
+    log = harness.run_emul(workdir)
+    assert "flagged_tiles=0/" in log
+    compare_with_golden(harness, workdir, "plain")
+
+
 @pytest.mark.parametrize("name", ["mix", "two_chr", "k7_150_2chr"])
 def test_parallel_text_parsers_match_golden(harness, workdir, name):
     """The multi-threaded read / SAM parsers (used for large files) forced onto the small golden cases: '@' header, -k records,

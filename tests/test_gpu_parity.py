@@ -22,6 +22,8 @@ def run_cuda(ag, harness, work, dump=False):
     harness.prepare_tmp(work)  # tmp/_contigs.fa, tmp/_genome.N.fa — input normalisation, outside the hot path
     ctx = ag.Context(k=p["kMer"], insert_variation=p["insertVariation"], coverage=p["coverage"])
     ctx.load_reads_fasta(os.path.join(work, "tmp", "_reads.fa"))
+    if dump:
+        ctx.keep_node_counts(True)
     dumps = []
     for u in range(harness.n_units(work)):
         ctx.prepare_unit(os.path.join(work, "tmp"), u)

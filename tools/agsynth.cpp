@@ -215,7 +215,7 @@ int main(int argc, char** argv) {
         }
 
         // ---- contigs: tiles of the target --------------------------------------------------------------
-        for (long s = p.contig_gap / 2; s + 300 < T; s += p.contig_len + p.contig_gap) {
+        for (long s = std::max(0L, p.contig_gap / 2); s + 300 < T; s += p.contig_len + p.contig_gap) {   // a negative gap makes the tiles overlap
             long e = std::min(T - 1, s + p.contig_len);
             // vary length a little so chunk sizes differ
             e = std::max(s + 250, e - (long)rng.below(p.contig_len / 10 + 1));
