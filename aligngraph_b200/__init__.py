@@ -38,7 +38,7 @@ class Stats(C.Structure):
 class UnitView(C.Structure):
     _fields_ = [("ref", C.c_void_p), ("n_ref", C.c_uint32), ("n_tail", C.c_uint32), ("cm_start", C.c_void_p), ("cm", C.c_void_p),
                 ("n_cm", C.c_uint32), ("chain_pos", C.c_void_p), ("chain_base", C.c_void_p), ("aln", C.c_void_p), ("n_aln", C.c_uint64),
-                ("ext", C.c_void_p), ("n_ext", C.c_uint64)]
+                ("ext", C.c_void_p), ("n_ext", C.c_uint64), ("threads", C.c_void_p), ("n_threads", C.c_uint32)]
 
 
 _lib = None
@@ -66,6 +66,7 @@ def load_library(path=None):
         "ag_get_reads": (i32, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(u64), C.POINTER(u32), C.POINTER(u32)]),
         "ag_begin_unit": (i32, [vp, i32, vp, u32]),
         "ag_set_contimers": (i32, [vp, vp, vp, u32, vp, vp, vp, u32]),
+        "ag_set_contig_threads": (i32, [vp, vp, u32, vp, vp, u32, vp, u32]),
         "ag_add_alignments": (i32, [vp, vp, u64, vp, u64]),
         "ag_build": (i32, [vp]),
         "ag_extend": (i32, [vp]),
@@ -162,6 +163,9 @@ class Context:
 
     def begin_unit(self, unit, ref_ptr, n_ref):
         self._ck(self._lib.ag_begin_unit(self._h, unit, ref_ptr, n_ref), "ag_begin_unit")
+
+    def set_contig_threads(self, threads, n_threads, chain_pos, chain_base, n_cm, tail_ptr, n_tail):
+        self._ck(self._lib.ag_set_contig_threads(self._h, threads, n_threads, chain_pos, chain_base, n_cm, tail_ptr, n_tail), "ag_set_contig_threads")
 
     def set_contimers(self, cm_start, cm, n_cm, chain_pos, chain_base, tail_ptr, n_tail):
         self._ck(self._lib.ag_set_contimers(self._h, cm_start, cm, n_cm, chain_pos, chain_base, tail_ptr, n_tail), "ag_set_contimers")

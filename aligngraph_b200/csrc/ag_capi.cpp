@@ -24,6 +24,7 @@ struct ag_ctx {
     bool uploaded = false;  // the staged unit arrays are resident on the device
     AgUnitResult res;
     std::string err, dump;
+    std::vector<u64> exc_keys;
     double s_parse = 0, s_device = 0, s_post = 0;
     u64 n_aln = 0, n_walks = 0, n_emitted = 0;
 };
@@ -55,13 +56,24 @@ void ag_destroy(ag_ctx* ctx) { if (!ctx) return; if (ctx->dev) ctx->dev->unpin_a
 const char* ag_last_error(const ag_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 const char* ag_create_error(void) { return g_create_error.c_str(); }
 
+// host -> device copy of the context's packed reads.  The non-ACGT bit plane is all zeros except where the parser recorded an exception,
+// so when that list is complete only the list travels (8 bytes per non-ACGT character) and the device rebuilds the plane.
+static void upload_reads(ag_ctx* ctx) {
+    const AgReads& r = ctx->reads;
+    if (r.exc_complete && r.exc.size() * 8 < r.nmask.size() * 4) {
+        ctx->exc_keys.resize(r.exc.size());
+        for (size_t i = 0; i < r.exc.size(); i++) ctx->exc_keys[i] = r.exc[i].first;
+        ctx->dev->set_reads_sparse(r.bases.data(), ctx->exc_keys.data(), ctx->exc_keys.size(), r.len.data(), r.n_pairs, r.stride2, r.stridem);
+    } else ctx->dev->set_reads(r.bases.data(), r.nmask.data(), r.len.data(), r.n_pairs, r.stride2, r.stridem, false);
+}
+
 int ag_set_reads(ag_ctx* ctx, const uint32_t* bases2, const uint32_t* nmask, const uint16_t* pair_len, uint64_t n_pairs, uint32_t stride2, uint32_t stridem) {
     return guard(ctx, [&] {
         ctx->dev->unpin_all();
         AgReads& r = ctx->reads;
         r.n_pairs = n_pairs; r.stride2 = stride2; r.stridem = stridem;
         r.bases.assign((const u32*)bases2, (const u32*)bases2 + 2 * n_pairs * stride2); r.nmask.assign((const u32*)nmask, (const u32*)nmask + 2 * n_pairs * stridem); r.len.assign(pair_len, pair_len + n_pairs);
-        r.exc.clear();
+        r.exc.clear(); r.exc_complete = false;
         ctx->dev->set_reads(bases2, nmask, pair_len, n_pairs, stride2, stridem, false);
         ctx->have_reads = true;
     });
@@ -71,14 +83,14 @@ int ag_set_reads_device(ag_ctx* ctx, const uint32_t* d_bases2, const uint32_t* d
         ctx->dev->unpin_all();
         AgReads& r = ctx->reads;
         r.n_pairs = n_pairs; r.stride2 = stride2; r.stridem = stridem;
-        r.bases.resize(2 * n_pairs * stride2); r.nmask.resize(2 * n_pairs * stridem); r.len.resize(n_pairs); r.exc.clear();
+        r.bases.resize(2 * n_pairs * stride2); r.nmask.resize(2 * n_pairs * stridem); r.len.resize(n_pairs); r.exc.clear(); r.exc_complete = false;
         ctx->dev->set_reads(d_bases2, d_nmask, d_pair_len, n_pairs, stride2, stridem, true);
         ctx->dev->copy_reads_to_host(r.bases.data(), r.nmask.data(), r.len.data());
         ctx->have_reads = true;
     });
 }
 int ag_set_read_exceptions(ag_ctx* ctx, const uint64_t* keys, const char* chars, uint64_t n) {
-    return guard(ctx, [&] { ctx->reads.exc.clear(); for (uint64_t i = 0; i < n; i++) ctx->reads.exc.push_back({keys[i], chars[i]}); });
+    return guard(ctx, [&] { ctx->reads.exc.clear(); ctx->reads.exc_complete = false; for (uint64_t i = 0; i < n; i++) ctx->reads.exc.push_back({keys[i], chars[i]}); });
 }
 int ag_load_reads_fasta(ag_ctx* ctx, const char* path) {
     return guard(ctx, [&] {
@@ -86,8 +98,7 @@ int ag_load_reads_fasta(ag_ctx* ctx, const char* path) {
         auto t0 = std::chrono::steady_clock::now();
         ag_parse_reads(path, ctx->reads);
         ctx->s_parse += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-        const AgReads& r = ctx->reads;
-        ctx->dev->set_reads(r.bases.data(), r.nmask.data(), r.len.data(), r.n_pairs, r.stride2, r.stridem, false);
+        upload_reads(ctx);
         ctx->have_reads = true;
     });
 }
@@ -112,9 +123,26 @@ int ag_set_contimers(ag_ctx* ctx, const uint32_t* cm_start, const ag_cm_c* cm, u
         AgUnit& u = ctx->unit; ctx->uploaded = false;
         u.ref.resize(u.n_ref);
         if (n_tail) u.ref.append(tail_bases, n_tail);
+        u.threads.clear();
         u.cm_start.assign(cm_start, cm_start + u.ref.size() + 1);
         u.cm.assign((const ag_cm*)cm, (const ag_cm*)cm + n_cm);
         u.chain_pos.assign(chain_pos, chain_pos + n_cm); u.chain_base.assign(chain_base, n_cm);
+    });
+}
+int ag_set_contig_threads(ag_ctx* ctx, const ag_cthread_c* threads, uint32_t n_threads, const uint32_t* chain_pos, const char* chain_base, uint32_t n_cm,
+                          const char* tail_bases, uint32_t n_tail) {
+    return guard(ctx, [&] {
+        ctx->dev->unpin_all();
+        AgUnit& u = ctx->unit; ctx->uploaded = false;
+        u.ref.resize(u.n_ref);
+        if (n_tail) u.ref.append(tail_bases, n_tail);
+        u.threads.assign((const ag_cthread*)threads, (const ag_cthread*)threads + n_threads);
+        u.cm_start.clear(); u.cm.clear();
+        u.chain_pos.assign(chain_pos, chain_pos + n_cm); u.chain_base.assign(chain_base, n_cm);
+        for (uint32_t i = 0; i < n_threads; i++)
+            if (u.threads[i].first > u.threads[i].term || u.threads[i].term >= n_cm || (i && u.threads[i].first != u.threads[i - 1].term + 1) || (!i && u.threads[i].first != 0))
+                throw AgHostError{"CONTIG ALIGNMENT ERROR"};
+        if (n_threads ? u.threads.back().term + 1 != n_cm : n_cm != 0) throw AgHostError{"CONTIG ALIGNMENT ERROR"};
     });
 }
 int ag_add_alignments(ag_ctx* ctx, const ag_aln_c* aln, uint64_t n, const ag_seg_c* ext, uint64_t n_ext) {
@@ -264,9 +292,11 @@ int ag_run_units_files(ag_ctx** ctxs, int n_ctx, const char* tmp_dir, int first_
 
 int ag_get_unit(ag_ctx* ctx, ag_unit_view* out) {
     return guard(ctx, [&] {
-        const AgUnit& u = ctx->unit;
+        AgUnit& u = ctx->unit;
+        if (u.cm_start.size() != u.ref.size() + 1 || u.cm.size() != u.chain_pos.size()) { ctx->dev->unpin_all(); ag_expand_contimers(u); }   // table view on demand
         out->ref = u.ref.data(); out->n_ref = u.n_ref; out->n_tail = (uint32_t)u.ref.size() - u.n_ref;
         out->cm_start = u.cm_start.data(); out->cm = (const ag_cm_c*)u.cm.data(); out->n_cm = (uint32_t)u.cm.size();
+        out->threads = (const ag_cthread_c*)u.threads.data(); out->n_threads = (uint32_t)u.threads.size();
         out->chain_pos = u.chain_pos.data(); out->chain_base = u.chain_base.data();
         out->aln = (const ag_aln_c*)u.aln.data(); out->n_aln = u.aln.size(); out->ext = (const ag_seg_c*)u.ext.data(); out->n_ext = u.ext.size();
     });
@@ -301,8 +331,7 @@ void* ag_cuda_stream(ag_ctx* ctx) { return ctx ? ctx->dev->stream() : nullptr; }
 int ag_invalidate_device_inputs(ag_ctx* ctx) { return guard(ctx, [&] { ctx->uploaded = false; }); }
 int ag_reupload_reads(ag_ctx* ctx) {
     return guard(ctx, [&] {
-        const AgReads& r = ctx->reads;
-        ctx->dev->set_reads(r.bases.data(), r.nmask.data(), r.len.data(), r.n_pairs, r.stride2, r.stridem, false);
+        upload_reads(ctx);
     });
 }
 int ag_formalize_inputs(ag_ctx* ctx, const char* contig_fa, const char* genome_fa, const char* tmp_dir, int part, int* n_units) {
@@ -317,7 +346,8 @@ int ag_pin_staged(ag_ctx* ctx) {
         AgDevice& d = *ctx->dev; const AgReads& r = ctx->reads; const AgUnit& u = ctx->unit;
         d.unpin_all();
         d.pin(r.bases.data(), r.bases.size() * 4); d.pin(r.nmask.data(), r.nmask.size() * 4); d.pin(r.len.data(), r.len.size() * 2);
-        d.pin(u.ref.data(), u.ref.size()); d.pin(u.cm_start.data(), u.cm_start.size() * 4); d.pin(u.cm.data(), u.cm.size() * sizeof(ag_cm));
+        d.pin(u.ref.data(), u.ref.size()); if (u.threads.empty()) { d.pin(u.cm_start.data(), u.cm_start.size() * 4); d.pin(u.cm.data(), u.cm.size() * sizeof(ag_cm)); }
+        d.pin(u.threads.data(), u.threads.size() * sizeof(ag_cthread));
         d.pin(u.chain_pos.data(), u.chain_pos.size() * 4); d.pin(u.chain_base.data(), u.chain_base.size());
         d.pin(u.aln.data(), u.aln.size() * sizeof(ag_aln)); d.pin(u.ext.data(), u.ext.size() * sizeof(ag_seg));
     });

@@ -348,12 +348,16 @@ AG_HD u32 ag_pool_new(ag_plist& pl, const ag_ovfpool& pool, const ag_nodem& c, b
 // Returns the item index (stable: lists only grow at the tail); oslot = pool slot of the item, NONE when it sits in a slot.
 AG_HD u32 ag_touch_slots(ag_plist& pl, const ag_slots& sv, const ag_ovfpool& pool, const ag_nodem& c, bool bump, int code, u32 sread, u32 soff_len, int iv, u32& oslot) {
     oslot = AG_NONE;
-    const u32 nloc = pl.n < (u32)AG_NODE_SCAP ? pl.n : (u32)AG_NODE_SCAP;
-    for (u32 i = 0; i < nloc; i++)
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (u32 i = 0; i < (u32)AG_NODE_SCAP; i++) {   // fixed trip count: slot addresses become immediates
+        if (i >= pl.n) break;
         if (ag_compat23(c.cid0, c.coff0, c.moff, sv.f(AG_F_CID0, i), sv.f(AG_F_COFF0, i), sv.f(AG_F_MOFF, i), iv)) {
             if (bump) { sv.f(AG_F_COV, i)++; if (code >= 0) sv.f(AG_F_CNT + (u32)code, i)++; }
             return i;
         }
+    }
     if (pl.n > (u32)AG_NODE_SCAP) {
         u32 i = AG_NODE_SCAP;
         for (u32 o = pl.ovf_head; o != AG_NONE; o = pool.next[o], i++) {
@@ -387,7 +391,8 @@ AG_HD u32 ag_touch_pool(ag_plist& pl, const ag_ovfpool& pool, const ag_nodem& c,
 
 // record "the call that bumped (item, oslot) continues on item `nb` of the next position"
 AG_HD void ag_note_succ(const ag_slots& sv, const ag_ovfpool& pool, u32 item, u32 oslot, u32 nb) {
-    if (oslot == AG_NONE) sv.f(AG_F_SUCC, item) |= 1u << nb; else pool.node[oslot].succ |= 1u << nb;
+    if (oslot != AG_NONE) pool.node[oslot].succ |= 1u << nb;
+    else if (item < (u32)AG_NODE_SCAP) sv.f(AG_F_SUCC, item) |= 1u << nb;   // (an item beyond the slots without a pool slot: pool exhausted, the sweep is repeated)
 }
 
 // What one lane (= one unit position q) does with one alignment of its tile during the node sweep.

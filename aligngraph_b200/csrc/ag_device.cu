@@ -211,6 +211,48 @@ __global__ void k_keys(DevView d) {
     for (u32 j = 0; j < n; j++) { d.keys[off + j] = t0 + j; d.vals[off + j] = i; atomicAdd(&d.tile_cnt[t0 + j], 1u); }
 }
 
+// non-ACGT bit plane of the reads from its list of set bits (key = read * 65536 + offset)
+__global__ void k_nmask_scatter(const u64* __restrict__ keys, u64 n, u32* nmask, u32 stridem, u64 n_reads) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u64 read = keys[i] >> 16; const u32 off = (u32)(keys[i] & 0xFFFFu);
+    if (read < n_reads && (off >> 5) < stridem) atomicOr(&nmask[read * stridem + (off >> 5)], 1u << (off & 31));
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// contiMer table from the contig threads (loadContigAlignment's product, AG:884-1177, re-derived on the device instead of being
+// uploaded: 20 bytes per contiMer stay off the PCIe link).  Position p's list holds the contiMers with chain_pos == p in push order,
+// i.e. by increasing chain index: count -> scan -> fill in arrival order -> per-position insertion sort by chain index.
+// ---------------------------------------------------------------------------------------------------------------------------
+__global__ void k_cm_count(const u32* __restrict__ chain_pos, u32 n_cm, u32 n_pos, u32* cnt, int* err) {
+    u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_cm) return;
+    u32 p = chain_pos[k];
+    if (p >= n_pos) { *err = 7; return; }
+    atomicAdd(&cnt[p], 1u);
+}
+__global__ void k_cm_fill(const u32* __restrict__ chain_pos, u32 n_cm, const ag_cthread* __restrict__ th, u32 n_th, const u32* __restrict__ cm_start, u32* fill, ag_cm* cm, int* err) {
+    u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_cm) return;
+    u32 lo = 0, hi = n_th;   // last thread with first <= k
+    while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (th[mid].first <= k) lo = mid; else hi = mid; }
+    const ag_cthread t = th[lo];
+    if (n_th == 0 || k < t.first || k > t.term) { *err = 7; return; }
+    const u32 p = chain_pos[k];
+    ag_cm m; m.cid = t.cid; m.coff = k < t.term ? t.coff_first + (k - t.first) : t.coff_term; m.chain = k; m.term = t.term;
+    cm[cm_start[p] + atomicAdd(&fill[p], 1u)] = m;
+}
+__global__ void k_cm_sort(const u32* __restrict__ cm_start, u32 n_pos, ag_cm* cm) {
+    u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pos) return;
+    const u32 a = cm_start[p], n = cm_start[p + 1] - a;
+    for (u32 i = 1; i < n; i++) {
+        ag_cm x = cm[a + i]; u32 j = i;
+        while (j > 0 && cm[a + j - 1].chain > x.chain) { cm[a + j] = cm[a + j - 1]; j--; }
+        cm[a + j] = x;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------------
 // k_cm1: per-position summary of the contiMer table (one 8-byte load per lookup in the sweeps)
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -778,9 +820,9 @@ struct Timer {
 struct AgDevice::Impl {
     cudaStream_t st = nullptr;
     // reads
-    DBuf<u32> r_bases, r_nmask; DBuf<uint16_t> r_len; ag_reads reads{}; u64 n_pairs = 0; bool reads_owned = false;
+    DBuf<u32> r_bases, r_nmask; DBuf<uint16_t> r_len; DBuf<u64> r_exc; ag_reads reads{}; u64 n_pairs = 0; bool reads_owned = false;
     // unit inputs
-    DBuf<unsigned char> ref, chain_base; DBuf<u32> cm_start, chain_pos; DBuf<ag_cm> cm; DBuf<ag_aln> aln; DBuf<ag_seg> ext;
+    DBuf<unsigned char> ref, chain_base; DBuf<u32> cm_start, chain_pos; DBuf<ag_cm> cm; DBuf<ag_cthread> cthreads; DBuf<ag_aln> aln; DBuf<ag_seg> ext;
     u32 n_ref = 0, n_pos = 0, n_cm = 0, n_aln = 0;
     // build products
     DBuf<ag_alnp> alnp; DBuf<ag_fast> fast; DBuf<u32> ntiles, key_off, keys, vals, keys2, vals2, hist, tile_cnt, tile_start, tile_flag, many, many_prefix;
@@ -813,6 +855,7 @@ AgDevice::~AgDevice() {
     // DBuf members are plain; free what we own
     Impl& m = *m_;
     if (m.reads_owned) { m.r_bases.release(); m.r_nmask.release(); m.r_len.release(); }
+    m.r_exc.release();
     DBuf<unsigned char>* b8[] = {&m.ref, &m.chain_base, &m.out_bases, &m.occ};
     for (auto* b : b8) b->release();
     DBuf<u32>* b32[] = {&m.cm_start, &m.chain_pos, &m.ntiles, &m.key_off, &m.keys, &m.vals, &m.keys2, &m.vals2, &m.hist, &m.tile_cnt,
@@ -820,7 +863,7 @@ AgDevice::~AgDevice() {
                         &m.eovf_target, &m.eovf_next, &m.walk_next, &m.parent, &m.cmin, &m.cmax, &m.sel_start, &m.sel_tails};
     for (auto* b : b32) b->release();
     for (int i = 0; i < 4; i++) m.scanner.lvl[i].release();
-    m.cm.release(); m.aln.release(); m.ext.release(); m.alnp.release(); m.fast.release(); m.tile_state.release(); m.ovf_node.release(); m.err.release();
+    m.cm.release(); m.cthreads.release(); m.aln.release(); m.ext.release(); m.alnp.release(); m.fast.release(); m.tile_state.release(); m.ovf_node.release(); m.err.release();
     m.node_c.release(); m.node_w.release(); m.walks.release(); m.walks2.release(); m.cm1.release(); m.mat_chains.release(); m.mat_detours.release(); m.pos_term.release(); m.cand_rank.release(); m.cand_node.release(); m.cand_label.release(); m.fprev.release(); m.msuf.release(); m.mnode.release(); m.indeg.release(); m.fnext.release(); m.chain_a.release(); m.chain_b.release(); m.changed.release(); m.sel_off.release();
     m.h_walks.release(); m.h_bases.release(); m.h_occ.release();
     if (m.st) cudaStreamDestroy(m.st);
@@ -873,6 +916,25 @@ void AgDevice::set_reads(const u32* bases, const u32* nmask, const uint16_t* len
     m.reads.stride2 = stride2; m.reads.stridem = stridem;
 }
 
+void AgDevice::set_reads_sparse(const u32* bases, const u64* exc_keys, u64 n_exc, const uint16_t* len, u64 n_pairs, u32 stride2, u32 stridem) {
+    CK(cudaSetDevice(dev_));
+    Impl& m = *m_;
+    m.n_pairs = n_pairs;
+    Timer tm(m.st);
+    m.r_bases.ensure(2 * n_pairs * stride2 + 1); m.r_nmask.ensure(2 * n_pairs * stridem + 1); m.r_len.ensure(n_pairs + 1); m.r_exc.ensure(n_exc + 1);
+    CK(cudaMemcpyAsync(m.r_bases.p, bases, 2 * n_pairs * stride2 * sizeof(u32), cudaMemcpyHostToDevice, m.st));
+    CK(cudaMemcpyAsync(m.r_len.p, len, n_pairs * sizeof(uint16_t), cudaMemcpyHostToDevice, m.st));
+    CK(cudaMemsetAsync(m.r_nmask.p, 0, 2 * n_pairs * stridem * sizeof(u32), m.st));
+    if (n_exc) {
+        CK(cudaMemcpyAsync(m.r_exc.p, exc_keys, n_exc * sizeof(u64), cudaMemcpyHostToDevice, m.st));
+        k_nmask_scatter<<<(unsigned)((n_exc + 255) / 256), 256, 0, m.st>>>(m.r_exc.p, n_exc, m.r_nmask.p, stridem, 2 * n_pairs); launches_++;
+    }
+    m.reads.bases = m.r_bases.p; m.reads.nmask = m.r_nmask.p; m.reads.len = m.r_len.p; m.reads_owned = true;
+    m.reads.stride2 = stride2; m.reads.stridem = stridem;
+    t_.h2d += tm.stop();
+    t_.h2d_bytes += 2 * n_pairs * stride2 * sizeof(u32) + n_pairs * sizeof(uint16_t) + n_exc * sizeof(u64);
+}
+
 void AgDevice::copy_reads_to_host(u32* bases, u32* nmask, uint16_t* len) {
     CK(cudaSetDevice(dev_));
     Impl& m = *m_;
@@ -888,19 +950,41 @@ void AgDevice::load_unit(const AgUnitInput& in) {
     Timer tm(m.st);
     m.n_ref = in.n_ref; m.n_pos = in.n_pos; m.n_cm = in.n_cm; m.n_aln = (u32)in.n_aln;
     if (in.n_aln >= 0xFFFFFFF0ull) throw AgError{"too many alignments for one unit"};
+    const bool derive = in.threads != nullptr || in.cm_start == nullptr;   // contiMer table from the contig threads (else: explicit table)
     m.ref.ensure(in.n_pos + 1); m.cm_start.ensure((size_t)in.n_pos + 2); m.cm.ensure(in.n_cm + 1); m.chain_pos.ensure(in.n_cm + 1);
     m.chain_base.ensure(in.n_cm + 1); m.aln.ensure(in.n_aln + 1); m.ext.ensure(in.n_ext + 1);
     CK(cudaMemcpyAsync(m.ref.p, in.ref, in.n_pos, cudaMemcpyHostToDevice, m.st));
-    CK(cudaMemcpyAsync(m.cm_start.p, in.cm_start, ((size_t)in.n_pos + 1) * sizeof(u32), cudaMemcpyHostToDevice, m.st));
+    size_t table_bytes = 0;
+    if (in.n_aln) CK(cudaMemcpyAsync(m.aln.p, in.aln, in.n_aln * sizeof(ag_aln), cudaMemcpyHostToDevice, m.st));
+    if (in.n_ext) CK(cudaMemcpyAsync(m.ext.p, in.ext, in.n_ext * sizeof(ag_seg), cudaMemcpyHostToDevice, m.st));
     if (in.n_cm) {
-        CK(cudaMemcpyAsync(m.cm.p, in.cm, (size_t)in.n_cm * sizeof(ag_cm), cudaMemcpyHostToDevice, m.st));
         CK(cudaMemcpyAsync(m.chain_pos.p, in.chain_pos, (size_t)in.n_cm * sizeof(u32), cudaMemcpyHostToDevice, m.st));
         CK(cudaMemcpyAsync(m.chain_base.p, in.chain_base, in.n_cm, cudaMemcpyHostToDevice, m.st));
     }
-    if (in.n_aln) CK(cudaMemcpyAsync(m.aln.p, in.aln, in.n_aln * sizeof(ag_aln), cudaMemcpyHostToDevice, m.st));
-    if (in.n_ext) CK(cudaMemcpyAsync(m.ext.p, in.ext, in.n_ext * sizeof(ag_seg), cudaMemcpyHostToDevice, m.st));
+    if (!derive) {
+        CK(cudaMemcpyAsync(m.cm_start.p, in.cm_start, ((size_t)in.n_pos + 1) * sizeof(u32), cudaMemcpyHostToDevice, m.st));
+        if (in.n_cm) CK(cudaMemcpyAsync(m.cm.p, in.cm, (size_t)in.n_cm * sizeof(ag_cm), cudaMemcpyHostToDevice, m.st));
+        table_bytes = ((size_t)in.n_pos + 1) * 4 + (size_t)in.n_cm * sizeof(ag_cm);
+    } else {
+        m.cthreads.ensure(in.n_threads + 1); m.many.ensure((size_t)in.n_pos + 2);
+        if (in.n_threads) CK(cudaMemcpyAsync(m.cthreads.p, in.threads, (size_t)in.n_threads * sizeof(ag_cthread), cudaMemcpyHostToDevice, m.st));
+        table_bytes = (size_t)in.n_threads * sizeof(ag_cthread);
+        CK(cudaMemsetAsync(m.err.p, 0, sizeof(int), m.st));
+        CK(cudaMemsetAsync(m.many.p, 0, ((size_t)in.n_pos + 1) * sizeof(u32), m.st));
+        if (in.n_cm) { k_cm_count<<<(in.n_cm + 255) / 256, 256, 0, m.st>>>(m.chain_pos.p, in.n_cm, in.n_pos, m.many.p, m.err.p); launches_++; }
+        m.scanner.run(m.many.p, m.cm_start.p, in.n_pos, m.st);
+        if (in.n_cm) {
+            CK(cudaMemsetAsync(m.many.p, 0, ((size_t)in.n_pos + 1) * sizeof(u32), m.st));
+            k_cm_fill<<<(in.n_cm + 255) / 256, 256, 0, m.st>>>(m.chain_pos.p, in.n_cm, m.cthreads.p, in.n_threads, m.cm_start.p, m.many.p, m.cm.p, m.err.p); launches_++;
+            k_cm_sort<<<(in.n_pos + 255) / 256, 256, 0, m.st>>>(m.cm_start.p, in.n_pos, m.cm.p); launches_++;
+        }
+        int err = 0;
+        CK(cudaMemcpyAsync(&err, m.err.p, sizeof(int), cudaMemcpyDeviceToHost, m.st));
+        CK(cudaStreamSynchronize(m.st));
+        if (err) throw AgError{"CONTIG ALIGNMENT ERROR: inconsistent contig threads"};
+    }
     t_.h2d += tm.stop();
-    t_.h2d_bytes += in.n_pos + ((size_t)in.n_pos + 1) * 4 + (size_t)in.n_cm * (sizeof(ag_cm) + 5) + in.n_aln * sizeof(ag_aln) + in.n_ext * sizeof(ag_seg);
+    t_.h2d_bytes += in.n_pos + (size_t)in.n_cm * 5 + table_bytes + in.n_aln * sizeof(ag_aln) + in.n_ext * sizeof(ag_seg);
 }
 
 void AgDevice::build() {

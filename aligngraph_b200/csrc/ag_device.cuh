@@ -8,6 +8,7 @@
 struct AgUnitInput {
     const char* ref;            // unit bases followed by the contig-insertion tail (AG:981-1036), n_pos bytes
     u32 n_ref, n_pos;
+    const ag_cthread* threads; u32 n_threads;   // contig threads: when given, the device derives cm_start / cm itself and they may be null
     const u32* cm_start;        // n_pos + 1
     const ag_cm* cm; u32 n_cm;
     const u32* chain_pos;       // n_cm, chain-major
@@ -36,6 +37,8 @@ public:
     // reads: 2-bit packed + non-ACGT bit plane, fixed stride per read; len per pair.  `on_device` = pointers are device pointers
     // (the NCCL broadcast target); otherwise they are copied H2D.
     void set_reads(const u32* bases, const u32* nmask, const uint16_t* len, u64 n_pairs, u32 stride2, u32 stridem, bool on_device);
+    // the same from host memory, the non-ACGT plane given as its list of set bits (key = read * 65536 + offset): the plane is rebuilt here
+    void set_reads_sparse(const u32* bases, const u64* exc_keys, u64 n_exc, const uint16_t* len, u64 n_pairs, u32 stride2, u32 stridem);
     void copy_reads_to_host(u32* bases, u32* nmask, uint16_t* len);
     void set_params(int k, int iv, int coverage) { k_ = k; iv_ = iv; cov_ = coverage; }
     // keep coverage + base counters per node after the build (24 B per node; only the node dump of the tests needs them)

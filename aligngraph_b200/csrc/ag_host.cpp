@@ -100,7 +100,7 @@ static void pack_init(AgReads& out, size_t n_reads, u32 maxlen) {
     out.stride2 = (maxlen + 15) / 16; out.stridem = (maxlen + 31) / 32;
     if (!out.stride2) out.stride2 = out.stridem = 1;
     out.bases.assign_zero(n_reads * out.stride2); out.nmask.assign_zero(n_reads * out.stridem);
-    out.n_pairs = n_reads / 2; out.len.assign(out.n_pairs, 0); out.exc.clear();
+    out.n_pairs = n_reads / 2; out.len.assign(out.n_pairs, 0); out.exc.clear(); out.exc_complete = true;   // every packer below records each mask bit in exc
 }
 static void pack_one(AgReads& out, size_t r, const char* s, size_t n) {
     u32* b = &out.bases[r * out.stride2]; u32* m = &out.nmask[r * out.stridem];
@@ -342,6 +342,22 @@ static void load_chunks(const std::string& contigs_fa, std::vector<Chunk>& ch) {
     for (size_t i = 0; i < ch.size(); i++) { ch[i].id = c.chunks[i].first; ch[i].bases = c.chunks[i].second; }
 }
 
+void ag_expand_contimers(const ag_cthread* threads, size_t n_threads, const u32* chain_pos, size_t n_cm, size_t n_pos, std::vector<u32>& cm_start, std::vector<ag_cm>& cm) {
+    cm_start.assign(n_pos + 1, 0);
+    for (size_t k = 0; k < n_cm; k++) cm_start[chain_pos[k] + 1]++;
+    for (size_t i = 0; i < n_pos; i++) cm_start[i + 1] += cm_start[i];
+    cm.assign(n_cm, ag_cm{});
+    std::vector<u32> fill(cm_start.begin(), cm_start.end() - 1);
+    for (size_t i = 0; i < n_threads; i++) {
+        const ag_cthread& t = threads[i];
+        for (u32 k = t.first; k <= t.term; k++) {   // threads are stored in push order, so every position's list comes out in push order
+            ag_cm m; m.cid = t.cid; m.coff = k < t.term ? t.coff_first + (k - t.first) : t.coff_term; m.chain = k; m.term = t.term;
+            cm[fill[chain_pos[k]]++] = m;
+        }
+    }
+}
+void ag_expand_contimers(AgUnit& u) { ag_expand_contimers(u.threads.data(), u.threads.size(), u.chain_pos.data(), u.chain_pos.size(), u.ref.size(), u.cm_start, u.cm); }
+
 void ag_thread_contigs(const std::string& contigs_fa, const std::string& psl_path, std::string& initial_text, AgUnit& u) {
     // ---- chunks (AG:322-359) ----
     auto T0 = std::chrono::steady_clock::now();
@@ -397,9 +413,9 @@ void ag_thread_contigs(const std::string& contigs_fa, const std::string& psl_pat
     // ---- thread every surviving set through the unit (AG:884-1177) ----
     struct Push { u32 pos, cid, coff; char base; };
     std::vector<Push> pushes;          // chain-major: one thread after the other, each in walking order
-    std::vector<u32> term_of;          // per push: index of its thread's terminal push
     std::vector<u32> count(u.n_ref, 0);  // contiMers per position so far (grows with the tail)
-    { size_t cap = 0; for (const Chunk& c : ch) for (const auto& st : c.sets) cap += st.size() + 1; pushes.reserve(cap); term_of.reserve(cap); }
+    { size_t cap = 0; for (const Chunk& c : ch) for (const auto& st : c.sets) cap += st.size() + 1; pushes.reserve(cap); }
+    u.threads.clear(); u.cm_start.clear(); u.cm.clear();
     u.ref.resize(u.n_ref);
     for (size_t sp = 0; sp < ch.size(); sp++) {
         Chunk& c = ch[sp];
@@ -445,28 +461,19 @@ void ag_thread_contigs(const std::string& contigs_fa, const std::string& psl_pat
                 if (tp >= u.ref.size()) throw AgHostError{"CONTIG ALIGNMENT ERROR"};
                 push(tp, (u32)i, u.ref[tp]);
             }
-            term_of.resize(pushes.size(), 0);
-            for (size_t k = first_push; k < pushes.size(); k++) term_of[k] = (u32)pushes.size() - 1;
+            if (pushes.size() > first_push) {
+                ag_cthread t; t.first = (u32)first_push; t.term = (u32)pushes.size() - 1; t.cid = (u32)sp; t.coff_first = pushes[first_push].coff; t.coff_term = pushes.back().coff;
+                for (size_t k = first_push; k < t.term; k++)   // contig offsets advance by one per contiMer up to the terminal
+                    if (pushes[k].coff != t.coff_first + (u32)(k - first_push)) throw AgHostError{"internal: contig thread offsets are not consecutive"};
+                u.threads.push_back(t);
+            }
             if (flipped) revcomp(c.bases);
         }
     }
     lap("threading");
-    // ---- CSR by position, push order preserved ----
-    size_t n_pos = u.ref.size();
-    u.cm_start.assign(n_pos + 1, 0);
-    for (const Push& p : pushes) u.cm_start[p.pos + 1]++;
-    for (size_t i = 0; i < n_pos; i++) u.cm_start[i + 1] += u.cm_start[i];
-    u.cm.assign(pushes.size(), ag_cm{});
+    // ---- chain-major arrays; the position-ordered table (CSR, push order preserved) is derived from them on the device ----
     u.chain_pos.resize(pushes.size()); u.chain_base.resize(pushes.size());
-    {
-        std::vector<u32> fill(u.cm_start.begin(), u.cm_start.end() - 1);
-        for (size_t k = 0; k < pushes.size(); k++) {
-            const Push& p = pushes[k];
-            ag_cm m; m.cid = p.cid; m.coff = p.coff; m.chain = (u32)k; m.term = term_of[k];
-            u.cm[fill[p.pos]++] = m;
-            u.chain_pos[k] = p.pos; u.chain_base[k] = p.base;
-        }
-    }
+    for (size_t k = 0; k < pushes.size(); k++) { u.chain_pos[k] = pushes[k].pos; u.chain_base[k] = pushes[k].base; }
     lap("csr");
     // ---- tmp/_initial_contigs.N.fa: original contigs with >= 50 % of their chunks threaded (AG:1179-1216) ----
     Out out(&initial_text);

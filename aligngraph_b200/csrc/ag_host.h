@@ -32,6 +32,7 @@ struct AgReads {
     AgZVec<u32> bases, nmask;        // 2 bits / base, 16 per word; 1 bit / base, 32 per word; fixed stride per read
     std::vector<uint16_t> len;       // per pair
     std::vector<std::pair<u64, char>> exc;  // (read * 65536 + offset, original character) for every non-ACGT character, sorted
+    bool exc_complete = false;       // exc lists EVERY set bit of nmask (true after ag_parse_reads / ag_pack_reads): the plane can be rebuilt from it
     u64 n_pairs = 0;
     u32 stride2 = 0, stridem = 0;
     char at(u32 read, u32 rc, u32 rlen, u32 off) const;  // character of the oriented read (AG:854-865 leaves non-ACGT unchanged)
@@ -44,7 +45,8 @@ void ag_pack_reads(const std::vector<std::string>& seqs, AgReads& out);
 struct AgUnit {
     std::string ref;                 // unit bases + contig-insertion tail
     u32 n_ref = 0;
-    std::vector<u32> cm_start;       // CSR over positions (ref.size() + 1)
+    std::vector<ag_cthread> threads; // contig threads; when non-empty (or cm empty) the contiMer table below is derived from them
+    std::vector<u32> cm_start;       // CSR over positions (ref.size() + 1) — only filled by ag_expand_contimers / ag_set_contimers
     std::vector<ag_cm> cm;
     std::vector<u32> chain_pos;      // chain-major
     std::string chain_base;
@@ -54,6 +56,10 @@ struct AgUnit {
 void ag_load_genome(const std::string& path, AgUnit& u);                                         // AG:287-320
 // contig chunks + PSL -> contiMer table + the text of tmp/_initial_contigs.N.fa                       // AG:1219-1231
 void ag_thread_contigs(const std::string& contigs_fa, const std::string& psl, std::string& initial_text, AgUnit& u);
+// position-ordered contiMer table (cm_start, cm) from the contig threads — what the device derives itself; host callers that want to
+// look at the table (tests, ag_get_unit) call this
+void ag_expand_contimers(AgUnit& u);
+void ag_expand_contimers(const ag_cthread* threads, size_t n_threads, const u32* chain_pos, size_t n_cm, size_t n_pos, std::vector<u32>& cm_start, std::vector<ag_cm>& cm);
 // SAM -> surviving alignments in processing order                                                 // AG:1233-1277, 1644-1656, 1872-1895
 void ag_parse_sam(const std::string& path, const AgReads& reads, AgUnit& u);
 

@@ -17,7 +17,9 @@ struct AgUnitResult {
 inline AgUnitInput ag_unit_input(const AgUnit& u) {
     AgUnitInput in;
     in.ref = u.ref.data(); in.n_ref = u.n_ref; in.n_pos = (u32)u.ref.size();
-    in.cm_start = u.cm_start.data(); in.cm = u.cm.data(); in.n_cm = (u32)u.cm.size();
+    in.threads = u.threads.empty() ? nullptr : u.threads.data(); in.n_threads = (u32)u.threads.size();
+    const bool table = u.cm_start.size() == u.ref.size() + 1 && u.cm.size() == u.chain_pos.size();   // explicit table (ag_set_contimers / expanded)
+    in.cm_start = table ? u.cm_start.data() : nullptr; in.cm = table ? u.cm.data() : nullptr; in.n_cm = (u32)u.chain_pos.size();
     in.chain_pos = u.chain_pos.data(); in.chain_base = u.chain_base.data();
     in.aln = u.aln.data(); in.n_aln = u.aln.size(); in.ext = u.ext.data(); in.n_ext = u.ext.size();
     return in;

@@ -53,6 +53,11 @@ struct ag_cm {
     u32 term;   // chain index of the terminal contiMer (nextID == -1) of this thread
 };
 
+// One contig thread: a chunk's position set threaded through the unit (AG:884-1177).  Its contiMers are the chain-major range
+// [first, term]; contigOffset of chain index k is coff_first + (k - first) for k < term and coff_term for the terminal (AG:1121-1148).
+// The position-ordered contiMer table (CSR + ag_cm records) is a pure function of these descriptors and chain_pos: the device builds it.
+struct ag_cthread { u32 first, term, cid, coff_first, coff_term; };
+
 // node while it is being built (k_nodes) — the founder fields never change after creation (AG:1381)
 struct ag_nodeb {
     u32 cid, coff, cid0, coff0, moff;  // match fields; mate chromosome id is 0 whenever moff != NONE

@@ -12,7 +12,7 @@ de-dup/join and scaffolding, ending with the unit's FASTA text in host memory.
 Printed JSON (one line, rank 0):
   value   Mbp of reference genome processed per second, all GPUs, inputs already resident in HBM when the timed region starts
   e2e     same metric through the array-level C ABI from pinned HOST buffers (reads + unit arrays copied H2D every step, results D2H)
-  roofline  dominant kernel (k_nodes) against the measured HBM peak; cpu_baseline  the reference CPU path on a bounded sample
+  roofline  dominant kernel (k_build) against the measured HBM peak; cpu_baseline  the reference CPU path on a bounded sample
 """
 import argparse
 import ctypes
@@ -351,16 +351,17 @@ def b200_arm(args):
         except Exception:
             pass
         peak = peaks.get("hbm_gbs", 6650.0)
-        # dominant kernel: k_nodes.  Algorithmic bytes of one launch: tile keys + prepared alignment records + packed
-        # bases of the left mates + contiMer table + node records written.
+        # dominant kernel: k_build (node sweep + common-case edges).  Algorithmic bytes of one launch: per tile key the
+        # alignment index, its 32-byte prepared record and the left mate's packed bases + non-ACGT plane; per position the contiMer
+        # summary, reference base and CSR entry; per node the final records written (16 + 16 + 8 + 4).
         L = SHAPE["readlen"]
-        alg = st["n_keys"] * (4 + 32 + 8 + (L + 3) // 4 + (L + 7) // 8) + UNIT_BP * (4 + 4 + 4 + 1) + st["n_nodes"] * 52
+        alg = st["n_keys"] * (4 + 32 + (L + 3) // 4 + (L + 7) // 8) + UNIT_BP * (8 + 1 + 4) + st["n_nodes"] * 44
         nodes_ms = st["ms_nodes"] / K
         achieved = alg / nodes_ms / 1e6
         pairs = UNIT_BP * 50 // 200
         k1_equiv = pairs * (2 * ((L + 3) // 4) + 32 + 16 * (L - SHAPE["kmer"])) / ((st["ms_prep"] + st["ms_sort"] + st["ms_nodes"]) / K) / 1e6
         traffic = None
-        try:   # DRAM bytes of one k_nodes launch from the committed `ncu --set full` capture of this same workload (profiles/README.md)
+        try:   # DRAM bytes of one k_build launch from the committed `ncu --set full` capture of this same workload (profiles/README.md)
             traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["traffic"]
         except Exception:
             pass
@@ -372,7 +373,7 @@ def b200_arm(args):
                     "d2h_bytes_per_step": int(st_e2e["d2h_bytes"] / K), "ms_per_step": round(ms_e2e / K, 3)},
             "gpu_launches": int(st["kernel_launches"]),
             "clocks": clock_info,
-            "roofline": {"bound": "hbm", "kernel": "k_nodes", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+            "roofline": {"bound": "hbm", "kernel": "k_build", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                          "traffic": traffic, "alg_bytes_per_launch": int(alg), "ms_per_launch": round(nodes_ms, 4),
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                          "survey_k1_equiv_gbs": round(k1_equiv, 1)},

@@ -50,6 +50,9 @@ typedef struct ag_aln_c { uint32_t pair, flags, dst1, sl1, dst2, sl2, ext_idx, p
 /* contiMer (ContiMer, AG:51-62) in position-CSR order; `chain` indexes the chain-major arrays (the next contiMer of the same
  * contig thread is chain+1), `term` is the chain index of the thread's terminal contiMer (nextID == -1). */
 typedef struct ag_cm_c { uint32_t cid, coff, chain, term; } ag_cm_c;
+/* one contig thread (a chunk's position set threaded through the unit, updateGenomeWithContig AG:884-1177): its contiMers are the
+ * chain-major range [first, term]; contigOffset of chain index k = coff_first + (k - first), the terminal (AG:1121-1148) has coff_term */
+typedef struct ag_cthread_c { uint32_t first, term, cid, coff_first, coff_term; } ag_cthread_c;
 
 typedef struct ag_stats {
     /* device milliseconds (CUDA events on the context's stream), accumulated since ag_reset_stats */
@@ -84,6 +87,10 @@ int ag_get_reads(ag_ctx* ctx, const uint32_t** bases2, const uint32_t** nmask, c
 int ag_begin_unit(ag_ctx* ctx, int unit_id, const char* ref_bases, uint32_t n_ref);                       /* loadGenome, AG:287 */
 int ag_set_contimers(ag_ctx* ctx, const uint32_t* cm_start /* n_ref+n_tail+1 */, const ag_cm_c* cm, uint32_t n_cm,
                      const uint32_t* chain_pos, const char* chain_base, const char* tail_bases, uint32_t n_tail); /* result of loadContigAlignment, AG:1219 */
+/* the same result of loadContigAlignment in compact form: contig threads in push order + the chain-major position / base arrays; the
+ * position-ordered table (cm_start, cm) is then derived on the device (20 bytes per contiMer less to upload) */
+int ag_set_contig_threads(ag_ctx* ctx, const ag_cthread_c* threads, uint32_t n_threads, const uint32_t* chain_pos, const char* chain_base, uint32_t n_cm,
+                          const char* tail_bases, uint32_t n_tail);
 int ag_add_alignments(ag_ctx* ctx, const ag_aln_c* aln, uint64_t n, const ag_seg_c* ext, uint64_t n_ext); /* parsing half of loadReadAlignment, AG:1872 */
 int ag_build(ag_ctx* ctx);   /* graph half of loadReadAlignment: updateGenomeWithRead / updateKMer, AG:1635-1870, AG:1353-1624 */
 int ag_extend(ag_ctx* ctx);  /* extendContigs + scaffoldContigs, AG:2382, AG:2396 */
@@ -105,6 +112,7 @@ typedef struct ag_unit_view {
     const char* ref; uint32_t n_ref, n_tail;
     const uint32_t* cm_start; const ag_cm_c* cm; uint32_t n_cm; const uint32_t* chain_pos; const char* chain_base;
     const ag_aln_c* aln; uint64_t n_aln; const ag_seg_c* ext; uint64_t n_ext;
+    const ag_cthread_c* threads; uint32_t n_threads;   /* contig threads (empty when the unit was staged through ag_set_contimers) */
 } ag_unit_view;
 int ag_get_unit(ag_ctx* ctx, ag_unit_view* out);
 

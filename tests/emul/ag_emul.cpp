@@ -33,7 +33,14 @@ public:
     bool force_all_edges = getenv("AG_EMUL_ALL_EDGES") != nullptr;   // run the generic edge sweep on every tile (must change nothing)
 
     void set_reads(const AgReads& r) { rd.bases = r.bases.data(); rd.nmask = r.nmask.data(); rd.len = r.len.data(); rd.stride2 = r.stride2; rd.stridem = r.stridem; }
-    void load_unit(const AgUnitInput& i) { in = i; }
+    std::vector<u32> own_cm_start; std::vector<ag_cm> own_cm;
+    void load_unit(const AgUnitInput& i) {
+        in = i;
+        if (!in.cm_start) {   // the product derives the position-ordered contiMer table on the device (k_cm_count / k_cm_fill / k_cm_sort)
+            ag_expand_contimers(in.threads, in.n_threads, in.chain_pos, in.n_cm, in.n_pos, own_cm_start, own_cm);
+            in.cm_start = own_cm_start.data(); in.cm = own_cm.data();
+        }
+    }
 
     ag_cmtab cmt() const { ag_cmtab t; t.start = in.cm_start; t.cm = in.cm; return t; }
     // same single-candidate shortcut as the kernels' for_candidates_fast

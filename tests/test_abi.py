@@ -34,7 +34,7 @@ def test_python_binding_covers_the_header(lib):
 
 def test_struct_sizes():
     assert ctypes.sizeof(ag.Params) == 16
-    assert ctypes.sizeof(ag.UnitView) == 88
+    assert ctypes.sizeof(ag.UnitView) == 104
 
 
 def test_no_cpu_fallback(lib):

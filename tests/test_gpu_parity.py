@@ -72,7 +72,8 @@ def test_run_unit_files_is_the_five_calls(ag, harness, workdir):
 
 
 def test_array_level_equals_file_level(ag, harness, workdir):
-    """Feeding the staged packed arrays back through ag_begin_unit / ag_set_contimers / ag_add_alignments gives the same FASTA."""
+    """Feeding the staged packed arrays back through ag_begin_unit / ag_set_contimers (explicit contiMer table) or ag_set_contig_threads
+    (compact form, table derived on the device) / ag_add_alignments gives the same FASTA."""
     harness.synth(workdir, **cases.GOLDEN["mix"])
     harness.prepare_tmp(workdir)
     p = harness.read_command(workdir)
@@ -85,9 +86,16 @@ def test_array_level_equals_file_level(ag, harness, workdir):
     b.begin_unit(0, v.ref, v.n_ref)
     b.set_contimers(v.cm_start, v.cm, v.n_cm, v.chain_pos, v.chain_base, v.ref + v.n_ref, v.n_tail)
     b.add_alignments(v.aln, v.n_aln, v.ext, v.n_ext)
+    c = ag.Context(k=p["kMer"], insert_variation=p["insertVariation"], coverage=p["coverage"])   # compact form: contig threads
+    c.load_reads_fasta(os.path.join(workdir, "tmp", "_reads.fa"))
+    c.begin_unit(0, v.ref, v.n_ref)
+    c.set_contig_threads(v.threads, v.n_threads, v.chain_pos, v.chain_base, v.n_cm, v.ref + v.n_ref, v.n_tail)
+    c.add_alignments(v.aln, v.n_aln, v.ext, v.n_ext)
     b.build(); b.extend()
+    c.build(); c.extend()
     a.build(); a.extend()
     assert a.text(1) == b.text(1) and a.text(2) == b.text(2) and len(a.text(1)) > 0
+    assert c.text(1) == b.text(1) and c.text(2) == b.text(2)
     g = os.path.join(os.path.dirname(__file__), "golden", "mix")
     assert b.text(1) == open(os.path.join(g, "_pre_extended_contigs.0.fa"), "rb").read()
     assert b.text(2) == open(os.path.join(g, "_extended_contigs.0.fa"), "rb").read()

@@ -1,0 +1,32 @@
+"""Build tuning variants of the library (compile-time knobs of the tile sweeps) into aligngraph_b200/_variants/lib_<name>.so;
+tools/variants.sh then runs bench.py against each of them on the GPU box (AG_LIB_PATH selects the library)."""
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from aligngraph_b200 import build as b  # noqa: E402
+
+VARIANTS = {
+    "minb5": ["-DAG_NODES_MINB=5"],
+    "minb4": ["-DAG_NODES_MINB=4"],
+    "minb4_scap3": ["-DAG_NODES_MINB=4", "-DAG_NODE_SCAP=3"],
+    "minb5_chunk128": ["-DAG_NODES_MINB=5", "-DAG_NCHUNK_NODES=128"],
+    "minb6_chunk32": ["-DAG_NODES_MINB=6", "-DAG_NCHUNK_NODES=32"],
+}
+
+
+def main(names):
+    out = os.path.join(b.HERE, "_variants")
+    os.makedirs(out, exist_ok=True)
+    for name in names or VARIANTS:
+        lib = os.path.join(out, f"lib_{name}.so")
+        cmd = ["nvcc", *b.ARCH, *b.COMMON, *VARIANTS[name], "-shared", "-o", lib,
+               os.path.join(b.CSRC, "ag_device.cu"), os.path.join(b.CSRC, "ag_host.cpp"), os.path.join(b.CSRC, "ag_capi.cpp")]
+        subprocess.run(cmd, check=True)
+        print(lib)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])
