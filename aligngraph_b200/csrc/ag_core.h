@@ -310,9 +310,31 @@ template <class F> AG_HD void ag_for_candidates(const ag_cmtab& t, u32 pos, u32 
 #define AG_NODE_SCAP 2
 #endif
 enum { AG_F_CID0 = 0, AG_F_COFF0 = 1, AG_F_MOFF = 2, AG_F_COV = 3, AG_F_CNT = 4, AG_F_SREAD = 9, AG_F_SL = 10, AG_F_SUCC = 11, AG_NF = 12 };
+// A thread's slots.  On the device they sit in shared memory and are addressed through a 32-bit shared-space address with ld/st.shared
+// (the address stays in one register; generic pointers into dynamic shared memory make the compiler re-derive the window base over and
+// over); the host emulation uses a plain array.  Word index of (field, slot) = field * fstride + slot * nstride.
 struct ag_slots {
+#ifdef __CUDACC__   // nvcc (both passes see the same layout; the host pass never executes these)
+    u32 saddr;
+    static constexpr u32 fstride = AG_NODE_SCAP * AG_TILE, nstride = AG_TILE;
+    __host__ __device__ __forceinline__ u32 ld(u32 field, u32 i) const {
+        u32 v = 0;
+#ifdef __CUDA_ARCH__
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr + (field * fstride + i * nstride) * 4u));
+#endif
+        return v;
+    }
+    __host__ __device__ __forceinline__ void st(u32 field, u32 i, u32 v) const {
+#ifdef __CUDA_ARCH__
+        asm volatile("st.shared.u32 [%0], %1;" :: "r"(saddr + (field * fstride + i * nstride) * 4u), "r"(v) : "memory");
+#endif
+    }
+#else
     u32* base; u32 fstride, nstride;
-    AG_HD u32& f(u32 field, u32 i) const { return base[field * fstride + i * nstride]; }
+    inline u32 ld(u32 field, u32 i) const { return base[field * fstride + i * nstride]; }
+    inline void st(u32 field, u32 i, u32 v) const { base[field * fstride + i * nstride] = v; }
+#endif
+    AG_HD void inc(u32 field, u32 i) const { st(field, i, ld(field, i) + 1u); }
 };
 struct ag_plist { u32 n, ovf_head, ovf_tail; };  // n counts slot nodes + pool nodes
 struct ag_ovfpool { ag_nodeb* node; u32* next; u32* count; u32 cap; int* err; };
@@ -345,16 +367,15 @@ AG_HD u32 ag_pool_new(ag_plist& pl, const ag_ovfpool& pool, const ag_nodem& c, b
 }
 
 // One candidate of one touch on a slot-mode position: first-compatible lookup, bump or create (AG:1375-1389 / AG:1493-1506).
-// Returns the item index (stable: lists only grow at the tail); oslot = pool slot of the item, NONE when it sits in a slot.
-AG_HD u32 ag_touch_slots(ag_plist& pl, const ag_slots& sv, const ag_ovfpool& pool, const ag_nodem& c, bool bump, int code, u32 sread, u32 soff_len, int iv, u32& oslot) {
-    oslot = AG_NONE;
+// Returns the item index (stable: lists only grow at the tail).
+AG_HD u32 ag_touch_slots(ag_plist& pl, const ag_slots& sv, const ag_ovfpool& pool, const ag_nodem& c, bool bump, int code, u32 sread, u32 soff_len, int iv) {
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
     for (u32 i = 0; i < (u32)AG_NODE_SCAP; i++) {   // fixed trip count: slot addresses become immediates
         if (i >= pl.n) break;
-        if (ag_compat23(c.cid0, c.coff0, c.moff, sv.f(AG_F_CID0, i), sv.f(AG_F_COFF0, i), sv.f(AG_F_MOFF, i), iv)) {
-            if (bump) { sv.f(AG_F_COV, i)++; if (code >= 0) sv.f(AG_F_CNT + (u32)code, i)++; }
+        if (ag_compat23(c.cid0, c.coff0, c.moff, sv.ld(AG_F_CID0, i), sv.ld(AG_F_COFF0, i), sv.ld(AG_F_MOFF, i), iv)) {
+            if (bump) { sv.inc(AG_F_COV, i); if (code >= 0) sv.inc(AG_F_CNT + (u32)code, i); }
             return i;
         }
     }
@@ -362,102 +383,90 @@ AG_HD u32 ag_touch_slots(ag_plist& pl, const ag_slots& sv, const ag_ovfpool& poo
         u32 i = AG_NODE_SCAP;
         for (u32 o = pl.ovf_head; o != AG_NONE; o = pool.next[o], i++) {
             ag_nodeb* h = &pool.node[o];
-            if (ag_compat23(c.cid0, c.coff0, c.moff, h->cid0, h->coff0, h->moff, iv)) { if (bump) { h->cov++; if (code >= 0) h->cnt[code]++; } oslot = o; return i; }
+            if (ag_compat23(c.cid0, c.coff0, c.moff, h->cid0, h->coff0, h->moff, iv)) { if (bump) { h->cov++; if (code >= 0) h->cnt[code]++; } return i; }
         }
     }
     const u32 i = pl.n;
     if (i < (u32)AG_NODE_SCAP) {
-        sv.f(AG_F_CID0, i) = c.cid0; sv.f(AG_F_COFF0, i) = c.coff0; sv.f(AG_F_MOFF, i) = c.moff;
-        sv.f(AG_F_COV, i) = bump ? 1u : 0u;
-        for (u32 j = 0; j < 5; j++) sv.f(AG_F_CNT + j, i) = (bump && code == (int)j) ? 1u : 0u;
-        sv.f(AG_F_SREAD, i) = sread; sv.f(AG_F_SL, i) = soff_len; sv.f(AG_F_SUCC, i) = 0;
-    } else {
-        oslot = ag_pool_new(pl, pool, c, bump, code, sread, soff_len);
-        if (oslot == AG_NONE) return i;
-    }
+        sv.st(AG_F_CID0, i, c.cid0); sv.st(AG_F_COFF0, i, c.coff0); sv.st(AG_F_MOFF, i, c.moff);
+        sv.st(AG_F_COV, i, bump ? 1u : 0u);
+        for (u32 j = 0; j < 5; j++) sv.st(AG_F_CNT + j, i, (bump && code == (int)j) ? 1u : 0u);
+        sv.st(AG_F_SREAD, i, sread); sv.st(AG_F_SL, i, soff_len); sv.st(AG_F_SUCC, i, 0u);
+    } else if (ag_pool_new(pl, pool, c, bump, code, sread, soff_len) == AG_NONE) return i;
     pl.n = i + 1;
     return i;
 }
 
 // the same on a position that holds several contiMers: every node is a pool record and all three clauses are evaluated
-AG_HD u32 ag_touch_pool(ag_plist& pl, const ag_ovfpool& pool, const ag_nodem& c, bool bump, int code, u32 sread, u32 soff_len, int iv, u32& oslot) {
+AG_HD u32 ag_touch_pool(ag_plist& pl, const ag_ovfpool& pool, const ag_nodem& c, bool bump, int code, u32 sread, u32 soff_len, int iv) {
     u32 i = 0;
     for (u32 o = pl.ovf_head; o != AG_NONE; o = pool.next[o], i++)
-        if (ag_compat_b(c, pool.node[o], iv)) { ag_nodeb* h = &pool.node[o]; if (bump) { h->cov++; if (code >= 0) h->cnt[code]++; } oslot = o; return i; }
-    oslot = ag_pool_new(pl, pool, c, bump, code, sread, soff_len);
-    if (oslot != AG_NONE) pl.n = i + 1;
+        if (ag_compat_b(c, pool.node[o], iv)) { ag_nodeb* h = &pool.node[o]; if (bump) { h->cov++; if (code >= 0) h->cnt[code]++; } return i; }
+    if (ag_pool_new(pl, pool, c, bump, code, sread, soff_len) != AG_NONE) pl.n = i + 1;
     return i;
 }
 
-// record "the call that bumped (item, oslot) continues on item `nb` of the next position"
-AG_HD void ag_note_succ(const ag_slots& sv, const ag_ovfpool& pool, u32 item, u32 oslot, u32 nb) {
-    if (oslot != AG_NONE) pool.node[oslot].succ |= 1u << nb;
-    else if (item < (u32)AG_NODE_SCAP) sv.f(AG_F_SUCC, item) |= 1u << nb;   // (an item beyond the slots without a pool slot: pool exhausted, the sweep is repeated)
+// record "the call that bumped item `item` of this (slot-mode) position continues on item `nb` of the next position"
+AG_HD void ag_note_succ(const ag_plist& pl, const ag_slots& sv, const ag_ovfpool& pool, u32 item, u32 nb) {
+    if (item < (u32)AG_NODE_SCAP) { sv.st(AG_F_SUCC, item, sv.ld(AG_F_SUCC, item) | (1u << nb)); return; }
+    u32 o = pl.ovf_head;                                   // rare: the item lives in the pool chain
+    for (u32 i = AG_NODE_SCAP; i < item && o != AG_NONE; i++) o = pool.next[o];
+    if (o != AG_NONE) pool.node[o].succ |= 1u << nb;        // (NONE: pool exhausted, the sweep is repeated)
 }
 
-// What one lane (= one unit position q) does with one alignment of its tile during the node sweep.
-//   want: a call starts at q (kind-1 touch), so an edge to the alignment's item at the call's successor position is due;
-//   sh:   the item this lane resolved, offered to the lane on its left as that successor item — only for CLEAN alignments (successor
-//         position = q + 1, i.e. the next lane, and exactly one candidate per touch); NONE otherwise.
-// An edge that cannot be settled through (want, sh of the right neighbour) flags the tile for the generic edge sweep: flag 1 when the
+// What one lane (= one unit position q) does with one alignment of its tile during the node sweep.  Result:
+//   want:   a call starts at q (kind-1 touch), so an edge to the alignment's item at the call's successor position is due;
+//   return: the item this lane resolved, offered to the lane on its left as that successor item — only for CLEAN alignments (successor
+//           position = q + 1, i.e. the next lane, and exactly one candidate per touch); NONE otherwise.
+// An edge that cannot be settled through (want, item of the right neighbour) flags the tile for the generic edge sweep: flag 1 when the
 // alignment is not clean (the generic sweep then handles exactly the non-clean alignments of the tile), flag 2 when a clean alignment
 // met an item index >= 32 (the generic sweep then redoes every call of the tile; edges are de-duplicated).
-struct ag_lane_out { u32 sh, item, oslot; bool want; };
 
 // rare cases (several contiMers on either side, multi-segment CIGARs, gap chains): the reference's nested candidate enumeration
 // (AG:1369-1477).  Out of line and by value so that the hot path keeps its list state in registers.
 struct ag_gen_ret { ag_plist pl; bool want; };
 template <class CodeF>
-AG_HD_COLD ag_gen_ret ag_lane_generic(ag_plist pl, const ag_slots sv, const ag_ovfpool pool, const ag_cmtab cmt, const ag_cm1 ca, const ag_touch t, u32 q, u32 sread, int iv,
-                                      CodeF codef) {
+AG_HD_COLD ag_gen_ret ag_lane_generic(ag_plist pl, const ag_slots sv, const ag_ovfpool pool, const ag_cmtab cmt, const ag_cm1 ca, const ag_fast f, const ag_alnp* ap,
+                                      const ag_seg* ext, u32 q, u32 k, int iv, bool force_generic, CodeF codef) {
+    ag_gen_ret r; r.pl = pl; r.want = false;
+    ag_touch t;
+    if (f.simple && !force_generic) t = ag_fast_touch(f, q, k);
+    else { t = ag_locate(*ap, ext, q, k); if (!t.kind) return r; }
     int code = -1;
     if (t.kind == 1 && t.slen) code = codef(t.soff);
     const u32 sl = t.soff | (t.slen << 16);
     const bool bump = t.kind == 1;
     const bool slots = ca.cid != AG_CM_MANY;
     ag_for_candidates(cmt, q, t.mate, [&](const ag_nodem& c) {
-        u32 o;
-        if (slots) ag_touch_slots(pl, sv, pool, c, bump, code, sread, sl, iv, o);
-        else ag_touch_pool(pl, pool, c, bump, code, sread, sl, iv, o);
+        if (slots) ag_touch_slots(pl, sv, pool, c, bump, code, f.read, sl, iv);
+        else ag_touch_pool(pl, pool, c, bump, code, f.read, sl, iv);
     });
-    ag_gen_ret r; r.pl = pl; r.want = bump;
+    r.pl = pl; r.want = bump;
     return r;
 }
 
-AG_HD_COLD ag_touch ag_locate_cold(const ag_alnp* ap, const ag_seg* ext, u32 q, u32 k) { return ag_locate(*ap, ext, q, k); }
 AG_HD u32 ag_fast_mate(const ag_fast& f, u32 q) { return (q - f.mlo < f.mlen) ? q + f.mdelta : AG_NONE; }
-
-// the common case: simple alignment (one M segment per mate), at most one contiMer at q (ca) and at the mate position (cb)
-template <class CodeF>
-AG_HD void ag_lane_fast(ag_lane_out& out, ag_plist& pl, const ag_slots& sv, const ag_ovfpool& pool, const ag_cm1& ca, const ag_cm1& cb, const ag_fast& f, u32 q, u32 mate,
-                        u32 k, int iv, CodeF codef) {
-    const u32 d = q - f.lo, len = f.lsrc_len >> 16, a = (f.lsrc_len & 0xFFFFu) + d;
-    const bool bump = d < f.span;                             // a call starts here (kind 1); else the stand-alone k2 of the last call
-    const u32 slen = bump ? k : ag_min_u32(k, len - a);
-    int code = -1;
-    if (bump && slen) code = codef(a);
-    ag_nodem c; c.cid = ca.cid; c.coff = ca.coff; c.cid0 = cb.cid; c.coff0 = cb.coff; c.moff = mate;
-    out.item = ag_touch_slots(pl, sv, pool, c, bump, code, f.read, a | (slen << 16), iv, out.oslot);
-    out.sh = out.item; out.want = bump;
-}
 
 // everything one lane does with one tile alignment whose touch range contains q (q - f.lo <= f.span)
 template <class CodeF>
-AG_HD void ag_lane_touch(ag_lane_out& out, ag_plist& pl, const ag_slots& sv, const ag_ovfpool& pool, const ag_cmtab& cmt, const ag_cm1* cm1, const ag_cm1& ca, const ag_fast& f,
-                         const ag_alnp* ap, const ag_seg* ext, u32 q, u32 k, int iv, bool force_generic, CodeF codef) {
-    out.sh = AG_NONE; out.item = 0; out.oslot = AG_NONE; out.want = false;
-    if ((f.simple & AG_FAST_CLEAN) && !force_generic) {   // one candidate by construction: neither ca nor cb can be AG_CM_MANY
+AG_HD u32 ag_lane_touch(bool& want, ag_plist& pl, const ag_slots& sv, const ag_ovfpool& pool, const ag_cmtab& cmt, const ag_cm1* cm1, const ag_cm1& ca, const ag_fast& f,
+                        const ag_alnp* ap, const ag_seg* ext, u32 q, u32 k, int iv, bool force_generic, CodeF codef) {
+    if ((f.simple & AG_FAST_CLEAN) && !force_generic) {
+        // the common case: one M segment per mate and at most one contiMer at q and at the mate position => exactly one candidate
         const u32 mate = ag_fast_mate(f, q);
-        ag_cm1 cb; cb.cid = cb.coff = AG_NONE;
-        if (mate != AG_NONE) cb = cm1[mate];
-        ag_lane_fast(out, pl, sv, pool, ca, cb, f, q, mate, k, iv, codef);
-        return;
+        ag_nodem c; c.cid = ca.cid; c.coff = ca.coff; c.cid0 = c.coff0 = AG_NONE; c.moff = mate;
+        if (mate != AG_NONE) { const ag_cm1 cb = cm1[mate]; c.cid0 = cb.cid; c.coff0 = cb.coff; }
+        const u32 d = q - f.lo, len = f.lsrc_len >> 16, a = (f.lsrc_len & 0xFFFFu) + d;
+        const bool bump = d < f.span;                             // a call starts here (kind 1); else the stand-alone k2 of the last call
+        const u32 slen = bump ? k : ag_min_u32(k, len - a);
+        int code = -1;
+        if (bump && slen) code = codef(a);
+        want = bump;
+        return ag_touch_slots(pl, sv, pool, c, bump, code, f.read, a | (slen << 16), iv);
     }
-    ag_touch t;
-    if (f.simple && !force_generic) t = ag_fast_touch(f, q, k);
-    else { t = ag_locate_cold(ap, ext, q, k); if (!t.kind) return; }
-    const ag_gen_ret r = ag_lane_generic(pl, sv, pool, cmt, ca, t, q, f.read, iv, codef);
-    pl = r.pl; out.want = r.want;
+    const ag_gen_ret r = ag_lane_generic(pl, sv, pool, cmt, ca, f, ap, ext, q, k, iv, force_generic, codef);
+    pl = r.pl; want = r.want;
+    return AG_NONE;
 }
 
 // first node of the FINAL list [nb, nb + n) compatible with candidate c

@@ -163,9 +163,10 @@ struct DevView {
     ag_alnp* alnp; ag_fast* fast; u32* ntiles; u32* key_off;
     u32* keys; u32* vals; u32* tile_cnt; u32* tile_start; u32 n_tiles;
     ag_ovfpool ovf;
-    u32* ticket; unsigned long long* tile_state; u32* tile_flag; u32* n_nodes_out; u32 node_cap;
-    u32* pos_node;
-    ag_nodec* node_c; ag_nodew* node_w; u32* node_sref; u32* node_pos; u32* node_cc;
+    u32* tile_flag; u32* tile_base; u32* tile_nodes; u32* tile_prefix; u32* pool_count; u32 node_cap;
+    u32* pos_pool; u32* pos_node;
+    ag_nodec* pool_c; ag_nodew* pool_w; u32* pool_sref; u32* pool_pos; u32* pool_cc;      // node records in sweep order (tile blocks in arbitrary order)
+    ag_nodec* node_c; ag_nodew* node_w; u32* node_sref; u32* node_pos; u32* node_cc;      // the same in position order (k_succ)
     u32* eovf_head; u32* eovf_target; u32* eovf_next; u32* eovf_count; u32 eovf_cap;
     u32* walk_next; u32* parent; u32* cmin; u32* cmax;
     u32* cand_rank; u32* cand_node; u32* cand_label;
@@ -268,7 +269,7 @@ __global__ void k_cm1(DevView d, ag_cm1* out, unsigned char* pos_term, u32* many
 
 // ---------------------------------------------------------------------------------------------------------------------------
 // k_build: the node sweep, with the edges of the common case settled in the same pass.
-//   * one CTA per tile (handed out by ticket), 8 warps x (31 owned positions + 1 halo lane), one thread per position;
+//   * one CTA per tile, 8 warps x (31 owned positions + 1 halo lane), one thread per position;
 //   * the tile's alignments arrive sorted by global alignment order and are staged through shared memory in chunks (touch
 //     arithmetic pre-reduced to ag_fast by k_prep, the left mates' packed bases next to them); each warp keeps only the entries that
 //     overlap its 32 positions (ballot) and every thread replays the reference's first-compatible clustering on a node list held in
@@ -277,8 +278,8 @@ __global__ void k_cm1(DevView d, ag_cm1* out, unsigned char* pos_term, u32* many
 //     the NEXT lane resolves for the same alignment in the same iteration: one shuffle yields the edge (AG:1590-1623), kept as a bit per
 //     successor item until the final node indices exist (k_succ).  Calls that cannot be settled this way (multi-segment CIGARs, several
 //     contiMers on a side, item >= 32) flag the tile for the generic edge sweep k_edges;
-//   * the tiles' node counts are chained by a decoupled look-back, so nodes are written straight into their final, position-ordered
-//     records — no intermediate pool, no second pass.
+//   * a tile's nodes go out as ONE block of final-format records at an atomically reserved offset (no ordering between tiles, nobody
+//     waits); k_succ moves the blocks into position order while it expands the successor bits.
 // ---------------------------------------------------------------------------------------------------------------------------
 #ifndef AG_NCHUNK
 #define AG_NCHUNK 128
@@ -290,39 +291,37 @@ __global__ void k_cm1(DevView d, ag_cm1* out, unsigned char* pos_term, u32* many
 #define AG_EDGES_MINB 5
 #endif
 #ifndef AG_NCHUNK_NODES
-#define AG_NCHUNK_NODES 64
+#define AG_NCHUNK_NODES 128
 #endif
 constexpr int NCHUNK = AG_NCHUNK;            // chunk of tile alignments staged per round in k_edges
-constexpr int NCHUNK_N = AG_NCHUNK_NODES;    // ... in k_build (smaller: its shared memory also holds the node lists and the reads)
+constexpr int NCHUNK_N = AG_NCHUNK_NODES;    // ... in k_build
 constexpr int NODE_SCAP = AG_NODE_SCAP;                         // nodes per position kept in shared memory; more spill to the pool
 constexpr int NODES_SMEM = AG_NF * NODE_SCAP * AG_TILE * 4;     // bytes of dynamic shared memory for the node lists
 constexpr int READ_WORDS_MAX = 24;                              // stage reads of up to 256 bases (16 + 8 words) per chunk entry
-constexpr unsigned long long ST_AGG = 1ull << 62, ST_INC = 2ull << 62, ST_VAL = (1ull << 62) - 1;
 
 __device__ __forceinline__ void emit_node(const DevView& d, u32 v, u32 q, char refb, u32 cid, u32 coff, u32 cid0, u32 coff0, u32 moff, u32 cov, const u32* cnt,
                                           u32 sread, u32 sl, u32 succ) {
     ag_nodec c; c.cid = cid; c.coff = coff; c.cid0 = cid0; c.coff0 = coff0;
-    d.node_c[v] = c;
+    d.pool_c[v] = c;
     ag_nodew w; w.succ0 = succ; w.succ1 = AG_NONE; w.moff = moff; w.misc = ag_node_misc(cid, coff, cov, cnt, refb, d.coverage);  // succ0 holds the item mask until k_succ
-    d.node_w[v] = w;
-    *reinterpret_cast<uint2*>(d.node_sref + 2 * (size_t)v) = make_uint2(sread, sl);
-    d.node_pos[v] = q;
-    if (d.node_cc) { u32* o = d.node_cc + 6 * (size_t)v; o[0] = cov; for (int j = 0; j < 5; j++) o[1 + j] = cnt[j]; }
+    d.pool_w[v] = w;
+    *reinterpret_cast<uint2*>(d.pool_sref + 2 * (size_t)v) = make_uint2(sread, sl);
+    d.pool_pos[v] = q;
+    if (d.pool_cc) { u32* o = d.pool_cc + 6 * (size_t)v; o[0] = cov; for (int j = 0; j < 5; j++) o[1 + j] = cnt[j]; }
 }
 
 __global__ void __launch_bounds__(AG_TILE, AG_NODES_MINB) k_build(DevView d) {
-    extern __shared__ u32 s_nodes[];
-    u32* const s_reads = s_nodes + AG_NF * NODE_SCAP * AG_TILE;   // [NCHUNK_N][rw] raw words of every chunk entry's left mate (bases, then mask)
+    extern __shared__ u32 s_dyn[];                                  // [AG_NF][NODE_SCAP][AG_TILE] node slots, then [NCHUNK_N][rw] staged read words
     __shared__ ag_fast s_f[NCHUNK_N];
     __shared__ u32 s_idx[NCHUNK_N];
     __shared__ u32 s_scan[33];
-    __shared__ u32 s_base, s_tile, s_flag, s_total;
-    if (threadIdx.x == 0) { s_tile = atomicAdd(d.ticket, 1u); s_flag = 0; }
-    __syncthreads();
-    const u32 tile = s_tile, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ u32 s_base, s_flag;
+    constexpr u32 READS0 = AG_NF * NODE_SCAP * AG_TILE;             // word offset of the staged reads inside s_dyn
+    const u32 tile = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 wq0 = tile * AG_TPOS + warp * AG_WPOS, q = wq0 + lane;   // lane 31 = halo: first position of the next warp / tile
     const bool active = q < d.n_ref, owner = active && lane < AG_WPOS;
-    ag_slots sv; sv.base = s_nodes + threadIdx.x; sv.fstride = NODE_SCAP * AG_TILE; sv.nstride = AG_TILE;
+    if (threadIdx.x == 0) s_flag = 0;
+    ag_slots sv; sv.saddr = (u32)__cvta_generic_to_shared(s_dyn + threadIdx.x);
     ag_plist pl; pl.n = 0; pl.ovf_head = pl.ovf_tail = AG_NONE;
     ag_cm1 ca; ca.cid = ca.coff = AG_NONE;
     if (active) ca = d.cm1[q];
@@ -330,19 +329,22 @@ __global__ void __launch_bounds__(AG_TILE, AG_NODES_MINB) k_build(DevView d) {
     const u32 kb = d.tile_start[tile], ke = d.tile_start[tile + 1];
     for (u32 c0 = kb; c0 < ke; c0 += NCHUNK_N) {
         const u32 cn = min((u32)NCHUNK_N, ke - c0);
-        if (threadIdx.x < cn) {
+        if (c0 != kb) __syncthreads();                             // everybody is done with the previous chunk
+        if (threadIdx.x < cn) {   // stage entry: prepared record + the left mate's packed bases and non-ACGT plane (one barrier per chunk)
             const u32 idx = d.vals[c0 + threadIdx.x];
+            const ag_fast f = d.fast[idx];
             s_idx[threadIdx.x] = idx;
-            s_f[threadIdx.x] = d.fast[idx];
+            s_f[threadIdx.x] = f;
+            if (rw) {
+                const u32 read = f.read >> 1;
+                const u32* __restrict__ gb = d.reads.bases + (u64)read * s2;
+                const u32* __restrict__ gm = d.reads.nmask + (u64)read * d.reads.stridem;
+                u32* o = s_dyn + READS0 + threadIdx.x * rw;
+                for (u32 j = 0; j < s2; j++) o[j] = gb[j];
+                for (u32 j = s2; j < rw; j++) o[j] = gm[j - s2];
+            }
         }
         __syncthreads();
-        if (rw) {  // stage the left mates' packed bases + non-ACGT plane: two dependent global loads per touch become shared-memory reads
-            for (u32 w = threadIdx.x; w < cn * rw; w += AG_TILE) {
-                const u32 e = w / rw, j = w - e * rw, read = s_f[e].read >> 1;
-                s_reads[w] = j < s2 ? d.reads.bases[(u64)read * s2 + j] : d.reads.nmask[(u64)read * d.reads.stridem + (j - s2)];
-            }
-            __syncthreads();
-        }
         for (u32 r0 = 0; r0 < cn; r0 += 32) {
             // which of these 32 entries touch any of the warp's 32 positions?
             bool ov = false;
@@ -352,69 +354,52 @@ __global__ void __launch_bounds__(AG_TILE, AG_NODES_MINB) k_build(DevView d) {
                 const u32 a = r0 + (u32)__ffs((int)mask) - 1;
                 mask &= mask - 1;
                 const ag_fast f = s_f[a];
-                ag_lane_out out; out.sh = AG_NONE; out.item = 0; out.oslot = AG_NONE; out.want = false;
+                u32 item = AG_NONE; bool want = false;
                 if (active && q - f.lo <= f.span) {
-                    const u32* rd = s_reads + a * rw;
-                    const ag_reads reads = d.reads;
+                    const u32 roff = READS0 + a * rw;
                     const u32 fread = f.read, flen = f.lsrc_len >> 16;
+                    const ag_reads reads = d.reads;
                     auto codef = [=](u32 soff) -> int {
                         if (!rw) return reads.code(fread, flen, soff);
                         const u32 rc = fread & 1, i = rc ? flen - 1 - soff : soff;
-                        if ((rd[s2 + (i >> 5)] >> (i & 31)) & 1) return 4;
-                        const u32 c = (rd[i >> 4] >> ((i & 15) * 2)) & 3;
+                        if ((s_dyn[roff + s2 + (i >> 5)] >> (i & 31)) & 1) return 4;
+                        const u32 c = (s_dyn[roff + (i >> 4)] >> ((i & 15) * 2)) & 3;
                         return rc ? 3 - (int)c : (int)c;
                     };
-                    ag_lane_touch(out, pl, sv, d.ovf, d.cmt, d.cm1, ca, f, d.alnp + s_idx[a], d.ext, q, (u32)d.k, d.iv, false, codef);
+                    item = ag_lane_touch(want, pl, sv, d.ovf, d.cmt, d.cm1, ca, f, d.alnp + s_idx[a], d.ext, q, (u32)d.k, d.iv, false, codef);
                 }
                 // the call that starts at q continues on the item the next lane resolved for this alignment
-                const u32 nb = __shfl_down_sync(0xFFFFFFFFu, out.sh, 1);
-                if (out.want && lane < AG_WPOS) {
-                    if (out.sh != AG_NONE && nb < 32u) ag_note_succ(sv, d.ovf, out.item, out.oslot, nb);
-                    else if (out.sh == AG_NONE) atomicOr(&s_flag, 1u);   // not a clean alignment
-                    else atomicOr(&s_flag, 2u);                          // successor item index does not fit the mask
+                const u32 nb = __shfl_down_sync(0xFFFFFFFFu, item, 1);
+                if (want && lane < AG_WPOS) {
+                    if (item != AG_NONE && nb < 32u) ag_note_succ(pl, sv, d.ovf, item, nb);
+                    else atomicOr(&s_flag, item == AG_NONE ? 1u : 2u);   // 1: not a clean alignment; 2: successor item does not fit the mask
                 }
             }
         }
-        __syncthreads();
     }
-    // ---- the tile's first node index: decoupled look-back over the tiles' node counts (every predecessor has started: tickets) ----
+    // ---- the tile's nodes go out as one block at an atomically reserved offset ----
     u32 total; const u32 ex = block_excl_scan(owner ? pl.n : 0u, s_scan, total);
     if (threadIdx.x == 0) {
-        volatile unsigned long long* st = d.tile_state;
-        unsigned long long excl = 0;
-        if (tile == 0) st[0] = ST_INC | total;
-        else {
-            st[tile] = ST_AGG | total;
-            for (u32 t = tile; t-- > 0;) {
-                unsigned long long x;
-                do { x = st[t]; } while ((x >> 62) == 0);
-                excl += x & ST_VAL;
-                if ((x >> 62) == 2) break;
-            }
-            st[tile] = ST_INC | (excl + total);
-        }
-        u32 b = (u32)excl;
-        if (excl + total > d.node_cap) { *d.err = 3; b = AG_NONE; }
-        s_base = b; s_total = (u32)(excl + total);
+        u32 b = total ? atomicAdd(d.pool_count, total) : 0u;
+        d.tile_base[tile] = b; d.tile_nodes[tile] = total;
         if (s_flag) d.tile_flag[tile] = s_flag;
-        if (tile == d.n_tiles - 1) *d.n_nodes_out = (u32)(excl + total);
+        if (total && (unsigned long long)b + total > d.node_cap) { *d.err = 3; b = AG_NONE; }
+        s_base = b;
     }
     __syncthreads();
-    if (tile == d.n_tiles - 1)  // CSR tail: the contig-insertion positions behind the unit hold no nodes
-        for (u32 p = d.n_ref + threadIdx.x; p <= d.n_pos; p += AG_TILE) d.pos_node[p] = s_total;
     if (!owner) return;
-    if (s_base == AG_NONE) { d.pos_node[q] = 0; return; }
+    if (s_base == AG_NONE) { d.pos_pool[q] = 0; return; }
     u32 v = s_base + ex;
-    d.pos_node[q] = v;
+    d.pos_pool[q] = v;
     if (!pl.n) return;
     const char refb = (char)d.ref[q];
     if (ca.cid != AG_CM_MANY) {
         const u32 nloc = pl.n < (u32)NODE_SCAP ? pl.n : (u32)NODE_SCAP;
         for (u32 i = 0; i < nloc; i++, v++) {
             u32 cnt[5];
-            for (u32 j = 0; j < 5; j++) cnt[j] = sv.f(AG_F_CNT + j, i);
-            emit_node(d, v, q, refb, ca.cid, ca.coff, sv.f(AG_F_CID0, i), sv.f(AG_F_COFF0, i), sv.f(AG_F_MOFF, i), sv.f(AG_F_COV, i), cnt, sv.f(AG_F_SREAD, i), sv.f(AG_F_SL, i),
-                      sv.f(AG_F_SUCC, i));
+            for (u32 j = 0; j < 5; j++) cnt[j] = sv.ld(AG_F_CNT + j, i);
+            emit_node(d, v, q, refb, ca.cid, ca.coff, sv.ld(AG_F_CID0, i), sv.ld(AG_F_COFF0, i), sv.ld(AG_F_MOFF, i), sv.ld(AG_F_COV, i), cnt, sv.ld(AG_F_SREAD, i),
+                      sv.ld(AG_F_SL, i), sv.ld(AG_F_SUCC, i));
         }
     }
     for (u32 o = pl.ovf_head; o != AG_NONE; o = d.ovf.next[o], v++) {
@@ -424,33 +409,46 @@ __global__ void __launch_bounds__(AG_TILE, AG_NODES_MINB) k_build(DevView d) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
-// k_succ: successor-item bits -> successor node indices, subject to the contig-consistency predicate of AG:1600-1615
+// k_posfix / k_succ: tile blocks -> position order (final index = block's rank offset + index inside the block), successor-item
+// bits -> successor node indices, subject to the contig-consistency predicate of AG:1600-1615
 // ---------------------------------------------------------------------------------------------------------------------------
+__global__ void k_posfix(DevView d, u32 n_nodes) {
+    const u32 q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q > d.n_pos) return;
+    if (q >= d.n_ref) { d.pos_node[q] = n_nodes; return; }   // the contig-insertion positions behind the unit hold no nodes
+    const u32 t = q / AG_TPOS;
+    d.pos_node[q] = d.pos_pool[q] - d.tile_base[t] + d.tile_prefix[t];
+}
 __global__ void k_succ(DevView d, u32 n_nodes) {
-    const u32 v = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 v = blockIdx.x * blockDim.x + threadIdx.x;   // index in sweep order
     if (v >= n_nodes) return;
-    ag_nodew w = d.node_w[v];
+    const u32 q = d.pool_pos[v], t = q / AG_TPOS;
+    const u32 f = v - d.tile_base[t] + d.tile_prefix[t];   // index in position order
+    ag_nodew w = d.pool_w[v];
+    const ag_nodec x = d.pool_c[v];
     u32 mask = w.succ0, head = AG_NONE;
     w.succ0 = AG_NONE;
     if (mask) {
-        const u32 b1 = d.pos_node[d.node_pos[v] + 1];
-        const ag_nodec x = d.node_c[v];
+        const u32 p1 = d.pos_pool[q + 1], f1 = d.pos_node[q + 1];
         while (mask) {
-            const u32 t = b1 + (u32)__ffs((int)mask) - 1;
+            const u32 j = (u32)__ffs((int)mask) - 1;
             mask &= mask - 1;
-            if (!ag_edge_ok_c(x, d.node_c[t], d.iv)) continue;
-            if (w.succ0 == AG_NONE) w.succ0 = t;
-            else if (w.succ1 == AG_NONE) w.succ1 = t;
+            if (!ag_edge_ok_c(x, d.pool_c[p1 + j], d.iv)) continue;
+            const u32 tg = f1 + j;
+            if (w.succ0 == AG_NONE) w.succ0 = tg;
+            else if (w.succ1 == AG_NONE) w.succ1 = tg;
             else {
                 const u32 o = atomicAdd(d.eovf_count, 1u);
                 if (o >= d.eovf_cap) { *d.err = 4; break; }
-                d.eovf_target[o] = t; d.eovf_next[o] = head; head = o;
+                d.eovf_target[o] = tg; d.eovf_next[o] = head; head = o;
                 w.misc |= AG_NW_OVF;
             }
         }
     }
-    if (head != AG_NONE) d.eovf_head[v] = head;
-    d.node_w[v] = w;
+    if (head != AG_NONE) d.eovf_head[f] = head;
+    d.node_c[f] = x; d.node_w[f] = w; d.node_pos[f] = q;
+    *reinterpret_cast<uint2*>(d.node_sref + 2 * (size_t)f) = *reinterpret_cast<const uint2*>(d.pool_sref + 2 * (size_t)v);
+    if (d.node_cc) for (int j = 0; j < 6; j++) d.node_cc[6 * (size_t)f + j] = d.pool_cc[6 * (size_t)v + j];
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -826,7 +824,7 @@ struct AgDevice::Impl {
     u32 n_ref = 0, n_pos = 0, n_cm = 0, n_aln = 0;
     // build products
     DBuf<ag_alnp> alnp; DBuf<ag_fast> fast; DBuf<u32> ntiles, key_off, keys, vals, keys2, vals2, hist, tile_cnt, tile_start, tile_flag, many, many_prefix;
-    DBuf<unsigned long long> tile_state;
+    DBuf<u32> tile_base, tile_nodes, tile_prefix, pos_pool, pool_sref, pool_pos, pool_cc; DBuf<ag_nodec> pool_c; DBuf<ag_nodew> pool_w;
     DBuf<ag_nodeb> ovf_node; DBuf<u32> ovf_next, counters; DBuf<int> err;
     DBuf<u32> pos_node;
     DBuf<ag_nodec> node_c; DBuf<ag_nodew> node_w; DBuf<u32> node_sref, node_pos, node_cc;
@@ -838,7 +836,7 @@ struct AgDevice::Impl {
     u32 n_tiles = 0, n_keys = 0, n_nodes = 0;
     u32 node_cap = 0, ovf_cap = 0, eovf_cap = 0, walk_cap = 0;
     DevView view{};
-    // counters layout: [0] n_nodes, [1] ovf_count, [2] eovf_count, [3] walk_count, [4,5] materialise items, [6] tile ticket
+    // counters layout: [0] n_nodes (pool_count), [1] ovf_count, [2] eovf_count, [3] walk_count, [4,5] materialise items
 };
 
 AgDevice::AgDevice(int device) : m_(new Impl), dev_(device) {
@@ -859,11 +857,11 @@ AgDevice::~AgDevice() {
     DBuf<unsigned char>* b8[] = {&m.ref, &m.chain_base, &m.out_bases, &m.occ};
     for (auto* b : b8) b->release();
     DBuf<u32>* b32[] = {&m.cm_start, &m.chain_pos, &m.ntiles, &m.key_off, &m.keys, &m.vals, &m.keys2, &m.vals2, &m.hist, &m.tile_cnt,
-                        &m.tile_start, &m.tile_flag, &m.many, &m.many_prefix, &m.ovf_next, &m.counters, &m.pos_node, &m.node_sref, &m.node_pos, &m.node_cc, &m.eovf_head,
+                        &m.tile_start, &m.tile_flag, &m.tile_base, &m.tile_nodes, &m.tile_prefix, &m.pos_pool, &m.pool_sref, &m.pool_pos, &m.pool_cc, &m.many, &m.many_prefix, &m.ovf_next, &m.counters, &m.pos_node, &m.node_sref, &m.node_pos, &m.node_cc, &m.eovf_head,
                         &m.eovf_target, &m.eovf_next, &m.walk_next, &m.parent, &m.cmin, &m.cmax, &m.sel_start, &m.sel_tails};
     for (auto* b : b32) b->release();
     for (int i = 0; i < 4; i++) m.scanner.lvl[i].release();
-    m.cm.release(); m.cthreads.release(); m.aln.release(); m.ext.release(); m.alnp.release(); m.fast.release(); m.tile_state.release(); m.ovf_node.release(); m.err.release();
+    m.cm.release(); m.cthreads.release(); m.aln.release(); m.ext.release(); m.alnp.release(); m.fast.release(); m.pool_c.release(); m.pool_w.release(); m.ovf_node.release(); m.err.release();
     m.node_c.release(); m.node_w.release(); m.walks.release(); m.walks2.release(); m.cm1.release(); m.mat_chains.release(); m.mat_detours.release(); m.pos_term.release(); m.cand_rank.release(); m.cand_node.release(); m.cand_label.release(); m.fprev.release(); m.msuf.release(); m.mnode.release(); m.indeg.release(); m.fnext.release(); m.chain_a.release(); m.chain_b.release(); m.changed.release(); m.sel_off.release();
     m.h_walks.release(); m.h_bases.release(); m.h_occ.release();
     if (m.st) cudaStreamDestroy(m.st);
@@ -999,16 +997,15 @@ void AgDevice::build() {
     d.cmt.start = m.cm_start.p; d.cmt.cm = m.cm.p; d.chain_pos = m.chain_pos.p; d.chain_base = m.chain_base.p;
     d.aln = m.aln.p; d.n_aln = nA; d.ext = m.ext.p; d.k = k_; d.iv = iv_; d.coverage = cov_;
     m.alnp.ensure(nA + 1); m.fast.ensure(nA + 1); m.ntiles.ensure(nA + 1); m.key_off.ensure((size_t)nA + 2);
-    m.tile_cnt.ensure(m.n_tiles + 2); m.tile_start.ensure(m.n_tiles + 2); m.tile_flag.ensure(m.n_tiles + 2); m.tile_state.ensure(m.n_tiles + 2);
+    m.tile_cnt.ensure(m.n_tiles + 2); m.tile_start.ensure(m.n_tiles + 2); m.tile_flag.ensure(m.n_tiles + 2);
     m.pos_node.ensure((size_t)n_pos + 2);
     d.alnp = m.alnp.p; d.fast = m.fast.p; d.ntiles = m.ntiles.p; d.key_off = m.key_off.p;
-    d.tile_cnt = m.tile_cnt.p; d.tile_start = m.tile_start.p; d.n_tiles = m.n_tiles; d.tile_flag = m.tile_flag.p; d.tile_state = m.tile_state.p;
+    d.tile_cnt = m.tile_cnt.p; d.tile_start = m.tile_start.p; d.n_tiles = m.n_tiles; d.tile_flag = m.tile_flag.p;
     d.pos_node = m.pos_node.p;
     d.err = m.err.p;
     CK(cudaMemsetAsync(m.err.p, 0, sizeof(int), st));
     CK(cudaMemsetAsync(m.counters.p, 0, 8 * sizeof(u32), st));
     CK(cudaMemsetAsync(m.tile_cnt.p, 0, (m.n_tiles + 1) * sizeof(u32), st));
-    CK(cudaMemsetAsync(m.pos_node.p, 0, ((size_t)n_pos + 1) * sizeof(u32), st));
 
     m.cm1.ensure((size_t)n_pos + 2); d.cm1 = m.cm1.p; m.pos_term.ensure((size_t)n_pos + 2); d.pos_term = m.pos_term.p;
     m.many.ensure((size_t)n_pos + 2); m.many_prefix.ensure((size_t)n_pos + 2); d.many_prefix = m.many_prefix.p;
@@ -1056,15 +1053,16 @@ void AgDevice::build() {
     {
         Timer tm(st);
         if (!m.node_cap) m.node_cap = std::max<u32>(1u << 20, 3 * n_ref + (1u << 16));
+        m.tile_base.ensure(m.n_tiles + 2); m.tile_nodes.ensure(m.n_tiles + 2); m.tile_prefix.ensure(m.n_tiles + 2); m.pos_pool.ensure((size_t)n_pos + 2);
+        d.tile_base = m.tile_base.p; d.tile_nodes = m.tile_nodes.p; d.tile_prefix = m.tile_prefix.p; d.pos_pool = m.pos_pool.p;
         for (;;) {
-            m.node_c.ensure((size_t)m.node_cap + 1); m.node_w.ensure((size_t)m.node_cap + 1); m.node_sref.ensure(2 * (size_t)m.node_cap + 2); m.node_pos.ensure((size_t)m.node_cap + 1);
-            if (keep_counts_) m.node_cc.ensure(6 * (size_t)m.node_cap + 6);
+            m.pool_c.ensure((size_t)m.node_cap + 1); m.pool_w.ensure((size_t)m.node_cap + 1); m.pool_sref.ensure(2 * (size_t)m.node_cap + 2); m.pool_pos.ensure((size_t)m.node_cap + 1);
+            if (keep_counts_) m.pool_cc.ensure(6 * (size_t)m.node_cap + 6);
             if (!m.ovf_cap) m.ovf_cap = std::max<u32>(1u << 18, n_ref / 8);
             m.ovf_node.ensure(m.ovf_cap); m.ovf_next.ensure(m.ovf_cap);
-            d.node_c = m.node_c.p; d.node_w = m.node_w.p; d.node_sref = m.node_sref.p; d.node_pos = m.node_pos.p; d.node_cc = keep_counts_ ? m.node_cc.p : nullptr;
-            d.node_cap = m.node_cap; d.n_nodes_out = m.counters.p + 0; d.ticket = m.counters.p + 6;
+            d.pool_c = m.pool_c.p; d.pool_w = m.pool_w.p; d.pool_sref = m.pool_sref.p; d.pool_pos = m.pool_pos.p; d.pool_cc = keep_counts_ ? m.pool_cc.p : nullptr;
+            d.node_cap = m.node_cap; d.pool_count = m.counters.p + 0;
             d.ovf.node = m.ovf_node.p; d.ovf.next = m.ovf_next.p; d.ovf.count = m.counters.p + 1; d.ovf.cap = m.ovf_cap; d.ovf.err = m.err.p;
-            CK(cudaMemsetAsync(m.tile_state.p, 0, ((size_t)m.n_tiles + 1) * sizeof(unsigned long long), st));
             CK(cudaMemsetAsync(m.tile_flag.p, 0, ((size_t)m.n_tiles + 1) * sizeof(u32), st));
             if (m.n_tiles) { k_build<<<m.n_tiles, AG_TILE, NODES_SMEM + NCHUNK_N * d.rw * 4, st>>>(d); launches_++; }
             int err = 0;
@@ -1082,12 +1080,17 @@ void AgDevice::build() {
         t_.nodes += tm.stop();
     }
     m.n_nodes = nn; t_.n_nodes = nn; t_.n_keys = m.n_keys; t_.n_tiles = m.n_tiles;
-    // ---- successor bits -> successor indices --------------------------------------------------------------------------------------
+    // ---- tile blocks -> position order, successor bits -> successor indices -------------------------------------------------------
     {
         Timer tm(st);
+        m.node_c.ensure((size_t)nn + 1); m.node_w.ensure((size_t)nn + 1); m.node_sref.ensure(2 * (size_t)nn + 2); m.node_pos.ensure((size_t)nn + 1);
+        if (keep_counts_) m.node_cc.ensure(6 * (size_t)nn + 6);
+        d.node_c = m.node_c.p; d.node_w = m.node_w.p; d.node_sref = m.node_sref.p; d.node_pos = m.node_pos.p; d.node_cc = keep_counts_ ? m.node_cc.p : nullptr;
         m.eovf_head.ensure(nn + 1);
         m.eovf_cap = std::max<u32>(1u << 18, nn / 8); m.eovf_target.ensure(m.eovf_cap); m.eovf_next.ensure(m.eovf_cap);
         d.eovf_head = m.eovf_head.p; d.eovf_target = m.eovf_target.p; d.eovf_next = m.eovf_next.p; d.eovf_count = m.counters.p + 2; d.eovf_cap = m.eovf_cap;
+        m.scanner.run(m.tile_nodes.p, m.tile_prefix.p, m.n_tiles, st);
+        k_posfix<<<(n_pos + 1 + 255) / 256, 256, 0, st>>>(d, nn); launches_++;
         if (nn) { k_succ<<<(nn + 255) / 256, 256, 0, st>>>(d, nn); launches_++; }
         t_.finalize += tm.stop();
     }

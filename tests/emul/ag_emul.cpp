@@ -95,34 +95,34 @@ public:
                 for (u32 idx : tiles[tile]) {
                     const ag_fast f = fast[idx];
                     if (!(f.lo <= wq0 + 31 && f.lo + f.span >= wq0)) continue;
-                    ag_lane_out out[32];
+                    u32 item[32]; bool want[32];
                     for (u32 l = 0; l < 32; l++) {
                         const u32 q = wq0 + l;
-                        out[l].sh = AG_NONE; out[l].item = 0; out[l].oslot = AG_NONE; out[l].want = false;
+                        item[l] = AG_NONE; want[l] = false;
                         if (q < n_ref && q - f.lo <= f.span) {
                             auto codef = [&](u32 soff) -> int { return rd.code(f.read, f.lsrc_len >> 16, soff); };
-                            ag_lane_touch(out[l], pl[l], sv[l], pool, ct, cm1.data(), ca[l], f, &alnp[idx], in.ext, q, (u32)k, iv, force_generic, codef);
+                            item[l] = ag_lane_touch(want[l], pl[l], sv[l], pool, ct, cm1.data(), ca[l], f, &alnp[idx], in.ext, q, (u32)k, iv, force_generic, codef);
                         }
                     }
                     for (u32 l = 0; l < AG_WPOS; l++) {
-                        if (!out[l].want) continue;
-                        const u32 nb = out[l + 1].sh;
-                        if (out[l].sh != AG_NONE && nb < 32u) ag_note_succ(sv[l], pool, out[l].item, out[l].oslot, nb);
-                        else tile_flag[tile] |= (out[l].sh == AG_NONE) ? 1 : 2;
+                        if (!want[l]) continue;
+                        const u32 nb = item[l + 1];
+                        if (item[l] != AG_NONE && nb < 32u) ag_note_succ(pl[l], sv[l], pool, item[l], nb);
+                        else tile_flag[tile] |= (item[l] == AG_NONE) ? 1 : 2;
                     }
                 }
                 if (err) return false;
-                for (u32 l = 0; l < AG_WPOS; l++) {  // write-out in position order (the kernel's look-back gives the same indices)
+                for (u32 l = 0; l < AG_WPOS; l++) {  // write-out in position order (the kernel writes tile blocks in arbitrary order; k_succ moves them into this order)
                     const u32 q = wq0 + l;
                     if (q >= n_ref) break;
                     pos_node[q] = (u32)nodeb.size();
                     if (ca[l].cid != AG_CM_MANY) {
                         const u32 nloc = pl[l].n < (u32)AG_NODE_SCAP ? pl[l].n : (u32)AG_NODE_SCAP;
                         for (u32 i = 0; i < nloc; i++) {
-                            ag_nodeb b; b.cid = ca[l].cid; b.coff = ca[l].coff; b.cid0 = sv[l].f(AG_F_CID0, i); b.coff0 = sv[l].f(AG_F_COFF0, i); b.moff = sv[l].f(AG_F_MOFF, i);
-                            b.cov = sv[l].f(AG_F_COV, i);
-                            for (u32 j = 0; j < 5; j++) b.cnt[j] = sv[l].f(AG_F_CNT + j, i);
-                            b.sread = sv[l].f(AG_F_SREAD, i); b.soff_len = sv[l].f(AG_F_SL, i); b.succ = sv[l].f(AG_F_SUCC, i);
+                            ag_nodeb b; b.cid = ca[l].cid; b.coff = ca[l].coff; b.cid0 = sv[l].ld(AG_F_CID0, i); b.coff0 = sv[l].ld(AG_F_COFF0, i); b.moff = sv[l].ld(AG_F_MOFF, i);
+                            b.cov = sv[l].ld(AG_F_COV, i);
+                            for (u32 j = 0; j < 5; j++) b.cnt[j] = sv[l].ld(AG_F_CNT + j, i);
+                            b.sread = sv[l].ld(AG_F_SREAD, i); b.soff_len = sv[l].ld(AG_F_SL, i); b.succ = sv[l].ld(AG_F_SUCC, i);
                             nodeb.push_back(b);
                         }
                     }

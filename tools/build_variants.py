@@ -12,8 +12,8 @@ VARIANTS = {
     "minb5": ["-DAG_NODES_MINB=5"],
     "minb4": ["-DAG_NODES_MINB=4"],
     "minb4_scap3": ["-DAG_NODES_MINB=4", "-DAG_NODE_SCAP=3"],
-    "minb5_chunk128": ["-DAG_NODES_MINB=5", "-DAG_NCHUNK_NODES=128"],
-    "minb6_chunk32": ["-DAG_NODES_MINB=6", "-DAG_NCHUNK_NODES=32"],
+    "minb6_chunk64": ["-DAG_NODES_MINB=6", "-DAG_NCHUNK_NODES=64"],
+    "minb5_chunk256": ["-DAG_NODES_MINB=5", "-DAG_NCHUNK_NODES=256"],
 }
 
 
