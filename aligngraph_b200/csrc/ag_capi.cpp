@@ -111,7 +111,7 @@ int ag_get_reads(ag_ctx* ctx, const uint32_t** bases2, const uint32_t** nmask, c
 
 int ag_begin_unit(ag_ctx* ctx, int unit_id, const char* ref_bases, uint32_t n_ref) {
     return guard(ctx, [&] {
-        ctx->dev->unpin_all(); ctx->unit = AgUnit(); ctx->res = AgUnitResult(); ctx->unit_id = unit_id; ctx->uploaded = false;
+        ctx->dev->unpin_all(); ctx->unit = AgUnit(); ctx->res.reset(); ctx->unit_id = unit_id; ctx->uploaded = false;
         ctx->unit.ref.assign(ref_bases, n_ref); ctx->unit.n_ref = n_ref;
         ctx->unit.cm_start.assign((size_t)n_ref + 1, 0);
     });
@@ -177,7 +177,7 @@ int ag_extend(ag_ctx* ctx) {
         eng.extend(walks);
         std::vector<u32> sel;
         ag_select_emitted(walks, sel);
-        std::string bases; std::vector<u64> offs;
+        char* bases = nullptr; std::vector<u64> offs;
         eng.materialize(walks, sel, bases, offs);
         std::vector<unsigned char> occ;
         eng.occupancy(occ);
@@ -195,8 +195,9 @@ int ag_extend(ag_ctx* ctx) {
 
 int ag_get_text(ag_ctx* ctx, int which, const char** text, uint64_t* len) {
     return guard(ctx, [&] {
-        const std::string& s = which == 0 ? ctx->res.initial_text : which == 1 ? ctx->res.pre_text : ctx->res.ext_text;
-        *text = s.data(); *len = s.size();
+        const char* tp = which == 0 ? ctx->res.initial_text.data() : which == 1 ? ctx->res.pre_text.data() : ctx->res.ext_text.data();
+        const size_t tn = which == 0 ? ctx->res.initial_text.size() : which == 1 ? ctx->res.pre_text.size() : ctx->res.ext_text.size();
+        *text = tp; *len = tn;
     });
 }
 
@@ -204,7 +205,7 @@ int ag_prepare_unit_files(ag_ctx* ctx, const char* tmp_dir, int unit_id) {
     return guard(ctx, [&] {
         if (!ctx->have_reads) throw AgHostError{"reads not set"};
         auto t0 = std::chrono::steady_clock::now();
-        ctx->dev->unpin_all(); ctx->unit = AgUnit(); ctx->res = AgUnitResult(); ctx->unit_id = unit_id; ctx->uploaded = false;
+        ctx->dev->unpin_all(); ctx->unit = AgUnit(); ctx->res.reset(); ctx->unit_id = unit_id; ctx->uploaded = false;
         ag_prepare_unit(ctx->reads, tmp_dir, unit_id, ctx->unit, ctx->res.initial_text);
         ctx->s_parse += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     });
@@ -270,7 +271,7 @@ int ag_run_units_files(ag_ctx** ctxs, int n_ctx, const char* tmp_dir, int first_
             if (!p->error.empty()) { ctx->err = p->error; rc = 1; }
             else {
                 ctx->dev->unpin_all();
-                ctx->unit = std::move(p->unit); ctx->res = AgUnitResult(); ctx->res.initial_text = std::move(p->initial_text);
+                ctx->unit = std::move(p->unit); ctx->res.reset(); ctx->res.initial_text = std::move(p->initial_text);
                 ctx->unit_id = u; ctx->uploaded = false; ctx->s_parse += p->s_parse;
                 rc = ag_build(ctx);
                 if (!rc) rc = ag_extend(ctx);

@@ -735,18 +735,19 @@ __global__ void k_materialize_seq(DevView d, const u32* __restrict__ starts, con
 
 // materialisation in two steps when chains are valid: (1) one thread per emitted walk hops from chain head to chain head and emits
 // work items, (2) one thread per chain item writes that chain's consensus bases, one warp per detour item copies the contig bases
-struct MatItem { u32 a, n; u64 off; };  // chain item: a = head node, n = nodes; detour item: a = first chain-major index, n = bases
-__global__ void k_mat_items(DevView d, const u32* __restrict__ starts, const u64* __restrict__ offs, u32 n, MatItem* chains, MatItem* detours, u32* counts, u32 cap) {
+struct MatItem { u32 a, n; u64 off; };  // detour item: a = first chain-major index, n = bases
+// A chain belongs to at most one walk (it is marked as a whole), so "where does this chain's run of bases END in the output" can be kept
+// per chain tail; every node then finds its own byte: end - (nodes from here to the tail).  One thread per node, no pointer chasing.
+__global__ void k_mat_items(DevView d, const u32* __restrict__ starts, const u64* __restrict__ offs, u32 n, u32* tail_end, MatItem* detours, u32* counts, u32 cap) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     u64 off = offs[i];
     u32 v = starts[i];
     while (v != AG_NONE) {
-        ag_chain c = d.chain[v];
-        u32 o = atomicAdd(&counts[0], 1u);
-        if (o < cap) { MatItem it; it.a = v; it.n = c.len; it.off = off; chains[o] = it; } else *d.err = 6;
+        const ag_chain c = d.chain[v];
         off += c.len;
-        u32 t = c.tail;
+        const u32 t = c.tail;
+        tail_end[t] = (u32)off;
         if (d.node_w[t].misc & AG_NW_DETOUR) {
             ag_cm m = d.cmt.cm[d.cmt.start[d.node_pos[t]]];
             u32 o2 = atomicAdd(&counts[1], 1u);
@@ -756,13 +757,12 @@ __global__ void k_mat_items(DevView d, const u32* __restrict__ starts, const u64
         v = d.walk_next[t];
     }
 }
-__global__ void k_mat_chains(DevView d, const MatItem* __restrict__ items, const u32* counts, unsigned char* out) {
-    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= counts[0]) return;
-    MatItem it = items[i];
-    unsigned char* o = out + it.off;
-    u32 v = it.a;
-    for (u32 j = 0; j < it.n; j++) { *o++ = (unsigned char)(d.node_w[v].misc & 0xFF); v = d.fnext[v]; }
+__global__ void k_mat_nodes(DevView d, u32 n_nodes, const u32* __restrict__ tail_end, unsigned char* out) {
+    u32 v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_nodes) return;
+    const ag_chain c = d.chain[v];
+    const u32 e = tail_end[c.tail];
+    if (e != AG_NONE) out[e - c.len] = (unsigned char)(d.node_w[v].misc & 0xFF);
 }
 __global__ void k_mat_detours(DevView d, const MatItem* __restrict__ items, const u32* counts, unsigned char* out) {
     u32 w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -829,9 +829,9 @@ struct AgDevice::Impl {
     DBuf<u32> pos_node;
     DBuf<ag_nodec> node_c; DBuf<ag_nodew> node_w; DBuf<u32> node_sref, node_pos, node_cc;
     DBuf<u32> eovf_head, eovf_target, eovf_next;
-    DBuf<u32> walk_next, parent, cmin, cmax; DBuf<ag_walk> walks, walks2; DBuf<ag_cm1> cm1; DBuf<MatItem> mat_chains, mat_detours; u32 n_cand = 0; DBuf<unsigned char> pos_term; DBuf<u32> indeg, fnext, fprev, msuf, mnode, cand_rank, cand_node, cand_label; DBuf<ag_chain> chain_a, chain_b; DBuf<int> changed;
+    DBuf<u32> walk_next, parent, cmin, cmax; DBuf<ag_walk> walks, walks2; DBuf<ag_cm1> cm1; DBuf<MatItem> mat_detours; DBuf<u32> tail_end; u32 n_cand = 0; DBuf<unsigned char> pos_term; DBuf<u32> indeg, fnext, fprev, msuf, mnode, cand_rank, cand_node, cand_label; DBuf<ag_chain> chain_a, chain_b; DBuf<int> changed;
     DBuf<unsigned char> out_bases, occ; DBuf<u32> sel_start, sel_tails; DBuf<u64> sel_off;
-    PinnedBuf h_walks, h_bases, h_occ;
+    PinnedBuf h_walks, h_bases, h_occ, h_sel;
     Scanner scanner;
     u32 n_tiles = 0, n_keys = 0, n_nodes = 0;
     u32 node_cap = 0, ovf_cap = 0, eovf_cap = 0, walk_cap = 0;
@@ -862,8 +862,8 @@ AgDevice::~AgDevice() {
     for (auto* b : b32) b->release();
     for (int i = 0; i < 4; i++) m.scanner.lvl[i].release();
     m.cm.release(); m.cthreads.release(); m.aln.release(); m.ext.release(); m.alnp.release(); m.fast.release(); m.pool_c.release(); m.pool_w.release(); m.ovf_node.release(); m.err.release();
-    m.node_c.release(); m.node_w.release(); m.walks.release(); m.walks2.release(); m.cm1.release(); m.mat_chains.release(); m.mat_detours.release(); m.pos_term.release(); m.cand_rank.release(); m.cand_node.release(); m.cand_label.release(); m.fprev.release(); m.msuf.release(); m.mnode.release(); m.indeg.release(); m.fnext.release(); m.chain_a.release(); m.chain_b.release(); m.changed.release(); m.sel_off.release();
-    m.h_walks.release(); m.h_bases.release(); m.h_occ.release();
+    m.node_c.release(); m.node_w.release(); m.walks.release(); m.walks2.release(); m.cm1.release(); m.mat_detours.release(); m.tail_end.release(); m.pos_term.release(); m.cand_rank.release(); m.cand_node.release(); m.cand_label.release(); m.fprev.release(); m.msuf.release(); m.mnode.release(); m.indeg.release(); m.fnext.release(); m.chain_a.release(); m.chain_b.release(); m.changed.release(); m.sel_off.release();
+    m.h_walks.release(); m.h_bases.release(); m.h_occ.release(); m.h_sel.release();
     if (m.st) cudaStreamDestroy(m.st);
     delete m_;
 }
@@ -1229,31 +1229,33 @@ void AgDevice::extend(std::vector<ag_walk>& walks) {
     t_.n_walks = walks.size();
 }
 
-void AgDevice::materialize(const std::vector<ag_walk>& walks, const std::vector<u32>& sel, std::string& bases, std::vector<u64>& offs) {
+void AgDevice::materialize(const std::vector<ag_walk>& walks, const std::vector<u32>& sel, char*& bases, std::vector<u64>& offs) {
     CK(cudaSetDevice(dev_));
     Impl& m = *m_; cudaStream_t st = m.st; DevView& d = m.view;
     offs.assign(sel.size() + 1, 0);
-    std::vector<u32> starts(sel.size());
-    std::vector<u32> tails(3 * sel.size());
+    bases = nullptr;
+    if (sel.empty()) return;
+    m.h_sel.ensure(sel.size() * (sizeof(u64) + 4 * sizeof(u32)) + 64);   // page-locked staging: offsets, start nodes, tail descriptors
+    u64* h_off = (u64*)m.h_sel.p; u32* h_start = (u32*)(h_off + sel.size()); u32* h_tails = h_start + sel.size();
     for (size_t i = 0; i < sel.size(); i++) {
         const ag_walk& r = walks[sel[i]];
         u32 tl = ag_walk_tail_len(r);
-        starts[i] = r.start_node; offs[i + 1] = offs[i] + r.len + tl;
-        tails[3 * i] = r.tail_sread; tails[3 * i + 1] = tl ? r.tail_soff_len : 0; tails[3 * i + 2] = r.len;
+        h_start[i] = r.start_node; offs[i + 1] = offs[i] + r.len + tl; h_off[i] = offs[i];
+        h_tails[3 * i] = r.tail_sread; h_tails[3 * i + 1] = tl ? r.tail_soff_len : 0; h_tails[3 * i + 2] = r.len;
     }
-    bases.assign(offs.back(), '\0');
-    if (sel.empty()) return;
+    if (offs.back() >= 0xFFFFFFF0ull) throw AgError{"materialise: more than 4 GB of contig bases in one unit"};
     Timer tm(st);
     m.sel_start.ensure(sel.size() + 1); m.sel_off.ensure(sel.size() + 1); m.out_bases.ensure(offs.back() + 1); m.sel_tails.ensure(3 * sel.size() + 1);
-    CK(cudaMemcpyAsync(m.sel_tails.p, tails.data(), tails.size() * sizeof(u32), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(m.sel_start.p, starts.data(), starts.size() * sizeof(u32), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(m.sel_off.p, offs.data(), sel.size() * sizeof(u64), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(m.sel_off.p, h_off, sel.size() * sizeof(u64), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(m.sel_start.p, h_start, sel.size() * sizeof(u32), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(m.sel_tails.p, h_tails, 3 * sel.size() * sizeof(u32), cudaMemcpyHostToDevice, st));
     if (chains_valid_) {
-        u32 cap = m.n_cand + 1;
-        m.mat_chains.ensure(cap); m.mat_detours.ensure(cap);
+        const u32 cap = m.n_cand + 1, nn = m.n_nodes;
+        m.mat_detours.ensure(cap); m.tail_end.ensure((size_t)nn + 1);
         CK(cudaMemsetAsync(m.counters.p + 4, 0, 2 * sizeof(u32), st));
-        k_mat_items<<<((u32)sel.size() + 127) / 128, 128, 0, st>>>(d, m.sel_start.p, m.sel_off.p, (u32)sel.size(), m.mat_chains.p, m.mat_detours.p, m.counters.p + 4, cap); launches_++;
-        k_mat_chains<<<(cap + 127) / 128, 128, 0, st>>>(d, m.mat_chains.p, m.counters.p + 4, m.out_bases.p); launches_++;
+        CK(cudaMemsetAsync(m.tail_end.p, 0xFF, (size_t)nn * sizeof(u32), st));
+        k_mat_items<<<((u32)sel.size() + 127) / 128, 128, 0, st>>>(d, m.sel_start.p, m.sel_off.p, (u32)sel.size(), m.tail_end.p, m.mat_detours.p, m.counters.p + 4, cap); launches_++;
+        k_mat_nodes<<<(nn + 255) / 256, 256, 0, st>>>(d, nn, m.tail_end.p, m.out_bases.p); launches_++;
         k_mat_detours<<<(cap + 3) / 4, 128, 0, st>>>(d, m.mat_detours.p, m.counters.p + 4, m.out_bases.p); launches_++;
     } else {
         k_materialize_seq<<<((u32)sel.size() + 127) / 128, 128, 0, st>>>(d, m.sel_start.p, m.sel_off.p, (u32)sel.size(), m.out_bases.p); launches_++;
@@ -1265,9 +1267,9 @@ void AgDevice::materialize(const std::vector<ag_walk>& walks, const std::vector<
     CK(cudaMemcpyAsync(&err, m.err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (err) throw AgError{"materialise item buffer exhausted"};
-    memcpy(&bases[0], m.h_bases.p, offs.back());
+    bases = (char*)m.h_bases.p;   // the post passes read (and patch) the page-locked buffer in place
     t_.materialize += tm.stop();
-    t_.h2d_bytes += sel.size() * 12; t_.d2h_bytes += offs.back();
+    t_.h2d_bytes += sel.size() * 24; t_.d2h_bytes += offs.back();
 }
 
 void AgDevice::occupancy(std::vector<unsigned char>& bits) {

@@ -49,8 +49,9 @@ public:
     void build();
     // coverage filter + walk simulation; fills `walks` (unsorted on return from the device, sorted here by start node)
     void extend(std::vector<ag_walk>& walks);
-    // materialise the selected walks' base strings (without tails); out[i] gets walks[sel[i]].len bytes
-    void materialize(const std::vector<ag_walk>& walks, const std::vector<u32>& sel, std::string& bases, std::vector<u64>& offs);
+    // materialise the selected walks' base strings (loop bases + tail); contig i occupies bases[offs[i], offs[i + 1]).  `bases` points into
+    // a page-locked buffer owned by the device object (valid until the next call); the post passes patch and read it in place
+    void materialize(const std::vector<ag_walk>& walks, const std::vector<u32>& sel, char*& bases, std::vector<u64>& offs);
     // occupancy bitmap (any node or contiMer at a position) for the scaffold gap test (AG:2428)
     void occupancy(std::vector<unsigned char>& bits);
     void dump_nodes(AgNodeDump& d);

@@ -1,4 +1,6 @@
 // Host side of the B200 AlignGraph hot path — see ag_host.h.  Reference citations: AG:line = AlignGraph/AlignGraph.cpp.
+#include <sched.h>
+#include <condition_variable>
 #include "ag_host.h"
 #include <algorithm>
 #include <cstring>
@@ -132,6 +134,52 @@ static int host_threads() {
     unsigned h = std::thread::hardware_concurrency();
     return (int)std::min<unsigned>(h ? h : 1, 32);
 }
+
+// ---- host thread team: persistent workers for the text formatters (the reference is single-threaded; these loops are pure copies) ----
+namespace {
+struct Team {
+    std::vector<std::thread> th;
+    std::mutex m; std::condition_variable cv, cv_done;
+    const std::function<void(int)>* job = nullptr;
+    int n_chunks = 0, active = 0; unsigned long gen = 0; bool stop = false;
+    std::atomic<int> next{0};
+    std::mutex run_m;   // one job at a time (several contexts may share the team)
+    int size = 1;
+    Team() {
+        int T = 0;
+        if (const char* e = getenv("AG_THREADS")) T = atoi(e);
+        if (T <= 0) {
+            cpu_set_t set; CPU_ZERO(&set);
+            T = sched_getaffinity(0, sizeof set, &set) == 0 ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
+            T = std::min(T, 16);
+        }
+        size = std::max(T, 1);
+        for (int i = 1; i < size; i++) th.emplace_back([this] { work(); });
+    }
+    ~Team() { { std::lock_guard<std::mutex> l(m); stop = true; } cv.notify_all(); for (auto& t : th) t.join(); }
+    void drain() { for (;;) { int c = next.fetch_add(1); if (c >= n_chunks) break; (*job)(c); } }
+    void work() {
+        unsigned long seen = 0;
+        for (;;) {
+            { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return stop || gen != seen; }); if (stop) return; seen = gen; }
+            drain();
+            { std::lock_guard<std::mutex> l(m); if (--active == 0) cv_done.notify_one(); }
+        }
+    }
+    void run(int n, const std::function<void(int)>& fn) {
+        if (n <= 0) return;
+        if (size == 1 || n == 1) { for (int c = 0; c < n; c++) fn(c); return; }
+        std::lock_guard<std::mutex> rl(run_m);
+        { std::lock_guard<std::mutex> l(m); job = &fn; n_chunks = n; next = 0; active = (int)th.size(); gen++; }
+        cv.notify_all();
+        drain();
+        std::unique_lock<std::mutex> l(m); cv_done.wait(l, [&] { return active == 0; });
+    }
+};
+Team& team() { static Team t; return t; }
+}  // namespace
+void ag_parallel_chunks(int n_chunks, const std::function<void(int)>& fn) { team().run(n_chunks, fn); }
+int ag_team_size() { return team().size; }
 
 // Fast path for the file formalizeInput writes (AG:3455-3471): strictly alternating ">id" / one sequence line.  Chunks of the mapped
 // file are scanned and packed by several threads; anything irregular (multi-line record, empty line, odd record count, unequal mates)
@@ -790,19 +838,40 @@ void ag_select_emitted(const std::vector<ag_walk>& walks, std::vector<u32>& sel)
     }
 }
 
-void ag_make_contigs(const std::vector<ag_walk>& walks, const std::vector<u32>& sel, std::string& bases, const std::vector<u64>& offs,
-                     const AgReads& reads, std::vector<AgContig>& contigs, std::string& pre_text) {
-    Out out(&pre_text);
-    out.b->reserve(bases.size() + bases.size() / 60 + sel.size() * 96 + 64);
+static inline size_t wrapped_len(size_t n) { return n + (n + 59) / 60; }   // 60 columns, newline after the last base (AG:2179-2184)
+static inline char* wrap60_to(char* p, const char* s, size_t n) {
+    for (size_t i = 0; i < n; i += 60) { size_t m = std::min<size_t>(60, n - i); memcpy(p, s + i, m); p += m; *p++ = '\n'; }
+    return p;
+}
+// split [0, n) into chunks of roughly equal output bytes for the thread team; cut[i] .. cut[i + 1] is chunk i
+static std::vector<size_t> byte_chunks(const std::vector<size_t>& off /* n + 1 prefix offsets */) {
+    const size_t n = off.size() - 1, total = off.back();
+    int want = std::max(1, std::min<int>(ag_team_size() * 4, (int)(total / (64 << 10)) + 1));
+    std::vector<size_t> cut(1, 0);
+    for (int c = 1; c < want; c++) {
+        size_t target = total / want * c;
+        size_t i = (size_t)(std::lower_bound(off.begin(), off.end(), target) - off.begin());
+        if (i > cut.back() && i < n) cut.push_back(i);
+    }
+    cut.push_back(n);
+    return cut;
+}
+
+void ag_make_contigs(const std::vector<ag_walk>& walks, const std::vector<u32>& sel, char* bases, const std::vector<u64>& offs,
+                     const AgReads& reads, std::vector<AgContig>& contigs, AgText& pre_text) {
+    auto tp0 = std::chrono::steady_clock::now();
     contigs.clear(); contigs.resize(sel.size());
     const bool patch = !reads.exc.empty();
+    // pass 1 (sequential, light): contig records + header strings + where every contig's text goes
+    std::string hdr; hdr.reserve(sel.size() * 72);
+    std::vector<size_t> hoff(sel.size() + 1, 0), toff(sel.size() + 1, 0);
     for (size_t i = 0; i < sel.size(); i++) {
         const ag_walk& r = walks[sel[i]];
         AgContig& c = contigs[i];
         c.extended = (int)(r.flags & 1);
         c.sid = 0; c.soff = r.soff; c.eid = 0; c.eoff = r.eoff;
         c.sid0 = r.soff0 == AG_NONE ? AG_NONE : 0; c.soff0 = r.soff0;
-        c.p = bases.data() + offs[i]; c.n = (size_t)(offs[i + 1] - offs[i]);
+        c.p = bases + offs[i]; c.n = (size_t)(offs[i + 1] - offs[i]);
         u32 mode = (r.flags >> 1) & 3;
         if (mode == 1) { c.eid0 = AG_NONE; c.eoff0 = AG_NONE; }  // walk ended on a contiMer (AG:2158-2162)
         else {
@@ -810,16 +879,38 @@ void ag_make_contigs(const std::vector<ag_walk>& walks, const std::vector<u32>& 
             u32 slen = r.tail_soff_len >> 16, soff = r.tail_soff_len & 0xFFFFu, read = r.tail_sread >> 1, rc = r.tail_sread & 1;
             if (patch && slen > 1) {  // the device wrote 'N' for every masked base; put the original characters back (AG:2167 copies s verbatim)
                 u32 rlen = reads.len[read >> 1];
-                char* t = &bases[offs[i] + r.len];
+                char* t = bases + offs[i] + r.len;
                 for (u32 j = 1; j < slen; j++) t[j - 1] = reads.at(read, rc, rlen, soff + j);
             }
             c.eoff = c.eoff + slen - 1; c.eoff0 = c.eoff0 + slen - 1;   // size_t arithmetic truncated to u32 (AG:2170-2171)
         }
-        out.ch('>'); out.num(i); out.put(", ", 2); out.inum(c.extended); out.put(", ", 2);
-        out.num(c.sid); out.put(", ", 2); out.num(c.soff); out.put(", ", 2); out.num(c.eid); out.put(", ", 2); out.num(c.eoff); out.put(", ", 2);
-        out.num(c.sid0); out.put(", ", 2); out.num(c.soff0); out.put(", ", 2); out.num(c.eid0); out.put(", ", 2); out.num(c.eoff0); out.put(" \n", 2);
-        out.wrap60(c.p, c.n);
+        {   // ">i, extended, sid, soff, eid, eoff, sid0, soff0, eid0, eoff0 \n"  (AG:2178): one append per header
+            char hb[160]; char* w = hb;
+            auto num = [&](unsigned long v) { char t[24]; int k = 24; do { t[--k] = (char)('0' + v % 10); v /= 10; } while (v); memcpy(w, t + k, (size_t)(24 - k)); w += 24 - k; };
+            auto sep = [&]() { *w++ = ','; *w++ = ' '; };
+            *w++ = '>'; num(i); sep();
+            if (c.extended < 0) { *w++ = '-'; num((unsigned long)(-(long)c.extended)); } else num((unsigned long)c.extended);
+            sep(); num(c.sid); sep(); num(c.soff); sep(); num(c.eid); sep(); num(c.eoff); sep(); num(c.sid0); sep(); num(c.soff0); sep(); num(c.eid0); sep(); num(c.eoff0);
+            *w++ = ' '; *w++ = '\n';
+            hdr.append(hb, (size_t)(w - hb));
+        }
+        hoff[i + 1] = hdr.size();
+        toff[i + 1] = toff[i] + (hoff[i + 1] - hoff[i]) + wrapped_len(c.n);
     }
+    // pass 2 (thread team): header + 60-column body of every contig at its offset
+    auto tp1 = std::chrono::steady_clock::now();
+    if (getenv("AG_POST_TIMING")) fprintf(stderr, "  [make_contigs] records + headers %.2f ms\n", std::chrono::duration<double>(tp1 - tp0).count() * 1e3);
+    pre_text.set_size(toff.back());
+    const std::vector<size_t> cut = byte_chunks(toff);
+    char* const T = pre_text.data();
+    ag_parallel_chunks((int)cut.size() - 1, [&](int ch) {
+        for (size_t i = cut[ch]; i < cut[ch + 1]; i++) {
+            char* p = T + toff[i];
+            memcpy(p, hdr.data() + hoff[i], hoff[i + 1] - hoff[i]); p += hoff[i + 1] - hoff[i];
+            wrap60_to(p, contigs[i].p, contigs[i].n);
+        }
+    });
+    if (getenv("AG_POST_TIMING")) fprintf(stderr, "  [make_contigs] fill %.2f ms (%d chunks, team %d)\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - tp1).count() * 1e3, (int)cut.size() - 1, ag_team_size());
 }
 
 static inline int contain(const AgContig& a, const AgContig& b) { return a.sid == b.sid && a.eid == b.eid && a.soff <= b.soff && a.eoff >= b.eoff; }
@@ -865,8 +956,10 @@ static inline int overlap(u32 x1, u32 y1, u32 x2, u32 y2) {  // AG:2388-2394
            (x1 <= x2 && x2 <= y2 && y2 <= y1 && (int)y2 - (int)x2 > 0) || (x2 <= x1 && x1 <= y1 && y1 <= y2 && (int)y1 - (int)x1 > 0);
 }
 
-void ag_scaffold(std::vector<AgContig>& cs, const std::string& ref, const std::vector<unsigned char>& occ, std::string& text) {
-    std::vector<std::string> sc;
+void ag_scaffold(std::vector<AgContig>& cs, const std::string& ref, const std::vector<unsigned char>& occ, AgText& text) {
+    // a scaffold = a list of pieces (contig sequences and reference gap fills); nothing is copied until the text is written
+    struct Piece { const char* p; size_t n; };
+    std::vector<Piece> pieces; std::vector<size_t> first(1, 0);   // pieces of scaffold i: [first[i], first[i + 1])
     auto occupied = [&](u32 p) { return (size_t)(p >> 3) < occ.size() && ((occ[p >> 3] >> (p & 7)) & 1); };
     // the reference scans EVERY later contig for a chaining partner (quadratic); only contigs with extended == 1 can ever satisfy the
     // test and `extended` does not change here, so scanning that sub-list in the same order is equivalent
@@ -874,7 +967,7 @@ void ag_scaffold(std::vector<AgContig>& cs, const std::string& ref, const std::v
     for (u32 i = 0; i < cs.size(); i++) if (cs[i].extended == 1) ext1.push_back(i);
     for (u32 cp = 0; cp < cs.size(); cp++) {
         if (!(cs[cp].sid != AG_NONE && cs[cp].extended == 1)) continue;
-        sc.emplace_back(cs[cp].data(), cs[cp].size());
+        pieces.push_back(Piece{cs[cp].data(), cs[cp].size()});
         cs[cp].sid = AG_NONE;
         int cont = 1;
         while (cs[cp].sid0 == cs[cp].eid0 && cont) {
@@ -886,18 +979,40 @@ void ag_scaffold(std::vector<AgContig>& cs, const std::string& ref, const std::v
                 if (b.soff > a.eoff) {
                     u32 gap = b.soff - a.eoff - 1; int covered = 0;
                     for (u32 i = 0; i < gap; i++) if (occupied(a.eoff + i + 1)) covered++;
-                    if ((gap != 0 && (double)covered / gap >= 0.5) || gap == 0) { for (u32 i = 0; i < gap; i++) sc.back().push_back(ref[a.eoff + i + 1]); }
+                    if ((gap != 0 && (double)covered / gap >= 0.5) || gap == 0) { if (gap) pieces.push_back(Piece{ref.data() + a.eoff + 1, gap}); }   // reference bases fill the gap (AG:2428-2436)
                     else continue;
                 }
-                sc.back().append(b.data(), b.size());
+                pieces.push_back(Piece{b.data(), b.size()});
                 b.sid = AG_NONE;
                 cp = c0; cont = 1;
                 break;
             }
         }
+        first.push_back(pieces.size());
     }
-    Out out(&text);
-    for (size_t i = 0; i < sc.size(); i++) { out.ch('>'); out.num(i); out.ch('\n'); out.wrap60(sc[i]); }
+    const size_t ns = first.size() - 1;
+    std::string hdr; std::vector<size_t> hoff(ns + 1, 0), toff(ns + 1, 0);
+    { Out out(&hdr); for (size_t i = 0; i < ns; i++) {
+        out.ch('>'); out.num(i); out.ch('\n'); hoff[i + 1] = hdr.size();
+        size_t n = 0; for (size_t k = first[i]; k < first[i + 1]; k++) n += pieces[k].n;
+        toff[i + 1] = toff[i] + (hoff[i + 1] - hoff[i]) + wrapped_len(n);
+    } }
+    text.set_size(toff.back());
+    const std::vector<size_t> cut = byte_chunks(toff);
+    char* const T = text.data();
+    ag_parallel_chunks((int)cut.size() - 1, [&](int ch) {
+        for (size_t i = cut[ch]; i < cut[ch + 1]; i++) {
+            char* p = T + toff[i];
+            memcpy(p, hdr.data() + hoff[i], hoff[i + 1] - hoff[i]); p += hoff[i + 1] - hoff[i];
+            if (first[i + 1] - first[i] == 1) { wrap60_to(p, pieces[first[i]].p, pieces[first[i]].n); continue; }
+            size_t col = 0;   // 60-column wrapping across the pieces
+            for (size_t k = first[i]; k < first[i + 1]; k++) {
+                const char* q = pieces[k].p; size_t n = pieces[k].n;
+                while (n) { size_t m = std::min(n, 60 - col); memcpy(p, q, m); p += m; q += m; n -= m; col += m; if (col == 60) { *p++ = '\n'; col = 0; } }
+            }
+            if (col) *p++ = '\n';
+        }
+    });
 }
 
 // =============================================================================================================================
@@ -972,6 +1087,12 @@ int ag_formalize_genome(const std::string& in_path, const std::string& tmp, int 
     return unit;
 }
 
+void ag_write_file(const std::string& path, const AgText& text) {
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) throw AgHostError{"CANNOT OPEN FILE!"};
+    if (!text.empty()) fwrite(text.data(), 1, text.size(), f);
+    fclose(f);
+}
 void ag_write_file(const std::string& path, const std::string& text) {
     FILE* f = fopen(path.c_str(), "wb");
     if (!f) throw AgHostError{"CANNOT OPEN FILE!"};

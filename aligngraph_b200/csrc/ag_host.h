@@ -3,6 +3,7 @@
 // graph build and the walk run on the device (ag_device.cu).
 #pragma once
 #include "ag_types.h"
+#include <functional>
 #include <string>
 #include <vector>
 #include <cstdio>
@@ -26,6 +27,30 @@ template <class T> struct AgZVec {
     size_t size() const { return n; }
     T& operator[](size_t i) { return p[i]; } const T& operator[](size_t i) const { return p[i]; }
 };  // message the CLI prints on stdout before exit(-1), as the reference does
+
+// Text output buffer whose growth does not zero-fill (the formatters write every byte, several threads at once) and whose capacity
+// survives from unit to unit.
+struct AgText {
+    char* p = nullptr; size_t n = 0, cap = 0;
+    AgText() {}
+    AgText(const AgText& o) { assign(o.p, o.n); }
+    AgText& operator=(const AgText& o) { if (this != &o) assign(o.p, o.n); return *this; }
+    AgText(AgText&& o) noexcept : p(o.p), n(o.n), cap(o.cap) { o.p = nullptr; o.n = o.cap = 0; }
+    AgText& operator=(AgText&& o) noexcept { if (this != &o) { free(p); p = o.p; n = o.n; cap = o.cap; o.p = nullptr; o.n = o.cap = 0; } return *this; }
+    ~AgText() { free(p); }
+    void set_size(size_t m) {   // contents undefined afterwards
+        if (m > cap) { free(p); cap = m + m / 8 + 64; p = (char*)malloc(cap); if (!p) { cap = 0; throw AgHostError{"out of host memory"}; } }
+        n = m;
+    }
+    void assign(const char* s, size_t m) { set_size(m); if (m) memcpy(p, s, m); }
+    void clear() { n = 0; }
+    const char* data() const { return p; } char* data() { return p; }
+    size_t size() const { return n; } bool empty() const { return n == 0; }
+    bool operator==(const std::string& s) const { return s.size() == n && (n == 0 || memcmp(s.data(), p, n) == 0); }
+};
+// run fn(chunk) for chunk = 0 .. n_chunks-1 on the host thread team (persistent workers + the caller; AG_THREADS / affinity-aware)
+void ag_parallel_chunks(int n_chunks, const std::function<void(int)>& fn);
+int ag_team_size();
 
 // ---- reads (tmp/_reads.fa, AG:361-404) -----------------------------------------------------------------------------------
 struct AgReads {
@@ -75,16 +100,17 @@ struct AgContig {
 void ag_select_emitted(const std::vector<ag_walk>& walks, std::vector<u32>& sel);
 // emitted contigs as views into `bases` (loop bases + s[1..] tail per walk, written by the device; characters outside ACGT are
 // restored here from the reads' exception list) + the text of tmp/_pre_extended_contigs.N.fa
-void ag_make_contigs(const std::vector<ag_walk>& walks, const std::vector<u32>& sel, std::string& bases, const std::vector<u64>& offs,
-                     const AgReads& reads, std::vector<AgContig>& contigs, std::string& pre_text);
+void ag_make_contigs(const std::vector<ag_walk>& walks, const std::vector<u32>& sel, char* bases, const std::vector<u64>& offs,
+                     const AgReads& reads, std::vector<AgContig>& contigs, AgText& pre_text);
 void ag_dedup_join(std::vector<AgContig>& contigs);                                               // AG:2296-2380
 // AG:2396-2464; occ = bitmap "position holds a node or a contiMer"
-void ag_scaffold(std::vector<AgContig>& contigs, const std::string& ref, const std::vector<unsigned char>& occ, std::string& text);
+void ag_scaffold(std::vector<AgContig>& contigs, const std::string& ref, const std::vector<unsigned char>& occ, AgText& text);
 
 // ---- input normalisation re-run by --resume (AG:3228-3345, AG:3347-3418) ----------------------------------------------------
 void ag_formalize_contigs(const std::string& in_path, const std::string& tmp, std::vector<std::string>& contig_ids);
 int ag_formalize_genome(const std::string& in_path, const std::string& tmp, int part, std::vector<std::string>& genome_ids);
 void ag_write_file(const std::string& path, const std::string& text);
+void ag_write_file(const std::string& path, const AgText& text);
 // glibc tuning for the staging buffers (see ag_host.cpp); no-op when AG_NO_MALLOPT is set
 void ag_tune_malloc();
 

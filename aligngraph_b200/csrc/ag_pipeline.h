@@ -9,9 +9,10 @@
 #include <cstdio>
 
 struct AgUnitResult {
-    std::string initial_text, pre_text, ext_text;  // tmp/_initial_contigs.N.fa, _pre_extended_contigs.N.fa, _extended_contigs.N.fa
+    std::string initial_text; AgText pre_text, ext_text;  // tmp/_initial_contigs.N.fa, _pre_extended_contigs.N.fa, _extended_contigs.N.fa
     double t_parse = 0, t_device = 0, t_post = 0;  // wall seconds: host parsing / device section incl. copies / host post passes
     u64 n_aln = 0, n_walks = 0, n_emitted = 0;
+    void reset() { initial_text.clear(); pre_text.clear(); ext_text.clear(); t_parse = t_device = t_post = 0; n_aln = n_walks = n_emitted = 0; }   // keeps the buffers' capacity
 };
 
 inline AgUnitInput ag_unit_input(const AgUnit& u) {
@@ -48,7 +49,7 @@ template <class Engine> void ag_process_unit(Engine& eng, const AgReads& reads, 
     eng.extend(walks);
     std::vector<u32> sel;
     ag_select_emitted(walks, sel);
-    std::string bases; std::vector<u64> offs;
+    char* bases = nullptr; std::vector<u64> offs;   // bases: engine-owned buffer (page-locked on the device), valid until the next materialize
     eng.materialize(walks, sel, bases, offs);
     std::vector<unsigned char> occ;
     eng.occupancy(occ);

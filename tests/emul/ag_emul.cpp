@@ -309,18 +309,34 @@ public:
         }
     }
 
-    void materialize(const std::vector<ag_walk>& walks, const std::vector<u32>& sel, std::string& bases, std::vector<u64>& offs) {
+    std::string bases_buf;
+    void materialize(const std::vector<ag_walk>& walks, const std::vector<u32>& sel, char*& bases_out, std::vector<u64>& offs) {
         offs.assign(sel.size() + 1, 0);
         for (size_t i = 0; i < sel.size(); i++) offs[i + 1] = offs[i] + walks[sel[i]].len + ag_walk_tail_len(walks[sel[i]]);
+        std::string& bases = bases_buf;
         bases.assign(offs.back(), '\0');
+        bases_out = bases.empty() ? nullptr : &bases[0];
         ag_cmtab ct = cmt();
+        std::vector<u32> tail_end(n_nodes, AG_NONE);
         for (size_t i = 0; i < sel.size(); i++) {
             size_t o = offs[i];
-            for (u32 v = walks[sel[i]].start_node; v != AG_NONE;) {
-                bases[o++] = (char)(node_w[v].misc & 0xFF);
-                if (!use_chains && !(node_w[v].misc & AG_NW_STOP)) { v = fnext[v]; continue; }   // k_materialize_seq
-                if (node_w[v].misc & AG_NW_DETOUR) { ag_cm m = ct.cm[ct.start[node_pos[v]]]; for (u32 e = m.chain + 1; e <= m.term; e++) bases[o++] = in.chain_base[e]; }
-                v = (use_chains && fnext[v] != AG_NONE) ? fnext[v] : walk_next[v];
+            if (use_chains) {   // k_mat_items: hop from chain to chain, note where every chain's run of bases ends; detours copied right away
+                for (u32 v = walks[sel[i]].start_node; v != AG_NONE;) {
+                    const ag_chain c = chain[v];
+                    o += c.len;
+                    const u32 t = c.tail;
+                    if (tail_end[t] != AG_NONE) throw AgHostError{"emul: a chain was emitted twice"};
+                    tail_end[t] = (u32)o;
+                    if (node_w[t].misc & AG_NW_DETOUR) { ag_cm m = ct.cm[ct.start[node_pos[t]]]; for (u32 e = m.chain + 1; e <= m.term; e++) bases[o++] = in.chain_base[e]; }
+                    v = walk_next[t];
+                }
+            } else {            // k_materialize_seq
+                for (u32 v = walks[sel[i]].start_node; v != AG_NONE;) {
+                    bases[o++] = (char)(node_w[v].misc & 0xFF);
+                    if (!(node_w[v].misc & AG_NW_STOP)) { v = fnext[v]; continue; }
+                    if (node_w[v].misc & AG_NW_DETOUR) { ag_cm m = ct.cm[ct.start[node_pos[v]]]; for (u32 e = m.chain + 1; e <= m.term; e++) bases[o++] = in.chain_base[e]; }
+                    v = walk_next[v];
+                }
             }
             {   // k_mat_tails
                 const ag_walk& r = walks[sel[i]];
@@ -329,6 +345,9 @@ public:
             }
             if (o != offs[i + 1]) throw AgHostError{"emul: walk length mismatch"};
         }
+        if (use_chains)   // k_mat_nodes: every node of an emitted chain writes its own byte
+            for (u32 v = 0; v < n_nodes; v++) { const u32 e = tail_end[chain[v].tail]; if (e != AG_NONE) bases[e - chain[v].len] = (char)(node_w[v].misc & 0xFF); }
+        for (size_t i = 0; i < bases.size(); i++) if (!bases[i]) throw AgHostError{"emul: hole in the materialised bases"};
     }
 
     void occupancy(std::vector<unsigned char>& bits) {
