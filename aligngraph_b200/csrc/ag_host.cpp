@@ -916,6 +916,7 @@ void ag_make_contigs(const std::vector<ag_walk>& walks, const std::vector<u32>& 
 static inline int contain(const AgContig& a, const AgContig& b) { return a.sid == b.sid && a.eid == b.eid && a.soff <= b.soff && a.eoff >= b.eoff; }
 
 void ag_dedup_join(std::vector<AgContig>& cs) {
+    struct Lap { std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now(); ~Lap() { if (getenv("AG_POST_TIMING")) fprintf(stderr, "  [dedup_join] %.2f ms\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() * 1e3); } } lap;
     int n = (int)cs.size();
     for (int a = 0; a < n; a++) {  // forward containment (AG:2303-2320)
         if (cs[a].extended != 1) continue;
@@ -942,10 +943,7 @@ void ag_dedup_join(std::vector<AgContig>& cs) {
             AgContig& t = cs[lastb];
             t.extended = 2;
             u32 from = cs[a].eoff - t.soff + 1;
-            if (from < t.size()) {
-                if (cs[a].own.empty()) cs[a].own.assign(cs[a].p, cs[a].n);
-                cs[a].own.append(t.data() + from, t.size() - from);
-            }
+            if (from < t.size()) t.pieces_from(from, cs[a].more);   // the reference appends t's suffix (AG:2368-2370); here only views
             cs[a].eid = t.eid; cs[a].eoff = t.eoff; cs[a].eid0 = t.eid0; cs[a].eoff0 = t.eoff0;
         }
     }
@@ -957,8 +955,9 @@ static inline int overlap(u32 x1, u32 y1, u32 x2, u32 y2) {  // AG:2388-2394
 }
 
 void ag_scaffold(std::vector<AgContig>& cs, const std::string& ref, const std::vector<unsigned char>& occ, AgText& text) {
+    auto ts0 = std::chrono::steady_clock::now();
     // a scaffold = a list of pieces (contig sequences and reference gap fills); nothing is copied until the text is written
-    struct Piece { const char* p; size_t n; };
+    typedef AgPiece Piece;
     std::vector<Piece> pieces; std::vector<size_t> first(1, 0);   // pieces of scaffold i: [first[i], first[i + 1])
     auto occupied = [&](u32 p) { return (size_t)(p >> 3) < occ.size() && ((occ[p >> 3] >> (p & 7)) & 1); };
     // the reference scans EVERY later contig for a chaining partner (quadratic); only contigs with extended == 1 can ever satisfy the
@@ -967,7 +966,7 @@ void ag_scaffold(std::vector<AgContig>& cs, const std::string& ref, const std::v
     for (u32 i = 0; i < cs.size(); i++) if (cs[i].extended == 1) ext1.push_back(i);
     for (u32 cp = 0; cp < cs.size(); cp++) {
         if (!(cs[cp].sid != AG_NONE && cs[cp].extended == 1)) continue;
-        pieces.push_back(Piece{cs[cp].data(), cs[cp].size()});
+        cs[cp].pieces_from(0, pieces);
         cs[cp].sid = AG_NONE;
         int cont = 1;
         while (cs[cp].sid0 == cs[cp].eid0 && cont) {
@@ -975,6 +974,8 @@ void ag_scaffold(std::vector<AgContig>& cs, const std::string& ref, const std::v
             for (size_t e = (size_t)(std::upper_bound(ext1.begin(), ext1.end(), cp) - ext1.begin()); e < ext1.size(); e++) {
                 const u32 c0 = ext1[e];
                 const AgContig& a = cs[cp]; AgContig& b = cs[c0];
+                // contigs are in start-position order and every case of overlap() needs b.soff <= a.eoff0: nothing further can match
+                if (a.eoff0 != AG_NONE && b.soff != AG_NONE && b.soff > a.eoff0 && b.sid != AG_NONE) break;
                 if (!(a.eid0 == b.sid && b.sid == b.eid && overlap(a.soff0, a.eoff0, b.soff, b.eoff) && b.extended == 1)) continue;
                 if (b.soff > a.eoff) {
                     u32 gap = b.soff - a.eoff - 1; int covered = 0;
@@ -982,7 +983,7 @@ void ag_scaffold(std::vector<AgContig>& cs, const std::string& ref, const std::v
                     if ((gap != 0 && (double)covered / gap >= 0.5) || gap == 0) { if (gap) pieces.push_back(Piece{ref.data() + a.eoff + 1, gap}); }   // reference bases fill the gap (AG:2428-2436)
                     else continue;
                 }
-                pieces.push_back(Piece{b.data(), b.size()});
+                b.pieces_from(0, pieces);
                 b.sid = AG_NONE;
                 cp = c0; cont = 1;
                 break;
@@ -991,6 +992,7 @@ void ag_scaffold(std::vector<AgContig>& cs, const std::string& ref, const std::v
         first.push_back(pieces.size());
     }
     const size_t ns = first.size() - 1;
+    auto ts1 = std::chrono::steady_clock::now();
     std::string hdr; std::vector<size_t> hoff(ns + 1, 0), toff(ns + 1, 0);
     { Out out(&hdr); for (size_t i = 0; i < ns; i++) {
         out.ch('>'); out.num(i); out.ch('\n'); hoff[i + 1] = hdr.size();
@@ -1013,6 +1015,8 @@ void ag_scaffold(std::vector<AgContig>& cs, const std::string& ref, const std::v
             if (col) *p++ = '\n';
         }
     });
+    if (getenv("AG_POST_TIMING")) fprintf(stderr, "  [scaffold] chaining %.2f ms, text %.2f ms (%zu scaffolds)\n", std::chrono::duration<double>(ts1 - ts0).count() * 1e3,
+                                          std::chrono::duration<double>(std::chrono::steady_clock::now() - ts1).count() * 1e3, ns);
 }
 
 // =============================================================================================================================

@@ -89,12 +89,18 @@ void ag_expand_contimers(const ag_cthread* threads, size_t n_threads, const u32*
 void ag_parse_sam(const std::string& path, const AgReads& reads, AgUnit& u);
 
 // ---- post passes --------------------------------------------------------------------------------------------------------------------
+struct AgPiece { const char* p; size_t n; };
 struct AgContig {
     int extended; u32 sid, soff, eid, eoff, sid0, soff0, eid0, eoff0;
     const char* p = nullptr; size_t n = 0;  // bases: a view into the materialised buffer ...
-    std::string own;                        // ... or an owned string once the contig has been joined with another (AG:2368-2370)
-    const char* data() const { return own.empty() ? p : own.data(); }
-    size_t size() const { return own.empty() ? n : own.size(); }
+    std::vector<AgPiece> more;              // ... followed by views of the contigs it has been joined with (AG:2368-2370); nothing is copied
+    size_t size() const { size_t t = n; for (const AgPiece& q : more) t += q.n; return t; }
+    // append the pieces of this contig from byte offset `from` on to `out`
+    void pieces_from(size_t from, std::vector<AgPiece>& out) const {
+        if (from < n) out.push_back(AgPiece{p + from, n - from});
+        size_t skip = from > n ? from - n : 0;
+        for (const AgPiece& q : more) { if (skip >= q.n) { skip -= q.n; continue; } out.push_back(AgPiece{q.p + skip, q.n - skip}); skip = 0; }
+    }
 };
 // emission filter of extdContigs1 (AG:2176-2189): indices of the walks that are written to _pre_extended_contigs
 void ag_select_emitted(const std::vector<ag_walk>& walks, std::vector<u32>& sel);
