@@ -517,6 +517,7 @@ struct ag_walkctx {
     const u32* chain_pos;     // chain-major: unit position of every contiMer
     u32* walk_next;           // per node: next node of the walk that marked it, or NONE
     const ag_chain* chain;    // forced-link chains
+    const ag_hrec* hrec;      // per chain head: packed hop record (valid for live, non-interior nodes)
     // exact sequential replay (skip rule, AG:2194-2202): a chain can be entered at an interior node, so marks are kept as a marked SUFFIX
     // per chain, indexed by the chain's tail: msuf = nodes marked at the tail end, mnode = first marked node
     u32* msuf; u32* mnode; const u32* fprev;
@@ -554,48 +555,68 @@ AG_HD u32 ag_forced_succ(const ag_nodew* nw, const u32* ovf_head, const u32* ovf
     return w;
 }
 
-// Simulate the walk that starts at untraversed node `start`.  Marks nodes, records the path in walk_next / the detour bit.
+// Simulate the walk that starts at untraversed chain head `start`.  Marks nodes, records the path in walk_next / the detour bit.
+// A chain of forced links is marked as one (only its head carries the mark: interior nodes are never inspected by anyone else).
 AG_HD ag_walk ag_walk_from(const ag_walkctx& w, u32 start) {
     ag_walk r;
-    ag_nodew cur = w.nw[start];
-    r.start_node = start; r.soff = w.node_pos[start]; r.soff0 = cur.moff;
-    u32 v = start, len = 0, ext = 0;
+    const ag_nodew sn = w.nw[start];
+    r.start_node = start; r.soff = w.node_pos[start]; r.soff0 = sn.moff;
+    ag_hrec h = w.hrec[start];
+    u32 v = start, vmisc = sn.misc, len = 0, ext = 0, t;
     for (;;) {
-        // kMerTag == 1 step on an untraversed node (AG:1997-2060)
-        len++;
-        if (cur.misc & AG_NW_HASCONTIG) ext = 1;
-        cur.misc |= AG_NW_TRAV;
-        w.nw[v].misc = cur.misc;
-        if (w.chain) {  // a chain of forced links is marked as one: jump to its tail (interior nodes are never inspected by anyone else)
-            ag_chain c = w.chain[v];
-            if (c.tail != v) { len += c.len - 1; if (c.flg) ext = 1; v = c.tail; cur = w.nw[v]; }
+        // kMerTag == 1 steps over the chain headed by v (AG:1997-2060)
+        vmisc |= AG_NW_TRAV;
+        w.nw[v].misc = vmisc;
+        len += h.len;
+        if (h.flg) ext = 1;
+        t = h.tail;
+        const u32 tmisc = (t == v) ? vmisc : h.tmisc;
+        // untraversed successors of the tail (AG:2020-2032); the hop records of both candidates are fetched with their marks
+        u32 cnt = 0, pick = AG_NONE, pmisc = 0;
+        ag_hrec ph = h;
+        {
+            ag_nodew r0, r1; ag_hrec g0 = h, g1 = h;
+            r0.misc = r1.misc = AG_NW_TRAV;
+            if (h.ts0 != AG_NONE) { r0 = w.nw[h.ts0]; g0 = w.hrec[h.ts0]; }
+            if (h.ts1 != AG_NONE) { r1 = w.nw[h.ts1]; g1 = w.hrec[h.ts1]; }
+            if (!(r0.misc & AG_NW_TRAV)) { cnt++; pick = h.ts0; pmisc = r0.misc; ph = g0; }
+            if (!(r1.misc & AG_NW_TRAV)) { cnt++; pick = h.ts1; pmisc = r1.misc; ph = g1; }
+            if (tmisc & AG_NW_OVF)
+                for (u32 o = w.ovf_head[t]; o != AG_NONE; o = w.ovf_next[o]) {
+                    const u32 s = w.ovf_target[o]; const ag_nodew rr = w.nw[s];
+                    if (!(rr.misc & AG_NW_TRAV)) { cnt++; pick = s; pmisc = rr.misc; ph = w.hrec[s]; }
+                }
         }
-        u32 pick; ag_nodew prec;
-        u32 cnt = ag_live_succ(w, v, cur, pick, prec);
-        if (cnt == 1) { w.walk_next[v] = pick; v = pick; cur = prec; continue; }
-        u32 p = w.node_pos[v];
-        u32 c0 = w.cmt.start[p];
+        if (cnt == 1) { w.walk_next[t] = pick; v = pick; vmisc = pmisc; h = ph; continue; }
+        const u32 p = w.node_pos[t];
+        const u32 c0 = w.cmt.start[p];
         if (w.cmt.start[p + 1] - c0 == 1 && w.cmt.cm[c0].chain != w.cmt.cm[c0].term) {
             // switch to the contiMer thread (AG:2047-2057), run to its terminal (AG:2064-2072), try to re-enter (AG:2093-2136)
-            ag_cm m = w.cmt.cm[c0];
+            const ag_cm m = w.cmt.cm[c0];
             len += m.term - m.chain; ext = 1;
-            w.nw[v].misc = cur.misc | AG_NW_DETOUR;
-            u32 z = w.chain_pos[m.term];
+            w.nw[t].misc = tmisc | AG_NW_DETOUR;
+            const u32 z = w.chain_pos[m.term];
             u32 live = 0, item = AG_NONE; ag_nodew irec;
             for (u32 x = w.pos_node[z]; x < w.pos_node[z + 1]; x++) { ag_nodew xr = w.nw[x]; if (!(xr.misc & AG_NW_TRAV)) { live++; item = x; irec = xr; } }
             u32 pick2 = AG_NONE, cnt2 = 0; ag_nodew prec2;
             if (live == 1) cnt2 = ag_live_succ(w, item, irec, pick2, prec2);
-            if (cnt2 == 1) { w.walk_next[v] = pick2; v = pick2; cur = prec2; continue; }
-            w.walk_next[v] = AG_NONE;
+            if (cnt2 == 1) { w.walk_next[t] = pick2; v = pick2; vmisc = prec2.misc; h = w.hrec[pick2]; continue; }
+            w.walk_next[t] = AG_NONE;
             r.eoff = z; r.eoff0 = AG_NONE; r.flags = ext | (1u << 1);  // kMerTag -2
             break;
         }
-        w.walk_next[v] = AG_NONE;
-        r.eoff = p; r.eoff0 = cur.moff; r.flags = ext | (0u << 1);  // kMerTag -1
+        w.walk_next[t] = AG_NONE;
+        r.eoff = p; r.eoff0 = h.tmoff; r.flags = ext | (0u << 1);  // kMerTag -1
         break;
     }
-    r.len = len; r.last_node = v;
+    r.len = len; r.last_node = t;
     return r;
+}
+
+// hop record of chain head v (k_hrec)
+AG_HD ag_hrec ag_make_hrec(const ag_chain& c, const ag_nodew& tail) {
+    ag_hrec h; h.tail = c.tail; h.len = c.len; h.flg = c.flg; h.ts0 = tail.succ0; h.ts1 = tail.succ1; h.tmisc = tail.misc; h.tmoff = tail.moff; h.pad = 0;
+    return h;
 }
 
 // ---- exact sequential replay with chains ----------------------------------------------------------------------------------

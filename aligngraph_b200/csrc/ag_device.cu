@@ -170,7 +170,7 @@ struct DevView {
     u32* eovf_head; u32* eovf_target; u32* eovf_next; u32* eovf_count; u32 eovf_cap;
     u32* walk_next; u32* parent; u32* cmin; u32* cmax;
     u32* cand_rank; u32* cand_node; u32* cand_label;
-    unsigned char* pos_term; u32* indeg; u32* fnext; u32* fprev; u32* msuf; u32* mnode; ag_chain* chain_a; ag_chain* chain_b; const ag_chain* chain; int* changed;
+    unsigned char* pos_term; u32* indeg; u32* fnext; u32* fprev; u32* msuf; u32* mnode; ag_chain* chain_a; ag_chain* chain_b; const ag_chain* chain; ag_hrec* hrec; int* changed;
     ag_walk* walks; ag_walk* walks_sorted; u32* walk_count; u32 walk_cap;
     int* err;
     int k, iv, coverage;
@@ -592,7 +592,7 @@ __global__ void k_uf_flatten(DevView d, u32 n_cand) {
 __device__ __forceinline__ ag_walkctx make_ctx(const DevView& d) {
     ag_walkctx w;
     w.nw = d.node_w; w.node_pos = d.node_pos; w.pos_node = d.pos_node; w.ovf_head = d.eovf_head; w.ovf_target = d.eovf_target;
-    w.ovf_next = d.eovf_next; w.cmt = d.cmt; w.chain_pos = d.chain_pos; w.walk_next = d.walk_next; w.chain = d.chain; w.msuf = d.msuf; w.mnode = d.mnode; w.fprev = d.fprev;
+    w.ovf_next = d.eovf_next; w.cmt = d.cmt; w.chain_pos = d.chain_pos; w.walk_next = d.walk_next; w.chain = d.chain; w.hrec = d.hrec; w.msuf = d.msuf; w.mnode = d.mnode; w.fprev = d.fprev;
     return w;
 }
 __device__ __forceinline__ void push_walk(const DevView& d, ag_walk r) {
@@ -668,6 +668,15 @@ __global__ void k_cand_scatter(DevView d, u32 n_nodes, const u32* flag) {
     d.cand_node[i] = v;
 }
 
+// hop records of the chain heads (= start candidates)
+__global__ void k_hrec(DevView d, u32 n_cand) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cand) return;
+    const u32 v = d.cand_node[i];
+    const ag_chain c = d.chain[v];
+    d.hrec[v] = ag_make_hrec(c, d.node_w[c.tail]);
+}
+
 // one thread per component (the candidate whose chain tail is the union-find root): replay the scan (AG:1972-1990) over the
 // component's start candidates, in node order
 __global__ void k_walk_components(DevView d, u32 n_cand) {
@@ -686,13 +695,15 @@ __global__ void k_walk_components(DevView d, u32 n_cand) {
 }
 
 // put the walk records in scan order (= by start node): flag the start nodes, exclusive scan, scatter
-__global__ void k_walk_flag(DevView d, u32 nw, u32* flag) {
+// `key` maps a start node to its slot in scan order: the candidate index (component replay: every walk starts at a chain head, and the
+// candidates are compacted in node order) or, with key == nullptr, the node index itself (sequential replay: any node can start a walk)
+__global__ void k_walk_flag(DevView d, u32 nw, const u32* __restrict__ key, u32* flag) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nw) flag[d.walks[i].start_node] = 1;
+    if (i < nw) { const u32 s = d.walks[i].start_node; flag[key ? key[s] : s] = 1; }
 }
-__global__ void k_walk_scatter(DevView d, u32 nw, const u32* rank) {
+__global__ void k_walk_scatter(DevView d, u32 nw, const u32* __restrict__ key, const u32* rank) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nw) { ag_walk r = d.walks[i]; d.walks_sorted[rank[r.start_node]] = r; }
+    if (i < nw) { ag_walk r = d.walks[i]; const u32 s = r.start_node; d.walks_sorted[rank[key ? key[s] : s]] = r; }
 }
 
 // exact sequential replay including the 1000-position skip (AG:2194-2202); used only when a >100 kbp contig was emitted
@@ -829,7 +840,7 @@ struct AgDevice::Impl {
     DBuf<u32> pos_node;
     DBuf<ag_nodec> node_c; DBuf<ag_nodew> node_w; DBuf<u32> node_sref, node_pos, node_cc;
     DBuf<u32> eovf_head, eovf_target, eovf_next;
-    DBuf<u32> walk_next, parent, cmin, cmax; DBuf<ag_walk> walks, walks2; DBuf<ag_cm1> cm1; DBuf<MatItem> mat_detours; DBuf<u32> tail_end; u32 n_cand = 0; DBuf<unsigned char> pos_term; DBuf<u32> indeg, fnext, fprev, msuf, mnode, cand_rank, cand_node, cand_label; DBuf<ag_chain> chain_a, chain_b; DBuf<int> changed;
+    DBuf<u32> walk_next, parent, cmin, cmax; DBuf<ag_walk> walks, walks2; DBuf<ag_cm1> cm1; DBuf<MatItem> mat_detours; DBuf<u32> tail_end; u32 n_cand = 0; DBuf<unsigned char> pos_term; DBuf<u32> indeg, fnext, fprev, msuf, mnode, cand_rank, cand_node, cand_label; DBuf<ag_chain> chain_a, chain_b; DBuf<ag_hrec> hrec; DBuf<int> changed;
     DBuf<unsigned char> out_bases, occ; DBuf<u32> sel_start, sel_tails; DBuf<u64> sel_off;
     PinnedBuf h_walks, h_bases, h_occ, h_sel;
     Scanner scanner;
@@ -862,7 +873,7 @@ AgDevice::~AgDevice() {
     for (auto* b : b32) b->release();
     for (int i = 0; i < 4; i++) m.scanner.lvl[i].release();
     m.cm.release(); m.cthreads.release(); m.aln.release(); m.ext.release(); m.alnp.release(); m.fast.release(); m.pool_c.release(); m.pool_w.release(); m.ovf_node.release(); m.err.release();
-    m.node_c.release(); m.node_w.release(); m.walks.release(); m.walks2.release(); m.cm1.release(); m.mat_detours.release(); m.tail_end.release(); m.pos_term.release(); m.cand_rank.release(); m.cand_node.release(); m.cand_label.release(); m.fprev.release(); m.msuf.release(); m.mnode.release(); m.indeg.release(); m.fnext.release(); m.chain_a.release(); m.chain_b.release(); m.changed.release(); m.sel_off.release();
+    m.node_c.release(); m.node_w.release(); m.walks.release(); m.walks2.release(); m.cm1.release(); m.mat_detours.release(); m.tail_end.release(); m.pos_term.release(); m.cand_rank.release(); m.cand_node.release(); m.cand_label.release(); m.fprev.release(); m.msuf.release(); m.mnode.release(); m.indeg.release(); m.fnext.release(); m.chain_a.release(); m.chain_b.release(); m.hrec.release(); m.changed.release(); m.sel_off.release();
     m.h_walks.release(); m.h_bases.release(); m.h_occ.release(); m.h_sel.release();
     if (m.st) cudaStreamDestroy(m.st);
     delete m_;
@@ -1152,6 +1163,8 @@ void AgDevice::walk_components() {
     unsigned gc = (nc + 255) / 256;
     {
         Timer tm(st);
+        m.hrec.ensure((size_t)nn + 1); d.hrec = m.hrec.p;
+        k_hrec<<<gc, 256, 0, st>>>(d, nc); launches_++;
         k_uf_tails<<<gc, 256, 0, st>>>(d, nc); launches_++;
         k_uf_flatten<<<gc, 256, 0, st>>>(d, nc); launches_++;
         t_.components += tm.stop();
@@ -1200,10 +1213,12 @@ void AgDevice::extend(std::vector<ag_walk>& walks) {
         if (err) throw AgError{"walk record buffer exhausted"};
         walks.resize(nw);
         if (nw) {  // records into scan order on the device (the component threads append them in arbitrary order)
-            CK(cudaMemsetAsync(m.parent.p, 0, (size_t)nn * sizeof(u32), st));
-            k_walk_flag<<<(nw + 255) / 256, 256, 0, st>>>(d, nw, m.parent.p); launches_++;
-            m.scanner.run(m.parent.p, m.cmin.p, nn, st);
-            k_walk_scatter<<<(nw + 255) / 256, 256, 0, st>>>(d, nw, m.cmin.p); launches_++;
+            const u32* key = chains_valid_ ? m.cand_rank.p : nullptr;
+            const size_t slots = chains_valid_ ? (size_t)m.n_cand : (size_t)nn;
+            CK(cudaMemsetAsync(m.parent.p, 0, slots * sizeof(u32), st));
+            k_walk_flag<<<(nw + 255) / 256, 256, 0, st>>>(d, nw, key, m.parent.p); launches_++;
+            m.scanner.run(m.parent.p, m.cmin.p, slots, st);
+            k_walk_scatter<<<(nw + 255) / 256, 256, 0, st>>>(d, nw, key, m.cmin.p); launches_++;
             m.h_walks.ensure((size_t)nw * sizeof(ag_walk));
             CK(cudaMemcpyAsync(m.h_walks.p, m.walks2.p, (size_t)nw * sizeof(ag_walk), cudaMemcpyDeviceToHost, st));
         }
