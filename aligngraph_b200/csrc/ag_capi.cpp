@@ -18,7 +18,7 @@ struct ag_ctx {
     AgDevice* dev = nullptr;
     ag_params params{};
     AgReads reads;
-    bool have_reads = false;
+    bool have_reads = false, reads_dirty = false;   // reads_dirty: a re-upload was requested; it is issued by the next ag_build, behind the unit's uploads
     AgUnit unit;
     int unit_id = -1;
     bool uploaded = false;  // the staged unit arrays are resident on the device
@@ -58,13 +58,14 @@ const char* ag_create_error(void) { return g_create_error.c_str(); }
 
 // host -> device copy of the context's packed reads.  The non-ACGT bit plane is all zeros except where the parser recorded an exception,
 // so when that list is complete only the list travels (8 bytes per non-ACGT character) and the device rebuilds the plane.
-static void upload_reads(ag_ctx* ctx) {
+static void upload_reads(ag_ctx* ctx, bool overlap = false) {
     const AgReads& r = ctx->reads;
     if (r.exc_complete && r.exc.size() * 8 < r.nmask.size() * 4) {
         ctx->exc_keys.resize(r.exc.size());
         for (size_t i = 0; i < r.exc.size(); i++) ctx->exc_keys[i] = r.exc[i].first;
-        ctx->dev->set_reads_sparse(r.bases.data(), ctx->exc_keys.data(), ctx->exc_keys.size(), r.len.data(), r.n_pairs, r.stride2, r.stridem);
+        ctx->dev->set_reads_sparse(r.bases.data(), ctx->exc_keys.data(), ctx->exc_keys.size(), r.len.data(), r.n_pairs, r.stride2, r.stridem, overlap);
     } else ctx->dev->set_reads(r.bases.data(), r.nmask.data(), r.len.data(), r.n_pairs, r.stride2, r.stridem, false);
+    ctx->reads_dirty = false;
 }
 
 int ag_set_reads(ag_ctx* ctx, const uint32_t* bases2, const uint32_t* nmask, const uint16_t* pair_len, uint64_t n_pairs, uint32_t stride2, uint32_t stridem) {
@@ -162,6 +163,7 @@ int ag_build(ag_ctx* ctx) {
         if (!ctx->have_reads) throw AgHostError{"reads not set"};
         auto t0 = std::chrono::steady_clock::now();
         if (!ctx->uploaded) { ctx->dev->load_unit(ag_unit_input(ctx->unit)); ctx->uploaded = true; }
+        if (ctx->reads_dirty) upload_reads(ctx, true);   // overlaps the unit's table / prep / bucket kernels
         ctx->dev->build();
         ctx->s_device += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         ctx->n_aln += ctx->unit.aln.size();
@@ -332,7 +334,8 @@ void* ag_cuda_stream(ag_ctx* ctx) { return ctx ? ctx->dev->stream() : nullptr; }
 int ag_invalidate_device_inputs(ag_ctx* ctx) { return guard(ctx, [&] { ctx->uploaded = false; }); }
 int ag_reupload_reads(ag_ctx* ctx) {
     return guard(ctx, [&] {
-        upload_reads(ctx);
+        if (!ctx->have_reads) throw AgHostError{"reads not set"};
+        ctx->reads_dirty = true;
     });
 }
 int ag_formalize_inputs(ag_ctx* ctx, const char* contig_fa, const char* genome_fa, const char* tmp_dir, int part, int* n_units) {

@@ -875,6 +875,7 @@ AgDevice::~AgDevice() {
     m.cm.release(); m.cthreads.release(); m.aln.release(); m.ext.release(); m.alnp.release(); m.fast.release(); m.pool_c.release(); m.pool_w.release(); m.ovf_node.release(); m.err.release();
     m.node_c.release(); m.node_w.release(); m.walks.release(); m.walks2.release(); m.cm1.release(); m.mat_detours.release(); m.tail_end.release(); m.pos_term.release(); m.cand_rank.release(); m.cand_node.release(); m.cand_label.release(); m.fprev.release(); m.msuf.release(); m.mnode.release(); m.indeg.release(); m.fnext.release(); m.chain_a.release(); m.chain_b.release(); m.hrec.release(); m.changed.release(); m.sel_off.release();
     m.h_walks.release(); m.h_bases.release(); m.h_occ.release(); m.h_sel.release();
+    if (st2_) { cudaStreamSynchronize((cudaStream_t)st2_); cudaStreamDestroy((cudaStream_t)st2_); cudaEventDestroy((cudaEvent_t)ev_main_); cudaEventDestroy((cudaEvent_t)ev_reads_); }
     if (m.st) cudaStreamDestroy(m.st);
     delete m_;
 }
@@ -904,7 +905,7 @@ float AgDevice::timer_stop() {
     float ms = 0; CK(cudaEventElapsedTime(&ms, (cudaEvent_t)ev0_, (cudaEvent_t)ev1_));
     return ms;
 }
-void AgDevice::sync() { CK(cudaSetDevice(dev_)); CK(cudaStreamSynchronize(m_->st)); }
+void AgDevice::sync() { CK(cudaSetDevice(dev_)); if (st2_) CK(cudaStreamSynchronize((cudaStream_t)st2_)); CK(cudaStreamSynchronize(m_->st)); }
 
 void AgDevice::set_reads(const u32* bases, const u32* nmask, const uint16_t* len, u64 n_pairs, u32 stride2, u32 stridem, bool on_device) {
     CK(cudaSetDevice(dev_));
@@ -925,19 +926,27 @@ void AgDevice::set_reads(const u32* bases, const u32* nmask, const uint16_t* len
     m.reads.stride2 = stride2; m.reads.stridem = stridem;
 }
 
-void AgDevice::set_reads_sparse(const u32* bases, const u64* exc_keys, u64 n_exc, const uint16_t* len, u64 n_pairs, u32 stride2, u32 stridem) {
+void AgDevice::set_reads_sparse(const u32* bases, const u64* exc_keys, u64 n_exc, const uint16_t* len, u64 n_pairs, u32 stride2, u32 stridem, bool overlap) {
     CK(cudaSetDevice(dev_));
     Impl& m = *m_;
     m.n_pairs = n_pairs;
     Timer tm(m.st);
     m.r_bases.ensure(2 * n_pairs * stride2 + 1); m.r_nmask.ensure(2 * n_pairs * stridem + 1); m.r_len.ensure(n_pairs + 1); m.r_exc.ensure(n_exc + 1);
-    CK(cudaMemcpyAsync(m.r_bases.p, bases, 2 * n_pairs * stride2 * sizeof(u32), cudaMemcpyHostToDevice, m.st));
-    CK(cudaMemcpyAsync(m.r_len.p, len, n_pairs * sizeof(uint16_t), cudaMemcpyHostToDevice, m.st));
-    CK(cudaMemsetAsync(m.r_nmask.p, 0, 2 * n_pairs * stridem * sizeof(u32), m.st));
-    if (n_exc) {
-        CK(cudaMemcpyAsync(m.r_exc.p, exc_keys, n_exc * sizeof(u64), cudaMemcpyHostToDevice, m.st));
-        k_nmask_scatter<<<(unsigned)((n_exc + 255) / 256), 256, 0, m.st>>>(m.r_exc.p, n_exc, m.r_nmask.p, stridem, 2 * n_pairs); launches_++;
+    CK(cudaMemcpyAsync(m.r_len.p, len, n_pairs * sizeof(uint16_t), cudaMemcpyHostToDevice, m.st));   // k_prep needs the lengths: main stream
+    cudaStream_t cs = m.st;
+    if (overlap) {
+        if (!st2_) { cudaStream_t s2; cudaEvent_t a, b; CK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming)); st2_ = s2; ev_main_ = a; ev_reads_ = b; }
+        cs = (cudaStream_t)st2_;
+        CK(cudaEventRecord((cudaEvent_t)ev_main_, m.st));            // behind everything already queued on the main stream
+        CK(cudaStreamWaitEvent(cs, (cudaEvent_t)ev_main_, 0));
     }
+    CK(cudaMemcpyAsync(m.r_bases.p, bases, 2 * n_pairs * stride2 * sizeof(u32), cudaMemcpyHostToDevice, cs));
+    CK(cudaMemsetAsync(m.r_nmask.p, 0, 2 * n_pairs * stridem * sizeof(u32), cs));
+    if (n_exc) {
+        CK(cudaMemcpyAsync(m.r_exc.p, exc_keys, n_exc * sizeof(u64), cudaMemcpyHostToDevice, cs));
+        k_nmask_scatter<<<(unsigned)((n_exc + 255) / 256), 256, 0, cs>>>(m.r_exc.p, n_exc, m.r_nmask.p, stridem, 2 * n_pairs); launches_++;
+    }
+    if (overlap) { CK(cudaEventRecord((cudaEvent_t)ev_reads_, cs)); reads_pending_ = true; }
     m.reads.bases = m.r_bases.p; m.reads.nmask = m.r_nmask.p; m.reads.len = m.r_len.p; m.reads_owned = true;
     m.reads.stride2 = stride2; m.reads.stridem = stridem;
     t_.h2d += tm.stop();
@@ -947,6 +956,7 @@ void AgDevice::set_reads_sparse(const u32* bases, const u64* exc_keys, u64 n_exc
 void AgDevice::copy_reads_to_host(u32* bases, u32* nmask, uint16_t* len) {
     CK(cudaSetDevice(dev_));
     Impl& m = *m_;
+    if (st2_) CK(cudaStreamSynchronize((cudaStream_t)st2_));
     CK(cudaMemcpyAsync(bases, m.reads.bases, 2 * m.n_pairs * m.reads.stride2 * sizeof(u32), cudaMemcpyDeviceToHost, m.st));
     CK(cudaMemcpyAsync(nmask, m.reads.nmask, 2 * m.n_pairs * m.reads.stridem * sizeof(u32), cudaMemcpyDeviceToHost, m.st));
     CK(cudaMemcpyAsync(len, m.reads.len, m.n_pairs * sizeof(uint16_t), cudaMemcpyDeviceToHost, m.st));
@@ -1075,6 +1085,7 @@ void AgDevice::build() {
             d.node_cap = m.node_cap; d.pool_count = m.counters.p + 0;
             d.ovf.node = m.ovf_node.p; d.ovf.next = m.ovf_next.p; d.ovf.count = m.counters.p + 1; d.ovf.cap = m.ovf_cap; d.ovf.err = m.err.p;
             CK(cudaMemsetAsync(m.tile_flag.p, 0, ((size_t)m.n_tiles + 1) * sizeof(u32), st));
+            if (reads_pending_) { CK(cudaStreamWaitEvent(st, (cudaEvent_t)ev_reads_, 0)); reads_pending_ = false; }   // overlapped reads upload (set_reads_sparse)
             if (m.n_tiles) { k_build<<<m.n_tiles, AG_TILE, NODES_SMEM + NCHUNK_N * d.rw * 4, st>>>(d); launches_++; }
             int err = 0;
             CK(cudaMemcpyAsync(&err, m.err.p, sizeof(int), cudaMemcpyDeviceToHost, st));

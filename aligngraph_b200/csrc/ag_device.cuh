@@ -38,7 +38,9 @@ public:
     // (the NCCL broadcast target); otherwise they are copied H2D.
     void set_reads(const u32* bases, const u32* nmask, const uint16_t* len, u64 n_pairs, u32 stride2, u32 stridem, bool on_device);
     // the same from host memory, the non-ACGT plane given as its list of set bits (key = read * 65536 + offset): the plane is rebuilt here
-    void set_reads_sparse(const u32* bases, const u64* exc_keys, u64 n_exc, const uint16_t* len, u64 n_pairs, u32 stride2, u32 stridem);
+    // `overlap`: the bulk of the copy (packed bases, exception list) goes on a second stream BEHIND whatever the main stream holds now
+    // (the unit's own uploads), so that it runs under the unit's table / prep / bucket kernels; build() waits for it before the node sweep
+    void set_reads_sparse(const u32* bases, const u64* exc_keys, u64 n_exc, const uint16_t* len, u64 n_pairs, u32 stride2, u32 stridem, bool overlap = false);
     void copy_reads_to_host(u32* bases, u32* nmask, uint16_t* len);
     void set_params(int k, int iv, int coverage) { k_ = k; iv_ = iv; cov_ = coverage; }
     // keep coverage + base counters per node after the build (24 B per node; only the node dump of the tests needs them)
@@ -74,6 +76,8 @@ private:
     AgTimings t_;
     u64 launches_ = 0;
     void *ev0_ = nullptr, *ev1_ = nullptr;
+    void *st2_ = nullptr, *ev_main_ = nullptr, *ev_reads_ = nullptr;   // copy stream of the overlapped reads upload
+    bool reads_pending_ = false;
     std::vector<void*> pinned_;
     bool chains_valid_ = false, attr_done_ = false, keep_counts_ = false;
     void walk_components();
