@@ -97,6 +97,8 @@ void revcomp(std::string& s) {  // AG:854-865
 // reads
 // =============================================================================================================================
 static inline int base_code(char c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1; }
+struct BaseLut { unsigned char v[256]; BaseLut() { for (int i = 0; i < 256; i++) v[i] = 4; v['A'] = 0; v['C'] = 1; v['G'] = 2; v['T'] = 3; } unsigned char operator[](unsigned char c) const { return v[c]; } };
+static const BaseLut kBaseLut;   // 0-3 for ACGT, 4 for anything else (AG:1349 counts those as 'N'; lower case is not ACGT for the reference)
 
 static void pack_init(AgReads& out, size_t n_reads, u32 maxlen) {
     out.stride2 = (maxlen + 15) / 16; out.stridem = (maxlen + 31) / 32;
@@ -216,7 +218,9 @@ static bool parse_reads_parallel(const char* p, size_t n, AgReads& out) {
         }
         nrec[t] = cnt; maxlen[t] = mx;
     };
+    auto tr0 = std::chrono::steady_clock::now();
     { std::vector<std::thread> th; for (int t = 0; t < T; t++) th.emplace_back(scan, t); for (auto& x : th) x.join(); }
+    auto tr1 = std::chrono::steady_clock::now();
     size_t total = 0, mx = 0;
     std::vector<size_t> base((size_t)T + 1, 0);
     for (int t = 0; t < T; t++) { if (bad[t]) return false; base[t] = total; total += nrec[t]; mx = std::max(mx, maxlen[t]); }
@@ -233,18 +237,42 @@ static bool parse_reads_parallel(const char* p, size_t n, AgReads& out) {
             const char* l = (const char*)memchr(sq, '\n', (size_t)(e - sq));
             size_t len = (size_t)(l - sq);
             u32* b = B + r * out.stride2; u32* m = M + r * out.stridem;
-            for (size_t i = 0; i < len; i++) {
-                int c = base_code(sq[i]);
-                if (c < 0) { m[i >> 5] |= 1u << (i & 31); exc[t].push_back({(u64)r * 65536 + i, sq[i]}); }
-                else b[i >> 4] |= (u32)c << ((i & 15) * 2);
+            for (size_t i = 0; i < len; i += 16) {   // one packed word at a time, no read-modify-write per base
+                const size_t w16 = std::min<size_t>(16, len - i);
+                u32 w = 0, nonacgt = 0;
+                size_t j = 0;
+                for (; j + 8 <= w16; j += 8) {   // eight characters per step in a 64-bit word
+                    uint64_t x; memcpy(&x, sq + i + j, 8);
+                    const uint64_t c = ((x >> 1) ^ (x >> 2)) & 0x0303030303030303ull;             // A C G T -> 0 1 2 3 in every byte
+                    const uint64_t c0 = c & 0x0101010101010101ull, c1 = (c >> 1) & 0x0101010101010101ull;
+                    const uint64_t expect = 0x4141414141414141ull + c0 * 2 + c1 * 6 + (c0 & c1) * 0x0B;   // 'A' 'C' 'G' 'T' rebuilt from the code
+                    if (x == expect) {
+                        uint64_t y = (c | (c >> 6)) & 0x000F000F000F000Full;
+                        y = (y | (y >> 12)) & 0x000000FF000000FFull;
+                        y = (y | (y >> 24)) & 0xFFFFull;
+                        w |= (u32)y << (2 * j);
+                    } else {
+                        for (size_t t8 = 0; t8 < 8; t8++) { const u32 cc = kBaseLut[(unsigned char)sq[i + j + t8]]; w |= (cc & 3u) << (2 * (j + t8)); nonacgt |= (cc >> 2) << (j + t8); }
+                    }
+                }
+                for (; j < w16; j++) { const u32 cc = kBaseLut[(unsigned char)sq[i + j]]; w |= (cc & 3u) << (2 * j); nonacgt |= (cc >> 2) << j; }
+                b[i >> 4] = w;
+                if (nonacgt) {
+                    m[i >> 5] |= nonacgt << (i & 31);
+                    for (size_t t16 = 0; t16 < w16; t16++) if ((nonacgt >> t16) & 1) exc[t].push_back({(u64)r * 65536 + i + t16, sq[i + t16]});
+                }
             }
             rlen[r] = (uint16_t)len;
             r++; q = l + 1;
         }
     };
+    auto tr2 = std::chrono::steady_clock::now();
     { std::vector<std::thread> th; for (int t = 0; t < T; t++) th.emplace_back(pack, t); for (auto& x : th) x.join(); }
+    auto tr3 = std::chrono::steady_clock::now();
     for (size_t i = 0; i + 1 < total; i += 2) { if (rlen[i] != rlen[i + 1]) throw AgHostError{"INCONSISTENT PE FILES!"}; out.len[i / 2] = rlen[i]; }
     for (int t = 0; t < T; t++) out.exc.insert(out.exc.end(), exc[t].begin(), exc[t].end());
+    if (getenv("AG_POST_TIMING")) { auto tr4 = std::chrono::steady_clock::now(); auto ms = [](auto a, auto b) { return std::chrono::duration<double>(b - a).count() * 1e3; };
+        fprintf(stderr, "  [reads] scan %.0f ms, alloc %.0f ms, pack %.0f ms, tail %.0f ms (%d threads)\n", ms(tr0, tr1), ms(tr1, tr2), ms(tr2, tr3), ms(tr3, tr4), T); }
     return true;
 }
 

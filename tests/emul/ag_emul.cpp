@@ -387,6 +387,18 @@ int main(int argc, char** argv) {
         std::string a = argv[i];
         if (a == "--dir") dir = argv[++i];
         else if (a == "--dump-nodes") dump = 1;
+        else if (a == "--check-read-packers") {   // the multi-threaded word-at-a-time packer against the character-at-a-time one, on one FASTA file
+            const std::string path = argv[++i];
+            std::vector<std::string> seqs;
+            { FILE* f = fopen(path.c_str(), "rb"); if (!f) return 2; char* line = nullptr; size_t cap = 0; ssize_t n;
+              while ((n = getline(&line, &cap, f)) > 0) { if (line[n - 1] == '\n') n--; if (n && line[0] != '>') seqs.emplace_back(line, (size_t)n); } free(line); fclose(f); }
+            setenv("AG_PARSE_PARALLEL_MIN", "0", 1);
+            AgReads p, q; ag_parse_reads(path, p); ag_pack_reads(seqs, q);
+            const bool ok = p.n_pairs == q.n_pairs && p.stride2 == q.stride2 && p.stridem == q.stridem && p.bases.size() == q.bases.size() &&
+                            memcmp(p.bases.data(), q.bases.data(), p.bases.size() * 4) == 0 && memcmp(p.nmask.data(), q.nmask.data(), p.nmask.size() * 4) == 0 && p.len == q.len && p.exc == q.exc;
+            printf("%s pairs=%lu exceptions=%zu\n", ok ? "IDENTICAL" : "DIFFERENT", (unsigned long)p.n_pairs, p.exc.size());
+            return ok ? 0 : 1;
+        }
         else if (a == "--first") first = atoi(argv[++i]);
         else if (a == "--last") last = atoi(argv[++i]);
         else { fprintf(stderr, "ag_emul: unknown option %s\n", a.c_str()); return 2; }

@@ -90,3 +90,20 @@ def test_empty_line_truncates_like_the_reference(harness, workdir):
     harness.run_oracle(base)
     harness.run_emul(other, env={"AG_PARSE_PARALLEL_MIN": "0", "AG_THREADS": "4"})
     assert harness.unit_outputs(base, 0) == harness.unit_outputs(other, 0)
+
+
+def test_word_at_a_time_read_packer_equals_sequential(harness, tmp_path):
+    """The multi-threaded reads parser packs eight characters per step (64-bit SWAR); on reads full of N, IUPAC and lower-case
+    characters and of ragged lengths it must produce exactly the arrays of the character-at-a-time packer."""
+    import random
+    import subprocess
+    rnd = random.Random(5)
+    alphabet = "ACGTACGTACGTACGTNacgtRY"
+    path = tmp_path / "mix.fa"
+    with open(path, "w") as f:
+        for i in range(20000):
+            n = 37 + (rnd.randrange(120) if i % 3 == 0 else 100)
+            for _ in range(2):
+                f.write(f">{i}\n{''.join(rnd.choice(alphabet) for _ in range(n))}\n")
+    r = subprocess.run([harness.EMUL, "--check-read-packers", str(path)], capture_output=True, text=True)
+    assert r.returncode == 0 and "IDENTICAL" in r.stdout, r.stdout + r.stderr
