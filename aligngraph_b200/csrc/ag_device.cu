@@ -677,16 +677,33 @@ __global__ void k_hrec(DevView d, u32 n_cand) {
     d.hrec[v] = ag_make_hrec(c, d.node_w[c.tail]);
 }
 
-// one thread per component (the candidate whose chain tail is the union-find root): replay the scan (AG:1972-1990) over the
-// component's start candidates, in node order
+// One WARP per component (the warp of the candidate whose chain tail is the union-find root): the replay of the scan (AG:1972-1990)
+// over the component's start candidates, in node order, is sequential and runs on lane 0; the critical path of the whole kernel is the
+// largest component (a few hundred candidates, every one two or three dependent loads of never-touched lines).  So all 32 lanes first
+// pull the records the replay is going to read — walk record, hop record, position, founder string of every candidate, and the walk
+// records of the chain tails and of their successors — into L1/L2.
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 __global__ void k_walk_components(DevView d, u32 n_cand) {
-    u32 i0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 i0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (i0 >= n_cand) return;
     const u32 r = d.chain[d.cand_node[i0]].tail;
     if (d.parent[r] != r) return;
+    const u32 lo = d.cmin[r], hi = d.cmax[r];
+    if (hi - lo >= 8) {
+        for (u32 i = lo + lane; i <= hi; i += 32) {
+            if (d.cand_label[i] != r) continue;
+            const u32 v = d.cand_node[i];
+            prefetch_l1(&d.node_w[v]); prefetch_l1(&d.node_pos[v]);
+            const ag_hrec h = d.hrec[v];
+            prefetch_l1(&d.node_w[h.tail]); prefetch_l1(&d.node_pos[h.tail]); prefetch_l1(&d.walk_next[h.tail]); prefetch_l1(&d.node_sref[2 * (size_t)h.tail]);
+            if (h.ts0 != AG_NONE) prefetch_l1(&d.node_w[h.ts0]);
+            if (h.ts1 != AG_NONE) prefetch_l1(&d.node_w[h.ts1]);
+        }
+        __syncwarp();
+    }
+    if (lane) return;
     ag_walkctx w = make_ctx(d);
-    const u32 hi = d.cmax[r];
-    for (u32 i = d.cmin[r]; i <= hi; i++) {
+    for (u32 i = lo; i <= hi; i++) {
         if (d.cand_label[i] != r) continue;
         u32 v = d.cand_node[i];
         if (d.node_w[v].misc & AG_NW_TRAV) continue;
@@ -694,7 +711,6 @@ __global__ void k_walk_components(DevView d, u32 n_cand) {
     }
 }
 
-// put the walk records in scan order (= by start node): flag the start nodes, exclusive scan, scatter
 // `key` maps a start node to its slot in scan order: the candidate index (component replay: every walk starts at a chain head, and the
 // candidates are compacted in node order) or, with key == nullptr, the node index itself (sequential replay: any node can start a walk)
 __global__ void k_walk_flag(DevView d, u32 nw, const u32* __restrict__ key, u32* flag) {
@@ -817,10 +833,12 @@ __global__ void k_occupancy(DevView d, unsigned char* bits) {
     bits[b] = x;
 }
 
-struct Timer {
+struct Timer {   // section timer: CUDA events on the launching stream; the event pair is cached per host thread (sections never nest)
     cudaEvent_t a, b; cudaStream_t st;
-    Timer(cudaStream_t s) : st(s) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); }
-    float stop() { cudaEventRecord(b, st); cudaEventSynchronize(b); float ms = 0; cudaEventElapsedTime(&ms, a, b); cudaEventDestroy(a); cudaEventDestroy(b); return ms; }
+    static cudaEvent_t* pair() { static thread_local cudaEvent_t ev[2] = {nullptr, nullptr}; static thread_local int dev = -1; int cur = -1; cudaGetDevice(&cur);
+                                 if (!ev[0] || dev != cur) { cudaEventCreate(&ev[0]); cudaEventCreate(&ev[1]); dev = cur; } return ev; }
+    Timer(cudaStream_t s) : st(s) { cudaEvent_t* e = pair(); a = e[0]; b = e[1]; cudaEventRecord(a, st); }
+    float stop() { cudaEventRecord(b, st); cudaEventSynchronize(b); float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
 };
 
 }  // namespace
@@ -842,7 +860,7 @@ struct AgDevice::Impl {
     DBuf<u32> eovf_head, eovf_target, eovf_next;
     DBuf<u32> walk_next, parent, cmin, cmax; DBuf<ag_walk> walks, walks2; DBuf<ag_cm1> cm1; DBuf<MatItem> mat_detours; DBuf<u32> tail_end; u32 n_cand = 0; DBuf<unsigned char> pos_term; DBuf<u32> indeg, fnext, fprev, msuf, mnode, cand_rank, cand_node, cand_label; DBuf<ag_chain> chain_a, chain_b; DBuf<ag_hrec> hrec; DBuf<int> changed;
     DBuf<unsigned char> out_bases, occ; DBuf<u32> sel_start, sel_tails; DBuf<u64> sel_off;
-    PinnedBuf h_walks, h_bases, h_occ, h_sel;
+    PinnedBuf h_walks, h_bases, h_occ, h_sel, h_s;   // h_s: page-locked landing zone of the scalar read-backs (a pageable destination makes every copy a synchronous staged transfer)
     Scanner scanner;
     u32 n_tiles = 0, n_keys = 0, n_nodes = 0;
     u32 node_cap = 0, ovf_cap = 0, eovf_cap = 0, walk_cap = 0;
@@ -857,7 +875,7 @@ AgDevice::AgDevice(int device) : m_(new Impl), dev_(device) {
     CK(cudaStreamCreateWithFlags(&m_->st, cudaStreamNonBlocking));
     stream_ = m_->st;
     m_->scanner.launches = &launches_;
-    m_->counters.ensure(8); m_->err.ensure(1);
+    m_->counters.ensure(8); m_->err.ensure(1); m_->h_s.ensure(256);
 }
 AgDevice::~AgDevice() {
     cudaSetDevice(dev_);
@@ -874,7 +892,7 @@ AgDevice::~AgDevice() {
     for (int i = 0; i < 4; i++) m.scanner.lvl[i].release();
     m.cm.release(); m.cthreads.release(); m.aln.release(); m.ext.release(); m.alnp.release(); m.fast.release(); m.pool_c.release(); m.pool_w.release(); m.ovf_node.release(); m.err.release();
     m.node_c.release(); m.node_w.release(); m.walks.release(); m.walks2.release(); m.cm1.release(); m.mat_detours.release(); m.tail_end.release(); m.pos_term.release(); m.cand_rank.release(); m.cand_node.release(); m.cand_label.release(); m.fprev.release(); m.msuf.release(); m.mnode.release(); m.indeg.release(); m.fnext.release(); m.chain_a.release(); m.chain_b.release(); m.hrec.release(); m.changed.release(); m.sel_off.release();
-    m.h_walks.release(); m.h_bases.release(); m.h_occ.release(); m.h_sel.release();
+    m.h_walks.release(); m.h_bases.release(); m.h_occ.release(); m.h_sel.release(); m.h_s.release();
     if (st2_) { cudaStreamSynchronize((cudaStream_t)st2_); cudaStreamDestroy((cudaStream_t)st2_); cudaEventDestroy((cudaEvent_t)ev_main_); cudaEventDestroy((cudaEvent_t)ev_reads_); }
     if (m.st) cudaStreamDestroy(m.st);
     delete m_;
@@ -1040,9 +1058,10 @@ void AgDevice::build() {
         Timer tm(st);
         if (nA) { k_prep<<<(nA + 255) / 256, 256, 0, st>>>(d); launches_++; }
         m.scanner.run(m.ntiles.p, m.key_off.p, nA, st);
-        u32 nk = 0;
-        CK(cudaMemcpyAsync(&nk, m.key_off.p + nA, sizeof(u32), cudaMemcpyDeviceToHost, st));
+        volatile u32* hs = (volatile u32*)m.h_s.p;
+        CK(cudaMemcpyAsync((void*)hs, m.key_off.p + nA, sizeof(u32), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
+        const u32 nk = hs[0];
         m.n_keys = nk;
         m.keys.ensure(nk + 1); m.vals.ensure(nk + 1); m.keys2.ensure(nk + 1); m.vals2.ensure(nk + 1);
         d.keys = m.keys.p; d.vals = m.vals.p;
@@ -1087,10 +1106,11 @@ void AgDevice::build() {
             CK(cudaMemsetAsync(m.tile_flag.p, 0, ((size_t)m.n_tiles + 1) * sizeof(u32), st));
             if (reads_pending_) { CK(cudaStreamWaitEvent(st, (cudaEvent_t)ev_reads_, 0)); reads_pending_ = false; }   // overlapped reads upload (set_reads_sparse)
             if (m.n_tiles) { k_build<<<m.n_tiles, AG_TILE, NODES_SMEM + NCHUNK_N * d.rw * 4, st>>>(d); launches_++; }
-            int err = 0;
-            CK(cudaMemcpyAsync(&err, m.err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(&nn, m.counters.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
+            volatile u32* hs = (volatile u32*)m.h_s.p;
+            CK(cudaMemcpyAsync((void*)(hs + 0), m.err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync((void*)(hs + 1), m.counters.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
+            const int err = (int)hs[0]; nn = hs[1];
             if (err == 0) break;
             if (err == 2) throw AgError{"BOWTIE ALIGNMENT ERROR: alignment outside the unit"};
             if (err == 3 && m.node_cap < (1u << 31)) m.node_cap = m.node_cap * 2;           // node table too small: grow and redo the sweep
@@ -1120,12 +1140,12 @@ void AgDevice::build() {
     {
         Timer tm(st);
         if (m.n_tiles && nn) { k_edges<<<m.n_tiles, AG_TILE, 0, st>>>(d); launches_++; }
-        int err = 0; u32 cnt[4];
-        CK(cudaMemcpyAsync(&err, m.err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(cnt, m.counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+        volatile u32* hs = (volatile u32*)m.h_s.p;
+        CK(cudaMemcpyAsync((void*)(hs + 0), m.err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync((void*)(hs + 4), m.counters.p, 4 * sizeof(u32), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        if (err) throw AgError{"edge overflow pool exhausted"};
-        t_.n_edges_ovf = cnt[2];
+        if (hs[0]) throw AgError{"edge overflow pool exhausted"};
+        t_.n_edges_ovf = hs[4 + 2];
         t_.edges += tm.stop();
     }
 }
@@ -1148,10 +1168,10 @@ void AgDevice::walk_components() {
             k_rank<<<g, 256, 0, st>>>(a, b, nn, m.changed.p); launches_++;
             std::swap(a, b);
             if (round >= 1) {
-                int ch = 0;
-                CK(cudaMemcpyAsync(&ch, m.changed.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+                volatile u32* hs = (volatile u32*)m.h_s.p;
+                CK(cudaMemcpyAsync((void*)hs, m.changed.p, sizeof(int), cudaMemcpyDeviceToHost, st));
                 CK(cudaStreamSynchronize(st));
-                if (!ch) break;
+                if (!hs[0]) break;
             }
         }
         d.chain = a;
@@ -1161,8 +1181,10 @@ void AgDevice::walk_components() {
         k_cand_flag<<<g, 256, 0, st>>>(d, nn, m.indeg.p); launches_++;
         m.scanner.run(m.indeg.p, m.cand_rank.p, nn, st);
         k_cand_scatter<<<g, 256, 0, st>>>(d, nn, m.indeg.p); launches_++;
-        CK(cudaMemcpyAsync(&m.n_cand, m.cand_rank.p + nn, sizeof(u32), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        { volatile u32* hs = (volatile u32*)m.h_s.p;
+          CK(cudaMemcpyAsync((void*)hs, m.cand_rank.p + nn, sizeof(u32), cudaMemcpyDeviceToHost, st));
+          CK(cudaStreamSynchronize(st));
+          m.n_cand = hs[0]; }
         t_.chains += tm.stop();
     }
     const u32 nc = m.n_cand;
@@ -1182,7 +1204,7 @@ void AgDevice::walk_components() {
     }
     {
         Timer tm(st);
-        k_walk_components<<<gc, 256, 0, st>>>(d, nc); launches_++;
+        k_walk_components<<<(unsigned)(((size_t)nc * 32 + 255) / 256), 256, 0, st>>>(d, nc); launches_++;
         t_.walk += tm.stop();
     }
     chains_valid_ = true;
@@ -1217,11 +1239,12 @@ void AgDevice::extend(std::vector<ag_walk>& walks) {
     walk_components();
     auto fetch = [&]() {
         Timer tm(st);
-        u32 nw = 0; int err = 0;
-        CK(cudaMemcpyAsync(&nw, m.counters.p + 3, sizeof(u32), cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(&err, m.err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        volatile u32* hs = (volatile u32*)m.h_s.p;
+        CK(cudaMemcpyAsync((void*)(hs + 0), m.counters.p + 3, sizeof(u32), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync((void*)(hs + 1), m.err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        if (err) throw AgError{"walk record buffer exhausted"};
+        const u32 nw = hs[0];
+        if (hs[1]) throw AgError{"walk record buffer exhausted"};
         walks.resize(nw);
         if (nw) {  // records into scan order on the device (the component threads append them in arbitrary order)
             const u32* key = chains_valid_ ? m.cand_rank.p : nullptr;
@@ -1289,10 +1312,10 @@ void AgDevice::materialize(const std::vector<ag_walk>& walks, const std::vector<
     k_mat_tails<<<((u32)sel.size() + 127) / 128, 128, 0, st>>>(d, m.sel_tails.p, m.sel_off.p, (u32)sel.size(), m.out_bases.p); launches_++;
     m.h_bases.ensure(offs.back());
     CK(cudaMemcpyAsync(m.h_bases.p, m.out_bases.p, offs.back(), cudaMemcpyDeviceToHost, st));
-    int err = 0;
-    CK(cudaMemcpyAsync(&err, m.err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    volatile u32* hs = (volatile u32*)m.h_s.p;
+    CK(cudaMemcpyAsync((void*)hs, m.err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    if (err) throw AgError{"materialise item buffer exhausted"};
+    if (hs[0]) throw AgError{"materialise item buffer exhausted"};
     bases = (char*)m.h_bases.p;   // the post passes read (and patch) the page-locked buffer in place
     t_.materialize += tm.stop();
     t_.h2d_bytes += sel.size() * 24; t_.d2h_bytes += offs.back();

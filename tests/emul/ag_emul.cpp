@@ -270,6 +270,14 @@ public:
         for (u32 i = 0; i < cand.size(); i++) { u32 r = find(chain[cand[i]].tail); label[i] = r; cmin[r] = std::min(cmin[r], i); cmax[r] = std::max(cmax[r], i); }
         ag_walkctx w = ctx();
         // components are replayed from the LAST candidate's root to the first to make sure nothing depends on cross-component order
+        if (getenv("AG_EMUL_COMPONENT_STATS")) {
+            std::vector<u32> sz(n_nodes, 0); u32 ncomp = 0, mx = 0, mxspan = 0; std::vector<u32> hist(8, 0);
+            for (u32 i = 0; i < cand.size(); i++) sz[label[i]]++;
+            for (u32 v = 0; v < n_nodes; v++) if (sz[v]) { ncomp++; mx = std::max(mx, sz[v]); mxspan = std::max(mxspan, cmax[v] - cmin[v] + 1); u32 b = 0; while ((1u << (2 * b + 2)) <= sz[v] && b < 7) b++; hist[b]++; }
+            fprintf(stderr, "components: %u over %zu candidates, largest %u candidates, widest candidate range %u; sizes <4,<16,<64,<256,<1k,<4k,<16k,more:", ncomp, cand.size(), mx, mxspan);
+            for (u32 b = 0; b < 8; b++) fprintf(stderr, " %u", hist[b]);
+            fprintf(stderr, "\n");
+        }
         for (u32 i0 = (u32)cand.size(); i0-- > 0;) {
             const u32 r = chain[cand[i0]].tail;
             if (find(r) != r) continue;
