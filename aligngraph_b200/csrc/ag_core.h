@@ -588,11 +588,9 @@ AG_HD ag_walk ag_walk_from(const ag_walkctx& w, u32 start) {
                 }
         }
         if (cnt == 1) { w.walk_next[t] = pick; v = pick; vmisc = pmisc; h = ph; continue; }
-        const u32 p = w.node_pos[t];
-        const u32 c0 = w.cmt.start[p];
-        if (w.cmt.start[p + 1] - c0 == 1 && w.cmt.cm[c0].chain != w.cmt.cm[c0].term) {
+        if (h.tcm != AG_NONE) {
             // switch to the contiMer thread (AG:2047-2057), run to its terminal (AG:2064-2072), try to re-enter (AG:2093-2136)
-            const ag_cm m = w.cmt.cm[c0];
+            const ag_cm m = w.cmt.cm[h.tcm];
             len += m.term - m.chain; ext = 1;
             w.nw[t].misc = tmisc | AG_NW_DETOUR;
             const u32 z = w.chain_pos[m.term];
@@ -606,16 +604,18 @@ AG_HD ag_walk ag_walk_from(const ag_walkctx& w, u32 start) {
             break;
         }
         w.walk_next[t] = AG_NONE;
-        r.eoff = p; r.eoff0 = h.tmoff; r.flags = ext | (0u << 1);  // kMerTag -1
+        r.eoff = w.node_pos[t]; r.eoff0 = h.tmoff; r.flags = ext | (0u << 1);  // kMerTag -1
         break;
     }
     r.len = len; r.last_node = t;
     return r;
 }
 
-// hop record of chain head v (k_hrec)
-AG_HD ag_hrec ag_make_hrec(const ag_chain& c, const ag_nodew& tail) {
-    ag_hrec h; h.tail = c.tail; h.len = c.len; h.flg = c.flg; h.ts0 = tail.succ0; h.ts1 = tail.succ1; h.tmisc = tail.misc; h.tmoff = tail.moff; h.pad = 0;
+// hop record of chain head v (k_hrec); p = unit position of the chain's tail
+AG_HD ag_hrec ag_make_hrec(const ag_chain& c, const ag_nodew& tail, const ag_cmtab& cmt, u32 p) {
+    ag_hrec h; h.tail = c.tail; h.len = c.len; h.flg = c.flg; h.ts0 = tail.succ0; h.ts1 = tail.succ1; h.tmisc = tail.misc; h.tmoff = tail.moff;
+    const u32 c0 = cmt.start[p];
+    h.tcm = (cmt.start[p + 1] - c0 == 1 && cmt.cm[c0].chain != cmt.cm[c0].term) ? c0 : AG_NONE;
     return h;
 }
 

@@ -171,7 +171,7 @@ struct DevView {
     u32* walk_next; u32* parent; u32* cmin; u32* cmax;
     u32* cand_rank; u32* cand_node; u32* cand_label;
     unsigned char* pos_term; u32* indeg; u32* fnext; u32* fprev; u32* msuf; u32* mnode; ag_chain* chain_a; ag_chain* chain_b; const ag_chain* chain; ag_hrec* hrec; int* changed;
-    ag_walk* walks; ag_walk* walks_sorted; u32* walk_count; u32 walk_cap;
+    ag_walk* walks; ag_walk* walks_sorted; u32* walk_count; u32 walk_cap; u32* walk_used;
     int* err;
     int k, iv, coverage;
     u32 rw;  // words per staged read (stride2 + stridem) when the tile sweeps keep the chunk's reads in shared memory, else 0
@@ -674,7 +674,7 @@ __global__ void k_hrec(DevView d, u32 n_cand) {
     if (i >= n_cand) return;
     const u32 v = d.cand_node[i];
     const ag_chain c = d.chain[v];
-    d.hrec[v] = ag_make_hrec(c, d.node_w[c.tail]);
+    d.hrec[v] = ag_make_hrec(c, d.node_w[c.tail], d.cmt, d.node_pos[c.tail]);
 }
 
 // One WARP per component (the warp of the candidate whose chain tail is the union-find root): the replay of the scan (AG:1972-1990)
@@ -707,19 +707,21 @@ __global__ void k_walk_components(DevView d, u32 n_cand) {
         if (d.cand_label[i] != r) continue;
         u32 v = d.cand_node[i];
         if (d.node_w[v].misc & AG_NW_TRAV) continue;
-        push_walk(d, ag_walk_from(w, v));
+        d.walks[i] = ag_walk_from(w, v);   // slot = candidate index: no counter on the sequential path; fetch() compacts the used slots in order
+        d.walk_used[i] = 1;
     }
 }
 
 // `key` maps a start node to its slot in scan order: the candidate index (component replay: every walk starts at a chain head, and the
 // candidates are compacted in node order) or, with key == nullptr, the node index itself (sequential replay: any node can start a walk)
-__global__ void k_walk_flag(DevView d, u32 nw, const u32* __restrict__ key, u32* flag) {
+// component replay: the used slots (one per candidate that started a walk), compacted in candidate = scan order; the founder string of
+// the walk's last node is attached here, off the replay's sequential path
+__global__ void k_walk_compact(DevView d, u32 n_cand, const u32* __restrict__ rank) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nw) { const u32 s = d.walks[i].start_node; flag[key ? key[s] : s] = 1; }
-}
-__global__ void k_walk_scatter(DevView d, u32 nw, const u32* __restrict__ key, const u32* rank) {
-    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nw) { ag_walk r = d.walks[i]; const u32 s = r.start_node; d.walks_sorted[rank[key ? key[s] : s]] = r; }
+    if (i >= n_cand || !d.walk_used[i]) return;
+    ag_walk r = d.walks[i];
+    r.tail_sread = d.node_sref[2 * (size_t)r.last_node]; r.tail_soff_len = d.node_sref[2 * (size_t)r.last_node + 1];
+    d.walks_sorted[rank[i]] = r;
 }
 
 // exact sequential replay including the 1000-position skip (AG:2194-2202); used only when a >100 kbp contig was emitted
@@ -858,7 +860,7 @@ struct AgDevice::Impl {
     DBuf<u32> pos_node;
     DBuf<ag_nodec> node_c; DBuf<ag_nodew> node_w; DBuf<u32> node_sref, node_pos, node_cc;
     DBuf<u32> eovf_head, eovf_target, eovf_next;
-    DBuf<u32> walk_next, parent, cmin, cmax; DBuf<ag_walk> walks, walks2; DBuf<ag_cm1> cm1; DBuf<MatItem> mat_detours; DBuf<u32> tail_end; u32 n_cand = 0; DBuf<unsigned char> pos_term; DBuf<u32> indeg, fnext, fprev, msuf, mnode, cand_rank, cand_node, cand_label; DBuf<ag_chain> chain_a, chain_b; DBuf<ag_hrec> hrec; DBuf<int> changed;
+    DBuf<u32> walk_next, parent, cmin, cmax, walk_used; DBuf<ag_walk> walks, walks2; DBuf<ag_cm1> cm1; DBuf<MatItem> mat_detours; DBuf<u32> tail_end; u32 n_cand = 0; DBuf<unsigned char> pos_term; DBuf<u32> indeg, fnext, fprev, msuf, mnode, cand_rank, cand_node, cand_label; DBuf<ag_chain> chain_a, chain_b; DBuf<ag_hrec> hrec; DBuf<int> changed;
     DBuf<unsigned char> out_bases, occ; DBuf<u32> sel_start, sel_tails; DBuf<u64> sel_off;
     PinnedBuf h_walks, h_bases, h_occ, h_sel, h_s;   // h_s: page-locked landing zone of the scalar read-backs (a pageable destination makes every copy a synchronous staged transfer)
     Scanner scanner;
@@ -887,7 +889,7 @@ AgDevice::~AgDevice() {
     for (auto* b : b8) b->release();
     DBuf<u32>* b32[] = {&m.cm_start, &m.chain_pos, &m.ntiles, &m.key_off, &m.keys, &m.vals, &m.keys2, &m.vals2, &m.hist, &m.tile_cnt,
                         &m.tile_start, &m.tile_flag, &m.tile_base, &m.tile_nodes, &m.tile_prefix, &m.pos_pool, &m.pool_sref, &m.pool_pos, &m.pool_cc, &m.many, &m.many_prefix, &m.ovf_next, &m.counters, &m.pos_node, &m.node_sref, &m.node_pos, &m.node_cc, &m.eovf_head,
-                        &m.eovf_target, &m.eovf_next, &m.walk_next, &m.parent, &m.cmin, &m.cmax, &m.sel_start, &m.sel_tails};
+                        &m.eovf_target, &m.eovf_next, &m.walk_next, &m.parent, &m.cmin, &m.cmax, &m.walk_used, &m.sel_start, &m.sel_tails};
     for (auto* b : b32) b->release();
     for (int i = 0; i < 4; i++) m.scanner.lvl[i].release();
     m.cm.release(); m.cthreads.release(); m.aln.release(); m.ext.release(); m.alnp.release(); m.fast.release(); m.pool_c.release(); m.pool_w.release(); m.ovf_node.release(); m.err.release();
@@ -1190,8 +1192,9 @@ void AgDevice::walk_components() {
     const u32 nc = m.n_cand;
     t_.n_components = nc;
     // every walk starts at a chain head, so the candidate count bounds the number of walk records
-    m.walk_cap = nc + 1; m.walks.ensure(m.walk_cap); m.walks2.ensure(m.walk_cap);
-    d.walks = m.walks.p; d.walks_sorted = m.walks2.p; d.walk_cap = m.walk_cap;
+    m.walk_cap = nc + 1; m.walks.ensure(m.walk_cap); m.walks2.ensure(m.walk_cap); m.walk_used.ensure((size_t)nc + 2);
+    d.walks = m.walks.p; d.walks_sorted = m.walks2.p; d.walk_cap = m.walk_cap; d.walk_used = m.walk_used.p;
+    CK(cudaMemsetAsync(m.walk_used.p, 0, ((size_t)nc + 1) * sizeof(u32), st));
     if (!nc) { chains_valid_ = true; return; }
     unsigned gc = (nc + 255) / 256;
     {
@@ -1240,24 +1243,29 @@ void AgDevice::extend(std::vector<ag_walk>& walks) {
     auto fetch = [&]() {
         Timer tm(st);
         volatile u32* hs = (volatile u32*)m.h_s.p;
-        CK(cudaMemcpyAsync((void*)(hs + 0), m.counters.p + 3, sizeof(u32), cudaMemcpyDeviceToHost, st));
+        u32 nw = 0;
+        const ag_walk* src = nullptr;
+        if (chains_valid_) {   // component replay: slot i belongs to candidate i; compact the used slots (candidates are in node = scan order)
+            const u32 nc = m.n_cand;
+            m.scanner.run(m.walk_used.p, m.cmin.p, nc, st);
+            if (nc) { k_walk_compact<<<(nc + 255) / 256, 256, 0, st>>>(d, nc, m.cmin.p); launches_++; }
+            CK(cudaMemcpyAsync((void*)(hs + 0), m.cmin.p + nc, sizeof(u32), cudaMemcpyDeviceToHost, st));
+            src = m.walks2.p;
+        } else {               // sequential replay: one thread appended the records in scan order
+            CK(cudaMemcpyAsync((void*)(hs + 0), m.counters.p + 3, sizeof(u32), cudaMemcpyDeviceToHost, st));
+            src = m.walks.p;
+        }
         CK(cudaMemcpyAsync((void*)(hs + 1), m.err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        const u32 nw = hs[0];
+        nw = hs[0];
         if (hs[1]) throw AgError{"walk record buffer exhausted"};
         walks.resize(nw);
-        if (nw) {  // records into scan order on the device (the component threads append them in arbitrary order)
-            const u32* key = chains_valid_ ? m.cand_rank.p : nullptr;
-            const size_t slots = chains_valid_ ? (size_t)m.n_cand : (size_t)nn;
-            CK(cudaMemsetAsync(m.parent.p, 0, slots * sizeof(u32), st));
-            k_walk_flag<<<(nw + 255) / 256, 256, 0, st>>>(d, nw, key, m.parent.p); launches_++;
-            m.scanner.run(m.parent.p, m.cmin.p, slots, st);
-            k_walk_scatter<<<(nw + 255) / 256, 256, 0, st>>>(d, nw, key, m.cmin.p); launches_++;
+        if (nw) {
             m.h_walks.ensure((size_t)nw * sizeof(ag_walk));
-            CK(cudaMemcpyAsync(m.h_walks.p, m.walks2.p, (size_t)nw * sizeof(ag_walk), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(m.h_walks.p, src, (size_t)nw * sizeof(ag_walk), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            memcpy(walks.data(), m.h_walks.p, (size_t)nw * sizeof(ag_walk));
         }
-        CK(cudaStreamSynchronize(st));
-        if (nw) memcpy(walks.data(), m.h_walks.p, (size_t)nw * sizeof(ag_walk));
         t_.d2h += tm.stop();
         t_.d2h_bytes += (size_t)nw * sizeof(ag_walk);
     };

@@ -251,7 +251,7 @@ public:
         for (u32 v = 0; v < n_nodes; v++) if (live(v)) { n_live++; if (!(node_w[v].misc & AG_NW_INTERIOR)) { cand.push_back(v); max_chain = std::max(max_chain, chain[v].len); } }
         n_heads = (u32)cand.size();
         hrec.assign(n_nodes, ag_hrec{});   // k_hrec
-        for (u32 h : cand) hrec[h] = ag_make_hrec(chain[h], node_w[chain[h].tail]);
+        for (u32 h : cand) hrec[h] = ag_make_hrec(chain[h], node_w[chain[h].tail], ct, node_pos[chain[h].tail]);
         // components over chain tails (k_uf_tails, k_uf_flatten)
         for (u32 h : cand) {
             const u32 t = chain[h].tail;
