@@ -46,6 +46,7 @@ AG_HD void ag_tile_range(u32 lo, u32 hi, u32 n_tiles, u32& t0, u32& t1) {  // ti
     if (t0 > t1) t0 = t1;
 }
 
+AG_HD u32 ag_min_u32(u32 a, u32 b) { return a < b ? a : b; }
 AG_HD int ag_absdiff(u32 a, u32 b) {  // abs((int)(a - b)) on unsigned operands, as the reference writes it (AG:1296)
     int d = (int)(a - b);
     return d < 0 ? -d : d;
@@ -89,6 +90,23 @@ AG_HD u32 ag_num_calls(const ag_segv& L, u32 len, u32 k) {
 AG_HD ag_prep_out ag_prep(const ag_aln& a, const ag_seg* ext, u32 len, u32 k) {
     ag_prep_out o;
     u32 n1 = (a.flags >> 8) & 0xFF, n2 = (a.flags >> 16) & 0xFF;
+    if (n1 == 1 && n2 == 1) {   // one M segment per mate (by far the common case): the loops below collapse to a few adds and compares
+        const u32 src1 = a.sl1 & 0xFFFFu, len1 = a.sl1 >> 16, src2 = a.sl2 & 0xFFFFu, len2 = a.sl2 >> 16;
+        const u32 limit = len > k ? len - k : 0;
+        const u32 lo = src1 > src2 ? src1 : src2;
+        u32 hi = ag_min_u32(src1 + len1, src2 + len2); if (hi > limit) hi = limit;
+        const bool swap = lo < hi && (a.dst1 + (lo - src1)) > (a.dst2 + (lo - src2));   // AG:1672-1679
+        const u32 lsrc = swap ? src2 : src1, llen = swap ? len2 : len1, ldst = swap ? a.dst2 : a.dst1;
+        const u32 frL = swap ? ((a.flags >> 1) & 1) : (a.flags & 1);
+        o.p.left_read = ((2 * a.pair + (swap ? 1 : 0)) << 1) | frL;
+        o.p.len_nseg = len | (1u << 16) | (1u << 24);
+        o.p.l_dst = ldst; o.p.l_sl = swap ? a.sl2 : a.sl1; o.p.r_dst = swap ? a.dst1 : a.dst2; o.p.r_sl = swap ? a.sl1 : a.sl2;
+        o.p.ext_l = a.ext_idx; o.p.ext_r = a.ext_idx;
+        const u32 below = limit > lsrc ? ag_min_u32(limit - lsrc, llen) : 0;
+        const u32 c = llen == 0 ? 0 : ag_min_u32(below, llen - 1);                       // ag_num_calls
+        o.any = c > 0; o.lo = c ? ldst : 0; o.span = c;
+        return o;
+    }
     ag_segv m1, m2;
     m1.n = n1; m1.dst0 = a.dst1; m1.sl0 = a.sl1; m1.ext = ext + a.ext_idx;
     m2.n = n2; m2.dst0 = a.dst2; m2.sl0 = a.sl2; m2.ext = ext + a.ext_idx + (n1 > 1 ? n1 : 0);
@@ -140,7 +158,6 @@ struct ag_touch {
     u32 npos, nmate, nsoff, nslen;  // successor of the call (kind 1 only)
 };
 
-AG_HD u32 ag_min_u32(u32 a, u32 b) { return a < b ? a : b; }
 
 AG_HD ag_touch ag_locate(const ag_alnp& p, const ag_seg* ext, u32 q, u32 k) {
     ag_touch t; t.kind = 0; t.soff = t.slen = 0; t.mate = AG_NONE; t.npos = t.nmate = AG_NONE; t.nsoff = t.nslen = 0;

@@ -794,10 +794,11 @@ __global__ void k_mat_nodes(DevView d, u32 n_nodes, const u32* __restrict__ tail
     if (e != AG_NONE) out[e - c.len] = (unsigned char)(d.node_w[v].misc & 0xFF);
 }
 __global__ void k_mat_detours(DevView d, const MatItem* __restrict__ items, const u32* counts, unsigned char* out) {
-    u32 w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (w >= counts[1]) return;
-    MatItem it = items[w];
-    for (u32 j = lane; j < it.n; j += 32) out[it.off + j] = d.chain_base[it.a + j];
+    // one CTA per detour item (a run of contig bases, typically thousands): byte copies, coalesced across the CTA
+    for (u32 w = blockIdx.x; w < counts[1]; w += gridDim.x) {
+        const MatItem it = items[w];
+        for (u32 j = threadIdx.x; j < it.n; j += blockDim.x) out[it.off + j] = d.chain_base[it.a + j];
+    }
 }
 
 // s[1..] of the last node of every selected walk that ended in the k-mer graph (AG:2164-2168); characters outside ACGT come out as 'N'
@@ -1313,7 +1314,7 @@ void AgDevice::materialize(const std::vector<ag_walk>& walks, const std::vector<
         CK(cudaMemsetAsync(m.tail_end.p, 0xFF, (size_t)nn * sizeof(u32), st));
         k_mat_items<<<((u32)sel.size() + 127) / 128, 128, 0, st>>>(d, m.sel_start.p, m.sel_off.p, (u32)sel.size(), m.tail_end.p, m.mat_detours.p, m.counters.p + 4, cap); launches_++;
         k_mat_nodes<<<(nn + 255) / 256, 256, 0, st>>>(d, nn, m.tail_end.p, m.out_bases.p); launches_++;
-        k_mat_detours<<<(cap + 3) / 4, 128, 0, st>>>(d, m.mat_detours.p, m.counters.p + 4, m.out_bases.p); launches_++;
+        k_mat_detours<<<std::min<u32>(cap, 148u * 8u), 256, 0, st>>>(d, m.mat_detours.p, m.counters.p + 4, m.out_bases.p); launches_++;
     } else {
         k_materialize_seq<<<((u32)sel.size() + 127) / 128, 128, 0, st>>>(d, m.sel_start.p, m.sel_off.p, (u32)sel.size(), m.out_bases.p); launches_++;
     }
