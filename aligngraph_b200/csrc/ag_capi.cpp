@@ -173,25 +173,12 @@ int ag_build(ag_ctx* ctx) {
 // extension half of ag_process_unit (kept separate so that ag_build can be timed / inspected on its own)
 int ag_extend(ag_ctx* ctx) {
     return guard(ctx, [&] {
-        auto t0 = std::chrono::steady_clock::now();
-        AgDevice& eng = *ctx->dev;
-        std::vector<ag_walk> walks;
-        eng.extend(walks);
-        std::vector<u32> sel;
-        ag_select_emitted(walks, sel);
-        char* bases = nullptr; std::vector<u64> offs;
-        eng.materialize(walks, sel, bases, offs);
-        std::vector<unsigned char> occ;
-        eng.occupancy(occ);
-        auto t1 = std::chrono::steady_clock::now();
-        std::vector<AgContig> contigs;
-        ag_make_contigs(walks, sel, bases, offs, ctx->reads, contigs, ctx->res.pre_text);
-        ag_dedup_join(contigs);
-        ag_scaffold(contigs, ctx->unit.ref, occ, ctx->res.ext_text);
-        auto t2 = std::chrono::steady_clock::now();
-        ctx->s_device += std::chrono::duration<double>(t1 - t0).count();
-        ctx->s_post += std::chrono::duration<double>(t2 - t1).count();
-        ctx->n_walks += walks.size(); ctx->n_emitted += sel.size();
+        AgUnitResult& r = ctx->res;
+        const double d0 = r.t_device, p0 = r.t_post;
+        u64 nw = 0, ne = 0;
+        ag_extend_unit(*ctx->dev, ctx->reads, ctx->unit.ref, r, nw, ne);
+        ctx->s_device += r.t_device - d0; ctx->s_post += r.t_post - p0;
+        ctx->n_walks += nw; ctx->n_emitted += ne;
     });
 }
 

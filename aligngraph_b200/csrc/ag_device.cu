@@ -108,45 +108,49 @@ struct Scanner {
 };
 
 // ---------------------------------------------------------------------------------------------------------------------------
-// stable LSD radix sort of (key = tile, val = alignment index), 4 bits per pass
+// stable LSD radix sort of (key = tile, val = alignment index), RS_BITS bits per pass
 // ---------------------------------------------------------------------------------------------------------------------------
-constexpr int RS_T = 256, RS_I = 8, RS_B = RS_T * RS_I;
+constexpr int RS_T = 256, RS_I = 8, RS_B = RS_T * RS_I, RS_BITS = 5, RS_BINS = 1 << RS_BITS;
 
 __global__ void k_rs_hist(const u32* __restrict__ keys, u32* __restrict__ hist, size_t n, int shift, unsigned nb) {
-    __shared__ u32 h[16];
-    if (threadIdx.x < 16) h[threadIdx.x] = 0;
+    __shared__ u32 h[RS_BINS];
+    if (threadIdx.x < RS_BINS) h[threadIdx.x] = 0;
     __syncthreads();
     size_t base = (size_t)blockIdx.x * RS_B;
-    for (int i = threadIdx.x; i < RS_B; i += RS_T) if (base + i < n) atomicAdd(&h[(keys[base + i] >> shift) & 15], 1u);
+    for (int i = threadIdx.x; i < RS_B; i += RS_T) if (base + i < n) atomicAdd(&h[(keys[base + i] >> shift) & (RS_BINS - 1)], 1u);
     __syncthreads();
-    if (threadIdx.x < 16) hist[(size_t)threadIdx.x * nb + blockIdx.x] = h[threadIdx.x];
+    if (threadIdx.x < RS_BINS) hist[(size_t)threadIdx.x * nb + blockIdx.x] = h[threadIdx.x];
 }
 
 __global__ void k_rs_scatter(const u32* __restrict__ keys, const u32* __restrict__ vals, u32* __restrict__ okeys, u32* __restrict__ ovals,
                              const u32* __restrict__ hist_scanned, size_t n, int shift, unsigned nb) {
-    __shared__ u32 cnt[16 * RS_T];  // [digit][thread]
+    // counters in flat (digit, thread) order, f = digit * RS_T + thread, stored skewed by one word per 32 so that both access patterns —
+    // [digit][thread] while counting / ranking and "thread t owns flat entries [RS_BINS t, RS_BINS t + RS_BINS)" in the scan — are
+    // free of bank conflicts
+    constexpr int NF = RS_BINS * RS_T;
+    __shared__ u32 cnt[NF + NF / 32];
     __shared__ u32 sm[33];
-    __shared__ u32 bin_start[17];
+    __shared__ u32 bin_start[RS_BINS + 1];
+    auto at = [&](int f) -> u32& { return cnt[f + (f >> 5)]; };
     const int t = threadIdx.x;
     size_t base = (size_t)blockIdx.x * RS_B + (size_t)t * RS_I;
     u32 k[RS_I], v[RS_I];
-    for (int d = 0; d < 16; d++) cnt[d * RS_T + t] = 0;
+    for (int d = 0; d < RS_BINS; d++) at(d * RS_T + t) = 0;
     for (int i = 0; i < RS_I; i++)
-        if (base + i < n) { k[i] = keys[base + i]; v[i] = vals[base + i]; cnt[((k[i] >> shift) & 15) * RS_T + t]++; }
+        if (base + i < n) { k[i] = keys[base + i]; v[i] = vals[base + i]; at((int)((k[i] >> shift) & (RS_BINS - 1)) * RS_T + t)++; }
     __syncthreads();
-    // exclusive scan of the 4096 counters in (digit, thread) order: thread t owns flat entries [16 t, 16 t + 16)
-    u32 loc[16], s = 0;
-    for (int j = 0; j < 16; j++) { loc[j] = cnt[t * 16 + j]; s += loc[j]; }
+    u32 s = 0;
+    for (int j = 0; j < RS_BINS; j++) s += at(t * RS_BINS + j);
     u32 total; u32 ex = block_excl_scan(s, sm, total);
-    for (int j = 0; j < 16; j++) { cnt[t * 16 + j] = ex; ex += loc[j]; }
+    for (int j = 0; j < RS_BINS; j++) { const u32 c = at(t * RS_BINS + j); at(t * RS_BINS + j) = ex; ex += c; }
     __syncthreads();
-    if (t < 16) bin_start[t] = cnt[t * RS_T];
-    if (t == 0) bin_start[16] = total;
+    if (t < RS_BINS) bin_start[t] = at(t * RS_T);
+    if (t == 0) bin_start[RS_BINS] = total;
     __syncthreads();
     for (int i = 0; i < RS_I; i++)
         if (base + i < n) {
-            u32 d = (k[i] >> shift) & 15;
-            u32 r = cnt[d * RS_T + t]++;
+            u32 d = (k[i] >> shift) & (RS_BINS - 1);
+            u32 r = at((int)d * RS_T + t)++;
             size_t dst = (size_t)hist_scanned[(size_t)d * nb + blockIdx.x] + (r - bin_start[d]);
             okeys[dst] = k[i]; ovals[dst] = v[i];
         }
@@ -896,6 +900,7 @@ AgDevice::~AgDevice() {
     m.cm.release(); m.cthreads.release(); m.aln.release(); m.ext.release(); m.alnp.release(); m.fast.release(); m.pool_c.release(); m.pool_w.release(); m.ovf_node.release(); m.err.release();
     m.node_c.release(); m.node_w.release(); m.walks.release(); m.walks2.release(); m.cm1.release(); m.mat_detours.release(); m.tail_end.release(); m.pos_term.release(); m.cand_rank.release(); m.cand_node.release(); m.cand_label.release(); m.fprev.release(); m.msuf.release(); m.mnode.release(); m.indeg.release(); m.fnext.release(); m.chain_a.release(); m.chain_b.release(); m.hrec.release(); m.changed.release(); m.sel_off.release();
     m.h_walks.release(); m.h_bases.release(); m.h_occ.release(); m.h_sel.release(); m.h_s.release();
+    if (ev_mat0_) { cudaEventDestroy((cudaEvent_t)ev_mat0_); cudaEventDestroy((cudaEvent_t)ev_mat1_); }
     if (st2_) { cudaStreamSynchronize((cudaStream_t)st2_); cudaStreamDestroy((cudaStream_t)st2_); cudaEventDestroy((cudaEvent_t)ev_main_); cudaEventDestroy((cudaEvent_t)ev_reads_); }
     if (m.st) cudaStreamDestroy(m.st);
     delete m_;
@@ -1079,11 +1084,11 @@ void AgDevice::build() {
         if (nk) {
             int bits = 1; while ((1ull << bits) < (u64)m.n_tiles) bits++;
             unsigned nb = (nk + RS_B - 1) / RS_B;
-            m.hist.ensure((size_t)16 * nb + 2);
+            m.hist.ensure((size_t)RS_BINS * nb + 2);
             u32 *ka = m.keys.p, *va = m.vals.p, *kb = m.keys2.p, *vb = m.vals2.p;
-            for (int shift = 0; shift < bits; shift += 4) {
+            for (int shift = 0; shift < bits; shift += RS_BITS) {
                 k_rs_hist<<<nb, RS_T, 0, st>>>(ka, m.hist.p, nk, shift, nb); launches_++;
-                m.scanner.run(m.hist.p, m.hist.p, (size_t)16 * nb, st, 0, 0);
+                m.scanner.run(m.hist.p, m.hist.p, (size_t)RS_BINS * nb, st, 0, 0);
                 k_rs_scatter<<<nb, RS_T, 0, st>>>(ka, va, kb, vb, m.hist.p, nk, shift, nb); launches_++;
                 std::swap(ka, kb); std::swap(va, vb);
             }
@@ -1287,7 +1292,7 @@ void AgDevice::extend(std::vector<ag_walk>& walks) {
     t_.n_walks = walks.size();
 }
 
-void AgDevice::materialize(const std::vector<ag_walk>& walks, const std::vector<u32>& sel, char*& bases, std::vector<u64>& offs) {
+void AgDevice::materialize_begin(const std::vector<ag_walk>& walks, const std::vector<u32>& sel, char*& bases, std::vector<u64>& offs) {
     CK(cudaSetDevice(dev_));
     Impl& m = *m_; cudaStream_t st = m.st; DevView& d = m.view;
     offs.assign(sel.size() + 1, 0);
@@ -1302,7 +1307,8 @@ void AgDevice::materialize(const std::vector<ag_walk>& walks, const std::vector<
         h_tails[3 * i] = r.tail_sread; h_tails[3 * i + 1] = tl ? r.tail_soff_len : 0; h_tails[3 * i + 2] = r.len;
     }
     if (offs.back() >= 0xFFFFFFF0ull) throw AgError{"materialise: more than 4 GB of contig bases in one unit"};
-    Timer tm(st);
+    if (!ev_mat0_) { cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b)); ev_mat0_ = a; ev_mat1_ = b; }
+    CK(cudaEventRecord((cudaEvent_t)ev_mat0_, st));
     m.sel_start.ensure(sel.size() + 1); m.sel_off.ensure(sel.size() + 1); m.out_bases.ensure(offs.back() + 1); m.sel_tails.ensure(3 * sel.size() + 1);
     CK(cudaMemcpyAsync(m.sel_off.p, h_off, sel.size() * sizeof(u64), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(m.sel_start.p, h_start, sel.size() * sizeof(u32), cudaMemcpyHostToDevice, st));
@@ -1322,27 +1328,46 @@ void AgDevice::materialize(const std::vector<ag_walk>& walks, const std::vector<
     m.h_bases.ensure(offs.back());
     CK(cudaMemcpyAsync(m.h_bases.p, m.out_bases.p, offs.back(), cudaMemcpyDeviceToHost, st));
     volatile u32* hs = (volatile u32*)m.h_s.p;
-    CK(cudaMemcpyAsync((void*)hs, m.err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    if (hs[0]) throw AgError{"materialise item buffer exhausted"};
-    bases = (char*)m.h_bases.p;   // the post passes read (and patch) the page-locked buffer in place
-    t_.materialize += tm.stop();
+    CK(cudaMemcpyAsync((void*)(hs + 16), m.err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord((cudaEvent_t)ev_mat1_, st));
+    bases = (char*)m.h_bases.p;   // the post passes read (and patch) the page-locked buffer in place — after materialize_wait()
+    mat_pending_ = true; mat_bytes_ = offs.back();
     t_.h2d_bytes += sel.size() * 24; t_.d2h_bytes += offs.back();
 }
 
-void AgDevice::occupancy(std::vector<unsigned char>& bits) {
+void AgDevice::materialize_wait() {
+    if (!mat_pending_) return;
+    CK(cudaSetDevice(dev_));
+    Impl& m = *m_;
+    mat_pending_ = false;
+    CK(cudaEventSynchronize((cudaEvent_t)ev_mat1_));
+    float ms = 0; CK(cudaEventElapsedTime(&ms, (cudaEvent_t)ev_mat0_, (cudaEvent_t)ev_mat1_));
+    t_.materialize += ms;
+    if (((volatile u32*)m.h_s.p)[16]) throw AgError{"materialise item buffer exhausted"};
+}
+
+void AgDevice::occupancy_begin() {
     CK(cudaSetDevice(dev_));
     Impl& m = *m_; cudaStream_t st = m.st;
-    size_t nb = ((size_t)m.n_pos + 7) / 8;
-    bits.assign(nb, 0);
+    const size_t nb = ((size_t)m.n_pos + 7) / 8;
+    occ_pending_ = true;
     if (!nb) return;
     m.occ.ensure(nb + 1);
     k_occupancy<<<((u32)nb + 255) / 256, 256, 0, st>>>(m.view, m.occ.p); launches_++;
     m.h_occ.ensure(nb);
     CK(cudaMemcpyAsync(m.h_occ.p, m.occ.p, nb, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    memcpy(bits.data(), m.h_occ.p, nb);
     t_.d2h_bytes += nb;
+}
+void AgDevice::occupancy_wait(std::vector<unsigned char>& bits) {
+    CK(cudaSetDevice(dev_));
+    Impl& m = *m_;
+    if (!occ_pending_) occupancy_begin();
+    occ_pending_ = false;
+    const size_t nb = ((size_t)m.n_pos + 7) / 8;
+    bits.assign(nb, 0);
+    if (!nb) return;
+    CK(cudaStreamSynchronize(m.st));
+    memcpy(bits.data(), m.h_occ.p, nb);
 }
 
 void AgDevice::dump_nodes(AgNodeDump& dd) {

@@ -53,9 +53,15 @@ public:
     void extend(std::vector<ag_walk>& walks);
     // materialise the selected walks' base strings (loop bases + tail); contig i occupies bases[offs[i], offs[i + 1]).  `bases` points into
     // a page-locked buffer owned by the device object (valid until the next call); the post passes patch and read it in place
-    void materialize(const std::vector<ag_walk>& walks, const std::vector<u32>& sel, char*& bases, std::vector<u64>& offs);
+    void materialize(const std::vector<ag_walk>& walks, const std::vector<u32>& sel, char*& bases, std::vector<u64>& offs) { materialize_begin(walks, sel, bases, offs); materialize_wait(); }
+    // the same in two halves: _begin queues the kernels and the copy and returns at once (`bases` / `offs` are final, the bytes are not
+    // there yet), _wait blocks until they are
+    void materialize_begin(const std::vector<ag_walk>& walks, const std::vector<u32>& sel, char*& bases, std::vector<u64>& offs);
+    void materialize_wait();
     // occupancy bitmap (any node or contiMer at a position) for the scaffold gap test (AG:2428)
-    void occupancy(std::vector<unsigned char>& bits);
+    void occupancy(std::vector<unsigned char>& bits) { occupancy_begin(); occupancy_wait(bits); }
+    void occupancy_begin();
+    void occupancy_wait(std::vector<unsigned char>& bits);
     void dump_nodes(AgNodeDump& d);
     void sync();
     void pin(const void* p, size_t bytes);
@@ -77,7 +83,8 @@ private:
     u64 launches_ = 0;
     void *ev0_ = nullptr, *ev1_ = nullptr;
     void *st2_ = nullptr, *ev_main_ = nullptr, *ev_reads_ = nullptr;   // copy stream of the overlapped reads upload
-    bool reads_pending_ = false;
+    bool reads_pending_ = false, mat_pending_ = false, occ_pending_ = false;
+    void *ev_mat0_ = nullptr, *ev_mat1_ = nullptr; size_t mat_bytes_ = 0;
     std::vector<void*> pinned_;
     bool chains_valid_ = false, attr_done_ = false, keep_counts_ = false;
     void walk_components();

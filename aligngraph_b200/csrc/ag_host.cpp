@@ -885,14 +885,14 @@ static std::vector<size_t> byte_chunks(const std::vector<size_t>& off /* n + 1 p
     return cut;
 }
 
-void ag_make_contigs(const std::vector<ag_walk>& walks, const std::vector<u32>& sel, char* bases, const std::vector<u64>& offs,
-                     const AgReads& reads, std::vector<AgContig>& contigs, AgText& pre_text) {
+void ag_make_contigs_begin(const std::vector<ag_walk>& walks, const std::vector<u32>& sel, char* bases, const std::vector<u64>& offs,
+                           std::vector<AgContig>& contigs, AgMakeState& st) {
     auto tp0 = std::chrono::steady_clock::now();
     contigs.clear(); contigs.resize(sel.size());
-    const bool patch = !reads.exc.empty();
-    // pass 1 (sequential, light): contig records + header strings + where every contig's text goes
-    std::string hdr; hdr.reserve(sel.size() * 72);
-    std::vector<size_t> hoff(sel.size() + 1, 0), toff(sel.size() + 1, 0);
+    // sequential, light: contig records + header strings + where every contig's text goes.  Does not read the bases.
+    std::string& hdr = st.hdr; hdr.clear(); hdr.reserve(sel.size() * 72);
+    std::vector<size_t>& hoff = st.hoff; std::vector<size_t>& toff = st.toff;
+    hoff.assign(sel.size() + 1, 0); toff.assign(sel.size() + 1, 0);
     for (size_t i = 0; i < sel.size(); i++) {
         const ag_walk& r = walks[sel[i]];
         AgContig& c = contigs[i];
@@ -904,12 +904,7 @@ void ag_make_contigs(const std::vector<ag_walk>& walks, const std::vector<u32>& 
         if (mode == 1) { c.eid0 = AG_NONE; c.eoff0 = AG_NONE; }  // walk ended on a contiMer (AG:2158-2162)
         else {
             c.eid0 = r.eoff0 == AG_NONE ? AG_NONE : 0; c.eoff0 = r.eoff0;
-            u32 slen = r.tail_soff_len >> 16, soff = r.tail_soff_len & 0xFFFFu, read = r.tail_sread >> 1, rc = r.tail_sread & 1;
-            if (patch && slen > 1) {  // the device wrote 'N' for every masked base; put the original characters back (AG:2167 copies s verbatim)
-                u32 rlen = reads.len[read >> 1];
-                char* t = bases + offs[i] + r.len;
-                for (u32 j = 1; j < slen; j++) t[j - 1] = reads.at(read, rc, rlen, soff + j);
-            }
+            const u32 slen = r.tail_soff_len >> 16;
             c.eoff = c.eoff + slen - 1; c.eoff0 = c.eoff0 + slen - 1;   // size_t arithmetic truncated to u32 (AG:2170-2171)
         }
         {   // ">i, extended, sid, soff, eid, eoff, sid0, soff0, eid0, eoff0 \n"  (AG:2178): one append per header
@@ -925,20 +920,42 @@ void ag_make_contigs(const std::vector<ag_walk>& walks, const std::vector<u32>& 
         hoff[i + 1] = hdr.size();
         toff[i + 1] = toff[i] + (hoff[i + 1] - hoff[i]) + wrapped_len(c.n);
     }
-    // pass 2 (thread team): header + 60-column body of every contig at its offset
+    if (getenv("AG_POST_TIMING")) fprintf(stderr, "  [make_contigs] records + headers %.2f ms\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - tp0).count() * 1e3);
+}
+
+void ag_make_contigs_finish(const std::vector<ag_walk>& walks, const std::vector<u32>& sel, char* bases, const std::vector<u64>& offs,
+                            const AgReads& reads, const std::vector<AgContig>& contigs, const AgMakeState& st, AgText& pre_text) {
     auto tp1 = std::chrono::steady_clock::now();
-    if (getenv("AG_POST_TIMING")) fprintf(stderr, "  [make_contigs] records + headers %.2f ms\n", std::chrono::duration<double>(tp1 - tp0).count() * 1e3);
+    if (!reads.exc.empty())   // the device wrote 'N' for every masked base of a tail; put the original characters back (AG:2167 copies s verbatim)
+        for (size_t i = 0; i < sel.size(); i++) {
+            const ag_walk& r = walks[sel[i]];
+            if (((r.flags >> 1) & 3) == 1) continue;
+            const u32 slen = r.tail_soff_len >> 16, soff = r.tail_soff_len & 0xFFFFu, read = r.tail_sread >> 1, rc = r.tail_sread & 1;
+            if (slen <= 1) continue;
+            const u32 rlen = reads.len[read >> 1];
+            char* t = bases + offs[i] + r.len;
+            for (u32 j = 1; j < slen; j++) t[j - 1] = reads.at(read, rc, rlen, soff + j);
+        }
+    // thread team: header + 60-column body of every contig at its offset
+    const std::vector<size_t>& hoff = st.hoff; const std::vector<size_t>& toff = st.toff;
     pre_text.set_size(toff.back());
     const std::vector<size_t> cut = byte_chunks(toff);
     char* const T = pre_text.data();
     ag_parallel_chunks((int)cut.size() - 1, [&](int ch) {
         for (size_t i = cut[ch]; i < cut[ch + 1]; i++) {
             char* p = T + toff[i];
-            memcpy(p, hdr.data() + hoff[i], hoff[i + 1] - hoff[i]); p += hoff[i + 1] - hoff[i];
+            memcpy(p, st.hdr.data() + hoff[i], hoff[i + 1] - hoff[i]); p += hoff[i + 1] - hoff[i];
             wrap60_to(p, contigs[i].p, contigs[i].n);
         }
     });
     if (getenv("AG_POST_TIMING")) fprintf(stderr, "  [make_contigs] fill %.2f ms (%d chunks, team %d)\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - tp1).count() * 1e3, (int)cut.size() - 1, ag_team_size());
+}
+
+void ag_make_contigs(const std::vector<ag_walk>& walks, const std::vector<u32>& sel, char* bases, const std::vector<u64>& offs,
+                     const AgReads& reads, std::vector<AgContig>& contigs, AgText& pre_text) {
+    AgMakeState st;
+    ag_make_contigs_begin(walks, sel, bases, offs, contigs, st);
+    ag_make_contigs_finish(walks, sel, bases, offs, reads, contigs, st, pre_text);
 }
 
 static inline int contain(const AgContig& a, const AgContig& b) { return a.sid == b.sid && a.eid == b.eid && a.soff <= b.soff && a.eoff >= b.eoff; }

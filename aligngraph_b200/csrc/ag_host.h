@@ -108,6 +108,13 @@ void ag_select_emitted(const std::vector<ag_walk>& walks, std::vector<u32>& sel)
 // restored here from the reads' exception list) + the text of tmp/_pre_extended_contigs.N.fa
 void ag_make_contigs(const std::vector<ag_walk>& walks, const std::vector<u32>& sel, char* bases, const std::vector<u64>& offs,
                      const AgReads& reads, std::vector<AgContig>& contigs, AgText& pre_text);
+// the same in two halves, so that the first (contig records, header lines, text offsets — nothing that reads the bases) can run while the
+// device is still materialising and copying them
+struct AgMakeState { std::string hdr; std::vector<size_t> hoff, toff; };
+void ag_make_contigs_begin(const std::vector<ag_walk>& walks, const std::vector<u32>& sel, char* bases, const std::vector<u64>& offs,
+                           std::vector<AgContig>& contigs, AgMakeState& st);
+void ag_make_contigs_finish(const std::vector<ag_walk>& walks, const std::vector<u32>& sel, char* bases, const std::vector<u64>& offs,
+                            const AgReads& reads, const std::vector<AgContig>& contigs, const AgMakeState& st, AgText& pre_text);
 void ag_dedup_join(std::vector<AgContig>& contigs);                                               // AG:2296-2380
 // AG:2396-2464; occ = bitmap "position holds a node or a contiMer"
 void ag_scaffold(std::vector<AgContig>& contigs, const std::string& ref, const std::vector<unsigned char>& occ, AgText& text);

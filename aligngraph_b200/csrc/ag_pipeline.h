@@ -40,32 +40,44 @@ inline void ag_prepare_unit(const AgReads& reads, const std::string& tmp, int un
                                           std::chrono::duration<double>(t2 - t1).count() * 1e3, std::chrono::duration<double>(t3 - t2).count() * 1e3);
 }
 
+// extendContigs + scaffoldContigs (AG:4774-4776) on a built graph.  The device materialises and copies the contig bases while the host
+// already prepares everything that does not read them (contig records, header lines, text offsets).
+template <class Engine> void ag_extend_unit(Engine& eng, const AgReads& reads, const std::string& ref, AgUnitResult& r, u64& n_walks, u64& n_emitted) {
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<ag_walk> walks;
+    eng.extend(walks);
+    std::vector<u32> sel;
+    ag_select_emitted(walks, sel);
+    char* bases = nullptr; std::vector<u64> offs;   // bases: engine-owned buffer (page-locked on the device), valid after materialize_wait until the next materialize
+    eng.materialize_begin(walks, sel, bases, offs);
+    eng.occupancy_begin();
+    std::vector<AgContig> contigs; AgMakeState ms;
+    ag_make_contigs_begin(walks, sel, bases, offs, contigs, ms);
+    eng.materialize_wait();
+    auto t1 = std::chrono::steady_clock::now();
+    ag_make_contigs_finish(walks, sel, bases, offs, reads, contigs, ms, r.pre_text);
+    auto t1a = std::chrono::steady_clock::now();
+    ag_dedup_join(contigs);
+    auto t1b = std::chrono::steady_clock::now();
+    std::vector<unsigned char> occ;
+    eng.occupancy_wait(occ);
+    ag_scaffold(contigs, ref, occ, r.ext_text);
+    auto t2 = std::chrono::steady_clock::now();
+    if (getenv("AG_POST_TIMING")) fprintf(stderr, "[post] make (second half) %.2f ms, dedup_join %.2f ms, scaffold %.2f ms\n", std::chrono::duration<double>(t1a - t1).count() * 1e3,
+                                          std::chrono::duration<double>(t1b - t1a).count() * 1e3, std::chrono::duration<double>(t2 - t1b).count() * 1e3);
+    r.t_device += std::chrono::duration<double>(t1 - t0).count();
+    r.t_post += std::chrono::duration<double>(t2 - t1).count();
+    n_walks = walks.size(); n_emitted = sel.size();
+}
+
 // graph build + extendContigs + scaffoldContigs on prepared arrays
 template <class Engine> void ag_process_unit(Engine& eng, const AgReads& reads, const AgUnit& u, AgUnitResult& r) {
     auto t0 = std::chrono::steady_clock::now();
     eng.load_unit(ag_unit_input(u));
     eng.build();
-    std::vector<ag_walk> walks;
-    eng.extend(walks);
-    std::vector<u32> sel;
-    ag_select_emitted(walks, sel);
-    char* bases = nullptr; std::vector<u64> offs;   // bases: engine-owned buffer (page-locked on the device), valid until the next materialize
-    eng.materialize(walks, sel, bases, offs);
-    std::vector<unsigned char> occ;
-    eng.occupancy(occ);
-    auto t1 = std::chrono::steady_clock::now();
-    std::vector<AgContig> contigs;
-    ag_make_contigs(walks, sel, bases, offs, reads, contigs, r.pre_text);
-    auto t1a = std::chrono::steady_clock::now();
-    ag_dedup_join(contigs);
-    auto t1b = std::chrono::steady_clock::now();
-    ag_scaffold(contigs, u.ref, occ, r.ext_text);
-    auto t2 = std::chrono::steady_clock::now();
-    if (getenv("AG_POST_TIMING")) fprintf(stderr, "[post] select+make %.2f ms, dedup_join %.2f ms, scaffold %.2f ms\n", std::chrono::duration<double>(t1a - t1).count() * 1e3,
-                                          std::chrono::duration<double>(t1b - t1a).count() * 1e3, std::chrono::duration<double>(t2 - t1b).count() * 1e3);
-    r.t_device += std::chrono::duration<double>(t1 - t0).count();
-    r.t_post += std::chrono::duration<double>(t2 - t1).count();
-    r.n_aln = u.aln.size(); r.n_walks = walks.size(); r.n_emitted = sel.size();
+    r.t_device += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    ag_extend_unit(eng, reads, u.ref, r, r.n_walks, r.n_emitted);
+    r.n_aln = u.aln.size();
 }
 
 template <class Engine> void ag_run_unit_files(Engine& eng, const AgReads& reads, const std::string& tmp, int unit, AgUnitResult& r, bool write = true) {

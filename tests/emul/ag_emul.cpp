@@ -360,6 +360,10 @@ public:
         for (size_t i = 0; i < bases.size(); i++) if (!bases[i]) throw AgHostError{"emul: hole in the materialised bases"};
     }
 
+    void materialize_begin(const std::vector<ag_walk>& walks, const std::vector<u32>& sel, char*& bases_out, std::vector<u64>& offs) { materialize(walks, sel, bases_out, offs); }
+    void materialize_wait() {}
+    void occupancy_begin() {}
+    void occupancy_wait(std::vector<unsigned char>& bits) { occupancy(bits); }
     void occupancy(std::vector<unsigned char>& bits) {
         bits.assign(((size_t)in.n_pos + 7) / 8, 0);
         for (u32 p = 0; p < in.n_pos; p++) {
