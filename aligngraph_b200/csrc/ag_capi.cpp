@@ -233,7 +233,10 @@ int ag_run_units_files(ag_ctx** ctxs, int n_ctx, const char* tmp_dir, int first_
     if (prefetch < 1) prefetch = 1;
     const std::string tmp = tmp_dir;
     const AgReads& reads = ctxs[0]->reads;
+    const int n_prep = std::min(prefetch, n_units);
+    const int cores = std::max(1u, std::thread::hardware_concurrency());
     auto preparer = [&]() {
+        ag_set_thread_budget(std::max(1, (cores + n_prep - 1) / n_prep));   // the preparers run side by side: share the cores out between their parsers
         for (;;) {
             int u = next_prepare.fetch_add(1);
             if (u >= last) return;
@@ -272,7 +275,6 @@ int ag_run_units_files(ag_ctx** ctxs, int n_ctx, const char* tmp_dir, int first_
         }
     };
     std::vector<std::thread> th;
-    int n_prep = std::min(prefetch, n_units);
     for (int i = 0; i < n_prep; i++) th.emplace_back(preparer);
     for (int i = 1; i < n_ctx; i++) th.emplace_back(worker, ctxs[i]);
     worker(ctxs[0]);

@@ -131,7 +131,10 @@ static size_t parallel_min_bytes() {  // files smaller than this are parsed sequ
     if (const char* e = getenv("AG_PARSE_PARALLEL_MIN")) return (size_t)atol(e);
     return (size_t)1 << 22;
 }
+static thread_local int t_thread_budget = 0;
+void ag_set_thread_budget(int n) { t_thread_budget = n; }
 static int host_threads() {
+    if (t_thread_budget > 0) return t_thread_budget;   // a caller that runs several parsers side by side shares the cores out (ag_run_units_files)
     if (const char* e = getenv("AG_THREADS")) { int n = atoi(e); if (n > 0) return n; }
     unsigned h = std::thread::hardware_concurrency();
     return (int)std::min<unsigned>(h ? h : 1, 32);

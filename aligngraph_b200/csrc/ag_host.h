@@ -51,6 +51,8 @@ struct AgText {
 // run fn(chunk) for chunk = 0 .. n_chunks-1 on the host thread team (persistent workers + the caller; AG_THREADS / affinity-aware)
 void ag_parallel_chunks(int n_chunks, const std::function<void(int)>& fn);
 int ag_team_size();
+// thread budget of the text parsers called from THIS thread (0 = default: AG_THREADS or all cores)
+void ag_set_thread_budget(int n);
 
 // ---- reads (tmp/_reads.fa, AG:361-404) -----------------------------------------------------------------------------------
 struct AgReads {
