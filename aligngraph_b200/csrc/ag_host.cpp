@@ -734,7 +734,7 @@ static bool parse_sam_parallel(const char* p, size_t n, const AgReads& reads, Ag
     std::vector<Grp> group;   // surviving records of the current pair, in file order
     auto flush_group = [&]() {
         if (group.empty()) return;
-        const u32 rlen = reads.len[recs[group[0].t][group[0].i].sid];
+        const u32 rlen = group.size() > 1 ? reads.len[recs[group[0].t][group[0].i].sid] : 0;   // only the duplicate rule needs it
         for (size_t pp = 0; pp < group.size(); pp++) {
             const PRec& r = recs[group[pp].t][group[pp].i];
             bool dup = false;
