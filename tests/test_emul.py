@@ -79,6 +79,15 @@ def test_parallel_text_parsers_match_golden(harness, workdir, name):
     compare_with_golden(harness, workdir, name)
 
 
+@pytest.mark.parametrize("threads", ["1", "7"])
+def test_post_passes_do_not_depend_on_the_thread_team(harness, workdir, threads):
+    """The FASTA text is formatted by a host thread team (contigs split into byte-balanced chunks); one thread or seven, the files
+    are those of the reference."""
+    harness.synth(workdir, **cases.GOLDEN["two_chr"])
+    harness.run_emul(workdir, env={"AG_THREADS": threads})
+    compare_with_golden(harness, workdir, "two_chr")
+
+
 import edge_cases
 
 
