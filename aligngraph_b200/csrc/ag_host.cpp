@@ -490,10 +490,12 @@ void ag_thread_contigs(const std::string& contigs_fa, const std::string& psl_pat
     }
     lap("psl+sets");
     // ---- thread every surviving set through the unit (AG:884-1177) ----
-    struct Push { u32 pos, cid, coff; char base; };
-    std::vector<Push> pushes;          // chain-major: one thread after the other, each in walking order
-    std::vector<u32> count(u.n_ref, 0);  // contiMers per position so far (grows with the tail)
-    { size_t cap = 0; for (const Chunk& c : ch) for (const auto& st : c.sets) cap += st.size() + 1; pushes.reserve(cap); }
+    // chain-major output, written in place: one thread after the other, each in walking order (the position-ordered table — CSR, push
+    // order preserved — is derived from these arrays on the device)
+    std::vector<u32>& cpos = u.chain_pos; std::string& cbase = u.chain_base;
+    cpos.clear(); cbase.clear();
+    std::vector<unsigned char> count(u.n_ref, 0);  // contiMers per position so far, saturating at 255 (only ">= 2" matters); grows with the tail
+    { size_t cap = 0; for (const Chunk& c : ch) for (const auto& st : c.sets) cap += st.size() + 1; cpos.reserve(cap); cbase.reserve(cap); }
     u.threads.clear(); u.cm_start.clear(); u.cm.clear();
     u.ref.resize(u.n_ref);
     for (size_t sp = 0; sp < ch.size(); sp++) {
@@ -508,52 +510,66 @@ void ag_thread_contigs(const std::string& contigs_fa, const std::string& psl_pat
             bool flipped = false;
             if (c.fr[pp] == 1) { revcomp(c.bases); flipped = true; }
             c.outputted = 1;
-            size_t first_push = pushes.size();
-            auto push = [&](u32 pos, u32 coff, char base) {
+            const size_t first_push = cpos.size();
+            u32 coff_first = AG_NONE, coff_prev = AG_NONE, coff_last = 0; bool consecutive = true;
+            auto push = [&](u32 pos, u32 coff, char base, bool terminal) {
                 if (pos >= count.size()) throw AgHostError{"CONTIG ALIGNMENT ERROR"};
-                pushes.push_back(Push{pos, (u32)sp, coff, base}); count[pos]++;
+                if (coff_first == AG_NONE) coff_first = coff;
+                else if (!terminal && coff != coff_prev + 1) consecutive = false;   // contig offsets advance by one per contiMer up to the terminal
+                coff_prev = coff; coff_last = coff;
+                cpos.push_back(pos); cbase.push_back(base);
+                if (count[pos] != 255) count[pos]++;
             };
             u32 cur = AG_NONE, nxt = AG_NONE;
             bool have_next = false;
             size_t i;
             for (i = 0; i + 1 < ps.size(); i++) {
                 if (ps[i] == AG_NONE) continue;
+                if (ps[i + 1] != AG_NONE) {
+                    // a run of aligned bases i .. r-1: every one but the last has an aligned successor => ordinary steps (AG:1075-1118), appended in bulk
+                    size_t r = i + 2;
+                    while (r < ps.size() && ps[r] != AG_NONE) r++;
+                    const size_t cnt = r - 1 - i;
+                    for (size_t k = i; k < r - 1; k++) { const u32 pos = ps[k]; if (pos >= count.size()) throw AgHostError{"CONTIG ALIGNMENT ERROR"}; if (count[pos] != 255) count[pos]++; }
+                    if (coff_first == AG_NONE) coff_first = (u32)i; else if ((u32)i != coff_prev + 1) consecutive = false;
+                    coff_prev = coff_last = (u32)(r - 2);
+                    cpos.insert(cpos.end(), ps.begin() + (long)i, ps.begin() + (long)(r - 1));
+                    cbase.append(c.bases, i, cnt);
+                    cur = ps[r - 2]; nxt = ps[r - 1]; have_next = true;
+                    i = r - 2;   // the run's last base (index r-1) is looked at by the next iteration: it is followed by an unaligned base or is the contig's last
+                    continue;
+                }
                 cur = ps[i]; nxt = ps[i + 1]; have_next = nxt != AG_NONE;
                 char base = c.bases[i];
                 if (nxt == AG_NONE) {  // bases inserted relative to the unit: append them behind the unit (SI = 0 => always "large", AG:974-1042)
                     for (size_t m = i + 2; m < ps.size(); m++) {
                         if (ps[m] == AG_NONE) continue;
                         nxt = ps[m]; have_next = true;
-                        push(cur, (u32)i, base);
+                        push(cur, (u32)i, base, false);
                         for (size_t j = i + 1; j < m; j++) {
                             u.ref.push_back(c.bases[j]); count.push_back(0);
-                            push((u32)u.ref.size() - 1, (u32)j, c.bases[j]);
+                            push((u32)u.ref.size() - 1, (u32)j, c.bases[j], false);
                         }
                         i = m - 1;
                         break;
                     }
-                } else push(cur, (u32)i, base);  // ordinary step or deletion (SD = 0 => "large", AG:1075-1118)
+                } else push(cur, (u32)i, base, false);  // ordinary step or deletion (SD = 0 => "large", AG:1075-1118)
             }
             if (cur != AG_NONE) {
                 // terminal contiMer carries the UNIT's base (AG:1121-1148)
                 u32 tp = have_next ? nxt : cur;
                 if (tp >= u.ref.size()) throw AgHostError{"CONTIG ALIGNMENT ERROR"};
-                push(tp, (u32)i, u.ref[tp]);
+                push(tp, (u32)i, u.ref[tp], true);
             }
-            if (pushes.size() > first_push) {
-                ag_cthread t; t.first = (u32)first_push; t.term = (u32)pushes.size() - 1; t.cid = (u32)sp; t.coff_first = pushes[first_push].coff; t.coff_term = pushes.back().coff;
-                for (size_t k = first_push; k < t.term; k++)   // contig offsets advance by one per contiMer up to the terminal
-                    if (pushes[k].coff != t.coff_first + (u32)(k - first_push)) throw AgHostError{"internal: contig thread offsets are not consecutive"};
+            if (cpos.size() > first_push) {
+                if (!consecutive) throw AgHostError{"internal: contig thread offsets are not consecutive"};
+                ag_cthread t; t.first = (u32)first_push; t.term = (u32)cpos.size() - 1; t.cid = (u32)sp; t.coff_first = coff_first; t.coff_term = coff_last;
                 u.threads.push_back(t);
             }
             if (flipped) revcomp(c.bases);
         }
     }
     lap("threading");
-    // ---- chain-major arrays; the position-ordered table (CSR, push order preserved) is derived from them on the device ----
-    u.chain_pos.resize(pushes.size()); u.chain_base.resize(pushes.size());
-    for (size_t k = 0; k < pushes.size(); k++) { u.chain_pos[k] = pushes[k].pos; u.chain_base[k] = pushes[k].base; }
-    lap("csr");
     // ---- tmp/_initial_contigs.N.fa: original contigs with >= 50 % of their chunks threaded (AG:1179-1216) ----
     Out out(&initial_text);
     size_t c = 0, cp = 0;
