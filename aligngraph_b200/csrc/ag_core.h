@@ -272,6 +272,51 @@ struct ag_reads {
     }
 };
 
+// Oriented 4-bit codes of a read, eight per word: nibble t of word j = code (0-3, 4 = not ACGT) of ORIENTED offset 8j + t, i.e. what
+// ag_reads::code(read_rc, len, 8j + t) returns; nibbles of offsets >= len are unspecified.  `b` / `m` = the read's packed words (2 bits per
+// base / 1 bit per base), nb2 / nbm = their number.  Staging reads in this form turns the base lookup of a touch into one shift and mask.
+AG_HD u32 ag_code4_word_ref(const u32* b, const u32* m, u32 rc, u32 len, u32 j) {   // plain per-base definition
+    u32 w = 0;
+    for (u32 t = 0; t < 8; t++) {
+        const u32 soff = 8 * j + t;
+        if (soff >= len) break;
+        const u32 i = rc ? len - 1 - soff : soff;
+        const u32 nb = (m[i >> 5] >> (i & 31)) & 1, c = (b[i >> 4] >> ((i & 15) * 2)) & 3;
+        w |= (nb ? 4u : (rc ? 3u - c : c)) << (4 * t);
+    }
+    return w;
+}
+AG_HD u32 ag_brev32(u32 x) {
+#ifdef __CUDA_ARCH__
+    return __brev(x);
+#else
+    x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1); x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+    x = ((x >> 4) & 0x0F0F0F0Fu) | ((x & 0x0F0F0F0Fu) << 4); x = ((x >> 8) & 0x00FF00FFu) | ((x & 0x00FF00FFu) << 8);
+    return (x >> 16) | (x << 16);
+#endif
+}
+AG_HD u32 ag_code4_word(const u32* b, const u32* m, u32 nb2, u32 nbm, u32 rc, u32 len, u32 j) {   // the same, eight bases at a time
+    u32 x16, m8;
+    if (!rc) {
+        if (8 * j >= len) return 0;
+        x16 = (b[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;
+        m8 = (m[j >> 2] >> ((j & 3) * 8)) & 0xFFu;
+    } else {
+        if (8 * j + 7 >= len) return ag_code4_word_ref(b, m, rc, len, j);   // the read's last word on the reverse strand: fewer than eight bases
+        const u32 lo = len - 8 - 8 * j;                                      // raw offsets lo .. lo + 7, to be reversed and complemented
+        const u32 wi = lo >> 4, mi = lo >> 5;
+        const u64 vb = (u64)b[wi] | (wi + 1 < nb2 ? (u64)b[wi + 1] << 32 : 0);
+        const u64 vm = (u64)m[mi] | (mi + 1 < nbm ? (u64)m[mi + 1] << 32 : 0);
+        u32 r = ag_brev32((u32)((vb >> ((lo & 15) * 2)) & 0xFFFFu)) >> 16;    // bit reversal reverses the groups but also swaps the two bits of each
+        r = ((r & 0xAAAAu) >> 1) | ((r & 0x5555u) << 1);
+        x16 = r ^ 0xFFFFu;                                                    // complement: 3 - c
+        m8 = ag_brev32((u32)((vm >> (lo & 31)) & 0xFFu)) >> 24;
+    }
+    u32 x = x16; x = (x | (x << 8)) & 0x00FF00FFu; x = (x | (x << 4)) & 0x0F0F0F0Fu; x = (x | (x << 2)) & 0x33333333u;   // 2-bit groups -> nibbles
+    u32 k = m8;  k = (k | (k << 12)) & 0x000F000Fu; k = (k | (k << 6)) & 0x03030303u; k = (k | (k << 3)) & 0x11111111u;   // mask bits -> bit 0 of the nibbles
+    return (x & ~(k * 3u)) | (k << 2);
+}
+
 // ---------------------------------------------------------------------------------------------------------------------------
 // candidates and the compatibility predicate
 // ---------------------------------------------------------------------------------------------------------------------------

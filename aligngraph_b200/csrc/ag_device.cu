@@ -297,6 +297,9 @@ __global__ void k_cm1(DevView d, ag_cm1* out, unsigned char* pos_term, u32* many
 #ifndef AG_NCHUNK_NODES
 #define AG_NCHUNK_NODES 128
 #endif
+#ifndef AG_CODE4
+#define AG_CODE4 0   // 1: stage the left mates as oriented 4-bit codes (ag_code4_word) instead of their raw packed words — NOT yet measured on the GPU
+#endif
 constexpr int NCHUNK = AG_NCHUNK;            // chunk of tile alignments staged per round in k_edges
 constexpr int NCHUNK_N = AG_NCHUNK_NODES;    // ... in k_build
 constexpr int NODE_SCAP = AG_NODE_SCAP;                         // nodes per position kept in shared memory; more spill to the pool
@@ -334,6 +337,18 @@ __global__ void __launch_bounds__(AG_TILE, AG_NODES_MINB) k_build(DevView d) {
     for (u32 c0 = kb; c0 < ke; c0 += NCHUNK_N) {
         const u32 cn = min((u32)NCHUNK_N, ke - c0);
         if (c0 != kb) __syncthreads();                             // everybody is done with the previous chunk
+#if AG_CODE4
+        if (threadIdx.x < cn) { const u32 idx = d.vals[c0 + threadIdx.x]; s_idx[threadIdx.x] = idx; s_f[threadIdx.x] = d.fast[idx]; }
+        if (rw) {   // oriented 4-bit codes, one (entry, word) task at a time over the whole CTA; the tasks re-read idx / read / length (L1) so one barrier suffices
+            const u32 sm_ = d.reads.stridem;
+            for (u32 task = threadIdx.x; task < cn * rw; task += AG_TILE) {
+                const u32 e = task / rw, j = task - e * rw;
+                const ag_fast* gf = d.fast + d.vals[c0 + e];
+                const u32 read_rc = gf->read, len = gf->lsrc_len >> 16, read = read_rc >> 1;
+                s_dyn[READS0 + task] = ag_code4_word(d.reads.bases + (u64)read * s2, d.reads.nmask + (u64)read * sm_, s2, sm_, read_rc & 1, len, j);
+            }
+        }
+#else
         if (threadIdx.x < cn) {   // stage entry: prepared record + the left mate's packed bases and non-ACGT plane (one barrier per chunk)
             const u32 idx = d.vals[c0 + threadIdx.x];
             const ag_fast f = d.fast[idx];
@@ -348,6 +363,7 @@ __global__ void __launch_bounds__(AG_TILE, AG_NODES_MINB) k_build(DevView d) {
                 for (u32 j = s2; j < rw; j++) o[j] = gm[j - s2];
             }
         }
+#endif
         __syncthreads();
         for (u32 r0 = 0; r0 < cn; r0 += 32) {
             // which of these 32 entries touch any of the warp's 32 positions?
@@ -365,6 +381,9 @@ __global__ void __launch_bounds__(AG_TILE, AG_NODES_MINB) k_build(DevView d) {
                     const ag_reads reads = d.reads;
                     auto codef = [=](u32 soff) -> int {
                         if (!rw) return reads.code(fread, flen, soff);
+#if AG_CODE4
+                        return (int)((s_dyn[roff + (soff >> 3)] >> ((soff & 7) * 4)) & 7u);
+#endif
                         const u32 rc = fread & 1, i = rc ? flen - 1 - soff : soff;
                         if ((s_dyn[roff + s2 + (i >> 5)] >> (i & 31)) & 1) return 4;
                         const u32 c = (s_dyn[roff + (i >> 4)] >> ((i & 15) * 2)) & 3;
@@ -1058,8 +1077,12 @@ void AgDevice::build() {
     m.many.ensure((size_t)n_pos + 2); m.many_prefix.ensure((size_t)n_pos + 2); d.many_prefix = m.many_prefix.p;
     if (n_pos) { k_cm1<<<(n_pos + 255) / 256, 256, 0, st>>>(d, m.cm1.p, m.pos_term.p, m.many.p); launches_++; }
     m.scanner.run(m.many.p, m.many_prefix.p, n_pos, st);
-    if (!attr_done_) { CK(cudaFuncSetAttribute(k_build, cudaFuncAttributeMaxDynamicSharedMemorySize, NODES_SMEM + NCHUNK_N * READ_WORDS_MAX * 4)); attr_done_ = true; }  // per device
+    if (!attr_done_) { CK(cudaFuncSetAttribute(k_build, cudaFuncAttributeMaxDynamicSharedMemorySize, NODES_SMEM + NCHUNK_N * 32 * 4)); attr_done_ = true; }  // per device
+#if AG_CODE4
+    d.rw = (2 * m.reads.stride2 <= 32u) ? 2 * m.reads.stride2 : 0;   // words of oriented 4-bit codes per staged read (eight bases each)
+#else
     d.rw = (m.reads.stride2 + m.reads.stridem <= (u32)READ_WORDS_MAX) ? m.reads.stride2 + m.reads.stridem : 0;
+#endif
 
     // ---- prep + keys ------------------------------------------------------------------------------------------------
     {

@@ -399,6 +399,26 @@ int main(int argc, char** argv) {
         std::string a = argv[i];
         if (a == "--dir") dir = argv[++i];
         else if (a == "--dump-nodes") dump = 1;
+        else if (a == "--check-code4") {   // the eight-bases-at-a-time oriented 4-bit coder against its per-base definition and against ag_reads::code
+            std::vector<std::string> seqs; unsigned long long x = 88172645463325252ull; auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return (unsigned)(x >> 33); };
+            for (int i = 0; i < 4000; i++) { size_t n = 1 + rnd() % 256; std::string s1(n, 'A'), s2(n, 'A'); for (auto& ch : s1) ch = "ACGTACGTACGTNacgR"[rnd() % 17]; for (auto& ch : s2) ch = "ACGTACGTACGTNacgR"[rnd() % 17]; seqs.push_back(s1); seqs.push_back(s2); }
+            AgReads q; ag_pack_reads(seqs, q);
+            ag_reads rd; rd.bases = q.bases.data(); rd.nmask = q.nmask.data(); rd.len = q.len.data(); rd.stride2 = q.stride2; rd.stridem = q.stridem;
+            size_t bad = 0, checked = 0;
+            for (u32 read = 0; read < 2 * q.n_pairs; read++) {
+                const u32 len = q.len[read >> 1]; const u32* b = rd.bases + (size_t)read * rd.stride2; const u32* m = rd.nmask + (size_t)read * rd.stridem;
+                for (u32 rc = 0; rc < 2; rc++)
+                    for (u32 j = 0; j < (len + 7) / 8; j++) {
+                        const u32 w = ag_code4_word(b, m, rd.stride2, rd.stridem, rc, len, j), wr = ag_code4_word_ref(b, m, rc, len, j);
+                        for (u32 t = 0; t < 8 && 8 * j + t < len; t++) {
+                            const u32 c = (w >> (4 * t)) & 7, cr = (wr >> (4 * t)) & 7, cd = (u32)rd.code((read << 1) | rc, len, 8 * j + t);
+                            checked++; if (c != cr || c != cd) bad++;
+                        }
+                    }
+            }
+            printf("%s checked=%zu bad=%zu\n", bad ? "DIFFERENT" : "IDENTICAL", checked, bad);
+            return bad ? 1 : 0;
+        }
         else if (a == "--check-read-packers") {   // the multi-threaded word-at-a-time packer against the character-at-a-time one, on one FASTA file
             const std::string path = argv[++i];
             std::vector<std::string> seqs;

@@ -107,3 +107,12 @@ def test_word_at_a_time_read_packer_equals_sequential(harness, tmp_path):
                 f.write(f">{i}\n{''.join(rnd.choice(alphabet) for _ in range(n))}\n")
     r = subprocess.run([harness.EMUL, "--check-read-packers", str(path)], capture_output=True, text=True)
     assert r.returncode == 0 and "IDENTICAL" in r.stdout, r.stdout + r.stderr
+
+
+def test_oriented_4bit_coder_equals_per_base_lookup(harness):
+    """ag_code4_word (eight bases per step: window, bit reversal + complement on the reverse strand, spread to nibbles, non-ACGT override)
+    against its per-base definition and against ag_reads::code, for every offset of 8000 random reads of length 1..256 in both
+    orientations.  (The kernels stage reads in this form when built with -DAG_CODE4=1.)"""
+    import subprocess
+    r = subprocess.run([harness.EMUL, "--check-code4"], capture_output=True, text=True)
+    assert r.returncode == 0 and "IDENTICAL" in r.stdout, r.stdout + r.stderr

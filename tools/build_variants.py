@@ -9,11 +9,10 @@ sys.path.insert(0, ROOT)
 from aligngraph_b200 import build as b  # noqa: E402
 
 VARIANTS = {
+    "code4": ["-DAG_CODE4=1"],                                   # left mates staged as oriented 4-bit codes (CPU-verified coder, not yet timed)
+    "code4_minb5": ["-DAG_CODE4=1", "-DAG_NODES_MINB=5"],
     "minb5": ["-DAG_NODES_MINB=5"],
-    "minb4": ["-DAG_NODES_MINB=4"],
-    "minb4_scap3": ["-DAG_NODES_MINB=4", "-DAG_NODE_SCAP=3"],
     "minb6_chunk64": ["-DAG_NODES_MINB=6", "-DAG_NCHUNK_NODES=64"],
-    "minb5_chunk256": ["-DAG_NODES_MINB=5", "-DAG_NCHUNK_NODES=256"],
 }
 
 
