@@ -236,7 +236,10 @@ int ag_run_units_files(ag_ctx** ctxs, int n_ctx, const char* tmp_dir, int first_
     const int n_prep = std::min(prefetch, n_units);
     const int cores = std::max(1u, std::thread::hardware_concurrency());
     auto preparer = [&]() {
-        ag_set_thread_budget(std::max(1, (cores + n_prep - 1) / n_prep));   // the preparers run side by side: share the cores out between their parsers
+        // The preparers run side by side.  Measured on the 16-core GPU host (profiles/r02g_scale_c4_1gpu.json): letting every parser start its
+        // full set of threads keeps the cores busy through the others' serial phases (2.1 s for the 8 units of C4); a strict share-out
+        // (cores / n_prep each) is available through AG_PREP_THREADS but has not been timed.
+        if (const char* e = getenv("AG_PREP_THREADS")) { int n = atoi(e); if (n > 0) ag_set_thread_budget(n); else if (n < 0) ag_set_thread_budget(std::max(1, (cores + n_prep - 1) / n_prep)); }
         for (;;) {
             int u = next_prepare.fetch_add(1);
             if (u >= last) return;
