@@ -2,6 +2,7 @@
 #include <sched.h>
 #include <condition_variable>
 #include "ag_host.h"
+#include "ag_samcore.h"
 #include <algorithm>
 #include <cstring>
 #include <cstdlib>
@@ -589,7 +590,7 @@ namespace {
 struct SamRec { u32 tid, tstart, tend, tgap, sid, sstart, send, sgap, ssize, fr; };
 
 // AG:181-285.  Appends to `segs` (the caller clears — or, on the reference's `continue` paths, does not: AG:1258).
-void parse_sam(const char* s, size_t n, SamRec& r, std::vector<ag_seg>& segs) {
+void parse_sam_general(const char* s, size_t n, SamRec& r, std::vector<ag_seg>& segs) {   // any number of M segments
     const char* f[6]; size_t fl[6]; int nf = 0;
     const char* p = s; const char* end = s + n;
     while (nf < 6) {
@@ -624,6 +625,18 @@ void parse_sam(const char* s, size_t n, SamRec& r, std::vector<ag_seg>& segs) {
     r.tstart = (u32)(pos - 1);
     r.tend = r.tstart + (u32)total + (u32)del - (u32)ins;
     r.tgap = (u32)del;
+}
+
+// The same through the allocation-free record parser shared with the device (ag_samcore.h); CIGARs with more M segments than it keeps
+// inline go through the general version above.
+void parse_sam(const char* s, size_t n, SamRec& r, std::vector<ag_seg>& segs) {
+    ag_samline L;
+    ag_sam_parse_line(s, (u32)n, L);
+    if (L.err == AG_SAM_ERR_SEGS || n > 0xFFFFFFFFull) { parse_sam_general(s, n, r, segs); return; }
+    if (L.err == AG_SAM_ERR_CHAR) throw AgHostError{std::string("unknown character: ") + L.bad_char};
+    r.sid = L.sid; r.fr = L.fr; r.tid = L.tid; r.tstart = L.tstart; r.tend = L.tend; r.tgap = L.tgap;
+    r.sstart = L.sstart; r.send = L.send; r.sgap = L.sgap; r.ssize = L.ssize;
+    segs.insert(segs.end(), L.seg, L.seg + L.nseg);
 }
 
 // position of read offset 0 in the position set the reference would have built from `segs` (later segments overwrite)
