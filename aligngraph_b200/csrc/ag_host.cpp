@@ -673,6 +673,24 @@ void normalize(const std::vector<ag_seg>& in, u32 rlen, std::vector<ag_seg>& out
 }
 }  // namespace
 
+// self-check used by the CPU test-suite: the allocation-free record parser (ag_samcore.h) and the general one agree on one SAM line
+bool ag_selfcheck_sam_line(const char* s, size_t n) {
+    SamRec g; std::vector<ag_seg> gs; bool gthrow = false; char gch = 0;
+    try { parse_sam_general(s, n, g, gs); } catch (const AgHostError& e) { gthrow = true; gch = e.msg.empty() ? 0 : e.msg.back(); }
+    ag_samline L; ag_sam_parse_line(s, (u32)n, L);
+    if (gthrow) return L.err == AG_SAM_ERR_CHAR && L.bad_char == gch;
+    if (L.err == AG_SAM_ERR_CHAR) return false;
+    if (g.sid != L.sid || g.fr != L.fr || g.tid != L.tid) return false;
+    if (g.tid == AG_NONE) return gs.empty() && L.nseg == 0;
+    if (g.tstart != L.tstart || g.tend != L.tend || g.tgap != L.tgap || g.sstart != L.sstart || g.send != L.send || g.sgap != L.sgap || g.ssize != L.ssize) return false;
+    if (gs.size() != L.nseg) return false;
+    if (L.nseg > AG_SAM_MAXSEG) return L.err == AG_SAM_ERR_SEGS;
+    for (u32 k = 0; k < L.nseg; k++) if (gs[k].src != L.seg[k].src || gs[k].dst != L.seg[k].dst || gs[k].len != L.seg[k].len) return false;
+    return true;
+}
+namespace {
+}  // namespace
+
 // Parallel front half of ag_parse_sam for well-formed files ('@' lines only at the top, record pairs on consecutive lines, read ids
 // non-decreasing, no parse errors): threads turn text into per-pair records; the order-dependent part (1,000,000-pair batches and the
 // dropped record AG:1259, duplicate rule AG:1650-1655, strand check AG:1657-1671) then runs sequentially over those records exactly
@@ -718,36 +736,32 @@ static bool parse_sam_parallel(const char* p, size_t n, const AgReads& reads, Ag
     std::vector<std::vector<PRec>> recs((size_t)T);
     std::vector<std::vector<ag_seg>> segs((size_t)T);
     std::vector<char> bad((size_t)T, 0);
-    auto work = [&](int t) {
+    auto work = [&](int t) {   // one record pair at a time through the allocation-free functions of ag_samcore.h (the per-thread code of a future kernel)
         const char* q = p + cut[t]; const char* e = p + cut[t + 1];
-        std::vector<ag_seg> s1, s2, n1, n2;
         recs[t].reserve((size_t)(e - q) / 140 + 16);
-        try {
-            while (q < e) {
-                const char* l1 = (const char*)memchr(q, '\n', (size_t)(e - q));
-                if (!l1 || l1 + 1 >= e) { bad[t] = 1; return; }
-                const char* l2 = (const char*)memchr(l1 + 1, '\n', (size_t)(e - l1 - 1));
-                if (!l2 || *q == '@') { bad[t] = 1; return; }
-                SamRec a, b;
-                s1.clear(); s2.clear();
-                parse_sam(q, (size_t)(l1 - q), a, s1);
-                parse_sam(l1 + 1, (size_t)(l2 - l1 - 1), b, s2);
-                PRec r; r.sid = a.sid; r.flags = a.fr | (b.fr << 1); r.p0 = pos_at0(s1); r.seg_off = (u32)segs[t].size(); r.n1 = r.n2 = 0;
-                bool pass = a.tid != AG_NONE && b.tid != AG_NONE &&
-                    (double)(a.send - a.sstart - a.sgap) / a.ssize >= kReadThreshold && (double)(a.tend - a.tstart - a.tgap) / (a.tend - a.tstart) >= kReadThreshold &&
-                    (double)(b.send - b.sstart - b.sgap) / b.ssize >= kReadThreshold && (double)(b.tend - b.tstart - b.tgap) / (b.tend - b.tstart) >= kReadThreshold;
-                if (pass) {
-                    if (a.tid != 0 || b.tid != 0 || b.sid != a.sid || a.sid >= reads.n_pairs) { bad[t] = 1; return; }
-                    u32 rlen = reads.len[a.sid];
-                    normalize(s1, rlen, n1); normalize(s2, rlen, n2);
-                    if (n1.empty() || n2.empty() || n1.size() > 255 || n2.size() > 255) { bad[t] = 1; return; }
-                    r.flags |= 4; r.n1 = (uint16_t)n1.size(); r.n2 = (uint16_t)n2.size();
-                    segs[t].insert(segs[t].end(), n1.begin(), n1.end()); segs[t].insert(segs[t].end(), n2.begin(), n2.end());
-                }
-                recs[t].push_back(r);
-                q = l2 + 1;
+        segs[t].reserve((size_t)(e - q) / 70 + 16);
+        ag_samline a, b;
+        ag_seg n1[AG_SAM_MAXSEG], n2[AG_SAM_MAXSEG];
+        while (q < e) {
+            const char* l1 = (const char*)memchr(q, '\n', (size_t)(e - q));
+            if (!l1 || l1 + 1 >= e) { bad[t] = 1; return; }
+            const char* l2 = (const char*)memchr(l1 + 1, '\n', (size_t)(e - l1 - 1));
+            if (!l2 || *q == '@' || (size_t)(l2 - q) > 0x7FFFFFFFull) { bad[t] = 1; return; }
+            ag_sam_parse_line(q, (u32)(l1 - q), a);
+            ag_sam_parse_line(l1 + 1, (u32)(l2 - l1 - 1), b);
+            if (a.err || b.err) { bad[t] = 1; return; }   // unknown CIGAR character / very long CIGAR: the sequential parser reports or handles it
+            PRec r; r.sid = a.sid; r.flags = a.fr | (b.fr << 1); r.p0 = a.tid == AG_NONE ? AG_NONE : ag_sam_pos_at0(a.seg, a.nseg); r.seg_off = (u32)segs[t].size(); r.n1 = r.n2 = 0;
+            if (ag_sam_mate_pass(a, kReadThreshold) && ag_sam_mate_pass(b, kReadThreshold)) {
+                if (a.tid != 0 || b.tid != 0 || b.sid != a.sid || a.sid >= reads.n_pairs) { bad[t] = 1; return; }
+                const u32 rlen = reads.len[a.sid];
+                u32 c1 = 0, c2 = 0;
+                if (ag_sam_normalize(a.seg, a.nseg, rlen, n1, c1) || ag_sam_normalize(b.seg, b.nseg, rlen, n2, c2) || !c1 || !c2) { bad[t] = 1; return; }
+                r.flags |= 4; r.n1 = (uint16_t)c1; r.n2 = (uint16_t)c2;
+                segs[t].insert(segs[t].end(), n1, n1 + c1); segs[t].insert(segs[t].end(), n2, n2 + c2);
             }
-        } catch (const AgHostError&) { bad[t] = 1; }
+            recs[t].push_back(r);
+            q = l2 + 1;
+        }
     };
     { std::vector<std::thread> th; for (int t = 0; t < T; t++) th.emplace_back(work, t); for (auto& x : th) x.join(); }
     for (int t = 0; t < T; t++) if (bad[t]) return false;

@@ -89,6 +89,7 @@ void ag_expand_contimers(AgUnit& u);
 void ag_expand_contimers(const ag_cthread* threads, size_t n_threads, const u32* chain_pos, size_t n_cm, size_t n_pos, std::vector<u32>& cm_start, std::vector<ag_cm>& cm);
 // SAM -> surviving alignments in processing order                                                 // AG:1233-1277, 1644-1656, 1872-1895
 void ag_parse_sam(const std::string& path, const AgReads& reads, AgUnit& u);
+bool ag_selfcheck_sam_line(const char* s, size_t n);   // tests: ag_samcore.h record parser == general record parser on this line
 
 // ---- post passes --------------------------------------------------------------------------------------------------------------------
 struct AgPiece { const char* p; size_t n; };

@@ -77,3 +77,30 @@ AG_HD void ag_sam_parse_line(const char* s, u32 n, ag_samline& r) {
 AG_HD bool ag_sam_mate_pass(const ag_samline& a, double threshold) {
     return a.tid != AG_NONE && (double)(a.send - a.sstart - a.sgap) / a.ssize >= threshold && (double)(a.tend - a.tstart - a.tgap) / (a.tend - a.tstart) >= threshold;
 }
+
+// Monotone, disjoint, merged segment list equivalent to the position set updateContig (AG:763-815) builds from one record's segments:
+// zero-length segments dropped, adjacent ones merged.  Returns 0 = ok, 1 = a segment runs past the read (the reference writes out of bounds:
+// reported as BOWTIE ALIGNMENT ERROR), 2 = segments overlap or go backwards (cannot come from one CIGAR; the general host path decides).
+AG_HD int ag_sam_normalize(const ag_seg* in, u32 n_in, u32 rlen, ag_seg* out, u32& n_out) {
+    n_out = 0;
+    for (u32 i = 0; i < n_in; i++) {
+        const ag_seg s = in[i];
+        if (!s.len) continue;
+        if ((u64)s.src + s.len > rlen) return 1;
+        if (n_out) {
+            ag_seg& b = out[n_out - 1];
+            if (s.src < b.src + b.len || s.dst < b.dst + b.len) return 2;
+            if (s.src == b.src + b.len && s.dst == b.dst + b.len) { b.len += s.len; continue; }
+        }
+        out[n_out++] = s;
+    }
+    return 0;
+}
+
+// unit position of read offset 0 in the position set of one record (later segments overwrite earlier ones, AG:809-814): the key of the
+// duplicate rule AG:1650-1655
+AG_HD u32 ag_sam_pos_at0(const ag_seg* segs, u32 n) {
+    u32 r = AG_NONE;
+    for (u32 i = 0; i < n; i++) if (segs[i].len && segs[i].src == 0) r = segs[i].dst;
+    return r;
+}

@@ -399,6 +399,22 @@ int main(int argc, char** argv) {
         std::string a = argv[i];
         if (a == "--dir") dir = argv[++i];
         else if (a == "--dump-nodes") dump = 1;
+        else if (a == "--check-sam-lines") {   // fuzz: random SAM records (CIGAR soup, odd RNAMEs, missing fields) through both record parsers
+            unsigned long long x = 0x9E3779B97F4A7C15ull; auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return (unsigned)(x >> 33); };
+            size_t bad = 0, total = 200000;
+            for (size_t it = 0; it < total; it++) {
+                std::string l = std::to_string(rnd() % 3000000) + "\t" + std::to_string(rnd() % 4096) + "\t";
+                switch (rnd() % 6) { case 0: l += "*"; break; case 1: l += "0"; break; case 2: l += "7.3"; break; case 3: l += "chr*1"; break; case 4: l += "12"; break; default: l += ".5"; }
+                l += "\t" + std::to_string(rnd() % 5000000) + "\t44\t";
+                const unsigned nops = rnd() % 9 == 0 ? 30 + rnd() % 40 : rnd() % 8;
+                for (unsigned k = 0; k < nops; k++) { if (rnd() % 11) l += std::to_string(rnd() % 160); l += "MMMMIDSS*MX="[rnd() % (rnd() % 50 ? 10 : 12)]; }
+                if (rnd() % 7) l += "\t=\t100\t300\t*\t*\tAS:i:0";
+                if (rnd() % 97 == 0) l = l.substr(0, rnd() % (l.size() + 1));   // truncated record
+                if (!ag_selfcheck_sam_line(l.data(), l.size())) { if (bad < 5) fprintf(stderr, "differs: %s\n", l.c_str()); bad++; }
+            }
+            printf("%s lines=%zu bad=%zu\n", bad ? "DIFFERENT" : "IDENTICAL", total, bad);
+            return bad ? 1 : 0;
+        }
         else if (a == "--check-code4") {   // the eight-bases-at-a-time oriented 4-bit coder against its per-base definition and against ag_reads::code
             std::vector<std::string> seqs; unsigned long long x = 88172645463325252ull; auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return (unsigned)(x >> 33); };
             for (int i = 0; i < 4000; i++) { size_t n = 1 + rnd() % 256; std::string s1(n, 'A'), s2(n, 'A'); for (auto& ch : s1) ch = "ACGTACGTACGTNacgR"[rnd() % 17]; for (auto& ch : s2) ch = "ACGTACGTACGTNacgR"[rnd() % 17]; seqs.push_back(s1); seqs.push_back(s2); }

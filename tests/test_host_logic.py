@@ -116,3 +116,11 @@ def test_oriented_4bit_coder_equals_per_base_lookup(harness):
     import subprocess
     r = subprocess.run([harness.EMUL, "--check-code4"], capture_output=True, text=True)
     assert r.returncode == 0 and "IDENTICAL" in r.stdout, r.stdout + r.stderr
+
+
+def test_allocation_free_sam_record_parser_equals_general_parser(harness):
+    """ag_samcore.h (host + device record parser: fields, CIGAR state machine incl. the '*' quirk and `unknown character`) against the
+    general parser on 200,000 fuzzed SAM lines."""
+    import subprocess
+    r = subprocess.run([harness.EMUL, "--check-sam-lines"], capture_output=True, text=True)
+    assert r.returncode == 0 and "IDENTICAL" in r.stdout, r.stdout + r.stderr
