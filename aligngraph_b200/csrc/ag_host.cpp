@@ -766,58 +766,115 @@ static bool parse_sam_parallel(const char* p, size_t n, const AgReads& reads, Ag
     { std::vector<std::thread> th; for (int t = 0; t < T; t++) th.emplace_back(work, t); for (auto& x : th) x.join(); }
     for (int t = 0; t < T; t++) if (bad[t]) return false;
     lap("parse threads");
-    u32 prev = 0; bool first_rec = true;
-    for (int t = 0; t < T; t++) for (const PRec& r : recs[t]) { if (!first_rec && r.sid < prev) return false; prev = r.sid; first_rec = false; }
-    // ---- sequential, order-dependent half (same logic as the sequential parser on already-parsed records) ----
-    u.aln.clear(); u.ext.clear();
-    { size_t nr = 0, ns = 0; for (int t = 0; t < T; t++) { nr += recs[t].size(); ns += segs[t].size(); } u.aln.reserve(nr); u.ext.reserve(ns / 8 + 16); }
-    const long n_pairs = (long)reads.n_pairs;
-    long first = 0, last = std::min<long>(kBatchPairs - 1, n_pairs - 1);
-    struct Grp { int t; size_t i; };
-    std::vector<Grp> group;   // surviving records of the current pair, in file order
-    auto flush_group = [&]() {
-        if (group.empty()) return;
-        const u32 rlen = group.size() > 1 ? reads.len[recs[group[0].t][group[0].i].sid] : 0;   // only the duplicate rule needs it
-        for (size_t pp = 0; pp < group.size(); pp++) {
-            const PRec& r = recs[group[pp].t][group[pp].i];
-            bool dup = false;
-            for (size_t q = 0; q < pp && !dup; q++) { const PRec& o = recs[group[q].t][group[q].i]; if (absdiff(r.p0, o.p0) < (int)rlen) dup = true; }
-            if (dup) continue;
-            u32 fr1 = r.flags & 1, fr2 = (r.flags >> 1) & 1;
-            if (!((fr1 == 1 && fr2 == 0) || (fr2 == 1 && fr1 == 0))) throw AgHostError{"BOWTIE ALIGNMENT ERROR"};
-            const ag_seg* sg = segs[group[pp].t].data() + r.seg_off;
-            ag_aln a; a.pair = r.sid; a.pad = 0;
-            a.flags = fr1 | (fr2 << 1) | ((u32)r.n1 << 8) | ((u32)r.n2 << 16);
-            a.dst1 = sg[0].dst; a.sl1 = sg[0].src | (sg[0].len << 16);
-            a.dst2 = sg[r.n1].dst; a.sl2 = sg[r.n1].src | (sg[r.n1].len << 16);
-            a.ext_idx = (u32)u.ext.size();
-            if (r.n1 > 1) u.ext.insert(u.ext.end(), sg, sg + r.n1);
-            if (r.n2 > 1) u.ext.insert(u.ext.end(), sg + r.n1, sg + r.n1 + r.n2);
-            u.aln.push_back(a);
+    // ---- order-dependent half, in data-parallel form (the shape a device version takes as well).  Preconditions checked here: read ids
+    // non-decreasing.  Then, exactly as the sequential parser behaves on such input:
+    //   * batches of 1,000,000 read ids (AG:1885-1894): the first record whose id lies beyond the current batch is consumed and LOST
+    //     (AG:1259) and the batch advances by one — a handful of positions, found by binary search on the sorted ids;
+    //   * a pair's surviving records form a group (consecutive records that passed AG:1261 with the same id, not separated by a lost
+    //     record); a record is dropped when its read-offset-0 position lies within one read length of ANY earlier record of its group
+    //     (AG:1650-1655), so every record decides for itself by looking back;
+    //   * output order = file order: count per chunk, prefix sums, fill. ----
+    std::vector<size_t> base((size_t)T + 1, 0);
+    for (int t = 0; t < T; t++) base[t + 1] = base[t] + recs[t].size();
+    const size_t N = base[T];
+    {   // sorted?
+        std::vector<char> unsorted((size_t)T, 0);
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; t++) th.emplace_back([&, t]() {
+            const std::vector<PRec>& r = recs[t];
+            for (size_t i = 1; i < r.size(); i++) if (r[i].sid < r[i - 1].sid) { unsorted[t] = 1; return; }
+            if (!r.empty()) for (int q = t - 1; q >= 0; q--) if (!recs[q].empty()) { if (r[0].sid < recs[q].back().sid) unsorted[t] = 1; break; } });
+        for (auto& x : th) x.join();
+        for (int t = 0; t < T; t++) if (unsorted[t]) return false;
+    }
+    auto first_greater = [&](long v) -> size_t {   // first global index whose id is > v
+        for (int t = 0; t < T; t++) {
+            const std::vector<PRec>& r = recs[t];
+            if (r.empty() || (long)r.back().sid <= v) continue;
+            size_t lo = 0, hi = r.size();
+            while (lo < hi) { size_t mid = (lo + hi) / 2; if ((long)r[mid].sid > v) hi = mid; else lo = mid + 1; }
+            return base[t] + lo;
         }
-        group.clear();
+        return N;
     };
-    bool done = false;
-    u32 cur_pair = AG_NONE;
-    for (int t = 0; t < T && !done; t++)
-        for (size_t i = 0; i < recs[t].size(); i++) {
-            const PRec& r = recs[t][i];
-            // ids are non-decreasing and `first` only grows, so `r.sid < first` (AG:1258) cannot happen for a record that was not dropped
-            while ((long)r.sid > last) {   // AG:1259: this record is consumed and lost; the next batch starts with the following record
-                flush_group(); cur_pair = AG_NONE;
-                if (last >= n_pairs - 1) { done = true; break; }
-                first = last + 1; last = std::min<long>(first + kBatchPairs - 1, n_pairs - 1);
-                goto next_record;
-            }
-            if (done) break;
-            if ((long)r.sid < first) goto next_record;
-            if (r.flags & 4) {
-                if (r.sid != cur_pair) { flush_group(); cur_pair = r.sid; }
-                group.push_back(Grp{t, i});
-            }
-        next_record:;
+    const long n_pairs = (long)reads.n_pairs;
+    std::vector<size_t> lost; size_t stop = N;
+    {
+        long first = 0, last = std::min<long>(kBatchPairs - 1, n_pairs - 1);
+        size_t i = 0;
+        for (;;) {
+            const size_t j = std::max(i, first_greater(last));
+            if (j >= N) break;
+            if (last >= n_pairs - 1) { stop = j; break; }   // ids beyond the read set: the reference stops reading here
+            lost.push_back(j);
+            first = last + 1; last = std::min<long>(first + kBatchPairs - 1, n_pairs - 1);
+            i = j + 1;
         }
-    flush_group();
+        (void)first;
+    }
+    auto is_lost = [&](size_t g) { return std::binary_search(lost.begin(), lost.end(), g); };
+    // survives(t, i): passes AG:1261, is neither lost nor beyond `stop`, and no earlier record of its group lies within one read length
+    auto survives = [&](int t, size_t i) -> bool {
+        const PRec& r = recs[t][i];
+        const size_t g = base[t] + i;
+        if (!(r.flags & 4) || g >= stop || (!lost.empty() && is_lost(g))) return false;
+        u32 rlen = 0; bool have_len = false;
+        int qt = t; size_t qi = i;
+        for (;;) {   // look back through the group
+            if (qi == 0) { do { qt--; } while (qt >= 0 && recs[qt].empty()); if (qt < 0) break; qi = recs[qt].size(); }
+            qi--;
+            const PRec& o = recs[qt][qi];
+            if (!lost.empty() && is_lost(base[qt] + qi)) break;     // a lost record closes the group before it
+            if (!(o.flags & 4)) continue;                           // records that failed the filter are invisible to the grouping
+            if (o.sid != r.sid) break;
+            if (!have_len) { rlen = reads.len[r.sid]; have_len = true; }
+            if (absdiff(r.p0, o.p0) < (int)rlen) return false;
+        }
+        return true;
+    };
+    std::vector<size_t> n_aln((size_t)T + 1, 0), n_ext((size_t)T + 1, 0);
+    std::vector<std::vector<unsigned char>> keep((size_t)T);
+    std::vector<char> strand_error((size_t)T, 0);
+    {
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; t++) th.emplace_back([&, t]() {
+            const std::vector<PRec>& r = recs[t];
+            keep[t].assign(r.size(), 0);
+            size_t ca = 0, ce = 0;
+            for (size_t i = 0; i < r.size(); i++) {
+                if (!survives(t, i)) continue;
+                const u32 fr1 = r[i].flags & 1, fr2 = (r[i].flags >> 1) & 1;
+                if (fr1 == fr2) { strand_error[t] = 1; return; }    // exactly one mate must be reverse (AG:1657-1671)
+                keep[t][i] = 1; ca++;
+                ce += (r[i].n1 > 1 ? r[i].n1 : 0) + (r[i].n2 > 1 ? r[i].n2 : 0);
+            }
+            n_aln[t + 1] = ca; n_ext[t + 1] = ce; });
+        for (auto& x : th) x.join();
+    }
+    for (int t = 0; t < T; t++) if (strand_error[t]) throw AgHostError{"BOWTIE ALIGNMENT ERROR"};
+    for (int t = 0; t < T; t++) { n_aln[t + 1] += n_aln[t]; n_ext[t + 1] += n_ext[t]; }
+    if (n_ext[T] >= 0xFFFFFFF0ull) return false;
+    u.aln.resize(n_aln[T]); u.ext.resize(n_ext[T]);
+    {
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; t++) th.emplace_back([&, t]() {
+            const std::vector<PRec>& r = recs[t];
+            size_t oa = n_aln[t], oe = n_ext[t];
+            for (size_t i = 0; i < r.size(); i++) {
+                if (!keep[t][i]) continue;
+                const PRec& x = r[i];
+                const ag_seg* sg = segs[t].data() + x.seg_off;
+                ag_aln a; a.pair = x.sid; a.pad = 0;
+                a.flags = (x.flags & 3u) | ((u32)x.n1 << 8) | ((u32)x.n2 << 16);
+                a.dst1 = sg[0].dst; a.sl1 = sg[0].src | (sg[0].len << 16);
+                a.dst2 = sg[x.n1].dst; a.sl2 = sg[x.n1].src | (sg[x.n1].len << 16);
+                a.ext_idx = (u32)oe;
+                if (x.n1 > 1) { std::copy(sg, sg + x.n1, u.ext.begin() + (long)oe); oe += x.n1; }
+                if (x.n2 > 1) { std::copy(sg + x.n1, sg + x.n1 + x.n2, u.ext.begin() + (long)oe); oe += x.n2; }
+                u.aln[oa++] = a;
+            } });
+        for (auto& x : th) x.join();
+    }
     lap("merge");
     return true;
 }

@@ -41,13 +41,19 @@ def test_unit_partition_two_ranks_gloo(tmp_path):
     assert r.stdout.count("ok") == 2
 
 
-def test_batch_boundary_drops_one_record(harness, workdir):
+import pytest
+
+
+@pytest.mark.parametrize("parallel", [False, True])
+@pytest.mark.parametrize("multi", [0.0, 0.4])
+def test_batch_boundary_drops_one_record(harness, workdir, parallel, multi):
     """AlignGraph.cpp:1259 consumes and loses the first record pair beyond each 1,000,000-pair batch.  A SAM whose read ids start at
-    999,998 crosses the boundary: the emulation (product host parser) and the oracle must agree on what survives."""
+    999,900 crosses the boundary: the product host parser (via the emulation) — the sequential one and the multi-threaded one with its
+    data-parallel batch / duplicate-rule half, without and with multi-hit groups around the boundary — and the oracle must agree."""
     import shutil
     import cases
     base = os.path.join(workdir, "a")
-    harness.synth(base, genome_bp=20000, coverage=40, seed=21, contig_len=3000)
+    harness.synth(base, genome_bp=20000, coverage=40, seed=21, contig_len=3000, multi=multi)
     tmp = os.path.join(base, "tmp")
     shift = 999_900
     # renumber: prepend `shift` dummy unaligned pairs of the same read length to the read file, shift the SAM ids
@@ -70,7 +76,7 @@ def test_batch_boundary_drops_one_record(harness, workdir):
     other = os.path.join(workdir, "b")
     shutil.copytree(base, other)
     harness.run_oracle(base)
-    harness.run_emul(other)
+    harness.run_emul(other, env={"AG_PARSE_PARALLEL_MIN": "0", "AG_THREADS": "5"} if parallel else None)
     assert harness.unit_outputs(base, 0) == harness.unit_outputs(other, 0)
     # and the boundary matters: dropping is visible in the oracle's event count vs. an unshifted run is not asserted here, only parity
 
