@@ -7,6 +7,8 @@ GOLDEN = {
                 read_err=0.005, header=1, contig_len=3000, contig_gap=400, seed=12),
     "k7_150_2chr": dict(genome_bp=40000, chroms=2, coverage=40, readlen=150, kmer=7, indel=0.002, softclip=0.2, contig_len=5000, seed=13),
     "two_chr": dict(genome_bp=40000, chroms=2, coverage=45, contig_len=3500, contig_gap=500, softclip=0.2, multi=0.1, seed=15),
+    # overlapping contig tiles: positions with two contiMers (several candidates per touch, AlignGraph.cpp:1369-1477) plus indels / multi-hits
+    "overlap_ctg": dict(genome_bp=30000, coverage=40, indel=0.002, softclip=0.2, multi=0.1, contig_len=3000, contig_gap=-1200, seed=16),
     "part2": dict(genome_bp=30000, part=2, coverage=30, indel=0.001, insert_sd=80, cov=10, seed=14),
 }
 
