@@ -78,6 +78,15 @@ def test_batch_boundary_drops_one_record(harness, workdir, parallel, multi):
     harness.run_oracle(base)
     harness.run_emul(other, env={"AG_PARSE_PARALLEL_MIN": "0", "AG_THREADS": "5"} if parallel else None)
     assert harness.unit_outputs(base, 0) == harness.unit_outputs(other, 0)
+    if parallel and multi and harness.have_reference():   # development container: the unmodified reference on the same input
+        ref = os.path.join(workdir, "r")
+        shutil.copytree(other, ref)
+        for f in os.listdir(os.path.join(ref, "tmp")):
+            if f.startswith(("_initial_contigs", "_pre_extended", "_extended_contigs", "_nodes")):
+                os.remove(os.path.join(ref, "tmp", f))
+        rc, _ = harness.run_reference(ref, optimized=True)
+        assert rc == 0
+        assert harness.unit_outputs(ref, 0) == harness.unit_outputs(base, 0)
     # and the boundary matters: dropping is visible in the oracle's event count vs. an unshifted run is not asserted here, only parity
 
 
