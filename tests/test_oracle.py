@@ -16,7 +16,7 @@ def test_oracle_matches_reference_golden(harness, workdir, name):
     compare_with_golden(harness, workdir, name)
 
 
-@pytest.mark.parametrize("name", ["a1", "a4", "deep", "longcontig", "bigchunk", "overlap", "manyitems"])
+@pytest.mark.parametrize("name", ["a1", "a4", "deep", "longcontig", "bigchunk", "overlap", "manyitems", "c4_shape", "c5_shape", "lowcov", "nocontigs"])
 def test_oracle_matches_live_reference(harness, workdir, name):
     if not harness.have_reference():
         pytest.skip("reference not built here (oracle/_ref absent)")
