@@ -399,6 +399,33 @@ int main(int argc, char** argv) {
         std::string a = argv[i];
         if (a == "--dir") dir = argv[++i];
         else if (a == "--dump-nodes") dump = 1;
+        else if (a == "--check-clean") {   // ag_fast_is_clean (prefix counts over both mates' ranges) against its definition, position by position
+            unsigned long long x = 0xD1B54A32D192ED03ull; auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return (unsigned)(x >> 33); };
+            const u32 n_pos = 5000; size_t bad = 0, total = 300000, n_clean = 0;
+            for (size_t it = 0; it < total; it++) {
+                std::vector<u32> many(n_pos + 1, 0), pre(n_pos + 2, 0);
+                const unsigned density = rnd() % 4 == 0 ? 0 : 1 + rnd() % 40;
+                for (u32 p = 0; p < n_pos; p++) many[p] = density && rnd() % (density * 25) == 0;
+                for (u32 p = 0; p <= n_pos; p++) pre[p + 1] = pre[p] + many[p];
+                const u32 len = 30 + rnd() % 200, k = 1 + rnd() % 9;
+                ag_aln al{}; al.pair = 0;
+                const u32 c5a = rnd() % 3 ? 0 : rnd() % 12, c3a = rnd() % 3 ? 0 : rnd() % 12, c5b = rnd() % 3 ? 0 : rnd() % 12, c3b = rnd() % 3 ? 0 : rnd() % 12;
+                const u32 la = len - c5a - c3a, lb = len - c5b - c3b;
+                al.dst1 = 300 + rnd() % 3000; al.sl1 = c5a | (la << 16);
+                al.dst2 = al.dst1 + (rnd() % 3 ? rnd() % 900 : 0) - (rnd() % 5 == 0 ? rnd() % 250 : 0); al.sl2 = c5b | (lb << 16);
+                al.flags = (rnd() & 1) | (1u << 8) | (1u << 16);
+                const ag_prep_out o = ag_prep(al, nullptr, len, k);
+                if (!o.any) continue;
+                ag_fast f = ag_fast_prep(o.p, o.lo, o.span);
+                bool def = f.simple != 0;
+                for (u32 q = f.lo; q <= f.lo + f.span && def; q++) { if (many[q]) def = false; const u32 m = ag_fast_mate(f, q); if (m != AG_NONE && many[m]) def = false; }
+                const bool got = ag_fast_is_clean(f, o.p, pre.data());
+                n_clean += got;
+                if (got != def) { if (bad < 5) fprintf(stderr, "differs: lo %u span %u mlo %u mlen %u mdelta %u def %d got %d\n", f.lo, f.span, f.mlo, f.mlen, f.mdelta, (int)def, (int)got); bad++; }
+            }
+            printf("%s checked=%zu clean=%zu bad=%zu\n", bad ? "DIFFERENT" : "IDENTICAL", total, n_clean, bad);
+            return bad ? 1 : 0;
+        }
         else if (a == "--check-sam-lines") {   // fuzz: random SAM records (CIGAR soup, odd RNAMEs, missing fields) through both record parsers
             unsigned long long x = 0x9E3779B97F4A7C15ull; auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return (unsigned)(x >> 33); };
             size_t bad = 0, total = 200000;

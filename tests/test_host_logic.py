@@ -139,3 +139,12 @@ def test_allocation_free_sam_record_parser_equals_general_parser(harness):
     import subprocess
     r = subprocess.run([harness.EMUL, "--check-sam-lines"], capture_output=True, text=True)
     assert r.returncode == 0 and "IDENTICAL" in r.stdout, r.stdout + r.stderr
+
+
+def test_clean_alignment_classification_equals_its_definition(harness):
+    """ag_fast_is_clean decides from two prefix-count differences whether every position an alignment touches — under its left mate and at
+    the mate positions the kernel will compute (ag_fast_mate) — holds at most one contiMer; only then are its edges settled inside the node
+    sweep.  Checked position by position on 300,000 random alignments (soft clips, swapped mates, partial overlaps)."""
+    import subprocess
+    r = subprocess.run([harness.EMUL, "--check-clean"], capture_output=True, text=True)
+    assert r.returncode == 0 and "IDENTICAL" in r.stdout, r.stdout + r.stderr
