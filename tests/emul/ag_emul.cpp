@@ -399,6 +399,22 @@ int main(int argc, char** argv) {
         std::string a = argv[i];
         if (a == "--dir") dir = argv[++i];
         else if (a == "--dump-nodes") dump = 1;
+        else if (a == "--check-tiles") {   // ag_tile_range: exactly the tiles whose owned positions or halo position meet the touched range
+            unsigned long long x = 0x2545F4914F6CDD1Dull; auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return (unsigned)(x >> 33); };
+            size_t bad = 0, total = 2000000;
+            for (size_t it = 0; it < total; it++) {
+                const u32 n_ref = 1 + rnd() % 5000, n_tiles = (n_ref + AG_TPOS - 1) / AG_TPOS;
+                const u32 lo = rnd() % n_ref, hi = lo + rnd() % (n_ref - lo);
+                u32 t0, t1; ag_tile_range(lo, hi, n_tiles, t0, t1);
+                for (u32 t = 0; t < n_tiles; t++) {
+                    const u32 a0 = t * AG_TPOS, a1 = a0 + AG_TPOS;                 // owned [a0, a1) + halo a1
+                    const bool meets = lo <= a1 && hi >= a0;
+                    if (meets != (t >= t0 && t <= t1)) bad++;
+                }
+            }
+            printf("%s checked=%zu bad=%zu\n", bad ? "DIFFERENT" : "IDENTICAL", total, bad);
+            return bad ? 1 : 0;
+        }
         else if (a == "--check-clean") {   // ag_fast_is_clean (prefix counts over both mates' ranges) against its definition, position by position
             unsigned long long x = 0xD1B54A32D192ED03ull; auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return (unsigned)(x >> 33); };
             const u32 n_pos = 5000; size_t bad = 0, total = 300000, n_clean = 0;

@@ -148,3 +148,11 @@ def test_clean_alignment_classification_equals_its_definition(harness):
     import subprocess
     r = subprocess.run([harness.EMUL, "--check-clean"], capture_output=True, text=True)
     assert r.returncode == 0 and "IDENTICAL" in r.stdout, r.stdout + r.stderr
+
+
+def test_tile_range_covers_owned_and_halo_positions(harness):
+    """A tile's key list must hold every alignment that touches one of its 248 owned positions or its halo position (the first position of the
+    next tile, replayed by lane 31 of the last warp) and nothing else: ag_tile_range against that definition on 2,000,000 random ranges."""
+    import subprocess
+    r = subprocess.run([harness.EMUL, "--check-tiles"], capture_output=True, text=True)
+    assert r.returncode == 0 and "IDENTICAL" in r.stdout, r.stdout + r.stderr
