@@ -64,6 +64,7 @@ def load_library(path=None):
         "ag_set_read_exceptions": (i32, [vp, vp, vp, u64]),
         "ag_load_reads_fasta": (i32, [vp, cp]),
         "ag_get_reads": (i32, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(u64), C.POINTER(u32), C.POINTER(u32)]),
+        "ag_broadcast_reads": (i32, [C.POINTER(vp), i32, vp]),
         "ag_begin_unit": (i32, [vp, i32, vp, u32]),
         "ag_set_contimers": (i32, [vp, vp, vp, u32, vp, vp, vp, u32]),
         "ag_set_contig_threads": (i32, [vp, vp, u32, vp, vp, u32, vp, u32]),

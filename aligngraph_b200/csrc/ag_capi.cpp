@@ -17,7 +17,7 @@ static_assert(sizeof(ag_aln_c) == sizeof(ag_aln) && sizeof(ag_seg_c) == sizeof(a
 struct ag_ctx {
     AgDevice* dev = nullptr;
     ag_params params{};
-    AgReads reads;
+    std::shared_ptr<AgReads> rp = std::make_shared<AgReads>();   // host copy of the read set; shared by the contexts of one run (ag_broadcast_reads)
     bool have_reads = false, reads_dirty = false;   // reads_dirty: a re-upload was requested; it is issued by the next ag_build, behind the unit's uploads
     AgUnit unit;
     int unit_id = -1;
@@ -43,7 +43,7 @@ extern "C" {
 
 int ag_create(const ag_params* params, ag_ctx** out) {
     if (!params || !out) { g_create_error = "null argument"; return 1; }
-    ag_tune_malloc();
+    if (getenv("AG_MALLOPT")) ag_tune_malloc();   // process-wide allocator policy: opt-in for library users (the CLI applies it in its own main)
     ag_ctx* c = new (std::nothrow) ag_ctx;
     if (!c) { g_create_error = "out of host memory"; return 3; }
     c->params = *params;
@@ -59,7 +59,7 @@ const char* ag_create_error(void) { return g_create_error.c_str(); }
 // host -> device copy of the context's packed reads.  The non-ACGT bit plane is all zeros except where the parser recorded an exception,
 // so when that list is complete only the list travels (8 bytes per non-ACGT character) and the device rebuilds the plane.
 static void upload_reads(ag_ctx* ctx, bool overlap = false) {
-    const AgReads& r = ctx->reads;
+    const AgReads& r = (*ctx->rp);
     if (r.exc_complete && r.exc.size() * 8 < r.nmask.size() * 4) {
         ctx->exc_keys.resize(r.exc.size());
         for (size_t i = 0; i < r.exc.size(); i++) ctx->exc_keys[i] = r.exc[i].first;
@@ -71,7 +71,8 @@ static void upload_reads(ag_ctx* ctx, bool overlap = false) {
 int ag_set_reads(ag_ctx* ctx, const uint32_t* bases2, const uint32_t* nmask, const uint16_t* pair_len, uint64_t n_pairs, uint32_t stride2, uint32_t stridem) {
     return guard(ctx, [&] {
         ctx->dev->unpin_all();
-        AgReads& r = ctx->reads;
+        ctx->rp = std::make_shared<AgReads>();   // detach from any run-wide shared copy
+        AgReads& r = (*ctx->rp);
         r.n_pairs = n_pairs; r.stride2 = stride2; r.stridem = stridem;
         r.bases.assign((const u32*)bases2, (const u32*)bases2 + 2 * n_pairs * stride2); r.nmask.assign((const u32*)nmask, (const u32*)nmask + 2 * n_pairs * stridem); r.len.assign(pair_len, pair_len + n_pairs);
         r.exc.clear(); r.exc_complete = false;
@@ -82,7 +83,8 @@ int ag_set_reads(ag_ctx* ctx, const uint32_t* bases2, const uint32_t* nmask, con
 int ag_set_reads_device(ag_ctx* ctx, const uint32_t* d_bases2, const uint32_t* d_nmask, const uint16_t* d_pair_len, uint64_t n_pairs, uint32_t stride2, uint32_t stridem) {
     return guard(ctx, [&] {
         ctx->dev->unpin_all();
-        AgReads& r = ctx->reads;
+        ctx->rp = std::make_shared<AgReads>();
+        AgReads& r = (*ctx->rp);
         r.n_pairs = n_pairs; r.stride2 = stride2; r.stridem = stridem;
         r.bases.resize(2 * n_pairs * stride2); r.nmask.resize(2 * n_pairs * stridem); r.len.resize(n_pairs); r.exc.clear(); r.exc_complete = false;
         ctx->dev->set_reads(d_bases2, d_nmask, d_pair_len, n_pairs, stride2, stridem, true);
@@ -91,13 +93,14 @@ int ag_set_reads_device(ag_ctx* ctx, const uint32_t* d_bases2, const uint32_t* d
     });
 }
 int ag_set_read_exceptions(ag_ctx* ctx, const uint64_t* keys, const char* chars, uint64_t n) {
-    return guard(ctx, [&] { ctx->reads.exc.clear(); ctx->reads.exc_complete = false; for (uint64_t i = 0; i < n; i++) ctx->reads.exc.push_back({keys[i], chars[i]}); });
+    return guard(ctx, [&] { (*ctx->rp).exc.clear(); (*ctx->rp).exc_complete = false; for (uint64_t i = 0; i < n; i++) (*ctx->rp).exc.push_back({keys[i], chars[i]}); });
 }
 int ag_load_reads_fasta(ag_ctx* ctx, const char* path) {
     return guard(ctx, [&] {
         ctx->dev->unpin_all();
         auto t0 = std::chrono::steady_clock::now();
-        ag_parse_reads(path, ctx->reads);
+        ctx->rp = std::make_shared<AgReads>();
+        ag_parse_reads(path, (*ctx->rp));
         ctx->s_parse += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         upload_reads(ctx);
         ctx->have_reads = true;
@@ -105,8 +108,24 @@ int ag_load_reads_fasta(ag_ctx* ctx, const char* path) {
 }
 int ag_get_reads(ag_ctx* ctx, const uint32_t** bases2, const uint32_t** nmask, const uint16_t** pair_len, uint64_t* n_pairs, uint32_t* stride2, uint32_t* stridem) {
     return guard(ctx, [&] {
-        const AgReads& r = ctx->reads;
+        const AgReads& r = (*ctx->rp);
         *bases2 = r.bases.data(); *nmask = r.nmask.data(); *pair_len = r.len.data(); *n_pairs = r.n_pairs; *stride2 = r.stride2; *stridem = r.stridem;
+    });
+}
+
+// One read set for all the contexts of a run: ctxs[0] has parsed / received it; the others share its host copy (exception list included,
+// so that contig tails print the original non-ACGT characters whichever GPU ran the unit, AG:2167) and receive the packed device buffers
+// through ONE broadcast (ncclBroadcast over NVLink).
+int ag_broadcast_reads(ag_ctx** ctxs, int n_ctx, ag_bcast_info* info) {
+    if (!ctxs || n_ctx <= 0 || !ctxs[0]) return 1;
+    return guard(ctxs[0], [&] {
+        if (!ctxs[0]->have_reads) throw AgHostError{"reads not set"};
+        std::vector<AgDevice*> devs;
+        for (int i = 0; i < n_ctx; i++) { if (!ctxs[i]) throw AgHostError{"null context"}; devs.push_back(ctxs[i]->dev); }
+        for (int i = 1; i < n_ctx; i++) { ctxs[i]->dev->unpin_all(); ctxs[i]->rp = ctxs[0]->rp; ctxs[i]->have_reads = true; ctxs[i]->reads_dirty = false; }
+        double s = 0; size_t b = 0;
+        const char* how = ag_device_broadcast_reads(devs.data(), n_ctx, &s, &b);
+        if (info) { info->seconds = s; info->bytes = b; info->nccl = strcmp(how, "nccl") == 0; }
     });
 }
 
@@ -176,7 +195,7 @@ int ag_extend(ag_ctx* ctx) {
         AgUnitResult& r = ctx->res;
         const double d0 = r.t_device, p0 = r.t_post;
         u64 nw = 0, ne = 0;
-        ag_extend_unit(*ctx->dev, ctx->reads, ctx->unit.ref, r, nw, ne);
+        ag_extend_unit(*ctx->dev, (*ctx->rp), ctx->unit.ref, r, nw, ne);
         ctx->s_device += r.t_device - d0; ctx->s_post += r.t_post - p0;
         ctx->n_walks += nw; ctx->n_emitted += ne;
     });
@@ -195,7 +214,7 @@ int ag_prepare_unit_files(ag_ctx* ctx, const char* tmp_dir, int unit_id) {
         if (!ctx->have_reads) throw AgHostError{"reads not set"};
         auto t0 = std::chrono::steady_clock::now();
         ctx->dev->unpin_all(); ctx->unit = AgUnit(); ctx->res.reset(); ctx->unit_id = unit_id; ctx->uploaded = false;
-        ag_prepare_unit(ctx->reads, tmp_dir, unit_id, ctx->unit, ctx->res.initial_text);
+        ag_prepare_unit((*ctx->rp), tmp_dir, unit_id, ctx->unit, ctx->res.initial_text);
         ctx->s_parse += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     });
 }
@@ -232,7 +251,8 @@ int ag_run_units_files(ag_ctx** ctxs, int n_ctx, const char* tmp_dir, int first_
     const int last = first_unit + n_units;
     if (prefetch < 1) prefetch = 1;
     const std::string tmp = tmp_dir;
-    const AgReads& reads = ctxs[0]->reads;
+    const AgReads& reads = (*ctxs[0]->rp);
+    std::atomic<bool> stop(false);   // a unit failed: no further units are started (the reference exits at the failing chromosome)
     const int n_prep = std::min(prefetch, n_units);
     const int cores = std::max(1u, std::thread::hardware_concurrency());
     auto preparer = [&]() {
@@ -243,7 +263,8 @@ int ag_run_units_files(ag_ctx** ctxs, int n_ctx, const char* tmp_dir, int first_
         for (;;) {
             int u = next_prepare.fetch_add(1);
             if (u >= last) return;
-            { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return u < consumed + prefetch + n_ctx; }); }
+            { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return u < consumed + prefetch + n_ctx || stop.load(); }); }
+            if (stop.load()) return;
             auto p = std::make_unique<Prepared>();
             auto t0 = std::chrono::steady_clock::now();
             try { ag_prepare_unit(reads, tmp, u, p->unit, p->initial_text); }
@@ -258,9 +279,9 @@ int ag_run_units_files(ag_ctx** ctxs, int n_ctx, const char* tmp_dir, int first_
     auto worker = [&](ag_ctx* ctx) {
         for (;;) {
             int u = next_run.fetch_add(1);
-            if (u >= last) return;
+            if (u >= last || stop.load()) return;
             std::unique_ptr<Prepared> p;
-            { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return ready.count(u) != 0; }); p = std::move(ready[u]); ready.erase(u); if (u + 1 > consumed) consumed = u + 1; }
+            { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return ready.count(u) != 0 || stop.load(); }); if (!ready.count(u)) return; p = std::move(ready[u]); ready.erase(u); if (u + 1 > consumed) consumed = u + 1; }
             cv.notify_all();
             int rc = 0;
             if (!p->error.empty()) { ctx->err = p->error; rc = 1; }
@@ -275,6 +296,7 @@ int ag_run_units_files(ag_ctx** ctxs, int n_ctx, const char* tmp_dir, int first_
             std::lock_guard<std::mutex> lk(mu);
             if (rc && !first_rc) first_rc = rc;
             if (done) done(u, rc, rc ? ctx->err.c_str() : "", user);
+            if (rc) { stop = true; cv.notify_all(); }
         }
     };
     std::vector<std::thread> th;
@@ -318,7 +340,7 @@ int ag_keep_node_counts(ag_ctx* ctx, int on) {
 int ag_dump_nodes_text(ag_ctx* ctx, const char** text, uint64_t* len) {
     return guard(ctx, [&] {
         AgNodeDump d; ctx->dev->dump_nodes(d);
-        ag_format_node_dump(d, ctx->reads, ctx->dump);
+        ag_format_node_dump(d, (*ctx->rp), ctx->dump);
         *text = ctx->dump.data(); *len = ctx->dump.size();
     });
 }
@@ -339,7 +361,7 @@ int ag_formalize_inputs(ag_ctx* ctx, const char* contig_fa, const char* genome_f
 }
 int ag_pin_staged(ag_ctx* ctx) {
     return guard(ctx, [&] {
-        AgDevice& d = *ctx->dev; const AgReads& r = ctx->reads; const AgUnit& u = ctx->unit;
+        AgDevice& d = *ctx->dev; const AgReads& r = (*ctx->rp); const AgUnit& u = ctx->unit;
         d.unpin_all();
         d.pin(r.bases.data(), r.bases.size() * 4); d.pin(r.nmask.data(), r.nmask.size() * 4); d.pin(r.len.data(), r.len.size() * 2);
         d.pin(u.ref.data(), u.ref.size()); if (u.threads.empty()) { d.pin(u.cm_start.data(), u.cm_start.size() * 4); d.pin(u.cm.data(), u.cm.size() * sizeof(ag_cm)); }

@@ -2,19 +2,25 @@
 // coverage filter (AG:1904-1918) and extension walk (AG:1954-2204).  Integer / indexing work, HBM- and latency-bound: no tensor
 // cores.  See DESIGN.md §3-§5 for the formulation, the HBM layout and the per-kernel algorithmic bytes.
 //
-//   k_prep        1 thread / alignment   resolve left mate, touch range, tile count               (AG:1657-1679)
+//   k_cm_count / k_cm_fill / k_cm_sort / k_cm1   contiMer table (CSR + per-position summary) from the uploaded contig threads  (AG:884-1177)
+//   k_prep        1 thread / alignment   resolve left mate, touch range, tile count, clean-alignment bit      (AG:1657-1679)
 //   k_keys        1 thread / alignment   emit (tile, alignment) keys in alignment order
-//   radix sort    stable LSD, 4-bit      bucket alignments by 256-position tile, order preserved
-//   k_nodes       1 CTA / tile, 1 thread / position   ordered first-compatible clustering      (AG:1353-1587)
-//   k_finalize    1 thread / position    position-ordered node table, consensus base, coverage filter (AG:1904-1918, 1944-1952)
-//   k_edges       1 CTA / tile           de-duplicated successor sets                            (AG:1590-1623)
-//   k_uf_*        union-find             independent walk components
-//   k_walk_*      1 thread / component   exact replay of the greedy walk                         (AG:1972-2162)
-//   k_materialize 1 thread / emitted walk  base strings
+//   k_rs_hist / k_rs_scatter   stable LSD radix sort, 5-bit digits: alignments bucketed by 248-position tile, order preserved
+//   k_build       1 CTA / tile, 1 thread / position (+ 1 halo lane per warp)   ordered first-compatible clustering (AG:1353-1587),
+//                 coverage filter + consensus base (AG:1904-1918, 1944-1952) and the common-case edges (AG:1590-1623) in one sweep
+//   k_posfix / k_succ   tile blocks -> position order, successor-item bits -> node indices
+//   k_edges       generic edge sweep, flagged tiles only                                                          (AG:1590-1623)
+//   k_indeg / k_links / k_rank_local / k_rank / k_cand_* / k_hrec   forced-link chains, start candidates, hop records
+//   k_uf_*        union-find over chain tails: independent walk components
+//   k_walk_components (1 warp / component) | k_walk_sequential (skip rule)   exact replay of the greedy walk    (AG:1972-2204)
+//   k_mat_*       base strings of the emitted walks; k_occupancy  bitmap for the scaffold gap test              (AG:2428)
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <chrono>
+#include <dlfcn.h>
+#include <nccl.h>   // types only: the library is bound with dlopen (ag_device_broadcast_reads)
 #include "ag_core.h"
 #include "ag_device.cuh"
 
@@ -1008,6 +1014,98 @@ void AgDevice::copy_reads_to_host(u32* bases, u32* nmask, uint16_t* len) {
     CK(cudaStreamSynchronize(m.st));
 }
 
+AgDevice::ReadsView AgDevice::reads_view() {
+    Impl& m = *m_;
+    ReadsView v;
+    v.bases = const_cast<u32*>(m.reads.bases); v.nmask = const_cast<u32*>(m.reads.nmask); v.len = const_cast<uint16_t*>(m.reads.len);
+    v.n_pairs = m.n_pairs; v.stride2 = m.reads.stride2; v.stridem = m.reads.stridem;
+    v.bases_bytes = 2 * m.n_pairs * m.reads.stride2 * sizeof(u32); v.nmask_bytes = 2 * m.n_pairs * m.reads.stridem * sizeof(u32); v.len_bytes = m.n_pairs * sizeof(uint16_t);
+    return v;
+}
+AgDevice::ReadsView AgDevice::reserve_reads(u64 n_pairs, u32 stride2, u32 stridem) {
+    CK(cudaSetDevice(dev_));
+    Impl& m = *m_;
+    m.n_pairs = n_pairs;
+    m.r_bases.ensure(2 * n_pairs * stride2 + 1); m.r_nmask.ensure(2 * n_pairs * stridem + 1); m.r_len.ensure(n_pairs + 1);
+    m.reads.bases = m.r_bases.p; m.reads.nmask = m.r_nmask.p; m.reads.len = m.r_len.p; m.reads_owned = true;
+    m.reads.stride2 = stride2; m.reads.stridem = stridem;
+    return reads_view();
+}
+
+// ---- one broadcast of the packed reads to every GPU of the run ---------------------------------------------------------
+// NCCL is bound at run time (dlopen): a single-GPU run needs no libnccl, and inside a process that already carries one (torch) the same
+// copy is used.  Single process, one communicator per device (ncclCommInitAll), the three buffers as one group.
+namespace {
+struct NcclApi {
+    void* h = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    bool ok = false;
+    NcclApi() {
+        if (getenv("AG_NO_NCCL")) return;
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) { h = dlopen(name, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+        if (!h) return;
+        CommInitAll = (decltype(CommInitAll))dlsym(h, "ncclCommInitAll"); CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
+        GroupStart = (decltype(GroupStart))dlsym(h, "ncclGroupStart"); GroupEnd = (decltype(GroupEnd))dlsym(h, "ncclGroupEnd");
+        Broadcast = (decltype(Broadcast))dlsym(h, "ncclBroadcast");
+        ok = CommInitAll && CommDestroy && GroupStart && GroupEnd && Broadcast;
+    }
+};
+NcclApi& nccl() { static NcclApi a; return a; }
+}  // namespace
+
+const char* ag_device_broadcast_reads(AgDevice** devs, int n, double* seconds, size_t* bytes) {
+    if (seconds) *seconds = 0;
+    if (bytes) *bytes = 0;
+    if (n <= 1) return "none";
+    devs[0]->sync();
+    const AgDevice::ReadsView src = devs[0]->reads_view();
+    std::vector<AgDevice::ReadsView> dst((size_t)n);
+    dst[0] = src;
+    for (int i = 1; i < n; i++) dst[i] = devs[i]->reserve_reads(src.n_pairs, src.stride2, src.stridem);
+    bool distinct = true;
+    for (int i = 0; i < n; i++) for (int j = 0; j < i; j++) if (devs[i]->device() == devs[j]->device()) distinct = false;
+    const auto t0 = std::chrono::steady_clock::now();
+    const char* how = "peer-copy";
+    bool done = false;
+    if (distinct && nccl().ok) {
+        std::vector<int> ids((size_t)n); for (int i = 0; i < n; i++) ids[i] = devs[i]->device();
+        std::vector<ncclComm_t> comm((size_t)n);
+        if (nccl().CommInitAll(comm.data(), n, ids.data()) == ncclSuccess) {
+            bool ok = true;
+            const void* sp[3] = {src.bases, src.nmask, src.len}; const size_t nb[3] = {src.bases_bytes, src.nmask_bytes, src.len_bytes};
+            for (int b = 0; b < 3 && ok; b++) {
+                ok = nccl().GroupStart() == ncclSuccess;
+                for (int i = 0; i < n && ok; i++) {
+                    CK(cudaSetDevice(devs[i]->device()));
+                    void* rp = b == 0 ? (void*)dst[i].bases : b == 1 ? (void*)dst[i].nmask : (void*)dst[i].len;
+                    ok = nccl().Broadcast(sp[b], rp, nb[b], ncclUint8, 0, comm[i], (cudaStream_t)devs[i]->stream()) == ncclSuccess;
+                }
+                ok = nccl().GroupEnd() == ncclSuccess && ok;
+            }
+            for (int i = 0; i < n; i++) devs[i]->sync();
+            for (int i = 0; i < n; i++) nccl().CommDestroy(comm[i]);
+            if (ok) { done = true; how = "nccl"; }
+        }
+    }
+    if (!done) {
+        for (int i = 1; i < n; i++) {
+            CK(cudaSetDevice(devs[i]->device()));
+            cudaStream_t st = (cudaStream_t)devs[i]->stream();
+            CK(cudaMemcpyPeerAsync(dst[i].bases, devs[i]->device(), src.bases, devs[0]->device(), src.bases_bytes, st));
+            CK(cudaMemcpyPeerAsync(dst[i].nmask, devs[i]->device(), src.nmask, devs[0]->device(), src.nmask_bytes, st));
+            CK(cudaMemcpyPeerAsync(dst[i].len, devs[i]->device(), src.len, devs[0]->device(), src.len_bytes, st));
+        }
+        for (int i = 1; i < n; i++) devs[i]->sync();
+    }
+    if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (bytes) *bytes = (src.bases_bytes + src.nmask_bytes + src.len_bytes) * (size_t)(n - 1);
+    return how;
+}
+
 void AgDevice::load_unit(const AgUnitInput& in) {
     CK(cudaSetDevice(dev_));
     Impl& m = *m_;
@@ -1091,7 +1189,9 @@ void AgDevice::build() {
         m.scanner.run(m.ntiles.p, m.key_off.p, nA, st);
         volatile u32* hs = (volatile u32*)m.h_s.p;
         CK(cudaMemcpyAsync((void*)hs, m.key_off.p + nA, sizeof(u32), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync((void*)(hs + 2), m.err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
+        if (hs[2] == 2) throw AgError{"BOWTIE ALIGNMENT ERROR: alignment outside the unit"};   // k_prep's verdict, read before the sweeps can overwrite the error word
         const u32 nk = hs[0];
         m.n_keys = nk;
         m.keys.ensure(nk + 1); m.vals.ensure(nk + 1); m.keys2.ensure(nk + 1); m.vals2.ensure(nk + 1);

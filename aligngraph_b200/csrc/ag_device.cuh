@@ -42,6 +42,11 @@ public:
     // (the unit's own uploads), so that it runs under the unit's table / prep / bucket kernels; build() waits for it before the node sweep
     void set_reads_sparse(const u32* bases, const u64* exc_keys, u64 n_exc, const uint16_t* len, u64 n_pairs, u32 stride2, u32 stridem, bool overlap = false);
     void copy_reads_to_host(u32* bases, u32* nmask, uint16_t* len);
+    // device-resident read set of this context as raw buffers (for the broadcast to the other GPUs of a run)
+    struct ReadsView { u32* bases; u32* nmask; uint16_t* len; size_t bases_bytes, nmask_bytes, len_bytes; u64 n_pairs; u32 stride2, stridem; };
+    ReadsView reads_view();
+    // make own, uninitialised buffers of this geometry the context's read set (the caller fills them: broadcast target)
+    ReadsView reserve_reads(u64 n_pairs, u32 stride2, u32 stridem);
     void set_params(int k, int iv, int coverage) { k_ = k; iv_ = iv; cov_ = coverage; }
     // keep coverage + base counters per node after the build (24 B per node; only the node dump of the tests needs them)
     void set_keep_counts(bool on) { keep_counts_ = on; }
@@ -90,6 +95,10 @@ private:
     void walk_components();
     void walk_sequential();
 };
+
+// One broadcast of the packed read set from devs[0] to devs[1..n-1]: ncclBroadcast over NVLink when libnccl can be loaded and
+// the devices are distinct, else cudaMemcpyPeerAsync / device-to-device copies.  Returns "nccl" or "peer-copy".
+const char* ag_device_broadcast_reads(AgDevice** devs, int n, double* seconds, size_t* bytes);
 
 // thrown on any CUDA failure or capacity error; the C ABI turns it into an error code + ag_last_error()
 struct AgError { std::string msg; };

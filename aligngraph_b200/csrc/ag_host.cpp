@@ -1463,7 +1463,8 @@ void ag_refinement(const std::string& tmp, int units, const std::vector<std::str
 
 // The host side stages hundreds of MB per unit in vectors.  By default glibc serves such blocks with mmap and returns them on free, so
 // every unit pays the page faults (and the kernel's page zeroing) again; keeping them on the heap makes the second and later units run
-// on warm memory.  Opt out with AG_NO_MALLOPT=1.
+// on warm memory.  This is process-wide allocator policy, so the library only applies it when asked to (AG_MALLOPT=1, see ag_create); the
+// drop-in CLI applies it in its own main().  AG_NO_MALLOPT=1 switches it off everywhere.
 void ag_tune_malloc() {
     static bool done = false;
     if (done || getenv("AG_NO_MALLOPT")) return;

@@ -149,7 +149,7 @@ static bool blat_call(const string& db, const string& query, const string& out) 
 static void run_blat(int units) {
     for (int u = 0; u < units; u++) {
         string n = std::to_string(u);
-        if (!blat_call("tmp/_genome." + n + ".fa", "tmp/_contigs.fa", "tmp/_contigs_genome." + n + ".psl")) die("BLAT CALL FAILED!");
+        if (!blat_call("tmp/_genome." + n + ".fa", "tmp/_contigs.fa", "tmp/_contigs_genome." + n + ".psl")) throw AgHostError{"BLAT CALL FAILED!"};
     }
 }
 static bool refine_blat(int unit, void*) {
@@ -161,6 +161,7 @@ int main(int argc, char* argv[]) {
     cout << "AlignGraph: algorithm for secondary de novo genome assembly guided by closely related references" << endl;
     cout << "By Ergude Bao, CS Department, UC-Riverside. All Rights Reserved" << endl << endl;
     time_t start = time(NULL), startAlign, endAlign;
+    ag_tune_malloc();   // the CLI owns its process: keep the large staging blocks on the heap from unit to unit
     {
         std::ofstream w("command.txt");
         if (!w.is_open()) { cout << "CANNOT OPEN FILE!" << endl; return 0; }
@@ -186,9 +187,13 @@ int main(int argc, char* argv[]) {
             units = ag_formalize_genome(o.genome, "tmp", o.part, genome_ids);
             startAlign = time(NULL);
             {   // parallelMap (AG:3720-3735): the read and the contig alignment jobs run side by side
-                std::thread t0(run_bowtie, o.low, o.high, units, o.tagIter);
-                std::thread t1(run_blat, units);
+                // a failure inside either thread is reported from the main thread after both have joined (message + exit(-1) as in the reference)
+                string err0, err1;
+                std::thread t0([&] { try { run_bowtie(o.low, o.high, units, o.tagIter); } catch (const AgHostError& e) { err0 = e.msg; } catch (...) { err0 = "BOWTIE2 CALL FAILED!"; } });
+                std::thread t1([&] { try { run_blat(units); } catch (const AgHostError& e) { err1 = e.msg; } catch (...) { err1 = "BLAT CALL FAILED!"; } });
                 t0.join(); t1.join();
+                if (!err0.empty()) die(err0);
+                if (!err1.empty()) die(err1);
             }
             endAlign = time(NULL);
             cout << "(0) Alignment finished" << endl;
@@ -231,18 +236,18 @@ int main(int argc, char* argv[]) {
         }
         // reads are parsed once and shared by every unit (the reference re-reads tmp/_reads.fa per chromosome, AG:1880)
         if (ag_load_reads_fasta(ctxs[0], "tmp/_reads.fa") != 0) die(ag_last_error(ctxs[0]));
-        for (size_t g = 1; g < ctxs.size(); g++) {
-            const uint32_t *b, *m; const uint16_t* l; uint64_t n; uint32_t s2, sm;
-            ag_get_reads(ctxs[0], &b, &m, &l, &n, &s2, &sm);
-            if (ag_set_reads(ctxs[g], b, m, l, n, s2, sm) != 0) die(ag_last_error(ctxs[g]));
+        if (ctxs.size() > 1) {   // ONE broadcast of the packed read buffer to the other GPUs; host copy incl. the exception list is shared
+            ag_bcast_info bi;
+            if (ag_broadcast_reads(ctxs.data(), (int)ctxs.size(), &bi) != 0) die(ag_last_error(ctxs[0]));
+            if (getenv("AG_STATS")) fprintf(stderr, "[ag] reads broadcast to %zu GPUs: %.1f MB in %.1f ms (%s)\n", ctxs.size() - 1, bi.bytes / 1e6, bi.seconds * 1e3, bi.nccl ? "ncclBroadcast" : "peer copy");
         }
         std::vector<string> errors((size_t)units);
         std::vector<char> done((size_t)units, 0);
         int printed = cp;
-        struct Progress { std::vector<string>* errors; std::vector<char>* done; int* printed; int units; std::ofstream* wcp; } pg{&errors, &done, &printed, units, &wcp};
+        struct Progress { std::vector<string>* errors; std::vector<char>* done; int* printed; int units; std::ofstream* wcp; int failed; } pg{&errors, &done, &printed, units, &wcp, -1};
         auto flush_progress = [](Progress& g) {  // progress lines and checkpoints strictly in unit order, as the reference emits them
-            while (*g.printed < g.units && (*g.done)[(size_t)*g.printed]) {
-                if (!(*g.errors)[(size_t)*g.printed].empty()) die((*g.errors)[(size_t)*g.printed]);
+            while (g.failed < 0 && *g.printed < g.units && (*g.done)[(size_t)*g.printed]) {
+                if (!(*g.errors)[(size_t)*g.printed].empty()) { g.failed = *g.printed; return; }   // reported by the main thread after the workers have returned
                 cout << endl << "CHROMOSOME " << *g.printed << ": " << endl;
                 cout << "(1) Chromosome loaded" << endl << "(2) Contig alignment loaded" << endl << "(3) Read alignment loaded" << endl
                      << "(4) Contigs extended" << endl << "(5) Contigs scaffolded" << endl;
@@ -262,6 +267,7 @@ int main(int argc, char* argv[]) {
         if (const char* e = getenv("AG_PREFETCH")) prefetch = atoi(e);
         ag_run_units_files(ctxs.data(), (int)ctxs.size(), "tmp", cp, units - cp, prefetch, on_done, &pg);
         flush_progress(pg);
+        if (pg.failed >= 0) die(errors[(size_t)pg.failed]);   // the reference prints the message and exits at the failing chromosome (exit(-1))
         if (getenv("AG_STATS")) {
             for (size_t g = 0; g < ctxs.size(); g++) {
                 ag_stats s; ag_get_stats(ctxs[g], &s);
@@ -277,8 +283,8 @@ int main(int argc, char* argv[]) {
         ag_refinement("tmp", units, genome_ids, contig_ids, o.tagUnique, o.ext, o.rmn, refine_blat, nullptr, true);  // #define TEST (AG:24) => in.fa / ex.fa
     } catch (const AgHostError& e) { die(e.msg); }
     if (o.tagMis == 1) {
-        // removeMisassembly (AG:3821-4297) re-runs Bowtie2/BLAT on the outputs; it is outside the accelerated path
-        cout << endl << "(6) Misassembly removal is not part of the B200 build yet; outputs are the un-corrected contigs" << endl;
+        // removeMisassembly (AG:3821-4297): never report success for a step that did not run
+        die("--misassemblyRemoval (AG:3821-4297) is not implemented in the B200 build: extendedContigs / remainingContigs above are the UN-corrected contigs");
     }
     time_t end = time(NULL);
     cout << endl << "FINISHED SUCCESSFULLY for " << end - start << " seconds (" << endAlign - startAlign << " seconds for alignment) :-)" << endl;

@@ -83,6 +83,12 @@ int ag_load_reads_fasta(ag_ctx* ctx, const char* path);
 /* packed host copy held by the context (after ag_load_reads_fasta) — lets a launcher broadcast it */
 int ag_get_reads(ag_ctx* ctx, const uint32_t** bases2, const uint32_t** nmask, const uint16_t** pair_len, uint64_t* n_pairs, uint32_t* stride2, uint32_t* stridem);
 
+/* one read set for every context of a run (one context per GPU): ctxs[0] holds it (ag_load_reads_fasta / ag_set_reads*); the others share
+ * its host copy and receive the packed device buffers through ONE broadcast — ncclBroadcast over NVLink when libnccl is loadable and the
+ * devices are distinct, cudaMemcpyPeerAsync otherwise (replaces the per-chromosome re-read of tmp/_reads.fa, AG:1880) */
+typedef struct ag_bcast_info { double seconds; uint64_t bytes; int nccl; } ag_bcast_info;
+int ag_broadcast_reads(ag_ctx** ctxs, int n_ctx, ag_bcast_info* info /* may be NULL */);
+
 /* ---- array level -------------------------------------------------------------------------------------------------------------- */
 int ag_begin_unit(ag_ctx* ctx, int unit_id, const char* ref_bases, uint32_t n_ref);                       /* loadGenome, AG:287 */
 int ag_set_contimers(ag_ctx* ctx, const uint32_t* cm_start /* n_ref+n_tail+1 */, const ag_cm_c* cm, uint32_t n_cm,

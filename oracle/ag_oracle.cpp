@@ -18,7 +18,7 @@
 // It is written as a *literal sequential* restatement (array-of-lists, same visiting order) so that every order-dependent
 // behaviour of the reference is reproduced; the product uses a different, position-parallel formulation.
 //
-// Parity pin: tests/test_oracle_vs_reference.py runs the unmodified reference (oracle/_ref, built by `make ref`) and this
+// Parity pin: tests/test_oracle.py runs the unmodified reference (oracle/_ref, built by `make ref`) and this
 // program on the same tmp/ inputs and byte-compares all three per-unit outputs; tests/golden/ holds outputs of the real
 // reference for the committed fixtures so the pin also holds where /root/reference is absent (the GPU box).
 #include <cstdio>

@@ -50,3 +50,31 @@ def test_no_gpu_is_a_loud_failure(tmp_path, harness):
     harness.synth(str(tmp_path), **cases.GOLDEN["plain"])
     r = subprocess.run([CLI, "--resume"], cwd=tmp_path, env=harness.stub_env(), capture_output=True, text=True)
     assert r.returncode == 255 and "no CUDA device" in r.stdout
+
+
+def _ratio_case(harness, d):
+    """`mix` (unaligned pairs, pairs failing the 0.6 filter, multi-hits) with --ratioCheck appended to the resumed command line."""
+    import cases
+    import shutil
+    harness.synth(d, **cases.GOLDEN["mix"])
+    shutil.copy(os.path.join(d, "reads_1.fa"), os.path.join(d, "tmp", "_reads_1.fa"))   # checkRatio only counts its '>' lines (AlignGraph.cpp:3762-3768)
+    with open(os.path.join(d, "tmp", "_command.txt"), "a") as f:
+        f.write("--ratioCheck\n")
+
+
+RATIO_LINE_MIX = " - 95.2333% reads aligned "   # printed by the unmodified reference (oracle/_ref) on this case; re-checked live below where it exists
+
+
+def test_ratio_check_line_matches_reference(tmp_path, harness):
+    """--ratioCheck (checkRatio, AlignGraph.cpp:3751-3819) prints the reference's percentage, character for character — before the
+    per-chromosome loop, so no GPU is needed to see it."""
+    d = str(tmp_path / "ours")
+    _ratio_case(harness, d)
+    r = subprocess.run([CLI, "--resume"], cwd=d, env=harness.stub_env(), capture_output=True, text=True)
+    ours = [l for l in r.stdout.splitlines() if "reads aligned" in l]
+    assert ours == [RATIO_LINE_MIX], r.stdout[-400:]
+    if harness.have_reference():
+        d2 = str(tmp_path / "ref")
+        _ratio_case(harness, d2)
+        rc, out = harness.run_reference(d2)
+        assert [l for l in out.splitlines() if "reads aligned" in l] == ours

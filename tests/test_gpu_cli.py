@@ -60,6 +60,31 @@ def test_cli_multi_device_env_same_output(harness, workdir):
     assert r.stdout.index("CHROMOSOME 0") < r.stdout.index("CHROMOSOME 1")
 
 
+def test_cli_multi_device_non_acgt_reads(harness, workdir):
+    """Units that run on a SECONDARY context must print the original non-ACGT characters of read tails (AlignGraph.cpp:2167), i.e. the
+    contexts of a run share one read set including its exception list (ag_broadcast_reads).  Two units, lower-case and 'N' reads,
+    contexts 0,0: per-unit files identical to the oracle's, whichever context ran the unit."""
+    import shutil
+    gpu, ora = os.path.join(workdir, "gpu"), os.path.join(workdir, "ora")
+    harness.synth(gpu, genome_bp=40000, chroms=2, coverage=45, contig_len=3500, contig_gap=500, n_rate=0.01, seed=77)
+    p = os.path.join(gpu, "tmp", "_reads.fa")
+    lines = open(p).read().split("\n")
+    with open(p, "w") as f:
+        for i, l in enumerate(lines):
+            if l:
+                f.write((l if l.startswith(">") or (i // 2) % 3 else l.lower()) + "\n")
+    shutil.copytree(gpu, ora)
+    harness.run_oracle(ora)
+    env = harness.stub_env(); env["AG_DEVICES"] = "0,0"; env["AG_PREFETCH"] = "2"
+    r = subprocess.run([CLI, "--resume"], cwd=gpu, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-500:]
+    pre = b""
+    for u in range(2):
+        assert harness.unit_outputs(gpu, u) == harness.unit_outputs(ora, u), f"unit {u}"
+        pre += harness.unit_outputs(gpu, u)[1]
+    assert any(c in pre for c in (b"a", b"c", b"g", b"t")), "the case must put lower-case tail characters into the output"
+
+
 def test_cli_usage_and_errors(workdir):
     r = subprocess.run([CLI], cwd=workdir, capture_output=True, text=True)
     assert r.returncode == 0 and "--read1 is the the first pair" in r.stdout
