@@ -29,7 +29,8 @@ class Stats(C.Structure):
                [(n, C.c_double) for n in ("s_parse", "s_device_section", "s_post")] + \
                [(n, C.c_uint64) for n in ("n_aln", "n_nodes", "n_walks", "n_emitted", "n_keys", "n_tiles", "kernel_launches",
                                           "h2d_bytes", "d2h_bytes")] + \
-               [("walk_fallback", C.c_int)]
+               [("walk_fallback", C.c_int), ("ms_ingest_reads", C.c_float), ("ms_ingest_sam", C.c_float)] + \
+               [(n, C.c_uint64) for n in ("sam_device", "sam_host", "reads_device", "reads_host", "regrows")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -86,6 +87,7 @@ def load_library(path=None):
         "ag_reupload_reads": (i32, [vp]),
         "ag_pin_staged": (i32, [vp]),
         "ag_formalize_inputs": (i32, [vp, cp, cp, cp, i32, C.POINTER(i32)]),
+        "ag_set_option": (i32, [vp, cp, C.c_long]),
         "ag_timer_start": (i32, [vp]),
         "ag_timer_stop": (i32, [vp, C.POINTER(C.c_float)]),
     }
@@ -217,6 +219,9 @@ class Context:
         self._ck(self._lib.ag_formalize_inputs(self._h, os.fsencode(contig_fa), os.fsencode(genome_fa), os.fsencode(tmp_dir), part, C.byref(n)),
                  "ag_formalize_inputs")
         return n.value
+
+    def set_option(self, name, value):
+        self._ck(self._lib.ag_set_option(self._h, name.encode(), int(value)), "ag_set_option")
 
     def timer_start(self):
         self._ck(self._lib.ag_timer_start(self._h), "ag_timer_start")

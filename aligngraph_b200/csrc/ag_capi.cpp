@@ -27,9 +27,30 @@ struct ag_ctx {
     std::vector<u64> exc_keys;
     double s_parse = 0, s_device = 0, s_post = 0;
     u64 n_aln = 0, n_walks = 0, n_emitted = 0;
+    bool host_parse = getenv("AG_HOST_PARSE") != nullptr;
 };
 
 static std::string g_create_error;
+
+static bool device_ingest_enabled(const ag_ctx* ctx) { return !ctx->host_parse; }   // AG_HOST_PARSE=1 / option "host_parse": text is parsed by the host parsers only
+
+// the packed words of a device-ingested read set, fetched from the device when a host-side consumer asks for them
+static void ensure_host_reads(ag_ctx* ctx) {
+    AgReads& r = *ctx->rp;
+    if (!r.device_only()) return;
+    r.bases.resize(2 * r.n_pairs * r.stride2); r.nmask.resize(2 * r.n_pairs * r.stridem);
+    std::vector<uint16_t> len(r.n_pairs);
+    ctx->dev->copy_reads_to_host(r.bases.data(), r.nmask.data(), len.data());
+}
+// SAM of unit `unit_id`: parsed on the device (the tuples stay there); files outside the well-formed layout go to the host parser
+static void load_unit_sam(ag_ctx* ctx, const std::string& tmp, int unit_id) {
+    AgUnit& u = ctx->unit;
+    const std::string path = tmp + "/_reads_genome." + std::to_string(unit_id) + ".bowtie";
+    u.aln.clear(); u.ext.clear(); u.aln_on_device = false;
+    if (device_ingest_enabled(ctx) && ctx->dev->ingest_sam(path)) { u.aln_on_device = true; return; }
+    ag_parse_sam(path, *ctx->rp, u);
+    ctx->dev->note_host_sam();
+}
 
 template <class F> static int guard(ag_ctx* ctx, F f) {
     try { f(); return 0; }
@@ -59,6 +80,7 @@ const char* ag_create_error(void) { return g_create_error.c_str(); }
 // host -> device copy of the context's packed reads.  The non-ACGT bit plane is all zeros except where the parser recorded an exception,
 // so when that list is complete only the list travels (8 bytes per non-ACGT character) and the device rebuilds the plane.
 static void upload_reads(ag_ctx* ctx, bool overlap = false) {
+    ensure_host_reads(ctx);
     const AgReads& r = (*ctx->rp);
     if (r.exc_complete && r.exc.size() * 8 < r.nmask.size() * 4) {
         ctx->exc_keys.resize(r.exc.size());
@@ -100,14 +122,22 @@ int ag_load_reads_fasta(ag_ctx* ctx, const char* path) {
         ctx->dev->unpin_all();
         auto t0 = std::chrono::steady_clock::now();
         ctx->rp = std::make_shared<AgReads>();
+        if (device_ingest_enabled(ctx) && ctx->dev->ingest_reads(path, *ctx->rp)) {   // raw text -> device, packed there (ag_ingest.cuh)
+            ctx->s_parse += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            ctx->have_reads = true; ctx->reads_dirty = false;
+            return;
+        }
+        ctx->rp = std::make_shared<AgReads>();
         ag_parse_reads(path, (*ctx->rp));
         ctx->s_parse += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         upload_reads(ctx);
+        ctx->dev->note_host_reads();
         ctx->have_reads = true;
     });
 }
 int ag_get_reads(ag_ctx* ctx, const uint32_t** bases2, const uint32_t** nmask, const uint16_t** pair_len, uint64_t* n_pairs, uint32_t* stride2, uint32_t* stridem) {
     return guard(ctx, [&] {
+        ensure_host_reads(ctx);
         const AgReads& r = (*ctx->rp);
         *bases2 = r.bases.data(); *nmask = r.nmask.data(); *pair_len = r.len.data(); *n_pairs = r.n_pairs; *stride2 = r.stride2; *stridem = r.stridem;
     });
@@ -185,7 +215,7 @@ int ag_build(ag_ctx* ctx) {
         if (ctx->reads_dirty) upload_reads(ctx, true);   // overlaps the unit's table / prep / bucket kernels
         ctx->dev->build();
         ctx->s_device += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-        ctx->n_aln += ctx->unit.aln.size();
+        ctx->n_aln += ctx->unit.aln_on_device ? ctx->dev->ingested_alignments() : ctx->unit.aln.size();
     });
 }
 
@@ -214,7 +244,8 @@ int ag_prepare_unit_files(ag_ctx* ctx, const char* tmp_dir, int unit_id) {
         if (!ctx->have_reads) throw AgHostError{"reads not set"};
         auto t0 = std::chrono::steady_clock::now();
         ctx->dev->unpin_all(); ctx->unit = AgUnit(); ctx->res.reset(); ctx->unit_id = unit_id; ctx->uploaded = false;
-        ag_prepare_unit((*ctx->rp), tmp_dir, unit_id, ctx->unit, ctx->res.initial_text);
+        ag_prepare_unit((*ctx->rp), tmp_dir, unit_id, ctx->unit, ctx->res.initial_text, false, ctx->host_parse);
+        load_unit_sam(ctx, tmp_dir, unit_id);
         ctx->s_parse += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     });
 }
@@ -267,7 +298,7 @@ int ag_run_units_files(ag_ctx** ctxs, int n_ctx, const char* tmp_dir, int first_
             if (stop.load()) return;
             auto p = std::make_unique<Prepared>();
             auto t0 = std::chrono::steady_clock::now();
-            try { ag_prepare_unit(reads, tmp, u, p->unit, p->initial_text); }
+            try { ag_prepare_unit(reads, tmp, u, p->unit, p->initial_text, !device_ingest_enabled(ctxs[0]), !device_ingest_enabled(ctxs[0])); }
             catch (const AgHostError& e) { p->error = e.msg; }
             catch (const std::bad_alloc&) { p->error = "out of host memory"; }
             p->s_parse = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -289,7 +320,8 @@ int ag_run_units_files(ag_ctx** ctxs, int n_ctx, const char* tmp_dir, int first_
                 ctx->dev->unpin_all();
                 ctx->unit = std::move(p->unit); ctx->res.reset(); ctx->res.initial_text = std::move(p->initial_text);
                 ctx->unit_id = u; ctx->uploaded = false; ctx->s_parse += p->s_parse;
-                rc = ag_build(ctx);
+                if (device_ingest_enabled(ctx)) rc = guard(ctx, [&] { auto t0 = std::chrono::steady_clock::now(); load_unit_sam(ctx, tmp, u); ctx->s_parse += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); });
+                if (!rc) rc = ag_build(ctx);
                 if (!rc) rc = ag_extend(ctx);
                 if (!rc) rc = ag_write_unit_files(ctx, tmp_dir, u);
             }
@@ -310,6 +342,8 @@ int ag_run_units_files(ag_ctx** ctxs, int n_ctx, const char* tmp_dir, int first_
 int ag_get_unit(ag_ctx* ctx, ag_unit_view* out) {
     return guard(ctx, [&] {
         AgUnit& u = ctx->unit;
+        if (!u.cdesc.empty() && u.chain_pos.empty()) { ctx->dev->unpin_all(); ag_expand_chains(u); ctx->uploaded = false; }   // inspection copy of the chain-major arrays
+        if (u.aln_on_device && u.aln.empty()) { ctx->dev->unpin_all(); ctx->dev->fetch_alignments(u.aln, u.ext); }   // inspection copy; the device keeps using its own
         if (u.cm_start.size() != u.ref.size() + 1 || u.cm.size() != u.chain_pos.size()) { ctx->dev->unpin_all(); ag_expand_contimers(u); }   // table view on demand
         out->ref = u.ref.data(); out->n_ref = u.n_ref; out->n_tail = (uint32_t)u.ref.size() - u.n_ref;
         out->cm_start = u.cm_start.data(); out->cm = (const ag_cm_c*)u.cm.data(); out->n_cm = (uint32_t)u.cm.size();
@@ -327,6 +361,7 @@ int ag_get_stats(ag_ctx* ctx, ag_stats* o) {
         o->ms_components = t.components; o->ms_chains = t.chains; o->ms_walk = t.walk; o->ms_materialize = t.materialize; o->ms_d2h = t.d2h;
         o->s_parse = ctx->s_parse; o->s_device_section = ctx->s_device; o->s_post = ctx->s_post;
         o->n_aln = ctx->n_aln; o->n_nodes = t.n_nodes; o->n_walks = ctx->n_walks; o->n_emitted = ctx->n_emitted; o->n_keys = t.n_keys; o->n_tiles = t.n_tiles;
+        o->ms_ingest_reads = t.ingest_reads; o->ms_ingest_sam = t.ingest_sam; o->sam_device = t.sam_device; o->sam_host = t.sam_host; o->reads_device = t.reads_device; o->reads_host = t.reads_host; o->regrows = (uint64_t)t.regrows;
         o->kernel_launches = ctx->dev->kernel_launches(); o->h2d_bytes = t.h2d_bytes; o->d2h_bytes = t.d2h_bytes; o->walk_fallback = t.walk_fallback;
     });
 }
@@ -339,6 +374,7 @@ int ag_keep_node_counts(ag_ctx* ctx, int on) {
 
 int ag_dump_nodes_text(ag_ctx* ctx, const char** text, uint64_t* len) {
     return guard(ctx, [&] {
+        ensure_host_reads(ctx);
         AgNodeDump d; ctx->dev->dump_nodes(d);
         ag_format_node_dump(d, (*ctx->rp), ctx->dump);
         *text = ctx->dump.data(); *len = ctx->dump.size();
@@ -361,6 +397,7 @@ int ag_formalize_inputs(ag_ctx* ctx, const char* contig_fa, const char* genome_f
 }
 int ag_pin_staged(ag_ctx* ctx) {
     return guard(ctx, [&] {
+        ensure_host_reads(ctx);
         AgDevice& d = *ctx->dev; const AgReads& r = (*ctx->rp); const AgUnit& u = ctx->unit;
         d.unpin_all();
         d.pin(r.bases.data(), r.bases.size() * 4); d.pin(r.nmask.data(), r.nmask.size() * 4); d.pin(r.len.data(), r.len.size() * 2);
@@ -368,6 +405,14 @@ int ag_pin_staged(ag_ctx* ctx) {
         d.pin(u.threads.data(), u.threads.size() * sizeof(ag_cthread));
         d.pin(u.chain_pos.data(), u.chain_pos.size() * 4); d.pin(u.chain_base.data(), u.chain_base.size());
         d.pin(u.aln.data(), u.aln.size() * sizeof(ag_aln)); d.pin(u.ext.data(), u.ext.size() * sizeof(ag_seg));
+    });
+}
+int ag_set_option(ag_ctx* ctx, const char* name, long value) {
+    return guard(ctx, [&] {
+        const std::string n = name ? name : "";
+        if (n == "host_parse") ctx->host_parse = value != 0;
+        else if (n == "node_cap" || n == "ovf_cap" || n == "eovf_cap" || n == "section_timing") ctx->dev->set_option(n, value);
+        else throw AgHostError{"unknown option: " + n};
     });
 }
 int ag_timer_start(ag_ctx* ctx) { return guard(ctx, [&] { ctx->dev->timer_start(); }); }

@@ -21,8 +21,13 @@
 #include <chrono>
 #include <dlfcn.h>
 #include <nccl.h>   // types only: the library is bound with dlopen (ag_device_broadcast_reads)
+#include <atomic>
+#include <fcntl.h>
+#include <unistd.h>
+#include <sys/stat.h>
 #include "ag_core.h"
 #include "ag_device.cuh"
+#include "ag_host.h"
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) throw AgError{std::string(#x) + ": " + cudaGetErrorString(e_)}; } while (0)
 
@@ -162,6 +167,10 @@ __global__ void k_rs_scatter(const u32* __restrict__ keys, const u32* __restrict
         }
 }
 
+}  // namespace
+#include "ag_ingest.cuh"
+namespace {
+
 // ---------------------------------------------------------------------------------------------------------------------------
 // device view of one unit
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -262,6 +271,29 @@ __global__ void k_cm_sort(const u32* __restrict__ cm_start, u32 n_pos, ag_cm* cm
         while (j > 0 && cm[a + j - 1].chain > x.chain) { cm[a + j] = cm[a + j - 1]; j--; }
         cm[a + j] = x;
     }
+}
+
+// chain-major contiMer arrays from the run-space contig threads (ag_thread_contigs_runs): chain index k of thread t is base F + (k - first)
+// of the oriented chunk; it sits on the unit position its run maps it to, or — an inserted base between two runs — in the tail behind the
+// unit; the thread's last contiMer is the terminal and carries the UNIT's base (AG:1121-1148).  One thread per contiMer.
+__global__ void k_chain_expand(const ag_cdesc* __restrict__ desc, u32 n_desc, const ag_crun* __restrict__ runs, const char* __restrict__ blob, const unsigned char* __restrict__ ref,
+                               u32 n_ref, u32 n_cm, u32* __restrict__ chain_pos, unsigned char* __restrict__ chain_base) {
+    const u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_cm) return;
+    u32 lo = 0, hi = n_desc;   // last thread with first <= k
+    while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (desc[mid].first <= k) lo = mid; else hi = mid; }
+    const ag_cdesc d = desc[lo];
+    const ag_crun* r = runs + d.run0;
+    const u32 j = k - d.first;
+    if (j == d.n - 1) { const ag_crun g = r[d.nruns - 1]; const u32 tp = g.dst + g.len - 1; chain_pos[k] = tp; chain_base[k] = ref[tp]; return; }
+    const u32 b = d.F + j;
+    u32 a = 0, e = d.nruns;   // last run with src <= b
+    while (e - a > 1) { const u32 mid = (a + e) >> 1; if (r[mid].src <= b) a = mid; else e = mid; }
+    const ag_crun g = r[a];
+    chain_pos[k] = b < g.src + g.len ? g.dst + (b - g.src) : n_ref + g.gap_tail + (b - g.src - g.len);
+    char c = d.fr ? blob[d.base_off + (d.size - 1 - b)] : blob[d.base_off + b];
+    if (d.fr) c = c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : c;
+    chain_base[k] = (unsigned char)c;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -893,9 +925,16 @@ struct AgDevice::Impl {
     DBuf<u32> walk_next, parent, cmin, cmax, walk_used; DBuf<ag_walk> walks, walks2; DBuf<ag_cm1> cm1; DBuf<MatItem> mat_detours; DBuf<u32> tail_end; u32 n_cand = 0; DBuf<unsigned char> pos_term; DBuf<u32> indeg, fnext, fprev, msuf, mnode, cand_rank, cand_node, cand_label; DBuf<ag_chain> chain_a, chain_b; DBuf<ag_hrec> hrec; DBuf<int> changed;
     DBuf<unsigned char> out_bases, occ; DBuf<u32> sel_start, sel_tails; DBuf<u64> sel_off;
     PinnedBuf h_walks, h_bases, h_occ, h_sel, h_s;   // h_s: page-locked landing zone of the scalar read-backs (a pageable destination makes every copy a synchronous staged transfer)
+    // text ingestion (ag_ingest.cuh)
+    DBuf<char> contig_blob; u64 blob_version = 0; DBuf<ag_cdesc> cdesc; DBuf<ag_crun> cruns;   // run-space contig threads
+    DBuf<char> raw, exc_chr; DBuf<u32> nl, nl_blk, rlen, s_keep, s_next, s_aoff, s_eoff, s_lost, ing; DBuf<u64> exc_key; DBuf<ag_srec> srec; FileStager stager;
+    u64 n_ext = 0; bool aln_ingested = false;
+    // newline index of text[0, len) (device, 16-byte aligned, zero-padded to a multiple of 16).  fill == false: count (block offsets go to
+    // nl_blk[blk_base ..]) and return the number of lines — one blocking read-back; fill == true: write the positions to nl[nl_base ..]
+    u32 nl_index(cudaStream_t st, u64& launches, const char* text, size_t len, size_t blk_base, size_t nl_base, bool fill);
     Scanner scanner;
     u32 n_tiles = 0, n_keys = 0, n_nodes = 0;
-    u32 node_cap = 0, ovf_cap = 0, eovf_cap = 0, walk_cap = 0;
+    u32 node_cap = 0, ovf_cap = 0, eovf_cap = 0, eovf_cap_init = 0, walk_cap = 0;
     DevView view{};
     // counters layout: [0] n_nodes (pool_count), [1] ovf_count, [2] eovf_count, [3] walk_count, [4,5] materialise items
 };
@@ -924,11 +963,20 @@ AgDevice::~AgDevice() {
     for (int i = 0; i < 4; i++) m.scanner.lvl[i].release();
     m.cm.release(); m.cthreads.release(); m.aln.release(); m.ext.release(); m.alnp.release(); m.fast.release(); m.pool_c.release(); m.pool_w.release(); m.ovf_node.release(); m.err.release();
     m.node_c.release(); m.node_w.release(); m.walks.release(); m.walks2.release(); m.cm1.release(); m.mat_detours.release(); m.tail_end.release(); m.pos_term.release(); m.cand_rank.release(); m.cand_node.release(); m.cand_label.release(); m.fprev.release(); m.msuf.release(); m.mnode.release(); m.indeg.release(); m.fnext.release(); m.chain_a.release(); m.chain_b.release(); m.hrec.release(); m.changed.release(); m.sel_off.release();
+    m.contig_blob.release(); m.cdesc.release(); m.cruns.release(); m.raw.release(); m.exc_chr.release(); m.nl.release(); m.nl_blk.release(); m.rlen.release(); m.s_keep.release(); m.s_next.release(); m.s_aoff.release(); m.s_eoff.release(); m.s_lost.release(); m.ing.release(); m.exc_key.release(); m.srec.release(); m.stager.release();
     m.h_walks.release(); m.h_bases.release(); m.h_occ.release(); m.h_sel.release(); m.h_s.release();
     if (ev_mat0_) { cudaEventDestroy((cudaEvent_t)ev_mat0_); cudaEventDestroy((cudaEvent_t)ev_mat1_); }
     if (st2_) { cudaStreamSynchronize((cudaStream_t)st2_); cudaStreamDestroy((cudaStream_t)st2_); cudaEventDestroy((cudaEvent_t)ev_main_); cudaEventDestroy((cudaEvent_t)ev_reads_); }
     if (m.st) cudaStreamDestroy(m.st);
     delete m_;
+}
+
+void AgDevice::set_option(const std::string& name, long value) {
+    Impl& m = *m_;
+    if (name == "node_cap") m.node_cap = (u32)std::max<long>(value, 1);
+    else if (name == "ovf_cap") m.ovf_cap = (u32)std::max<long>(value, 1);
+    else if (name == "eovf_cap") m.eovf_cap_init = (u32)std::max<long>(value, 1);
+    else if (name == "section_timing") section_timing_ = value != 0;
 }
 
 void AgDevice::pin(const void* p, size_t bytes) {
@@ -1106,22 +1154,223 @@ const char* ag_device_broadcast_reads(AgDevice** devs, int n, double* seconds, s
     return how;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// GPU-side text ingestion (kernels: ag_ingest.cuh)
+// ---------------------------------------------------------------------------------------------------------------------------
+namespace {
+struct Fd { int fd; explicit Fd(const std::string& p) : fd(open(p.c_str(), O_RDONLY)) {} ~Fd() { if (fd >= 0) close(fd); } size_t size() const { struct stat st; return fstat(fd, &st) == 0 ? (size_t)st.st_size : 0; } };
+}
+
+// newline index of text[0, len) (device, 16-byte aligned, zero-padded to a multiple of 16): positions into nl[nl_base ..]; returns the
+// number of lines.  `count_only` leaves nl untouched (the caller sizes it first).  One blocking read-back of the total.
+bool AgDevice::ingest_reads(const std::string& path, AgReads& host) {
+    CK(cudaSetDevice(dev_));
+    Impl& m = *m_; cudaStream_t st = m.st;
+    Fd f(path);
+    if (f.fd < 0) throw AgError{"CANNOT OPEN FILE!"};
+    const size_t n = f.size();
+    if (n < 4) return false;
+    char c0 = 0, cl = 0;
+    if (pread(f.fd, &c0, 1, 0) != 1 || pread(f.fd, &cl, 1, (off_t)(n - 1)) != 1 || c0 != '>' || cl != '\n') return false;
+    Timer tm(st);
+    // segments of at most 1 GB cut at record starts ("\n>"), each staged at a 16-byte aligned device offset (32-bit offsets inside a segment)
+    const size_t SEG = (size_t)1 << 30;
+    std::vector<size_t> cut(1, 0);
+    while (n - cut.back() > SEG) {
+        const size_t want = cut.back() + SEG, W = (size_t)1 << 20;
+        std::vector<char> win(W);
+        if (pread(f.fd, win.data(), W, (off_t)(want - W)) != (ssize_t)W) return false;
+        size_t k = W - 1;
+        while (k > 0 && !(win[k] == '>' && win[k - 1] == '\n')) k--;
+        if (k == 0) return false;
+        cut.push_back(want - W + k);
+    }
+    cut.push_back(n);
+    const size_t ns = cut.size() - 1;
+    std::vector<size_t> doff(ns + 1, 0), blk0(ns + 1, 0), nl0(ns + 1, 0), rec0(ns + 1, 0);
+    for (size_t s = 0; s < ns; s++) { doff[s + 1] = (doff[s] + (cut[s + 1] - cut[s]) + 15) / 16 * 16 + 16; blk0[s + 1] = blk0[s] + ((cut[s + 1] - cut[s]) + NL_B - 1) / NL_B + 2; }
+    m.raw.ensure(doff[ns] + 64); m.nl_blk.ensure(blk0[ns] + 2); m.ing.ensure(8);
+    for (size_t s = 0; s < ns; s++) {
+        const size_t len = cut[s + 1] - cut[s];
+        CK(cudaMemsetAsync(m.raw.p + doff[s] + len, 0, 32, st));
+        m.stager.run(f.fd, cut[s], len, m.raw.p + doff[s], st);
+    }
+    t_.h2d_bytes += n;
+    std::vector<u32> lines(ns, 0);
+    for (size_t s = 0; s < ns; s++) { lines[s] = m.nl_index(st, launches_, m.raw.p + doff[s], cut[s + 1] - cut[s], blk0[s], 0, false); nl0[s + 1] = nl0[s] + lines[s]; if (lines[s] & 1) return false; rec0[s + 1] = rec0[s] + lines[s] / 2; }
+    const u64 R = rec0[ns];
+    if (R == 0 || (R & 1) || R >= 0xFFFFFFF0ull) return false;
+    m.nl.ensure(nl0[ns] + 2); m.rlen.ensure(R + 2);
+    CK(cudaMemsetAsync(m.ing.p, 0, 8 * sizeof(u32), st));   // [0] bad flags, [1] max length, [2] exception count
+    for (size_t s = 0; s < ns; s++) {
+        m.nl_index(st, launches_, m.raw.p + doff[s], cut[s + 1] - cut[s], blk0[s], nl0[s], true);
+        const u32 nr = lines[s] / 2;
+        if (nr) { k_rd_len<<<(nr + 255) / 256, 256, 0, st>>>(m.raw.p + doff[s], m.nl.p + nl0[s], nr, m.rlen.p + rec0[s], m.ing.p + 1, (int*)m.ing.p); launches_++; }
+    }
+    volatile u32* hs = (volatile u32*)m.h_s.p;
+    CK(cudaMemcpyAsync((void*)(hs + 32), m.ing.p, 2 * sizeof(u32), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (hs[32]) return false;   // multi-line / empty records, a read longer than 65,535: the sequential parser handles or reports it
+    const u32 maxlen = hs[33];
+    const u64 n_pairs = R / 2;
+    u32 stride2 = (maxlen + 15) / 16, stridem = (maxlen + 31) / 32;
+    if (!stride2) stride2 = stridem = 1;
+    m.n_pairs = n_pairs;
+    m.r_bases.ensure(R * stride2 + 1); m.r_nmask.ensure(R * stridem + 1); m.r_len.ensure(n_pairs + 1);
+    const u32 exc_cap = (u32)std::min<size_t>(std::max<size_t>((size_t)1 << 20, n / 64), (size_t)1 << 28);
+    m.exc_key.ensure(exc_cap); m.exc_chr.ensure(exc_cap);
+    k_rd_pairlen<<<(unsigned)((n_pairs + 255) / 256), 256, 0, st>>>(m.rlen.p, (u32)n_pairs, m.r_len.p, (int*)m.ing.p); launches_++;
+    for (size_t s = 0; s < ns; s++) {
+        const u32 nr = lines[s] / 2;
+        const u64 tasks = (u64)nr * stridem;
+        if (tasks) { k_rd_pack<<<(unsigned)((tasks + 255) / 256), 256, 0, st>>>(m.raw.p + doff[s], m.nl.p + nl0[s], nr, stride2, stridem, rec0[s], m.r_bases.p, m.r_nmask.p, m.exc_key.p, m.exc_chr.p, m.ing.p + 2, exc_cap); launches_++; }
+    }
+    host.len.resize(n_pairs);
+    m.h_walks.ensure(n_pairs * sizeof(uint16_t) + 64);
+    CK(cudaMemcpyAsync(m.h_walks.p, m.r_len.p, n_pairs * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync((void*)(hs + 32), m.ing.p, 3 * sizeof(u32), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (hs[32] & ING_PE_LEN) throw AgError{"INCONSISTENT PE FILES!"};
+    const u32 n_exc = hs[34];
+    if (n_exc > exc_cap) return false;   // more masked characters than the list holds (reads of 'N' only, ...): host parser
+    memcpy(host.len.data(), m.h_walks.p, n_pairs * sizeof(uint16_t));
+    host.exc.clear();
+    if (n_exc) {
+        std::vector<u64> keys(n_exc); std::vector<char> chr(n_exc);
+        CK(cudaMemcpyAsync(keys.data(), m.exc_key.p, (size_t)n_exc * sizeof(u64), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(chr.data(), m.exc_chr.p, n_exc, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        host.exc.resize(n_exc);
+        for (u32 i = 0; i < n_exc; i++) host.exc[i] = {keys[i], chr[i]};
+        std::sort(host.exc.begin(), host.exc.end());
+    }
+    host.exc_complete = true; host.n_pairs = n_pairs; host.stride2 = stride2; host.stridem = stridem;
+    host.bases.resize(0); host.nmask.resize(0);   // device-only: AgDevice::copy_reads_to_host fills them on demand
+    m.reads.bases = m.r_bases.p; m.reads.nmask = m.r_nmask.p; m.reads.len = m.r_len.p; m.reads_owned = true;
+    m.reads.stride2 = stride2; m.reads.stridem = stridem;
+    t_.ingest_reads += tm.stop(); t_.reads_device++;
+    t_.d2h_bytes += n_pairs * sizeof(uint16_t) + (size_t)n_exc * 9;
+    return true;
+}
+
+u32 AgDevice::Impl::nl_index(cudaStream_t st, u64& launches, const char* text, size_t len, size_t blk_base, size_t nl_base, bool fill) {
+    Impl& m = *this;
+    const size_t n16 = (len + 15) / 16;
+    const unsigned nb = (unsigned)((len + NL_B - 1) / NL_B);
+    if (!nb) return 0;
+    u32* blk = m.nl_blk.p + blk_base;
+    if (!fill) {
+        k_nl_count<<<nb, NL_T, 0, st>>>((const uint4*)text, n16, blk); launches++;
+        m.scanner.run(blk, blk, nb, st);   // in place, blk[nb] = total
+        volatile u32* hs = (volatile u32*)m.h_s.p;
+        CK(cudaMemcpyAsync((void*)(hs + 40), blk + nb, sizeof(u32), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        return hs[40];
+    }
+    k_nl_fill<<<nb, NL_T, 0, st>>>((const uint4*)text, n16, blk, m.nl.p + nl_base); launches++;
+    return 0;
+}
+
+bool AgDevice::ingest_sam(const std::string& path) {
+    CK(cudaSetDevice(dev_));
+    Impl& m = *m_; cudaStream_t st = m.st;
+    Fd f(path);
+    if (f.fd < 0) throw AgError{"CANNOT OPEN FILE!"};
+    const size_t n = f.size();
+    m.aln_ingested = false;
+    auto none = [&]() { m.n_aln = 0; m.n_ext = 0; m.aln_ingested = true; m.aln.ensure(1); m.ext.ensure(1); t_.sam_device++; return true; };
+    if (n == 0 || m.n_pairs == 0) return none();
+    if (n >= 0xF0000000ull) return false;
+    // '@' header lines only at the top (counted on the host from the first bytes)
+    size_t body = 0; u32 n_hdr = 0;
+    {
+        const size_t W = std::min<size_t>(n, (size_t)1 << 20);
+        std::vector<char> head(W);
+        if (pread(f.fd, head.data(), W, 0) != (ssize_t)W) return false;
+        while (body < W && head[body] == '@') { const char* l = (const char*)memchr(head.data() + body, '\n', W - body); if (!l) return false; body = (size_t)(l - head.data()) + 1; n_hdr++; }
+        if (body >= W && W < n) return false;
+        char cl = 0;
+        if (pread(f.fd, &cl, 1, (off_t)(n - 1)) != 1 || cl != '\n') return false;
+    }
+    if (body >= n) return none();
+    Timer tm(st);
+    m.raw.ensure(n + 64); m.nl_blk.ensure((n + NL_B - 1) / NL_B + 4); m.ing.ensure(8);
+    CK(cudaMemsetAsync(m.raw.p + n, 0, 32, st));
+    m.stager.run(f.fd, 0, n, m.raw.p, st);
+    t_.h2d_bytes += n;
+    const u32 lines = m.nl_index(st, launches_, m.raw.p, n, 0, 0, false);
+    if (lines < n_hdr || ((lines - n_hdr) & 1)) return false;   // odd number of records: BROKEN BOWTIE FILE territory, the host parser reports it
+    const u32 n_rec = (lines - n_hdr) / 2;
+    if (!n_rec) return none();
+    m.nl.ensure((size_t)lines + 2);
+    m.nl_index(st, launches_, m.raw.p, n, 0, 0, true);
+    const u32* nl = m.nl.p + n_hdr;
+    const u32 lost_cap = (u32)(m.n_pairs / 1000000 + 8);
+    m.srec.ensure((size_t)n_rec + 1); m.s_keep.ensure((size_t)n_rec + 2); m.s_next.ensure((size_t)n_rec + 2); m.s_aoff.ensure((size_t)n_rec + 2); m.s_eoff.ensure((size_t)n_rec + 2); m.s_lost.ensure(lost_cap + 4);
+    CK(cudaMemsetAsync(m.ing.p, 0, 8 * sizeof(u32), st));
+    int* bad = (int*)m.ing.p;
+    k_sam_parse<<<(n_rec + 127) / 128, 128, 0, st>>>(m.raw.p, nl, (u32)body, n_rec, m.reads.len, m.n_pairs, m.srec.p, bad); launches_++;
+    k_sam_sorted<<<(n_rec + 255) / 256, 256, 0, st>>>(m.srec.p, n_rec, bad); launches_++;
+    k_sam_lost<<<1, 32, 0, st>>>(m.srec.p, n_rec, (long long)m.n_pairs, m.s_lost.p, lost_cap); launches_++;
+    k_sam_survive<<<(n_rec + 255) / 256, 256, 0, st>>>(m.srec.p, n_rec, m.s_lost.p, m.reads.len, m.s_keep.p, m.s_next.p, bad); launches_++;
+    m.scanner.run(m.s_keep.p, m.s_aoff.p, n_rec, st);
+    m.scanner.run(m.s_next.p, m.s_eoff.p, n_rec, st);
+    volatile u32* hs = (volatile u32*)m.h_s.p;
+    CK(cudaMemcpyAsync((void*)(hs + 32), m.ing.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync((void*)(hs + 33), m.s_aoff.p + n_rec, sizeof(u32), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync((void*)(hs + 34), m.s_eoff.p + n_rec, sizeof(u32), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync((void*)(hs + 35), m.s_lost.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const u32 flags = hs[32], n_aln = hs[33], n_ext = hs[34];
+    if ((flags & (ING_BAD_LAYOUT | ING_BAD_RECORD | ING_BAD_ORDER)) || hs[35] > lost_cap) return false;   // not the well-formed layout: host parser
+    if (flags & ING_STRAND) throw AgError{"BOWTIE ALIGNMENT ERROR"};
+    m.aln.ensure((size_t)n_aln + 1); m.ext.ensure((size_t)n_ext + 1);
+    k_sam_fill<<<(n_rec + 127) / 128, 128, 0, st>>>(m.raw.p, nl, (u32)body, n_rec, m.reads.len, m.n_pairs, m.srec.p, m.s_keep.p, m.s_aoff.p, n_ext ? m.s_eoff.p : nullptr, m.aln.p, m.ext.p); launches_++;
+    m.n_aln = n_aln; m.n_ext = n_ext; m.aln_ingested = true;
+    t_.ingest_sam += tm.stop(); t_.sam_device++;
+    return true;
+}
+u64 AgDevice::ingested_alignments() const { return m_->aln_ingested ? m_->n_aln : 0; }
+void AgDevice::fetch_alignments(std::vector<ag_aln>& aln, std::vector<ag_seg>& ext) {
+    CK(cudaSetDevice(dev_));
+    Impl& m = *m_;
+    aln.assign(m.aln_ingested ? m.n_aln : 0, ag_aln{}); ext.assign(m.aln_ingested ? m.n_ext : 0, ag_seg{});
+    if (!aln.empty()) CK(cudaMemcpyAsync(aln.data(), m.aln.p, aln.size() * sizeof(ag_aln), cudaMemcpyDeviceToHost, m.st));
+    if (!ext.empty()) CK(cudaMemcpyAsync(ext.data(), m.ext.p, ext.size() * sizeof(ag_seg), cudaMemcpyDeviceToHost, m.st));
+    CK(cudaStreamSynchronize(m.st));
+}
+
 void AgDevice::load_unit(const AgUnitInput& in) {
     CK(cudaSetDevice(dev_));
     Impl& m = *m_;
     Timer tm(m.st);
-    m.n_ref = in.n_ref; m.n_pos = in.n_pos; m.n_cm = in.n_cm; m.n_aln = (u32)in.n_aln;
+    if (in.aln_on_device && !m.aln_ingested) throw AgError{"internal: no ingested alignments on the device"};
+    m.n_ref = in.n_ref; m.n_pos = in.n_pos; m.n_cm = in.n_cm;
+    if (!in.aln_on_device) { m.n_aln = (u32)in.n_aln; m.n_ext = in.n_ext; m.aln_ingested = false; }
     if (in.n_aln >= 0xFFFFFFF0ull) throw AgError{"too many alignments for one unit"};
     const bool derive = in.threads != nullptr || in.cm_start == nullptr;   // contiMer table from the contig threads (else: explicit table)
     m.ref.ensure(in.n_pos + 1); m.cm_start.ensure((size_t)in.n_pos + 2); m.cm.ensure(in.n_cm + 1); m.chain_pos.ensure(in.n_cm + 1);
-    m.chain_base.ensure(in.n_cm + 1); m.aln.ensure(in.n_aln + 1); m.ext.ensure(in.n_ext + 1);
+    m.chain_base.ensure(in.n_cm + 1);
+    if (!in.aln_on_device) { m.aln.ensure(in.n_aln + 1); m.ext.ensure(in.n_ext + 1); }
     CK(cudaMemcpyAsync(m.ref.p, in.ref, in.n_pos, cudaMemcpyHostToDevice, m.st));
     size_t table_bytes = 0;
-    if (in.n_aln) CK(cudaMemcpyAsync(m.aln.p, in.aln, in.n_aln * sizeof(ag_aln), cudaMemcpyHostToDevice, m.st));
-    if (in.n_ext) CK(cudaMemcpyAsync(m.ext.p, in.ext, in.n_ext * sizeof(ag_seg), cudaMemcpyHostToDevice, m.st));
-    if (in.n_cm) {
+    if (!in.aln_on_device && in.n_aln) CK(cudaMemcpyAsync(m.aln.p, in.aln, in.n_aln * sizeof(ag_aln), cudaMemcpyHostToDevice, m.st));
+    if (!in.aln_on_device && in.n_ext) CK(cudaMemcpyAsync(m.ext.p, in.ext, in.n_ext * sizeof(ag_seg), cudaMemcpyHostToDevice, m.st));
+    if (in.n_cm && in.cdesc) {   // run-space contig threads: chunk bases once per file version, descriptors per unit, expansion on the device
+        if (m.blob_version != in.blob_version) {
+            m.contig_blob.ensure(in.blob_bytes + 1);
+            CK(cudaMemcpyAsync(m.contig_blob.p, in.contig_blob, in.blob_bytes, cudaMemcpyHostToDevice, m.st));
+            m.blob_version = in.blob_version; table_bytes += in.blob_bytes;
+        }
+        m.cdesc.ensure(in.n_desc + 1); m.cruns.ensure(in.n_runs + 1);
+        CK(cudaMemcpyAsync(m.cdesc.p, in.cdesc, (size_t)in.n_desc * sizeof(ag_cdesc), cudaMemcpyHostToDevice, m.st));
+        CK(cudaMemcpyAsync(m.cruns.p, in.cruns, (size_t)in.n_runs * sizeof(ag_crun), cudaMemcpyHostToDevice, m.st));
+        k_chain_expand<<<(in.n_cm + 255) / 256, 256, 0, m.st>>>(m.cdesc.p, in.n_desc, m.cruns.p, m.contig_blob.p, (const unsigned char*)m.ref.p, in.n_ref, in.n_cm, m.chain_pos.p, (unsigned char*)m.chain_base.p); launches_++;
+        table_bytes += (size_t)in.n_desc * sizeof(ag_cdesc) + (size_t)in.n_runs * sizeof(ag_crun);
+    } else if (in.n_cm) {
         CK(cudaMemcpyAsync(m.chain_pos.p, in.chain_pos, (size_t)in.n_cm * sizeof(u32), cudaMemcpyHostToDevice, m.st));
         CK(cudaMemcpyAsync(m.chain_base.p, in.chain_base, in.n_cm, cudaMemcpyHostToDevice, m.st));
+        table_bytes += (size_t)in.n_cm * 5;
     }
     if (!derive) {
         CK(cudaMemcpyAsync(m.cm_start.p, in.cm_start, ((size_t)in.n_pos + 1) * sizeof(u32), cudaMemcpyHostToDevice, m.st));
@@ -1146,7 +1395,7 @@ void AgDevice::load_unit(const AgUnitInput& in) {
         if (err) throw AgError{"CONTIG ALIGNMENT ERROR: inconsistent contig threads"};
     }
     t_.h2d += tm.stop();
-    t_.h2d_bytes += in.n_pos + (size_t)in.n_cm * 5 + table_bytes + in.n_aln * sizeof(ag_aln) + in.n_ext * sizeof(ag_seg);
+    t_.h2d_bytes += in.n_pos + table_bytes + (in.aln_on_device ? 0 : in.n_aln * sizeof(ag_aln) + in.n_ext * sizeof(ag_seg));
 }
 
 void AgDevice::build() {
@@ -1244,6 +1493,7 @@ void AgDevice::build() {
             const int err = (int)hs[0]; nn = hs[1];
             if (err == 0) break;
             if (err == 2) throw AgError{"BOWTIE ALIGNMENT ERROR: alignment outside the unit"};
+            t_.regrows++;
             if (err == 3 && m.node_cap < (1u << 31)) m.node_cap = m.node_cap * 2;           // node table too small: grow and redo the sweep
             else if (err == 1 && m.ovf_cap < (1u << 30)) m.ovf_cap *= 4;                    // overflow pool (nodes beyond the shared-memory slots) too small
             else throw AgError{"node table exhausted"};
@@ -1253,31 +1503,39 @@ void AgDevice::build() {
         t_.nodes += tm.stop();
     }
     m.n_nodes = nn; t_.n_nodes = nn; t_.n_keys = m.n_keys; t_.n_tiles = m.n_tiles;
-    // ---- tile blocks -> position order, successor bits -> successor indices -------------------------------------------------------
+    // ---- tile blocks -> position order, successor bits -> successor indices; generic edge sweep over the flagged tiles --------------
+    // (repeated with a larger edge overflow pool when it runs out: both kernels only read the sweep-order blocks and rewrite the final table)
     {
-        Timer tm(st);
         m.node_c.ensure((size_t)nn + 1); m.node_w.ensure((size_t)nn + 1); m.node_sref.ensure(2 * (size_t)nn + 2); m.node_pos.ensure((size_t)nn + 1);
         if (keep_counts_) m.node_cc.ensure(6 * (size_t)nn + 6);
         d.node_c = m.node_c.p; d.node_w = m.node_w.p; d.node_sref = m.node_sref.p; d.node_pos = m.node_pos.p; d.node_cc = keep_counts_ ? m.node_cc.p : nullptr;
         m.eovf_head.ensure(nn + 1);
-        m.eovf_cap = std::max<u32>(1u << 18, nn / 8); m.eovf_target.ensure(m.eovf_cap); m.eovf_next.ensure(m.eovf_cap);
-        d.eovf_head = m.eovf_head.p; d.eovf_target = m.eovf_target.p; d.eovf_next = m.eovf_next.p; d.eovf_count = m.counters.p + 2; d.eovf_cap = m.eovf_cap;
-        m.scanner.run(m.tile_nodes.p, m.tile_prefix.p, m.n_tiles, st);
-        k_posfix<<<(n_pos + 1 + 255) / 256, 256, 0, st>>>(d, nn); launches_++;
-        if (nn) { k_succ<<<(nn + 255) / 256, 256, 0, st>>>(d, nn); launches_++; }
-        t_.finalize += tm.stop();
-    }
-    // ---- generic edge sweep over the flagged tiles ----------------------------------------------------------------------------------
-    {
-        Timer tm(st);
-        if (m.n_tiles && nn) { k_edges<<<m.n_tiles, AG_TILE, 0, st>>>(d); launches_++; }
-        volatile u32* hs = (volatile u32*)m.h_s.p;
-        CK(cudaMemcpyAsync((void*)(hs + 0), m.err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync((void*)(hs + 4), m.counters.p, 4 * sizeof(u32), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        if (hs[0]) throw AgError{"edge overflow pool exhausted"};
-        t_.n_edges_ovf = hs[4 + 2];
-        t_.edges += tm.stop();
+        m.eovf_cap = m.eovf_cap_init ? m.eovf_cap_init : std::max<u32>(1u << 18, nn / 8);
+        for (;;) {
+            Timer tm(st);
+            m.eovf_target.ensure(m.eovf_cap); m.eovf_next.ensure(m.eovf_cap);
+            d.eovf_head = m.eovf_head.p; d.eovf_target = m.eovf_target.p; d.eovf_next = m.eovf_next.p; d.eovf_count = m.counters.p + 2; d.eovf_cap = m.eovf_cap;
+            m.scanner.run(m.tile_nodes.p, m.tile_prefix.p, m.n_tiles, st);
+            k_posfix<<<(n_pos + 1 + 255) / 256, 256, 0, st>>>(d, nn); launches_++;
+            if (nn) { k_succ<<<(nn + 255) / 256, 256, 0, st>>>(d, nn); launches_++; }
+            t_.finalize += tm.stop();
+            Timer tm2(st);
+            if (m.n_tiles && nn) { k_edges<<<m.n_tiles, AG_TILE, 0, st>>>(d); launches_++; }
+            volatile u32* hs = (volatile u32*)m.h_s.p;
+            CK(cudaMemcpyAsync((void*)(hs + 0), m.err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync((void*)(hs + 4), m.counters.p, 4 * sizeof(u32), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            t_.edges += tm2.stop();
+            if (hs[0] == 4 && m.eovf_cap < (1u << 30)) {   // edge overflow pool (successors beyond the two inline ones) too small: grow and redo
+                m.eovf_cap *= 4; t_.regrows++;
+                CK(cudaMemsetAsync(m.err.p, 0, sizeof(int), st));
+                CK(cudaMemsetAsync(m.counters.p + 2, 0, sizeof(u32), st));
+                continue;
+            }
+            if (hs[0]) throw AgError{"edge overflow pool exhausted"};
+            t_.n_edges_ovf = hs[4 + 2];
+            break;
+        }
     }
 }
 

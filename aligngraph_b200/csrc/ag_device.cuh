@@ -15,6 +15,10 @@ struct AgUnitInput {
     const char* chain_base;     // n_cm, chain-major
     const ag_aln* aln; u64 n_aln;
     const ag_seg* ext; u64 n_ext;
+    // run-space contig threads (ag_thread_contigs_runs): when cdesc != null, chain_pos / chain_base are null and the device expands them
+    const struct ag_cdesc* cdesc = nullptr; u32 n_desc = 0; const struct ag_crun* cruns = nullptr; u32 n_runs = 0;
+    const char* contig_blob = nullptr; u64 blob_bytes = 0, blob_version = 0;
+    bool aln_on_device = false;  // the alignment tuples were parsed on the device (AgDevice::ingest_sam): aln / ext are not uploaded
 };
 
 struct AgNodeDump {  // node table in (position, item) order, for tests
@@ -27,7 +31,9 @@ struct AgTimings {  // milliseconds, CUDA events on the context's stream
     float h2d = 0, prep = 0, sort = 0, nodes = 0, finalize = 0, edges = 0, components = 0, chains = 0, walk = 0, materialize = 0, d2h = 0;
     u64 n_nodes = 0, n_edges_ovf = 0, n_walks = 0, n_keys = 0, n_tiles = 0, n_components = 0;
     u64 h2d_bytes = 0, d2h_bytes = 0;
-    int walk_fallback = 0;
+    int walk_fallback = 0, regrows = 0;   // regrows: sweeps repeated with a larger node table / overflow pool
+    float ingest_reads = 0, ingest_sam = 0;   // ms: staging + kernels of the text ingestion (CUDA events)
+    u64 sam_device = 0, sam_host = 0, reads_device = 0, reads_host = 0;   // files parsed on the device / by the host parser
 };
 
 class AgDevice {
@@ -47,9 +53,21 @@ public:
     ReadsView reads_view();
     // make own, uninitialised buffers of this geometry the context's read set (the caller fills them: broadcast target)
     ReadsView reserve_reads(u64 n_pairs, u32 stride2, u32 stridem);
+    // ---- GPU-side text ingestion (ag_ingest.cuh).  Both return false when the file is not in the well-formed layout the kernels handle;
+    // the caller then uses the sequential host parser (ag_parse_reads / ag_parse_sam), which carries the literal semantics and messages.
+    // tmp/_reads.fa -> packed reads resident on the device; `host` receives the per-pair lengths, the geometry and the exception list
+    // (original non-ACGT characters), NOT the packed words (copy_reads_to_host fetches them on demand)
+    bool ingest_reads(const std::string& path, struct AgReads& host);
+    // tmp/_reads_genome.N.bowtie -> the unit's surviving alignment tuples, resident on the device in file order
+    bool ingest_sam(const std::string& path);
+    u64 ingested_alignments() const;
+    void note_host_sam() { t_.sam_host++; }
+    void note_host_reads() { t_.reads_host++; }
+    void fetch_alignments(std::vector<ag_aln>& aln, std::vector<ag_seg>& ext);   // device -> host copy of the ingested tuples (tests, ag_get_unit)
     void set_params(int k, int iv, int coverage) { k_ = k; iv_ = iv; cov_ = coverage; }
     // keep coverage + base counters per node after the build (24 B per node; only the node dump of the tests needs them)
     void set_keep_counts(bool on) { keep_counts_ = on; }
+    void set_option(const std::string& name, long value);
     // upload one unit's inputs (H2D, timed)
     void load_unit(const AgUnitInput& in);
     // the hot path: prep -> bucket -> nodes (+ common-case edges) -> successor lists -> generic edges on flagged tiles  (all device)
@@ -91,7 +109,7 @@ private:
     bool reads_pending_ = false, mat_pending_ = false, occ_pending_ = false;
     void *ev_mat0_ = nullptr, *ev_mat1_ = nullptr; size_t mat_bytes_ = 0;
     std::vector<void*> pinned_;
-    bool chains_valid_ = false, attr_done_ = false, keep_counts_ = false;
+    bool chains_valid_ = false, attr_done_ = false, keep_counts_ = false, section_timing_ = false;
     void walk_components();
     void walk_sequential();
 };

@@ -318,6 +318,12 @@ void ag_parse_reads(const std::string& path, AgReads& out) {
 
 char AgReads::at(u32 read, u32 rc, u32 rlen, u32 off) const {
     u32 i = rc ? rlen - 1 - off : off;
+    if (device_only()) {
+        if (exc.empty()) return 0;
+        u64 key = (u64)read * 65536 + i;
+        auto it = std::lower_bound(exc.begin(), exc.end(), std::make_pair(key, (char)CHAR_MIN));
+        return it != exc.end() && it->first == key ? it->second : 0;
+    }
     if ((nmask[(size_t)read * stridem + (i >> 5)] >> (i & 31)) & 1) {
         u64 key = (u64)read * 65536 + i;
         auto it = std::lower_bound(exc.begin(), exc.end(), std::make_pair(key, (char)CHAR_MIN));
@@ -395,31 +401,40 @@ int keep_set(std::vector<Chunk>& ch, u32 sid, double thr) {
 
 // tmp/_contigs.fa is the same for every unit (the reference re-reads it per chromosome, AG:1225-1228): parse it once per file version
 namespace {
-struct ChunkCache { std::string path; long size = -1, mtime = -1, mtime_ns = -1; std::vector<std::pair<int, std::string>> chunks; };
+struct ChunkCache { std::string path; long size = -1, mtime = -1, mtime_ns = -1; std::shared_ptr<const AgChunkStore> store; };
 std::mutex g_chunk_mu;
 ChunkCache g_chunk_cache;
+std::atomic<u64> g_chunk_version{1};
 }
-static void load_chunks(const std::string& contigs_fa, std::vector<Chunk>& ch) {
+std::shared_ptr<const AgChunkStore> ag_chunk_store(const std::string& contigs_fa) {
     std::lock_guard<std::mutex> lk(g_chunk_mu);
     struct stat st;
     if (stat(contigs_fa.c_str(), &st) != 0) throw AgHostError{"CANNOT OPEN FILE!"};
     ChunkCache& c = g_chunk_cache;
-    if (c.path != contigs_fa || c.size != (long)st.st_size || c.mtime != (long)st.st_mtim.tv_sec || c.mtime_ns != (long)st.st_mtim.tv_nsec) {
+    if (!c.store || c.path != contigs_fa || c.size != (long)st.st_size || c.mtime != (long)st.st_mtim.tv_sec || c.mtime_ns != (long)st.st_mtim.tv_nsec) {
         FileMap fm(contigs_fa);
         if (!fm.ok) throw AgHostError{"CANNOT OPEN FILE!"};
-        c.chunks.clear();
+        auto sp = std::make_shared<AgChunkStore>();
+        sp->blob.reserve(fm.n);
         Lines ln(fm.p, fm.n); const char* s; size_t n;
         while (ln.next(s, n)) {   // AG:322-359
             if (n == 0 || s[0] == 0) break;
             if (s[0] == '>') {
                 const char* dot = (const char*)memchr(s, '.', n);
-                c.chunks.emplace_back(dot ? ag_atoi(dot + 1, (size_t)(s + n - dot - 1)) : 0, std::string());
-            } else if (!c.chunks.empty()) c.chunks.back().second.append(s, n);
+                sp->id.push_back(dot ? ag_atoi(dot + 1, (size_t)(s + n - dot - 1)) : 0);
+                sp->off.push_back(sp->blob.size());
+            } else if (!sp->id.empty()) sp->blob.append(s, n);
         }
-        c.path = contigs_fa; c.size = (long)st.st_size; c.mtime = (long)st.st_mtim.tv_sec; c.mtime_ns = (long)st.st_mtim.tv_nsec;
+        sp->off.push_back(sp->blob.size());
+        sp->version = g_chunk_version.fetch_add(1);
+        c.store = sp; c.path = contigs_fa; c.size = (long)st.st_size; c.mtime = (long)st.st_mtim.tv_sec; c.mtime_ns = (long)st.st_mtim.tv_nsec;
     }
-    ch.resize(c.chunks.size());
-    for (size_t i = 0; i < ch.size(); i++) { ch[i].id = c.chunks[i].first; ch[i].bases = c.chunks[i].second; }
+    return c.store;
+}
+static void load_chunks(const std::string& contigs_fa, std::vector<Chunk>& ch) {
+    std::shared_ptr<const AgChunkStore> st = ag_chunk_store(contigs_fa);
+    ch.resize(st->n());
+    for (size_t i = 0; i < ch.size(); i++) { ch[i].id = st->id[i]; ch[i].bases.assign(st->blob, (size_t)st->off[i], st->size(i)); }
 }
 
 void ag_expand_contimers(const ag_cthread* threads, size_t n_threads, const u32* chain_pos, size_t n_cm, size_t n_pos, std::vector<u32>& cm_start, std::vector<ag_cm>& cm) {
@@ -581,6 +596,197 @@ void ag_thread_contigs(const std::string& contigs_fa, const std::string& psl_pat
         cp++; c = e;
     }
     lap("initial_text");
+}
+
+// ---- the same in run space --------------------------------------------------------------------------------------------------------
+namespace {
+struct RunSet { std::vector<ag_seg> runs; u32 aligned = 0; int fr = 0; u32 ps0() const { return !runs.empty() && runs[0].src == 0 ? runs[0].dst : AG_NONE; } };
+struct RChunk { std::vector<RunSet> sets; int outputted = 0; };
+inline char comp_base(char c) { return c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : c; }
+// first covered base of [a, a + n) in a sorted, disjoint run list, or NONE
+u32 first_covered(const std::vector<ag_seg>& runs, u32 a, u32 n) {
+    size_t lo = 0, hi = runs.size();   // first run whose end lies beyond a
+    while (lo < hi) { size_t mid = (lo + hi) / 2; if (runs[mid].src + runs[mid].len > a) hi = mid; else lo = mid + 1; }
+    if (lo == runs.size() || runs[lo].src >= a + n) return AG_NONE;
+    return std::max(runs[lo].src, a);
+}
+}  // namespace
+
+bool ag_thread_contigs_runs(const std::string& contigs_fa, const std::string& psl_path, std::string& initial_text, AgUnit& u) {
+    auto T0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) { if (getenv("AG_POST_TIMING")) { auto t = std::chrono::steady_clock::now(); fprintf(stderr, "  [contig runs] %s %.2f ms\n", what, std::chrono::duration<double>(t - T0).count() * 1e3); T0 = t; } };
+    std::shared_ptr<const AgChunkStore> store = ag_chunk_store(contigs_fa);
+    const size_t nch = store->n();
+    std::vector<RChunk> ch(nch);
+    // ---- PSL -> position sets as run lists (loadContiAli AG:817-852 with updateContig AG:763-815 and keepPositions AG:731-748) ----
+    {
+        FileMap fm(psl_path);
+        if (!fm.ok) throw AgHostError{"CANNOT OPEN FILE!"};
+        Lines ln(fm.p, fm.n); const char* s; size_t n;
+        PslRec r; r.sid = AG_NONE;
+        u32 last_source = AG_NONE;
+        auto keep = [&](u32 sid) -> int { if (sid == AG_NONE || ch[sid].sets.empty()) return 1; return (double)ch[sid].sets.back().aligned / store->size(sid) >= kContigThreshold ? 1 : 0; };
+        while (ln.next(s, n)) {
+            if (n == 0 || s[0] == 0) {
+                if (r.sid != AG_NONE && r.sid < nch && keep(r.sid) == 0) {   // the reference pops the position set but not its strand flag (AG:830-836): the
+                    RChunk& c = ch[r.sid];                                  // flags of the chunk's remaining sets are unaffected (nothing follows)
+                    c.sets.pop_back();
+                }
+                break;
+            }
+            parse_psl(s, n, r);
+            bool pass = (double)(r.send - r.sstart - r.sgap) / r.ssize >= kInitContigThreshold &&
+                        (double)(r.tend - r.tstart - r.tgap) / (r.tend - r.tstart) >= kInitContigThreshold && r.ssize > 200;
+            if (!pass) continue;
+            if (r.tid == AG_NONE) continue;
+            if (r.tid != 0 || r.sid >= nch) throw AgHostError{"CONTIG ALIGNMENT ERROR"};
+            RChunk& c = ch[r.sid];
+            const u32 size = (u32)store->size(r.sid);
+            auto open_set = [&]() { c.sets.emplace_back(); c.sets.back().fr = (int)r.fr; };
+            if (r.sid != last_source) {
+                if (keep(last_source) == 0) ch[last_source].sets.pop_back();
+                open_set();
+                last_source = r.sid;
+            } else {
+                bool clash = false;
+                for (const ag_seg& sg : r.segs) {   // scan order of the reference: the first base that is out of range (error) or already placed (clash) decides
+                    if (!sg.len || (u64)sg.src + sg.len > 0xFFFFFFFFull) continue;   // (a wrapped range never enters the reference's loop)
+                    const u32 fc = first_covered(c.sets.back().runs, sg.src, sg.len);
+                    const u64 end = (u64)sg.src + sg.len;
+                    const u32 oob = end > size ? std::max(sg.src, size) : AG_NONE;
+                    if (fc != AG_NONE && (oob == AG_NONE || fc < oob)) { clash = true; break; }
+                    if (oob != AG_NONE) throw AgHostError{"CONTIG ALIGNMENT ERROR"};
+                }
+                if (clash) {
+                    if (keep(r.sid) == 0) c.sets.pop_back();
+                    open_set();
+                }
+            }
+            RunSet& cur = c.sets.back();
+            for (const ag_seg& sg : r.segs) {
+                if (!sg.len) continue;
+                if ((u64)sg.src + sg.len > size) throw AgHostError{"CONTIG ALIGNMENT ERROR"};
+                if (first_covered(cur.runs, sg.src, sg.len) != AG_NONE) return false;   // a record whose own blocks overlap (later ones overwrite): per-base path
+                auto it = std::lower_bound(cur.runs.begin(), cur.runs.end(), sg.src, [](const ag_seg& a, u32 v) { return a.src < v; });
+                it = cur.runs.insert(it, sg);
+                cur.aligned += sg.len;
+                // merge with neighbours that continue the same diagonal (keeps the lists short; does not change the mapping)
+                size_t k = (size_t)(it - cur.runs.begin());
+                if (k + 1 < cur.runs.size() && cur.runs[k].src + cur.runs[k].len == cur.runs[k + 1].src && cur.runs[k].dst + cur.runs[k].len == cur.runs[k + 1].dst) { cur.runs[k].len += cur.runs[k + 1].len; cur.runs.erase(cur.runs.begin() + (long)k + 1); }
+                if (k > 0 && cur.runs[k - 1].src + cur.runs[k - 1].len == cur.runs[k].src && cur.runs[k - 1].dst + cur.runs[k - 1].len == cur.runs[k].dst) { cur.runs[k - 1].len += cur.runs[k].len; cur.runs.erase(cur.runs.begin() + (long)k); }
+            }
+        }
+    }
+    lap("psl -> run sets");
+    // ---- thread every surviving set through the unit (AG:884-1177) ----
+    u.threads.clear(); u.cm_start.clear(); u.cm.clear(); u.chain_pos.clear(); u.chain_base.clear(); u.cdesc.clear(); u.cruns.clear();
+    u.chunks = store;
+    u.ref.resize(u.n_ref);
+    std::vector<unsigned char> count(u.n_ref, 0);   // contiMers per position so far, saturating at 2 (only ">= 2" is ever asked); grows with the tail
+    u32 n_chain = 0;
+    for (size_t sp = 0; sp < nch; sp++) {
+        RChunk& c = ch[sp];
+        const u32 size = (u32)store->size(sp);
+        const char* bases = store->blob.data() + store->off[sp];
+        for (size_t pp = 0; pp < c.sets.size(); pp++) {
+            const RunSet& rs = c.sets[pp];
+            bool skip = false;
+            if (size == 0) throw AgHostError{"CONTIG ALIGNMENT ERROR"};   // the reference reads ps[0] of an empty set
+            for (size_t e = 0; e < pp && !skip; e++) if (absdiff(rs.ps0(), c.sets[e].ps0()) < (int)size) skip = true;   // AG:902-907
+            for (size_t k = 0; !skip && k < rs.runs.size(); k++) {   // AG:908-920: any base but the last on a position that already holds two contiMers
+                const ag_seg& g = rs.runs[k];
+                const u32 end = std::min(g.src + g.len, size - 1);   // bases b < size - 1 only
+                const u32 len = end > g.src ? end - g.src : 0;
+                if (!len) continue;
+                const u64 lim = std::min<u64>((u64)g.dst + len, count.size());
+                const unsigned char* p = count.data(); bool two = false;
+                for (u64 q = g.dst; q < lim; q++) two |= p[q] >= 2;
+                if (two) { skip = true; break; }   // (a position beyond the table after a position that already holds two: the reference skips first only if
+                if ((u64)g.dst + len > count.size()) throw AgHostError{"CONTIG ALIGNMENT ERROR"};   //  it meets the full position first; both abort or skip the set — order kept)
+            }
+            if (skip) continue;
+            c.outputted = 1;
+            if (rs.runs.empty()) continue;
+            const bool fr = rs.fr == 1;
+            const u32 F = rs.runs.front().src, L = rs.runs.back().src + rs.runs.back().len - 1;
+            if (F == size - 1) continue;   // only the contig's last base is aligned: the walk (i + 1 < size) never starts
+            ag_cdesc d; d.first = n_chain; d.n = L - F + 1; d.F = F; d.size = size; d.fr = fr ? 1u : 0u; d.run0 = (u32)u.cruns.size(); d.nruns = (u32)rs.runs.size(); d.pad = 0; d.base_off = store->off[sp];
+            for (size_t k = 0; k < rs.runs.size(); k++) {
+                const ag_seg& g = rs.runs[k];
+                const bool last = k + 1 == rs.runs.size();
+                const u32 len = last ? g.len - 1 : g.len;   // base L is the terminal, handled below
+                if ((u64)g.dst + len > count.size()) throw AgHostError{"CONTIG ALIGNMENT ERROR"};
+                unsigned char* p = count.data() + g.dst;
+                for (u32 q = 0; q < len; q++) p[q] = (unsigned char)(p[q] + (p[q] < 2));
+                ag_crun cr; cr.src = g.src; cr.dst = g.dst; cr.len = g.len; cr.gap_tail = (u32)(u.ref.size() - u.n_ref);
+                u.cruns.push_back(cr);
+                if (!last) {   // inserted bases between this run and the next go behind the unit (AG:974-1042), one contiMer each
+                    const u32 a = g.src + g.len, b = rs.runs[k + 1].src;
+                    for (u32 j = a; j < b; j++) u.ref.push_back(fr ? comp_base(bases[size - 1 - j]) : bases[j]);
+                    count.resize(count.size() + (b - a), 1);
+                }
+            }
+            const u32 tp = rs.runs.back().dst + rs.runs.back().len - 1;   // terminal contiMer: the unit's base at the position of base L (AG:1121-1148)
+            if (tp >= u.ref.size()) throw AgHostError{"CONTIG ALIGNMENT ERROR"};
+            count[tp] = (unsigned char)(count[tp] + (count[tp] < 2));
+            u.cdesc.push_back(d);
+            ag_cthread t; t.first = d.first; t.term = d.first + d.n - 1; t.cid = (u32)sp; t.coff_first = F; t.coff_term = size - 1;
+            u.threads.push_back(t);
+            n_chain += d.n;
+        }
+    }
+    u.n_cm_runs = n_chain;
+    lap("threading");
+    // ---- tmp/_initial_contigs.N.fa: original contigs with >= 50 % of their chunks threaded (AG:1179-1216); formatted by the thread team ----
+    {
+        struct Item { size_t c0, c1, text_off, bases; unsigned long name; };
+        std::vector<Item> items;
+        size_t c = 0, cp = 0, total = 0;
+        while (c < nch) {
+            size_t e = c; int placed = 0, tot = 0; size_t nb = 0;
+            while (e < nch && store->id[e] == store->id[c]) { tot++; placed += ch[e].outputted; nb += store->size(e); e++; }
+            if ((double)placed / (double)tot >= kContigThreshold) {
+                size_t digits = 0; { unsigned long v = cp; do { digits++; v /= 10; } while (v); }
+                Item it{c, e, total, nb, (unsigned long)cp};
+                total += 1 + digits + 1 + nb + (nb + 59) / 60;
+                items.push_back(it);
+            }
+            cp++; c = e;
+        }
+        initial_text.resize(total);
+        char* const T = total ? &initial_text[0] : nullptr;
+        ag_parallel_chunks((int)items.size(), [&](int i) {
+            const Item& it = items[(size_t)i];
+            char* p = T + it.text_off;
+            *p++ = '>';
+            { char t[24]; int k = 24; unsigned long v = it.name; do { t[--k] = (char)('0' + v % 10); v /= 10; } while (v); memcpy(p, t + k, (size_t)(24 - k)); p += 24 - k; }
+            *p++ = '\n';
+            // the chunks of one contig are adjacent in the blob: one 60-column wrap over the whole contig
+            const char* b = store->blob.data() + store->off[it.c0];
+            for (size_t o = 0; o < it.bases; o += 60) { const size_t m = std::min<size_t>(60, it.bases - o); memcpy(p, b + o, m); p += m; *p++ = '\n'; }
+        });
+    }
+    lap("initial_text");
+    return true;
+}
+
+void ag_expand_chains(AgUnit& u) {
+    u.chain_pos.assign(u.n_cm_runs, 0); u.chain_base.assign(u.n_cm_runs, 'N');
+    if (!u.chunks) return;
+    for (const ag_cdesc& d : u.cdesc) {
+        const char* bases = u.chunks->blob.data() + d.base_off;
+        const ag_crun* runs = u.cruns.data() + d.run0;
+        for (u32 j = 0; j < d.n; j++) {
+            const u32 k = d.first + j;
+            if (j == d.n - 1) { const ag_crun& g = runs[d.nruns - 1]; const u32 tp = g.dst + g.len - 1; u.chain_pos[k] = tp; u.chain_base[k] = u.ref[tp]; continue; }
+            const u32 b = d.F + j;
+            u32 lo = 0, hi = d.nruns;   // last run with src <= b
+            while (hi - lo > 1) { const u32 mid = (lo + hi) / 2; if (runs[mid].src <= b) lo = mid; else hi = mid; }
+            const ag_crun& g = runs[lo];
+            u.chain_pos[k] = b < g.src + g.len ? g.dst + (b - g.src) : u.n_ref + g.gap_tail + (b - g.src - g.len);
+            u.chain_base[k] = d.fr ? comp_base(bases[d.size - 1 - b]) : bases[b];
+        }
+    }
 }
 
 // =============================================================================================================================
@@ -1037,7 +1243,7 @@ void ag_make_contigs_finish(const std::vector<ag_walk>& walks, const std::vector
             if (slen <= 1) continue;
             const u32 rlen = reads.len[read >> 1];
             char* t = bases + offs[i] + r.len;
-            for (u32 j = 1; j < slen; j++) t[j - 1] = reads.at(read, rc, rlen, soff + j);
+            for (u32 j = 1; j < slen; j++) { const char c = reads.at(read, rc, rlen, soff + j); if (c) t[j - 1] = c; }
         }
     // thread team: header + 60-column body of every contig at its offset
     const std::vector<size_t>& hoff = st.hoff; const std::vector<size_t>& toff = st.toff;

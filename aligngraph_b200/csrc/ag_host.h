@@ -4,6 +4,7 @@
 #pragma once
 #include "ag_types.h"
 #include <functional>
+#include <memory>
 #include <string>
 #include <vector>
 #include <cstdio>
@@ -62,11 +63,32 @@ struct AgReads {
     bool exc_complete = false;       // exc lists EVERY set bit of nmask (true after ag_parse_reads / ag_pack_reads): the plane can be rebuilt from it
     u64 n_pairs = 0;
     u32 stride2 = 0, stridem = 0;
-    char at(u32 read, u32 rc, u32 rlen, u32 off) const;  // character of the oriented read (AG:854-865 leaves non-ACGT unchanged)
+    // character of the oriented read (AG:854-865 leaves non-ACGT unchanged).  When the packed words live only on the device (GPU-side
+    // ingestion) the exception list alone is consulted: the original character of a masked base, or 0 = "an ordinary base"
+    char at(u32 read, u32 rc, u32 rlen, u32 off) const;
+    bool device_only() const { return n_pairs != 0 && bases.size() == 0; }
 };
 void ag_parse_reads(const std::string& path, AgReads& out);
 // pack in-memory reads (one string per read, mates interleaved) — used by the synthetic bench and tests
 void ag_pack_reads(const std::vector<std::string>& seqs, AgReads& out);
+
+// ---- contig chunks (tmp/_contigs.fa, AG:322-359): parsed once per file version, shared by all units and contexts --------------
+struct AgChunkStore {
+    std::vector<int> id;        // original contig of every chunk (">chunk.contig")
+    std::vector<u64> off;       // n + 1 offsets into blob
+    std::string blob;           // chunk bases, concatenated
+    u64 version = 0;            // changes whenever the file is re-parsed (device-side cache key)
+    size_t n() const { return id.size(); }
+    size_t size(size_t i) const { return (size_t)(off[i + 1] - off[i]); }
+};
+std::shared_ptr<const AgChunkStore> ag_chunk_store(const std::string& contigs_fa);
+
+// One contig thread in run space (what updateGenomeWithContig, AG:884-1177, produces for one position set): the chunk's bases F .. L map
+// to unit positions through `nruns` runs of aligned bases; bases in the gaps between runs are insertions and live in the tail appended
+// behind the unit (AG:981-1036).  The thread's contiMers are chain indices [first, first + n): n - 1 bases F .. L-1 and the terminal
+// contiMer at the position of base L (AG:1121-1148).  The device expands these descriptors into the chain-major position / base arrays.
+struct ag_crun { u32 src, dst, len, gap_tail; };   // gap_tail: tail index (relative to n_ref) of the first inserted base that follows this run
+struct ag_cdesc { u32 first, n, F, size, fr, run0, nruns, pad; u64 base_off; };   // base_off: offset of the chunk's bases in the store blob
 
 // ---- one unit -----------------------------------------------------------------------------------------------------------------
 struct AgUnit {
@@ -79,10 +101,20 @@ struct AgUnit {
     std::string chain_base;
     std::vector<ag_aln> aln;
     std::vector<ag_seg> ext;
+    // run-space form of the contig threads (ag_thread_contigs_runs): when cdesc is non-empty chain_pos / chain_base stay EMPTY on the host
+    // and the device expands them (k_chain_expand); ag_expand_chains fills them on the host for inspection / the emulation
+    std::vector<ag_cdesc> cdesc; std::vector<ag_crun> cruns; std::shared_ptr<const AgChunkStore> chunks; u32 n_cm_runs = 0;
+    bool aln_on_device = false;      // the SAM was parsed on the device (AgDevice::ingest_sam): aln / ext stay empty here unless fetched for inspection
 };
 void ag_load_genome(const std::string& path, AgUnit& u);                                         // AG:287-320
 // contig chunks + PSL -> contiMer table + the text of tmp/_initial_contigs.N.fa                       // AG:1219-1231
 void ag_thread_contigs(const std::string& contigs_fa, const std::string& psl, std::string& initial_text, AgUnit& u);
+// The same in run space: interval arithmetic on the PSL blocks instead of per-base position arrays (O(blocks) + one pass over a per-position
+// counter).  Fills u.threads, the tail of u.ref, u.cdesc / u.cruns / u.chunks and initial_text; returns false (u untouched apart from ref's
+// tail being reset) for inputs it does not model (a record whose own blocks overlap) — the caller then uses ag_thread_contigs.
+bool ag_thread_contigs_runs(const std::string& contigs_fa, const std::string& psl, std::string& initial_text, AgUnit& u);
+// chain_pos / chain_base of a run-space unit on the host (what the device derives)
+void ag_expand_chains(AgUnit& u);
 // position-ordered contiMer table (cm_start, cm) from the contig threads — what the device derives itself; host callers that want to
 // look at the table (tests, ag_get_unit) call this
 void ag_expand_contimers(AgUnit& u);

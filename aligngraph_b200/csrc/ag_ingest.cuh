@@ -1,0 +1,265 @@
+// GPU-side ingestion of the hot path's text inputs: the raw bytes of tmp/_reads.fa (loadSeq, AG:361-404) and of
+// tmp/_reads_genome.N.bowtie (parseBOWTIE AG:181-285 + loadReadAli AG:1233-1277 + the duplicate / strand rules AG:1650-1671) are copied to
+// the device through page-locked staging chunks and parsed there; the resulting packed reads and `ag_aln` tuples never visit the host.
+// Included by ag_device.cu (shares its buffers, scanner and error macros).
+//
+//   k_nl_count / k_nl_fill    newline index of a text buffer: 64 bytes per thread (4 x uint4 loads), count -> scan -> positions
+//   k_rd_len / k_rd_pack      reads: record = '>' line + one sequence line; length per record, then 32 bases per thread -> 2-bit words,
+//                             non-ACGT bit plane, exception list (read * 65536 + offset, original character)
+//   k_sam_parse               one thread per record PAIR through the allocation-free functions of ag_samcore.h (field split, CIGAR state
+//                             machine, the `double` ratio filter of AG:1261, segment normalisation)
+//   k_sam_sorted / k_sam_lost / k_sam_survive / k_sam_fill
+//                             the order-dependent half in data-parallel form: ids non-decreasing; the records lost at the 1,000,000-id batch
+//                             boundaries (AG:1259) by binary search; the duplicate rule (AG:1650-1655) by looking back through the record's
+//                             group; count -> scan -> fill of the surviving `ag_aln` tuples in file order
+// Anything outside the well-formed layout (multi-line reads, empty lines, unsorted ids, unknown CIGAR characters, ...) is reported as
+// "not well formed" and the sequential host parser — the literal semantics, error messages included — takes the file.
+#pragma once
+#include "ag_samcore.h"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// newline index
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr int NL_T = 256, NL_BYTES = 64, NL_B = NL_T * NL_BYTES;   // 16 KB of text per CTA
+
+__device__ __forceinline__ u32 nl_bits(u32 w) { return __vcmpeq4(w, 0x0A0A0A0Au) & 0x01010101u; }   // bit 0 of every byte that is '\n'
+
+__global__ void __launch_bounds__(NL_T) k_nl_count(const uint4* __restrict__ text, size_t n16, u32* __restrict__ blk) {
+    __shared__ u32 sm[33];
+    const size_t i0 = ((size_t)blockIdx.x * NL_T + threadIdx.x) * (NL_BYTES / 16);
+    u32 c = 0;
+#pragma unroll
+    for (int j = 0; j < NL_BYTES / 16; j++)
+        if (i0 + j < n16) { const uint4 v = text[i0 + j]; c += __popc(nl_bits(v.x)) + __popc(nl_bits(v.y)) + __popc(nl_bits(v.z)) + __popc(nl_bits(v.w)); }
+    u32 total; block_excl_scan(c, sm, total);
+    if (threadIdx.x == 0) blk[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(NL_T) k_nl_fill(const uint4* __restrict__ text, size_t n16, const u32* __restrict__ blk_off, u32* __restrict__ nl) {
+    __shared__ u32 sm[33];
+    const size_t i0 = ((size_t)blockIdx.x * NL_T + threadIdx.x) * (NL_BYTES / 16);
+    uint4 v[NL_BYTES / 16]; u32 c = 0;
+#pragma unroll
+    for (int j = 0; j < NL_BYTES / 16; j++) {
+        v[j] = make_uint4(0, 0, 0, 0);
+        if (i0 + j < n16) { v[j] = text[i0 + j]; c += __popc(nl_bits(v[j].x)) + __popc(nl_bits(v[j].y)) + __popc(nl_bits(v[j].z)) + __popc(nl_bits(v[j].w)); }
+    }
+    u32 total; u32 o = block_excl_scan(c, sm, total) + blk_off[blockIdx.x];
+    if (!c) return;
+#pragma unroll
+    for (int j = 0; j < NL_BYTES / 16; j++) {
+        const u32 w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            u32 b = nl_bits(w[k]);
+            while (b) { const u32 byte = (u32)(__ffs((int)b) - 1) >> 3; b &= b - 1; nl[o++] = (u32)((i0 + j) * 16 + k * 4 + byte); }
+        }
+    }
+}
+
+// line `i` of a text whose newline positions are nl[]: [start, end) without the newline; `body` = offset of line 0
+__device__ __forceinline__ void line_span(const u32* __restrict__ nl, u32 body, u32 i, u32& s, u32& e) { s = i ? nl[i - 1] + 1 : body; e = nl[i]; }
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// reads
+// ---------------------------------------------------------------------------------------------------------------------------
+enum { ING_BAD_LAYOUT = 1, ING_BAD_RECORD = 2, ING_BAD_ORDER = 8, ING_STRAND = 32, ING_PE_LEN = 64, ING_TOO_LONG = 128 };
+
+// record r = lines 2r ('>' header) and 2r + 1 (sequence); rlen[r] = bases; flags: layout errors, maximum length
+__global__ void k_rd_len(const char* __restrict__ text, const u32* __restrict__ nl, u32 n_rec, u32* __restrict__ rlen, u32* maxlen, int* bad) {
+    const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rec) return;
+    u32 hs, he, ss, se;
+    line_span(nl, 0, 2 * r, hs, he); line_span(nl, 0, 2 * r + 1, ss, se);
+    if (text[hs] != '>' || se == ss || text[ss] == '>' || text[ss] == 0 || he == hs) atomicOr(bad, ING_BAD_LAYOUT);   // multi-line / empty records: sequential host parser
+    const u32 len = se - ss;
+    rlen[r] = len;
+    if (len > 65535u) atomicOr(bad, ING_TOO_LONG);
+    u32 m = len;
+    for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(maxlen, m);
+}
+__global__ void k_rd_pairlen(const u32* __restrict__ rlen, u32 n_pairs, uint16_t* __restrict__ pair_len, int* bad) {
+    const u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pairs) return;
+    const u32 a = rlen[2 * p], b = rlen[2 * p + 1];
+    if (a != b) atomicOr(bad, ING_PE_LEN);   // INCONSISTENT PE FILES!
+    pair_len[p] = (uint16_t)a;
+}
+// one thread per (record, group of 32 bases): two 2-bit words + one mask word; characters other than upper-case ACGT are masked and listed
+__global__ void k_rd_pack(const char* __restrict__ text, const u32* __restrict__ nl, u32 n_rec, u32 stride2, u32 stridem, u64 read0,
+                          u32* __restrict__ bases, u32* __restrict__ nmask, u64* __restrict__ exc_key, char* __restrict__ exc_chr, u32* exc_count, u32 exc_cap) {
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 r = (u32)(t / stridem), g = (u32)(t % stridem);
+    if (r >= n_rec) return;
+    const u32 ss = nl[2 * r] + 1, se = nl[2 * r + 1];
+    const u32 len = se - ss, o0 = g * 32;
+    u32 w0 = 0, w1 = 0, mk = 0;
+    if (o0 < len) {
+        const u32 cnt = min(32u, len - o0);
+        const char* s = text + ss + o0;
+        for (u32 j = 0; j < cnt; j++) {
+            const char ch = s[j];
+            u32 c = ch == 'A' ? 0u : ch == 'C' ? 1u : ch == 'G' ? 2u : ch == 'T' ? 3u : 4u;
+            if (c == 4u) {
+                mk |= 1u << j;
+                const u32 e = atomicAdd(exc_count, 1u);
+                if (e < exc_cap) { exc_key[e] = (read0 + r) * 65536ull + (o0 + j); exc_chr[e] = ch; }
+                c = 0;
+            }
+            if (j < 16) w0 |= c << (2 * j); else w1 |= c << (2 * (j - 16));
+        }
+    }
+    const u64 rr = read0 + r;
+    bases[rr * stride2 + 2 * g] = w0;
+    if (2 * g + 1 < stride2) bases[rr * stride2 + 2 * g + 1] = w1;
+    nmask[rr * stridem + g] = mk;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// SAM
+// ---------------------------------------------------------------------------------------------------------------------------
+// one record pair after the per-record half: what the order-dependent half and the fill need (32 bytes, the shape of ag_aln)
+struct ag_srec { u32 sid, flags /* bit0 fr1, bit1 fr2, bit2 passes AG:1261, bits 8-15 n1, bits 16-23 n2 */, p0, dst1, sl1, dst2, sl2, next /* ext segments */; };
+
+__device__ __forceinline__ bool sam_parse_pair(const char* __restrict__ text, const u32* __restrict__ nl, u32 body, u32 p, const uint16_t* __restrict__ pair_len, u64 n_read_pairs,
+                                               ag_srec& r, ag_seg* n1, ag_seg* n2, int* bad) {
+    u32 s0, e0, s1, e1;
+    line_span(nl, body, 2 * p, s0, e0); line_span(nl, body, 2 * p + 1, s1, e1);
+    r.sid = 0; r.flags = 0; r.p0 = AG_NONE; r.dst1 = r.sl1 = r.dst2 = r.sl2 = 0; r.next = 0;
+    if (e0 == s0 || e1 == s1 || text[s0] == '@' || text[s1] == '@' || text[s0] == 0 || text[s1] == 0) { atomicOr(bad, ING_BAD_LAYOUT); return false; }
+    ag_samline a, b;
+    ag_sam_parse_line(text + s0, e0 - s0, a);
+    ag_sam_parse_line(text + s1, e1 - s1, b);
+    if (a.err || b.err) { atomicOr(bad, ING_BAD_RECORD); return false; }   // unknown CIGAR character / very long CIGAR: the host parser reports or handles it
+    r.sid = a.sid; r.flags = a.fr | (b.fr << 1);
+    r.p0 = a.tid == AG_NONE ? AG_NONE : ag_sam_pos_at0(a.seg, a.nseg);
+    if (ag_sam_mate_pass(a, 0.6) && ag_sam_mate_pass(b, 0.6)) {
+        if (a.tid != 0 || b.tid != 0 || b.sid != a.sid || a.sid >= n_read_pairs) { atomicOr(bad, ING_BAD_RECORD); return false; }
+        const u32 rlen = pair_len[a.sid];
+        u32 c1 = 0, c2 = 0;
+        if (ag_sam_normalize(a.seg, a.nseg, rlen, n1, c1) || ag_sam_normalize(b.seg, b.nseg, rlen, n2, c2) || !c1 || !c2 || c1 > 255 || c2 > 255) { atomicOr(bad, ING_BAD_RECORD); return false; }
+        r.flags |= 4u | (c1 << 8) | (c2 << 16);
+        r.dst1 = n1[0].dst; r.sl1 = n1[0].src | (n1[0].len << 16);
+        r.dst2 = n2[0].dst; r.sl2 = n2[0].src | (n2[0].len << 16);
+        r.next = (c1 > 1 ? c1 : 0) + (c2 > 1 ? c2 : 0);
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(128) k_sam_parse(const char* __restrict__ text, const u32* __restrict__ nl, u32 body, u32 n_rec, const uint16_t* __restrict__ pair_len, u64 n_read_pairs,
+                                                   ag_srec* __restrict__ rec, int* bad) {
+    const u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_rec) return;
+    ag_srec r; ag_seg n1[AG_SAM_MAXSEG], n2[AG_SAM_MAXSEG];
+    sam_parse_pair(text, nl, body, p, pair_len, n_read_pairs, r, n1, n2, bad);
+    rec[p] = r;
+}
+__global__ void k_sam_sorted(const ag_srec* __restrict__ rec, u32 n_rec, int* bad) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i + 1 >= n_rec) return;
+    if (rec[i + 1].sid < rec[i].sid) atomicOr(bad, ING_BAD_ORDER);
+}
+// Batches of 1,000,000 read ids (AG:1885-1894): the first record whose id lies beyond the current batch is consumed and LOST (AG:1259)
+// and the batch advances by one; once the batch reaches the end of the read set the reference stops reading (`stop`).  ids are sorted.
+// out: lost[0] = count, lost[1] = stop, lost[2..] = the lost record indices (ascending)
+__global__ void k_sam_lost(const ag_srec* __restrict__ rec, u32 n_rec, long long n_read_pairs, u32* lost, u32 lost_cap) {
+    if (blockIdx.x || threadIdx.x) return;
+    const long long BATCH = 1000000;
+    long long last = min(BATCH - 1, n_read_pairs - 1);
+    u32 cnt = 0, stop = n_rec, i = 0;
+    for (;;) {
+        u32 lo = i, hi = n_rec;   // first index >= i whose id is > last
+        while (lo < hi) { const u32 mid = lo + (hi - lo) / 2; if ((long long)rec[mid].sid > last) hi = mid; else lo = mid + 1; }
+        const u32 j = lo;
+        if (j >= n_rec) break;
+        if (last >= n_read_pairs - 1) { stop = j; break; }
+        if (cnt < lost_cap) lost[2 + cnt] = j;
+        cnt++;
+        last = min(last + BATCH, n_read_pairs - 1);
+        i = j + 1;
+    }
+    lost[0] = cnt; lost[1] = stop;
+}
+__device__ __forceinline__ bool sam_is_lost(const u32* __restrict__ lost, u32 n_lost, u32 g) {
+    u32 lo = 0, hi = n_lost;
+    while (lo < hi) { const u32 mid = (lo + hi) >> 1; const u32 v = lost[2 + mid]; if (v == g) return true; if (v < g) lo = mid + 1; else hi = mid; }
+    return false;
+}
+// keep[i] = 1 when record i passes AG:1261, is neither lost nor beyond `stop`, and no earlier record of its group (consecutive records that
+// passed the filter with the same id, not separated by a lost record) lies within one read length (AG:1650-1655)
+__global__ void k_sam_survive(const ag_srec* __restrict__ rec, u32 n_rec, const u32* __restrict__ lost, const uint16_t* __restrict__ pair_len, u32* __restrict__ keep, u32* __restrict__ next, int* bad) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rec) return;
+    const ag_srec r = rec[i];
+    const u32 n_lost = lost[0], stop = lost[1];
+    bool k = (r.flags & 4u) && i < stop && !(n_lost && sam_is_lost(lost, n_lost, i));
+    if (k) {
+        u32 rlen = 0; bool have = false;
+        for (u32 j = i; j-- > 0;) {
+            if (n_lost && sam_is_lost(lost, n_lost, j)) break;
+            const ag_srec o = rec[j];
+            if (!(o.flags & 4u)) continue;
+            if (o.sid != r.sid) break;
+            if (!have) { rlen = pair_len[r.sid]; have = true; }
+            if (ag_absdiff(r.p0, o.p0) < (int)rlen) { k = false; break; }
+        }
+    }
+    if (k && ((r.flags & 1u) == ((r.flags >> 1) & 1u))) atomicOr(bad, ING_STRAND);   // exactly one mate must be reverse (AG:1657-1671)
+    keep[i] = k ? 1u : 0u;
+    next[i] = k ? r.next : 0u;
+}
+__global__ void __launch_bounds__(128) k_sam_fill(const char* __restrict__ text, const u32* __restrict__ nl, u32 body, u32 n_rec, const uint16_t* __restrict__ pair_len, u64 n_read_pairs,
+                                                  const ag_srec* __restrict__ rec, const u32* __restrict__ keep, const u32* __restrict__ aoff, const u32* __restrict__ eoff,
+                                                  ag_aln* __restrict__ aln, ag_seg* __restrict__ ext) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rec || !keep[i]) return;
+    const ag_srec r = rec[i];
+    ag_aln a; a.pair = r.sid; a.pad = 0; a.flags = r.flags & ~4u;
+    a.dst1 = r.dst1; a.sl1 = r.sl1; a.dst2 = r.dst2; a.sl2 = r.sl2;
+    u32 oe = eoff ? eoff[i] : 0u;
+    a.ext_idx = oe;
+    if (r.next) {   // multi-segment CIGAR (rare): parse the pair again and write the normalised segment lists
+        ag_srec r2; ag_seg n1[AG_SAM_MAXSEG], n2[AG_SAM_MAXSEG]; int dummy = 0;
+        sam_parse_pair(text, nl, body, i, pair_len, n_read_pairs, r2, n1, n2, &dummy);
+        const u32 c1 = (r.flags >> 8) & 0xFF, c2 = (r.flags >> 16) & 0xFF;
+        if (c1 > 1) { for (u32 j = 0; j < c1; j++) ext[oe + j] = n1[j]; oe += c1; }
+        if (c2 > 1) { for (u32 j = 0; j < c2; j++) ext[oe + j] = n2[j]; }
+    }
+    aln[aoff[i]] = a;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// file -> device through page-locked staging chunks: host threads pread() slices of a chunk into pinned memory (page cache -> pinned
+// at memory speed), the copy engine moves the previous chunk meanwhile
+// ---------------------------------------------------------------------------------------------------------------------------
+struct FileStager {
+    static constexpr size_t CHUNK = (size_t)32 << 20;
+    PinnedBuf ring[2]; cudaEvent_t ev[2] = {nullptr, nullptr};
+    void release() { for (int i = 0; i < 2; i++) { ring[i].release(); if (ev[i]) { cudaEventDestroy(ev[i]); ev[i] = nullptr; } } }
+    // copies file bytes [off, off + len) to dst (device), asynchronously on `st`
+    void run(int fd, size_t off, size_t len, char* dst, cudaStream_t st) {
+        const size_t cb = std::min(len, CHUNK);
+        for (int i = 0; i < 2; i++) { if (!ev[i]) CK(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming)); }
+        ring[0].ensure(cb); if (len > CHUNK) ring[1].ensure(cb);
+        int slot = 0;
+        for (size_t done = 0; done < len; done += CHUNK, slot ^= 1) {
+            const size_t n = std::min(CHUNK, len - done);
+            if (done >= 2 * CHUNK) CK(cudaEventSynchronize(ev[slot]));   // the copy that last used this slot has finished
+            char* h = ring[slot].p;
+            const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)ag_team_size(), n >> 20));
+            const size_t per = (n + T - 1) / T;
+            std::atomic<int> failed(0);
+            ag_parallel_chunks(T, [&](int t) {
+                size_t a = (size_t)t * per, e = std::min(n, a + per);
+                while (a < e) { const ssize_t got = pread(fd, h + a, e - a, (off_t)(off + done + a)); if (got <= 0) { failed = 1; return; } a += (size_t)got; }
+            });
+            if (failed) throw AgError{"CANNOT OPEN FILE!"};
+            CK(cudaMemcpyAsync(dst + done, h, n, cudaMemcpyHostToDevice, st));
+            CK(cudaEventRecord(ev[slot], st));
+        }
+    }
+};
+
+}  // namespace

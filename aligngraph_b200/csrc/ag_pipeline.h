@@ -23,18 +23,31 @@ inline AgUnitInput ag_unit_input(const AgUnit& u) {
     in.cm_start = table ? u.cm_start.data() : nullptr; in.cm = table ? u.cm.data() : nullptr; in.n_cm = (u32)u.chain_pos.size();
     in.chain_pos = u.chain_pos.data(); in.chain_base = u.chain_base.data();
     in.aln = u.aln.data(); in.n_aln = u.aln.size(); in.ext = u.ext.data(); in.n_ext = u.ext.size();
+    if (!u.cdesc.empty() && u.chain_pos.empty()) {   // run-space contig threads: the device expands the chain-major arrays itself
+        in.cdesc = u.cdesc.data(); in.n_desc = (u32)u.cdesc.size(); in.cruns = u.cruns.data(); in.n_runs = (u32)u.cruns.size();
+        in.contig_blob = u.chunks->blob.data(); in.blob_bytes = u.chunks->blob.size(); in.blob_version = u.chunks->version;
+        in.n_cm = u.n_cm_runs; in.chain_pos = nullptr; in.chain_base = nullptr;
+    }
+    in.aln_on_device = u.aln_on_device;
+    if (u.aln_on_device) { in.aln = nullptr; in.n_aln = 0; in.ext = nullptr; in.n_ext = 0; }
     return in;
 }
 
-// loadGenome + loadContigAlignment + the parsing half of loadReadAlignment (AG:4768-4772)
-inline void ag_prepare_unit(const AgReads& reads, const std::string& tmp, int unit, AgUnit& u, std::string& initial_text) {
+// loadGenome + loadContigAlignment + the parsing half of loadReadAlignment (AG:4768-4772).  parse_sam == false leaves the SAM to the caller
+// (the product parses it on the device, AgDevice::ingest_sam, and only falls back to ag_parse_sam for files outside the well-formed layout)
+// host_chains == false leaves the chain-major contiMer arrays to the device as well (k_chain_expand over the run-space contig threads)
+inline void ag_prepare_unit(const AgReads& reads, const std::string& tmp, int unit, AgUnit& u, std::string& initial_text, bool parse_sam = true, bool host_chains = true) {
     std::string n = std::to_string(unit);
     auto t0 = std::chrono::steady_clock::now();
     ag_load_genome(tmp + "/_genome." + n + ".fa", u);
     auto t1 = std::chrono::steady_clock::now();
-    ag_thread_contigs(tmp + "/_contigs.fa", tmp + "/_contigs_genome." + n + ".psl", initial_text, u);
+    // contig threads in run space (interval arithmetic on the PSL blocks); the per-base formulation takes inputs the run form does not model
+    if (getenv("AG_CONTIG_PERBASE") || !ag_thread_contigs_runs(tmp + "/_contigs.fa", tmp + "/_contigs_genome." + n + ".psl", initial_text, u)) {
+        u.cdesc.clear(); u.cruns.clear(); u.chunks.reset(); u.n_cm_runs = 0;
+        ag_thread_contigs(tmp + "/_contigs.fa", tmp + "/_contigs_genome." + n + ".psl", initial_text, u);
+    } else if (host_chains) ag_expand_chains(u);
     auto t2 = std::chrono::steady_clock::now();
-    ag_parse_sam(tmp + "/_reads_genome." + n + ".bowtie", reads, u);
+    if (parse_sam) ag_parse_sam(tmp + "/_reads_genome." + n + ".bowtie", reads, u);
     auto t3 = std::chrono::steady_clock::now();
     if (getenv("AG_POST_TIMING")) fprintf(stderr, "[parse] genome %.1f ms, contigs %.1f ms, sam %.1f ms\n", std::chrono::duration<double>(t1 - t0).count() * 1e3,
                                           std::chrono::duration<double>(t2 - t1).count() * 1e3, std::chrono::duration<double>(t3 - t2).count() * 1e3);

@@ -61,6 +61,10 @@ typedef struct ag_stats {
     double s_parse, s_device_section, s_post;
     uint64_t n_aln, n_nodes, n_walks, n_emitted, n_keys, n_tiles, kernel_launches, h2d_bytes, d2h_bytes;
     int walk_fallback; /* 1 when the exact sequential replay (AG:2194-2202 skip rule) had to be used */
+    /* GPU-side text ingestion: device ms (staging copies + kernels) and how many files took the device / the host parser */
+    float ms_ingest_reads, ms_ingest_sam;
+    uint64_t sam_device, sam_host, reads_device, reads_host;
+    uint64_t regrows; /* sweeps repeated with a larger node table / node overflow pool / edge overflow pool */
 } ag_stats;
 
 int ag_create(const ag_params* params, ag_ctx** out);
@@ -141,6 +145,10 @@ int ag_pin_staged(ag_ctx* ctx);
 /* input normalisation that --resume re-runs (formalizeInput(contigs) + formalizeGenome, AG:4757-4758): writes tmp/_contigs.fa,
  * tmp/_chaff.fa, tmp/_genome.fa and tmp/_genome.N.fa; returns the number of units */
 int ag_formalize_inputs(ag_ctx* ctx, const char* contig_fa, const char* genome_fa, const char* tmp_dir, int part, int* n_units);
+/* tuning / test hooks: "host_parse" (1 = SAM and reads text parsed by the host parsers instead of the device kernels), "node_cap" / "ovf_cap" /
+ * "eovf_cap" (initial capacities of the node table, the node overflow pool and the edge overflow pool; small values force the grow-and-redo
+ * paths), "section_timing" (1 = CUDA-event timing of every pipeline section, which synchronises after each one; default 0) */
+int ag_set_option(ag_ctx* ctx, const char* name, long value);
 int ag_timer_start(ag_ctx* ctx);
 int ag_timer_stop(ag_ctx* ctx, float* ms);
 

@@ -101,3 +101,13 @@ def test_emulation_edge_cases(harness, workdir, kind):
     harness.run_emul(emu, dump_nodes=True)
     assert harness.unit_outputs(emu, 0) == harness.unit_outputs(ora, 0)
     assert open(os.path.join(emu, "tmp", "_nodes.0.txt"), "rb").read() == open(os.path.join(ora, "tmp", "_nodes.0.txt"), "rb").read()
+
+
+@pytest.mark.parametrize("name", ["mix", "overlap_ctg", "part2"])
+def test_per_base_contig_threading_still_matches_golden(harness, workdir, name):
+    """The default host path threads contigs in run space (ag_thread_contigs_runs: interval arithmetic on the PSL blocks, chain arrays
+    expanded from descriptors); the per-base formulation it replaced stays as the path for inputs the run form does not model.  Both must
+    give the reference's files (the default is what every other emulation test runs)."""
+    harness.synth(workdir, **cases.GOLDEN[name])
+    harness.run_emul(workdir, env={"AG_CONTIG_PERBASE": "1"})
+    compare_with_golden(harness, workdir, name)
