@@ -252,9 +252,15 @@ int ag_prepare_unit_files(ag_ctx* ctx, const char* tmp_dir, int unit_id) {
 int ag_write_unit_files(ag_ctx* ctx, const char* tmp_dir, int unit_id) {
     return guard(ctx, [&] {
         std::string n = std::to_string(unit_id), tmp = tmp_dir;
-        ag_write_file(tmp + "/_initial_contigs." + n + ".fa", ctx->res.initial_text);
-        ag_write_file(tmp + "/_pre_extended_contigs." + n + ".fa", ctx->res.pre_text);
-        ag_write_file(tmp + "/_extended_contigs." + n + ".fa", ctx->res.ext_text);
+        std::string errs[3];
+        ag_parallel_chunks(3, [&](int i) {   // the three files side by side
+            try {
+                if (i == 0) ag_write_file(tmp + "/_initial_contigs." + n + ".fa", ctx->res.initial_text);
+                else if (i == 1) ag_write_file(tmp + "/_pre_extended_contigs." + n + ".fa", ctx->res.pre_text);
+                else ag_write_file(tmp + "/_extended_contigs." + n + ".fa", ctx->res.ext_text);
+            } catch (const AgHostError& e) { errs[i] = e.msg; }
+        });
+        for (const std::string& e : errs) if (!e.empty()) throw AgHostError{e};
     });
 }
 int ag_run_unit_files(ag_ctx* ctx, const char* tmp_dir, int unit_id) {

@@ -4,15 +4,19 @@
     python bench.py [--gpus N --steps K --warmup W]            # this repo's CUDA path (one process per GPU under torchrun)
     python bench.py --impl reference [--gpus N ...]            # the reference's own CPU implementation of the path
 
-Workload (config.workload): BASELINE.json configs[1] — E. coli-sized 4.6 Mbp unit, 50x synthetic 2x100 bp PE reads (insert 500 +- 50),
-k = 5, coverage = 20 — ONE such unit per GPU (weak scaling: chromosomes are farmed one per GPU).  A "step" is one
-full pass of the hot path over the rank's unit: positional de Bruijn graph build, coverage filter, extension walk, contig
-de-dup/join and scaffolding, ending with the unit's FASTA text in host memory.
+Workload (config.workload): --config c2 (default) = BASELINE.json configs[1] — E. coli-sized 4.6 Mbp unit, 50x synthetic 2x100 bp PE reads
+(insert 500 +- 50), k = 5, coverage = 20 — ONE such unit per GPU (weak scaling: chromosomes are farmed one per GPU, SURVEY.md §8e);
+--config c3 | c4 | c5 = configs[2..4] (4 x 12.5 Mbp; 8 x 25 Mbp 2x150 k=7; 2 x 100 Mbp --part 4), a fixed job of units dealt round-robin
+to the GPUs.  A "step" is one full pass of the hot path over the rank's unit(s).
 
 Printed JSON (one line, rank 0):
-  value   Mbp of reference genome processed per second, all GPUs, inputs already resident in HBM when the timed region starts
-  e2e     same metric through the array-level C ABI from pinned HOST buffers (reads + unit arrays copied H2D every step, results D2H)
-  roofline  dominant kernel (k_build) against the measured HBM peak; cpu_baseline  the reference CPU path on a bounded sample
+  value   Mbp of reference genome per second, all GPUs, inputs already resident in HBM when the timed region starts (device pipeline +
+          host post passes, ending with the unit's FASTA text in host memory)
+  e2e     the same metric as T_hot of SURVEY.md §8d: every step starts from the tmp/ TEXT files (reads FASTA, genome, PSL, SAM) in host
+          memory and ends with the three per-unit FASTA files written — host->device copies of the raw text, device-side parsing, graph
+          build, walk, post passes and file output all inside the timed region; this is what the reference arm's number covers too
+  roofline  dominant kernel (k_build) against the measured HBM peak;  cpu_baseline  the reference's CPU path on one full-size unit
+--impl reference: the unmodified reference (oracle/_ref, else the oracle port) on the SAME configuration, full-size units.
 """
 import argparse
 import ctypes
@@ -28,15 +32,44 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-UNIT_BP = 4_600_000          # configs[1]: E. coli-sized unit
-SAMPLE_BP = 1_150_000        # CPU legs: 1/4 of a unit, same shape (~6 s per pass on one host core of the GPU box)
-SHAPE = dict(coverage=50, readlen=100, insert_mean=500, insert_sd=50, kmer=5, cov=20, contig_len=10000, contig_gap=1000, snp=0.01)
-SEED = 20260925 + 2
+# BASELINE.json configs.  "c2" (configs[1], the configuration the metric is quoted on) is the default: ONE 4.6 Mbp unit per GPU, weak scaling.
+# c3 / c4 / c5 are the multi-chromosome configs[2..4]: a FIXED job of U units, unit u -> rank u mod N (strong scaling).
+CONFIGS = {
+    "c2": dict(unit_bp=4_600_000, units=None, part=1, readlen=100, kmer=5, seed=20260925 + 2, scaling="weak",
+               name="BASELINE configs[1] shape: one 4.6 Mbp unit per GPU"),
+    "c3": dict(unit_bp=12_500_000, units=4, part=1, readlen=100, kmer=5, seed=20260925 + 3, scaling="strong",
+               name="BASELINE configs[2]: 50 Mbp genome, 4 chromosomes of 12.5 Mbp"),
+    "c4": dict(unit_bp=25_000_000, units=8, part=1, readlen=150, kmer=7, seed=20260925 + 4, scaling="strong",
+               name="BASELINE configs[3]: 200 Mbp genome, 8 chromosomes of 25 Mbp"),
+    "c5": dict(unit_bp=25_000_000, units=8, part=4, readlen=150, kmer=7, seed=20260925 + 5, scaling="strong",
+               name="BASELINE configs[4]: 200 Mbp genome, 2 chromosomes of 100 Mbp, --part 4 (8 units of 25 Mbp)"),
+}
 METRIC = "graph-build+extend Mbp/s"
+
+
+def shape_of(cfg):
+    return dict(coverage=50, readlen=cfg["readlen"], insert_mean=500, insert_sd=50, kmer=cfg["kmer"], cov=20, contig_len=10000, contig_gap=1000, snp=0.01)
+
+
+def n_units_of(cfg, n_gpus):
+    return cfg["units"] if cfg["units"] else n_gpus
 
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
+
+
+def workload_config(cfg_name, n):
+    """The SAME dict for both arms (the driver compares them): it names the workload, not the implementation."""
+    cfg = CONFIGS[cfg_name]
+    units = n_units_of(cfg, n)
+    L = cfg["readlen"]
+    return {"workload": f"{cfg['name']}, 50x synthetic 2x{L} bp PE (insert 500+-50), k={cfg['kmer']}, coverage=20, 10 kbp contig tiles, SNP 1%; "
+                        f"every step = the whole hot path (loadGenome .. scaffoldContigs, AlignGraph.cpp:4768-4776) over {units} unit(s) from the tmp/ text files",
+            "config": cfg_name, "unit_bp": cfg["unit_bp"], "units": units, "pairs_per_unit": int(cfg["unit_bp"] * 50 / (2 * L)), "readlen": L, "k": cfg["kmer"],
+            "coverage_threshold": 20, "insert_variation": 50, "part": cfg["part"],
+            "parallelism": f"{units} unit(s) over {n} GPU(s), unit u -> GPU u mod N, no data-path collective",
+            "l2": "inputs + tables per step (> 1 GB per unit) exceed the 126 MB L2; no explicit flush"}
 
 
 # ------------------------------------------------------------------------------------------------------------------------------
@@ -79,59 +112,66 @@ def cpu_pass(sample_dirs):
     return max(spans), ("reference" if use_ref else "port")
 
 
-def make_samples(base, n):
+def make_unit_dirs(base, cfg_name, n_dirs):
+    """n_dirs single-unit work directories of the configuration's unit shape and FULL unit size (one reference process each)."""
     from oracle import harness
     from tools import synth
+    cfg = CONFIGS[cfg_name]
     harness.build_tools(with_emul=False)
     dirs = []
-    for i in range(n):
-        d = os.path.join(base, f"sample{i}")
-        synth.synth(d, genome_bp=SAMPLE_BP, seed=SEED + 100 + i, **SHAPE)
+    for i in range(n_dirs):
+        d = os.path.join(base, f"unit{i}")
+        synth.synth(d, genome_bp=cfg["unit_bp"], seed=cfg["seed"] + 100 + i, user_reads=0, **shape_of(cfg))
         harness.prepare_tmp(d)
         dirs.append(d)
     return dirs
 
 
 def reference_arm(args):
+    """The reference's own CPU implementation of the path on the SAME configuration: full-size units, one single-threaded process per
+    unit (its hot loop has no threads), min(units, host cores) at a time.  Every step is one full pass over all units."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     n = args.gpus
-    cores = min(n, os.cpu_count() or 1)
+    cfg = CONFIGS[args.config]
+    units = n_units_of(cfg, n)
+    cores = min(units, os.cpu_count() or 1)
     base = tempfile.mkdtemp(prefix="ag_bench_ref_")
     try:
-        dirs = make_samples(base, n)
+        dirs = make_unit_dirs(base, args.config, units)
         kind = "port"
-        for _ in range(args.warmup):
-            cpu_pass(dirs)
-        t0 = time.perf_counter()
+        t_probe0 = time.perf_counter()
+        warm = args.warmup
+        done_warm = 0
         worst = 0.0
+        t0 = time.perf_counter()
+        # warm-up passes only warm the page cache for a CPU process; they are capped so that W + K full-size passes fit the driver's limit
+        budget_s = float(os.environ.get("AG_REF_BUDGET_S", "1500"))
+        for i in range(warm):
+            s, kind = cpu_pass(dirs)
+            done_warm += 1
+            if (time.perf_counter() - t_probe0) + s * (args.steps + (warm - done_warm)) > budget_s:
+                break
+        t0 = time.perf_counter()
         for _ in range(args.steps):
             s, kind = cpu_pass(dirs)
             worst += s
         wall = time.perf_counter() - t0
-        value = n * SAMPLE_BP / 1e6 * args.steps / worst
+        value = units * cfg["unit_bp"] / 1e6 * args.steps / worst
         line = {
-            "impl": "reference", "metric": METRIC, "value": round(value, 5), "unit": "Mbp/s", "n_gpus": n, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": round(1000 * worst / args.steps, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
-            "data": "synthetic", "config": workload_config(n, sample=True),
+            "impl": "reference", "metric": METRIC, "value": round(value, 5), "unit": "Mbp/s", "n_gpus": n, "steps": args.steps, "warmup": done_warm,
+            "ms_per_step": round(1000 * worst / args.steps, 2), "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "u32",
+            "data": "synthetic", "config": workload_config(args.config, n),
             "cpu_baseline": {"value": round(value, 5), "unit": "Mbp/s", "cores": cores, "kind": kind,
-                             "sample": f"{n} unit(s) of {SAMPLE_BP} bp (1/4 of the {UNIT_BP} bp unit, same shape), one process per unit; hot path = span "
-                                       f"of the reference's progress lines (loadGenome..scaffoldContigs), text parsing included as in the reference"},
+                             "sample": f"{units} FULL-size unit(s) of {cfg['unit_bp']} bp, one single-threaded process per unit, {cores} at a time; hot path = span of the "
+                                       f"reference's progress lines (CHROMOSOME n .. (5) Contigs scaffolded): text parsing of the tmp/ files included, as for the GPU arm's e2e"},
             "e2e": {"value": round(value, 5), "unit": "Mbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": round(wall, 2),
         }
         emit(line)
     finally:
         shutil.rmtree(base, ignore_errors=True)
-
-
-def workload_config(n, sample=False):
-    bp = SAMPLE_BP if sample else UNIT_BP
-    return {"workload": f"BASELINE configs[1] shape: {bp / 1e6:g} Mbp unit x {n} (one per GPU), 50x synthetic 2x100 bp PE (insert 500+-50), k=5, "
-                        f"coverage=20, 10 kbp contig tiles, SNP 1%", "unit_bp": bp, "units": n, "pairs_per_unit": int(bp * 50 / 200), "readlen": 100, "k": 5,
-            "coverage_threshold": 20, "insert_variation": 50, "parallelism": f"units{n} (1 unit/GPU, no data-path collective; one NCCL broadcast of the packed reads)",
-            "l2": "inputs+tables per step (~1 GB) exceed the 126 MB L2; no explicit flush"}
 
 
 # ------------------------------------------------------------------------------------------------------------------------------
@@ -176,51 +216,58 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------------------------
 # this repo's arm
 # ------------------------------------------------------------------------------------------------------------------------------
+def bind_rank_cores(world, local):
+    """One process per GPU: give every rank its own block of host cores, local to its GPU's NUMA node where NVML knows it."""
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+        mine = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            words = (max(allowed) // 64) + 1
+            aff = []
+            for g in range(world):
+                mask = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(g), words)
+                aff.append(tuple(c for c in allowed if (mask[c // 64] >> (c % 64)) & 1))
+            peers = [g for g in range(world) if aff[g] == aff[local]]
+            if aff[local] and len(aff[local]) // len(peers) >= 2:
+                per = len(aff[local]) // len(peers)
+                i = peers.index(local)
+                mine = aff[local][i * per:(i + 1) * per]
+        except Exception:
+            mine = None
+        if mine is None:
+            per = len(allowed) // world
+            if per >= 2:
+                mine = allowed[local * per:(local + 1) * per]
+        if mine:
+            os.sched_setaffinity(0, set(mine))
+            os.environ.setdefault("AG_THREADS", str(len(mine)))   # host thread team / parser threads = this rank's core share
+    except (AttributeError, OSError):
+        pass
+
+
 def b200_arm(args):
     import torch
     import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        bind_rank_cores(world, local)   # before the library starts its thread team
+    os.environ.setdefault("AG_MALLOPT", "1")   # this process is the benchmark's own: keep the staging blocks on the heap from step to step
     import aligngraph_b200 as ag
     from aligngraph_b200 import build as _build
     from tools import synth
-    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+    if local == 0:
         _build.build()  # no-op when the in-tree library is newer than its sources
-
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus and world > 1:
         log(f"warning: WORLD_SIZE {world} != --gpus {args.gpus}")
     n = world
+    cfg = CONFIGS[args.config]
+    units = n_units_of(cfg, n)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
-        # one process per GPU: give every rank its own block of host cores (post passes and staging are memory-bound host work;
-        # unbound ranks pile up on one NUMA node)
-        try:
-            allowed = sorted(os.sched_getaffinity(0))
-            mine = None
-            try:   # cores local to this GPU (NVML), shared evenly by the ranks whose GPUs sit on the same NUMA node
-                import pynvml
-                pynvml.nvmlInit()
-                words = (max(allowed) // 64) + 1
-                aff = []
-                for g in range(world):
-                    mask = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(g), words)
-                    aff.append(tuple(c for c in allowed if (mask[c // 64] >> (c % 64)) & 1))
-                peers = [g for g in range(world) if aff[g] == aff[local]]
-                if aff[local] and len(aff[local]) // len(peers) >= 2:
-                    per = len(aff[local]) // len(peers)
-                    i = peers.index(local)
-                    mine = aff[local][i * per:(i + 1) * per]
-            except Exception:
-                mine = None
-            if mine is None:
-                per = len(allowed) // world
-                if per >= 2:
-                    mine = allowed[local * per:(local + 1) * per]
-            if mine:
-                os.sched_setaffinity(0, set(mine))
-        except (AttributeError, OSError):
-            pass
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
@@ -228,173 +275,134 @@ def b200_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- synthetic job: rank 0 writes the n-unit data set once; every rank parses only its own unit --------------------------
+    # ---- synthetic job: rank 0 writes the data set once (user inputs + the tmp/ files Bowtie2 / BLAT would have produced) -----------
     box = [None]
     if rank == 0:
         base = tempfile.mkdtemp(prefix="ag_bench_")
         t0 = time.perf_counter()
-        synth.synth(base, genome_bp=UNIT_BP * n, chroms=n, seed=SEED, **SHAPE)
-        log(f"[bench] synthetic data ({n} unit(s)) in {time.perf_counter() - t0:.1f} s -> {base}")
+        chroms = units // cfg["part"]
+        synth.synth(base, genome_bp=cfg["unit_bp"] * units, chroms=chroms, part=cfg["part"], seed=cfg["seed"], user_reads=0, **shape_of(cfg))
+        log(f"[bench] synthetic data ({units} unit(s)) in {time.perf_counter() - t0:.1f} s -> {base}")
         box[0] = base
     if world > 1:
         dist.broadcast_object_list(box, src=0)
     base = box[0]
     tmp = os.path.join(base, "tmp")
-    ctx = ag.Context(k=SHAPE["kmer"], insert_variation=50, coverage=SHAPE["cov"], device=local)
+    reads_fa = os.path.join(tmp, "_reads.fa")
+    ctx = ag.Context(k=cfg["kmer"], insert_variation=50, coverage=20, device=local)
     if rank == 0:
-        ctx.formalize_inputs(os.path.join(base, "contigs.fa"), os.path.join(base, "genome.fa"), tmp, 1)
+        got = ctx.formalize_inputs(os.path.join(base, "contigs.fa"), os.path.join(base, "genome.fa"), tmp, cfg["part"])
+        assert got == units, (got, units)
     barrier()
+    my_units = [u for u in range(units) if u % n == rank]
 
-    # ---- reads: parsed once on rank 0, one NCCL broadcast of the packed buffer -------------------------------
-    bcast = None
-    t_reads = time.perf_counter()
-    if world == 1:
-        ctx.load_reads_fasta(os.path.join(tmp, "_reads.fa"))
-    else:
-        import numpy as np
-        meta = [None]
-        if rank == 0:
-            ctx.load_reads_fasta(os.path.join(tmp, "_reads.fa"))
-            b, m, l, npairs, s2, sm = ctx.get_reads()
-            meta[0] = (npairs, s2, sm)
-        dist.broadcast_object_list(meta, src=0)
-        npairs, s2, sm = meta[0]
-        nbytes_each = [2 * npairs * s2 * 4, 2 * npairs * sm * 4, npairs * 2]  # byte buffers: NCCL has no 16-bit integer type
-        padded = [(cnt + world * 16 - 1) // (world * 16) * (world * 16) for cnt in nbytes_each]   # equal, 16-byte aligned slices for the all-gather
-        dev = [torch.zeros(cnt, dtype=torch.uint8, device="cuda") for cnt in padded]
-        if rank == 0:
-            host = [np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint8)), shape=(cnt,)) for p, cnt in zip((b, m, l), nbytes_each)]
-            for t, h in zip(dev, host):
-                t[:h.shape[0]].copy_(torch.from_numpy(h))
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for t in dev:
-            dist.broadcast(t, src=0)
-        e1.record(); torch.cuda.synchronize()
-        nbytes = sum(t.numel() * t.element_size() for t in dev)
-        ms = e0.elapsed_time(e1)
-        bcast = {"bytes": nbytes, "ms": round(ms, 3), "GBps": round(nbytes / ms / 1e6, 1)}
-        ctx.set_reads(dev[0].data_ptr(), dev[1].data_ptr(), dev[2].data_ptr(), npairs, s2, sm, on_device=True)
-        ctx._keep.append(dev)
-        # end-to-end leg at N > 1: every rank owns 1/N of the packed read buffer in pinned host memory (in a deployment: the slice of
-        # tmp/_reads.fa it parsed); per step it copies its slice H2D and one NCCL all-gather over NVLink rebuilds the full buffer on every
-        # GPU — the bandwidth-optimal form of the read broadcast, with constant host->device bytes per rank
-        slices = []
-        for t in dev:
-            n_sl = t.numel() // world
-            view = t[rank * n_sl:(rank + 1) * n_sl]
-            slices.append((view, view.cpu().pin_memory()))
-    t_reads = time.perf_counter() - t_reads
-
-    # ---- this rank's unit ----------------------------------------------------------------------------------------------------------
-    unit = rank
-    t0 = time.perf_counter()
-    ctx.prepare_unit(tmp, unit)
-    t_parse_unit = time.perf_counter() - t0
-    ctx.pin_staged()
-
-    def step():
-        ctx.build()
-        ctx.extend()
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    check_pre = ctx.text(1)
-    # ---- timed: inputs resident in HBM ------------------------------------------------------------------------------------------
-    ctx.reset_stats()
-    barrier()
+    # ---- (1) `value`: inputs resident in HBM.  Per unit: text ingested + arrays uploaded once (untimed), then K timed steps of the device
+    # pipeline + host post passes ending with the unit's FASTA text in host memory --------------------------------------------------------
+    ctx.load_reads_fasta(reads_fa)
+    W = max(args.warmup, 3); K = args.steps
+    ms = 0.0
+    stats = None
+    check = {}
     clocks = ClockSampler(local) if rank == 0 else None
-    ctx.timer_start()
-    for _ in range(args.steps):
-        step()
-    ms = ctx.timer_stop()
-    st = ctx.stats()
+    for u in my_units:
+        ctx.prepare_unit(tmp, u)
+        for _ in range(W):
+            ctx.build(); ctx.extend()
+        check[u] = ctx.text(1)
+        ctx.reset_stats()
+        barrier() if len(my_units) == 1 else torch.cuda.synchronize()
+        ctx.timer_start()
+        for _ in range(K):
+            ctx.build(); ctx.extend()
+        ms += ctx.timer_stop()
+        st = ctx.stats()
+        stats = st if stats is None else {k: (stats[k] + st[k]) if k != "walk_fallback" else max(stats[k], st[k]) for k in st}
     barrier()
-    # ---- timed: end to end through the array-level C ABI from pinned host buffers -------------------------------------------------
+
+    # ---- (2) `e2e` = T_hot: every step starts from the tmp/ TEXT files in host memory (page cache) and ends with the three
+    # per-unit FASTA files written: reads text -> device (parsed there), per unit genome / PSL / SAM text -> device, graph build, walk,
+    # post passes, file output.  The reads are ingested once per step and shared by the rank's units, as the product does per run ------
+    def e2e_step():
+        ctx.load_reads_fasta(reads_fa)
+        for u in my_units:
+            ctx.run_unit(tmp, u)
+
+    for _ in range(W):
+        e2e_step()
     ctx.reset_stats()
     barrier()
     ctx.timer_start()
-    reads_h2d = 0
-    for _ in range(args.steps):
-        if world == 1:
-            ctx.reupload_reads()
-        else:
-            for t, (view, host_slice) in zip(dev, slices):
-                view.copy_(host_slice, non_blocking=True)
-                dist.all_gather_into_tensor(t, view)
-                reads_h2d += host_slice.numel()
-            torch.cuda.synchronize()   # the library launches on its own stream
-        ctx.invalidate_device_inputs()
-        step()
+    for _ in range(K):
+        e2e_step()
     ms_e2e = ctx.timer_stop()
     st_e2e = ctx.stats()
     clock_info = clocks.stop() if clocks else None   # sampled every 100 ms across both timed regions
     barrier()
-    assert ctx.text(1) == check_pre and len(check_pre) > 0
-    # ---- file level (text in, text out), for reference: one pass --------------------------------------------------------------------
-    t0 = time.perf_counter()
-    ctx.prepare_unit(tmp, unit); ctx.build(); ctx.extend(); ctx.write_unit(tmp, unit)
-    t_file = time.perf_counter() - t0
+    for u in my_units:   # the files the timed region wrote are the ones the resident path produced
+        with open(os.path.join(tmp, f"_pre_extended_contigs.{u}.fa"), "rb") as f:
+            assert f.read() == check[u] and len(check[u]) > 0
 
-    t = torch.tensor([ms, ms_e2e, t_file, t_parse_unit], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e, t_file, t_parse_unit = t.tolist()
+    ms, ms_e2e = t.tolist()
+    cnt = torch.tensor([float(stats[k]) for k in ("n_aln", "n_nodes", "n_keys", "kernel_launches")] + [float(st_e2e["h2d_bytes"]), float(st_e2e["d2h_bytes"])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    tot_aln, tot_nodes, tot_keys, tot_launch, e2e_h2d, e2e_d2h = cnt.tolist()
 
     if rank == 0:
-        K = args.steps
-        mbp = n * UNIT_BP / 1e6
+        mbp = units * cfg["unit_bp"] / 1e6
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
         peak = peaks.get("hbm_gbs", 6650.0)
-        # dominant kernel: k_build (node sweep + common-case edges).  Algorithmic bytes of one launch: per tile key the
-        # alignment index, its 32-byte prepared record and the left mate's packed bases + non-ACGT plane; per position the contiMer
-        # summary, reference base and CSR entry; per node the final records written (16 + 16 + 8 + 4).
-        L = SHAPE["readlen"]
-        alg = st["n_keys"] * (4 + 32 + (L + 3) // 4 + (L + 7) // 8) + UNIT_BP * (8 + 1 + 4) + st["n_nodes"] * 44
-        nodes_ms = st["ms_nodes"] / K
+        # dominant kernel: k_build (node sweep + common-case edges).  Algorithmic bytes of one launch: per tile key the staged
+        # record (prepared alignment + the left mate's bases); per position the contiMer summary, reference base and CSR entry; per node the
+        # final records written (16 + 16 + 8 + 4).  Rank 0's launches (K per unit).
+        L = cfg["readlen"]
+        n_launch = K * len(my_units)
+        alg = stats["n_keys"] / max(len(my_units), 1) * (4 + 32 + (L + 3) // 4 + (L + 7) // 8) + cfg["unit_bp"] * (8 + 1 + 4) + stats["n_nodes"] / max(len(my_units), 1) * 44
+        nodes_ms = stats["ms_nodes"] / n_launch
         achieved = alg / nodes_ms / 1e6
-        pairs = UNIT_BP * 50 // 200
-        k1_equiv = pairs * (2 * ((L + 3) // 4) + 32 + 16 * (L - SHAPE["kmer"])) / ((st["ms_prep"] + st["ms_sort"] + st["ms_nodes"]) / K) / 1e6
         traffic = None
-        try:   # DRAM bytes of one k_build launch from the committed `ncu --set full` capture of this same workload (profiles/README.md)
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["traffic"]
+        try:   # DRAM bytes of one k_build launch from the committed `ncu --set full` capture of the c2 workload (profiles/README.md)
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["traffic"] if args.config == "c2" else None
         except Exception:
             pass
         line = {
-            "metric": METRIC, "value": round(mbp * K / (ms / 1000), 3), "unit": "Mbp/s", "n_gpus": n, "steps": K, "warmup": max(args.warmup, 3),
-            "ms_per_step": round(ms / K, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": workload_config(n),
-            "e2e": {"value": round(mbp * K / (ms_e2e / 1000), 3), "unit": "Mbp/s", "h2d_bytes_per_step": int((st_e2e["h2d_bytes"] + reads_h2d) / K),
-                    "d2h_bytes_per_step": int(st_e2e["d2h_bytes"] / K), "ms_per_step": round(ms_e2e / K, 3)},
-            "gpu_launches": int(st["kernel_launches"]),
+            "metric": METRIC, "value": round(mbp * K / (ms / 1000), 3), "unit": "Mbp/s", "n_gpus": n, "steps": K, "warmup": W,
+            "ms_per_step": round(ms / K, 3), "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": workload_config(args.config, n),
+            "e2e": {"value": round(mbp * K / (ms_e2e / 1000), 3), "unit": "Mbp/s", "h2d_bytes_per_step": int(e2e_h2d / K), "d2h_bytes_per_step": int(e2e_d2h / K),
+                    "ms_per_step": round(ms_e2e / K, 3),
+                    "scope": "T_hot from the tmp/ text files (reads FASTA, genome, PSL, SAM) to the three per-unit FASTA files on disk, through ag_load_reads_fasta + "
+                             "ag_run_unit_files; h2d/d2h bytes summed over all GPUs",
+                    "rank0_breakdown_ms_per_step": {"reads_ingest": round(st_e2e["ms_ingest_reads"] / K, 3), "sam_ingest": round(st_e2e["ms_ingest_sam"] / K, 3),
+                                                    "host_parse_s": round(st_e2e["s_parse"] / K * 1e3, 3), "device_section": round(st_e2e["s_device_section"] / K * 1e3, 3),
+                                                    "post_passes": round(st_e2e["s_post"] / K * 1e3, 3)},
+                    "text_parsed_on": {"sam_device": int(st_e2e["sam_device"]), "sam_host": int(st_e2e["sam_host"]), "reads_device": int(st_e2e["reads_device"]),
+                                       "reads_host": int(st_e2e["reads_host"])}},
+            "gpu_launches": int(tot_launch),
             "clocks": clock_info,
             "roofline": {"bound": "hbm", "kernel": "k_build", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                          "traffic": traffic, "alg_bytes_per_launch": int(alg), "ms_per_launch": round(nodes_ms, 4),
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
-                         "survey_k1_equiv_gbs": round(k1_equiv, 1)},
-            "device_ms_per_step": {k[3:]: round(st[k] / K, 4) for k in st if k.startswith("ms_")},
-            "counts_per_unit": {"alignments": int(st["n_aln"] / K), "nodes": int(st["n_nodes"]), "walks": int(st["n_walks"] / K),
-                                "emitted_contigs": int(st["n_emitted"] / K), "tile_keys": int(st["n_keys"])},
-            "host_s_per_step": {"device_section": round(st["s_device_section"] / K, 4), "post_passes": round(st["s_post"] / K, 4)},
-            "file_level": {"value": round(mbp / t_file, 3), "unit": "Mbp/s", "s_per_unit": round(t_file, 3),
-                           "note": "tmp/ text files in -> tmp/ FASTA out through ag_run_unit_files steps (SAM/PSL parse + device + write), reads parsed once: "
-                                   f"{t_reads:.2f} s extra", "parse_unit_s": round(t_parse_unit, 3)},
-            "reads_broadcast": bcast,
-            "walk_fallback": int(st["walk_fallback"]),
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"},
+            "device_ms_per_step": {k[3:]: round(stats[k] / K, 4) for k in stats if k.startswith("ms_")},
+            "counts": {"alignments": int(tot_aln / K), "nodes": int(tot_nodes), "tile_keys": int(tot_keys), "units": units},
+            "host_s_per_step": {"device_section": round(stats["s_device_section"] / K, 4), "post_passes": round(stats["s_post"] / K, 4)},
+            "walk_fallback": int(stats["walk_fallback"]),
         }
         if not args.no_cpu and n == 1:
-            try:
+            try:   # the reference's CPU implementation on ONE full-size unit of this configuration, timed once (~30 s for c2)
                 sdir = tempfile.mkdtemp(prefix="ag_bench_cpu_")
-                dirs = make_samples(sdir, 1)
+                dirs = make_unit_dirs(sdir, args.config, 1)
                 s, kind = cpu_pass(dirs)
-                line["cpu_baseline"] = {"value": round(SAMPLE_BP / 1e6 / s, 5), "unit": "Mbp/s", "cores": 1, "kind": kind,
-                                        "sample": f"one {SAMPLE_BP} bp unit (1/4 of the workload unit, same shape), hot path of the reference's CPU "
-                                                  f"implementation timed once: {s:.2f} s"}
+                line["cpu_baseline"] = {"value": round(cfg["unit_bp"] / 1e6 / s, 5), "unit": "Mbp/s", "cores": 1, "kind": kind,
+                                        "sample": f"one FULL-size unit ({cfg['unit_bp']} bp) of this configuration, hot path of the reference's CPU implementation "
+                                                  f"(text parsing included) timed once: {s:.2f} s"}
                 shutil.rmtree(sdir, ignore_errors=True)
             except Exception as e:  # the CPU leg must never take the GPU number down with it
                 line["cpu_baseline"] = {"value": None, "unit": "Mbp/s", "cores": 1, "kind": "port", "sample": f"failed: {e}"}
@@ -430,6 +438,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="BASELINE.json configuration (default c2 = configs[1], the one the metric is quoted on)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

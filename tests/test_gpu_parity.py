@@ -130,6 +130,32 @@ def test_baseline_config1_full_size_against_oracle(ag, harness, workdir):
     assert st["n_aln"] > 1_100_000 and st["walk_fallback"] == 0
 
 
+@pytest.mark.parametrize("name", ["mix", "manyitems", "overlap"])
+def test_capacity_regrow_paths(ag, harness, workdir, name):
+    """Node table, node overflow pool and edge overflow pool start far too small (ag_set_option test hooks): the sweeps must notice, grow
+    and repeat — same node table and files as the oracle, and the repeat counter shows that the loops ran."""
+    gpu, ora = os.path.join(workdir, "gpu"), os.path.join(workdir, "ora")
+    harness.synth(gpu, **(cases.GOLDEN[name] if name in cases.GOLDEN else cases.LIVE[name]))
+    shutil.copytree(gpu, ora)
+    harness.run_oracle(ora, dump_nodes=True)
+    p = harness.read_command(gpu)
+    harness.prepare_tmp(gpu)
+    ctx = ag.Context(k=p["kMer"], insert_variation=p["insertVariation"], coverage=p["coverage"])
+    ctx.set_option("node_cap", 512); ctx.set_option("ovf_cap", 16); ctx.set_option("eovf_cap", 4)
+    ctx.keep_node_counts(True)
+    ctx.load_reads_fasta(os.path.join(gpu, "tmp", "_reads.fa"))
+    ctx.prepare_unit(os.path.join(gpu, "tmp"), 0)
+    ctx.build()
+    dump = ctx.dump_nodes_text()
+    ctx.extend()
+    ctx.write_unit(os.path.join(gpu, "tmp"), 0)
+    st = ctx.stats()
+    ctx.close()
+    assert st["regrows"] >= 2, st
+    assert dump == open(os.path.join(ora, "tmp", "_nodes.0.txt"), "rb").read()
+    assert harness.unit_outputs(gpu, 0) == harness.unit_outputs(ora, 0)
+
+
 import edge_cases
 
 
