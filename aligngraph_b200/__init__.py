@@ -30,7 +30,8 @@ class Stats(C.Structure):
                [(n, C.c_uint64) for n in ("n_aln", "n_nodes", "n_walks", "n_emitted", "n_keys", "n_tiles", "kernel_launches",
                                           "h2d_bytes", "d2h_bytes")] + \
                [("walk_fallback", C.c_int), ("ms_ingest_reads", C.c_float), ("ms_ingest_sam", C.c_float)] + \
-               [(n, C.c_uint64) for n in ("sam_device", "sam_host", "reads_device", "reads_host", "regrows")]
+               [(n, C.c_uint64) for n in ("sam_device", "sam_host", "reads_device", "reads_host", "regrows")] + \
+               [("ms_stage", C.c_float), ("ms_build_kernel", C.c_float)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -72,11 +73,13 @@ def load_library(path=None):
         "ag_add_alignments": (i32, [vp, vp, u64, vp, u64]),
         "ag_build": (i32, [vp]),
         "ag_extend": (i32, [vp]),
+        "ag_process": (i32, [vp]),
         "ag_get_text": (i32, [vp, i32, C.POINTER(vp), C.POINTER(u64)]),
         "ag_prepare_unit_files": (i32, [vp, cp, i32]),
         "ag_write_unit_files": (i32, [vp, cp, i32]),
         "ag_run_unit_files": (i32, [vp, cp, i32]),
         "ag_run_units_files": (i32, [C.POINTER(vp), i32, cp, i32, i32, i32, vp, vp]),
+        "ag_run_job_files": (i32, [C.POINTER(vp), i32, cp, cp, C.POINTER(i32), i32, i32, vp, vp]),
         "ag_get_unit": (i32, [vp, C.POINTER(UnitView)]),
         "ag_get_stats": (i32, [vp, C.POINTER(Stats)]),
         "ag_reset_stats": (i32, [vp]),
@@ -152,6 +155,13 @@ class Context:
         rc = self._lib.ag_run_units_files(arr, 1, os.fsencode(tmp_dir), first, n, prefetch, None, None)
         self._ck(rc, "ag_run_units_files")
 
+    def run_job(self, tmp_dir, units, reads_fa=None, prefetch=2):
+        """The whole hot loop for `units` (ag_run_job_files, this context only); reads_fa: (re)load the read set as part of the job."""
+        arr = (C.c_void_p * 1)(self._h)
+        ul = (C.c_int * len(units))(*units)
+        rc = self._lib.ag_run_job_files(arr, 1, os.fsencode(tmp_dir), os.fsencode(reads_fa) if reads_fa else None, ul, len(units), prefetch, None, None)
+        self._ck(rc, "ag_run_job_files")
+
     def prepare_unit(self, tmp_dir, unit):
         self._ck(self._lib.ag_prepare_unit_files(self._h, os.fsencode(tmp_dir), unit), "ag_prepare_unit_files")
 
@@ -181,6 +191,10 @@ class Context:
 
     def extend(self):
         self._ck(self._lib.ag_extend(self._h), "ag_extend")
+
+    def process(self):
+        """build + extend as one step with a single host synchronisation (ag_process)."""
+        self._ck(self._lib.ag_process(self._h), "ag_process")
 
     def text(self, which):
         p, n = C.c_void_p(), C.c_uint64()

@@ -28,6 +28,7 @@ struct ag_ctx {
     double s_parse = 0, s_device = 0, s_post = 0;
     u64 n_aln = 0, n_walks = 0, n_emitted = 0;
     bool host_parse = getenv("AG_HOST_PARSE") != nullptr;
+    bool fused = false;
 };
 
 static std::string g_create_error;
@@ -214,9 +215,18 @@ int ag_build(ag_ctx* ctx) {
         if (!ctx->uploaded) { ctx->dev->load_unit(ag_unit_input(ctx->unit)); ctx->uploaded = true; }
         if (ctx->reads_dirty) upload_reads(ctx, true);   // overlaps the unit's table / prep / bucket kernels
         ctx->dev->build();
+        if (!ctx->fused) ctx->dev->build_sync();   // the stand-alone call reports the build's own errors; the fused step synchronises once, in ag_extend
         ctx->s_device += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         ctx->n_aln += ctx->unit.aln_on_device ? ctx->dev->ingested_alignments() : ctx->unit.aln.size();
     });
+}
+// graph build + extension as ONE step: the build is only queued, the walk is queued behind it, and the host waits once (ag_extend)
+int ag_process(ag_ctx* ctx) {
+    ctx->fused = true;
+    int rc = ag_build(ctx);
+    ctx->fused = false;
+    if (!rc) rc = ag_extend(ctx);
+    return rc;
 }
 
 // extension half of ag_process_unit (kept separate so that ag_build can be timed / inspected on its own)
@@ -265,8 +275,7 @@ int ag_write_unit_files(ag_ctx* ctx, const char* tmp_dir, int unit_id) {
 }
 int ag_run_unit_files(ag_ctx* ctx, const char* tmp_dir, int unit_id) {
     int rc = ag_prepare_unit_files(ctx, tmp_dir, unit_id);
-    if (!rc) rc = ag_build(ctx);
-    if (!rc) rc = ag_extend(ctx);
+    if (!rc) rc = ag_process(ctx);
     if (!rc) rc = ag_write_unit_files(ctx, tmp_dir, unit_id);
     return rc;
 }
@@ -275,50 +284,56 @@ int ag_run_unit_files(ag_ctx* ctx, const char* tmp_dir, int unit_id) {
 // packed arrays) while one worker thread per context uploads, builds, extends and writes.  Units are handed out in order; outputs do
 // not depend on the number of contexts or on timing (units are independent, AG:4779-4781).  `done` is called (serialised) after every
 // unit with its return code; the first failing unit's code is returned.
-int ag_run_units_files(ag_ctx** ctxs, int n_ctx, const char* tmp_dir, int first_unit, int n_units, int prefetch,
-                       void (*done)(int unit, int rc, const char* error, void* user), void* user) {
-    if (!ctxs || n_ctx <= 0 || n_units < 0) return 1;
-    if (n_units == 0) return 0;
-    for (int i = 0; i < n_ctx; i++) if (!ctxs[i] || !ctxs[i]->have_reads) { if (ctxs[i]) ctxs[i]->err = "reads not set"; return 1; }
+// The whole hot loop for a list of units: [reads] -> per unit (host: genome + contig threads; device: SAM, graph build, walk; host: post passes,
+// files).  `prefetch` host threads prepare units ahead (in list order) while one worker thread per context runs them; with reads_fa != NULL
+// the read set is (re)loaded as part of the job — raw text to ctxs[0]'s GPU, one broadcast to the others — while the preparers already work
+// on the first units.  Outputs do not depend on the number of contexts or on timing (units are independent, AG:4779-4781).
+static int run_units_impl(ag_ctx** ctxs, int n_ctx, const char* tmp_dir, const std::vector<int>& units, int prefetch, const char* reads_fa,
+                          void (*done)(int unit, int rc, const char* error, void* user), void* user) {
+    const int n_units = (int)units.size();
+    if (!ctxs || n_ctx <= 0) return 1;
+    for (int i = 0; i < n_ctx; i++) if (!ctxs[i]) return 1;
+    if (!reads_fa) for (int i = 0; i < n_ctx; i++) if (!ctxs[i]->have_reads) { ctxs[i]->err = "reads not set"; return 1; }
+    if (n_units == 0 && !reads_fa) return 0;
     struct Prepared { AgUnit unit; std::string initial_text, error; double s_parse = 0; };
     std::mutex mu; std::condition_variable cv;
-    std::map<int, std::unique_ptr<Prepared>> ready;
-    std::atomic<int> next_prepare(first_unit), next_run(first_unit);
-    int consumed = first_unit;   // units [first_unit, consumed) have been taken by workers (bounds the look-ahead)
-    const int last = first_unit + n_units;
+    std::map<int, std::unique_ptr<Prepared>> ready;   // by position in `units`
+    std::atomic<int> next_prepare(0), next_run(0);
+    int consumed = 0;   // list positions [0, consumed) have been taken by workers (bounds the look-ahead)
     if (prefetch < 1) prefetch = 1;
     const std::string tmp = tmp_dir;
-    const AgReads& reads = (*ctxs[0]->rp);
+    const bool host_sam = !device_ingest_enabled(ctxs[0]);
     std::atomic<bool> stop(false);   // a unit failed: no further units are started (the reference exits at the failing chromosome)
-    const int n_prep = std::min(prefetch, n_units);
+    const int n_prep = std::min(prefetch, std::max(n_units, 1));
     const int cores = std::max(1u, std::thread::hardware_concurrency());
     auto preparer = [&]() {
         // The preparers run side by side.  Measured on the 16-core GPU host (profiles/r02g_scale_c4_1gpu.json): letting every parser start its
-        // full set of threads keeps the cores busy through the others' serial phases (2.1 s for the 8 units of C4); a strict share-out
-        // (cores / n_prep each) is available through AG_PREP_THREADS but has not been timed.
+        // full set of threads keeps the cores busy through the others' serial phases; a strict share-out (cores / n_prep each) is available
+        // through AG_PREP_THREADS.
         if (const char* e = getenv("AG_PREP_THREADS")) { int n = atoi(e); if (n > 0) ag_set_thread_budget(n); else if (n < 0) ag_set_thread_budget(std::max(1, (cores + n_prep - 1) / n_prep)); }
         for (;;) {
-            int u = next_prepare.fetch_add(1);
-            if (u >= last) return;
-            { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return u < consumed + prefetch + n_ctx || stop.load(); }); }
+            int i = next_prepare.fetch_add(1);
+            if (i >= n_units) return;
+            { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return i < consumed + prefetch + n_ctx || stop.load(); }); }
             if (stop.load()) return;
             auto p = std::make_unique<Prepared>();
             auto t0 = std::chrono::steady_clock::now();
-            try { ag_prepare_unit(reads, tmp, u, p->unit, p->initial_text, !device_ingest_enabled(ctxs[0]), !device_ingest_enabled(ctxs[0])); }
+            try { ag_prepare_unit(*ctxs[0]->rp, tmp, units[(size_t)i], p->unit, p->initial_text, host_sam, host_sam); }
             catch (const AgHostError& e) { p->error = e.msg; }
             catch (const std::bad_alloc&) { p->error = "out of host memory"; }
             p->s_parse = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-            { std::lock_guard<std::mutex> lk(mu); ready[u] = std::move(p); }
+            { std::lock_guard<std::mutex> lk(mu); ready[i] = std::move(p); }
             cv.notify_all();
         }
     };
     int first_rc = 0;
     auto worker = [&](ag_ctx* ctx) {
         for (;;) {
-            int u = next_run.fetch_add(1);
-            if (u >= last || stop.load()) return;
+            int i = next_run.fetch_add(1);
+            if (i >= n_units || stop.load()) return;
+            const int u = units[(size_t)i];
             std::unique_ptr<Prepared> p;
-            { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return ready.count(u) != 0 || stop.load(); }); if (!ready.count(u)) return; p = std::move(ready[u]); ready.erase(u); if (u + 1 > consumed) consumed = u + 1; }
+            { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return ready.count(i) != 0 || stop.load(); }); if (!ready.count(i)) return; p = std::move(ready[i]); ready.erase(i); if (i + 1 > consumed) consumed = i + 1; }
             cv.notify_all();
             int rc = 0;
             if (!p->error.empty()) { ctx->err = p->error; rc = 1; }
@@ -326,9 +341,8 @@ int ag_run_units_files(ag_ctx** ctxs, int n_ctx, const char* tmp_dir, int first_
                 ctx->dev->unpin_all();
                 ctx->unit = std::move(p->unit); ctx->res.reset(); ctx->res.initial_text = std::move(p->initial_text);
                 ctx->unit_id = u; ctx->uploaded = false; ctx->s_parse += p->s_parse;
-                if (device_ingest_enabled(ctx)) rc = guard(ctx, [&] { auto t0 = std::chrono::steady_clock::now(); load_unit_sam(ctx, tmp, u); ctx->s_parse += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); });
-                if (!rc) rc = ag_build(ctx);
-                if (!rc) rc = ag_extend(ctx);
+                if (!host_sam) rc = guard(ctx, [&] { auto t0 = std::chrono::steady_clock::now(); load_unit_sam(ctx, tmp, u); ctx->s_parse += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); });
+                if (!rc) rc = ag_process(ctx);
                 if (!rc) rc = ag_write_unit_files(ctx, tmp_dir, u);
             }
             std::lock_guard<std::mutex> lk(mu);
@@ -338,11 +352,32 @@ int ag_run_units_files(ag_ctx** ctxs, int n_ctx, const char* tmp_dir, int first_
         }
     };
     std::vector<std::thread> th;
-    for (int i = 0; i < n_prep; i++) th.emplace_back(preparer);
+    auto load_reads = [&]() -> int {
+        int rc = ag_load_reads_fasta(ctxs[0], reads_fa);
+        if (!rc && n_ctx > 1) rc = ag_broadcast_reads(ctxs, n_ctx, nullptr);
+        return rc;
+    };
+    int rc_reads = 0;
+    if (reads_fa && host_sam) rc_reads = load_reads();                       // the host SAM parser needs the read lengths: reads first
+    if (!rc_reads) for (int i = 0; i < n_prep && n_units; i++) th.emplace_back(preparer);
+    if (reads_fa && !host_sam) rc_reads = load_reads();                      // raw text -> GPU while the preparers parse the first units' genome / PSL
+    if (rc_reads) { stop = true; cv.notify_all(); for (auto& t : th) t.join(); return rc_reads; }
     for (int i = 1; i < n_ctx; i++) th.emplace_back(worker, ctxs[i]);
     worker(ctxs[0]);
     for (auto& t : th) t.join();
     return first_rc;
+}
+
+int ag_run_units_files(ag_ctx** ctxs, int n_ctx, const char* tmp_dir, int first_unit, int n_units, int prefetch,
+                       void (*done)(int unit, int rc, const char* error, void* user), void* user) {
+    if (n_units < 0) return 1;
+    std::vector<int> units; for (int u = 0; u < n_units; u++) units.push_back(first_unit + u);
+    return run_units_impl(ctxs, n_ctx, tmp_dir, units, prefetch, nullptr, done, user);
+}
+int ag_run_job_files(ag_ctx** ctxs, int n_ctx, const char* tmp_dir, const char* reads_fa, const int* units, int n_units, int prefetch,
+                     void (*done)(int unit, int rc, const char* error, void* user), void* user) {
+    if (n_units < 0 || (n_units && !units)) return 1;
+    return run_units_impl(ctxs, n_ctx, tmp_dir, std::vector<int>(units, units + n_units), prefetch, reads_fa, done, user);
 }
 
 int ag_get_unit(ag_ctx* ctx, ag_unit_view* out) {
@@ -367,7 +402,7 @@ int ag_get_stats(ag_ctx* ctx, ag_stats* o) {
         o->ms_components = t.components; o->ms_chains = t.chains; o->ms_walk = t.walk; o->ms_materialize = t.materialize; o->ms_d2h = t.d2h;
         o->s_parse = ctx->s_parse; o->s_device_section = ctx->s_device; o->s_post = ctx->s_post;
         o->n_aln = ctx->n_aln; o->n_nodes = t.n_nodes; o->n_walks = ctx->n_walks; o->n_emitted = ctx->n_emitted; o->n_keys = t.n_keys; o->n_tiles = t.n_tiles;
-        o->ms_ingest_reads = t.ingest_reads; o->ms_ingest_sam = t.ingest_sam; o->sam_device = t.sam_device; o->sam_host = t.sam_host; o->reads_device = t.reads_device; o->reads_host = t.reads_host; o->regrows = (uint64_t)t.regrows;
+        o->ms_ingest_reads = t.ingest_reads; o->ms_ingest_sam = t.ingest_sam; o->sam_device = t.sam_device; o->sam_host = t.sam_host; o->reads_device = t.reads_device; o->reads_host = t.reads_host; o->regrows = (uint64_t)t.regrows; o->ms_stage = t.stage; o->ms_build_kernel = t.build_kernel;
         o->kernel_launches = ctx->dev->kernel_launches(); o->h2d_bytes = t.h2d_bytes; o->d2h_bytes = t.d2h_bytes; o->walk_fallback = t.walk_fallback;
     });
 }
@@ -417,7 +452,7 @@ int ag_set_option(ag_ctx* ctx, const char* name, long value) {
     return guard(ctx, [&] {
         const std::string n = name ? name : "";
         if (n == "host_parse") ctx->host_parse = value != 0;
-        else if (n == "node_cap" || n == "ovf_cap" || n == "eovf_cap" || n == "section_timing") ctx->dev->set_option(n, value);
+        else if (n == "node_cap" || n == "ovf_cap" || n == "eovf_cap" || n == "key_cap" || n == "cand_cap" || n == "hwalk_cap" || n == "rank_rounds" || n == "tma") ctx->dev->set_option(n, value);
         else throw AgHostError{"unknown option: " + n};
     });
 }

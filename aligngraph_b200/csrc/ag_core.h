@@ -21,6 +21,7 @@
 #define AG_ATOMIC_MIN(p, v) atomicMin((p), (v))
 #define AG_ATOMIC_MAX(p, v) atomicMax((p), (v))
 #define AG_ATOMIC_CAS(p, c, v) atomicCAS((p), (c), (v))
+#define AG_ATOMIC_OR(p, v) atomicOr((p), (v))
 #else
 template <class T> static inline T ag_host_add(T* p, T v) { T o = *p; *p = o + v; return o; }
 template <class T> static inline T ag_host_min(T* p, T v) { T o = *p; if (v < o) *p = v; return o; }
@@ -30,6 +31,7 @@ template <class T> static inline T ag_host_cas(T* p, T c, T v) { T o = *p; if (o
 #define AG_ATOMIC_MIN(p, v) ag_host_min((p), (v))
 #define AG_ATOMIC_MAX(p, v) ag_host_max((p), (v))
 #define AG_ATOMIC_CAS(p, c, v) ag_host_cas((p), (c), (v))
+#define AG_ATOMIC_OR(p, v) (*(p) |= (v))
 #endif
 
 // Tile geometry of the node / edge sweeps: a CTA of AG_TILE threads = 8 warps; a warp owns AG_WPOS = 31 consecutive unit positions
@@ -215,12 +217,18 @@ struct ag_fast {
     u32 mdelta;          // ... where the mate position is q + mdelta            (all modulo 2^32, like the reference's unsigned math)
     u32 read;            // (read index << 1) | rc of the left mate
     u32 simple;          // 0: use ag_locate on the prepared record; bit 0: fast path valid; bit 1 (AG_FAST_CLEAN): every position the alignment
-                         // touches — on the left mate and at the mate positions — holds at most one contiMer, so every touch has one candidate
+                         // touches — on the left mate and at the mate positions — holds at most one contiMer, so every touch has one candidate;
+                         // bit 2 (AG_FAST_LINEAR): the contiMers under the mate positions it touches are one linear stretch of one contig thread
+                         // (or there are none), so the mate-side match fields of every touch are (mcid0, q + mcd) without a table look-up
+    u32 mcid0, mcd;      // see AG_FAST_LINEAR
+    u32 aln, pad;        // alignment index (the prepared record of the generic path); 48 bytes = three 16-byte vectors
 };
 #define AG_FAST_CLEAN 2u
+#define AG_FAST_LINEAR 4u
 
-AG_HD ag_fast ag_fast_prep(const ag_alnp& p, u32 lo, u32 span) {
+AG_HD ag_fast ag_fast_prep(const ag_alnp& p, u32 lo, u32 span, u32 aln_index = 0) {
     ag_fast f;
+    f.mcid0 = AG_NONE; f.mcd = 0; f.aln = aln_index; f.pad = 0;
     f.lo = lo; f.span = span; f.read = p.left_read;
     u32 len = p.len_nseg & 0xFFFFu;
     f.simple = (((p.len_nseg >> 16) & 0xFF) == 1 && ((p.len_nseg >> 24) & 0xFF) == 1) ? 1u : 0u;
@@ -243,6 +251,12 @@ AG_HD bool ag_fast_is_clean(const ag_fast& f, const ag_alnp& p, const u32* many_
     const u32 a = p.r_dst + (u32)(qa - mlo), b = p.r_dst + (u32)(qb - mlo);
     return many_prefix[b + 1] == many_prefix[a];
 }
+
+// lin_prefix[p] = number of positions 1 .. p-1 ... precisely: exclusive scan (n_pos + 1 entries) of brk[], where brk[p] = 1 when the contiMer
+// summary of p does NOT continue that of p - 1 (both empty, or the same contig one offset further); brk[0] = 0
+AG_HD u32 ag_cm1_break(const struct ag_cm1& prev, const struct ag_cm1& cur);
+// clean + linear classification of a prepared alignment (k_prep): sets AG_FAST_CLEAN / AG_FAST_LINEAR and the linear mate fields
+AG_HD void ag_fast_classify(ag_fast& f, const ag_alnp& p, const u32* many_prefix, const u32* lin_prefix, const struct ag_cm1* cm1);
 
 // touch of a simple alignment at position q; requires q - f.lo <= f.span
 AG_HD ag_touch ag_fast_touch(const ag_fast& f, u32 q, u32 k) {
@@ -345,6 +359,27 @@ AG_HD ag_cm1 ag_make_cm1(const ag_cmtab& t, u32 pos) {
     return r;
 }
 
+AG_HD u32 ag_cm1_break(const ag_cm1& prev, const ag_cm1& cur) {
+    if (prev.cid == AG_NONE && cur.cid == AG_NONE) return 0u;
+    if (prev.cid == AG_NONE || cur.cid == AG_NONE || prev.cid == AG_CM_MANY || cur.cid == AG_CM_MANY) return 1u;
+    return (prev.cid == cur.cid && cur.coff == prev.coff + 1) ? 0u : 1u;
+}
+AG_HD void ag_fast_classify(ag_fast& f, const ag_alnp& p, const u32* many_prefix, const u32* lin_prefix, const ag_cm1* cm1) {
+    if (!ag_fast_is_clean(f, p, many_prefix)) return;
+    f.simple |= AG_FAST_CLEAN;
+    // mate positions the touches look at (as in ag_fast_is_clean): r_dst + (q - mlo) for q in [lo, lo + span] with 0 <= q - mlo < mlen
+    const long long mlo = (long long)f.lo + (long long)(p.r_sl & 0xFFFFu) - (long long)(p.l_sl & 0xFFFFu);
+    const long long qa = (long long)f.lo > mlo ? (long long)f.lo : mlo;
+    const long long qe = (long long)f.lo + f.span, me = mlo + (long long)f.mlen - 1;
+    const long long qb = qe < me ? qe : me;
+    if (qa > qb) { f.simple |= AG_FAST_LINEAR; f.mcid0 = AG_NONE; f.mcd = 0; return; }   // no touch has a mate position
+    const u32 a = p.r_dst + (u32)(qa - mlo), b = p.r_dst + (u32)(qb - mlo);
+    if (lin_prefix[b + 1] != lin_prefix[a + 1]) return;                                   // a break inside (a, b]
+    const ag_cm1 c = cm1[a];
+    f.simple |= AG_FAST_LINEAR; f.mcid0 = c.cid;
+    f.mcd = c.cid == AG_NONE ? 0u : f.mdelta + c.coff - a;                                // coff0 of the touch at q = c.coff + (q + mdelta - a)
+}
+
 // Enumerate the candidates of a touch at `pos` with mate position `mate` in the reference's order: contiMers at pos (outer) x
 // contiMers at the mate position (inner); an empty side contributes one "-1" entry (AG:1369-1477).
 template <class F> AG_HD void ag_for_candidates(const ag_cmtab& t, u32 pos, u32 mate, F f) {
@@ -416,7 +451,7 @@ AG_HD bool ag_compat23(u32 cid0, u32 coff0, u32 moff, u32 ycid0, u32 ycoff0, u32
 // whole sweep is repeated with a larger pool)
 AG_HD u32 ag_pool_new(ag_plist& pl, const ag_ovfpool& pool, const ag_nodem& c, bool bump, int code, u32 sread, u32 soff_len) {
     u32 o = AG_ATOMIC_ADD(pool.count, 1u);
-    if (o >= pool.cap) { *pool.err = 1; return AG_NONE; }
+    if (o >= pool.cap) { AG_ATOMIC_OR(pool.err, 1); return AG_NONE; }   // bit E_OVF of the step's error word
     pool.next[o] = AG_NONE;
     if (pl.ovf_tail == AG_NONE) pl.ovf_head = o; else pool.next[pl.ovf_tail] = o;
     pl.ovf_tail = o;
@@ -517,7 +552,10 @@ AG_HD u32 ag_lane_touch(bool& want, ag_plist& pl, const ag_slots& sv, const ag_o
         // the common case: one M segment per mate and at most one contiMer at q and at the mate position => exactly one candidate
         const u32 mate = ag_fast_mate(f, q);
         ag_nodem c; c.cid = ca.cid; c.coff = ca.coff; c.cid0 = c.coff0 = AG_NONE; c.moff = mate;
-        if (mate != AG_NONE) { const ag_cm1 cb = cm1[mate]; c.cid0 = cb.cid; c.coff0 = cb.coff; }
+        if (mate != AG_NONE) {
+            if (f.simple & AG_FAST_LINEAR) { c.cid0 = f.mcid0; c.coff0 = f.mcid0 != AG_NONE ? q + f.mcd : AG_NONE; }
+            else { const ag_cm1 cb = cm1[mate]; c.cid0 = cb.cid; c.coff0 = cb.coff; }
+        }
         const u32 d = q - f.lo, len = f.lsrc_len >> 16, a = (f.lsrc_len & 0xFFFFu) + d;
         const bool bump = d < f.span;                             // a call starts here (kind 1); else the stand-alone k2 of the last call
         const u32 slen = bump ? k : ag_min_u32(k, len - a);

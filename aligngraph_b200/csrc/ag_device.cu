@@ -123,8 +123,9 @@ struct Scanner {
 // ---------------------------------------------------------------------------------------------------------------------------
 constexpr int RS_T = 256, RS_I = 8, RS_B = RS_T * RS_I, RS_BITS = 5, RS_BINS = 1 << RS_BITS;
 
-__global__ void k_rs_hist(const u32* __restrict__ keys, u32* __restrict__ hist, size_t n, int shift, unsigned nb) {
+__global__ void k_rs_hist(const u32* __restrict__ keys, u32* __restrict__ hist, const u32* __restrict__ n_ptr, u32 cap, int shift, unsigned nb) {
     __shared__ u32 h[RS_BINS];
+    const size_t n = min(*n_ptr, cap);   // (more keys than the buffers hold: E_KEY_CAP is set, the step is repeated)
     if (threadIdx.x < RS_BINS) h[threadIdx.x] = 0;
     __syncthreads();
     size_t base = (size_t)blockIdx.x * RS_B;
@@ -134,7 +135,8 @@ __global__ void k_rs_hist(const u32* __restrict__ keys, u32* __restrict__ hist, 
 }
 
 __global__ void k_rs_scatter(const u32* __restrict__ keys, const u32* __restrict__ vals, u32* __restrict__ okeys, u32* __restrict__ ovals,
-                             const u32* __restrict__ hist_scanned, size_t n, int shift, unsigned nb) {
+                             const u32* __restrict__ hist_scanned, const u32* __restrict__ n_ptr, u32 cap, int shift, unsigned nb) {
+    const size_t n = min(*n_ptr, cap);
     // counters in flat (digit, thread) order, f = digit * RS_T + thread, stored skewed by one word per 32 so that both access patterns —
     // [digit][thread] while counting / ranking and "thread t owns flat entries [RS_BINS t, RS_BINS t + RS_BINS)" in the scan — are
     // free of bank conflicts
@@ -174,10 +176,18 @@ namespace {
 // ---------------------------------------------------------------------------------------------------------------------------
 // device view of one unit
 // ---------------------------------------------------------------------------------------------------------------------------
+// error word of a step (bits, set with atomicOr; read once at the step's single synchronisation point)
+enum : int { E_OVF = 1, E_BAD_ALN = 2, E_NODE_CAP = 4, E_EDGE_OVF = 8, E_WALK_CAP = 16, E_MAT_CAP = 32, E_CM = 64, E_KEY_CAP = 128, E_CAND_CAP = 256, E_HWALK_CAP = 512, E_RANK_MORE = 1024 };
+// fixed launch geometry of the loops over nodes / candidates whose trip count only the device knows
+constexpr unsigned GS_BLOCKS = 148 * 8, GS_T = 256;
+constexpr int E_FATAL = E_OVF | E_NODE_CAP | E_EDGE_OVF | E_CM | E_KEY_CAP | E_CAND_CAP | E_RANK_MORE;   // the step is repeated with larger capacities: later kernels skip their work
+#define AG_BAIL(d) do { if (*(volatile int*)(d).err & E_FATAL) return; } while (0)
+#define AG_FOR_N(v, n) for (u32 v = blockIdx.x * blockDim.x + threadIdx.x, n_ = (n), s_ = gridDim.x * blockDim.x; v < n_; v += s_)
+
 struct DevView {
     ag_reads reads;
     const unsigned char* ref; u32 n_ref, n_pos;
-    ag_cmtab cmt; const ag_cm1* cm1; const u32* many_prefix; const u32* chain_pos; const unsigned char* chain_base;
+    ag_cmtab cmt; const ag_cm1* cm1; const u32* many_prefix; const u32* lin_prefix; const u32* chain_pos; const unsigned char* chain_base;
     const ag_aln* aln; u32 n_aln; const ag_seg* ext;
     ag_alnp* alnp; ag_fast* fast; u32* ntiles; u32* key_off;
     u32* keys; u32* vals; u32* tile_cnt; u32* tile_start; u32 n_tiles;
@@ -193,6 +203,11 @@ struct DevView {
     ag_walk* walks; ag_walk* walks_sorted; u32* walk_count; u32 walk_cap; u32* walk_used;
     int* err;
     int k, iv, coverage;
+    const int* err_load;                   // error word of the unit upload (contig thread kernels)
+    const u32* nk_ptr; u32 key_cap;        // number of tile keys (device), capacity of the key buffers
+    const u32* nn_ptr;                     // number of nodes (device) = pool_count
+    const u32* ncand_ptr; u32 cand_cap;    // number of walk start candidates (device), capacity of the per-candidate arrays
+    ag_walk* walks_host; u32 hwalk_cap;    // page-locked host buffer the compacted walk records are written to
     u32 rw;  // words per staged read (stride2 + stridem) when the tile sweeps keep the chunk's reads in shared memory, else 0
 };
 
@@ -211,9 +226,9 @@ __global__ void k_prep(DevView d) {
     for (u32 j = 0; j < L.n; j++) { ag_seg s = L.get(j); if (s.dst + s.len > d.n_ref || s.src + s.len > len) bad = true; }
     for (u32 j = 0; j < R.n; j++) { ag_seg s = R.get(j); if (s.dst + s.len > d.n_ref || s.src + s.len > len) bad = true; }
     if (o.any && o.lo + o.span >= d.n_ref) bad = true;
-    if (bad) { *d.err = 2; o.any = 0; }
-    ag_fast f = ag_fast_prep(o.p, o.lo, o.span);
-    if (o.any && ag_fast_is_clean(f, o.p, d.many_prefix)) f.simple |= AG_FAST_CLEAN;
+    if (bad) { atomicOr(d.err, E_BAD_ALN); o.any = 0; }
+    ag_fast f = ag_fast_prep(o.p, o.lo, o.span, i);
+    if (o.any) ag_fast_classify(f, o.p, d.many_prefix, d.lin_prefix, d.cm1);
     d.alnp[i] = o.p; d.fast[i] = f;
     u32 nt = 0;
     if (o.any) { u32 t0, t1; ag_tile_range(o.lo, o.lo + o.span, d.n_tiles, t0, t1); nt = t1 - t0 + 1; }
@@ -228,6 +243,7 @@ __global__ void k_keys(DevView d) {
     const ag_fast f = d.fast[i];
     u32 t0, t1; ag_tile_range(f.lo, f.lo + f.span, d.n_tiles, t0, t1);
     u32 off = d.key_off[i];
+    if ((u64)off + n > d.key_cap) { atomicOr(d.err, E_KEY_CAP); return; }
     for (u32 j = 0; j < n; j++) { d.keys[off + j] = t0 + j; d.vals[off + j] = i; atomicAdd(&d.tile_cnt[t0 + j], 1u); }
 }
 
@@ -248,7 +264,7 @@ __global__ void k_cm_count(const u32* __restrict__ chain_pos, u32 n_cm, u32 n_po
     u32 k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_cm) return;
     u32 p = chain_pos[k];
-    if (p >= n_pos) { *err = 7; return; }
+    if (p >= n_pos) { atomicOr(err, E_CM); return; }
     atomicAdd(&cnt[p], 1u);
 }
 __global__ void k_cm_fill(const u32* __restrict__ chain_pos, u32 n_cm, const ag_cthread* __restrict__ th, u32 n_th, const u32* __restrict__ cm_start, u32* fill, ag_cm* cm, int* err) {
@@ -257,7 +273,7 @@ __global__ void k_cm_fill(const u32* __restrict__ chain_pos, u32 n_cm, const ag_
     u32 lo = 0, hi = n_th;   // last thread with first <= k
     while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (th[mid].first <= k) lo = mid; else hi = mid; }
     const ag_cthread t = th[lo];
-    if (n_th == 0 || k < t.first || k > t.term) { *err = 7; return; }
+    if (n_th == 0 || k < t.first || k > t.term) { atomicOr(err, E_CM); return; }
     const u32 p = chain_pos[k];
     ag_cm m; m.cid = t.cid; m.coff = k < t.term ? t.coff_first + (k - t.first) : t.coff_term; m.chain = k; m.term = t.term;
     cm[cm_start[p] + atomicAdd(&fill[p], 1u)] = m;
@@ -299,11 +315,12 @@ __global__ void k_chain_expand(const ag_cdesc* __restrict__ desc, u32 n_desc, co
 // ---------------------------------------------------------------------------------------------------------------------------
 // k_cm1: per-position summary of the contiMer table (one 8-byte load per lookup in the sweeps)
 // ---------------------------------------------------------------------------------------------------------------------------
-__global__ void k_cm1(DevView d, ag_cm1* out, unsigned char* pos_term, u32* many) {
+__global__ void k_cm1(DevView d, ag_cm1* out, unsigned char* pos_term, u32* many, u32* brk) {
     u32 p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= d.n_pos) return;
     const ag_cm1 c = ag_make_cm1(d.cmt, p);
     out[p] = c; many[p] = c.cid == AG_CM_MANY ? 1u : 0u;
+    brk[p] = p ? ag_cm1_break(ag_make_cm1(d.cmt, p - 1), c) : 0u;
     unsigned char t = 0;
     for (u32 e = d.cmt.start[p]; e < d.cmt.start[p + 1]; e++) if (d.cmt.cm[e].chain == d.cmt.cm[e].term) t = 1;
     pos_term[p] = t;
@@ -362,6 +379,7 @@ __global__ void __launch_bounds__(AG_TILE, AG_NODES_MINB) k_build(DevView d) {
     __shared__ u32 s_scan[33];
     __shared__ u32 s_base, s_flag;
     constexpr u32 READS0 = AG_NF * NODE_SCAP * AG_TILE;             // word offset of the staged reads inside s_dyn
+    if (*(volatile int*)d.err & E_KEY_CAP) return;                 // incomplete key list: the step is repeated with a larger key buffer
     const u32 tile = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 wq0 = tile * AG_TPOS + warp * AG_WPOS, q = wq0 + lane;   // lane 31 = halo: first position of the next warp / tile
     const bool active = q < d.n_ref, owner = active && lane < AG_WPOS;
@@ -444,7 +462,147 @@ __global__ void __launch_bounds__(AG_TILE, AG_NODES_MINB) k_build(DevView d) {
         u32 b = total ? atomicAdd(d.pool_count, total) : 0u;
         d.tile_base[tile] = b; d.tile_nodes[tile] = total;
         if (s_flag) d.tile_flag[tile] = s_flag;
-        if (total && (unsigned long long)b + total > d.node_cap) { *d.err = 3; b = AG_NONE; }
+        if (total && (unsigned long long)b + total > d.node_cap) { atomicOr(d.err, E_NODE_CAP); b = AG_NONE; }
+        s_base = b;
+    }
+    __syncthreads();
+    if (!owner) return;
+    if (s_base == AG_NONE) { d.pos_pool[q] = 0; return; }
+    u32 v = s_base + ex;
+    d.pos_pool[q] = v;
+    if (!pl.n) return;
+    const char refb = (char)d.ref[q];
+    if (ca.cid != AG_CM_MANY) {
+        const u32 nloc = pl.n < (u32)NODE_SCAP ? pl.n : (u32)NODE_SCAP;
+        for (u32 i = 0; i < nloc; i++, v++) {
+            u32 cnt[5];
+            for (u32 j = 0; j < 5; j++) cnt[j] = sv.ld(AG_F_CNT + j, i);
+            emit_node(d, v, q, refb, ca.cid, ca.coff, sv.ld(AG_F_CID0, i), sv.ld(AG_F_COFF0, i), sv.ld(AG_F_MOFF, i), sv.ld(AG_F_COV, i), cnt, sv.ld(AG_F_SREAD, i),
+                      sv.ld(AG_F_SL, i), sv.ld(AG_F_SUCC, i));
+        }
+    }
+    for (u32 o = pl.ovf_head; o != AG_NONE; o = d.ovf.next[o], v++) {
+        const ag_nodeb b = d.ovf.node[o];
+        emit_node(d, v, q, refb, b.cid, b.coff, b.cid0, b.coff0, b.moff, b.cov, b.cnt, b.sread, b.soff_len, b.succ);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// k_stage + k_build_tma: the node sweep fed by bulk-asynchronous (TMA) copies.
+//   k_stage gathers, per tile key in sorted order, everything the sweep needs about that alignment into ONE contiguous record: the 48-byte
+//   prepared header (ag_fast) followed by the left mate as ORIENTED 4-bit codes, eight per word (ag_code4_word).  A tile's records are then
+//   a single contiguous, 16-byte aligned byte range, which k_build_tma brings into shared memory with cp.async.bulk (1-D TMA) signalled
+//   through an mbarrier — two chunks in flight — instead of every thread chasing vals -> fast -> reads with dependent scalar loads.  The
+//   base of a touch is one shift + mask on a staged word; the mate-side match fields of a LINEAR alignment are register arithmetic.
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr int ST_CH = 48;                    // records per staged chunk (two chunks resident)
+constexpr int ST_HDR_W = 12;                 // header words (sizeof(ag_fast) / 4)
+static_assert(sizeof(ag_fast) == ST_HDR_W * 4, "staged header = ag_fast");
+
+__global__ void k_stage(DevView d, u32* __restrict__ stage, u32 rsw) {
+    if (*(volatile int*)d.err & E_KEY_CAP) return;
+    const ag_reads rd = d.reads;
+    AG_FOR_N(i, min(*d.nk_ptr, d.key_cap)) {
+        const u32 idx = d.vals[i];
+        const uint4* src = reinterpret_cast<const uint4*>(d.fast + idx);
+        uint4* dst = reinterpret_cast<uint4*>(stage + (size_t)i * rsw);
+        const uint4 h0 = src[0], h1 = src[1], h2 = src[2];
+        dst[0] = h0; dst[1] = h1; dst[2] = h2;
+        const u32 read_rc = h1.z, len = h0.z >> 16, read = read_rc >> 1;
+        const u32* b = rd.bases + (u64)read * rd.stride2; const u32* mk = rd.nmask + (u64)read * rd.stridem;
+        u32* cw = stage + (size_t)i * rsw + ST_HDR_W;
+        const u32 nw = (len + 7) >> 3;
+        for (u32 j = 0; j < rsw - ST_HDR_W; j += 4) {
+            uint4 w;
+            w.x = j + 0 < nw ? ag_code4_word(b, mk, rd.stride2, rd.stridem, read_rc & 1, len, j + 0) : 0u;
+            w.y = j + 1 < nw ? ag_code4_word(b, mk, rd.stride2, rd.stridem, read_rc & 1, len, j + 1) : 0u;
+            w.z = j + 2 < nw ? ag_code4_word(b, mk, rd.stride2, rd.stridem, read_rc & 1, len, j + 2) : 0u;
+            w.w = j + 3 < nw ? ag_code4_word(b, mk, rd.stride2, rd.stridem, read_rc & 1, len, j + 3) : 0u;
+            *reinterpret_cast<uint4*>(cw + j) = w;
+        }
+    }
+}
+
+__device__ __forceinline__ void mbar_init(u32 bar, u32 count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(u32 bar, u32 bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(u32 dst_smem, const void* src, u32 bytes, u32 bar) {   // 1-D TMA: global -> shared, completion counted in bytes on the mbarrier
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" :: "r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(AG_TILE, AG_NODES_MINB) k_build_tma(DevView d, const u32* __restrict__ stage, u32 rsw) {
+    extern __shared__ __align__(128) u32 s_dyn[];                   // [AG_NF][NODE_SCAP][AG_TILE] node slots, then 2 x [ST_CH][rsw] staged records
+    __shared__ __align__(8) unsigned long long s_bar[2];
+    __shared__ u32 s_scan[33];
+    __shared__ u32 s_base, s_flag;
+    if (*(volatile int*)d.err & E_KEY_CAP) return;
+    constexpr u32 STAGE0 = AG_NF * NODE_SCAP * AG_TILE;             // word offset of the staged chunks inside s_dyn (a multiple of 4 words)
+    const u32 tile = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 wq0 = tile * AG_TPOS + warp * AG_WPOS, q = wq0 + lane;   // lane 31 = halo: first position of the next warp / tile
+    const bool active = q < d.n_ref, owner = active && lane < AG_WPOS;
+    const u32 kb = d.tile_start[tile], ke = d.tile_start[tile + 1];
+    const u32 nchunks = (ke - kb + ST_CH - 1) / ST_CH;
+    const u32 bar0 = (u32)__cvta_generic_to_shared(&s_bar[0]), stage_s = (u32)__cvta_generic_to_shared(s_dyn + STAGE0);
+    const u32 chunk_bytes = ST_CH * rsw * 4;
+    auto issue = [&](u32 c) {   // one elected thread: arm the chunk's barrier with its byte count, start the bulk copy
+        const u32 n = min((u32)ST_CH, ke - (kb + c * ST_CH)), bytes = n * rsw * 4, bar = bar0 + 8 * (c & 1);
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(stage_s + (c & 1) * chunk_bytes, stage + (size_t)(kb + c * ST_CH) * rsw, bytes, bar);
+    };
+    if (threadIdx.x == 0) {
+        s_flag = 0;
+        mbar_init(bar0, 1); mbar_init(bar0 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { if (nchunks > 0) issue(0); if (nchunks > 1) issue(1); }
+    ag_slots sv; sv.saddr = (u32)__cvta_generic_to_shared(s_dyn + threadIdx.x);
+    ag_plist pl; pl.n = 0; pl.ovf_head = pl.ovf_tail = AG_NONE;
+    ag_cm1 ca; ca.cid = ca.coff = AG_NONE;
+    if (active) ca = d.cm1[q];
+    const u32 kmer = (u32)d.k;
+    for (u32 c = 0; c < nchunks; c++) {
+        const u32 cn = min((u32)ST_CH, ke - (kb + c * ST_CH));
+        mbar_wait(bar0 + 8 * (c & 1), (c >> 1) & 1);
+        const u32* buf = s_dyn + STAGE0 + (c & 1) * (ST_CH * rsw);
+        for (u32 r0 = 0; r0 < cn; r0 += 32) {
+            // which of these 32 records touch any of the warp's 32 positions?
+            bool ov = false;
+            if (r0 + lane < cn) { const uint2 ls = *reinterpret_cast<const uint2*>(buf + (r0 + lane) * rsw); ov = ls.x <= wq0 + 31 && ls.x + ls.y >= wq0; }
+            u32 mask = __ballot_sync(0xFFFFFFFFu, ov);
+            while (mask) {
+                const u32 a = r0 + (u32)__ffs((int)mask) - 1;
+                mask &= mask - 1;
+                const u32* rec = buf + a * rsw;
+                const ag_fast& f = *reinterpret_cast<const ag_fast*>(rec);   // fields are read from shared memory where they are used
+                u32 item = AG_NONE; bool want = false;
+                if (active && q - f.lo <= f.span) {
+                    const u32* cw = rec + ST_HDR_W;
+                    auto codef = [=](u32 soff) -> int { return (int)((cw[soff >> 3] >> ((soff & 7) * 4)) & 7u); };
+                    item = ag_lane_touch(want, pl, sv, d.ovf, d.cmt, d.cm1, ca, f, d.alnp + f.aln, d.ext, q, kmer, d.iv, false, codef);
+                }
+                // the call that starts at q continues on the item the next lane resolved for this alignment
+                const u32 nb = __shfl_down_sync(0xFFFFFFFFu, item, 1);
+                if (want && lane < AG_WPOS) {
+                    if (item != AG_NONE && nb < 32u) ag_note_succ(pl, sv, d.ovf, item, nb);
+                    else atomicOr(&s_flag, item == AG_NONE ? 1u : 2u);   // 1: not a clean alignment; 2: successor item does not fit the mask
+                }
+            }
+        }
+        if (c + 2 < nchunks) {   // everybody is done with this buffer: refill it with the chunk after next
+            __syncthreads();
+            if (threadIdx.x == 0) issue(c + 2);
+        }
+    }
+    // ---- the tile's nodes go out as one block at an atomically reserved offset ----
+    u32 total; const u32 ex = block_excl_scan(owner ? pl.n : 0u, s_scan, total);
+    if (threadIdx.x == 0) {
+        u32 b = total ? atomicAdd(d.pool_count, total) : 0u;
+        d.tile_base[tile] = b; d.tile_nodes[tile] = total;
+        if (s_flag) d.tile_flag[tile] = s_flag;
+        if (total && (unsigned long long)b + total > d.node_cap) { atomicOr(d.err, E_NODE_CAP); b = AG_NONE; }
         s_base = b;
     }
     __syncthreads();
@@ -473,43 +631,46 @@ __global__ void __launch_bounds__(AG_TILE, AG_NODES_MINB) k_build(DevView d) {
 // k_posfix / k_succ: tile blocks -> position order (final index = block's rank offset + index inside the block), successor-item
 // bits -> successor node indices, subject to the contig-consistency predicate of AG:1600-1615
 // ---------------------------------------------------------------------------------------------------------------------------
-__global__ void k_posfix(DevView d, u32 n_nodes) {
+__global__ void k_posfix(DevView d) {
     const u32 q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q > d.n_pos) return;
+    AG_BAIL(d);
+    const u32 n_nodes = min(*d.nn_ptr, d.node_cap);
     if (q >= d.n_ref) { d.pos_node[q] = n_nodes; return; }   // the contig-insertion positions behind the unit hold no nodes
     const u32 t = q / AG_TPOS;
     d.pos_node[q] = d.pos_pool[q] - d.tile_base[t] + d.tile_prefix[t];
 }
-__global__ void k_succ(DevView d, u32 n_nodes) {
-    const u32 v = blockIdx.x * blockDim.x + threadIdx.x;   // index in sweep order
-    if (v >= n_nodes) return;
-    const u32 q = d.pool_pos[v], t = q / AG_TPOS;
-    const u32 f = v - d.tile_base[t] + d.tile_prefix[t];   // index in position order
-    ag_nodew w = d.pool_w[v];
-    const ag_nodec x = d.pool_c[v];
-    u32 mask = w.succ0, head = AG_NONE;
-    w.succ0 = AG_NONE;
-    if (mask) {
-        const u32 p1 = d.pos_pool[q + 1], f1 = d.pos_node[q + 1];
-        while (mask) {
-            const u32 j = (u32)__ffs((int)mask) - 1;
-            mask &= mask - 1;
-            if (!ag_edge_ok_c(x, d.pool_c[p1 + j], d.iv)) continue;
-            const u32 tg = f1 + j;
-            if (w.succ0 == AG_NONE) w.succ0 = tg;
-            else if (w.succ1 == AG_NONE) w.succ1 = tg;
-            else {
-                const u32 o = atomicAdd(d.eovf_count, 1u);
-                if (o >= d.eovf_cap) { *d.err = 4; break; }
-                d.eovf_target[o] = tg; d.eovf_next[o] = head; head = o;
-                w.misc |= AG_NW_OVF;
+__global__ void k_succ(DevView d) {
+    AG_BAIL(d);
+    AG_FOR_N(v, min(*d.nn_ptr, d.node_cap)) {   // v: index in sweep order
+        const u32 q = d.pool_pos[v], t = q / AG_TPOS;
+        const u32 f = v - d.tile_base[t] + d.tile_prefix[t];   // index in position order
+        ag_nodew w = d.pool_w[v];
+        const ag_nodec x = d.pool_c[v];
+        u32 mask = w.succ0, head = AG_NONE;
+        w.succ0 = AG_NONE;
+        if (mask) {
+            const u32 p1 = d.pos_pool[q + 1], f1 = d.pos_node[q + 1];
+            while (mask) {
+                const u32 j = (u32)__ffs((int)mask) - 1;
+                mask &= mask - 1;
+                if (!ag_edge_ok_c(x, d.pool_c[p1 + j], d.iv)) continue;
+                const u32 tg = f1 + j;
+                if (w.succ0 == AG_NONE) w.succ0 = tg;
+                else if (w.succ1 == AG_NONE) w.succ1 = tg;
+                else {
+                    const u32 o = atomicAdd(d.eovf_count, 1u);
+                    if (o >= d.eovf_cap) { atomicOr(d.err, E_EDGE_OVF); break; }
+                    d.eovf_target[o] = tg; d.eovf_next[o] = head; head = o;
+                    w.misc |= AG_NW_OVF;
+                }
             }
         }
+        if (head != AG_NONE) d.eovf_head[f] = head;
+        d.node_c[f] = x; d.node_w[f] = w; d.node_pos[f] = q;
+        *reinterpret_cast<uint2*>(d.node_sref + 2 * (size_t)f) = *reinterpret_cast<const uint2*>(d.pool_sref + 2 * (size_t)v);
+        if (d.node_cc) for (int j = 0; j < 6; j++) d.node_cc[6 * (size_t)f + j] = d.pool_cc[6 * (size_t)v + j];
     }
-    if (head != AG_NONE) d.eovf_head[f] = head;
-    d.node_c[f] = x; d.node_w[f] = w; d.node_pos[f] = q;
-    *reinterpret_cast<uint2*>(d.node_sref + 2 * (size_t)f) = *reinterpret_cast<const uint2*>(d.pool_sref + 2 * (size_t)v);
-    if (d.node_cc) for (int j = 0; j < 6; j++) d.node_cc[6 * (size_t)f + j] = d.pool_cc[6 * (size_t)v + j];
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -523,7 +684,7 @@ __device__ __forceinline__ void add_edge(const DevView& d, u32 v, u32 tgt) {
     if (w->succ1 == AG_NONE) { w->succ1 = tgt; return; }
     if (w->misc & AG_NW_OVF) { for (u32 o = d.eovf_head[v]; o != AG_NONE; o = d.eovf_next[o]) if (d.eovf_target[o] == tgt) return; }
     u32 o = atomicAdd(d.eovf_count, 1u);
-    if (o >= d.eovf_cap) { *d.err = 4; return; }
+    if (o >= d.eovf_cap) { atomicOr(d.err, E_EDGE_OVF); return; }
     d.eovf_target[o] = tgt;
     d.eovf_next[o] = (w->misc & AG_NW_OVF) ? d.eovf_head[v] : AG_NONE;
     d.eovf_head[v] = o;
@@ -546,6 +707,7 @@ __global__ void __launch_bounds__(AG_TILE, AG_EDGES_MINB) k_edges(DevView d) {
     const u32 tile = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 tflag = d.tile_flag[tile];
     if (!tflag) return;
+    AG_BAIL(d);
     const bool all = (tflag & 2u) != 0;                   // else: only the alignments that are not clean
     const u32 wq0 = tile * AG_TPOS + warp * AG_WPOS, q = wq0 + lane;
     u32 nb0 = 0, nn0 = 0;
@@ -617,18 +779,17 @@ __device__ __forceinline__ void uf_unite(u32* parent, u32 a, u32 b) {
     }
 }
 
-__global__ void k_uf_init(DevView d, u32 n_nodes) {
-    u32 v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= n_nodes) return;
-    d.parent[v] = v; d.cmin[v] = AG_NONE; d.cmax[v] = 0; d.walk_next[v] = AG_NONE; d.fprev[v] = AG_NONE;
+__global__ void k_uf_init(DevView d) {
+    AG_BAIL(d);
+    AG_FOR_N(v, *d.nn_ptr) { d.parent[v] = v; d.cmin[v] = AG_NONE; d.cmax[v] = 0; d.walk_next[v] = AG_NONE; d.fprev[v] = AG_NONE; d.indeg[v] = 0; }
 }
 // Components over chain TAILS.  Only a chain's tail has live successors outside its chain and only a tail can
 // leave through a contiMer detour (interior nodes always see exactly one untraversed successor), so the relations a walk can follow are:
 // tail -> chains of its live successors (AG:2022-2032) and tail -> chains of the live nodes at its detour's terminal position
 // (AG:2093-2114).  One thread per start candidate (= chain head), ~1/66 of the nodes.
-__global__ void k_uf_tails(DevView d, u32 n_cand) {
-    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_cand) return;
+__global__ void k_uf_tails(DevView d) {
+    AG_BAIL(d);
+    AG_FOR_N(i, *d.ncand_ptr) {
     const u32 t = d.chain[d.cand_node[i]].tail;
     const ag_nodew w = d.node_w[t];
     if (w.succ0 != AG_NONE && !(d.node_w[w.succ0].misc & AG_NW_FILTERED)) uf_unite(d.parent, t, d.chain[w.succ0].tail);
@@ -636,18 +797,20 @@ __global__ void k_uf_tails(DevView d, u32 n_cand) {
     if (w.misc & AG_NW_OVF)
         for (u32 o = d.eovf_head[t]; o != AG_NONE; o = d.eovf_next[o]) { u32 s = d.eovf_target[o]; if (!(d.node_w[s].misc & AG_NW_FILTERED)) uf_unite(d.parent, t, d.chain[s].tail); }
     const u32 p = d.node_pos[t], c0 = d.cmt.start[p];
-    if (d.cmt.start[p + 1] - c0 != 1) return;
+    if (d.cmt.start[p + 1] - c0 != 1) continue;
     const ag_cm m = d.cmt.cm[c0];
-    if (m.chain == m.term) return;
+    if (m.chain == m.term) continue;
     const u32 z = d.chain_pos[m.term];
     for (u32 x = d.pos_node[z]; x < d.pos_node[z + 1]; x++) if (!(d.node_w[x].misc & AG_NW_FILTERED)) uf_unite(d.parent, t, d.chain[x].tail);
+    }
 }
-__global__ void k_uf_flatten(DevView d, u32 n_cand) {
-    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_cand) return;
-    u32 r = uf_find(d.parent, d.chain[d.cand_node[i]].tail);
-    d.cand_label[i] = r;
-    atomicMin(&d.cmin[r], i); atomicMax(&d.cmax[r], i);
+__global__ void k_uf_flatten(DevView d) {
+    AG_BAIL(d);
+    AG_FOR_N(i, *d.ncand_ptr) {
+        u32 r = uf_find(d.parent, d.chain[d.cand_node[i]].tail);
+        d.cand_label[i] = r;
+        atomicMin(&d.cmin[r], i); atomicMax(&d.cmax[r], i);
+    }
 }
 
 __device__ __forceinline__ ag_walkctx make_ctx(const DevView& d) {
@@ -658,48 +821,55 @@ __device__ __forceinline__ ag_walkctx make_ctx(const DevView& d) {
 }
 __device__ __forceinline__ void push_walk(const DevView& d, ag_walk r) {
     u32 o = atomicAdd(d.walk_count, 1u);
-    if (o >= d.walk_cap) { *d.err = 5; return; }
+    if (o >= d.walk_cap) { atomicOr(d.err, E_WALK_CAP); return; }
     r.tail_sread = d.node_sref[2 * (size_t)r.last_node]; r.tail_soff_len = d.node_sref[2 * (size_t)r.last_node + 1];
     d.walks[o] = r;
 }
 
 // ---- forced-link chains: in-degrees, links, list ranking (Wyllie pointer jumping, double-buffered) ------------------------------
-__global__ void k_indeg(DevView d, u32 n_nodes) {
-    u32 v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= n_nodes) return;
+__global__ void k_indeg(DevView d) {
+    AG_BAIL(d);
+    AG_FOR_N(v, *d.nn_ptr) {
     ag_nodew w = d.node_w[v];
-    if (w.misc & AG_NW_FILTERED) return;
+    if (w.misc & AG_NW_FILTERED) continue;
     if (w.succ0 != AG_NONE && !(d.node_w[w.succ0].misc & AG_NW_FILTERED)) atomicAdd(&d.indeg[w.succ0], 1u);
     if (w.succ1 != AG_NONE && !(d.node_w[w.succ1].misc & AG_NW_FILTERED)) atomicAdd(&d.indeg[w.succ1], 1u);
     if (w.misc & AG_NW_OVF) for (u32 o = d.eovf_head[v]; o != AG_NONE; o = d.eovf_next[o]) { u32 s = d.eovf_target[o]; if (!(d.node_w[s].misc & AG_NW_FILTERED)) atomicAdd(&d.indeg[s], 1u); }
+    }
 }
-__global__ void k_links(DevView d, u32 n_nodes) {
-    u32 v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= n_nodes) return;
+__global__ void k_links(DevView d) {
+    AG_BAIL(d);
+    AG_FOR_N(v, *d.nn_ptr) {
     u32 w = ag_forced_succ(d.node_w, d.eovf_head, d.eovf_target, d.eovf_next, d.indeg, d.pos_term, d.node_pos, v);
     d.fnext[v] = w;
     if (w != AG_NONE) { atomicOr(&d.node_w[w].misc, AG_NW_INTERIOR); d.fprev[w] = v; }
     ag_chain c; c.jump = w; c.tail = v; c.len = 1; c.flg = (d.node_w[v].misc & AG_NW_HASCONTIG) ? 1u : 0u;
     d.chain_a[v] = c;
-}
-__global__ void k_rank(const ag_chain* __restrict__ in, ag_chain* __restrict__ out, u32 n_nodes, int* changed) {
-    u32 v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= n_nodes) return;
-    ag_chain c = in[v];
-    if (c.jump != AG_NONE) {
-        ag_chain j = in[c.jump];
-        c.len += j.len; c.flg += j.flg; c.tail = j.tail; c.jump = j.jump;
-        if (c.jump != AG_NONE) *changed = 1;
     }
-    out[v] = c;
+}
+// one global pointer-jumping round (double-buffered); `last`: a record that is still open afterwards asks for more rounds (E_RANK_MORE:
+// the step is repeated with a larger round count, remembered by the context)
+__global__ void k_rank(const ag_chain* __restrict__ in, ag_chain* __restrict__ out, const u32* __restrict__ nn_ptr, int* err, int last) {
+    if (*(volatile int*)err & (E_FATAL & ~E_RANK_MORE)) return;
+    AG_FOR_N(v, *nn_ptr) {
+        ag_chain c = in[v];
+        if (c.jump != AG_NONE) {
+            ag_chain j = in[c.jump];
+            c.len += j.len; c.flg += j.flg; c.tail = j.tail; c.jump = j.jump;
+            if (last && c.jump != AG_NONE) atomicOr(err, E_RANK_MORE);
+        }
+        out[v] = c;
+    }
 }
 
 // list ranking, step 1: pointer jumping inside blocks of 1024 consecutive nodes in shared memory.  Forced links point to higher node
 // indices and chains are short-range (the next node is the next position), so almost every chain is finished here; what remains are
 // links that leave the block, resolved by a few global k_rank rounds.
-__global__ void __launch_bounds__(1024) k_rank_local(ag_chain* recs, u32 n_nodes) {
+__global__ void __launch_bounds__(1024) k_rank_local(ag_chain* recs, const u32* __restrict__ nn_ptr, const int* err) {
     __shared__ ag_chain sa[1024], sb[1024];
+    const u32 n_nodes = *nn_ptr;
     const u32 b0 = blockIdx.x * 1024u, v = b0 + threadIdx.x;
+    if (b0 >= n_nodes || (*(volatile const int*)err & E_FATAL)) return;
     ag_chain c; c.jump = AG_NONE; c.tail = v; c.len = 0; c.flg = 0;
     if (v < n_nodes) c = recs[v];
     sa[threadIdx.x] = c;
@@ -717,25 +887,25 @@ __global__ void __launch_bounds__(1024) k_rank_local(ag_chain* recs, u32 n_nodes
 
 // walk starts can only be live nodes that are not chain-interior: compact them (in node order) so that a component's replay does not
 // have to step over every node of its range
-__global__ void k_cand_flag(DevView d, u32 n_nodes, u32* flag) {
-    u32 v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= n_nodes) return;
-    flag[v] = (d.node_w[v].misc & (AG_NW_FILTERED | AG_NW_INTERIOR)) ? 0u : 1u;
+__global__ void k_cand_flag(DevView d, u32* flag) {   // covers the whole node capacity: entries beyond the node count are 0 for the scan
+    const bool dead = (*(volatile int*)d.err & E_FATAL) != 0;
+    const u32 nn = dead ? 0u : *d.nn_ptr;
+    AG_FOR_N(v, d.node_cap) flag[v] = (v < nn && !(d.node_w[v].misc & (AG_NW_FILTERED | AG_NW_INTERIOR))) ? 1u : 0u;
 }
-__global__ void k_cand_scatter(DevView d, u32 n_nodes, const u32* flag) {
-    u32 v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= n_nodes || !flag[v]) return;
-    u32 i = d.cand_rank[v];
-    d.cand_node[i] = v;
+__global__ void k_cand_scatter(DevView d, const u32* flag) {
+    AG_BAIL(d);
+    if (*d.ncand_ptr > d.cand_cap) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(d.err, E_CAND_CAP); return; }
+    AG_FOR_N(v, *d.nn_ptr) if (flag[v]) d.cand_node[d.cand_rank[v]] = v;
 }
 
 // hop records of the chain heads (= start candidates)
-__global__ void k_hrec(DevView d, u32 n_cand) {
-    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_cand) return;
-    const u32 v = d.cand_node[i];
-    const ag_chain c = d.chain[v];
-    d.hrec[v] = ag_make_hrec(c, d.node_w[c.tail], d.cmt, d.node_pos[c.tail]);
+__global__ void k_hrec(DevView d) {
+    AG_BAIL(d);
+    AG_FOR_N(i, *d.ncand_ptr) {
+        const u32 v = d.cand_node[i];
+        const ag_chain c = d.chain[v];
+        d.hrec[v] = ag_make_hrec(c, d.node_w[c.tail], d.cmt, d.node_pos[c.tail]);
+    }
 }
 
 // One WARP per component (the warp of the candidate whose chain tail is the union-find root): the replay of the scan (AG:1972-1990)
@@ -744,45 +914,72 @@ __global__ void k_hrec(DevView d, u32 n_cand) {
 // pull the records the replay is going to read — walk record, hop record, position, founder string of every candidate, and the walk
 // records of the chain tails and of their successors — into L1/L2.
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
-__global__ void k_walk_components(DevView d, u32 n_cand) {
-    const u32 i0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (i0 >= n_cand) return;
-    const u32 r = d.chain[d.cand_node[i0]].tail;
-    if (d.parent[r] != r) return;
-    const u32 lo = d.cmin[r], hi = d.cmax[r];
-    if (hi - lo >= 8) {
-        for (u32 i = lo + lane; i <= hi; i += 32) {
-            if (d.cand_label[i] != r) continue;
-            const u32 v = d.cand_node[i];
-            prefetch_l1(&d.node_w[v]); prefetch_l1(&d.node_pos[v]);
-            const ag_hrec h = d.hrec[v];
-            prefetch_l1(&d.node_w[h.tail]); prefetch_l1(&d.node_pos[h.tail]); prefetch_l1(&d.walk_next[h.tail]); prefetch_l1(&d.node_sref[2 * (size_t)h.tail]);
-            if (h.ts0 != AG_NONE) prefetch_l1(&d.node_w[h.ts0]);
-            if (h.ts1 != AG_NONE) prefetch_l1(&d.node_w[h.ts1]);
+__global__ void k_walk_components(DevView d, u32* next_cand) {
+    AG_BAIL(d);
+    const u32 n_cand = *d.ncand_ptr;
+    const u32 lane = threadIdx.x & 31;
+    for (;;) {   // persistent warps (the candidate count is only known on the device) that draw candidates four at a time: a warp busy with a
+        u32 c0 = 0;   // large component does not hold back the candidates behind it
+        if (lane == 0) c0 = atomicAdd(next_cand, 4u);
+        c0 = __shfl_sync(0xFFFFFFFFu, c0, 0);
+        if (c0 >= n_cand) break;
+      for (u32 i0 = c0; i0 < min(c0 + 4u, n_cand); i0++) {
+        const u32 r = d.chain[d.cand_node[i0]].tail;
+        if (d.parent[r] != r) continue;
+        const u32 lo = d.cmin[r], hi = d.cmax[r];
+        if (hi - lo >= 8) {
+            for (u32 i = lo + lane; i <= hi; i += 32) {
+                if (d.cand_label[i] != r) continue;
+                const u32 v = d.cand_node[i];
+                prefetch_l1(&d.node_w[v]); prefetch_l1(&d.node_pos[v]);
+                const ag_hrec h = d.hrec[v];
+                prefetch_l1(&d.node_w[h.tail]); prefetch_l1(&d.node_pos[h.tail]); prefetch_l1(&d.walk_next[h.tail]); prefetch_l1(&d.node_sref[2 * (size_t)h.tail]);
+                if (h.ts0 != AG_NONE) prefetch_l1(&d.node_w[h.ts0]);
+                if (h.ts1 != AG_NONE) prefetch_l1(&d.node_w[h.ts1]);
+            }
+            __syncwarp();
+        }
+        if (lane == 0) {
+            ag_walkctx w = make_ctx(d);
+            for (u32 i = lo; i <= hi; i++) {
+                if (d.cand_label[i] != r) continue;
+                u32 v = d.cand_node[i];
+                if (d.node_w[v].misc & AG_NW_TRAV) continue;
+                d.walks[i] = ag_walk_from(w, v);   // slot = candidate index: no counter on the sequential path; k_walk_compact compacts the used slots in order
+                d.walk_used[i] = 1;
+            }
         }
         __syncwarp();
-    }
-    if (lane) return;
-    ag_walkctx w = make_ctx(d);
-    for (u32 i = lo; i <= hi; i++) {
-        if (d.cand_label[i] != r) continue;
-        u32 v = d.cand_node[i];
-        if (d.node_w[v].misc & AG_NW_TRAV) continue;
-        d.walks[i] = ag_walk_from(w, v);   // slot = candidate index: no counter on the sequential path; fetch() compacts the used slots in order
-        d.walk_used[i] = 1;
+      }
     }
 }
 
-// `key` maps a start node to its slot in scan order: the candidate index (component replay: every walk starts at a chain head, and the
-// candidates are compacted in node order) or, with key == nullptr, the node index itself (sequential replay: any node can start a walk)
-// component replay: the used slots (one per candidate that started a walk), compacted in candidate = scan order; the founder string of
-// the walk's last node is attached here, off the replay's sequential path
-__global__ void k_walk_compact(DevView d, u32 n_cand, const u32* __restrict__ rank) {
-    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_cand || !d.walk_used[i]) return;
-    ag_walk r = d.walks[i];
-    r.tail_sread = d.node_sref[2 * (size_t)r.last_node]; r.tail_soff_len = d.node_sref[2 * (size_t)r.last_node + 1];
-    d.walks_sorted[rank[i]] = r;
+// component replay: the used slots (one per candidate that started a walk), compacted in candidate = scan order (candidates are in node
+// order, so that IS the scan order of AG:1972-1990) straight into the page-locked host buffer; the founder string of the walk's last node
+// is attached here, off the replay's sequential path.  rank = exclusive scan of walk_used over the candidate capacity.
+__global__ void k_walk_compact(DevView d, const u32* __restrict__ rank) {
+    AG_BAIL(d);
+    if (rank[d.cand_cap] > d.hwalk_cap) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(d.err, E_HWALK_CAP); return; }
+    AG_FOR_N(i, *d.ncand_ptr) {
+        if (!d.walk_used[i]) continue;
+        ag_walk r = d.walks[i];
+        r.tail_sread = d.node_sref[2 * (size_t)r.last_node]; r.tail_soff_len = d.node_sref[2 * (size_t)r.last_node + 1];
+        d.walks_sorted[rank[i]] = r;
+    }
+}
+// the compacted records to the page-locked host buffer, 8 bytes per lane: full 256-byte writes over PCIe
+__global__ void k_walk_to_host(DevView d, const u32* __restrict__ rank) {
+    AG_BAIL(d);
+    const u32 nw = rank[d.cand_cap];
+    if (nw > d.hwalk_cap) return;
+    const uint2* __restrict__ src = reinterpret_cast<const uint2*>(d.walks_sorted); uint2* dst = reinterpret_cast<uint2*>(d.walks_host);
+    AG_FOR_N(i, nw * (u32)(sizeof(ag_walk) / 8)) dst[i] = src[i];
+}
+// everything the host wants to know about the step, gathered into one block for ONE device->host copy
+__global__ void k_status(DevView d, const u32* __restrict__ counters, const u32* __restrict__ walk_rank, u32* __restrict__ out) {
+    if (blockIdx.x || threadIdx.x) return;
+    out[0] = (u32)(*d.err | *d.err_load); out[1] = counters[0]; out[2] = counters[1]; out[3] = counters[2]; out[4] = *d.nk_ptr;
+    out[5] = d.ncand_ptr ? *d.ncand_ptr : 0u; out[6] = walk_rank ? walk_rank[d.cand_cap] : 0u;
 }
 
 // exact sequential replay including the 1000-position skip (AG:2194-2202); used only when a >100 kbp contig was emitted
@@ -841,7 +1038,7 @@ __global__ void k_mat_items(DevView d, const u32* __restrict__ starts, const u64
         if (d.node_w[t].misc & AG_NW_DETOUR) {
             ag_cm m = d.cmt.cm[d.cmt.start[d.node_pos[t]]];
             u32 o2 = atomicAdd(&counts[1], 1u);
-            if (o2 < cap) { MatItem it; it.a = m.chain + 1; it.n = m.term - m.chain; it.off = off; detours[o2] = it; } else *d.err = 6;
+            if (o2 < cap) { MatItem it; it.a = m.chain + 1; it.n = m.term - m.chain; it.off = off; detours[o2] = it; } else atomicOr(d.err, E_MAT_CAP);
             off += m.term - m.chain;
         }
         v = d.walk_next[t];
@@ -905,6 +1102,22 @@ struct Timer {   // section timer: CUDA events on the launching stream; the even
     float stop() { cudaEventRecord(b, st); cudaEventSynchronize(b); float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
 };
 
+// Section times without stalling the stream: an event pair per section is only RECORDED while the step is being queued; the elapsed
+// times are read after the step's single synchronisation point (collect()).
+struct SectionTimes {
+    static constexpr int MAX = 64;
+    cudaEvent_t ev[2 * MAX]; float* dst[MAX]; int n = 0, made = 0;
+    void begin(cudaStream_t st, float* where) {
+        if (n == MAX) { cudaStreamSynchronize(st); collect(); }
+        while (made <= n) { cudaEventCreate(&ev[2 * made]); cudaEventCreate(&ev[2 * made + 1]); made++; }
+        dst[n] = where; cudaEventRecord(ev[2 * n], st);
+    }
+    void end(cudaStream_t st) { cudaEventRecord(ev[2 * n + 1], st); n++; }
+    void collect() { for (int i = 0; i < n; i++) { float ms = 0; if (cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]) == cudaSuccess) *dst[i] += ms; } n = 0; }   // after a sync that covers every recorded event
+    void release() { for (int i = 0; i < 2 * made; i++) cudaEventDestroy(ev[i]); made = n = 0; }
+};
+struct Section { SectionTimes& t; cudaStream_t st; Section(SectionTimes& t_, cudaStream_t s, float* where) : t(t_), st(s) { t.begin(st, where); } ~Section() { t.end(st); } };
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -916,7 +1129,7 @@ struct AgDevice::Impl {
     DBuf<unsigned char> ref, chain_base; DBuf<u32> cm_start, chain_pos; DBuf<ag_cm> cm; DBuf<ag_cthread> cthreads; DBuf<ag_aln> aln; DBuf<ag_seg> ext;
     u32 n_ref = 0, n_pos = 0, n_cm = 0, n_aln = 0;
     // build products
-    DBuf<ag_alnp> alnp; DBuf<ag_fast> fast; DBuf<u32> ntiles, key_off, keys, vals, keys2, vals2, hist, tile_cnt, tile_start, tile_flag, many, many_prefix;
+    DBuf<ag_alnp> alnp; DBuf<ag_fast> fast; DBuf<u32> ntiles, key_off, keys, vals, keys2, vals2, hist, tile_cnt, tile_start, tile_flag, many, many_prefix, brk, lin_prefix; DBuf<u32> stage;
     DBuf<u32> tile_base, tile_nodes, tile_prefix, pos_pool, pool_sref, pool_pos, pool_cc; DBuf<ag_nodec> pool_c; DBuf<ag_nodew> pool_w;
     DBuf<ag_nodeb> ovf_node; DBuf<u32> ovf_next, counters; DBuf<int> err;
     DBuf<u32> pos_node;
@@ -935,6 +1148,12 @@ struct AgDevice::Impl {
     Scanner scanner;
     u32 n_tiles = 0, n_keys = 0, n_nodes = 0;
     u32 node_cap = 0, ovf_cap = 0, eovf_cap = 0, eovf_cap_init = 0, walk_cap = 0;
+    u32 key_cap = 0, cand_cap = 0, hwalk_cap = 0, n_walks = 0; int rank_rounds = 2;
+    u32 unit_n_ref = 0; u64 unit_n_aln = 0;   // the unit the capacities above were last derived for
+    PinnedBuf h_wrec;                        // compacted walk records, written by k_walk_compact straight into host memory
+    DBuf<u32> status, walk_rank; DBuf<int> err_load; SectionTimes sections;
+    bool key_cap_hooked = false; u32 node_cap_hook = 0, ovf_cap_hook = 0;   // test hooks (set_option): initial capacities instead of the size-derived ones
+    bool build_queued = false, walk_queued = false;   // queued on the stream, not yet checked by finish()
     DevView view{};
     // counters layout: [0] n_nodes (pool_count), [1] ovf_count, [2] eovf_count, [3] walk_count, [4,5] materialise items
 };
@@ -946,7 +1165,7 @@ AgDevice::AgDevice(int device) : m_(new Impl), dev_(device) {
     CK(cudaStreamCreateWithFlags(&m_->st, cudaStreamNonBlocking));
     stream_ = m_->st;
     m_->scanner.launches = &launches_;
-    m_->counters.ensure(8); m_->err.ensure(1); m_->h_s.ensure(256);
+    m_->counters.ensure(8); m_->err.ensure(1); m_->h_s.ensure(256); m_->status.ensure(16); m_->err_load.ensure(1); CK(cudaMemset(m_->err_load.p, 0, sizeof(int)));
 }
 AgDevice::~AgDevice() {
     cudaSetDevice(dev_);
@@ -957,13 +1176,14 @@ AgDevice::~AgDevice() {
     DBuf<unsigned char>* b8[] = {&m.ref, &m.chain_base, &m.out_bases, &m.occ};
     for (auto* b : b8) b->release();
     DBuf<u32>* b32[] = {&m.cm_start, &m.chain_pos, &m.ntiles, &m.key_off, &m.keys, &m.vals, &m.keys2, &m.vals2, &m.hist, &m.tile_cnt,
-                        &m.tile_start, &m.tile_flag, &m.tile_base, &m.tile_nodes, &m.tile_prefix, &m.pos_pool, &m.pool_sref, &m.pool_pos, &m.pool_cc, &m.many, &m.many_prefix, &m.ovf_next, &m.counters, &m.pos_node, &m.node_sref, &m.node_pos, &m.node_cc, &m.eovf_head,
+                        &m.tile_start, &m.tile_flag, &m.tile_base, &m.tile_nodes, &m.tile_prefix, &m.pos_pool, &m.pool_sref, &m.pool_pos, &m.pool_cc, &m.many, &m.many_prefix, &m.brk, &m.lin_prefix, &m.stage, &m.ovf_next, &m.counters, &m.pos_node, &m.node_sref, &m.node_pos, &m.node_cc, &m.eovf_head,
                         &m.eovf_target, &m.eovf_next, &m.walk_next, &m.parent, &m.cmin, &m.cmax, &m.walk_used, &m.sel_start, &m.sel_tails};
     for (auto* b : b32) b->release();
     for (int i = 0; i < 4; i++) m.scanner.lvl[i].release();
     m.cm.release(); m.cthreads.release(); m.aln.release(); m.ext.release(); m.alnp.release(); m.fast.release(); m.pool_c.release(); m.pool_w.release(); m.ovf_node.release(); m.err.release();
     m.node_c.release(); m.node_w.release(); m.walks.release(); m.walks2.release(); m.cm1.release(); m.mat_detours.release(); m.tail_end.release(); m.pos_term.release(); m.cand_rank.release(); m.cand_node.release(); m.cand_label.release(); m.fprev.release(); m.msuf.release(); m.mnode.release(); m.indeg.release(); m.fnext.release(); m.chain_a.release(); m.chain_b.release(); m.hrec.release(); m.changed.release(); m.sel_off.release();
     m.contig_blob.release(); m.cdesc.release(); m.cruns.release(); m.raw.release(); m.exc_chr.release(); m.nl.release(); m.nl_blk.release(); m.rlen.release(); m.s_keep.release(); m.s_next.release(); m.s_aoff.release(); m.s_eoff.release(); m.s_lost.release(); m.ing.release(); m.exc_key.release(); m.srec.release(); m.stager.release();
+    m.h_wrec.release(); m.walk_rank.release(); m.status.release(); m.err_load.release(); m.sections.release();
     m.h_walks.release(); m.h_bases.release(); m.h_occ.release(); m.h_sel.release(); m.h_s.release();
     if (ev_mat0_) { cudaEventDestroy((cudaEvent_t)ev_mat0_); cudaEventDestroy((cudaEvent_t)ev_mat1_); }
     if (st2_) { cudaStreamSynchronize((cudaStream_t)st2_); cudaStreamDestroy((cudaStream_t)st2_); cudaEventDestroy((cudaEvent_t)ev_main_); cudaEventDestroy((cudaEvent_t)ev_reads_); }
@@ -973,8 +1193,13 @@ AgDevice::~AgDevice() {
 
 void AgDevice::set_option(const std::string& name, long value) {
     Impl& m = *m_;
-    if (name == "node_cap") m.node_cap = (u32)std::max<long>(value, 1);
-    else if (name == "ovf_cap") m.ovf_cap = (u32)std::max<long>(value, 1);
+    if (name == "node_cap") { m.node_cap_hook = (u32)std::max<long>(value, 1); m.unit_n_ref = 0; }
+    else if (name == "ovf_cap") { m.ovf_cap_hook = (u32)std::max<long>(value, 1); m.unit_n_ref = 0; }
+    else if (name == "key_cap") { m.key_cap = (u32)std::max<long>(value, 1); m.key_cap_hooked = true; }
+    else if (name == "cand_cap") m.cand_cap = (u32)std::max<long>(value, 1);
+    else if (name == "hwalk_cap") m.hwalk_cap = (u32)std::max<long>(value, 1);
+    else if (name == "tma") tma_off_ = value == 0;
+    else if (name == "rank_rounds") m.rank_rounds = (int)std::max<long>(value, 1);
     else if (name == "eovf_cap") m.eovf_cap_init = (u32)std::max<long>(value, 1);
     else if (name == "section_timing") section_timing_ = value != 0;
 }
@@ -1163,15 +1388,21 @@ struct Fd { int fd; explicit Fd(const std::string& p) : fd(open(p.c_str(), O_RDO
 
 // newline index of text[0, len) (device, 16-byte aligned, zero-padded to a multiple of 16): positions into nl[nl_base ..]; returns the
 // number of lines.  `count_only` leaves nl untouched (the caller sizes it first).  One blocking read-back of the total.
+static bool ing_fallback(const char* what, int where) {   // AG_DEBUG_INGEST=1: say why a file was handed to the host parser
+    static const bool dbg = getenv("AG_DEBUG_INGEST") != nullptr;
+    if (dbg) fprintf(stderr, "[ag ingest] %s: not the well-formed layout (check %d) -> host parser\n", what, where);
+    return false;
+}
+
 bool AgDevice::ingest_reads(const std::string& path, AgReads& host) {
     CK(cudaSetDevice(dev_));
     Impl& m = *m_; cudaStream_t st = m.st;
     Fd f(path);
     if (f.fd < 0) throw AgError{"CANNOT OPEN FILE!"};
     const size_t n = f.size();
-    if (n < 4) return false;
+    if (n < 4) return ing_fallback("reads", 1);
     char c0 = 0, cl = 0;
-    if (pread(f.fd, &c0, 1, 0) != 1 || pread(f.fd, &cl, 1, (off_t)(n - 1)) != 1 || c0 != '>' || cl != '\n') return false;
+    if (pread(f.fd, &c0, 1, 0) != 1 || pread(f.fd, &cl, 1, (off_t)(n - 1)) != 1 || c0 != '>' || cl != '\n') return ing_fallback("reads", 2);
     Timer tm(st);
     // segments of at most 1 GB cut at record starts ("\n>"), each staged at a 16-byte aligned device offset (32-bit offsets inside a segment)
     const size_t SEG = (size_t)1 << 30;
@@ -1179,10 +1410,10 @@ bool AgDevice::ingest_reads(const std::string& path, AgReads& host) {
     while (n - cut.back() > SEG) {
         const size_t want = cut.back() + SEG, W = (size_t)1 << 20;
         std::vector<char> win(W);
-        if (pread(f.fd, win.data(), W, (off_t)(want - W)) != (ssize_t)W) return false;
+        if (pread(f.fd, win.data(), W, (off_t)(want - W)) != (ssize_t)W) return ing_fallback("reads", 3);
         size_t k = W - 1;
         while (k > 0 && !(win[k] == '>' && win[k - 1] == '\n')) k--;
-        if (k == 0) return false;
+        if (k == 0) return ing_fallback("reads", 4);
         cut.push_back(want - W + k);
     }
     cut.push_back(n);
@@ -1193,13 +1424,13 @@ bool AgDevice::ingest_reads(const std::string& path, AgReads& host) {
     for (size_t s = 0; s < ns; s++) {
         const size_t len = cut[s + 1] - cut[s];
         CK(cudaMemsetAsync(m.raw.p + doff[s] + len, 0, 32, st));
-        m.stager.run(f.fd, cut[s], len, m.raw.p + doff[s], st);
+        m.stager.run(f.fd, cut[s], len, m.raw.p + doff[s], st, dev_);
     }
     t_.h2d_bytes += n;
     std::vector<u32> lines(ns, 0);
-    for (size_t s = 0; s < ns; s++) { lines[s] = m.nl_index(st, launches_, m.raw.p + doff[s], cut[s + 1] - cut[s], blk0[s], 0, false); nl0[s + 1] = nl0[s] + lines[s]; if (lines[s] & 1) return false; rec0[s + 1] = rec0[s] + lines[s] / 2; }
+    for (size_t s = 0; s < ns; s++) { lines[s] = m.nl_index(st, launches_, m.raw.p + doff[s], cut[s + 1] - cut[s], blk0[s], 0, false); nl0[s + 1] = nl0[s] + lines[s]; if (lines[s] & 1) return ing_fallback("reads", 5); rec0[s + 1] = rec0[s] + lines[s] / 2; }
     const u64 R = rec0[ns];
-    if (R == 0 || (R & 1) || R >= 0xFFFFFFF0ull) return false;
+    if (R == 0 || (R & 1) || R >= 0xFFFFFFF0ull) return ing_fallback("reads", 6);
     m.nl.ensure(nl0[ns] + 2); m.rlen.ensure(R + 2);
     CK(cudaMemsetAsync(m.ing.p, 0, 8 * sizeof(u32), st));   // [0] bad flags, [1] max length, [2] exception count
     for (size_t s = 0; s < ns; s++) {
@@ -1210,7 +1441,7 @@ bool AgDevice::ingest_reads(const std::string& path, AgReads& host) {
     volatile u32* hs = (volatile u32*)m.h_s.p;
     CK(cudaMemcpyAsync((void*)(hs + 32), m.ing.p, 2 * sizeof(u32), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    if (hs[32]) return false;   // multi-line / empty records, a read longer than 65,535: the sequential parser handles or reports it
+    if (hs[32]) return ing_fallback("reads", 7);   // multi-line / empty records, a read longer than 65,535: the sequential parser handles or reports it
     const u32 maxlen = hs[33];
     const u64 n_pairs = R / 2;
     u32 stride2 = (maxlen + 15) / 16, stridem = (maxlen + 31) / 32;
@@ -1232,7 +1463,7 @@ bool AgDevice::ingest_reads(const std::string& path, AgReads& host) {
     CK(cudaStreamSynchronize(st));
     if (hs[32] & ING_PE_LEN) throw AgError{"INCONSISTENT PE FILES!"};
     const u32 n_exc = hs[34];
-    if (n_exc > exc_cap) return false;   // more masked characters than the list holds (reads of 'N' only, ...): host parser
+    if (n_exc > exc_cap) return ing_fallback("reads", 8);   // more masked characters than the list holds (reads of 'N' only, ...): host parser
     memcpy(host.len.data(), m.h_walks.p, n_pairs * sizeof(uint16_t));
     host.exc.clear();
     if (n_exc) {
@@ -1280,26 +1511,26 @@ bool AgDevice::ingest_sam(const std::string& path) {
     m.aln_ingested = false;
     auto none = [&]() { m.n_aln = 0; m.n_ext = 0; m.aln_ingested = true; m.aln.ensure(1); m.ext.ensure(1); t_.sam_device++; return true; };
     if (n == 0 || m.n_pairs == 0) return none();
-    if (n >= 0xF0000000ull) return false;
+    if (n >= 0xF0000000ull) return ing_fallback("sam", 101);
     // '@' header lines only at the top (counted on the host from the first bytes)
     size_t body = 0; u32 n_hdr = 0;
     {
         const size_t W = std::min<size_t>(n, (size_t)1 << 20);
         std::vector<char> head(W);
-        if (pread(f.fd, head.data(), W, 0) != (ssize_t)W) return false;
-        while (body < W && head[body] == '@') { const char* l = (const char*)memchr(head.data() + body, '\n', W - body); if (!l) return false; body = (size_t)(l - head.data()) + 1; n_hdr++; }
-        if (body >= W && W < n) return false;
+        if (pread(f.fd, head.data(), W, 0) != (ssize_t)W) return ing_fallback("sam", 102);
+        while (body < W && head[body] == '@') { const char* l = (const char*)memchr(head.data() + body, '\n', W - body); if (!l) return ing_fallback("sam", 103); body = (size_t)(l - head.data()) + 1; n_hdr++; }
+        if (body >= W && W < n) return ing_fallback("sam", 104);
         char cl = 0;
-        if (pread(f.fd, &cl, 1, (off_t)(n - 1)) != 1 || cl != '\n') return false;
+        if (pread(f.fd, &cl, 1, (off_t)(n - 1)) != 1 || cl != '\n') return ing_fallback("sam", 105);
     }
     if (body >= n) return none();
     Timer tm(st);
     m.raw.ensure(n + 64); m.nl_blk.ensure((n + NL_B - 1) / NL_B + 4); m.ing.ensure(8);
     CK(cudaMemsetAsync(m.raw.p + n, 0, 32, st));
-    m.stager.run(f.fd, 0, n, m.raw.p, st);
+    m.stager.run(f.fd, 0, n, m.raw.p, st, dev_);
     t_.h2d_bytes += n;
     const u32 lines = m.nl_index(st, launches_, m.raw.p, n, 0, 0, false);
-    if (lines < n_hdr || ((lines - n_hdr) & 1)) return false;   // odd number of records: BROKEN BOWTIE FILE territory, the host parser reports it
+    if (lines < n_hdr || ((lines - n_hdr) & 1)) return ing_fallback("sam", 106);   // odd number of records: BROKEN BOWTIE FILE territory, the host parser reports it
     const u32 n_rec = (lines - n_hdr) / 2;
     if (!n_rec) return none();
     m.nl.ensure((size_t)lines + 2);
@@ -1322,7 +1553,7 @@ bool AgDevice::ingest_sam(const std::string& path) {
     CK(cudaMemcpyAsync((void*)(hs + 35), m.s_lost.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const u32 flags = hs[32], n_aln = hs[33], n_ext = hs[34];
-    if ((flags & (ING_BAD_LAYOUT | ING_BAD_RECORD | ING_BAD_ORDER)) || hs[35] > lost_cap) return false;   // not the well-formed layout: host parser
+    if ((flags & (ING_BAD_LAYOUT | ING_BAD_RECORD | ING_BAD_ORDER)) || hs[35] > lost_cap) return ing_fallback("sam", 107);   // not the well-formed layout: host parser
     if (flags & ING_STRAND) throw AgError{"BOWTIE ALIGNMENT ERROR"};
     m.aln.ensure((size_t)n_aln + 1); m.ext.ensure((size_t)n_ext + 1);
     k_sam_fill<<<(n_rec + 127) / 128, 128, 0, st>>>(m.raw.p, nl, (u32)body, n_rec, m.reads.len, m.n_pairs, m.srec.p, m.s_keep.p, m.s_aoff.p, n_ext ? m.s_eoff.p : nullptr, m.aln.p, m.ext.p); launches_++;
@@ -1343,7 +1574,7 @@ void AgDevice::fetch_alignments(std::vector<ag_aln>& aln, std::vector<ag_seg>& e
 void AgDevice::load_unit(const AgUnitInput& in) {
     CK(cudaSetDevice(dev_));
     Impl& m = *m_;
-    Timer tm(m.st);
+    Section sec(m.sections, m.st, &t_.h2d);
     if (in.aln_on_device && !m.aln_ingested) throw AgError{"internal: no ingested alignments on the device"};
     m.n_ref = in.n_ref; m.n_pos = in.n_pos; m.n_cm = in.n_cm;
     if (!in.aln_on_device) { m.n_aln = (u32)in.n_aln; m.n_ext = in.n_ext; m.aln_ingested = false; }
@@ -1380,30 +1611,40 @@ void AgDevice::load_unit(const AgUnitInput& in) {
         m.cthreads.ensure(in.n_threads + 1); m.many.ensure((size_t)in.n_pos + 2);
         if (in.n_threads) CK(cudaMemcpyAsync(m.cthreads.p, in.threads, (size_t)in.n_threads * sizeof(ag_cthread), cudaMemcpyHostToDevice, m.st));
         table_bytes = (size_t)in.n_threads * sizeof(ag_cthread);
-        CK(cudaMemsetAsync(m.err.p, 0, sizeof(int), m.st));
+        CK(cudaMemsetAsync(m.err_load.p, 0, sizeof(int), m.st));
         CK(cudaMemsetAsync(m.many.p, 0, ((size_t)in.n_pos + 1) * sizeof(u32), m.st));
-        if (in.n_cm) { k_cm_count<<<(in.n_cm + 255) / 256, 256, 0, m.st>>>(m.chain_pos.p, in.n_cm, in.n_pos, m.many.p, m.err.p); launches_++; }
+        if (in.n_cm) { k_cm_count<<<(in.n_cm + 255) / 256, 256, 0, m.st>>>(m.chain_pos.p, in.n_cm, in.n_pos, m.many.p, m.err_load.p); launches_++; }
         m.scanner.run(m.many.p, m.cm_start.p, in.n_pos, m.st);
         if (in.n_cm) {
             CK(cudaMemsetAsync(m.many.p, 0, ((size_t)in.n_pos + 1) * sizeof(u32), m.st));
-            k_cm_fill<<<(in.n_cm + 255) / 256, 256, 0, m.st>>>(m.chain_pos.p, in.n_cm, m.cthreads.p, in.n_threads, m.cm_start.p, m.many.p, m.cm.p, m.err.p); launches_++;
+            k_cm_fill<<<(in.n_cm + 255) / 256, 256, 0, m.st>>>(m.chain_pos.p, in.n_cm, m.cthreads.p, in.n_threads, m.cm_start.p, m.many.p, m.cm.p, m.err_load.p); launches_++;
             k_cm_sort<<<(in.n_pos + 255) / 256, 256, 0, m.st>>>(m.cm_start.p, in.n_pos, m.cm.p); launches_++;
         }
-        int err = 0;
-        CK(cudaMemcpyAsync(&err, m.err.p, sizeof(int), cudaMemcpyDeviceToHost, m.st));
-        CK(cudaStreamSynchronize(m.st));
-        if (err) throw AgError{"CONTIG ALIGNMENT ERROR: inconsistent contig threads"};
+        // (an inconsistent thread list sets E_CM in the upload's error word: reported at the step's synchronisation point)
     }
-    t_.h2d += tm.stop();
     t_.h2d_bytes += in.n_pos + table_bytes + (in.aln_on_device ? 0 : in.n_aln * sizeof(ag_aln) + in.n_ext * sizeof(ag_seg));
 }
 
-void AgDevice::build() {
+// ---- the step: everything from the uploaded unit to the walk records is QUEUED without a single host round trip; finish() is the one
+// synchronisation point.  Buffer sizes the device alone knows (tile keys, nodes, overflow pools, start candidates, walk records) are
+// capacities with an overflow bit in the step's error word: finish() then grows the capacity and the step is queued again. ----------
+void AgDevice::build() { enqueue_build(); }
+
+void AgDevice::enqueue_build() {
     CK(cudaSetDevice(dev_));
     Impl& m = *m_;
     cudaStream_t st = m.st;
     const u32 nA = m.n_aln, n_ref = m.n_ref, n_pos = m.n_pos;
     m.n_tiles = (n_ref + AG_TPOS - 1) / AG_TPOS;
+    if (m.unit_n_ref != n_ref || m.unit_n_aln != nA) {   // a new unit: capacities from its size (kept when the same unit is built again)
+        m.unit_n_ref = n_ref; m.unit_n_aln = nA;
+        if (!m.key_cap_hooked) m.key_cap = std::max<u32>(m.key_cap, 2 * nA + 4096);
+        m.node_cap = m.node_cap_hook ? m.node_cap_hook : std::max<u32>(m.node_cap, std::max<u32>(1u << 20, 3 * n_ref + (1u << 16)));
+        if (m.ovf_cap_hook) m.ovf_cap = m.ovf_cap_hook;
+    }
+    if (!m.node_cap) m.node_cap = std::max<u32>(1u << 20, 3 * n_ref + (1u << 16));
+    if (!m.key_cap) m.key_cap = 2 * nA + 4096;
+    if (!m.ovf_cap) m.ovf_cap = std::max<u32>(1u << 18, n_ref / 8);
     DevView& d = m.view;
     d = DevView{};
     d.reads = m.reads; d.ref = m.ref.p; d.n_ref = n_ref; d.n_pos = n_pos;
@@ -1415,190 +1656,194 @@ void AgDevice::build() {
     d.alnp = m.alnp.p; d.fast = m.fast.p; d.ntiles = m.ntiles.p; d.key_off = m.key_off.p;
     d.tile_cnt = m.tile_cnt.p; d.tile_start = m.tile_start.p; d.n_tiles = m.n_tiles; d.tile_flag = m.tile_flag.p;
     d.pos_node = m.pos_node.p;
-    d.err = m.err.p;
+    d.err = m.err.p; d.err_load = m.err_load.p;
+    d.nk_ptr = m.key_off.p + nA; d.key_cap = m.key_cap; d.nn_ptr = m.counters.p + 0;
     CK(cudaMemsetAsync(m.err.p, 0, sizeof(int), st));
     CK(cudaMemsetAsync(m.counters.p, 0, 8 * sizeof(u32), st));
     CK(cudaMemsetAsync(m.tile_cnt.p, 0, (m.n_tiles + 1) * sizeof(u32), st));
 
     m.cm1.ensure((size_t)n_pos + 2); d.cm1 = m.cm1.p; m.pos_term.ensure((size_t)n_pos + 2); d.pos_term = m.pos_term.p;
     m.many.ensure((size_t)n_pos + 2); m.many_prefix.ensure((size_t)n_pos + 2); d.many_prefix = m.many_prefix.p;
-    if (n_pos) { k_cm1<<<(n_pos + 255) / 256, 256, 0, st>>>(d, m.cm1.p, m.pos_term.p, m.many.p); launches_++; }
+    m.brk.ensure((size_t)n_pos + 2); m.lin_prefix.ensure((size_t)n_pos + 2); d.lin_prefix = m.lin_prefix.p;
+    if (n_pos) { k_cm1<<<(n_pos + 255) / 256, 256, 0, st>>>(d, m.cm1.p, m.pos_term.p, m.many.p, m.brk.p); launches_++; }
     m.scanner.run(m.many.p, m.many_prefix.p, n_pos, st);
+    m.scanner.run(m.brk.p, m.lin_prefix.p, n_pos, st);
     if (!attr_done_) { CK(cudaFuncSetAttribute(k_build, cudaFuncAttributeMaxDynamicSharedMemorySize, NODES_SMEM + NCHUNK_N * 32 * 4)); attr_done_ = true; }  // per device
 #if AG_CODE4
     d.rw = (2 * m.reads.stride2 <= 32u) ? 2 * m.reads.stride2 : 0;   // words of oriented 4-bit codes per staged read (eight bases each)
 #else
     d.rw = (m.reads.stride2 + m.reads.stridem <= (u32)READ_WORDS_MAX) ? m.reads.stride2 + m.reads.stridem : 0;
 #endif
-
     // ---- prep + keys ------------------------------------------------------------------------------------------------
+    m.keys.ensure((size_t)m.key_cap + 1); m.vals.ensure((size_t)m.key_cap + 1); m.keys2.ensure((size_t)m.key_cap + 1); m.vals2.ensure((size_t)m.key_cap + 1);
+    d.keys = m.keys.p; d.vals = m.vals.p;
     {
-        Timer tm(st);
+        Section sec(m.sections, st, &t_.prep);
         if (nA) { k_prep<<<(nA + 255) / 256, 256, 0, st>>>(d); launches_++; }
         m.scanner.run(m.ntiles.p, m.key_off.p, nA, st);
-        volatile u32* hs = (volatile u32*)m.h_s.p;
-        CK(cudaMemcpyAsync((void*)hs, m.key_off.p + nA, sizeof(u32), cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync((void*)(hs + 2), m.err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        if (hs[2] == 2) throw AgError{"BOWTIE ALIGNMENT ERROR: alignment outside the unit"};   // k_prep's verdict, read before the sweeps can overwrite the error word
-        const u32 nk = hs[0];
-        m.n_keys = nk;
-        m.keys.ensure(nk + 1); m.vals.ensure(nk + 1); m.keys2.ensure(nk + 1); m.vals2.ensure(nk + 1);
-        d.keys = m.keys.p; d.vals = m.vals.p;
         if (nA) { k_keys<<<(nA + 255) / 256, 256, 0, st>>>(d); launches_++; }
         m.scanner.run(m.tile_cnt.p, m.tile_start.p, m.n_tiles, st);
-        t_.prep += tm.stop();
     }
-    // ---- bucket: stable radix sort by tile ---------------------------------------------------------------------------
+    // ---- bucket: stable radix sort by tile (key count on the device; grids sized by the capacity) ---------------------------------------
     {
-        Timer tm(st);
-        u32 nk = m.n_keys;
-        if (nk) {
+        Section sec(m.sections, st, &t_.sort);
+        if (nA) {
             int bits = 1; while ((1ull << bits) < (u64)m.n_tiles) bits++;
-            unsigned nb = (nk + RS_B - 1) / RS_B;
+            const unsigned nb = (m.key_cap + RS_B - 1) / RS_B;
             m.hist.ensure((size_t)RS_BINS * nb + 2);
             u32 *ka = m.keys.p, *va = m.vals.p, *kb = m.keys2.p, *vb = m.vals2.p;
             for (int shift = 0; shift < bits; shift += RS_BITS) {
-                k_rs_hist<<<nb, RS_T, 0, st>>>(ka, m.hist.p, nk, shift, nb); launches_++;
+                k_rs_hist<<<nb, RS_T, 0, st>>>(ka, m.hist.p, d.nk_ptr, m.key_cap, shift, nb); launches_++;
                 m.scanner.run(m.hist.p, m.hist.p, (size_t)RS_BINS * nb, st, 0, 0);
-                k_rs_scatter<<<nb, RS_T, 0, st>>>(ka, va, kb, vb, m.hist.p, nk, shift, nb); launches_++;
+                k_rs_scatter<<<nb, RS_T, 0, st>>>(ka, va, kb, vb, m.hist.p, d.nk_ptr, m.key_cap, shift, nb); launches_++;
                 std::swap(ka, kb); std::swap(va, vb);
             }
             d.keys = ka; d.vals = va;
         }
-        t_.sort += tm.stop();
     }
     // ---- nodes (+ the common-case edges as successor-item bits) -------------------------------------------------------------------
-    u32 nn = 0;
     {
-        Timer tm(st);
-        if (!m.node_cap) m.node_cap = std::max<u32>(1u << 20, 3 * n_ref + (1u << 16));
+        Section sec(m.sections, st, &t_.nodes);
         m.tile_base.ensure(m.n_tiles + 2); m.tile_nodes.ensure(m.n_tiles + 2); m.tile_prefix.ensure(m.n_tiles + 2); m.pos_pool.ensure((size_t)n_pos + 2);
         d.tile_base = m.tile_base.p; d.tile_nodes = m.tile_nodes.p; d.tile_prefix = m.tile_prefix.p; d.pos_pool = m.pos_pool.p;
-        for (;;) {
-            m.pool_c.ensure((size_t)m.node_cap + 1); m.pool_w.ensure((size_t)m.node_cap + 1); m.pool_sref.ensure(2 * (size_t)m.node_cap + 2); m.pool_pos.ensure((size_t)m.node_cap + 1);
-            if (keep_counts_) m.pool_cc.ensure(6 * (size_t)m.node_cap + 6);
-            if (!m.ovf_cap) m.ovf_cap = std::max<u32>(1u << 18, n_ref / 8);
-            m.ovf_node.ensure(m.ovf_cap); m.ovf_next.ensure(m.ovf_cap);
-            d.pool_c = m.pool_c.p; d.pool_w = m.pool_w.p; d.pool_sref = m.pool_sref.p; d.pool_pos = m.pool_pos.p; d.pool_cc = keep_counts_ ? m.pool_cc.p : nullptr;
-            d.node_cap = m.node_cap; d.pool_count = m.counters.p + 0;
-            d.ovf.node = m.ovf_node.p; d.ovf.next = m.ovf_next.p; d.ovf.count = m.counters.p + 1; d.ovf.cap = m.ovf_cap; d.ovf.err = m.err.p;
-            CK(cudaMemsetAsync(m.tile_flag.p, 0, ((size_t)m.n_tiles + 1) * sizeof(u32), st));
-            if (reads_pending_) { CK(cudaStreamWaitEvent(st, (cudaEvent_t)ev_reads_, 0)); reads_pending_ = false; }   // overlapped reads upload (set_reads_sparse)
-            if (m.n_tiles) { k_build<<<m.n_tiles, AG_TILE, NODES_SMEM + NCHUNK_N * d.rw * 4, st>>>(d); launches_++; }
-            volatile u32* hs = (volatile u32*)m.h_s.p;
-            CK(cudaMemcpyAsync((void*)(hs + 0), m.err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync((void*)(hs + 1), m.counters.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            const int err = (int)hs[0]; nn = hs[1];
-            if (err == 0) break;
-            if (err == 2) throw AgError{"BOWTIE ALIGNMENT ERROR: alignment outside the unit"};
-            t_.regrows++;
-            if (err == 3 && m.node_cap < (1u << 31)) m.node_cap = m.node_cap * 2;           // node table too small: grow and redo the sweep
-            else if (err == 1 && m.ovf_cap < (1u << 30)) m.ovf_cap *= 4;                    // overflow pool (nodes beyond the shared-memory slots) too small
-            else throw AgError{"node table exhausted"};
-            CK(cudaMemsetAsync(m.err.p, 0, sizeof(int), st));
-            CK(cudaMemsetAsync(m.counters.p, 0, 8 * sizeof(u32), st));
-        }
-        t_.nodes += tm.stop();
-    }
-    m.n_nodes = nn; t_.n_nodes = nn; t_.n_keys = m.n_keys; t_.n_tiles = m.n_tiles;
-    // ---- tile blocks -> position order, successor bits -> successor indices; generic edge sweep over the flagged tiles --------------
-    // (repeated with a larger edge overflow pool when it runs out: both kernels only read the sweep-order blocks and rewrite the final table)
-    {
-        m.node_c.ensure((size_t)nn + 1); m.node_w.ensure((size_t)nn + 1); m.node_sref.ensure(2 * (size_t)nn + 2); m.node_pos.ensure((size_t)nn + 1);
-        if (keep_counts_) m.node_cc.ensure(6 * (size_t)nn + 6);
-        d.node_c = m.node_c.p; d.node_w = m.node_w.p; d.node_sref = m.node_sref.p; d.node_pos = m.node_pos.p; d.node_cc = keep_counts_ ? m.node_cc.p : nullptr;
-        m.eovf_head.ensure(nn + 1);
-        m.eovf_cap = m.eovf_cap_init ? m.eovf_cap_init : std::max<u32>(1u << 18, nn / 8);
-        for (;;) {
-            Timer tm(st);
-            m.eovf_target.ensure(m.eovf_cap); m.eovf_next.ensure(m.eovf_cap);
-            d.eovf_head = m.eovf_head.p; d.eovf_target = m.eovf_target.p; d.eovf_next = m.eovf_next.p; d.eovf_count = m.counters.p + 2; d.eovf_cap = m.eovf_cap;
-            m.scanner.run(m.tile_nodes.p, m.tile_prefix.p, m.n_tiles, st);
-            k_posfix<<<(n_pos + 1 + 255) / 256, 256, 0, st>>>(d, nn); launches_++;
-            if (nn) { k_succ<<<(nn + 255) / 256, 256, 0, st>>>(d, nn); launches_++; }
-            t_.finalize += tm.stop();
-            Timer tm2(st);
-            if (m.n_tiles && nn) { k_edges<<<m.n_tiles, AG_TILE, 0, st>>>(d); launches_++; }
-            volatile u32* hs = (volatile u32*)m.h_s.p;
-            CK(cudaMemcpyAsync((void*)(hs + 0), m.err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync((void*)(hs + 4), m.counters.p, 4 * sizeof(u32), cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            t_.edges += tm2.stop();
-            if (hs[0] == 4 && m.eovf_cap < (1u << 30)) {   // edge overflow pool (successors beyond the two inline ones) too small: grow and redo
-                m.eovf_cap *= 4; t_.regrows++;
-                CK(cudaMemsetAsync(m.err.p, 0, sizeof(int), st));
-                CK(cudaMemsetAsync(m.counters.p + 2, 0, sizeof(u32), st));
-                continue;
+        m.pool_c.ensure((size_t)m.node_cap + 1); m.pool_w.ensure((size_t)m.node_cap + 1); m.pool_sref.ensure(2 * (size_t)m.node_cap + 2); m.pool_pos.ensure((size_t)m.node_cap + 1);
+        if (keep_counts_) m.pool_cc.ensure(6 * (size_t)m.node_cap + 6);
+        m.ovf_node.ensure(m.ovf_cap); m.ovf_next.ensure(m.ovf_cap);
+        d.pool_c = m.pool_c.p; d.pool_w = m.pool_w.p; d.pool_sref = m.pool_sref.p; d.pool_pos = m.pool_pos.p; d.pool_cc = keep_counts_ ? m.pool_cc.p : nullptr;
+        d.node_cap = m.node_cap; d.pool_count = m.counters.p + 0;
+        d.ovf.node = m.ovf_node.p; d.ovf.next = m.ovf_next.p; d.ovf.count = m.counters.p + 1; d.ovf.cap = m.ovf_cap; d.ovf.err = m.err.p;
+        CK(cudaMemsetAsync(m.tile_flag.p, 0, ((size_t)m.n_tiles + 1) * sizeof(u32), st));
+        if (reads_pending_) { CK(cudaStreamWaitEvent(st, (cudaEvent_t)ev_reads_, 0)); reads_pending_ = false; }   // overlapped reads upload (set_reads_sparse)
+        const u32 maxlen = m.reads.stride2 * 16;
+        const u32 rsw = (ST_HDR_W + (maxlen + 7) / 8 + 3) / 4 * 4;                       // staged record words: header + oriented 4-bit codes, 16-byte multiple
+        const size_t smem_tma = NODES_SMEM + 2 * (size_t)ST_CH * rsw * 4;
+        if (!tma_off_ && smem_tma <= 36 * 1024) {                                       // (reads of up to ~500 bases; longer ones take the per-thread staging kernel)
+            if (!attr_tma_done_) { CK(cudaFuncSetAttribute(k_build_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 36 * 1024)); attr_tma_done_ = true; }
+            m.stage.ensure((size_t)m.key_cap * rsw + 64);
+            {
+                Section sec2(m.sections, st, &t_.stage);
+                k_stage<<<GS_BLOCKS, GS_T, 0, st>>>(d, m.stage.p, rsw); launches_++;
             }
-            if (hs[0]) throw AgError{"edge overflow pool exhausted"};
-            t_.n_edges_ovf = hs[4 + 2];
-            break;
+            Section sec3(m.sections, st, &t_.build_kernel);
+            if (m.n_tiles) { k_build_tma<<<m.n_tiles, AG_TILE, smem_tma, st>>>(d, m.stage.p, rsw); launches_++; }
+        } else {
+            Section sec3(m.sections, st, &t_.build_kernel);
+            if (m.n_tiles) { k_build<<<m.n_tiles, AG_TILE, NODES_SMEM + NCHUNK_N * d.rw * 4, st>>>(d); launches_++; }
         }
     }
+    // ---- tile blocks -> position order, successor bits -> successor indices (arrays sized by the node CAPACITY) ----------------------------
+    {
+        Section sec(m.sections, st, &t_.finalize);
+        const size_t nc = m.node_cap;
+        m.node_c.ensure(nc + 1); m.node_w.ensure(nc + 1); m.node_sref.ensure(2 * nc + 2); m.node_pos.ensure(nc + 1);
+        if (keep_counts_) m.node_cc.ensure(6 * nc + 6);
+        d.node_c = m.node_c.p; d.node_w = m.node_w.p; d.node_sref = m.node_sref.p; d.node_pos = m.node_pos.p; d.node_cc = keep_counts_ ? m.node_cc.p : nullptr;
+        m.eovf_head.ensure(nc + 1);
+        if (!m.eovf_cap) m.eovf_cap = m.eovf_cap_init ? m.eovf_cap_init : std::max<u32>(1u << 18, m.node_cap / 16);
+        m.eovf_target.ensure(m.eovf_cap); m.eovf_next.ensure(m.eovf_cap);
+        d.eovf_head = m.eovf_head.p; d.eovf_target = m.eovf_target.p; d.eovf_next = m.eovf_next.p; d.eovf_count = m.counters.p + 2; d.eovf_cap = m.eovf_cap;
+        m.scanner.run(m.tile_nodes.p, m.tile_prefix.p, m.n_tiles, st);
+        k_posfix<<<(n_pos + 1 + 255) / 256, 256, 0, st>>>(d); launches_++;
+        k_succ<<<GS_BLOCKS, GS_T, 0, st>>>(d); launches_++;
+    }
+    // ---- generic edge sweep over the flagged tiles ----------------------------------------------------------------------------------
+    {
+        Section sec(m.sections, st, &t_.edges);
+        if (m.n_tiles) { k_edges<<<m.n_tiles, AG_TILE, 0, st>>>(d); launches_++; }
+    }
+    m.build_queued = true; m.walk_queued = false;
+    t_.n_tiles = m.n_tiles;
 }
 
-void AgDevice::walk_components() {
-    Impl& m = *m_; cudaStream_t st = m.st; DevView& d = m.view; u32 nn = m.n_nodes;
-    unsigned g = (nn + 255) / 256;
+// forced-link chains, start candidates, components, replay, compaction of the walk records into host memory — queued behind the build
+void AgDevice::enqueue_walk() {
+    Impl& m = *m_; cudaStream_t st = m.st; DevView& d = m.view;
+    const size_t nc = m.node_cap;
+    if (!m.cand_cap) m.cand_cap = (u32)std::max<size_t>(1u << 16, nc / 16);
+    if (!m.hwalk_cap) m.hwalk_cap = (u32)std::max<size_t>(1u << 16, m.n_ref / 16);
+    m.walk_next.ensure(nc + 1); m.parent.ensure(nc + 1); m.cmin.ensure(nc + 2); m.cmax.ensure(nc + 1);
+    d.walk_next = m.walk_next.p; d.parent = m.parent.p; d.cmin = m.cmin.p; d.cmax = m.cmax.p;
+    d.walk_count = m.counters.p + 3;
     {   // forced-link chains
-        Timer tm(st);
-        m.indeg.ensure(nn + 1); m.fnext.ensure(nn + 1); m.fprev.ensure(nn + 1); d.fprev = m.fprev.p; m.chain_a.ensure(nn + 1); m.chain_b.ensure(nn + 1); m.changed.ensure(1);
-        d.indeg = m.indeg.p; d.fnext = m.fnext.p; d.chain_a = m.chain_a.p; d.chain_b = m.chain_b.p; d.changed = m.changed.p;
-        CK(cudaMemsetAsync(m.indeg.p, 0, (size_t)nn * sizeof(u32), st));
-        k_uf_init<<<g, 256, 0, st>>>(d, nn); launches_++;
-        k_indeg<<<g, 256, 0, st>>>(d, nn); launches_++;
-        k_links<<<g, 256, 0, st>>>(d, nn); launches_++;
+        Section sec(m.sections, st, &t_.chains);
+        m.indeg.ensure(nc + 1); m.fnext.ensure(nc + 1); m.fprev.ensure(nc + 1); d.fprev = m.fprev.p; m.chain_a.ensure(nc + 1); m.chain_b.ensure(nc + 1);
+        d.indeg = m.indeg.p; d.fnext = m.fnext.p; d.chain_a = m.chain_a.p; d.chain_b = m.chain_b.p;
+        k_uf_init<<<GS_BLOCKS, GS_T, 0, st>>>(d); launches_++;
+        k_indeg<<<GS_BLOCKS, GS_T, 0, st>>>(d); launches_++;
+        k_links<<<GS_BLOCKS, GS_T, 0, st>>>(d); launches_++;
         ag_chain *a = m.chain_a.p, *b = m.chain_b.p;
-        k_rank_local<<<(nn + 1023) / 1024, 1024, 0, st>>>(a, nn); launches_++;
-        for (int round = 0; round < 32; round++) {  // links that leave a 1024-node block: log2(blocks spanned) + 1 global rounds
-            CK(cudaMemsetAsync(m.changed.p, 0, sizeof(int), st));
-            k_rank<<<g, 256, 0, st>>>(a, b, nn, m.changed.p); launches_++;
+        k_rank_local<<<(unsigned)((nc + 1023) / 1024), 1024, 0, st>>>(a, d.nn_ptr, m.err.p); launches_++;
+        for (int round = 0; round < m.rank_rounds; round++) {  // links that leave a 1024-node block: a fixed number of global rounds, more on request (E_RANK_MORE)
+            k_rank<<<GS_BLOCKS, GS_T, 0, st>>>(a, b, d.nn_ptr, m.err.p, round + 1 == m.rank_rounds ? 1 : 0); launches_++;
             std::swap(a, b);
-            if (round >= 1) {
-                volatile u32* hs = (volatile u32*)m.h_s.p;
-                CK(cudaMemcpyAsync((void*)hs, m.changed.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-                CK(cudaStreamSynchronize(st));
-                if (!hs[0]) break;
-            }
         }
         d.chain = a;
         // start candidates = chain heads, compacted in node order
-        m.cand_rank.ensure((size_t)nn + 2); m.cand_node.ensure(nn + 1); m.cand_label.ensure(nn + 1);
+        m.cand_rank.ensure(nc + 2); m.cand_node.ensure((size_t)m.cand_cap + 1); m.cand_label.ensure((size_t)m.cand_cap + 1);
         d.cand_rank = m.cand_rank.p; d.cand_node = m.cand_node.p; d.cand_label = m.cand_label.p;
-        k_cand_flag<<<g, 256, 0, st>>>(d, nn, m.indeg.p); launches_++;
-        m.scanner.run(m.indeg.p, m.cand_rank.p, nn, st);
-        k_cand_scatter<<<g, 256, 0, st>>>(d, nn, m.indeg.p); launches_++;
-        { volatile u32* hs = (volatile u32*)m.h_s.p;
-          CK(cudaMemcpyAsync((void*)hs, m.cand_rank.p + nn, sizeof(u32), cudaMemcpyDeviceToHost, st));
-          CK(cudaStreamSynchronize(st));
-          m.n_cand = hs[0]; }
-        t_.chains += tm.stop();
+        d.ncand_ptr = m.cand_rank.p + nc; d.cand_cap = m.cand_cap;
+        k_cand_flag<<<GS_BLOCKS, GS_T, 0, st>>>(d, m.indeg.p); launches_++;
+        m.scanner.run(m.indeg.p, m.cand_rank.p, nc, st);
+        k_cand_scatter<<<GS_BLOCKS, GS_T, 0, st>>>(d, m.indeg.p); launches_++;
     }
-    const u32 nc = m.n_cand;
-    t_.n_components = nc;
     // every walk starts at a chain head, so the candidate count bounds the number of walk records
-    m.walk_cap = nc + 1; m.walks.ensure(m.walk_cap); m.walks2.ensure(m.walk_cap); m.walk_used.ensure((size_t)nc + 2);
+    m.walk_cap = m.cand_cap + 1; m.walks.ensure(m.walk_cap); m.walk_used.ensure((size_t)m.cand_cap + 2);
+    m.h_wrec.ensure((size_t)m.hwalk_cap * sizeof(ag_walk));
+    m.walks2.ensure(m.walk_cap);
     d.walks = m.walks.p; d.walks_sorted = m.walks2.p; d.walk_cap = m.walk_cap; d.walk_used = m.walk_used.p;
-    CK(cudaMemsetAsync(m.walk_used.p, 0, ((size_t)nc + 1) * sizeof(u32), st));
-    if (!nc) { chains_valid_ = true; return; }
-    unsigned gc = (nc + 255) / 256;
+    d.walks_host = (ag_walk*)m.h_wrec.p; d.hwalk_cap = m.hwalk_cap;
+    CK(cudaMemsetAsync(m.walk_used.p, 0, ((size_t)m.cand_cap + 1) * sizeof(u32), st));
     {
-        Timer tm(st);
-        m.hrec.ensure((size_t)nn + 1); d.hrec = m.hrec.p;
-        k_hrec<<<gc, 256, 0, st>>>(d, nc); launches_++;
-        k_uf_tails<<<gc, 256, 0, st>>>(d, nc); launches_++;
-        k_uf_flatten<<<gc, 256, 0, st>>>(d, nc); launches_++;
-        t_.components += tm.stop();
+        Section sec(m.sections, st, &t_.components);
+        m.hrec.ensure(nc + 1); d.hrec = m.hrec.p;
+        k_hrec<<<GS_BLOCKS / 4, GS_T, 0, st>>>(d); launches_++;
+        k_uf_tails<<<GS_BLOCKS / 4, GS_T, 0, st>>>(d); launches_++;
+        k_uf_flatten<<<GS_BLOCKS / 4, GS_T, 0, st>>>(d); launches_++;
     }
     {
-        Timer tm(st);
-        k_walk_components<<<(unsigned)(((size_t)nc * 32 + 255) / 256), 256, 0, st>>>(d, nc); launches_++;
-        t_.walk += tm.stop();
+        Section sec(m.sections, st, &t_.walk);
+        k_walk_components<<<148 * 16, 256, 0, st>>>(d, m.counters.p + 6); launches_++;   // counters[6]: next candidate (zeroed with the other counters when the build was queued)
+    }
+    {
+        Section sec(m.sections, st, &t_.d2h);
+        m.walk_rank.ensure((size_t)m.cand_cap + 2);
+        m.scanner.run(m.walk_used.p, m.walk_rank.p, m.cand_cap, st);
+        k_walk_compact<<<GS_BLOCKS / 4, GS_T, 0, st>>>(d, m.walk_rank.p); launches_++;
+        k_walk_to_host<<<GS_BLOCKS / 4, GS_T, 0, st>>>(d, m.walk_rank.p); launches_++;
     }
     chains_valid_ = true;
+    m.walk_queued = true;
 }
+
+// The step's synchronisation point.  Returns true when a capacity was exceeded: it has been grown and the caller queues the step again.
+bool AgDevice::finish() {
+    Impl& m = *m_; cudaStream_t st = m.st; DevView& d = m.view;
+    if (!m.build_queued && !m.walk_queued) return false;
+    k_status<<<1, 32, 0, st>>>(d, m.counters.p, m.walk_queued ? m.walk_rank.p : nullptr, m.status.p); launches_++;
+    volatile u32* hs = (volatile u32*)m.h_s.p;
+    CK(cudaMemcpyAsync((void*)hs, m.status.p, 8 * sizeof(u32), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    m.sections.collect();
+    const int err = (int)hs[0];
+    const u32 nn = hs[1], nk = hs[4], ncand = hs[5], nw = hs[6];
+    if (err & E_BAD_ALN) { m.build_queued = false; throw AgError{"BOWTIE ALIGNMENT ERROR: alignment outside the unit"}; }
+    if (err & E_CM) { m.build_queued = false; throw AgError{"CONTIG ALIGNMENT ERROR: inconsistent contig threads"}; }
+    bool redo = false;
+    if (err & E_KEY_CAP) { m.key_cap = nk + nk / 8 + 4096; redo = true; }
+    if (err & E_NODE_CAP) { if (m.node_cap >= (1u << 31)) throw AgError{"node table exhausted"}; m.node_cap = std::max<u32>(m.node_cap * 2, nn + nn / 8); redo = true; }
+    if (err & E_OVF) { if (m.ovf_cap >= (1u << 30)) throw AgError{"node table exhausted"}; m.ovf_cap *= 4; redo = true; }
+    if (err & E_EDGE_OVF) { if (m.eovf_cap >= (1u << 30)) throw AgError{"edge overflow pool exhausted"}; m.eovf_cap *= 4; redo = true; }
+    if (err & E_CAND_CAP) { m.cand_cap = ncand + ncand / 8 + 1024; redo = true; }
+    if (err & E_HWALK_CAP) { m.hwalk_cap = nw + nw / 8 + 1024; redo = true; }
+    if (err & E_RANK_MORE) { if (m.rank_rounds >= 24) throw AgError{"internal: chain ranking did not converge"}; m.rank_rounds += 2; redo = true; }
+    if (err & (E_WALK_CAP | E_MAT_CAP)) throw AgError{"walk record buffer exhausted"};
+    if (redo) { t_.regrows++; m.build_queued = m.walk_queued = false; return true; }
+    m.n_nodes = nn; m.n_keys = nk; t_.n_nodes = nn; t_.n_keys = nk; t_.n_edges_ovf = hs[3];
+    if (m.walk_queued) { m.n_cand = ncand; m.n_walks = nw; t_.n_components = ncand; }
+    m.build_queued = m.walk_queued = false;
+    return false;
+}
+void AgDevice::build_sync() { while (finish()) enqueue_build(); }
 
 void AgDevice::walk_sequential() {
     Impl& m = *m_; cudaStream_t st = m.st; DevView& d = m.view; u32 nn = m.n_nodes;
@@ -1606,8 +1851,8 @@ void AgDevice::walk_sequential() {
     // reset marks to the coverage filter state and replay in one thread
     m.msuf.ensure(nn + 1); m.mnode.ensure(nn + 1); d.msuf = m.msuf.p; d.mnode = m.mnode.p;
     // with the skip rule a walk may start inside a chain: any live node can be a start
-    m.walk_cap = nn + 1; m.walks.ensure(m.walk_cap); m.walks2.ensure(m.walk_cap);
-    d.walks = m.walks.p; d.walks_sorted = m.walks2.p; d.walk_cap = m.walk_cap;
+    m.walk_cap = nn + 1; m.walks.ensure(m.walk_cap);
+    d.walks = m.walks.p; d.walk_cap = m.walk_cap;
     k_reset_marks<<<(nn + 255) / 256, 256, 0, st>>>(d, nn); launches_++;
     chains_valid_ = false;  // chains stay valid as data; materialisation switches to the STOP-bit rule
     CK(cudaMemsetAsync(m.counters.p + 3, 0, sizeof(u32), st));
@@ -1618,45 +1863,18 @@ void AgDevice::walk_sequential() {
 
 void AgDevice::extend(std::vector<ag_walk>& walks) {
     CK(cudaSetDevice(dev_));
-    Impl& m = *m_; cudaStream_t st = m.st; DevView& d = m.view; u32 nn = m.n_nodes;
+    Impl& m = *m_; cudaStream_t st = m.st;
     walks.clear();
-    if (!nn) return;
-    m.walk_next.ensure(nn + 1); m.parent.ensure(nn + 1); m.cmin.ensure(nn + 1); m.cmax.ensure(nn + 1);
-    m.cmin.ensure((size_t)nn + 2);
-    d.walk_next = m.walk_next.p; d.parent = m.parent.p; d.cmin = m.cmin.p; d.cmax = m.cmax.p;
-    d.walk_count = m.counters.p + 3;
-    CK(cudaMemsetAsync(m.counters.p + 3, 0, sizeof(u32), st));
-    walk_components();
-    auto fetch = [&]() {
-        Timer tm(st);
-        volatile u32* hs = (volatile u32*)m.h_s.p;
-        u32 nw = 0;
-        const ag_walk* src = nullptr;
-        if (chains_valid_) {   // component replay: slot i belongs to candidate i; compact the used slots (candidates are in node = scan order)
-            const u32 nc = m.n_cand;
-            m.scanner.run(m.walk_used.p, m.cmin.p, nc, st);
-            if (nc) { k_walk_compact<<<(nc + 255) / 256, 256, 0, st>>>(d, nc, m.cmin.p); launches_++; }
-            CK(cudaMemcpyAsync((void*)(hs + 0), m.cmin.p + nc, sizeof(u32), cudaMemcpyDeviceToHost, st));
-            src = m.walks2.p;
-        } else {               // sequential replay: one thread appended the records in scan order
-            CK(cudaMemcpyAsync((void*)(hs + 0), m.counters.p + 3, sizeof(u32), cudaMemcpyDeviceToHost, st));
-            src = m.walks.p;
-        }
-        CK(cudaMemcpyAsync((void*)(hs + 1), m.err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        nw = hs[0];
-        if (hs[1]) throw AgError{"walk record buffer exhausted"};
-        walks.resize(nw);
-        if (nw) {
-            m.h_walks.ensure((size_t)nw * sizeof(ag_walk));
-            CK(cudaMemcpyAsync(m.h_walks.p, src, (size_t)nw * sizeof(ag_walk), cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            memcpy(walks.data(), m.h_walks.p, (size_t)nw * sizeof(ag_walk));
-        }
-        t_.d2h += tm.stop();
-        t_.d2h_bytes += (size_t)nw * sizeof(ag_walk);
-    };
-    fetch();
+    if (!m.build_queued && !m.n_nodes) return;   // (checked build of an empty unit)
+    for (;;) {
+        enqueue_walk();                 // behind the build, which may still be in flight
+        if (!finish()) break;           // ONE blocking synchronisation for the whole build + walk
+        enqueue_build();                // a capacity was exceeded: everything again with the larger one
+    }
+    if (!m.n_nodes) return;
+    walks.resize(m.n_walks);
+    if (m.n_walks) memcpy(walks.data(), m.h_wrec.p, (size_t)m.n_walks * sizeof(ag_walk));   // written by k_walk_compact straight into page-locked host memory
+    t_.d2h_bytes += (size_t)m.n_walks * sizeof(ag_walk);
     // the 1000-position skip of the reference's scan (AG:2194-2202) only matters once a contig longer than 100 kbp has been
     // emitted; detect that on the emitted sequence and, if so, replay sequentially on the device (exact, slow, rare)
     {
@@ -1668,7 +1886,23 @@ void AgDevice::extend(std::vector<ag_walk>& walks) {
             bool contained = have && bso <= r.soff && beo >= eoff;
             if (!contained) { bso = r.soff; beo = eoff; have = true; if (beo - bso > 100000u) trigger = true; }
         }
-        if (trigger) { walk_sequential(); fetch(); }
+        if (trigger) {
+            walk_sequential();
+            volatile u32* hs = (volatile u32*)m.h_s.p;
+            CK(cudaMemcpyAsync((void*)(hs + 0), m.counters.p + 3, sizeof(u32), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync((void*)(hs + 1), m.err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            const u32 nw = hs[0];
+            if (hs[1]) throw AgError{"walk record buffer exhausted"};
+            walks.resize(nw);
+            if (nw) {
+                m.h_walks.ensure((size_t)nw * sizeof(ag_walk));
+                CK(cudaMemcpyAsync(m.h_walks.p, m.walks.p, (size_t)nw * sizeof(ag_walk), cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                memcpy(walks.data(), m.h_walks.p, (size_t)nw * sizeof(ag_walk));
+            }
+            t_.d2h_bytes += (size_t)nw * sizeof(ag_walk);
+        }
     }
     t_.n_walks = walks.size();
 }
@@ -1753,6 +1987,7 @@ void AgDevice::occupancy_wait(std::vector<unsigned char>& bits) {
 
 void AgDevice::dump_nodes(AgNodeDump& dd) {
     CK(cudaSetDevice(dev_));
+    build_sync();
     Impl& m = *m_; cudaStream_t st = m.st; u32 nn = m.n_nodes, n_pos = m.n_pos;
     if (!keep_counts_ || !m.view.node_cc) throw AgError{"node dump needs the per-node counters: set option keep_counts before building"};
     std::vector<u32> pos_node((size_t)n_pos + 1), cc(6 * (size_t)nn), sref(2 * (size_t)nn), npos(nn);

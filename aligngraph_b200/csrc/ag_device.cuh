@@ -32,6 +32,7 @@ struct AgTimings {  // milliseconds, CUDA events on the context's stream
     u64 n_nodes = 0, n_edges_ovf = 0, n_walks = 0, n_keys = 0, n_tiles = 0, n_components = 0;
     u64 h2d_bytes = 0, d2h_bytes = 0;
     int walk_fallback = 0, regrows = 0;   // regrows: sweeps repeated with a larger node table / overflow pool
+    float stage = 0, build_kernel = 0;        // inside `nodes`: the staging gather (k_stage) and the node sweep kernel itself
     float ingest_reads = 0, ingest_sam = 0;   // ms: staging + kernels of the text ingestion (CUDA events)
     u64 sam_device = 0, sam_host = 0, reads_device = 0, reads_host = 0;   // files parsed on the device / by the host parser
 };
@@ -70,8 +71,11 @@ public:
     void set_option(const std::string& name, long value);
     // upload one unit's inputs (H2D, timed)
     void load_unit(const AgUnitInput& in);
-    // the hot path: prep -> bucket -> nodes (+ common-case edges) -> successor lists -> generic edges on flagged tiles  (all device)
+    // the hot path: prep -> bucket -> nodes (+ common-case edges) -> successor lists -> generic edges on flagged tiles  (all device).
+    // build() only QUEUES the kernels; errors and capacity overflows surface at the next synchronisation point — build_sync() (blocks,
+    // checks, repeats the build with larger capacities if needed) or extend(), which queues the walk behind the build and synchronises once
     void build();
+    void build_sync();
     // coverage filter + walk simulation; fills `walks` (unsorted on return from the device, sorted here by start node)
     void extend(std::vector<ag_walk>& walks);
     // materialise the selected walks' base strings (loop bases + tail); contig i occupies bases[offs[i], offs[i + 1]).  `bases` points into
@@ -109,8 +113,11 @@ private:
     bool reads_pending_ = false, mat_pending_ = false, occ_pending_ = false;
     void *ev_mat0_ = nullptr, *ev_mat1_ = nullptr; size_t mat_bytes_ = 0;
     std::vector<void*> pinned_;
+    bool tma_off_ = false, attr_tma_done_ = false;
     bool chains_valid_ = false, attr_done_ = false, keep_counts_ = false, section_timing_ = false;
-    void walk_components();
+    void enqueue_build();
+    void enqueue_walk();
+    bool finish();
     void walk_sequential();
 };
 

@@ -231,34 +231,38 @@ __global__ void __launch_bounds__(128) k_sam_fill(const char* __restrict__ text,
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
-// file -> device through page-locked staging chunks: host threads pread() slices of a chunk into pinned memory (page cache -> pinned
-// at memory speed), the copy engine moves the previous chunk meanwhile
+// file -> device through page-locked staging chunks.  T host threads each own two pinned slots and take the file's chunks round-robin:
+// pread() into a slot (page cache -> pinned memory at memory speed), queue the slot's host->device copy, move on to the other slot; a
+// slot is reused once its copy has finished.  The copy engine therefore always has several chunks queued while the next ones are read.
 // ---------------------------------------------------------------------------------------------------------------------------
 struct FileStager {
-    static constexpr size_t CHUNK = (size_t)32 << 20;
-    PinnedBuf ring[2]; cudaEvent_t ev[2] = {nullptr, nullptr};
-    void release() { for (int i = 0; i < 2; i++) { ring[i].release(); if (ev[i]) { cudaEventDestroy(ev[i]); ev[i] = nullptr; } } }
-    // copies file bytes [off, off + len) to dst (device), asynchronously on `st`
-    void run(int fd, size_t off, size_t len, char* dst, cudaStream_t st) {
-        const size_t cb = std::min(len, CHUNK);
-        for (int i = 0; i < 2; i++) { if (!ev[i]) CK(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming)); }
-        ring[0].ensure(cb); if (len > CHUNK) ring[1].ensure(cb);
-        int slot = 0;
-        for (size_t done = 0; done < len; done += CHUNK, slot ^= 1) {
-            const size_t n = std::min(CHUNK, len - done);
-            if (done >= 2 * CHUNK) CK(cudaEventSynchronize(ev[slot]));   // the copy that last used this slot has finished
-            char* h = ring[slot].p;
-            const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)ag_team_size(), n >> 20));
-            const size_t per = (n + T - 1) / T;
-            std::atomic<int> failed(0);
-            ag_parallel_chunks(T, [&](int t) {
-                size_t a = (size_t)t * per, e = std::min(n, a + per);
-                while (a < e) { const ssize_t got = pread(fd, h + a, e - a, (off_t)(off + done + a)); if (got <= 0) { failed = 1; return; } a += (size_t)got; }
-            });
-            if (failed) throw AgError{"CANNOT OPEN FILE!"};
-            CK(cudaMemcpyAsync(dst + done, h, n, cudaMemcpyHostToDevice, st));
-            CK(cudaEventRecord(ev[slot], st));
-        }
+    static constexpr size_t CHUNK = (size_t)8 << 20;
+    static constexpr int MAXT = 16;
+    PinnedBuf ring; cudaEvent_t ev[2 * MAXT]; bool made = false, used[2 * MAXT] = {};
+    void release() { ring.release(); if (made) for (int i = 0; i < 2 * MAXT; i++) cudaEventDestroy(ev[i]); made = false; }
+    // copies file bytes [off, off + len) to dst (device), asynchronously on `st` (every copy has been QUEUED when this returns)
+    void run(int fd, size_t off, size_t len, char* dst, cudaStream_t st, int device) {
+        if (!len) return;
+        if (!made) { for (int i = 0; i < 2 * MAXT; i++) CK(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming)); made = true; }
+        const size_t n_chunks = (len + CHUNK - 1) / CHUNK;
+        const int T = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>((size_t)ag_team_size(), MAXT), n_chunks));
+        ring.ensure((size_t)2 * MAXT * CHUNK);
+        std::atomic<int> failed(0);
+        ag_parallel_chunks(T, [&](int t) {
+            cudaSetDevice(device);
+            size_t j = 0;
+            for (size_t k = (size_t)t; k < n_chunks; k += (size_t)T, j++) {
+                const int slot = 2 * t + (int)(j & 1);
+                if (used[slot]) cudaEventSynchronize(ev[slot]);   // the copy that last read this slot (this call's or an earlier one's) has finished
+                char* h = ring.p + (size_t)slot * CHUNK;
+                const size_t o = k * CHUNK, n = std::min(CHUNK, len - o);
+                size_t a = 0;
+                while (a < n) { const ssize_t got = pread(fd, h + a, n - a, (off_t)(off + o + a)); if (got <= 0) { failed = 1; return; } a += (size_t)got; }
+                if (cudaMemcpyAsync(dst + o, h, n, cudaMemcpyHostToDevice, st) != cudaSuccess) { failed = 2; return; }
+                cudaEventRecord(ev[slot], st); used[slot] = true;
+            }
+        });
+        if (failed) throw AgError{failed == 1 ? "CANNOT OPEN FILE!" : "host->device copy of a staged chunk failed"};
     }
 };
 

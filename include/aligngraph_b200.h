@@ -65,6 +65,7 @@ typedef struct ag_stats {
     float ms_ingest_reads, ms_ingest_sam;
     uint64_t sam_device, sam_host, reads_device, reads_host;
     uint64_t regrows; /* sweeps repeated with a larger node table / node overflow pool / edge overflow pool */
+    float ms_stage, ms_build_kernel; /* inside ms_nodes: staging gather (k_stage) and the node sweep kernel (k_build_tma / k_build) */
 } ag_stats;
 
 int ag_create(const ag_params* params, ag_ctx** out);
@@ -104,6 +105,9 @@ int ag_set_contig_threads(ag_ctx* ctx, const ag_cthread_c* threads, uint32_t n_t
 int ag_add_alignments(ag_ctx* ctx, const ag_aln_c* aln, uint64_t n, const ag_seg_c* ext, uint64_t n_ext); /* parsing half of loadReadAlignment, AG:1872 */
 int ag_build(ag_ctx* ctx);   /* graph half of loadReadAlignment: updateGenomeWithRead / updateKMer, AG:1635-1870, AG:1353-1624 */
 int ag_extend(ag_ctx* ctx);  /* extendContigs + scaffoldContigs, AG:2382, AG:2396 */
+/* ag_build + ag_extend as one step: every kernel from the uploaded unit to the walk records is queued without a host round trip and the
+ * host synchronises once (ag_build alone synchronises at its end so that it can report its own errors) */
+int ag_process(ag_ctx* ctx);
 /* which: 0 = tmp/_initial_contigs.N.fa (file level only), 1 = tmp/_pre_extended_contigs.N.fa, 2 = tmp/_extended_contigs.N.fa */
 int ag_get_text(ag_ctx* ctx, int which, const char** text, uint64_t* len);
 
@@ -117,6 +121,10 @@ int ag_run_unit_files(ag_ctx* ctx, const char* tmp_dir, int unit_id);
  * threads parsing units ahead of the GPUs.  `done` (may be NULL) is called after every unit, serialised, possibly out of unit order. */
 int ag_run_units_files(ag_ctx** ctxs, int n_ctx, const char* tmp_dir, int first_unit, int n_units, int prefetch,
                        void (*done)(int unit, int rc, const char* error, void* user), void* user);
+/* the whole hot loop (AG:4765-4783) for a list of units, read set included: tmp/_reads.fa (reads_fa; NULL = the contexts already hold the
+ * reads) is ingested on ctxs[0]'s GPU and broadcast to the other contexts while the preparer threads already parse the first units */
+int ag_run_job_files(ag_ctx** ctxs, int n_ctx, const char* tmp_dir, const char* reads_fa, const int* units, int n_units, int prefetch,
+                     void (*done)(int unit, int rc, const char* error, void* user), void* user);
 /* staged arrays of the current unit (valid until the next ag_begin_unit / ag_prepare_unit_files) */
 typedef struct ag_unit_view {
     const char* ref; uint32_t n_ref, n_tail;
@@ -146,8 +154,9 @@ int ag_pin_staged(ag_ctx* ctx);
  * tmp/_chaff.fa, tmp/_genome.fa and tmp/_genome.N.fa; returns the number of units */
 int ag_formalize_inputs(ag_ctx* ctx, const char* contig_fa, const char* genome_fa, const char* tmp_dir, int part, int* n_units);
 /* tuning / test hooks: "host_parse" (1 = SAM and reads text parsed by the host parsers instead of the device kernels), "node_cap" / "ovf_cap" /
- * "eovf_cap" (initial capacities of the node table, the node overflow pool and the edge overflow pool; small values force the grow-and-redo
- * paths), "section_timing" (1 = CUDA-event timing of every pipeline section, which synchronises after each one; default 0) */
+ * "eovf_cap" / "key_cap" / "cand_cap" / "hwalk_cap" (initial capacities of the node table, the node overflow pool, the edge overflow pool, the
+ * tile-key buffers, the start-candidate arrays and the host walk-record buffer; small values force the grow-and-redo path), "rank_rounds"
+ * (global list-ranking rounds queued per step), "tma" (0 = node sweep with per-thread staging, k_build, instead of the bulk-async staged k_build_tma) */
 int ag_set_option(ag_ctx* ctx, const char* name, long value);
 int ag_timer_start(ag_ctx* ctx);
 int ag_timer_stop(ag_ctx* ctx, float* ms);

@@ -65,12 +65,16 @@ public:
         cm1.resize((size_t)n_pos + 1);
         std::vector<u32> many_prefix((size_t)n_pos + 1, 0);
         for (u32 p = 0; p < n_pos; p++) { cm1[p] = ag_make_cm1(ct, p); many_prefix[p + 1] = many_prefix[p] + (cm1[p].cid == AG_CM_MANY ? 1u : 0u); }
+        std::vector<u32> lin_prefix((size_t)n_pos + 1, 0);   // exclusive scan of the break flags (k_cm1 + scan on the device)
+        for (u32 p = 0; p < n_pos; p++) lin_prefix[p + 1] = lin_prefix[p] + (p ? ag_cm1_break(cm1[p - 1], cm1[p]) : 0u);
+        const bool no_linear = getenv("AG_EMUL_NO_LINEAR") != nullptr;
         for (u32 i = 0; i < nA; i++) {  // k_prep + k_keys + sort
             ag_prep_out o = ag_prep(in.aln[i], in.ext, rd.len[in.aln[i].pair], (u32)k);
-            alnp[i] = o.p; fast[i] = ag_fast_prep(o.p, o.lo, o.span);
+            alnp[i] = o.p; fast[i] = ag_fast_prep(o.p, o.lo, o.span, i);
             if (!o.any) continue;
             if (o.lo + o.span >= n_ref) throw AgHostError{"BOWTIE ALIGNMENT ERROR"};
-            if (ag_fast_is_clean(fast[i], o.p, many_prefix.data())) fast[i].simple |= AG_FAST_CLEAN;
+            ag_fast_classify(fast[i], o.p, many_prefix.data(), lin_prefix.data(), cm1.data());
+            if (no_linear) fast[i].simple &= ~AG_FAST_LINEAR;
             u32 t0, t1; ag_tile_range(o.lo, o.lo + o.span, n_tiles, t0, t1);
             for (u32 t = t0; t <= t1; t++) tiles[t].push_back(i);
         }

@@ -51,3 +51,19 @@ def test_oracle_edge_cases_match_live_reference(harness, workdir, kind):
     assert rc == 0
     harness.run_oracle(ora)
     assert harness.unit_outputs(ref, 0) == harness.unit_outputs(ora, 0)
+
+
+def test_oracle_matches_live_reference_full_size_unit(harness, workdir):
+    """At size: BASELINE configs[1] (4.6 Mbp unit, 1.15 M pairs 2x100 at 50x — more than one 1,000,000-pair batch, AlignGraph.cpp:1259 / :390)
+    through the unmodified reference (-O2 build) and through the restatement: all three per-unit files byte-identical.  This pins the
+    oracle above the 1 M-pair mark, where the sha fixtures of the larger configurations (tests/golden/fullsize.json) rely on it."""
+    if not harness.have_reference():
+        pytest.skip("reference not built here (oracle/_ref absent)")
+    ref = os.path.join(workdir, "ref")
+    ora = os.path.join(workdir, "ora")
+    harness.synth(ref, genome_bp=4600000, coverage=50, readlen=100, insert_mean=500, insert_sd=50, kmer=5, cov=20, seed=20260927, user_reads=0)
+    shutil.copytree(ref, ora)
+    rc, _ = harness.run_reference(ref, optimized=True)
+    assert rc == 0
+    harness.run_oracle(ora)
+    assert harness.unit_outputs(ref, 0) == harness.unit_outputs(ora, 0)

@@ -26,8 +26,8 @@ for mode in ("device", "host"):
         ctx.reset_stats()
         t0 = time.perf_counter(); ctx.load_reads_fasta(os.path.join(tmp, "_reads.fa")); t1 = time.perf_counter()
         ctx.prepare_unit(tmp, 0); t2 = time.perf_counter()
-        ctx.build(); t3 = time.perf_counter()
-        ctx.extend(); t4 = time.perf_counter()
+        t3 = time.perf_counter()
+        ctx.process(); t4 = time.perf_counter()
         ctx.write_unit(tmp, 0); t5 = time.perf_counter()
         st = ctx.stats()
         rows.append(dict(reads=t1 - t0, prepare=t2 - t1, build=t3 - t2, extend=t4 - t3, write=t5 - t4, total=t5 - t0,
