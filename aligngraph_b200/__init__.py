@@ -30,7 +30,7 @@ class Stats(C.Structure):
                [(n, C.c_uint64) for n in ("n_aln", "n_nodes", "n_walks", "n_emitted", "n_keys", "n_tiles", "kernel_launches",
                                           "h2d_bytes", "d2h_bytes")] + \
                [("walk_fallback", C.c_int), ("ms_ingest_reads", C.c_float), ("ms_ingest_sam", C.c_float)] + \
-               [(n, C.c_uint64) for n in ("sam_device", "sam_host", "reads_device", "reads_host", "regrows")] + \
+               [(n, C.c_uint64) for n in ("sam_device", "sam_host", "reads_device", "reads_host", "regrows", "reads_windowed")] + \
                [("ms_stage", C.c_float), ("ms_build_kernel", C.c_float)]
 
     def as_dict(self):
@@ -91,6 +91,7 @@ def load_library(path=None):
         "ag_pin_staged": (i32, [vp]),
         "ag_formalize_inputs": (i32, [vp, cp, cp, cp, i32, C.POINTER(i32)]),
         "ag_set_option": (i32, [vp, cp, C.c_long]),
+        "ag_remove_misassembly_file": (i32, [vp, cp, cp, i32, cp, vp, vp]),
         "ag_timer_start": (i32, [vp]),
         "ag_timer_stop": (i32, [vp, C.POINTER(C.c_float)]),
     }

@@ -28,10 +28,13 @@ struct ag_ctx {
     double s_parse = 0, s_device = 0, s_post = 0;
     u64 n_aln = 0, n_walks = 0, n_emitted = 0;
     bool host_parse = getenv("AG_HOST_PARSE") != nullptr;
+    bool reads_window = getenv("AG_NO_READS_WINDOW") == nullptr;   // job-level loads may restrict the resident read set to the ids the job's SAM files reference
+    std::string reads_path;                                         // where the resident read set came from (to load the rest when a window turns out too small)
     bool fused = false;
 };
 
 static std::string g_create_error;
+extern "C" { static void load_reads_impl(ag_ctx* ctx, const char* path, long long win_lo, long long win_hi); }
 
 static bool device_ingest_enabled(const ag_ctx* ctx) { return !ctx->host_parse; }   // AG_HOST_PARSE=1 / option "host_parse": text is parsed by the host parsers only
 
@@ -49,6 +52,11 @@ static void load_unit_sam(ag_ctx* ctx, const std::string& tmp, int unit_id) {
     const std::string path = tmp + "/_reads_genome." + std::to_string(unit_id) + ".bowtie";
     u.aln.clear(); u.ext.clear(); u.aln_on_device = false;
     if (device_ingest_enabled(ctx) && ctx->dev->ingest_sam(path)) { u.aln_on_device = true; return; }
+    if (ctx->rp->windowed()) {   // only a window of the read set is resident and this file needs more (or the host parser
+        if (ctx->reads_path.empty()) throw AgHostError{"reads not set"};    // does, which looks up any read's length): load the whole set, then try again
+        load_reads_impl(ctx, ctx->reads_path.c_str(), -1, -1);
+        if (device_ingest_enabled(ctx) && ctx->dev->ingest_sam(path)) { u.aln_on_device = true; return; }
+    }
     ag_parse_sam(path, *ctx->rp, u);
     ctx->dev->note_host_sam();
 }
@@ -119,11 +127,15 @@ int ag_set_read_exceptions(ag_ctx* ctx, const uint64_t* keys, const char* chars,
     return guard(ctx, [&] { (*ctx->rp).exc.clear(); (*ctx->rp).exc_complete = false; for (uint64_t i = 0; i < n; i++) (*ctx->rp).exc.push_back({keys[i], chars[i]}); });
 }
 int ag_load_reads_fasta(ag_ctx* ctx, const char* path) {
-    return guard(ctx, [&] {
+    return guard(ctx, [&] { load_reads_impl(ctx, path, -1, -1); });
+}
+static void load_reads_impl(ag_ctx* ctx, const char* path, long long win_lo, long long win_hi) {
+    {
         ctx->dev->unpin_all();
+        ctx->reads_path = path;
         auto t0 = std::chrono::steady_clock::now();
         ctx->rp = std::make_shared<AgReads>();
-        if (device_ingest_enabled(ctx) && ctx->dev->ingest_reads(path, *ctx->rp)) {   // raw text -> device, packed there (ag_ingest.cuh)
+        if (device_ingest_enabled(ctx) && ctx->dev->ingest_reads(path, *ctx->rp, win_lo, win_hi)) {   // raw text -> device, packed there (ag_ingest.cuh)
             ctx->s_parse += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
             ctx->have_reads = true; ctx->reads_dirty = false;
             return;
@@ -134,7 +146,7 @@ int ag_load_reads_fasta(ag_ctx* ctx, const char* path) {
         upload_reads(ctx);
         ctx->dev->note_host_reads();
         ctx->have_reads = true;
-    });
+    }
 }
 int ag_get_reads(ag_ctx* ctx, const uint32_t** bases2, const uint32_t** nmask, const uint16_t** pair_len, uint64_t* n_pairs, uint32_t* stride2, uint32_t* stridem) {
     return guard(ctx, [&] {
@@ -284,6 +296,30 @@ int ag_run_unit_files(ag_ctx* ctx, const char* tmp_dir, int unit_id) {
 // packed arrays) while one worker thread per context uploads, builds, extends and writes.  Units are handed out in order; outputs do
 // not depend on the number of contexts or on timing (units are independent, AG:4779-4781).  `done` is called (serialised) after every
 // unit with its return code; the first failing unit's code is returned.
+// first and last read id of a SAM file (QNAME of the first record after the '@' lines and of the last line); false when there is no record
+static bool sam_id_range(const std::string& path, long long& lo, long long& hi) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    bool ok = false;
+    char buf[1 << 16];
+    auto id_of = [](const char* s, const char* e, long long& v) { v = 0; const char* p = s; bool any = false; while (p < e && *p >= '0' && *p <= '9') { v = v * 10 + (*p - '0'); p++; any = true; } return any && p < e && *p == '\t'; };
+    size_t got = fread(buf, 1, sizeof buf, f);
+    const char* p = buf; const char* e = buf + got;
+    while (p < e && *p == '@') { const char* l = (const char*)memchr(p, '\n', (size_t)(e - p)); if (!l) { p = e; break; } p = l + 1; }
+    if (p < e && id_of(p, e, lo)) {
+        if (fseek(f, 0, SEEK_END) == 0) {
+            const long n = ftell(f); const long w = n < (long)sizeof buf ? n : (long)sizeof buf;
+            if (fseek(f, n - w, SEEK_SET) == 0 && (got = fread(buf, 1, (size_t)w, f)) == (size_t)w && w > 1 && buf[w - 1] == '\n') {
+                long i = w - 2;
+                while (i >= 0 && buf[i] != '\n') i--;
+                if ((i >= 0 || w == n) && id_of(buf + i + 1, buf + w, hi)) ok = true;
+            }
+        }
+    }
+    fclose(f);
+    return ok;
+}
+
 // The whole hot loop for a list of units: [reads] -> per unit (host: genome + contig threads; device: SAM, graph build, walk; host: post passes,
 // files).  `prefetch` host threads prepare units ahead (in list order) while one worker thread per context runs them; with reads_fa != NULL
 // the read set is (re)loaded as part of the job — raw text to ctxs[0]'s GPU, one broadcast to the others — while the preparers already work
@@ -353,7 +389,14 @@ static int run_units_impl(ag_ctx** ctxs, int n_ctx, const char* tmp_dir, const s
     };
     std::vector<std::thread> th;
     auto load_reads = [&]() -> int {
-        int rc = ag_load_reads_fasta(ctxs[0], reads_fa);
+        // only the reads the job's SAM files can reference need to be resident: the id window spanned by their first and last records (files
+        // are in read order, AG:3602 --reorder); a record outside it is noticed when its SAM is parsed and the whole set is loaded then
+        long long wlo = -1, whi = -1;
+        if (ctxs[0]->reads_window && !host_sam && n_units) {
+            for (int u : units) { long long a, b; if (sam_id_range(tmp + "/_reads_genome." + std::to_string(u) + ".bowtie", a, b)) { if (a > b) std::swap(a, b); wlo = wlo < 0 ? a : std::min(wlo, a); whi = std::max(whi, b); } }
+            if (wlo < 0) wlo = whi = 0;   // no record anywhere: nothing will be looked up
+        }
+        int rc = guard(ctxs[0], [&] { load_reads_impl(ctxs[0], reads_fa, wlo, whi); });
         if (!rc && n_ctx > 1) rc = ag_broadcast_reads(ctxs, n_ctx, nullptr);
         return rc;
     };
@@ -402,7 +445,7 @@ int ag_get_stats(ag_ctx* ctx, ag_stats* o) {
         o->ms_components = t.components; o->ms_chains = t.chains; o->ms_walk = t.walk; o->ms_materialize = t.materialize; o->ms_d2h = t.d2h;
         o->s_parse = ctx->s_parse; o->s_device_section = ctx->s_device; o->s_post = ctx->s_post;
         o->n_aln = ctx->n_aln; o->n_nodes = t.n_nodes; o->n_walks = ctx->n_walks; o->n_emitted = ctx->n_emitted; o->n_keys = t.n_keys; o->n_tiles = t.n_tiles;
-        o->ms_ingest_reads = t.ingest_reads; o->ms_ingest_sam = t.ingest_sam; o->sam_device = t.sam_device; o->sam_host = t.sam_host; o->reads_device = t.reads_device; o->reads_host = t.reads_host; o->regrows = (uint64_t)t.regrows; o->ms_stage = t.stage; o->ms_build_kernel = t.build_kernel;
+        o->ms_ingest_reads = t.ingest_reads; o->ms_ingest_sam = t.ingest_sam; o->sam_device = t.sam_device; o->sam_host = t.sam_host; o->reads_device = t.reads_device; o->reads_host = t.reads_host; o->regrows = (uint64_t)t.regrows; o->reads_windowed = t.reads_windowed; o->ms_stage = t.stage; o->ms_build_kernel = t.build_kernel;
         o->kernel_launches = ctx->dev->kernel_launches(); o->h2d_bytes = t.h2d_bytes; o->d2h_bytes = t.d2h_bytes; o->walk_fallback = t.walk_fallback;
     });
 }
@@ -448,10 +491,24 @@ int ag_pin_staged(ag_ctx* ctx) {
         d.pin(u.aln.data(), u.aln.size() * sizeof(ag_aln)); d.pin(u.ext.data(), u.ext.size() * sizeof(ag_seg));
     });
 }
+// removeMisassembly (AG:4281-4297) for one output file; the per-base coverage pile-up runs on the context's GPU
+int ag_remove_misassembly_file(ag_ctx* ctx, const char* file, const char* id, int coverage, const char* tmp_dir, int (*align)(const char* id, void* user), void* user) {
+    return guard(ctx, [&] {
+        struct U { ag_ctx* ctx; int (*align)(const char*, void*); void* user; } u{ctx, align, user};
+        ag_remove_misassembly(file, id, coverage, tmp_dir,
+            [](const std::string& id_, void* p) -> bool { U* q = (U*)p; return q->align ? q->align(id_.c_str(), q->user) != 0 : true; },
+            [](const std::string& sam, const std::vector<u32>& len, std::vector<int>& cov, void* p) {
+                U* q = (U*)p;
+                if (!q->ctx->host_parse && q->ctx->dev->coverage_pileup(sam, len, cov)) return;
+                ag_coverage_pileup_host(sam, len, cov, nullptr);
+            }, &u);
+    });
+}
 int ag_set_option(ag_ctx* ctx, const char* name, long value) {
     return guard(ctx, [&] {
         const std::string n = name ? name : "";
         if (n == "host_parse") ctx->host_parse = value != 0;
+        else if (n == "reads_window") ctx->reads_window = value != 0;
         else if (n == "node_cap" || n == "ovf_cap" || n == "eovf_cap" || n == "key_cap" || n == "cand_cap" || n == "hwalk_cap" || n == "rank_rounds" || n == "tma") ctx->dev->set_option(n, value);
         else throw AgHostError{"unknown option: " + n};
     });

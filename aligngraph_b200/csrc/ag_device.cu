@@ -502,23 +502,25 @@ static_assert(sizeof(ag_fast) == ST_HDR_W * 4, "staged header = ag_fast");
 __global__ void k_stage(DevView d, u32* __restrict__ stage, u32 rsw) {
     if (*(volatile int*)d.err & E_KEY_CAP) return;
     const ag_reads rd = d.reads;
-    AG_FOR_N(i, min(*d.nk_ptr, d.key_cap)) {
-        const u32 idx = d.vals[i];
-        const uint4* src = reinterpret_cast<const uint4*>(d.fast + idx);
-        uint4* dst = reinterpret_cast<uint4*>(stage + (size_t)i * rsw);
-        const uint4 h0 = src[0], h1 = src[1], h2 = src[2];
-        dst[0] = h0; dst[1] = h1; dst[2] = h2;
-        const u32 read_rc = h1.z, len = h0.z >> 16, read = read_rc >> 1;
-        const u32* b = rd.bases + (u64)read * rd.stride2; const u32* mk = rd.nmask + (u64)read * rd.stridem;
-        u32* cw = stage + (size_t)i * rsw + ST_HDR_W;
-        const u32 nw = (len + 7) >> 3;
-        for (u32 j = 0; j < rsw - ST_HDR_W; j += 4) {
+    const u64 nk = min(*d.nk_ptr, d.key_cap);
+    const u32 vecs = rsw >> 2;                                      // 16-byte vectors per record
+    // eight lanes per key, one 16-byte vector each (more for long reads): a record goes out as one contiguous 16 x vecs byte burst
+    for (u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x, stride = (u64)gridDim.x * blockDim.x; g < nk * 8; g += stride) {
+        const u64 key = g >> 3;
+        const u32 idx = d.vals[key];
+        const ag_fast* f = d.fast + idx;
+        uint4* dst = reinterpret_cast<uint4*>(stage + key * rsw);
+        for (u32 part = (u32)(g & 7); part < vecs; part += 8) {
+            if (part < ST_HDR_W / 4) { dst[part] = reinterpret_cast<const uint4*>(f)[part]; continue; }
+            const u32 read_rc = f->read, len = f->lsrc_len >> 16, read = read_rc >> 1, rc = read_rc & 1, nw = (len + 7) >> 3;
+            const u32* b = rd.bases + (u64)read * rd.stride2; const u32* mk = rd.nmask + (u64)read * rd.stridem;
+            const u32 j = (part - ST_HDR_W / 4) * 4;
             uint4 w;
-            w.x = j + 0 < nw ? ag_code4_word(b, mk, rd.stride2, rd.stridem, read_rc & 1, len, j + 0) : 0u;
-            w.y = j + 1 < nw ? ag_code4_word(b, mk, rd.stride2, rd.stridem, read_rc & 1, len, j + 1) : 0u;
-            w.z = j + 2 < nw ? ag_code4_word(b, mk, rd.stride2, rd.stridem, read_rc & 1, len, j + 2) : 0u;
-            w.w = j + 3 < nw ? ag_code4_word(b, mk, rd.stride2, rd.stridem, read_rc & 1, len, j + 3) : 0u;
-            *reinterpret_cast<uint4*>(cw + j) = w;
+            w.x = j + 0 < nw ? ag_code4_word(b, mk, rd.stride2, rd.stridem, rc, len, j + 0) : 0u;
+            w.y = j + 1 < nw ? ag_code4_word(b, mk, rd.stride2, rd.stridem, rc, len, j + 1) : 0u;
+            w.z = j + 2 < nw ? ag_code4_word(b, mk, rd.stride2, rd.stridem, rc, len, j + 2) : 0u;
+            w.w = j + 3 < nw ? ag_code4_word(b, mk, rd.stride2, rd.stridem, rc, len, j + 3) : 0u;
+            dst[part] = w;
         }
     }
 }
@@ -530,6 +532,30 @@ __device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
 }
 __device__ __forceinline__ void bulk_g2s(u32 dst_smem, const void* src, u32 bytes, u32 bar) {   // 1-D TMA: global -> shared, completion counted in bytes on the mbarrier
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" :: "r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// shared-memory accesses of the sweep's inner loop through 32-bit shared-space addresses (no generic-pointer arithmetic, no cvta in the loop)
+__device__ __forceinline__ u32 lds1(u32 a) { u32 v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint2 lds2(u32 a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ uint4 lds4(u32 a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
+__device__ __forceinline__ void sts1(u32 a, u32 v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+constexpr u32 SLOT_FB = AG_NODE_SCAP * AG_TILE * 4;   // bytes between two fields of a thread's slots
+constexpr u32 SLOT_NB = AG_TILE * 4;                  // bytes between its two slots
+// |a - b| <= thr as the reference computes it on unsigned operands (abs((int)(a - b)), AG:1296): one add and one unsigned compare (thr < 2^30)
+__device__ __forceinline__ bool within(u32 a, u32 b, u32 thr) { return (a - b + thr) <= 2u * thr; }
+// clauses 2 and 3 of compatible() (AG:1300-1310) against slot `s` of this thread
+__device__ __forceinline__ bool slot_compatible(u32 saddr, u32 s, u32 cid0, u32 coff0, u32 moff, u32 thr) {
+    const u32 b = saddr + s * SLOT_NB;
+    const u32 ycid0 = lds1(b + AG_F_CID0 * SLOT_FB), ycoff0 = lds1(b + AG_F_COFF0 * SLOT_FB), ymoff = lds1(b + AG_F_MOFF * SLOT_FB);
+    const bool c2 = cid0 == AG_NONE || ycid0 == AG_NONE || cid0 != ycid0 || within(coff0, ycoff0, thr);
+    const bool c3 = moff == AG_NONE || ymoff == AG_NONE || within(moff, ymoff, thr);
+    return c2 && c3;
+}
+__device__ __forceinline__ void slot_bump(u32 saddr, u32 s, u32 code) {   // coverage and the base counter of an ordinary (k1) touch
+    const u32 b = saddr + s * SLOT_NB;
+    sts1(b + AG_F_COV * SLOT_FB, lds1(b + AG_F_COV * SLOT_FB) + 1u);
+    const u32 c = b + (AG_F_CNT + code) * SLOT_FB;
+    sts1(c, lds1(c) + 1u);
 }
 
 __global__ void __launch_bounds__(AG_TILE, AG_NODES_MINB) k_build_tma(DevView d, const u32* __restrict__ stage, u32 rsw) {
@@ -562,31 +588,63 @@ __global__ void __launch_bounds__(AG_TILE, AG_NODES_MINB) k_build_tma(DevView d,
     ag_plist pl; pl.n = 0; pl.ovf_head = pl.ovf_tail = AG_NONE;
     ag_cm1 ca; ca.cid = ca.coff = AG_NONE;
     if (active) ca = d.cm1[q];
-    const u32 kmer = (u32)d.k;
+    const u32 kmer = (u32)d.k, thr = (u32)(2 * d.iv + 5 * AG_EP), rs_bytes = rsw * 4;
+    // values the loop keeps in registers (opaque to the compiler, which would otherwise re-derive them from special registers every iteration)
+    u32 qp = active ? q : 0xFFFFFFF0u, wq = wq0, saddr = sv.saddr, edge_lane = lane < AG_WPOS ? 1u : 0u;
+    asm volatile("" : "+r"(qp), "+r"(wq), "+r"(saddr), "+r"(edge_lane));
+    const bool slots_mode = ca.cid != AG_CM_MANY;
     for (u32 c = 0; c < nchunks; c++) {
         const u32 cn = min((u32)ST_CH, ke - (kb + c * ST_CH));
         mbar_wait(bar0 + 8 * (c & 1), (c >> 1) & 1);
-        const u32* buf = s_dyn + STAGE0 + (c & 1) * (ST_CH * rsw);
+        const u32 buf_s = stage_s + (c & 1) * chunk_bytes;            // shared-space address of this chunk's records
         for (u32 r0 = 0; r0 < cn; r0 += 32) {
             // which of these 32 records touch any of the warp's 32 positions?
             bool ov = false;
-            if (r0 + lane < cn) { const uint2 ls = *reinterpret_cast<const uint2*>(buf + (r0 + lane) * rsw); ov = ls.x <= wq0 + 31 && ls.x + ls.y >= wq0; }
+            if (r0 + lane < cn) { const uint2 ls = lds2(buf_s + (r0 + lane) * rs_bytes); ov = ls.x <= wq + 31 && ls.x + ls.y >= wq; }
             u32 mask = __ballot_sync(0xFFFFFFFFu, ov);
             while (mask) {
                 const u32 a = r0 + (u32)__ffs((int)mask) - 1;
                 mask &= mask - 1;
-                const u32* rec = buf + a * rsw;
-                const ag_fast& f = *reinterpret_cast<const ag_fast*>(rec);   // fields are read from shared memory where they are used
+                const u32 rec = buf_s + a * rs_bytes;
+                const uint2 ls = lds2(rec);                          // lo, span
+                const u32 dq = qp - ls.x;
                 u32 item = AG_NONE; bool want = false;
-                if (active && q - f.lo <= f.span) {
-                    const u32* cw = rec + ST_HDR_W;
-                    auto codef = [=](u32 soff) -> int { return (int)((cw[soff >> 3] >> ((soff & 7) * 4)) & 7u); };
-                    item = ag_lane_touch(want, pl, sv, d.ovf, d.cmt, d.cm1, ca, f, d.alnp + f.aln, d.ext, q, kmer, d.iv, false, codef);
+                if (dq <= ls.y) {                                   // (inactive lanes carry a position no alignment reaches)
+                    const uint4 h1 = lds4(rec + 16);                // mlen, mdelta, read, flags
+                    if (slots_mode && (h1.w & (AG_FAST_CLEAN | AG_FAST_LINEAR)) == (AG_FAST_CLEAN | AG_FAST_LINEAR)) {
+                        // the common case: one candidate, its mate-side fields by arithmetic; first-compatible scan over the two shared-memory slots
+                        const uint2 h0 = lds2(rec + 8);             // lsrc | len << 16, mlo
+                        const uint2 h2 = lds2(rec + 32);            // mcid0, mcd
+                        const bool pm = (qp - h0.y) < h1.x;
+                        const u32 moff = pm ? qp + h1.y : AG_NONE;
+                        const u32 cid0 = pm ? h2.x : AG_NONE;
+                        const u32 coff0 = cid0 != AG_NONE ? qp + h2.y : AG_NONE;
+                        const bool bump = dq < ls.y;                // a call starts here (kind 1); else the stand-alone k2 of the last call
+                        const u32 aoff = (h0.x & 0xFFFFu) + dq;
+                        u32 code = 0;
+                        if (bump) code = (lds1(rec + ST_HDR_W * 4 + ((aoff >> 3) << 2)) >> ((aoff & 7u) << 2)) & 7u;
+                        want = bump;
+                        if (pl.n >= 1 && slot_compatible(saddr, 0, cid0, coff0, moff, thr)) { if (bump) slot_bump(saddr, 0, code); item = 0; }
+                        else if (pl.n >= 2 && slot_compatible(saddr, 1, cid0, coff0, moff, thr)) { if (bump) slot_bump(saddr, 1, code); item = 1; }
+                        else {   // a new node, or one of the (rare) nodes beyond the two slots: the general routine (it rescans the slots, harmlessly)
+                            ag_nodem cm; cm.cid = ca.cid; cm.coff = ca.coff; cm.cid0 = cid0; cm.coff0 = coff0; cm.moff = moff;
+                            const u32 len = h0.x >> 16, slen = bump ? kmer : ag_min_u32(kmer, len - aoff);
+                            item = ag_touch_slots(pl, sv, d.ovf, cm, bump, bump && slen ? (int)code : -1, h1.z, aoff | (slen << 16), d.iv);
+                        }
+                    } else {
+                        ag_fast f;
+                        { const uint4 g0 = lds4(rec), g2 = lds4(rec + 32);
+                          f.lo = g0.x; f.span = g0.y; f.lsrc_len = g0.z; f.mlo = g0.w; f.mlen = h1.x; f.mdelta = h1.y; f.read = h1.z; f.simple = h1.w; f.mcid0 = g2.x; f.mcd = g2.y; f.aln = g2.z; f.pad = 0; }
+                        const u32 cws = rec + ST_HDR_W * 4;
+                        auto codef = [=](u32 soff) -> int { return (int)((lds1(cws + ((soff >> 3) << 2)) >> ((soff & 7u) << 2)) & 7u); };
+                        item = ag_lane_touch(want, pl, sv, d.ovf, d.cmt, d.cm1, ca, f, d.alnp + f.aln, d.ext, qp, kmer, d.iv, false, codef);
+                    }
                 }
                 // the call that starts at q continues on the item the next lane resolved for this alignment
                 const u32 nb = __shfl_down_sync(0xFFFFFFFFu, item, 1);
-                if (want && lane < AG_WPOS) {
-                    if (item != AG_NONE && nb < 32u) ag_note_succ(pl, sv, d.ovf, item, nb);
+                if (want && edge_lane) {
+                    if (item < (u32)AG_NODE_SCAP && nb < 32u) { const u32 sa = saddr + item * SLOT_NB + AG_F_SUCC * SLOT_FB; sts1(sa, lds1(sa) | (1u << nb)); }
+                    else if (item != AG_NONE && nb < 32u) ag_note_succ(pl, sv, d.ovf, item, nb);
                     else atomicOr(&s_flag, item == AG_NONE ? 1u : 2u);   // 1: not a clean alignment; 2: successor item does not fit the mask
                 }
             }
@@ -1100,23 +1158,28 @@ struct Timer {   // section timer: CUDA events on the launching stream; the even
                                  if (!ev[0] || dev != cur) { cudaEventCreate(&ev[0]); cudaEventCreate(&ev[1]); dev = cur; } return ev; }
     Timer(cudaStream_t s) : st(s) { cudaEvent_t* e = pair(); a = e[0]; b = e[1]; cudaEventRecord(a, st); }
     float stop() { cudaEventRecord(b, st); cudaEventSynchronize(b); float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    double lap_ms() const { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() * 1e3; }
 };
 
 // Section times without stalling the stream: an event pair per section is only RECORDED while the step is being queued; the elapsed
 // times are read after the step's single synchronisation point (collect()).
 struct SectionTimes {
     static constexpr int MAX = 64;
-    cudaEvent_t ev[2 * MAX]; float* dst[MAX]; int n = 0, made = 0;
-    void begin(cudaStream_t st, float* where) {
-        if (n == MAX) { cudaStreamSynchronize(st); collect(); }
+    cudaEvent_t ev[2 * MAX]; float* dst[MAX]; int n = 0, made = 0, open = 0;
+    int begin(cudaStream_t st, float* where) {   // sections may nest: every one owns its event pair from begin()
+        if (n == MAX && open == 0) { cudaStreamSynchronize(st); collect(); }
+        if (n == MAX) return -1;
         while (made <= n) { cudaEventCreate(&ev[2 * made]); cudaEventCreate(&ev[2 * made + 1]); made++; }
-        dst[n] = where; cudaEventRecord(ev[2 * n], st);
+        const int id = n++;
+        dst[id] = where; cudaEventRecord(ev[2 * id], st); open++;
+        return id;
     }
-    void end(cudaStream_t st) { cudaEventRecord(ev[2 * n + 1], st); n++; }
+    void end(cudaStream_t st, int id) { if (id >= 0) { cudaEventRecord(ev[2 * id + 1], st); open--; } }
     void collect() { for (int i = 0; i < n; i++) { float ms = 0; if (cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]) == cudaSuccess) *dst[i] += ms; } n = 0; }   // after a sync that covers every recorded event
     void release() { for (int i = 0; i < 2 * made; i++) cudaEventDestroy(ev[i]); made = n = 0; }
 };
-struct Section { SectionTimes& t; cudaStream_t st; Section(SectionTimes& t_, cudaStream_t s, float* where) : t(t_), st(s) { t.begin(st, where); } ~Section() { t.end(st); } };
+struct Section { SectionTimes& t; cudaStream_t st; int id; Section(SectionTimes& t_, cudaStream_t s, float* where) : t(t_), st(s), id(t_.begin(s, where)) {} ~Section() { t.end(st, id); } };
 
 }  // namespace
 
@@ -1142,6 +1205,8 @@ struct AgDevice::Impl {
     DBuf<char> contig_blob; u64 blob_version = 0; DBuf<ag_cdesc> cdesc; DBuf<ag_crun> cruns;   // run-space contig threads
     DBuf<char> raw, exc_chr; DBuf<u32> nl, nl_blk, rlen, s_keep, s_next, s_aoff, s_eoff, s_lost, ing; DBuf<u64> exc_key; DBuf<ag_srec> srec; FileStager stager;
     u64 n_ext = 0; bool aln_ingested = false;
+    u64 win_lo = 0, win_hi = ~0ull;   // pair-id window of the read set that is resident (everything by default)
+    bool window_miss = false;          // the last ingest_sam met a read id outside the window
     // newline index of text[0, len) (device, 16-byte aligned, zero-padded to a multiple of 16).  fill == false: count (block offsets go to
     // nl_blk[blk_base ..]) and return the number of lines — one blocking read-back; fill == true: write the positions to nl[nl_base ..]
     u32 nl_index(cudaStream_t st, u64& launches, const char* text, size_t len, size_t blk_base, size_t nl_base, bool fill);
@@ -1165,6 +1230,7 @@ AgDevice::AgDevice(int device) : m_(new Impl), dev_(device) {
     CK(cudaStreamCreateWithFlags(&m_->st, cudaStreamNonBlocking));
     stream_ = m_->st;
     m_->scanner.launches = &launches_;
+    if (const char* e = getenv("AG_TMA")) tma_off_ = atoi(e) == 0;   // AG_TMA=0: node sweep with per-thread staging (k_build) instead of the bulk-async staged one
     m_->counters.ensure(8); m_->err.ensure(1); m_->h_s.ensure(256); m_->status.ensure(16); m_->err_load.ensure(1); CK(cudaMemset(m_->err_load.p, 0, sizeof(int)));
 }
 AgDevice::~AgDevice() {
@@ -1191,6 +1257,10 @@ AgDevice::~AgDevice() {
     delete m_;
 }
 
+void AgDevice::set_params(int k, int iv, int coverage) {
+    if (iv < 0 || iv > (1 << 28)) throw AgError{"--insertVariation out of range"};   // (the reference's 2 * iv + 25 is an int; the sweeps compare |a - b| <= 2 iv + 25 with one unsigned add)
+    k_ = k; iv_ = iv; cov_ = coverage;
+}
 void AgDevice::set_option(const std::string& name, long value) {
     Impl& m = *m_;
     if (name == "node_cap") { m.node_cap_hook = (u32)std::max<long>(value, 1); m.unit_n_ref = 0; }
@@ -1234,6 +1304,7 @@ void AgDevice::sync() { CK(cudaSetDevice(dev_)); if (st2_) CK(cudaStreamSynchron
 void AgDevice::set_reads(const u32* bases, const u32* nmask, const uint16_t* len, u64 n_pairs, u32 stride2, u32 stridem, bool on_device) {
     CK(cudaSetDevice(dev_));
     Impl& m = *m_;
+    m.win_lo = 0; m.win_hi = ~0ull;
     m.n_pairs = n_pairs;
     if (on_device) {
         m.reads.bases = bases; m.reads.nmask = nmask; m.reads.len = len; m.reads_owned = false;
@@ -1253,7 +1324,7 @@ void AgDevice::set_reads(const u32* bases, const u32* nmask, const uint16_t* len
 void AgDevice::set_reads_sparse(const u32* bases, const u64* exc_keys, u64 n_exc, const uint16_t* len, u64 n_pairs, u32 stride2, u32 stridem, bool overlap) {
     CK(cudaSetDevice(dev_));
     Impl& m = *m_;
-    m.n_pairs = n_pairs;
+    m.n_pairs = n_pairs; m.win_lo = 0; m.win_hi = ~0ull;
     Timer tm(m.st);
     m.r_bases.ensure(2 * n_pairs * stride2 + 1); m.r_nmask.ensure(2 * n_pairs * stridem + 1); m.r_len.ensure(n_pairs + 1); m.r_exc.ensure(n_exc + 1);
     CK(cudaMemcpyAsync(m.r_len.p, len, n_pairs * sizeof(uint16_t), cudaMemcpyHostToDevice, m.st));   // k_prep needs the lengths: main stream
@@ -1394,7 +1465,54 @@ static bool ing_fallback(const char* what, int where) {   // AG_DEBUG_INGEST=1: 
     return false;
 }
 
-bool AgDevice::ingest_reads(const std::string& path, AgReads& host) {
+// ---- a window of the read file.  tmp/_reads.fa is written by formalizeInput (AG:3455-3471) with the pair index as the id of both
+// mates, so record 2p / 2p + 1 carry ">p": the byte range of a pair-id window can be found by bisection on the file, without reading it.
+// Everything is verified (ids at both ends, the record count of the window) and anything unexpected means "no window".
+namespace {
+// offset of the first record start ('>' at a line start) at or after `from`, its id; n = file size.  false: none / not an integer id
+bool next_record(int fd, size_t n, size_t from, size_t& pos, long long& id) {
+    std::vector<char> buf;
+    for (size_t o = from; o < n;) {
+        const size_t w = std::min<size_t>((size_t)1 << 12, n - o);
+        buf.resize(w + 1);
+        size_t have = 0;
+        char prev = '\n';
+        if (o > 0) { if (pread(fd, &prev, 1, (off_t)(o - 1)) != 1) return false; }
+        if (pread(fd, buf.data(), w, (off_t)o) != (ssize_t)w) return false;
+        for (size_t i = 0; i < w; i++) {
+            const char before = i ? buf[i - 1] : prev;
+            if (buf[i] == '>' && before == '\n') {
+                char hd[32]; const size_t hw = std::min<size_t>(sizeof hd, n - (o + i));
+                if (pread(fd, hd, hw, (off_t)(o + i)) != (ssize_t)hw) return false;
+                long long v = 0; size_t k = 1; bool any = false;
+                while (k < hw && hd[k] >= '0' && hd[k] <= '9') { v = v * 10 + (hd[k] - '0'); k++; any = true; }
+                if (!any || k >= hw || hd[k] != '\n') return false;
+                pos = o + i; id = v; return true;
+            }
+        }
+        (void)have;
+        o += w;
+    }
+    return false;
+}
+// offset of the first record whose id is >= target (n when there is none); ids non-decreasing along the file
+bool first_record_with_id(int fd, size_t n, long long target, size_t& pos) {
+    size_t lo = 0, hi = n;   // smallest offset `o` such that the first record at or after o has id >= target (or there is none)
+    while (lo < hi) {
+        const size_t mid = lo + (hi - lo) / 2;
+        size_t p; long long id;
+        const bool found = next_record(fd, n, mid, p, id);
+        if (!found) {   // no record start at or after mid (or a malformed header: the caller's verification catches that)
+            hi = mid;
+        } else if (id >= target) hi = mid; else lo = p + 1;
+    }
+    size_t p; long long id;
+    if (lo >= n || !next_record(fd, n, lo, p, id)) { pos = n; return true; }
+    pos = p; return true;
+}
+}  // namespace
+
+bool AgDevice::ingest_reads(const std::string& path, AgReads& host, long long win_lo, long long win_hi) {
     CK(cudaSetDevice(dev_));
     Impl& m = *m_; cudaStream_t st = m.st;
     Fd f(path);
@@ -1403,11 +1521,36 @@ bool AgDevice::ingest_reads(const std::string& path, AgReads& host) {
     if (n < 4) return ing_fallback("reads", 1);
     char c0 = 0, cl = 0;
     if (pread(f.fd, &c0, 1, 0) != 1 || pread(f.fd, &cl, 1, (off_t)(n - 1)) != 1 || c0 != '>' || cl != '\n') return ing_fallback("reads", 2);
+    // ---- optional pair-id window [win_lo, win_hi]: only that byte range of the file is staged and packed (at its global record indices) ----
+    size_t b0 = 0, b1 = n; u64 rec_base = 0, total_pairs = 0; bool windowed = false;
+    if (win_lo >= 0 && win_hi >= win_lo) {
+        size_t p0, pl; long long id0, idl;
+        bool ok = next_record(f.fd, n, 0, p0, id0) && p0 == 0 && id0 == 0;
+        // the file's last two records must be the two mates of pair total - 1
+        long long id_last = -1, id_prev = -1;
+        for (size_t w = (size_t)1 << 12; ok && id_prev < 0 && w <= ((size_t)1 << 18); w <<= 3) {   // scan the tail backwards for the last two record starts
+            const size_t t0 = n > w ? n - w : 0;
+            std::vector<char> tb(n - t0);
+            if (pread(f.fd, tb.data(), tb.size(), (off_t)t0) != (ssize_t)tb.size()) { ok = false; break; }
+            size_t found[2]; int nf = 0;
+            for (size_t i = tb.size(); i-- > 0 && nf < 2;) if (tb[i] == '>' && (i ? tb[i - 1] == '\n' : t0 == 0)) found[nf++] = t0 + i;
+            if (nf == 2) { size_t q; ok = next_record(f.fd, n, found[0], q, id_last) && q == found[0] && next_record(f.fd, n, found[1], q, id_prev) && q == found[1]; break; }
+            if (t0 == 0) break;
+        }
+        if (ok) ok = id_last >= 0 && id_prev == id_last;
+        if (ok) { total_pairs = (u64)id_last + 1; ok = (u64)win_hi < total_pairs; }
+        if (ok) ok = first_record_with_id(f.fd, n, win_lo, b0) && first_record_with_id(f.fd, n, win_hi + 1, b1);
+        if (ok) ok = b0 < b1 && next_record(f.fd, n, b0, pl, idl) && pl == b0 && idl == win_lo;
+        if (ok && !(win_lo == 0 && (u64)win_hi + 1 == total_pairs)) { windowed = true; rec_base = 2 * (u64)win_lo; }
+        else { b0 = 0; b1 = n; }
+    }
+    const size_t n_file = n;
+    (void)n_file;
     Timer tm(st);
     // segments of at most 1 GB cut at record starts ("\n>"), each staged at a 16-byte aligned device offset (32-bit offsets inside a segment)
     const size_t SEG = (size_t)1 << 30;
-    std::vector<size_t> cut(1, 0);
-    while (n - cut.back() > SEG) {
+    std::vector<size_t> cut(1, b0);
+    while (b1 - cut.back() > SEG) {
         const size_t want = cut.back() + SEG, W = (size_t)1 << 20;
         std::vector<char> win(W);
         if (pread(f.fd, win.data(), W, (off_t)(want - W)) != (ssize_t)W) return ing_fallback("reads", 3);
@@ -1416,7 +1559,7 @@ bool AgDevice::ingest_reads(const std::string& path, AgReads& host) {
         if (k == 0) return ing_fallback("reads", 4);
         cut.push_back(want - W + k);
     }
-    cut.push_back(n);
+    cut.push_back(b1);
     const size_t ns = cut.size() - 1;
     std::vector<size_t> doff(ns + 1, 0), blk0(ns + 1, 0), nl0(ns + 1, 0), rec0(ns + 1, 0);
     for (size_t s = 0; s < ns; s++) { doff[s + 1] = (doff[s] + (cut[s + 1] - cut[s]) + 15) / 16 * 16 + 16; blk0[s + 1] = blk0[s] + ((cut[s + 1] - cut[s]) + NL_B - 1) / NL_B + 2; }
@@ -1426,11 +1569,17 @@ bool AgDevice::ingest_reads(const std::string& path, AgReads& host) {
         CK(cudaMemsetAsync(m.raw.p + doff[s] + len, 0, 32, st));
         m.stager.run(f.fd, cut[s], len, m.raw.p + doff[s], st, dev_);
     }
-    t_.h2d_bytes += n;
+    const bool probe = getenv("AG_POST_TIMING") != nullptr;
+    auto tp0 = std::chrono::steady_clock::now();
+    if (probe) { CK(cudaStreamSynchronize(st)); fprintf(stderr, "  [ingest reads] staged %.1f MB: host queued + copies done %.2f ms\n", (b1 - b0) / 1e6, tm.lap_ms()); tp0 = std::chrono::steady_clock::now(); }
+    t_.h2d_bytes += b1 - b0;
     std::vector<u32> lines(ns, 0);
     for (size_t s = 0; s < ns; s++) { lines[s] = m.nl_index(st, launches_, m.raw.p + doff[s], cut[s + 1] - cut[s], blk0[s], 0, false); nl0[s + 1] = nl0[s] + lines[s]; if (lines[s] & 1) return ing_fallback("reads", 5); rec0[s + 1] = rec0[s] + lines[s] / 2; }
-    const u64 R = rec0[ns];
+    const u64 R = rec0[ns];   // records staged (the window's, or the whole file's)
+    if (windowed && R != 2 * (u64)(win_hi - win_lo + 1)) return ingest_reads(path, host, -1, -1);   // ids are not the pair indices after all: whole file
     if (R == 0 || (R & 1) || R >= 0xFFFFFFF0ull) return ing_fallback("reads", 6);
+    const u64 R_total = windowed ? 2 * total_pairs : R;
+    if (R_total >= 0xFFFFFFF0ull) return ing_fallback("reads", 6);
     m.nl.ensure(nl0[ns] + 2); m.rlen.ensure(R + 2);
     CK(cudaMemsetAsync(m.ing.p, 0, 8 * sizeof(u32), st));   // [0] bad flags, [1] max length, [2] exception count
     for (size_t s = 0; s < ns; s++) {
@@ -1443,28 +1592,29 @@ bool AgDevice::ingest_reads(const std::string& path, AgReads& host) {
     CK(cudaStreamSynchronize(st));
     if (hs[32]) return ing_fallback("reads", 7);   // multi-line / empty records, a read longer than 65,535: the sequential parser handles or reports it
     const u32 maxlen = hs[33];
-    const u64 n_pairs = R / 2;
+    const u64 n_pairs = R_total / 2, w_pairs = R / 2, pair_base = rec_base / 2;
     u32 stride2 = (maxlen + 15) / 16, stridem = (maxlen + 31) / 32;
     if (!stride2) stride2 = stridem = 1;
-    m.n_pairs = n_pairs;
-    m.r_bases.ensure(R * stride2 + 1); m.r_nmask.ensure(R * stridem + 1); m.r_len.ensure(n_pairs + 1);
+    m.n_pairs = n_pairs; m.win_lo = pair_base; m.win_hi = pair_base + w_pairs - 1;
+    m.r_bases.ensure(R_total * stride2 + 1); m.r_nmask.ensure(R_total * stridem + 1); m.r_len.ensure(n_pairs + 1);
     const u32 exc_cap = (u32)std::min<size_t>(std::max<size_t>((size_t)1 << 20, n / 64), (size_t)1 << 28);
     m.exc_key.ensure(exc_cap); m.exc_chr.ensure(exc_cap);
-    k_rd_pairlen<<<(unsigned)((n_pairs + 255) / 256), 256, 0, st>>>(m.rlen.p, (u32)n_pairs, m.r_len.p, (int*)m.ing.p); launches_++;
+    k_rd_pairlen<<<(unsigned)((w_pairs + 255) / 256), 256, 0, st>>>(m.rlen.p, (u32)w_pairs, m.r_len.p + pair_base, (int*)m.ing.p); launches_++;
     for (size_t s = 0; s < ns; s++) {
         const u32 nr = lines[s] / 2;
         const u64 tasks = (u64)nr * stridem;
-        if (tasks) { k_rd_pack<<<(unsigned)((tasks + 255) / 256), 256, 0, st>>>(m.raw.p + doff[s], m.nl.p + nl0[s], nr, stride2, stridem, rec0[s], m.r_bases.p, m.r_nmask.p, m.exc_key.p, m.exc_chr.p, m.ing.p + 2, exc_cap); launches_++; }
+        if (tasks) { k_rd_pack<<<(unsigned)((tasks + 255) / 256), 256, 0, st>>>(m.raw.p + doff[s], m.nl.p + nl0[s], nr, stride2, stridem, rec_base + rec0[s], m.r_bases.p, m.r_nmask.p, m.exc_key.p, m.exc_chr.p, m.ing.p + 2, exc_cap); launches_++; }
     }
-    host.len.resize(n_pairs);
-    m.h_walks.ensure(n_pairs * sizeof(uint16_t) + 64);
-    CK(cudaMemcpyAsync(m.h_walks.p, m.r_len.p, n_pairs * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
+    host.len.assign(n_pairs, 0);   // (outside the window: not on the device either — see win_lo / win_hi)
+    m.h_walks.ensure(w_pairs * sizeof(uint16_t) + 64);
+    CK(cudaMemcpyAsync(m.h_walks.p, m.r_len.p + pair_base, w_pairs * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync((void*)(hs + 32), m.ing.p, 3 * sizeof(u32), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (hs[32] & ING_PE_LEN) throw AgError{"INCONSISTENT PE FILES!"};
     const u32 n_exc = hs[34];
     if (n_exc > exc_cap) return ing_fallback("reads", 8);   // more masked characters than the list holds (reads of 'N' only, ...): host parser
-    memcpy(host.len.data(), m.h_walks.p, n_pairs * sizeof(uint16_t));
+    memcpy(host.len.data() + pair_base, m.h_walks.p, w_pairs * sizeof(uint16_t));
+    host.win_lo = m.win_lo; host.win_hi = m.win_hi;
     host.exc.clear();
     if (n_exc) {
         std::vector<u64> keys(n_exc); std::vector<char> chr(n_exc);
@@ -1479,8 +1629,10 @@ bool AgDevice::ingest_reads(const std::string& path, AgReads& host) {
     host.bases.resize(0); host.nmask.resize(0);   // device-only: AgDevice::copy_reads_to_host fills them on demand
     m.reads.bases = m.r_bases.p; m.reads.nmask = m.r_nmask.p; m.reads.len = m.r_len.p; m.reads_owned = true;
     m.reads.stride2 = stride2; m.reads.stridem = stridem;
+    if (probe) fprintf(stderr, "  [ingest reads] kernels + read-backs %.2f ms\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - tp0).count() * 1e3);
     t_.ingest_reads += tm.stop(); t_.reads_device++;
-    t_.d2h_bytes += n_pairs * sizeof(uint16_t) + (size_t)n_exc * 9;
+    t_.d2h_bytes += w_pairs * sizeof(uint16_t) + (size_t)n_exc * 9;
+    if (windowed) t_.reads_windowed++;
     return true;
 }
 
@@ -1528,6 +1680,9 @@ bool AgDevice::ingest_sam(const std::string& path) {
     m.raw.ensure(n + 64); m.nl_blk.ensure((n + NL_B - 1) / NL_B + 4); m.ing.ensure(8);
     CK(cudaMemsetAsync(m.raw.p + n, 0, 32, st));
     m.stager.run(f.fd, 0, n, m.raw.p, st, dev_);
+    const bool probe = getenv("AG_POST_TIMING") != nullptr;
+    auto tp0 = std::chrono::steady_clock::now();
+    if (probe) { CK(cudaStreamSynchronize(st)); fprintf(stderr, "  [ingest sam] staged %.1f MB: host queued + copies done %.2f ms\n", n / 1e6, tm.lap_ms()); tp0 = std::chrono::steady_clock::now(); }
     t_.h2d_bytes += n;
     const u32 lines = m.nl_index(st, launches_, m.raw.p, n, 0, 0, false);
     if (lines < n_hdr || ((lines - n_hdr) & 1)) return ing_fallback("sam", 106);   // odd number of records: BROKEN BOWTIE FILE territory, the host parser reports it
@@ -1540,7 +1695,8 @@ bool AgDevice::ingest_sam(const std::string& path) {
     m.srec.ensure((size_t)n_rec + 1); m.s_keep.ensure((size_t)n_rec + 2); m.s_next.ensure((size_t)n_rec + 2); m.s_aoff.ensure((size_t)n_rec + 2); m.s_eoff.ensure((size_t)n_rec + 2); m.s_lost.ensure(lost_cap + 4);
     CK(cudaMemsetAsync(m.ing.p, 0, 8 * sizeof(u32), st));
     int* bad = (int*)m.ing.p;
-    k_sam_parse<<<(n_rec + 127) / 128, 128, 0, st>>>(m.raw.p, nl, (u32)body, n_rec, m.reads.len, m.n_pairs, m.srec.p, bad); launches_++;
+    m.window_miss = false;
+    k_sam_parse<<<(n_rec + 127) / 128, 128, 0, st>>>(m.raw.p, nl, (u32)body, n_rec, m.reads.len, m.n_pairs, m.win_lo, m.win_hi, m.srec.p, bad); launches_++;
     k_sam_sorted<<<(n_rec + 255) / 256, 256, 0, st>>>(m.srec.p, n_rec, bad); launches_++;
     k_sam_lost<<<1, 32, 0, st>>>(m.srec.p, n_rec, (long long)m.n_pairs, m.s_lost.p, lost_cap); launches_++;
     k_sam_survive<<<(n_rec + 255) / 256, 256, 0, st>>>(m.srec.p, n_rec, m.s_lost.p, m.reads.len, m.s_keep.p, m.s_next.p, bad); launches_++;
@@ -1553,14 +1709,65 @@ bool AgDevice::ingest_sam(const std::string& path) {
     CK(cudaMemcpyAsync((void*)(hs + 35), m.s_lost.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const u32 flags = hs[32], n_aln = hs[33], n_ext = hs[34];
-    if ((flags & (ING_BAD_LAYOUT | ING_BAD_RECORD | ING_BAD_ORDER)) || hs[35] > lost_cap) return ing_fallback("sam", 107);   // not the well-formed layout: host parser
+    if (flags & ING_WINDOW) m.window_miss = true;
+    if ((flags & (ING_BAD_LAYOUT | ING_BAD_RECORD | ING_BAD_ORDER | ING_WINDOW)) || hs[35] > lost_cap) return ing_fallback("sam", 107);   // not the well-formed layout: host parser
     if (flags & ING_STRAND) throw AgError{"BOWTIE ALIGNMENT ERROR"};
     m.aln.ensure((size_t)n_aln + 1); m.ext.ensure((size_t)n_ext + 1);
-    k_sam_fill<<<(n_rec + 127) / 128, 128, 0, st>>>(m.raw.p, nl, (u32)body, n_rec, m.reads.len, m.n_pairs, m.srec.p, m.s_keep.p, m.s_aoff.p, n_ext ? m.s_eoff.p : nullptr, m.aln.p, m.ext.p); launches_++;
+    k_sam_fill<<<(n_rec + 127) / 128, 128, 0, st>>>(m.raw.p, nl, (u32)body, n_rec, m.reads.len, m.n_pairs, m.win_lo, m.win_hi, m.srec.p, m.s_keep.p, m.s_aoff.p, n_ext ? m.s_eoff.p : nullptr, m.aln.p, m.ext.p); launches_++;
     m.n_aln = n_aln; m.n_ext = n_ext; m.aln_ingested = true;
+    if (probe) fprintf(stderr, "  [ingest sam] kernels + read-backs %.2f ms\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - tp0).count() * 1e3);
     t_.ingest_sam += tm.stop(); t_.sam_device++;
     return true;
 }
+bool AgDevice::coverage_pileup(const std::string& path, const std::vector<u32>& chunk_len, std::vector<int>& cov) {
+    CK(cudaSetDevice(dev_));
+    Impl& m = *m_; cudaStream_t st = m.st;
+    std::vector<u64> off(chunk_len.size() + 1, 0);
+    for (size_t i = 0; i < chunk_len.size(); i++) off[i + 1] = off[i] + chunk_len[i];
+    const u64 nb = off.back();
+    cov.assign(nb, 0);
+    Fd f(path);
+    if (f.fd < 0) throw AgError{"CANNOT OPEN FILE!"};
+    const size_t n = f.size();
+    if (n == 0 || nb == 0) return true;
+    if (n >= 0xF0000000ull || nb >= 0xFFFFFFF0ull) return ing_fallback("pileup", 201);
+    size_t body = 0; u32 n_hdr = 0;
+    {
+        const size_t W = std::min<size_t>(n, (size_t)4 << 20);
+        std::vector<char> head(W);
+        if (pread(f.fd, head.data(), W, 0) != (ssize_t)W) return ing_fallback("pileup", 202);
+        while (body < W && head[body] == '@') { const char* l = (const char*)memchr(head.data() + body, '\n', W - body); if (!l) return ing_fallback("pileup", 203); body = (size_t)(l - head.data()) + 1; n_hdr++; }
+        if (body >= W && W < n) return ing_fallback("pileup", 204);
+        char cl = 0;
+        if (pread(f.fd, &cl, 1, (off_t)(n - 1)) != 1 || cl != '\n') return ing_fallback("pileup", 205);
+    }
+    if (body >= n) return true;
+    m.raw.ensure(n + 64); m.nl_blk.ensure((n + NL_B - 1) / NL_B + 4); m.ing.ensure(8);
+    CK(cudaMemsetAsync(m.raw.p + n, 0, 32, st));
+    m.stager.run(f.fd, 0, n, m.raw.p, st, dev_);
+    const u32 lines = m.nl_index(st, launches_, m.raw.p, n, 0, 0, false);
+    if (lines < n_hdr || ((lines - n_hdr) & 1)) return ing_fallback("pileup", 206);
+    const u32 n_rec = (lines - n_hdr) / 2;
+    if (!n_rec) return true;
+    m.nl.ensure((size_t)lines + 2);
+    m.nl_index(st, launches_, m.raw.p, n, 0, 0, true);
+    DBuf<u64> d_off; DBuf<u32> diff, run;
+    d_off.ensure(off.size()); diff.ensure(nb + 2); run.ensure(nb + 3);
+    CK(cudaMemcpyAsync(d_off.p, off.data(), off.size() * sizeof(u64), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(diff.p, 0, (nb + 2) * sizeof(u32), st));
+    CK(cudaMemsetAsync(m.ing.p, 0, 8 * sizeof(u32), st));
+    k_cov_marks<<<(n_rec + 127) / 128, 128, 0, st>>>(m.raw.p, m.nl.p + n_hdr, (u32)body, n_rec, d_off.p, (u32)chunk_len.size(), diff.p, (int*)m.ing.p); launches_++;
+    m.scanner.run(diff.p, run.p, nb + 1, st);   // exclusive: run[i + 1] = coverage of base i (mod 2^32, i.e. exact)
+    int flags = 0;
+    CK(cudaMemcpyAsync(&flags, m.ing.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(cov.data(), run.p + 1, nb * sizeof(u32), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    d_off.release(); diff.release(); run.release();
+    if (flags) { cov.assign(nb, 0); return ing_fallback("pileup", 207); }
+    // an interval that crosses a chunk end would leak into the next chunk: intervals are clipped to their chunk in the kernel, so it cannot
+    return true;
+}
+bool AgDevice::sam_window_miss() const { return m_->window_miss; }
 u64 AgDevice::ingested_alignments() const { return m_->aln_ingested ? m_->n_aln : 0; }
 void AgDevice::fetch_alignments(std::vector<ag_aln>& aln, std::vector<ag_seg>& ext) {
     CK(cudaSetDevice(dev_));
@@ -1722,7 +1929,7 @@ void AgDevice::enqueue_build() {
             m.stage.ensure((size_t)m.key_cap * rsw + 64);
             {
                 Section sec2(m.sections, st, &t_.stage);
-                k_stage<<<GS_BLOCKS, GS_T, 0, st>>>(d, m.stage.p, rsw); launches_++;
+                k_stage<<<GS_BLOCKS * 2, GS_T, 0, st>>>(d, m.stage.p, rsw); launches_++;
             }
             Section sec3(m.sections, st, &t_.build_kernel);
             if (m.n_tiles) { k_build_tma<<<m.n_tiles, AG_TILE, smem_tma, st>>>(d, m.stage.p, rsw); launches_++; }

@@ -34,7 +34,7 @@ struct AgTimings {  // milliseconds, CUDA events on the context's stream
     int walk_fallback = 0, regrows = 0;   // regrows: sweeps repeated with a larger node table / overflow pool
     float stage = 0, build_kernel = 0;        // inside `nodes`: the staging gather (k_stage) and the node sweep kernel itself
     float ingest_reads = 0, ingest_sam = 0;   // ms: staging + kernels of the text ingestion (CUDA events)
-    u64 sam_device = 0, sam_host = 0, reads_device = 0, reads_host = 0;   // files parsed on the device / by the host parser
+    u64 sam_device = 0, sam_host = 0, reads_device = 0, reads_host = 0, reads_windowed = 0;   // files parsed on the device / by the host parser
 };
 
 class AgDevice {
@@ -58,14 +58,20 @@ public:
     // the caller then uses the sequential host parser (ag_parse_reads / ag_parse_sam), which carries the literal semantics and messages.
     // tmp/_reads.fa -> packed reads resident on the device; `host` receives the per-pair lengths, the geometry and the exception list
     // (original non-ACGT characters), NOT the packed words (copy_reads_to_host fetches them on demand)
-    bool ingest_reads(const std::string& path, struct AgReads& host);
+    // win_lo / win_hi >= 0: only the pairs of that id window are made resident (their byte range of the file is found by bisection; ids are
+    // the pair indices, AG:3455-3471) — ingest_sam then reports ids outside the window through sam_window_miss()
+    bool ingest_reads(const std::string& path, struct AgReads& host, long long win_lo = -1, long long win_hi = -1);
+    bool sam_window_miss() const;
     // tmp/_reads_genome.N.bowtie -> the unit's surviving alignment tuples, resident on the device in file order
     bool ingest_sam(const std::string& path);
+    // removeMisassembly's coverage pile-up (AG:3938-3978) of tmp/_reads_<id>_contigs.bowtie over the chunks of tmp/_<id>_contigs.fa; false: the
+    // file is not in the layout the kernel handles (the caller uses ag_coverage_pileup_host)
+    bool coverage_pileup(const std::string& sam_path, const std::vector<u32>& chunk_len, std::vector<int>& coverage);
     u64 ingested_alignments() const;
     void note_host_sam() { t_.sam_host++; }
     void note_host_reads() { t_.reads_host++; }
     void fetch_alignments(std::vector<ag_aln>& aln, std::vector<ag_seg>& ext);   // device -> host copy of the ingested tuples (tests, ag_get_unit)
-    void set_params(int k, int iv, int coverage) { k_ = k; iv_ = iv; cov_ = coverage; }
+    void set_params(int k, int iv, int coverage);
     // keep coverage + base counters per node after the build (24 B per node; only the node dump of the tests needs them)
     void set_keep_counts(bool on) { keep_counts_ = on; }
     void set_option(const std::string& name, long value);

@@ -17,6 +17,7 @@
 #include <chrono>
 #include <mutex>
 #include <atomic>
+#include <memory>
 
 namespace {
 
@@ -157,7 +158,7 @@ struct Team {
         if (T <= 0) {
             cpu_set_t set; CPU_ZERO(&set);
             T = sched_getaffinity(0, sizeof set, &set) == 0 ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
-            T = std::min(T, 16);
+            T = std::min(T, 32);
         }
         size = std::max(T, 1);
         for (int i = 1; i < size; i++) th.emplace_back([this] { work(); });
@@ -1376,7 +1377,9 @@ void ag_scaffold(std::vector<AgContig>& cs, const std::string& ref, const std::v
 // =============================================================================================================================
 // input normalisation (--resume re-runs these, AG:4757-4758)
 // =============================================================================================================================
-void ag_formalize_contigs(const std::string& in_path, const std::string& tmp, std::vector<std::string>& contig_ids) {
+// formalizeInput (contigs), AG:3228-3320: chunks of at most LARGE_CHUNK bases named ">chunk.contig"; contigs of <= 200 bases go to the chaff
+// file (only tmp/_contigs.fa has one: for tmp/_<id>_contigs.fa the reference writes them to a closed stream, i.e. drops them)
+void ag_formalize_contigs_to(const std::string& in_path, const std::string& out_path, const std::string& chaff_path, std::vector<std::string>& contig_ids) {
     FileMap fm(in_path);
     if (!fm.ok) throw AgHostError{"CANNOT OPEN FILE!"};
     std::vector<std::string> seqs, ids;
@@ -1388,7 +1391,9 @@ void ag_formalize_contigs(const std::string& in_path, const std::string& tmp, st
             else if (!seqs.empty()) seqs.back().append(s, n);
         }
     }
-    Out out(tmp + "/_contigs.fa"), chaff(tmp + "/_chaff.fa");
+    Out out(out_path);
+    std::unique_ptr<Out> chaff;
+    if (!chaff_path.empty()) chaff.reset(new Out(chaff_path));
     contig_ids.clear();
     unsigned long chunk = 0, real = 0;
     for (size_t c = 0; c < seqs.size(); c++) {
@@ -1407,8 +1412,11 @@ void ag_formalize_contigs(const std::string& in_path, const std::string& tmp, st
             }
             real++;
             contig_ids.push_back(ids[c]);
-        } else { chaff.ch('>'); chaff.put(ids[c]); chaff.ch('\n'); chaff.wrap60(q); }
+        } else if (chaff) { chaff->ch('>'); chaff->put(ids[c]); chaff->ch('\n'); chaff->wrap60(q); }
     }
+}
+void ag_formalize_contigs(const std::string& in_path, const std::string& tmp, std::vector<std::string>& contig_ids) {
+    ag_formalize_contigs_to(in_path, tmp + "/_contigs.fa", tmp + "/_chaff.fa", contig_ids);
 }
 
 int ag_formalize_genome(const std::string& in_path, const std::string& tmp, int part, std::vector<std::string>& genome_ids) {
@@ -1665,6 +1673,179 @@ void ag_refinement(const std::string& tmp, int units, const std::vector<std::str
     }
     if (test_in) for (size_t i = 0; i < init_tags.size(); i++) if (init_tags[i] == 1) { test_in->ch('>'); test_in->num(i); test_in->ch('\n'); test_in->wrap60(init[i]); }
     delete test_in; delete test_ex;
+}
+
+
+// =============================================================================================================================
+// removeMisassembly (AG:3821-4297)
+// =============================================================================================================================
+void ag_coverage_pileup_host(const std::string& sam_path, const std::vector<u32>& chunk_len, std::vector<int>& cov, void*) {   // AG:3923-3970
+    std::vector<size_t> off(chunk_len.size() + 1, 0);
+    for (size_t i = 0; i < chunk_len.size(); i++) off[i + 1] = off[i] + chunk_len[i];
+    cov.assign(off.back(), 0);
+    FileMap fm(sam_path);
+    if (!fm.ok) throw AgHostError{"CANNOT OPEN FILE!"};
+    Lines ln(fm.p, fm.n); const char* s; size_t n;
+    std::vector<ag_seg> s1, s2;
+    auto add = [&](const SamRec& r) {
+        if (r.tid >= chunk_len.size()) return;   // (the reference indexes without a check)
+        for (u32 bp = r.tstart; bp < r.tend && bp < chunk_len[r.tid]; bp++) cov[off[r.tid] + bp]++;
+    };
+    while (ln.next(s, n)) {
+        if (n == 0 || s[0] == 0) break;
+        if (s[0] == '@') continue;
+        SamRec a, b;
+        s1.clear(); s2.clear();
+        parse_sam(s, n, a, s1);
+        if (!ln.next(s, n) || n == 0 || s[0] == 0) throw AgHostError{"BROKEN BOWTIE FILE!"};
+        parse_sam(s, n, b, s2);
+        if (a.tid != AG_NONE && b.tid != AG_NONE) { add(a); add(b); }
+    }
+}
+
+namespace {
+struct MPos { u32 tid, ss, se, ts, te, fr; };   // ContigPosition; tid == NONE: deleted entry (p0)
+const MPos kP0 = {AG_NONE, AG_NONE, AG_NONE, AG_NONE, AG_NONE, AG_NONE};
+inline int m_conflict(u32 x1, u32 y1, u32 x2, u32 y2) {   // AG:3980-3988
+    return ((x1 <= x2 && x2 <= y1 && y1 <= y2 && (int)y1 - (int)x2 >= 100) || (x2 <= x1 && x1 <= y2 && y2 <= y1 && (int)y2 - (int)x1 >= 100) ||
+            (x1 <= x2 && x2 <= y2 && y2 <= y1 && (int)y2 - (int)x2 >= 100) || (x2 <= x1 && x1 <= y1 && y1 <= y2 && (int)y1 - (int)x1 >= 100) ||
+            (x1 <= x2 && y2 <= y1) || (x2 <= x1 && y1 <= y2)) ? 1 : 0;
+}
+inline int m_close(u32 y1, u32 x2, u32 threshold) { return (u32)abs((int)x2 - (int)y1) < threshold ? 1 : 0; }   // AG:3990-3996 (int < unsigned compares as unsigned)
+}  // namespace
+
+void ag_remove_misassembly(const std::string& file, const std::string& id, int coverage, const std::string& tmp, AgAlignFn align, AgPileupFn pileup, void* user) {
+    const double kMinThreshold = 0.1;   // MIN_THRESHOLD, AG:42
+    const std::string cfa = tmp + "/_" + id + "_contigs.fa";
+    std::vector<std::string> contig_ids;
+    ag_formalize_contigs_to(file, cfa, "", contig_ids);                         // formalizeInput(c, "tmp/_<id>_contigs.fa") — also resets contigIds
+    if (!align(id, user)) throw AgHostError{"BLAT CALL FAILED!"};               // makeAlignment, AG:3821-3850
+    // ---- loadPreContigs (AG:3852-3890): the chunks; loadContigs (AG:3892-3936): chunks regrouped into contigs ----
+    std::vector<std::string> chunk; std::vector<int> chunk_real;
+    {
+        FileMap fm(cfa);
+        if (!fm.ok) throw AgHostError{"CANNOT OPEN FILE!"};
+        Lines ln(fm.p, fm.n); const char* s; size_t n;
+        while (ln.next(s, n)) {
+            if (n == 0 || s[0] == 0) break;
+            if (s[0] == '>') { chunk.emplace_back(); const char* dot = (const char*)memchr(s, '.', n); chunk_real.push_back(dot ? ag_atoi(dot + 1, std::min<size_t>((size_t)(s + n - dot - 1), 9)) : ag_atoi(s + n, 0)); }
+            else if (!chunk.empty()) chunk.back().append(s, n);
+        }
+    }
+    std::vector<u32> chunk_len; for (auto& c : chunk) chunk_len.push_back((u32)c.size());
+    std::vector<int> chunk_cov;
+    pileup(tmp + "/_reads_" + id + "_contigs.bowtie", chunk_len, chunk_cov, user);   // loadReadAlignment, AG:3938-3978
+    std::vector<std::string> base; std::vector<std::vector<int>> cov;                  // per contig
+    {
+        int real_bak = -1; size_t o = 0;
+        for (size_t c = 0; c < chunk.size(); c++) {
+            if (chunk_real[c] > real_bak) { base.emplace_back(); cov.emplace_back(); real_bak = chunk_real[c]; }
+            if (base.empty()) { o += chunk[c].size(); continue; }   // (the reference would write through an empty vector)
+            base.back() += chunk[c];
+            cov.back().insert(cov.back().end(), chunk_cov.begin() + (long)o, chunk_cov.begin() + (long)(o + chunk[c].size()));
+            o += chunk[c].size();
+        }
+    }
+    // ---- loadContigAlignment (AG:4003-4145) ----
+    std::vector<std::vector<MPos>> positions(base.size());
+    {
+        FileMap fm(tmp + "/_" + id + "_contigs_genome.psl");
+        if (!fm.ok) throw AgHostError{"CANNOT OPEN FILE!"};
+        Lines ln(fm.p, fm.n); const char* s; size_t n;
+        PslRec r; int real_bak = -1; u32 source_bak = 0;
+        while (ln.next(s, n)) {
+            if (n == 0 || s[0] == 0) break;
+            parse_psl(s, n, r);
+            // parseBLAT's return value: the id after the '.' of the query name, else the query size (AG:505-521)
+            int real = (int)r.ssize;
+            { const char* f = s; int tab = 0; const char* fe = s + n;
+              for (const char* c = s; c <= fe; c++) if (c == fe || *c == '\t') { if (tab == 9) { const char* dot = (const char*)memchr(f, '.', (size_t)(c - f)); if (dot) real = ag_atoi(dot + 1, (size_t)(c - dot - 1)); } tab++; f = c + 1; } }
+            if (real > real_bak) { real_bak = real; source_bak = r.sid; }
+            u32 ss = (r.sid - source_bak) * (u32)kLargeChunk + r.sstart, se = (r.sid - source_bak) * (u32)kLargeChunk + r.send;
+            if (!(se - ss >= 100 && (double)(se - ss - r.sgap) / (se - ss) >= kMinThreshold && (double)(r.tend - r.tstart - r.tgap) / (double)(r.tend - r.tstart) >= kMinThreshold)) continue;
+            if (real < 0 || (size_t)real >= positions.size()) continue;   // (out of range in the reference)
+            std::vector<MPos>& ps = positions[(size_t)real];
+            int keep = 1;
+            for (size_t pp = 0; pp < ps.size(); pp++)
+                if (ps[pp].tid != AG_NONE && r.tid == ps[pp].tid && m_conflict(ss, se, ps[pp].ss, ps[pp].se)) {
+                    if (se - ss < ps[pp].se - ps[pp].ss) keep = 0; else ps[pp] = kP0;
+                }
+            if (keep) ps.push_back(MPos{r.tid, ss, se, r.tstart, r.tend, r.fr});
+        }
+    }
+    for (auto& ps : positions)   // join local alignments that continue each other (AG:4068-4082); the restart quirk (ppp = 0, then ++) is kept
+        for (size_t pp = 0; pp < ps.size(); pp++)
+            for (size_t ppp = 0; ppp < ps.size(); ppp++)
+                if (ppp != pp && ps[pp].tid != AG_NONE && ps[ppp].tid != AG_NONE && ps[pp].tid == ps[ppp].tid &&
+                    m_close(ps[pp].se, ps[ppp].ss, (u32)(abs((int)ps[pp].se - (int)ps[pp].ss) / 10)) && m_close(ps[pp].te, ps[ppp].ts, (u32)(abs((int)ps[pp].te - (int)ps[pp].ts) / 10)) &&
+                    ps[pp].fr == ps[ppp].fr) {
+                    ps[pp].se = ps[ppp].se; ps[pp].te = ps[ppp].te; ps[ppp] = kP0; ppp = 0;
+                }
+    for (auto& ps : positions)   // conflicting alignments to different places: keep the longer (AG:4084-4091)
+        for (size_t pp = 0; pp < ps.size(); pp++)
+            for (size_t ppp = pp + 1; ppp < ps.size(); ppp++)
+                if (ps[pp].tid != AG_NONE && ps[ppp].tid != AG_NONE && m_conflict(ps[pp].ss, ps[pp].se, ps[ppp].ss, ps[ppp].se)) {
+                    if (ps[pp].se - ps[pp].ss > ps[ppp].se - ps[ppp].ss) ps[ppp] = kP0; else ps[pp] = kP0;
+                }
+    for (size_t sp = 0; sp < positions.size(); sp++) {   // keep a distance between consecutive local alignments: cut at the coverage minimum (AG:4094-4142)
+        std::vector<MPos>& ps = positions[sp]; const std::vector<int>& cv = cov[sp];
+        auto cov_at = [&](long bp) -> int { return bp >= 0 && (size_t)bp < cv.size() ? cv[(size_t)bp] : 0; };
+        for (size_t pp = 0; pp < ps.size(); pp++)
+            for (size_t ppp = pp + 1; ppp < ps.size(); ppp++) {
+                if (ps[pp].tid == AG_NONE || ps[ppp].tid == AG_NONE) continue;
+                if (overlap(ps[pp].ss, ps[pp].se, ps[ppp].ss, ps[ppp].se)) {
+                    int mn = 99999, mp = -1, start, end;
+                    if (ps[pp].ss <= ps[ppp].ss) { start = (int)ps[ppp].ss; end = (int)ps[pp].se - 1; } else { start = (int)ps[pp].ss; end = (int)ps[ppp].se - 1; }
+                    for (int bp = start; bp <= end; bp++) if (cov_at(bp) < mn) { mn = cov_at(bp); mp = bp; }
+                    if (ps[pp].ss <= ps[ppp].ss) { ps[pp].se = (u32)mp; ps[ppp].ss = (u32)(mp + 1); } else { ps[ppp].se = (u32)mp; ps[pp].ss = (u32)(mp + 1); }
+                } else if (ps[pp].se == ps[ppp].ss) {
+                    if (cov_at((long)ps[pp].se - 1) < cov_at((long)ps[ppp].ss)) ps[pp].se--; else ps[ppp].ss++;
+                } else if (ps[ppp].se == ps[pp].ss) {
+                    if (cov_at((long)ps[ppp].se - 1) < cov_at((long)ps[pp].ss)) ps[ppp].se--; else ps[pp].ss++;
+                }
+            }
+    }
+    // ---- removeMasb (AG:4147-4279): -1 = safe, -2 = removed ----
+    for (size_t sp = 0; sp < positions.size(); sp++) {
+        std::vector<MPos>& ps = positions[sp]; std::vector<int>& cv = cov[sp];
+        bool whole = false;
+        for (const MPos& p : ps) if (p.tid != AG_NONE && (double)(p.se - p.ss) / cv.size() >= 0.8) { whole = true; break; }
+        if (whole) { std::fill(cv.begin(), cv.end(), -1); continue; }
+        for (const MPos& p : ps) if (p.tid != AG_NONE) for (u32 bp = p.ss; bp < p.se && bp < cv.size(); bp++) cv[bp] = -1;
+        const long sz = (long)cv.size();
+        int start = 0, end = 0, total = 0;
+        for (long bp = 0; bp < sz; bp++) {
+            if (cv[bp] == -1) continue;
+            if (bp != 0 && bp != sz - 1 && cv[bp - 1] == -1 && cv[bp + 1] == -1) { cv[bp] = cv[bp] < coverage ? -2 : -1; continue; }
+            if (bp == 0 || cv[bp - 1] == -1) { start = (int)bp; total = cv[bp]; }
+            else if (bp == sz - 1 || cv[bp + 1] == -1) {
+                end = (int)bp; total += cv[bp];
+                const int mark = total / (end - start + 1) < coverage ? -2 : -1;
+                for (int b = start; b <= end; b++) cv[b] = mark;
+            } else total += cv[bp];
+        }
+    }
+    Out out(std::string("corrected_") + file);
+    for (size_t cp = 0; cp < base.size(); cp++) {
+        const std::vector<int>& cv = cov[cp]; const std::string& bs = base[cp];
+        std::vector<std::string> split;
+        const long sz = (long)cv.size();
+        for (long bp = 0; bp < sz; bp++) {
+            if ((split.empty() && cv[bp] == -1) || (bp > 0 && cv[bp - 1] == -2 && cv[bp] == -1)) split.emplace_back();
+            if (cv[bp] == -1 && !split.empty()) split.back().push_back(bs[(size_t)bp]);
+            if (bp == sz - 1 || (cv[bp] == -1 && cv[bp + 1] == -2))
+                if (!split.empty() && split.back().size() <= 200) split.pop_back();
+        }
+        for (size_t sp = 0; sp < split.size(); sp++) {
+            out.ch('>'); if (cp < contig_ids.size()) out.put(contig_ids[cp]);
+            if (split.size() != 1) { out.put(" : part", 7); out.num(sp); }
+            out.ch('\n'); out.wrap60(split[sp]);
+        }
+    }
+    if (id == "remaining") {
+        FileMap fm(tmp + "/_chaff.fa");
+        if (fm.ok) { Lines ln(fm.p, fm.n); const char* s; size_t n; while (ln.next(s, n)) { if (n == 0 || s[0] == 0) break; out.put(s, n); out.ch('\n'); } }
+    }
 }
 
 // The host side stages hundreds of MB per unit in vectors.  By default glibc serves such blocks with mmap and returns them on free, so

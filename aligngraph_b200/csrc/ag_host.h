@@ -62,6 +62,8 @@ struct AgReads {
     std::vector<std::pair<u64, char>> exc;  // (read * 65536 + offset, original character) for every non-ACGT character, sorted
     bool exc_complete = false;       // exc lists EVERY set bit of nmask (true after ag_parse_reads / ag_pack_reads): the plane can be rebuilt from it
     u64 n_pairs = 0;
+    u64 win_lo = 0, win_hi = ~0ull;   // pair-id window for which lengths / packed words are held (everything unless the set was ingested for a window)
+    bool windowed() const { return win_hi != ~0ull && (win_lo != 0 || win_hi + 1 < n_pairs); }
     u32 stride2 = 0, stridem = 0;
     // character of the oriented read (AG:854-865 leaves non-ACGT unchanged).  When the packed words live only on the device (GPU-side
     // ingestion) the exception list alone is consulted: the original character of a masked base, or 0 = "an ordinary base"
@@ -167,6 +169,16 @@ int ag_max_read_length(const std::string& path);                                
 long ag_formalize_reads(const std::string& in1, const std::string& in2, const std::string& tmp);        // AG:3420
 void ag_distribute_alignments(const std::string& tmp, int units);                                       // AG:3545
 double ag_check_ratio(const std::string& tmp, int units);                                               // AG:3751
+// removeMisassembly (AG:3821-4297) for one output file (`id` = "extended" | "remaining"): formalize it into tmp/_<id>_contigs.fa, let `align`
+// run the aligners (bowtie2 reads -> contigs, BLAT contigs -> genome: command lines in the CLI), pile the read alignments up into a per-base
+// coverage (`pileup`: the device kernel in the product, ag_coverage_pileup_host in CPU tests), keep / break / drop contig regions, write
+// corrected_<file>.
+typedef bool (*AgAlignFn)(const std::string& id, void* user);
+typedef void (*AgPileupFn)(const std::string& sam_path, const std::vector<u32>& chunk_len, std::vector<int>& coverage, void* user);
+void ag_remove_misassembly(const std::string& file, const std::string& id, int coverage, const std::string& tmp, AgAlignFn align, AgPileupFn pileup, void* user);
+// per-base read coverage of the chunks of tmp/_<id>_contigs.fa from tmp/_reads_<id>_contigs.bowtie (AG:3923-3970), sequential host version
+void ag_coverage_pileup_host(const std::string& sam_path, const std::vector<u32>& chunk_len, std::vector<int>& coverage, void* user);
+void ag_formalize_contigs_to(const std::string& in_path, const std::string& out_path, const std::string& chaff_path /* empty: none */, std::vector<std::string>& contig_ids);
 void ag_refinement(const std::string& tmp, int units, const std::vector<std::string>& genome_ids, const std::vector<std::string>& contig_ids,
                    int unique_extension, const std::string& ext_path, const std::string& rmn_path, bool (*blat)(int unit, void* user), void* user,
                    bool write_test_files);                                                              // AG:2864

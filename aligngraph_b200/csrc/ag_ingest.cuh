@@ -64,7 +64,7 @@ __device__ __forceinline__ void line_span(const u32* __restrict__ nl, u32 body, 
 // ---------------------------------------------------------------------------------------------------------------------------
 // reads
 // ---------------------------------------------------------------------------------------------------------------------------
-enum { ING_BAD_LAYOUT = 1, ING_BAD_RECORD = 2, ING_BAD_ORDER = 8, ING_STRAND = 32, ING_PE_LEN = 64, ING_TOO_LONG = 128 };
+enum { ING_BAD_LAYOUT = 1, ING_BAD_RECORD = 2, ING_BAD_ORDER = 8, ING_STRAND = 32, ING_PE_LEN = 64, ING_TOO_LONG = 128, ING_WINDOW = 256 };
 
 // record r = lines 2r ('>' header) and 2r + 1 (sequence); rlen[r] = bases; flags: layout errors, maximum length
 __global__ void k_rd_len(const char* __restrict__ text, const u32* __restrict__ nl, u32 n_rec, u32* __restrict__ rlen, u32* maxlen, int* bad) {
@@ -124,7 +124,7 @@ __global__ void k_rd_pack(const char* __restrict__ text, const u32* __restrict__
 struct ag_srec { u32 sid, flags /* bit0 fr1, bit1 fr2, bit2 passes AG:1261, bits 8-15 n1, bits 16-23 n2 */, p0, dst1, sl1, dst2, sl2, next /* ext segments */; };
 
 __device__ __forceinline__ bool sam_parse_pair(const char* __restrict__ text, const u32* __restrict__ nl, u32 body, u32 p, const uint16_t* __restrict__ pair_len, u64 n_read_pairs,
-                                               ag_srec& r, ag_seg* n1, ag_seg* n2, int* bad) {
+                                               u64 win_lo, u64 win_hi, ag_srec& r, ag_seg* n1, ag_seg* n2, int* bad) {
     u32 s0, e0, s1, e1;
     line_span(nl, body, 2 * p, s0, e0); line_span(nl, body, 2 * p + 1, s1, e1);
     r.sid = 0; r.flags = 0; r.p0 = AG_NONE; r.dst1 = r.sl1 = r.dst2 = r.sl2 = 0; r.next = 0;
@@ -137,6 +137,7 @@ __device__ __forceinline__ bool sam_parse_pair(const char* __restrict__ text, co
     r.p0 = a.tid == AG_NONE ? AG_NONE : ag_sam_pos_at0(a.seg, a.nseg);
     if (ag_sam_mate_pass(a, 0.6) && ag_sam_mate_pass(b, 0.6)) {
         if (a.tid != 0 || b.tid != 0 || b.sid != a.sid || a.sid >= n_read_pairs) { atomicOr(bad, ING_BAD_RECORD); return false; }
+        if (a.sid < win_lo || a.sid > win_hi) { atomicOr(bad, ING_WINDOW); return false; }   // this read is not resident (windowed read set): the caller loads the whole set
         const u32 rlen = pair_len[a.sid];
         u32 c1 = 0, c2 = 0;
         if (ag_sam_normalize(a.seg, a.nseg, rlen, n1, c1) || ag_sam_normalize(b.seg, b.nseg, rlen, n2, c2) || !c1 || !c2 || c1 > 255 || c2 > 255) { atomicOr(bad, ING_BAD_RECORD); return false; }
@@ -149,11 +150,11 @@ __device__ __forceinline__ bool sam_parse_pair(const char* __restrict__ text, co
 }
 
 __global__ void __launch_bounds__(128) k_sam_parse(const char* __restrict__ text, const u32* __restrict__ nl, u32 body, u32 n_rec, const uint16_t* __restrict__ pair_len, u64 n_read_pairs,
-                                                   ag_srec* __restrict__ rec, int* bad) {
+                                                   u64 win_lo, u64 win_hi, ag_srec* __restrict__ rec, int* bad) {
     const u32 p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_rec) return;
     ag_srec r; ag_seg n1[AG_SAM_MAXSEG], n2[AG_SAM_MAXSEG];
-    sam_parse_pair(text, nl, body, p, pair_len, n_read_pairs, r, n1, n2, bad);
+    sam_parse_pair(text, nl, body, p, pair_len, n_read_pairs, win_lo, win_hi, r, n1, n2, bad);
     rec[p] = r;
 }
 __global__ void k_sam_sorted(const ag_srec* __restrict__ rec, u32 n_rec, int* bad) {
@@ -211,7 +212,7 @@ __global__ void k_sam_survive(const ag_srec* __restrict__ rec, u32 n_rec, const 
     next[i] = k ? r.next : 0u;
 }
 __global__ void __launch_bounds__(128) k_sam_fill(const char* __restrict__ text, const u32* __restrict__ nl, u32 body, u32 n_rec, const uint16_t* __restrict__ pair_len, u64 n_read_pairs,
-                                                  const ag_srec* __restrict__ rec, const u32* __restrict__ keep, const u32* __restrict__ aoff, const u32* __restrict__ eoff,
+                                                  u64 win_lo, u64 win_hi, const ag_srec* __restrict__ rec, const u32* __restrict__ keep, const u32* __restrict__ aoff, const u32* __restrict__ eoff,
                                                   ag_aln* __restrict__ aln, ag_seg* __restrict__ ext) {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_rec || !keep[i]) return;
@@ -222,7 +223,7 @@ __global__ void __launch_bounds__(128) k_sam_fill(const char* __restrict__ text,
     a.ext_idx = oe;
     if (r.next) {   // multi-segment CIGAR (rare): parse the pair again and write the normalised segment lists
         ag_srec r2; ag_seg n1[AG_SAM_MAXSEG], n2[AG_SAM_MAXSEG]; int dummy = 0;
-        sam_parse_pair(text, nl, body, i, pair_len, n_read_pairs, r2, n1, n2, &dummy);
+        sam_parse_pair(text, nl, body, i, pair_len, n_read_pairs, win_lo, win_hi, r2, n1, n2, &dummy);
         const u32 c1 = (r.flags >> 8) & 0xFF, c2 = (r.flags >> 16) & 0xFF;
         if (c1 > 1) { for (u32 j = 0; j < c1; j++) ext[oe + j] = n1[j]; oe += c1; }
         if (c2 > 1) { for (u32 j = 0; j < c2; j++) ext[oe + j] = n2[j]; }
@@ -231,13 +232,41 @@ __global__ void __launch_bounds__(128) k_sam_fill(const char* __restrict__ text,
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
+// read-vs-contig coverage pile-up of removeMisassembly (loadReadAlignment overload, AG:3938-3978): every pair with both mates aligned adds
+// one to the coverage of target bases [targetStart, targetEnd) of both mates.  One thread per record pair marks interval starts / ends in a
+// difference array (atomics); an inclusive scan turns it into the per-base coverage.
+// ---------------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_cov_marks(const char* __restrict__ text, const u32* __restrict__ nl, u32 body, u32 n_rec, const u64* __restrict__ chunk_off, u32 n_chunks,
+                                                   u32* __restrict__ diff, int* bad) {
+    const u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_rec) return;
+    u32 s0, e0, s1, e1;
+    line_span(nl, body, 2 * p, s0, e0); line_span(nl, body, 2 * p + 1, s1, e1);
+    if (e0 == s0 || e1 == s1 || text[s0] == '@' || text[s1] == '@' || text[s0] == 0 || text[s1] == 0) { atomicOr(bad, ING_BAD_LAYOUT); return; }
+    ag_samline a, b;
+    ag_sam_parse_line(text + s0, e0 - s0, a);
+    ag_sam_parse_line(text + s1, e1 - s1, b);
+    if (a.err == AG_SAM_ERR_CHAR || b.err == AG_SAM_ERR_CHAR) { atomicOr(bad, ING_BAD_RECORD); return; }   // `unknown character`: the host path reports it
+    if (a.tid == AG_NONE || b.tid == AG_NONE) return;
+    const ag_samline* r[2] = {&a, &b};
+    for (int k = 0; k < 2; k++) {
+        if (r[k]->tid >= n_chunks) continue;
+        const u64 o = chunk_off[r[k]->tid], len = chunk_off[r[k]->tid + 1] - o;
+        const u64 ts = r[k]->tstart, te = r[k]->tend < len ? r[k]->tend : len;
+        if (ts >= te) continue;
+        atomicAdd(&diff[o + ts], 1u);
+        atomicAdd(&diff[o + te], 0xFFFFFFFFu);   // -1 (diff has one entry more than there are bases)
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
 // file -> device through page-locked staging chunks.  T host threads each own two pinned slots and take the file's chunks round-robin:
 // pread() into a slot (page cache -> pinned memory at memory speed), queue the slot's host->device copy, move on to the other slot; a
 // slot is reused once its copy has finished.  The copy engine therefore always has several chunks queued while the next ones are read.
 // ---------------------------------------------------------------------------------------------------------------------------
 struct FileStager {
-    static constexpr size_t CHUNK = (size_t)8 << 20;
-    static constexpr int MAXT = 16;
+    static constexpr size_t CHUNK = (size_t)1 << 20;
+    static constexpr int MAXT = 32;
     PinnedBuf ring; cudaEvent_t ev[2 * MAXT]; bool made = false, used[2 * MAXT] = {};
     void release() { ring.release(); if (made) for (int i = 0; i < 2 * MAXT; i++) cudaEventDestroy(ev[i]); made = false; }
     // copies file bytes [off, off + len) to dst (device), asynchronously on `st` (every copy has been QUEUED when this returns)
@@ -248,6 +277,7 @@ struct FileStager {
         const int T = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>((size_t)ag_team_size(), MAXT), n_chunks));
         ring.ensure((size_t)2 * MAXT * CHUNK);
         std::atomic<int> failed(0);
+        static const bool no_read = getenv("AG_STAGE_NOREAD") != nullptr, no_copy = getenv("AG_STAGE_NOCOPY") != nullptr;   // diagnosis only: time the two halves apart
         ag_parallel_chunks(T, [&](int t) {
             cudaSetDevice(device);
             size_t j = 0;
@@ -257,8 +287,8 @@ struct FileStager {
                 char* h = ring.p + (size_t)slot * CHUNK;
                 const size_t o = k * CHUNK, n = std::min(CHUNK, len - o);
                 size_t a = 0;
-                while (a < n) { const ssize_t got = pread(fd, h + a, n - a, (off_t)(off + o + a)); if (got <= 0) { failed = 1; return; } a += (size_t)got; }
-                if (cudaMemcpyAsync(dst + o, h, n, cudaMemcpyHostToDevice, st) != cudaSuccess) { failed = 2; return; }
+                while (!no_read && a < n) { const ssize_t got = pread(fd, h + a, n - a, (off_t)(off + o + a)); if (got <= 0) { failed = 1; return; } a += (size_t)got; }
+                if (!no_copy && cudaMemcpyAsync(dst + o, h, n, cudaMemcpyHostToDevice, st) != cudaSuccess) { failed = 2; return; }
                 cudaEventRecord(ev[slot], st); used[slot] = true;
             }
         });

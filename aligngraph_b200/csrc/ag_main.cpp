@@ -283,8 +283,25 @@ int main(int argc, char* argv[]) {
         ag_refinement("tmp", units, genome_ids, contig_ids, o.tagUnique, o.ext, o.rmn, refine_blat, nullptr, true);  // #define TEST (AG:24) => in.fa / ex.fa
     } catch (const AgHostError& e) { die(e.msg); }
     if (o.tagMis == 1) {
-        // removeMisassembly (AG:3821-4297): never report success for a step that did not run
-        die("--misassemblyRemoval (AG:3821-4297) is not implemented in the B200 build: extendedContigs / remainingContigs above are the UN-corrected contigs");
+        // removeMisassembly (AG:4281-4297) on both output files: aligner command lines verbatim (makeAlignment, AG:3821-3850), coverage pile-up on the GPU
+        struct Mis { int low, high; } mis{o.low, o.high};
+        auto align = [](const char* id_, void* user) -> int {
+            const Mis& m = *(const Mis*)user; const string id = id_;
+            std::stringstream lo, hi; lo << m.low; hi << m.high;
+            string c = "bowtie2-build -f tmp/_" + id + "_contigs.fa tmp/_" + id + "_contigs > bowtie_doc.txt 2> bowtie_doc.txt";
+            if (system(c.c_str())) {}
+            c = "bowtie2 -f --no-mixed -k 1 -p 8 -I " + lo.str() + " -X " + hi.str() + " --no-discordant -x tmp/_" + id + "_contigs -1 tmp/_reads_1.fa -2 tmp/_reads_2.fa --reorder > tmp/_reads_" + id +
+                "_contigs.bowtie 2> bowtie_doc.txt";
+            if (system(c.c_str())) {}
+            return blat_call("tmp/_genome.fa", "tmp/_" + id + "_contigs.fa", "tmp/_" + id + "_contigs_genome.psl") ? 1 : 0;
+        };
+        ag_params p; p.k = o.k; p.insert_variation = o.iv; p.coverage = o.cov; p.device = devices[0];
+        ag_ctx* c = nullptr;
+        if (ag_create(&p, &c) != 0) die(ag_create_error());
+        if (ag_remove_misassembly_file(c, o.ext.c_str(), "extended", o.cov, "tmp", align, &mis) != 0) die(ag_last_error(c));
+        if (ag_remove_misassembly_file(c, o.rmn.c_str(), "remaining", o.cov, "tmp", align, &mis) != 0) die(ag_last_error(c));
+        ag_destroy(c);
+        cout << endl << "(6) Misassemblies removed" << endl;
     }
     time_t end = time(NULL);
     cout << endl << "FINISHED SUCCESSFULLY for " << end - start << " seconds (" << endAlign - startAlign << " seconds for alignment) :-)" << endl;

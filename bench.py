@@ -362,8 +362,10 @@ def b200_arm(args):
         # final records written (16 + 16 + 8 + 4).  Rank 0's launches (K per unit).
         L = cfg["readlen"]
         n_launch = K * len(my_units)
-        alg = stats["n_keys"] / max(len(my_units), 1) * (4 + 32 + (L + 3) // 4 + (L + 7) // 8) + cfg["unit_bp"] * (8 + 1 + 4) + stats["n_nodes"] / max(len(my_units), 1) * 44
-        nodes_ms = stats["ms_nodes"] / n_launch
+        tma = stats.get("ms_build_kernel", 0) > 0 and stats.get("ms_stage", 0) > 0
+        rec_bytes = ((12 + (L + 7) // 8 + 3) // 4 * 4) * 4 if tma else (4 + 32 + (L + 3) // 4 + (L + 7) // 8)   # staged record (48-byte header + 4-bit codes) | index + prepared record + packed words
+        alg = stats["n_keys"] / max(len(my_units), 1) * rec_bytes + cfg["unit_bp"] * (8 + 1 + 4) + stats["n_nodes"] / max(len(my_units), 1) * 44
+        nodes_ms = (stats["ms_build_kernel"] if stats.get("ms_build_kernel", 0) > 0 else stats["ms_nodes"]) / n_launch
         achieved = alg / nodes_ms / 1e6
         traffic = None
         try:   # DRAM bytes of one k_build launch from the committed `ncu --set full` capture of the c2 workload (profiles/README.md)
@@ -385,7 +387,7 @@ def b200_arm(args):
                                        "reads_host": int(st_e2e["reads_host"])}},
             "gpu_launches": int(tot_launch),
             "clocks": clock_info,
-            "roofline": {"bound": "hbm", "kernel": "k_build", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+            "roofline": {"bound": "hbm", "kernel": "k_build_tma" if tma else "k_build", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                          "traffic": traffic, "alg_bytes_per_launch": int(alg), "ms_per_launch": round(nodes_ms, 4),
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"},
             "device_ms_per_step": {k[3:]: round(stats[k] / K, 4) for k in stats if k.startswith("ms_")},

@@ -65,6 +65,7 @@ typedef struct ag_stats {
     float ms_ingest_reads, ms_ingest_sam;
     uint64_t sam_device, sam_host, reads_device, reads_host;
     uint64_t regrows; /* sweeps repeated with a larger node table / node overflow pool / edge overflow pool */
+    uint64_t reads_windowed; /* read sets ingested for the id window of the job's SAM files only */
     float ms_stage, ms_build_kernel; /* inside ms_nodes: staging gather (k_stage) and the node sweep kernel (k_build_tma / k_build) */
 } ag_stats;
 
@@ -153,7 +154,12 @@ int ag_pin_staged(ag_ctx* ctx);
 /* input normalisation that --resume re-runs (formalizeInput(contigs) + formalizeGenome, AG:4757-4758): writes tmp/_contigs.fa,
  * tmp/_chaff.fa, tmp/_genome.fa and tmp/_genome.N.fa; returns the number of units */
 int ag_formalize_inputs(ag_ctx* ctx, const char* contig_fa, const char* genome_fa, const char* tmp_dir, int part, int* n_units);
-/* tuning / test hooks: "host_parse" (1 = SAM and reads text parsed by the host parsers instead of the device kernels), "node_cap" / "ovf_cap" /
+/* removeMisassembly(file, distanceLow, distanceHigh, id, coverage, fastMap), AG:4281-4297, for one output file (`id` = "extended" or
+ * "remaining"): formalizes `file` into tmp/_<id>_contigs.fa, calls `align(id, user)` (non-zero = ok) which must run the reference's aligner
+ * commands (AG:3825-3849: bowtie2 reads -> contigs into tmp/_reads_<id>_contigs.bowtie, BLAT contigs -> genome into tmp/_<id>_contigs_genome.psl),
+ * piles the read alignments up into a per-base coverage on the GPU, and writes corrected_<file> in the current directory */
+int ag_remove_misassembly_file(ag_ctx* ctx, const char* file, const char* id, int coverage, const char* tmp_dir, int (*align)(const char* id, void* user), void* user);
+/* tuning / test hooks: "reads_window" (0 = ag_run_job_files always makes the whole read set resident), "host_parse" (1 = SAM and reads text parsed by the host parsers instead of the device kernels), "node_cap" / "ovf_cap" /
  * "eovf_cap" / "key_cap" / "cand_cap" / "hwalk_cap" (initial capacities of the node table, the node overflow pool, the edge overflow pool, the
  * tile-key buffers, the start-candidate arrays and the host walk-record buffer; small values force the grow-and-redo path), "rank_rounds"
  * (global list-ranking rounds queued per step), "tma" (0 = node sweep with per-thread staging, k_build, instead of the bulk-async staged k_build_tma) */

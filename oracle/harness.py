@@ -38,6 +38,7 @@ def build_tools(with_ref=True, with_emul=True):
     jobs = [
         (os.path.join(BIN, "ag_oracle"), [os.path.join(ORACLE, "ag_oracle.cpp")]),
         (os.path.join(BIN, "stubs", "pblat"), [os.path.join(ORACLE, "stubs", "pblat.cpp")]),
+        (os.path.join(BIN, "stubs", "bowtie2_contigs"), [os.path.join(ORACLE, "stubs", "bowtie2_contigs.cpp")]),
     ]
     for out, srcs in jobs:
         if _stale(out, srcs):

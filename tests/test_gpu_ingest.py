@@ -142,3 +142,57 @@ def test_device_ingest_full_size_unit(ag, harness, workdir):
     harness.synth(workdir, genome_bp=4600000, coverage=50, readlen=100, insert_mean=500, insert_sd=50, kmer=5, cov=20, seed=20260927)
     ud, st = check_same(ag, harness, workdir)
     assert ud[0][0] > 1_100_000
+
+
+def test_job_makes_only_the_referenced_reads_resident(ag, harness, workdir):
+    """ag_run_job_files loads the read set for the id window its units' SAM files span (found in the read file by bisection): unit 1 of a
+    two-chromosome job only needs the second half of tmp/_reads.fa.  Same files as the reference; a job over both units needs everything."""
+    import cases
+    from conftest import golden_dir
+    harness.synth(workdir, **cases.GOLDEN["two_chr"])
+    harness.prepare_tmp(workdir)
+    tmp = os.path.join(workdir, "tmp")
+    reads_fa = os.path.join(tmp, "_reads.fa")
+    p = harness.read_command(workdir)
+    ctx = ag.Context(k=p["kMer"], insert_variation=p["insertVariation"], coverage=p["coverage"])
+    ctx.run_job(tmp, [1], reads_fa=reads_fa)
+    st = ctx.stats()
+    assert st["reads_windowed"] == 1 and st["reads_device"] == 1 and st["sam_device"] == 1, st
+    assert st["h2d_bytes"] < 0.75 * os.path.getsize(reads_fa) + os.path.getsize(os.path.join(tmp, "_reads_genome.1.bowtie")) + 200000
+    g = golden_dir("two_chr")
+    for pat in harness.UNIT_FILES:
+        assert open(os.path.join(tmp, pat.format(1)), "rb").read() == open(os.path.join(g, pat.format(1)), "rb").read(), pat
+    ctx.reset_stats()
+    ctx.run_job(tmp, [0, 1], reads_fa=reads_fa)
+    st = ctx.stats()
+    assert st["reads_windowed"] == 0 and st["reads_device"] == 1 and st["sam_device"] == 2, st
+    for u in (0, 1):
+        for pat in harness.UNIT_FILES:
+            assert open(os.path.join(tmp, pat.format(u)), "rb").read() == open(os.path.join(g, pat.format(u)), "rb").read(), pat
+    ctx.close()
+
+
+def test_read_window_too_small_loads_the_whole_set(ag, harness, workdir):
+    """The window is only an estimate (first / last record of each SAM).  A file that references a read outside it — here a record of the other
+    chromosome's id range moved into the middle of unit 1's SAM, which also makes the file unsorted — must be noticed on the device, the whole
+    read set loaded, and the file handed to the host parser: same outputs as the oracle."""
+    import cases
+    gpu, ora = os.path.join(workdir, "gpu"), os.path.join(workdir, "ora")
+    harness.synth(gpu, **cases.GOLDEN["two_chr"])
+    tmp = os.path.join(gpu, "tmp")
+    s0 = open(os.path.join(tmp, "_reads_genome.0.bowtie")).read().split("\n")
+    s1 = open(os.path.join(tmp, "_reads_genome.1.bowtie")).read().split("\n")
+    s1 = [l for l in s1 if l]
+    mid = (len(s1) // 2) & ~1
+    s1[mid:mid] = s0[10:12]            # a pair of unit 0 (positions are valid in unit 1 as well: same chromosome length)
+    open(os.path.join(tmp, "_reads_genome.1.bowtie"), "w").write("\n".join(s1) + "\n")
+    shutil.copytree(gpu, ora)
+    harness.run_oracle(ora)
+    harness.prepare_tmp(gpu)
+    p = harness.read_command(gpu)
+    ctx = ag.Context(k=p["kMer"], insert_variation=p["insertVariation"], coverage=p["coverage"])
+    ctx.run_job(tmp, [1], reads_fa=os.path.join(tmp, "_reads.fa"))
+    st = ctx.stats()
+    ctx.close()
+    assert st["reads_windowed"] == 1 and st["reads_device"] == 2 and st["sam_host"] == 1, st
+    assert harness.unit_outputs(gpu, 1) == harness.unit_outputs(ora, 1)
