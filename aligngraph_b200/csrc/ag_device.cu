@@ -558,7 +558,10 @@ __device__ __forceinline__ void slot_bump(u32 saddr, u32 s, u32 code) {   // cov
     sts1(c, lds1(c) + 1u);
 }
 
-__global__ void __launch_bounds__(AG_TILE, AG_NODES_MINB) k_build_tma(DevView d, const u32* __restrict__ stage, u32 rsw) {
+#ifndef AG_TMA_MINB
+#define AG_TMA_MINB 5
+#endif
+__global__ void __launch_bounds__(AG_TILE, AG_TMA_MINB) k_build_tma(DevView d, const u32* __restrict__ stage, u32 rsw) {
     extern __shared__ __align__(128) u32 s_dyn[];                   // [AG_NF][NODE_SCAP][AG_TILE] node slots, then 2 x [ST_CH][rsw] staged records
     __shared__ __align__(8) unsigned long long s_bar[2];
     __shared__ u32 s_scan[33];
@@ -588,19 +591,20 @@ __global__ void __launch_bounds__(AG_TILE, AG_NODES_MINB) k_build_tma(DevView d,
     ag_plist pl; pl.n = 0; pl.ovf_head = pl.ovf_tail = AG_NONE;
     ag_cm1 ca; ca.cid = ca.coff = AG_NONE;
     if (active) ca = d.cm1[q];
-    const u32 kmer = (u32)d.k, thr = (u32)(2 * d.iv + 5 * AG_EP), rs_bytes = rsw * 4;
-    // values the loop keeps in registers (opaque to the compiler, which would otherwise re-derive them from special registers every iteration)
-    u32 qp = active ? q : 0xFFFFFFF0u, wq = wq0, saddr = sv.saddr, edge_lane = lane < AG_WPOS ? 1u : 0u;
-    asm volatile("" : "+r"(qp), "+r"(wq), "+r"(saddr), "+r"(edge_lane));
+    const u32 kmer = (u32)d.k;
+    // values the loop keeps in registers (opaque to the compiler, which would otherwise re-derive them from special registers / constants every iteration)
+    u32 qp = active ? q : 0xFFFFFFF0u, wq = wq0, saddr = sv.saddr, edge_lane = lane < AG_WPOS ? 1u : 0u, thr = (u32)(2 * d.iv + 5 * AG_EP), rs_bytes = rsw * 4, lane_p = lane;
+    asm volatile("" : "+r"(qp), "+r"(wq), "+r"(saddr), "+r"(edge_lane), "+r"(thr), "+r"(rs_bytes), "+r"(lane_p));
     const bool slots_mode = ca.cid != AG_CM_MANY;
     for (u32 c = 0; c < nchunks; c++) {
         const u32 cn = min((u32)ST_CH, ke - (kb + c * ST_CH));
         mbar_wait(bar0 + 8 * (c & 1), (c >> 1) & 1);
-        const u32 buf_s = stage_s + (c & 1) * chunk_bytes;            // shared-space address of this chunk's records
+        u32 buf_s = stage_s + (c & 1) * chunk_bytes;                  // shared-space address of this chunk's records
+        asm volatile("" : "+r"(buf_s));
         for (u32 r0 = 0; r0 < cn; r0 += 32) {
             // which of these 32 records touch any of the warp's 32 positions?
             bool ov = false;
-            if (r0 + lane < cn) { const uint2 ls = lds2(buf_s + (r0 + lane) * rs_bytes); ov = ls.x <= wq + 31 && ls.x + ls.y >= wq; }
+            if (r0 + lane_p < cn) { const uint2 ls = lds2(buf_s + (r0 + lane_p) * rs_bytes); ov = ls.x <= wq + 31 && ls.x + ls.y >= wq; }
             u32 mask = __ballot_sync(0xFFFFFFFFu, ov);
             while (mask) {
                 const u32 a = r0 + (u32)__ffs((int)mask) - 1;
@@ -622,7 +626,7 @@ __global__ void __launch_bounds__(AG_TILE, AG_NODES_MINB) k_build_tma(DevView d,
                         const bool bump = dq < ls.y;                // a call starts here (kind 1); else the stand-alone k2 of the last call
                         const u32 aoff = (h0.x & 0xFFFFu) + dq;
                         u32 code = 0;
-                        if (bump) code = (lds1(rec + ST_HDR_W * 4 + ((aoff >> 3) << 2)) >> ((aoff & 7u) << 2)) & 7u;
+                        if (bump) code = (lds1(rec + ST_HDR_W * 4 + ((aoff >> 1) & 0xFFFCu)) >> ((aoff << 2) & 28u)) & 7u;
                         want = bump;
                         if (pl.n >= 1 && slot_compatible(saddr, 0, cid0, coff0, moff, thr)) { if (bump) slot_bump(saddr, 0, code); item = 0; }
                         else if (pl.n >= 2 && slot_compatible(saddr, 1, cid0, coff0, moff, thr)) { if (bump) slot_bump(saddr, 1, code); item = 1; }

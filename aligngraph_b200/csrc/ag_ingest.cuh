@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(128) k_cov_marks(const char* __restrict__ text
 // slot is reused once its copy has finished.  The copy engine therefore always has several chunks queued while the next ones are read.
 // ---------------------------------------------------------------------------------------------------------------------------
 struct FileStager {
-    static constexpr size_t CHUNK = (size_t)1 << 20;
+    static constexpr size_t CHUNK = (size_t)4 << 20;
     static constexpr int MAXT = 32;
     PinnedBuf ring; cudaEvent_t ev[2 * MAXT]; bool made = false, used[2 * MAXT] = {};
     void release() { ring.release(); if (made) for (int i = 0; i < 2 * MAXT; i++) cudaEventDestroy(ev[i]); made = false; }

@@ -34,3 +34,21 @@ LIVE = {
     "manyitems": dict(genome_bp=16000, coverage=1200, insert_mean=5000, insert_sd=2500, contig_len=3000, seed=62, cov=3),
     "nocontigs": dict(genome_bp=30000, coverage=50, seed=7, contig_len=150, contig_gap=5000),
 }
+
+
+def add_misassemblies(work_dir, seed=7):
+    """Append three contigs that removeMisassembly (AlignGraph.cpp:3821-4297) has to act on to <work_dir>/contigs.fa — none of them is in the
+    contig alignment, so they pass through the hot loop into remainingContigs.fa untouched: (1) a chimera of two genome stretches around
+    700 random bases (no read covers the junk: the contig is broken into two parts), (2) a genome stretch with 350 random bases at its end
+    (the tail is cut off), (3) 320 random bases (removed altogether)."""
+    import os
+    import random
+    rnd = random.Random(seed)
+    g = "".join(l.strip() for l in open(os.path.join(work_dir, "genome.fa")) if not l.startswith(">"))
+    junk = lambda n: "".join(rnd.choice("ACGT") for _ in range(n))
+    extra = [("chimera", g[2000:3500] + junk(700) + g[12000:13500]), ("junktail", g[20000:21800] + junk(350)), ("alljunk", junk(320))]
+    with open(os.path.join(work_dir, "contigs.fa"), "a") as f:
+        for name, seq in extra:
+            f.write(">" + name + "\n")
+            for i in range(0, len(seq), 60):
+                f.write(seq[i:i + 60] + "\n")

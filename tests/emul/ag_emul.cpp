@@ -494,6 +494,30 @@ int main(int argc, char** argv) {
             printf("%s pairs=%lu exceptions=%zu\n", ok ? "IDENTICAL" : "DIFFERENT", (unsigned long)p.n_pairs, p.exc.size());
             return ok ? 0 : 1;
         }
+        else if (a == "--remove-misassembly") {   // <file> <id> <coverage> <run-aligners>: removeMisassembly's host logic in the current directory.
+            // run-aligners = 0: on aligner outputs already in tmp/ (left there by the reference); 1: run the aligners on $PATH with the
+            // reference's command lines (AlignGraph.cpp:3825-3849; the harness puts its stubs there), after writing tmp/_reads_1.fa,
+            // tmp/_reads_2.fa and tmp/_genome.fa from reads_1.fa / reads_2.fa / genome.fa as a fresh run does
+            const std::string file = argv[++i], id = argv[++i]; const int cov = atoi(argv[++i]); const int run = atoi(argv[++i]);
+            try {
+                if (run) {
+                    if (system("mkdir -p tmp")) {}
+                    std::vector<std::string> gids;
+                    ag_formalize_reads("reads_1.fa", "reads_2.fa", "tmp");
+                    ag_formalize_genome("genome.fa", "tmp", 1, gids);
+                }
+                ag_remove_misassembly(file, id, cov, "tmp", run ? [](const std::string& id_, void*) -> bool {
+                    std::string c = "bowtie2-build -f tmp/_" + id_ + "_contigs.fa tmp/_" + id_ + "_contigs > bowtie_doc.txt 2> bowtie_doc.txt";
+                    if (system(c.c_str())) {}
+                    c = "bowtie2 -f --no-mixed -k 1 -p 8 -I 0 -X 1500 --no-discordant -x tmp/_" + id_ + "_contigs -1 tmp/_reads_1.fa -2 tmp/_reads_2.fa --reorder > tmp/_reads_" + id_ + "_contigs.bowtie 2> bowtie_doc.txt";
+                    if (system(c.c_str())) {}
+                    c = "pblat tmp/_genome.fa tmp/_" + id_ + "_contigs.fa -noHead tmp/_" + id_ + "_contigs_genome.psl -fastMap -threads=8 > blat_doc.txt 2> blat_doc.txt";
+                    return system(c.c_str()) == 0;
+                } : [](const std::string&, void*) -> bool { return true; }, ag_coverage_pileup_host, nullptr);
+            }
+            catch (const AgHostError& e) { printf("%s\n", e.msg.c_str()); return 255; }
+            return 0;
+        }
         else if (a == "--first") first = atoi(argv[++i]);
         else if (a == "--last") last = atoi(argv[++i]);
         else { fprintf(stderr, "ag_emul: unknown option %s\n", a.c_str()); return 2; }

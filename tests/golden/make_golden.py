@@ -55,3 +55,21 @@ for name in ("plain", "two_chr"):
         f.write(f"fresh run (stub bowtie2/pblat), reference exit code {rc}; stdout tail: {out[-200:]!r}\n")
     print(name + "_fresh", "reference exit", rc, "ext bytes", os.path.getsize(os.path.join(dst, "extendedContigs.fa")))
     shutil.rmtree(work)
+
+# removeMisassembly (AlignGraph.cpp:3821-4297): a fresh run with --misassemblyRemoval on `plain` plus three contigs it has to act on
+# (tests/cases.py add_misassemblies); the stub aligners serve the read-vs-contig and contig-vs-genome alignments as well
+work = tempfile.mkdtemp(prefix="ag_golden_")
+params = dict(cases.GOLDEN["plain"]); params["misasm"] = 1
+harness.synth(work, **params)
+cases.add_misassemblies(work)
+args = harness.prepare_fresh(work)
+rc, out = harness.run_fresh(os.path.join(harness.REF, "AlignGraph_shipped"), work, args)
+dst = os.path.join(ROOT, "tests", "golden", "misasm_fresh")
+shutil.rmtree(dst, ignore_errors=True)
+os.makedirs(dst)
+for f in ("extendedContigs.fa", "remainingContigs.fa", "corrected_extendedContigs.fa", "corrected_remainingContigs.fa"):
+    shutil.copy(os.path.join(work, f), dst)
+with open(os.path.join(dst, "README.txt"), "w") as f:
+    f.write(f"fresh run with --misassemblyRemoval (stub bowtie2 / bowtie2_contigs / pblat), reference exit code {rc}; stdout tail: {out[-120:]!r}\n")
+print("misasm_fresh reference exit", rc, {f: os.path.getsize(os.path.join(dst, f)) for f in os.listdir(dst)})
+shutil.rmtree(work)

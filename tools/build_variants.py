@@ -9,6 +9,8 @@ sys.path.insert(0, ROOT)
 from aligngraph_b200 import build as b  # noqa: E402
 
 VARIANTS = {
+    "tma_minb5": ["-DAG_TMA_MINB=5"],                            # TMA-staged node sweep at 48 registers / 5 CTAs per SM
+    "tma_minb4": ["-DAG_TMA_MINB=4"],                            # ... at 64 registers / 4 CTAs per SM
     "code4": ["-DAG_CODE4=1"],                                   # left mates staged as oriented 4-bit codes (CPU-verified coder, not yet timed)
     "code4_minb5": ["-DAG_CODE4=1", "-DAG_NODES_MINB=5"],
     "minb5": ["-DAG_NODES_MINB=5"],
