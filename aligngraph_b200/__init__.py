@@ -92,6 +92,7 @@ def load_library(path=None):
         "ag_formalize_inputs": (i32, [vp, cp, cp, cp, i32, C.POINTER(i32)]),
         "ag_set_option": (i32, [vp, cp, C.c_long]),
         "ag_remove_misassembly_file": (i32, [vp, cp, cp, i32, cp, vp, vp]),
+        "ag_containment_search_files": (i32, [vp, cp, cp, cp]),
         "ag_timer_start": (i32, [vp]),
         "ag_timer_stop": (i32, [vp, C.POINTER(C.c_float)]),
     }

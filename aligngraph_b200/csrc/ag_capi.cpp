@@ -491,6 +491,13 @@ int ag_pin_staged(ag_ctx* ctx) {
         d.pin(u.aln.data(), u.aln.size() * sizeof(ag_aln)); d.pin(u.ext.data(), u.ext.size() * sizeof(ag_seg));
     });
 }
+// the aligner call of refinement() (AG:2957-2983) without an aligner: seed-and-verify containment search, candidate verification on the GPU
+int ag_containment_search_files(ag_ctx* ctx, const char* db_fa, const char* query_fa, const char* out_psl) {
+    return guard(ctx, [&] {
+        ag_contain_search(db_fa, query_fa, out_psl,
+            [](const AgSeqSet& db, const AgSeqSet& qs, const std::vector<AgPlacement>& cand, std::vector<u32>& match, void* p) { ((ag_ctx*)p)->dev->verify_placements(db, qs, cand, match); }, ctx);
+    });
+}
 // removeMisassembly (AG:4281-4297) for one output file; the per-base coverage pile-up runs on the context's GPU
 int ag_remove_misassembly_file(ag_ctx* ctx, const char* file, const char* id, int coverage, const char* tmp_dir, int (*align)(const char* id, void* user), void* user) {
     return guard(ctx, [&] {

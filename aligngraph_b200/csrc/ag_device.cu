@@ -1217,7 +1217,7 @@ struct AgDevice::Impl {
     Scanner scanner;
     u32 n_tiles = 0, n_keys = 0, n_nodes = 0;
     u32 node_cap = 0, ovf_cap = 0, eovf_cap = 0, eovf_cap_init = 0, walk_cap = 0;
-    u32 key_cap = 0, cand_cap = 0, hwalk_cap = 0, n_walks = 0; int rank_rounds = 2;
+    u32 key_cap = 0, cand_cap = 0, hwalk_cap = 0, n_walks = 0; int rank_rounds = 1;   // one global list-ranking round (chains that leave their 1024-node block once); more on request (E_RANK_MORE)
     u32 unit_n_ref = 0; u64 unit_n_aln = 0;   // the unit the capacities above were last derived for
     PinnedBuf h_wrec;                        // compacted walk records, written by k_walk_compact straight into host memory
     DBuf<u32> status, walk_rank; DBuf<int> err_load; SectionTimes sections;
@@ -1770,6 +1770,26 @@ bool AgDevice::coverage_pileup(const std::string& path, const std::vector<u32>& 
     if (flags) { cov.assign(nb, 0); return ing_fallback("pileup", 207); }
     // an interval that crosses a chunk end would leak into the next chunk: intervals are clipped to their chunk in the kernel, so it cannot
     return true;
+}
+void AgDevice::verify_placements(const AgSeqSet& db, const AgSeqSet& qs, const std::vector<AgPlacement>& cand, std::vector<u32>& match) {
+    CK(cudaSetDevice(dev_));
+    Impl& m = *m_; cudaStream_t st = m.st;
+    match.assign(cand.size(), 0);
+    if (cand.empty()) return;
+    DBuf<char> d_db, d_q; DBuf<u64> d_dbo, d_qo; DBuf<ag_place> d_c; DBuf<u32> d_m;
+    d_db.ensure(db.blob.size() + 1); d_q.ensure(qs.blob.size() + 1); d_dbo.ensure(db.off.size()); d_qo.ensure(qs.off.size()); d_c.ensure(cand.size()); d_m.ensure(cand.size());
+    std::vector<ag_place> hc(cand.size());
+    for (size_t i = 0; i < cand.size(); i++) { hc[i].q = cand[i].q; hc[i].strand = cand[i].strand; hc[i].t = cand[i].t; hc[i].pad = 0; hc[i].start = cand[i].start; }
+    CK(cudaMemcpyAsync(d_db.p, db.blob.data(), db.blob.size(), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_q.p, qs.blob.data(), qs.blob.size(), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_dbo.p, db.off.data(), db.off.size() * sizeof(u64), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_qo.p, qs.off.data(), qs.off.size() * sizeof(u64), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_c.p, hc.data(), hc.size() * sizeof(ag_place), cudaMemcpyHostToDevice, st));
+    const u32 nc = (u32)cand.size();
+    k_verify_placements<<<(unsigned)(((size_t)nc * 32 + 255) / 256), 256, 0, st>>>(d_db.p, d_dbo.p, d_q.p, d_qo.p, d_c.p, nc, d_m.p); launches_++;
+    CK(cudaMemcpyAsync(match.data(), d_m.p, (size_t)nc * sizeof(u32), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    d_db.release(); d_q.release(); d_dbo.release(); d_qo.release(); d_c.release(); d_m.release();
 }
 bool AgDevice::sam_window_miss() const { return m_->window_miss; }
 u64 AgDevice::ingested_alignments() const { return m_->aln_ingested ? m_->n_aln : 0; }

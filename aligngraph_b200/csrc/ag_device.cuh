@@ -67,6 +67,8 @@ public:
     // removeMisassembly's coverage pile-up (AG:3938-3978) of tmp/_reads_<id>_contigs.bowtie over the chunks of tmp/_<id>_contigs.fa; false: the
     // file is not in the layout the kernel handles (the caller uses ag_coverage_pileup_host)
     bool coverage_pileup(const std::string& sam_path, const std::vector<u32>& chunk_len, std::vector<int>& coverage);
+    // matching bases of the candidate placements of ag_contain_search (refinement without BLAT), on the device
+    void verify_placements(const struct AgSeqSet& db, const struct AgSeqSet& queries, const std::vector<struct AgPlacement>& cand, std::vector<u32>& match);
     u64 ingested_alignments() const;
     void note_host_sam() { t_.sam_host++; }
     void note_host_reads() { t_.reads_host++; }

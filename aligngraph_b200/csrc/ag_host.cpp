@@ -1199,11 +1199,20 @@ void ag_make_contigs_begin(const std::vector<ag_walk>& walks, const std::vector<
                            std::vector<AgContig>& contigs, AgMakeState& st) {
     auto tp0 = std::chrono::steady_clock::now();
     contigs.clear(); contigs.resize(sel.size());
-    // sequential, light: contig records + header strings + where every contig's text goes.  Does not read the bases.
-    std::string& hdr = st.hdr; hdr.clear(); hdr.reserve(sel.size() * 72);
+    // contig records + header strings + where every contig's text goes (nothing here reads the bases).  Headers are formatted by the thread
+    // team into fixed slots, then packed.
+    std::string& hdr = st.hdr;
     std::vector<size_t>& hoff = st.hoff; std::vector<size_t>& toff = st.toff;
     hoff.assign(sel.size() + 1, 0); toff.assign(sel.size() + 1, 0);
-    for (size_t i = 0; i < sel.size(); i++) {
+    const size_t SLOT = 160;
+    static thread_local std::vector<char> slots;   // (one materialisation at a time per calling thread)
+    std::vector<unsigned char> hlen(sel.size());
+    slots.resize(sel.size() * SLOT);
+    char* const slot_base = slots.data();   // (the team's threads must not name the thread_local themselves: each would see its own, empty one)
+    const int nchunk = (int)std::min<size_t>((sel.size() + 511) / 512, (size_t)std::max(1, ag_team_size() * 2));
+    const size_t per = nchunk ? (sel.size() + (size_t)nchunk - 1) / (size_t)nchunk : 0;
+    ag_parallel_chunks(nchunk, [&](int ch) {
+      for (size_t i = (size_t)ch * per; i < std::min(sel.size(), ((size_t)ch + 1) * per); i++) {
         const ag_walk& r = walks[sel[i]];
         AgContig& c = contigs[i];
         c.extended = (int)(r.flags & 1);
@@ -1217,19 +1226,23 @@ void ag_make_contigs_begin(const std::vector<ag_walk>& walks, const std::vector<
             const u32 slen = r.tail_soff_len >> 16;
             c.eoff = c.eoff + slen - 1; c.eoff0 = c.eoff0 + slen - 1;   // size_t arithmetic truncated to u32 (AG:2170-2171)
         }
-        {   // ">i, extended, sid, soff, eid, eoff, sid0, soff0, eid0, eoff0 \n"  (AG:2178): one append per header
-            char hb[160]; char* w = hb;
+        {   // ">i, extended, sid, soff, eid, eoff, sid0, soff0, eid0, eoff0 \n"  (AG:2178)
+            char* hb = slot_base + i * SLOT; char* w = hb;
             auto num = [&](unsigned long v) { char t[24]; int k = 24; do { t[--k] = (char)('0' + v % 10); v /= 10; } while (v); memcpy(w, t + k, (size_t)(24 - k)); w += 24 - k; };
             auto sep = [&]() { *w++ = ','; *w++ = ' '; };
             *w++ = '>'; num(i); sep();
             if (c.extended < 0) { *w++ = '-'; num((unsigned long)(-(long)c.extended)); } else num((unsigned long)c.extended);
             sep(); num(c.sid); sep(); num(c.soff); sep(); num(c.eid); sep(); num(c.eoff); sep(); num(c.sid0); sep(); num(c.soff0); sep(); num(c.eid0); sep(); num(c.eoff0);
             *w++ = ' '; *w++ = '\n';
-            hdr.append(hb, (size_t)(w - hb));
+            hlen[i] = (unsigned char)(w - hb);
         }
-        hoff[i + 1] = hdr.size();
-        toff[i + 1] = toff[i] + (hoff[i + 1] - hoff[i]) + wrapped_len(c.n);
-    }
+      }
+    });
+    for (size_t i = 0; i < sel.size(); i++) { hoff[i + 1] = hoff[i] + hlen[i]; toff[i + 1] = toff[i] + hlen[i] + wrapped_len((size_t)(offs[i + 1] - offs[i])); }
+    hdr.resize(hoff.back());
+    ag_parallel_chunks(nchunk, [&](int ch) {
+        for (size_t i = (size_t)ch * per; i < std::min(sel.size(), ((size_t)ch + 1) * per); i++) memcpy(&hdr[hoff[i]], slot_base + i * SLOT, hlen[i]);
+    });
     if (getenv("AG_POST_TIMING")) fprintf(stderr, "  [make_contigs] records + headers %.2f ms\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - tp0).count() * 1e3);
 }
 
@@ -1675,6 +1688,124 @@ void ag_refinement(const std::string& tmp, int units, const std::vector<std::str
     delete test_in; delete test_ex;
 }
 
+
+
+// =============================================================================================================================
+// built-in containment search for refinement() when no BLAT is installed (see ag_host.h)
+// =============================================================================================================================
+namespace {
+void load_seqset(const std::string& path, AgSeqSet& out) {
+    FileMap fm(path);
+    if (!fm.ok) throw AgHostError{"CANNOT OPEN FILE!"};
+    out.names.clear(); out.off.clear(); out.blob.clear();
+    Lines ln(fm.p, fm.n); const char* s; size_t n;
+    while (ln.next(s, n)) {
+        if (n == 0) { if (!ln.good) break; continue; }
+        if (s[0] == '>') { out.names.emplace_back(s + 1, n - 1); out.off.push_back(out.blob.size()); }
+        else if (!out.names.empty()) out.blob.append(s, n);
+    }
+    out.off.push_back(out.blob.size());
+}
+inline char comp_c(char c) { return c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : c; }
+inline u64 hash24(const char* p) { u64 h = 1469598103934665603ull; for (int i = 0; i < 24; i++) { h ^= (unsigned char)p[i]; h *= 1099511628211ull; } return h; }
+}  // namespace
+
+void ag_verify_placements_host(const AgSeqSet& db, const AgSeqSet& qs, const std::vector<AgPlacement>& cand, std::vector<u32>& match, void*) {
+    match.assign(cand.size(), 0);
+    for (size_t c = 0; c < cand.size(); c++) {
+        const AgPlacement& p = cand[c];
+        const char* q = qs.blob.data() + qs.off[p.q]; const size_t len = qs.len(p.q);
+        const char* t = db.blob.data() + db.off[p.t] + p.start;
+        u32 m = 0;
+        for (size_t i = 0; i < len; i++) m += (p.strand ? comp_c(q[len - 1 - i]) : q[i]) == t[i];
+        match[c] = m;
+    }
+}
+
+void ag_contain_search(const std::string& db_fa, const std::string& query_fa, const std::string& out_psl, AgVerifyFn verify, void* user) {
+    const size_t K = 24;
+    AgSeqSet db, qs;
+    load_seqset(db_fa, db); load_seqset(query_fa, qs);
+    // index of the database 24-mers: (hash, sequence, offset), sorted
+    struct Ent { u64 h; u32 t; u32 i; };
+    std::vector<Ent> idx;
+    for (size_t t = 0; t < db.n(); t++) { const char* s = db.blob.data() + db.off[t]; const size_t L = db.len(t); for (size_t i = 0; i + K <= L; i++) idx.push_back(Ent{hash24(s + i), (u32)t, (u32)i}); }
+    std::sort(idx.begin(), idx.end(), [](const Ent& a, const Ent& b) { return a.h != b.h ? a.h < b.h : a.t != b.t ? a.t < b.t : a.i < b.i; });
+    auto hits = [&](const char* kmer, std::vector<std::pair<u32, u32>>& out) {   // occurrences of the 24-mer, in (sequence, offset) order
+        out.clear();
+        const u64 h = hash24(kmer);
+        auto it = std::lower_bound(idx.begin(), idx.end(), h, [](const Ent& a, u64 v) { return a.h < v; });
+        for (; it != idx.end() && it->h == h; ++it) if (memcmp(db.blob.data() + db.off[it->t] + it->i, kmer, K) == 0) out.push_back({it->t, it->i});
+    };
+    // oriented queries and their full-length candidates
+    std::vector<AgPlacement> cand; std::vector<size_t> first;   // candidates of (query, strand) = [first[2q + strand], first[2q + strand + 1])
+    std::vector<std::string> oriented(2 * qs.n());
+    std::vector<std::pair<u32, u32>> hv;
+    for (size_t q = 0; q < qs.n(); q++)
+        for (u32 strand = 0; strand < 2; strand++) {
+            first.push_back(cand.size());
+            std::string& s = oriented[2 * q + strand];
+            s.assign(qs.blob.data() + qs.off[q], qs.len(q));
+            if (strand) { std::reverse(s.begin(), s.end()); for (char& c : s) c = comp_c(c); }
+            if (s.size() < K) continue;
+            std::vector<std::pair<u32, long>> seen;
+            for (size_t off = 0; off + K <= s.size(); off += std::max<size_t>(K, s.size() / 16)) {
+                hits(s.data() + off, hv);
+                for (auto& h : hv) {
+                    const long start = (long)h.second - (long)off;
+                    if (start < 0 || start + (long)s.size() > (long)db.len(h.first)) continue;
+                    if (std::find(seen.begin(), seen.end(), std::make_pair(h.first, start)) != seen.end()) continue;
+                    seen.push_back({h.first, start});
+                    cand.push_back(AgPlacement{(u32)q, strand, h.first, start});
+                }
+            }
+        }
+    first.push_back(cand.size());
+    std::vector<u32> match;
+    verify(db, qs, cand, match, user);
+    Out out(out_psl);
+    char line[512];
+    for (size_t q = 0; q < qs.n(); q++)
+        for (u32 strand = 0; strand < 2; strand++) {
+            const std::string& s = oriented[2 * q + strand];
+            if (s.size() < K) continue;
+            bool placed = false;
+            for (size_t c = first[2 * q + strand]; c < first[2 * q + strand + 1]; c++) {
+                const long m = match[c];
+                if (m * 10 < (long)s.size() * 9) continue;
+                placed = true;
+                const AgPlacement& p = cand[c];
+                int n = snprintf(line, sizeof line, "%ld\t%ld\t0\t0\t0\t0\t0\t0\t%c\t%s\t%zu\t0\t%zu\t%s\t%zu\t%ld\t%ld\t1\t%zu,\t0,\t%ld,\n", m, (long)s.size() - m, strand ? '-' : '+',
+                                 qs.names[q].c_str(), s.size(), s.size(), db.names[p.t].c_str(), db.len(p.t), p.start, p.start + (long)s.size(), s.size(), p.start);
+                out.put(line, (size_t)n);
+            }
+            if (placed) continue;
+            // local ungapped alignments: seeds every K bases, every new diagonal extended both ways with an X-drop (match +1, mismatch -3, drop 30)
+            std::vector<std::pair<std::pair<u32, long>, long>> done;
+            for (size_t off = 0; off + K <= s.size(); off += K) {
+                hits(s.data() + off, hv);
+                for (auto& h : hv) {
+                    const u32 t = h.first; const long diag = (long)h.second - (long)off; const char* ts = db.blob.data() + db.off[t]; const long tl = (long)db.len(t);
+                    long qa = (long)off, qe = (long)off + (long)K;
+                    { long score = 0, best = 0, i = qe, be = qe;
+                      while (i < (long)s.size() && i + diag < tl) { score += s[(size_t)i] == ts[i + diag] ? 1 : -3; i++; if (score > best) { best = score; be = i; } if (score < best - 30) break; }
+                      qe = be; }
+                    { long score = 0, best = 0, i = qa - 1, bs = qa;
+                      while (i >= 0 && i + diag >= 0) { score += s[(size_t)i] == ts[i + diag] ? 1 : -3; if (score > best) { best = score; bs = i; } if (score < best - 30) break; i--; }
+                      qa = bs; }
+                    if (qe - qa < 100) continue;
+                    const auto key = std::make_pair(std::make_pair(t, diag), qa);
+                    if (std::find(done.begin(), done.end(), key) != done.end()) continue;
+                    done.push_back(key);
+                    long m = 0;
+                    for (long i = qa; i < qe; i++) m += s[(size_t)i] == ts[i + diag];
+                    int n = snprintf(line, sizeof line, "%ld\t%ld\t0\t0\t0\t0\t0\t0\t%c\t%s\t%zu\t%ld\t%ld\t%s\t%zu\t%ld\t%ld\t1\t%ld,\t%ld,\t%ld,\n", m, (qe - qa) - m, strand ? '-' : '+',
+                                     qs.names[q].c_str(), s.size(), qa, qe, db.names[t].c_str(), (size_t)tl, qa + diag, qe + diag, qe - qa, qa, qa + diag);
+                    out.put(line, (size_t)n);
+                }
+            }
+        }
+}
 
 // =============================================================================================================================
 // removeMisassembly (AG:3821-4297)

@@ -169,6 +169,18 @@ int ag_max_read_length(const std::string& path);                                
 long ag_formalize_reads(const std::string& in1, const std::string& in2, const std::string& tmp);        // AG:3420
 void ag_distribute_alignments(const std::string& tmp, int units);                                       // AG:3545
 double ag_check_ratio(const std::string& tmp, int units);                                               // AG:3751
+// Built-in replacement for the aligner call of refinement() (AG:2957-2983: `pblat <extended contigs> <truncated initial contigs> -noHead out.psl`)
+// when no BLAT is installed: ungapped seed-and-verify containment search.  Every query (<= 20 kbp by construction, AG:2891-2953) is placed on
+// every database sequence, either strand, by exact 24-mer seeds and a full-length comparison (>= 90 % identity: refinement only keeps
+// alignments covering >= 80 % of the query, AG:3059); a query without any full-length placement gets its local ungapped alignments
+// (seed + X-drop).  Output: single-block PSL lines (-noHead), one per placement.  `verify` counts the matching bases of every candidate
+// placement — the device kernel in the product, ag_verify_placements_host in CPU tests.
+struct AgPlacement { u32 q, strand, t; long start; };
+struct AgSeqSet { std::vector<std::string> names; std::vector<u64> off; std::string blob; size_t n() const { return names.size(); } size_t len(size_t i) const { return (size_t)(off[i + 1] - off[i]); } };
+typedef void (*AgVerifyFn)(const AgSeqSet& db, const AgSeqSet& queries, const std::vector<AgPlacement>& cand, std::vector<u32>& match, void* user);
+void ag_verify_placements_host(const AgSeqSet& db, const AgSeqSet& queries, const std::vector<AgPlacement>& cand, std::vector<u32>& match, void* user);
+void ag_contain_search(const std::string& db_fa, const std::string& query_fa, const std::string& out_psl, AgVerifyFn verify, void* user);
+
 // removeMisassembly (AG:3821-4297) for one output file (`id` = "extended" | "remaining"): formalize it into tmp/_<id>_contigs.fa, let `align`
 // run the aligners (bowtie2 reads -> contigs, BLAT contigs -> genome: command lines in the CLI), pile the read alignments up into a per-base
 // coverage (`pileup`: the device kernel in the product, ag_coverage_pileup_host in CPU tests), keep / break / drop contig regions, write

@@ -260,6 +260,28 @@ __global__ void __launch_bounds__(128) k_cov_marks(const char* __restrict__ text
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
+// built-in containment search of refinement() (ag_contain_search): matching bases of every candidate placement of a query (either strand)
+// on a database sequence.  One warp per candidate, lanes stride over the query (coalesced byte loads), shuffle reduction.
+// ---------------------------------------------------------------------------------------------------------------------------
+struct ag_place { u32 q, strand, t, pad; long long start; };
+__global__ void k_verify_placements(const char* __restrict__ db, const u64* __restrict__ db_off, const char* __restrict__ qs, const u64* __restrict__ q_off,
+                                    const ag_place* __restrict__ cand, u32 n_cand, u32* __restrict__ match) {
+    const u32 w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n_cand) return;
+    const ag_place p = cand[w];
+    const char* q = qs + q_off[p.q]; const u32 len = (u32)(q_off[p.q + 1] - q_off[p.q]);
+    const char* t = db + db_off[p.t] + p.start;
+    u32 m = 0;
+    for (u32 i = lane; i < len; i += 32) {
+        char c = p.strand ? q[len - 1 - i] : q[i];
+        if (p.strand) c = c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : c;
+        m += c == t[i];
+    }
+    for (int o = 16; o; o >>= 1) m += __shfl_xor_sync(0xFFFFFFFFu, m, o);
+    if (lane == 0) match[w] = m;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
 // file -> device through page-locked staging chunks.  T host threads each own two pinned slots and take the file's chunks round-robin:
 // pread() into a slot (page cache -> pinned memory at memory speed), queue the slot's host->device copy, move on to the other slot; a
 // slot is reused once its copy has finished.  The copy engine therefore always has several chunks queued while the next ones are read.

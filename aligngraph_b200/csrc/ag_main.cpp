@@ -152,9 +152,14 @@ static void run_blat(int units) {
         if (!blat_call("tmp/_genome." + n + ".fa", "tmp/_contigs.fa", "tmp/_contigs_genome." + n + ".psl")) throw AgHostError{"BLAT CALL FAILED!"};
     }
 }
-static bool refine_blat(int unit, void*) {
+// refinement's aligner call (AG:2957-2983).  Without pblat / blat on $PATH (or with AG_BUILTIN_CONTAINMENT=1) the library's own containment
+// search produces the PSL: the reference would stop with BLAT CALL FAILED!, this build can finish the run on a host that has no BLAT.
+static bool refine_blat(int unit, void* user) {
     string n = std::to_string(unit);
-    return blat_call("tmp/_extended_contigs." + n + ".fa", "tmp/_short_initial_contigs." + n + ".fa", "tmp/_short_initial_contigs_extended_contigs." + n + ".psl");
+    const string db = "tmp/_extended_contigs." + n + ".fa", q = "tmp/_short_initial_contigs." + n + ".fa", out = "tmp/_short_initial_contigs_extended_contigs." + n + ".psl";
+    if (!getenv("AG_BUILTIN_CONTAINMENT") && blat_call(db, q, out)) return true;
+    ag_ctx* ctx = (ag_ctx*)user;
+    return ctx && ag_containment_search_files(ctx, db.c_str(), q.c_str(), out.c_str()) == 0;
 }
 
 int main(int argc, char* argv[]) {
@@ -279,9 +284,15 @@ int main(int argc, char* argv[]) {
         for (ag_ctx* c : ctxs) ag_destroy(c);
     }
 
-    try {
-        ag_refinement("tmp", units, genome_ids, contig_ids, o.tagUnique, o.ext, o.rmn, refine_blat, nullptr, true);  // #define TEST (AG:24) => in.fa / ex.fa
-    } catch (const AgHostError& e) { die(e.msg); }
+    {
+        ag_params p; p.k = o.k; p.insert_variation = o.iv; p.coverage = o.cov; p.device = devices[0];
+        ag_ctx* rc = nullptr;
+        if (ag_create(&p, &rc) != 0) die(ag_create_error());
+        try {
+            ag_refinement("tmp", units, genome_ids, contig_ids, o.tagUnique, o.ext, o.rmn, refine_blat, rc, true);  // #define TEST (AG:24) => in.fa / ex.fa
+        } catch (const AgHostError& e) { ag_destroy(rc); die(e.msg); }
+        ag_destroy(rc);
+    }
     if (o.tagMis == 1) {
         // removeMisassembly (AG:4281-4297) on both output files: aligner command lines verbatim (makeAlignment, AG:3821-3850), coverage pile-up on the GPU
         struct Mis { int low, high; } mis{o.low, o.high};

@@ -154,6 +154,11 @@ int ag_pin_staged(ag_ctx* ctx);
 /* input normalisation that --resume re-runs (formalizeInput(contigs) + formalizeGenome, AG:4757-4758): writes tmp/_contigs.fa,
  * tmp/_chaff.fa, tmp/_genome.fa and tmp/_genome.N.fa; returns the number of units */
 int ag_formalize_inputs(ag_ctx* ctx, const char* contig_fa, const char* genome_fa, const char* tmp_dir, int part, int* n_units);
+/* the aligner call inside refinement() (AG:2957-2983: pblat <db> <query> -noHead <out> -fastMap) for hosts without BLAT: ungapped seed-and-verify
+ * containment search of every query (the truncated initial contigs, <= 20 kbp) in every database sequence (the extended contigs), either
+ * strand — exact 24-mer seeds, full-length comparison on the GPU (>= 90 % identity), local X-drop alignments for queries that do not fit
+ * anywhere — written as single-block PSL lines */
+int ag_containment_search_files(ag_ctx* ctx, const char* db_fa, const char* query_fa, const char* out_psl);
 /* removeMisassembly(file, distanceLow, distanceHigh, id, coverage, fastMap), AG:4281-4297, for one output file (`id` = "extended" or
  * "remaining"): formalizes `file` into tmp/_<id>_contigs.fa, calls `align(id, user)` (non-zero = ok) which must run the reference's aligner
  * commands (AG:3825-3849: bowtie2 reads -> contigs into tmp/_reads_<id>_contigs.bowtie, BLAT contigs -> genome into tmp/_<id>_contigs_genome.psl),

@@ -494,6 +494,11 @@ int main(int argc, char** argv) {
             printf("%s pairs=%lu exceptions=%zu\n", ok ? "IDENTICAL" : "DIFFERENT", (unsigned long)p.n_pairs, p.exc.size());
             return ok ? 0 : 1;
         }
+        else if (a == "--contain-search") {   // <db.fa> <query.fa> <out.psl>: the built-in containment search of refinement(), candidates verified on the host
+            const std::string db = argv[++i], q = argv[++i], out = argv[++i];
+            try { ag_contain_search(db, q, out, ag_verify_placements_host, nullptr); } catch (const AgHostError& e) { printf("%s\n", e.msg.c_str()); return 255; }
+            return 0;
+        }
         else if (a == "--remove-misassembly") {   // <file> <id> <coverage> <run-aligners>: removeMisassembly's host logic in the current directory.
             // run-aligners = 0: on aligner outputs already in tmp/ (left there by the reference); 1: run the aligners on $PATH with the
             // reference's command lines (AlignGraph.cpp:3825-3849; the harness puts its stubs there), after writing tmp/_reads_1.fa,
