@@ -31,7 +31,7 @@ class Stats(C.Structure):
                                           "h2d_bytes", "d2h_bytes")] + \
                [("walk_fallback", C.c_int), ("ms_ingest_reads", C.c_float), ("ms_ingest_sam", C.c_float)] + \
                [(n, C.c_uint64) for n in ("sam_device", "sam_host", "reads_device", "reads_host", "regrows", "reads_windowed")] + \
-               [("ms_stage", C.c_float), ("ms_build_kernel", C.c_float)]
+               [("ms_stage", C.c_float), ("ms_build_kernel", C.c_float), ("ms_select", C.c_float)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -65,6 +65,7 @@ def load_library(path=None):
         "ag_set_reads_device": (i32, [vp, vp, vp, vp, u64, u32, u32]),
         "ag_set_read_exceptions": (i32, [vp, vp, vp, u64]),
         "ag_load_reads_fasta": (i32, [vp, cp]),
+        "ag_load_reads_for_units": (i32, [vp, cp, cp, C.POINTER(i32), i32]),
         "ag_get_reads": (i32, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(u64), C.POINTER(u32), C.POINTER(u32)]),
         "ag_broadcast_reads": (i32, [C.POINTER(vp), i32, vp]),
         "ag_begin_unit": (i32, [vp, i32, vp, u32]),
@@ -135,6 +136,10 @@ class Context:
     # ---- reads ---------------------------------------------------------------------------------------------------------
     def load_reads_fasta(self, path):
         self._ck(self._lib.ag_load_reads_fasta(self._h, os.fsencode(path)), "ag_load_reads_fasta")
+
+    def load_reads_for_units(self, reads_fa, tmp_dir, units):
+        ul = (C.c_int * len(units))(*units)
+        self._ck(self._lib.ag_load_reads_for_units(self._h, os.fsencode(reads_fa), os.fsencode(tmp_dir), ul, len(units)), "ag_load_reads_for_units")
 
     def get_reads(self):
         """(bases_ptr, nmask_ptr, len_ptr, n_pairs, stride2, stridem) of the packed host copy."""

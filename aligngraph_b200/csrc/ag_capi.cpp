@@ -241,13 +241,36 @@ int ag_process(ag_ctx* ctx) {
     return rc;
 }
 
+// extendContigs + scaffoldContigs on the device engine's fused path: walk, emission filter and materialisation are one queued step with a
+// single synchronisation (AgDevice::extend_emitted); the host continues with the emitted contigs only
+static void extend_unit_fused(AgDevice& dev, const AgReads& reads, const std::string& ref, AgUnitResult& r, u64& n_walks, u64& n_emitted) {
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<ag_walk> em; char* bases = nullptr; std::vector<u64> offs;
+    dev.extend_emitted(em, bases, offs, n_walks);
+    auto t1 = std::chrono::steady_clock::now();
+    std::vector<u32> sel(em.size());
+    for (size_t i = 0; i < sel.size(); i++) sel[i] = (u32)i;
+    std::vector<AgContig> contigs; AgMakeState ms;
+    ag_make_contigs_begin(em, sel, bases, offs, contigs, ms);
+    ag_make_contigs_finish(em, sel, bases, offs, reads, contigs, ms, r.pre_text);
+    ag_dedup_join(contigs);
+    std::vector<unsigned char> occ;
+    dev.occupancy_wait(occ);
+    ag_scaffold(contigs, ref, occ, r.ext_text);
+    auto t2 = std::chrono::steady_clock::now();
+    r.t_device += std::chrono::duration<double>(t1 - t0).count();
+    r.t_post += std::chrono::duration<double>(t2 - t1).count();
+    n_emitted = em.size();
+}
+
 // extension half of ag_process_unit (kept separate so that ag_build can be timed / inspected on its own)
 int ag_extend(ag_ctx* ctx) {
     return guard(ctx, [&] {
         AgUnitResult& r = ctx->res;
         const double d0 = r.t_device, p0 = r.t_post;
         u64 nw = 0, ne = 0;
-        ag_extend_unit(*ctx->dev, (*ctx->rp), ctx->unit.ref, r, nw, ne);
+        if (ctx->dev->fused_extend()) extend_unit_fused(*ctx->dev, (*ctx->rp), ctx->unit.ref, r, nw, ne);
+        else ag_extend_unit(*ctx->dev, (*ctx->rp), ctx->unit.ref, r, nw, ne);
         ctx->s_device += r.t_device - d0; ctx->s_post += r.t_post - p0;
         ctx->n_walks += nw; ctx->n_emitted += ne;
     });
@@ -320,6 +343,21 @@ static bool sam_id_range(const std::string& path, long long& lo, long long& hi) 
     return ok;
 }
 
+// only the reads a set of units can reference need to be resident: the id window spanned by the first and last records of their SAM files (files
+// are in read order, AG:3602 --reorder); a record outside it is noticed when its SAM is parsed and the whole set is loaded then
+static void units_read_window(const std::string& tmp, const std::vector<int>& units, long long& wlo, long long& whi) {
+    wlo = whi = -1;
+    for (int u : units) { long long a, b; if (sam_id_range(tmp + "/_reads_genome." + std::to_string(u) + ".bowtie", a, b)) { if (a > b) std::swap(a, b); wlo = wlo < 0 ? a : std::min(wlo, a); whi = std::max(whi, b); } }
+    if (wlo < 0) wlo = whi = 0;   // no record anywhere: nothing will be looked up
+}
+int ag_load_reads_for_units(ag_ctx* ctx, const char* reads_fa, const char* tmp_dir, const int* units, int n_units) {
+    return guard(ctx, [&] {
+        long long wlo = -1, whi = -1;
+        if (ctx->reads_window && !ctx->host_parse && n_units > 0) units_read_window(tmp_dir, std::vector<int>(units, units + n_units), wlo, whi);
+        load_reads_impl(ctx, reads_fa, wlo, whi);
+    });
+}
+
 // The whole hot loop for a list of units: [reads] -> per unit (host: genome + contig threads; device: SAM, graph build, walk; host: post passes,
 // files).  `prefetch` host threads prepare units ahead (in list order) while one worker thread per context runs them; with reads_fa != NULL
 // the read set is (re)loaded as part of the job — raw text to ctxs[0]'s GPU, one broadcast to the others — while the preparers already work
@@ -389,13 +427,8 @@ static int run_units_impl(ag_ctx** ctxs, int n_ctx, const char* tmp_dir, const s
     };
     std::vector<std::thread> th;
     auto load_reads = [&]() -> int {
-        // only the reads the job's SAM files can reference need to be resident: the id window spanned by their first and last records (files
-        // are in read order, AG:3602 --reorder); a record outside it is noticed when its SAM is parsed and the whole set is loaded then
         long long wlo = -1, whi = -1;
-        if (ctxs[0]->reads_window && !host_sam && n_units) {
-            for (int u : units) { long long a, b; if (sam_id_range(tmp + "/_reads_genome." + std::to_string(u) + ".bowtie", a, b)) { if (a > b) std::swap(a, b); wlo = wlo < 0 ? a : std::min(wlo, a); whi = std::max(whi, b); } }
-            if (wlo < 0) wlo = whi = 0;   // no record anywhere: nothing will be looked up
-        }
+        if (ctxs[0]->reads_window && !host_sam && n_units) units_read_window(tmp, units, wlo, whi);
         int rc = guard(ctxs[0], [&] { load_reads_impl(ctxs[0], reads_fa, wlo, whi); });
         if (!rc && n_ctx > 1) rc = ag_broadcast_reads(ctxs, n_ctx, nullptr);
         return rc;
@@ -445,7 +478,7 @@ int ag_get_stats(ag_ctx* ctx, ag_stats* o) {
         o->ms_components = t.components; o->ms_chains = t.chains; o->ms_walk = t.walk; o->ms_materialize = t.materialize; o->ms_d2h = t.d2h;
         o->s_parse = ctx->s_parse; o->s_device_section = ctx->s_device; o->s_post = ctx->s_post;
         o->n_aln = ctx->n_aln; o->n_nodes = t.n_nodes; o->n_walks = ctx->n_walks; o->n_emitted = ctx->n_emitted; o->n_keys = t.n_keys; o->n_tiles = t.n_tiles;
-        o->ms_ingest_reads = t.ingest_reads; o->ms_ingest_sam = t.ingest_sam; o->sam_device = t.sam_device; o->sam_host = t.sam_host; o->reads_device = t.reads_device; o->reads_host = t.reads_host; o->regrows = (uint64_t)t.regrows; o->reads_windowed = t.reads_windowed; o->ms_stage = t.stage; o->ms_build_kernel = t.build_kernel;
+        o->ms_ingest_reads = t.ingest_reads; o->ms_ingest_sam = t.ingest_sam; o->sam_device = t.sam_device; o->sam_host = t.sam_host; o->reads_device = t.reads_device; o->reads_host = t.reads_host; o->regrows = (uint64_t)t.regrows; o->reads_windowed = t.reads_windowed; o->ms_stage = t.stage; o->ms_build_kernel = t.build_kernel; o->ms_select = t.select;
         o->kernel_launches = ctx->dev->kernel_launches(); o->h2d_bytes = t.h2d_bytes; o->d2h_bytes = t.d2h_bytes; o->walk_fallback = t.walk_fallback;
     });
 }
@@ -516,7 +549,7 @@ int ag_set_option(ag_ctx* ctx, const char* name, long value) {
         const std::string n = name ? name : "";
         if (n == "host_parse") ctx->host_parse = value != 0;
         else if (n == "reads_window") ctx->reads_window = value != 0;
-        else if (n == "node_cap" || n == "ovf_cap" || n == "eovf_cap" || n == "key_cap" || n == "cand_cap" || n == "hwalk_cap" || n == "rank_rounds" || n == "tma") ctx->dev->set_option(n, value);
+        else if (n == "node_cap" || n == "ovf_cap" || n == "eovf_cap" || n == "key_cap" || n == "cand_cap" || n == "hwalk_cap" || n == "rank_rounds" || n == "tma" || n == "bases_cap" || n == "fused_extend") ctx->dev->set_option(n, value);
         else throw AgHostError{"unknown option: " + n};
     });
 }

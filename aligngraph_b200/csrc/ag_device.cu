@@ -82,6 +82,30 @@ __device__ __forceinline__ u32 block_excl_scan(u32 v, u32* smem /* 32 */, u32& t
     __syncthreads();
     return r;
 }
+// exclusive prefix MAXIMUM over u32 (identity 0), one element per thread of a single CTA with a running carry: out[i] = max(in[0 .. i-1]).
+// The emission filter of extdContigs1 (AG:2176-2189) over the walk records is exactly this (fused extension path); a few 10^5 elements at most.
+__global__ void __launch_bounds__(1024) k_excl_max_scan(const u32* __restrict__ in, u32* __restrict__ out, const u32* __restrict__ n_ptr, u32 cap) {
+    __shared__ u32 sw[32];
+    __shared__ u32 carry;
+    const u32 n = min(*n_ptr, cap), lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (u32 base = 0; base < n; base += 1024) {
+        const u32 i = base + threadIdx.x;
+        const u32 v = i < n ? in[i] : 0u;
+        u32 x = v;   // inclusive warp max
+        for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= (u32)o) x = max(x, y); }
+        if (lane == 31) sw[warp] = x;
+        __syncthreads();
+        u32 pre = carry;   // maximum of everything before this warp
+        for (u32 w = 0; w < warp; w++) pre = max(pre, sw[w]);
+        const u32 up = __shfl_up_sync(0xFFFFFFFFu, x, 1);
+        if (i < n) out[i] = lane ? max(pre, up) : pre;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = max(pre, x);
+        __syncthreads();
+    }
+}
 
 __global__ void k_scan_sums(const u32* __restrict__ in, u32* __restrict__ sums, size_t n) {
     __shared__ u32 sm[33];
@@ -177,10 +201,10 @@ namespace {
 // device view of one unit
 // ---------------------------------------------------------------------------------------------------------------------------
 // error word of a step (bits, set with atomicOr; read once at the step's single synchronisation point)
-enum : int { E_OVF = 1, E_BAD_ALN = 2, E_NODE_CAP = 4, E_EDGE_OVF = 8, E_WALK_CAP = 16, E_MAT_CAP = 32, E_CM = 64, E_KEY_CAP = 128, E_CAND_CAP = 256, E_HWALK_CAP = 512, E_RANK_MORE = 1024 };
+enum : int { E_OVF = 1, E_BAD_ALN = 2, E_NODE_CAP = 4, E_EDGE_OVF = 8, E_WALK_CAP = 16, E_MAT_CAP = 32, E_CM = 64, E_KEY_CAP = 128, E_CAND_CAP = 256, E_HWALK_CAP = 512, E_RANK_MORE = 1024, E_BASES_CAP = 2048 };
 // fixed launch geometry of the loops over nodes / candidates whose trip count only the device knows
 constexpr unsigned GS_BLOCKS = 148 * 8, GS_T = 256;
-constexpr int E_FATAL = E_OVF | E_NODE_CAP | E_EDGE_OVF | E_CM | E_KEY_CAP | E_CAND_CAP | E_RANK_MORE;   // the step is repeated with larger capacities: later kernels skip their work
+constexpr int E_FATAL = E_OVF | E_NODE_CAP | E_EDGE_OVF | E_CM | E_KEY_CAP | E_CAND_CAP | E_RANK_MORE | E_HWALK_CAP | E_BASES_CAP;   // the step is repeated with larger capacities: later kernels skip their work
 #define AG_BAIL(d) do { if (*(volatile int*)(d).err & E_FATAL) return; } while (0)
 #define AG_FOR_N(v, n) for (u32 v = blockIdx.x * blockDim.x + threadIdx.x, n_ = (n), s_ = gridDim.x * blockDim.x; v < n_; v += s_)
 
@@ -208,6 +232,7 @@ struct DevView {
     const u32* nn_ptr;                     // number of nodes (device) = pool_count
     const u32* ncand_ptr; u32 cand_cap;    // number of walk start candidates (device), capacity of the per-candidate arrays
     ag_walk* walks_host; u32 hwalk_cap;    // page-locked host buffer the compacted walk records are written to
+    u32 bases_cap;                         // capacity of the materialised base buffer (fused extension path)
     u32 rw;  // words per staged read (stride2 + stridem) when the tile sweeps keep the chunk's reads in shared memory, else 0
 };
 
@@ -1037,11 +1062,61 @@ __global__ void k_walk_to_host(DevView d, const u32* __restrict__ rank) {
     const uint2* __restrict__ src = reinterpret_cast<const uint2*>(d.walks_sorted); uint2* dst = reinterpret_cast<uint2*>(d.walks_host);
     AG_FOR_N(i, nw * (u32)(sizeof(ag_walk) / 8)) dst[i] = src[i];
 }
+// ---- fused extension path: emission filter, offsets and materialisation inputs on the device (no host round trip between walk and bases) ----
+// Walk records arrive compacted in scan order, i.e. by non-decreasing start position, so `contain(previous emitted, this)` (AG:2176, AG:1897-1902)
+// reduces to "this walk's end does not pass the furthest end seen so far": emitted[i] = (i == 0) || E[i] > max(E[0 .. i-1]), E = the end offset
+// with the tail adjustment of AG:2164-2173 in the reference's own unsigned arithmetic.
+__global__ void k_sel_prepare(DevView d, const u32* __restrict__ walk_rank, u32* __restrict__ E) {
+    AG_BAIL(d);
+    AG_FOR_N(i, min(walk_rank[d.cand_cap], d.hwalk_cap)) {
+        const ag_walk r = d.walks_sorted[i];
+        u32 eoff = r.eoff;
+        if (((r.flags >> 1) & 3) != 1) eoff = eoff + (r.tail_soff_len >> 16) - 1;
+        E[i] = eoff;
+    }
+}
+__global__ void k_sel_flag(DevView d, const u32* __restrict__ walk_rank, const u32* __restrict__ E, const u32* __restrict__ M, u32* __restrict__ flag, u32* __restrict__ len, u32* trigger) {
+    const bool dead = (*(volatile int*)d.err & E_FATAL) != 0;
+    const u32 nw = dead ? 0u : min(walk_rank[d.cand_cap], d.hwalk_cap);
+    AG_FOR_N(i, d.hwalk_cap) {   // covers the capacity: zeros behind the walk count for the scans
+        u32 f = 0, l = 0;
+        if (i < nw && (i == 0 || E[i] > M[i])) {
+            const ag_walk r = d.walks_sorted[i];
+            f = 1; l = r.len + ag_walk_tail_len(r);
+            if (E[i] - r.soff > 100000u) atomicOr(trigger, 1u);   // a contig of more than 100 kbp switches the reference's 1000-position skip on (AG:2194-2202): exact sequential replay
+        }
+        flag[i] = f; len[i] = l;
+    }
+}
+// compacted materialisation inputs of the emitted walks + their records for the host
+__global__ void k_sel_fill(DevView d, const u32* __restrict__ walk_rank, const u32* __restrict__ flag, const u32* __restrict__ srank, const u32* __restrict__ soff,
+                           u32* __restrict__ sel_start, u64* __restrict__ sel_off, u32* __restrict__ sel_tails, ag_walk* __restrict__ sel_walks, u32* __restrict__ sel_off32) {
+    AG_BAIL(d);
+    const u32 nw = min(walk_rank[d.cand_cap], d.hwalk_cap);
+    if (soff[d.hwalk_cap] > d.bases_cap) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(d.err, E_BASES_CAP); return; }
+    AG_FOR_N(i, nw) {
+        if (!flag[i]) continue;
+        const ag_walk r = d.walks_sorted[i];
+        const u32 j = srank[i], tl = ag_walk_tail_len(r);
+        sel_start[j] = r.start_node; sel_off[j] = soff[i]; sel_off32[j] = soff[i];
+        sel_tails[3 * j] = r.tail_sread; sel_tails[3 * j + 1] = tl ? r.tail_soff_len : 0u; sel_tails[3 * j + 2] = r.len;
+        sel_walks[j] = r;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) sel_off32[srank[d.hwalk_cap]] = soff[d.hwalk_cap];   // closing offset
+}
+// device buffer -> page-locked host buffer, 16 bytes per lane (count in 16-byte units from the device)
+__global__ void k_to_host16(const uint4* __restrict__ src, uint4* __restrict__ dst, const u32* __restrict__ n_items, u32 item_bytes, u32 extra_items, const int* err) {
+    if (*(volatile const int*)err & E_FATAL) return;
+    const u64 n16 = ((u64)(*n_items + extra_items) * item_bytes + 15) / 16;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x, s = (u64)gridDim.x * blockDim.x; i < n16; i += s) dst[i] = src[i];
+}
+
 // everything the host wants to know about the step, gathered into one block for ONE device->host copy
-__global__ void k_status(DevView d, const u32* __restrict__ counters, const u32* __restrict__ walk_rank, u32* __restrict__ out) {
+__global__ void k_status(DevView d, const u32* __restrict__ counters, const u32* __restrict__ walk_rank, const u32* __restrict__ sel, u32* __restrict__ out) {
     if (blockIdx.x || threadIdx.x) return;
     out[0] = (u32)(*d.err | *d.err_load); out[1] = counters[0]; out[2] = counters[1]; out[3] = counters[2]; out[4] = *d.nk_ptr;
     out[5] = d.ncand_ptr ? *d.ncand_ptr : 0u; out[6] = walk_rank ? walk_rank[d.cand_cap] : 0u;
+    out[7] = sel ? sel[0] : 0u; out[8] = sel ? sel[1] : 0u; out[9] = sel ? sel[2] : 0u;   // fused extension: emitted walks, their bases, >100 kbp trigger
 }
 
 // exact sequential replay including the 1000-position skip (AG:2194-2202); used only when a >100 kbp contig was emitted
@@ -1087,9 +1162,9 @@ __global__ void k_materialize_seq(DevView d, const u32* __restrict__ starts, con
 struct MatItem { u32 a, n; u64 off; };  // detour item: a = first chain-major index, n = bases
 // A chain belongs to at most one walk (it is marked as a whole), so "where does this chain's run of bases END in the output" can be kept
 // per chain tail; every node then finds its own byte: end - (nodes from here to the tail).  One thread per node, no pointer chasing.
-__global__ void k_mat_items(DevView d, const u32* __restrict__ starts, const u64* __restrict__ offs, u32 n, u32* tail_end, MatItem* detours, u32* counts, u32 cap) {
-    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+__global__ void k_mat_items(DevView d, const u32* __restrict__ starts, const u64* __restrict__ offs, u32 n, const u32* __restrict__ n_ptr, u32* tail_end, MatItem* detours, u32* counts, u32 cap) {
+    if (n_ptr) { AG_BAIL(d); n = *n_ptr; }
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     u64 off = offs[i];
     u32 v = starts[i];
     while (v != AG_NONE) {
@@ -1105,13 +1180,15 @@ __global__ void k_mat_items(DevView d, const u32* __restrict__ starts, const u64
         }
         v = d.walk_next[t];
     }
+    }
 }
-__global__ void k_mat_nodes(DevView d, u32 n_nodes, const u32* __restrict__ tail_end, unsigned char* out) {
-    u32 v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= n_nodes) return;
-    const ag_chain c = d.chain[v];
-    const u32 e = tail_end[c.tail];
-    if (e != AG_NONE) out[e - c.len] = (unsigned char)(d.node_w[v].misc & 0xFF);
+__global__ void k_mat_nodes(DevView d, u32 n_nodes, const u32* __restrict__ n_ptr, const u32* __restrict__ tail_end, unsigned char* out) {
+    if (n_ptr) { AG_BAIL(d); n_nodes = *n_ptr; }
+    for (u32 v = blockIdx.x * blockDim.x + threadIdx.x; v < n_nodes; v += gridDim.x * blockDim.x) {
+        const ag_chain c = d.chain[v];
+        const u32 e = tail_end[c.tail];
+        if (e != AG_NONE) out[e - c.len] = (unsigned char)(d.node_w[v].misc & 0xFF);
+    }
 }
 __global__ void k_mat_detours(DevView d, const MatItem* __restrict__ items, const u32* counts, unsigned char* out) {
     // one CTA per detour item (a run of contig bases, typically thousands): byte copies, coalesced across the CTA
@@ -1123,15 +1200,16 @@ __global__ void k_mat_detours(DevView d, const MatItem* __restrict__ items, cons
 
 // s[1..] of the last node of every selected walk that ended in the k-mer graph (AG:2164-2168); characters outside ACGT come out as 'N'
 // here and are restored on the host from the reads' exception list
-__global__ void k_mat_tails(DevView d, const u32* __restrict__ tails /* per walk: sread, soff_len, loop length */, const u64* __restrict__ offs, u32 n, unsigned char* out) {
-    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const u32 sread = tails[3 * i], sl = tails[3 * i + 1], len = tails[3 * i + 2];
-    const u32 slen = sl >> 16, soff = sl & 0xFFFFu;
-    if (slen < 2) return;
-    const u32 rlen = d.reads.len[sread >> 2];
-    unsigned char* o = out + offs[i] + len;
-    for (u32 j = 1; j < slen; j++) { int c = d.reads.code(sread, rlen, soff + j); *o++ = (unsigned char)"ACGTN"[c]; }
+__global__ void k_mat_tails(DevView d, const u32* __restrict__ tails /* per walk: sread, soff_len, loop length */, const u64* __restrict__ offs, u32 n, const u32* __restrict__ n_ptr, unsigned char* out) {
+    if (n_ptr) { AG_BAIL(d); n = *n_ptr; }
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const u32 sread = tails[3 * i], sl = tails[3 * i + 1], len = tails[3 * i + 2];
+        const u32 slen = sl >> 16, soff = sl & 0xFFFFu;
+        if (slen < 2) continue;
+        const u32 rlen = d.reads.len[sread >> 2];
+        unsigned char* o = out + offs[i] + len;
+        for (u32 j = 1; j < slen; j++) { int c = d.reads.code(sread, rlen, soff + j); *o++ = (unsigned char)"ACGTN"[c]; }
+    }
 }
 
 __global__ void k_reset_marks(DevView d, u32 n_nodes) {
@@ -1217,12 +1295,15 @@ struct AgDevice::Impl {
     Scanner scanner;
     u32 n_tiles = 0, n_keys = 0, n_nodes = 0;
     u32 node_cap = 0, ovf_cap = 0, eovf_cap = 0, eovf_cap_init = 0, walk_cap = 0;
-    u32 key_cap = 0, cand_cap = 0, hwalk_cap = 0, n_walks = 0; int rank_rounds = 1;   // one global list-ranking round (chains that leave their 1024-node block once); more on request (E_RANK_MORE)
+    u32 key_cap = 0, cand_cap = 0, hwalk_cap = 0, n_walks = 0; int rank_rounds = 2;   // global list-ranking rounds queued per step (chains that leave their 1024-node block); more on request (E_RANK_MORE)
     u32 unit_n_ref = 0; u64 unit_n_aln = 0;   // the unit the capacities above were last derived for
     PinnedBuf h_wrec;                        // compacted walk records, written by k_walk_compact straight into host memory
     DBuf<u32> status, walk_rank; DBuf<int> err_load; SectionTimes sections;
     bool key_cap_hooked = false; u32 node_cap_hook = 0, ovf_cap_hook = 0;   // test hooks (set_option): initial capacities instead of the size-derived ones
-    bool build_queued = false, walk_queued = false;   // queued on the stream, not yet checked by finish()
+    bool build_queued = false, walk_queued = false, select_queued = false;   // queued on the stream, not yet checked by finish()
+    // fused extension path: emission filter + materialisation queued behind the walk
+    u32 bases_cap = 0, n_sel = 0, sel_bases = 0; bool sel_trigger = false;
+    DBuf<u32> sel_E, sel_M, sel_flag, sel_len, sel_rank, sel_soff, sel_info, sel_off32; DBuf<ag_walk> sel_walks; PinnedBuf h_selw, h_selo;
     DevView view{};
     // counters layout: [0] n_nodes (pool_count), [1] ovf_count, [2] eovf_count, [3] walk_count, [4,5] materialise items
 };
@@ -1253,6 +1334,7 @@ AgDevice::~AgDevice() {
     m.cm.release(); m.cthreads.release(); m.aln.release(); m.ext.release(); m.alnp.release(); m.fast.release(); m.pool_c.release(); m.pool_w.release(); m.ovf_node.release(); m.err.release();
     m.node_c.release(); m.node_w.release(); m.walks.release(); m.walks2.release(); m.cm1.release(); m.mat_detours.release(); m.tail_end.release(); m.pos_term.release(); m.cand_rank.release(); m.cand_node.release(); m.cand_label.release(); m.fprev.release(); m.msuf.release(); m.mnode.release(); m.indeg.release(); m.fnext.release(); m.chain_a.release(); m.chain_b.release(); m.hrec.release(); m.changed.release(); m.sel_off.release();
     m.contig_blob.release(); m.cdesc.release(); m.cruns.release(); m.raw.release(); m.exc_chr.release(); m.nl.release(); m.nl_blk.release(); m.rlen.release(); m.s_keep.release(); m.s_next.release(); m.s_aoff.release(); m.s_eoff.release(); m.s_lost.release(); m.ing.release(); m.exc_key.release(); m.srec.release(); m.stager.release();
+    m.sel_E.release(); m.sel_M.release(); m.sel_flag.release(); m.sel_len.release(); m.sel_rank.release(); m.sel_soff.release(); m.sel_info.release(); m.sel_off32.release(); m.sel_walks.release(); m.h_selw.release(); m.h_selo.release();
     m.h_wrec.release(); m.walk_rank.release(); m.status.release(); m.err_load.release(); m.sections.release();
     m.h_walks.release(); m.h_bases.release(); m.h_occ.release(); m.h_sel.release(); m.h_s.release();
     if (ev_mat0_) { cudaEventDestroy((cudaEvent_t)ev_mat0_); cudaEventDestroy((cudaEvent_t)ev_mat1_); }
@@ -1273,6 +1355,8 @@ void AgDevice::set_option(const std::string& name, long value) {
     else if (name == "cand_cap") m.cand_cap = (u32)std::max<long>(value, 1);
     else if (name == "hwalk_cap") m.hwalk_cap = (u32)std::max<long>(value, 1);
     else if (name == "tma") tma_off_ = value == 0;
+    else if (name == "bases_cap") m.bases_cap = (u32)std::max<long>(value, 1);
+    else if (name == "fused_extend") fused_off_ = value == 0;
     else if (name == "rank_rounds") m.rank_rounds = (int)std::max<long>(value, 1);
     else if (name == "eovf_cap") m.eovf_cap_init = (u32)std::max<long>(value, 1);
     else if (name == "section_timing") section_timing_ = value != 0;
@@ -2050,9 +2134,9 @@ void AgDevice::enqueue_walk() {
 bool AgDevice::finish() {
     Impl& m = *m_; cudaStream_t st = m.st; DevView& d = m.view;
     if (!m.build_queued && !m.walk_queued) return false;
-    k_status<<<1, 32, 0, st>>>(d, m.counters.p, m.walk_queued ? m.walk_rank.p : nullptr, m.status.p); launches_++;
+    k_status<<<1, 32, 0, st>>>(d, m.counters.p, m.walk_queued ? m.walk_rank.p : nullptr, m.select_queued ? m.sel_info.p : nullptr, m.status.p); launches_++;
     volatile u32* hs = (volatile u32*)m.h_s.p;
-    CK(cudaMemcpyAsync((void*)hs, m.status.p, 8 * sizeof(u32), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync((void*)hs, m.status.p, 12 * sizeof(u32), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     m.sections.collect();
     const int err = (int)hs[0];
@@ -2066,15 +2150,111 @@ bool AgDevice::finish() {
     if (err & E_EDGE_OVF) { if (m.eovf_cap >= (1u << 30)) throw AgError{"edge overflow pool exhausted"}; m.eovf_cap *= 4; redo = true; }
     if (err & E_CAND_CAP) { m.cand_cap = ncand + ncand / 8 + 1024; redo = true; }
     if (err & E_HWALK_CAP) { m.hwalk_cap = nw + nw / 8 + 1024; redo = true; }
+    if (err & E_BASES_CAP) { m.bases_cap = hs[8] + hs[8] / 8 + (1u << 20); redo = true; }
     if (err & E_RANK_MORE) { if (m.rank_rounds >= 24) throw AgError{"internal: chain ranking did not converge"}; m.rank_rounds += 2; redo = true; }
     if (err & (E_WALK_CAP | E_MAT_CAP)) throw AgError{"walk record buffer exhausted"};
-    if (redo) { t_.regrows++; m.build_queued = m.walk_queued = false; return true; }
+    if (redo) { t_.regrows++; m.build_queued = m.walk_queued = m.select_queued = false; occ_pending_ = false; return true; }
     m.n_nodes = nn; m.n_keys = nk; t_.n_nodes = nn; t_.n_keys = nk; t_.n_edges_ovf = hs[3];
     if (m.walk_queued) { m.n_cand = ncand; m.n_walks = nw; t_.n_components = ncand; }
-    m.build_queued = m.walk_queued = false;
+    if (m.select_queued) { m.n_sel = hs[7]; m.sel_bases = hs[8]; m.sel_trigger = hs[9] != 0; }
+    m.build_queued = m.walk_queued = m.select_queued = false;
     return false;
 }
 void AgDevice::build_sync() { while (finish()) enqueue_build(); }
+
+// emission filter, output offsets, materialisation and the copies to page-locked host memory — queued behind the walk, no host round trip
+void AgDevice::enqueue_select() {
+    Impl& m = *m_; cudaStream_t st = m.st; DevView& d = m.view;
+    const size_t wc = m.hwalk_cap;
+    if (!m.bases_cap) m.bases_cap = (u32)std::min<u64>(0xFFFFFF00ull, (u64)m.n_ref + m.n_ref / 4 + (1u << 20));
+    d.bases_cap = m.bases_cap;
+    m.sel_E.ensure(wc + 2); m.sel_M.ensure(wc + 2); m.sel_flag.ensure(wc + 2); m.sel_len.ensure(wc + 2); m.sel_rank.ensure(wc + 2); m.sel_soff.ensure(wc + 2); m.sel_info.ensure(8);
+    m.sel_start.ensure(wc + 1); m.sel_off.ensure(wc + 1); m.sel_tails.ensure(3 * wc + 1); m.sel_walks.ensure(wc + 1); m.sel_off32.ensure(wc + 2);
+    m.out_bases.ensure((size_t)m.bases_cap + 16);
+    m.h_selw.ensure(wc * sizeof(ag_walk) + 64); m.h_selo.ensure((wc + 2) * sizeof(u32) + 64); m.h_bases.ensure((size_t)m.bases_cap + 16);
+    {
+        Section sec(m.sections, st, &t_.select);
+        CK(cudaMemsetAsync(m.sel_info.p, 0, 8 * sizeof(u32), st));
+        k_sel_prepare<<<GS_BLOCKS / 4, GS_T, 0, st>>>(d, m.walk_rank.p, m.sel_E.p); launches_++;
+        k_excl_max_scan<<<1, 1024, 0, st>>>(m.sel_E.p, m.sel_M.p, m.walk_rank.p + m.cand_cap, m.hwalk_cap); launches_++;
+        k_sel_flag<<<GS_BLOCKS / 4, GS_T, 0, st>>>(d, m.walk_rank.p, m.sel_E.p, m.sel_M.p, m.sel_flag.p, m.sel_len.p, m.sel_info.p + 2); launches_++;
+        m.scanner.run(m.sel_flag.p, m.sel_rank.p, wc, st);    // sel_rank[wc] = emitted walks
+        m.scanner.run(m.sel_len.p, m.sel_soff.p, wc, st);     // sel_soff[wc] = their bases
+        CK(cudaMemcpyAsync(m.sel_info.p + 0, m.sel_rank.p + wc, sizeof(u32), cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(m.sel_info.p + 1, m.sel_soff.p + wc, sizeof(u32), cudaMemcpyDeviceToDevice, st));
+        k_sel_fill<<<GS_BLOCKS / 4, GS_T, 0, st>>>(d, m.walk_rank.p, m.sel_flag.p, m.sel_rank.p, m.sel_soff.p, m.sel_start.p, m.sel_off.p, m.sel_tails.p, m.sel_walks.p, m.sel_off32.p); launches_++;
+    }
+    {
+        Section sec(m.sections, st, &t_.materialize);
+        const u32* n_sel = m.sel_info.p + 0;
+        const u32 cap = m.cand_cap + 1;
+        m.mat_detours.ensure(cap); m.tail_end.ensure((size_t)m.node_cap + 1);
+        CK(cudaMemsetAsync(m.counters.p + 4, 0, 2 * sizeof(u32), st));
+        CK(cudaMemsetAsync(m.tail_end.p, 0xFF, (size_t)m.node_cap * sizeof(u32), st));
+        k_mat_items<<<GS_BLOCKS / 8, 128, 0, st>>>(d, m.sel_start.p, m.sel_off.p, 0, n_sel, m.tail_end.p, m.mat_detours.p, m.counters.p + 4, cap); launches_++;
+        k_mat_nodes<<<GS_BLOCKS, GS_T, 0, st>>>(d, 0, d.nn_ptr, m.tail_end.p, m.out_bases.p); launches_++;
+        k_mat_detours<<<148u * 8u, 256, 0, st>>>(d, m.mat_detours.p, m.counters.p + 4, m.out_bases.p); launches_++;
+        k_mat_tails<<<GS_BLOCKS / 8, 128, 0, st>>>(d, m.sel_tails.p, m.sel_off.p, 0, n_sel, m.out_bases.p); launches_++;
+        // results to page-locked host memory: emitted walk records, their offsets, the bases (counts known to the device only)
+        k_to_host16<<<GS_BLOCKS / 4, GS_T, 0, st>>>((const uint4*)m.sel_walks.p, (uint4*)m.h_selw.p, n_sel, (u32)sizeof(ag_walk), 0, m.err.p); launches_++;
+        k_to_host16<<<GS_BLOCKS / 4, GS_T, 0, st>>>((const uint4*)m.sel_off32.p, (uint4*)m.h_selo.p, n_sel, 4u, 1, m.err.p); launches_++;
+        k_to_host16<<<GS_BLOCKS, GS_T, 0, st>>>((const uint4*)m.out_bases.p, (uint4*)m.h_bases.p, m.sel_info.p + 1, 1u, 0, m.err.p); launches_++;
+    }
+    m.select_queued = true;
+}
+
+// extendContigs1 up to the emitted contigs as ONE queued step: walk, emission filter, materialisation, copies — and one synchronisation.
+// `emitted` = the walk records that pass the emission filter, in scan order; contig i = bases[offs[i], offs[i + 1]).
+void AgDevice::extend_emitted(std::vector<ag_walk>& emitted, char*& bases, std::vector<u64>& offs, u64& n_walks) {
+    CK(cudaSetDevice(dev_));
+    Impl& m = *m_;
+    emitted.clear(); offs.assign(1, 0); bases = nullptr; n_walks = 0;
+    if (!m.build_queued && !m.n_nodes) { occupancy_begin(); return; }
+    for (;;) {
+        enqueue_walk();
+        enqueue_select();
+        occupancy_begin();
+        if (!finish()) break;
+        enqueue_build();
+    }
+    n_walks = m.n_walks; t_.n_walks = m.n_walks;
+    if (m.sel_trigger) {   // a > 100 kbp contig: the reference's scan skips positions from here on (AG:2194-2202) — exact sequential replay, host emission filter
+        std::vector<ag_walk> walks;
+        walk_sequential();
+        cudaStream_t st = m.st;
+        volatile u32* hs = (volatile u32*)m.h_s.p;
+        CK(cudaMemcpyAsync((void*)(hs + 0), m.counters.p + 3, sizeof(u32), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync((void*)(hs + 1), m.err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const u32 nw = hs[0];
+        if (hs[1]) throw AgError{"walk record buffer exhausted"};
+        walks.resize(nw);
+        if (nw) {
+            m.h_walks.ensure((size_t)nw * sizeof(ag_walk));
+            CK(cudaMemcpyAsync(m.h_walks.p, m.walks.p, (size_t)nw * sizeof(ag_walk), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            memcpy(walks.data(), m.h_walks.p, (size_t)nw * sizeof(ag_walk));
+        }
+        n_walks = nw; t_.n_walks = nw;
+        std::vector<u32> sel;
+        ag_select_emitted(walks, sel);
+        materialize_begin(walks, sel, bases, offs);
+        materialize_wait();
+        emitted.resize(sel.size());
+        for (size_t i = 0; i < sel.size(); i++) emitted[i] = walks[sel[i]];
+        t_.d2h_bytes += (size_t)nw * sizeof(ag_walk);
+        return;
+    }
+    const u32 ns = m.n_sel;
+    emitted.resize(ns); offs.assign((size_t)ns + 1, 0);
+    if (ns) {
+        memcpy(emitted.data(), m.h_selw.p, (size_t)ns * sizeof(ag_walk));
+        const u32* o32 = (const u32*)m.h_selo.p;
+        for (u32 i = 0; i <= ns; i++) offs[i] = o32[i];
+    }
+    bases = (char*)m.h_bases.p;
+    t_.d2h_bytes += (size_t)ns * sizeof(ag_walk) + m.sel_bases;
+}
 
 void AgDevice::walk_sequential() {
     Impl& m = *m_; cudaStream_t st = m.st; DevView& d = m.view; u32 nn = m.n_nodes;
@@ -2164,13 +2344,13 @@ void AgDevice::materialize_begin(const std::vector<ag_walk>& walks, const std::v
         m.mat_detours.ensure(cap); m.tail_end.ensure((size_t)nn + 1);
         CK(cudaMemsetAsync(m.counters.p + 4, 0, 2 * sizeof(u32), st));
         CK(cudaMemsetAsync(m.tail_end.p, 0xFF, (size_t)nn * sizeof(u32), st));
-        k_mat_items<<<((u32)sel.size() + 127) / 128, 128, 0, st>>>(d, m.sel_start.p, m.sel_off.p, (u32)sel.size(), m.tail_end.p, m.mat_detours.p, m.counters.p + 4, cap); launches_++;
-        k_mat_nodes<<<(nn + 255) / 256, 256, 0, st>>>(d, nn, m.tail_end.p, m.out_bases.p); launches_++;
+        k_mat_items<<<((u32)sel.size() + 127) / 128, 128, 0, st>>>(d, m.sel_start.p, m.sel_off.p, (u32)sel.size(), nullptr, m.tail_end.p, m.mat_detours.p, m.counters.p + 4, cap); launches_++;
+        k_mat_nodes<<<(nn + 255) / 256, 256, 0, st>>>(d, nn, nullptr, m.tail_end.p, m.out_bases.p); launches_++;
         k_mat_detours<<<std::min<u32>(cap, 148u * 8u), 256, 0, st>>>(d, m.mat_detours.p, m.counters.p + 4, m.out_bases.p); launches_++;
     } else {
         k_materialize_seq<<<((u32)sel.size() + 127) / 128, 128, 0, st>>>(d, m.sel_start.p, m.sel_off.p, (u32)sel.size(), m.out_bases.p); launches_++;
     }
-    k_mat_tails<<<((u32)sel.size() + 127) / 128, 128, 0, st>>>(d, m.sel_tails.p, m.sel_off.p, (u32)sel.size(), m.out_bases.p); launches_++;
+    k_mat_tails<<<((u32)sel.size() + 127) / 128, 128, 0, st>>>(d, m.sel_tails.p, m.sel_off.p, (u32)sel.size(), nullptr, m.out_bases.p); launches_++;
     m.h_bases.ensure(offs.back());
     CK(cudaMemcpyAsync(m.h_bases.p, m.out_bases.p, offs.back(), cudaMemcpyDeviceToHost, st));
     volatile u32* hs = (volatile u32*)m.h_s.p;

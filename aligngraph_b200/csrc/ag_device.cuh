@@ -32,6 +32,7 @@ struct AgTimings {  // milliseconds, CUDA events on the context's stream
     u64 n_nodes = 0, n_edges_ovf = 0, n_walks = 0, n_keys = 0, n_tiles = 0, n_components = 0;
     u64 h2d_bytes = 0, d2h_bytes = 0;
     int walk_fallback = 0, regrows = 0;   // regrows: sweeps repeated with a larger node table / overflow pool
+    float select = 0;                        // emission filter + materialisation inputs on the device (fused extension path)
     float stage = 0, build_kernel = 0;        // inside `nodes`: the staging gather (k_stage) and the node sweep kernel itself
     float ingest_reads = 0, ingest_sam = 0;   // ms: staging + kernels of the text ingestion (CUDA events)
     u64 sam_device = 0, sam_host = 0, reads_device = 0, reads_host = 0, reads_windowed = 0;   // files parsed on the device / by the host parser
@@ -86,6 +87,12 @@ public:
     void build_sync();
     // coverage filter + walk simulation; fills `walks` (unsorted on return from the device, sorted here by start node)
     void extend(std::vector<ag_walk>& walks);
+    // extendContigs1 (AG:1954-2204) up to the emitted contigs as ONE queued step behind the build: walk, emission filter (a prefix maximum over
+    // the walk records), materialisation and the copies to page-locked host memory; a single synchronisation.  `emitted` = the walk records that
+    // pass the emission filter, in scan order; contig i = bases[offs[i], offs[i + 1]) (valid until the next call); the occupancy bitmap has been
+    // queued as well (occupancy_wait)
+    void extend_emitted(std::vector<ag_walk>& emitted, char*& bases, std::vector<u64>& offs, u64& n_walks);
+    bool fused_extend() const { return !fused_off_; }
     // materialise the selected walks' base strings (loop bases + tail); contig i occupies bases[offs[i], offs[i + 1]).  `bases` points into
     // a page-locked buffer owned by the device object (valid until the next call); the post passes patch and read it in place
     void materialize(const std::vector<ag_walk>& walks, const std::vector<u32>& sel, char*& bases, std::vector<u64>& offs) { materialize_begin(walks, sel, bases, offs); materialize_wait(); }
@@ -121,10 +128,11 @@ private:
     bool reads_pending_ = false, mat_pending_ = false, occ_pending_ = false;
     void *ev_mat0_ = nullptr, *ev_mat1_ = nullptr; size_t mat_bytes_ = 0;
     std::vector<void*> pinned_;
-    bool tma_off_ = false, attr_tma_done_ = false;
+    bool tma_off_ = false, attr_tma_done_ = false, fused_off_ = false;
     bool chains_valid_ = false, attr_done_ = false, keep_counts_ = false, section_timing_ = false;
     void enqueue_build();
     void enqueue_walk();
+    void enqueue_select();
     bool finish();
     void walk_sequential();
 };

@@ -287,31 +287,36 @@ __global__ void k_verify_placements(const char* __restrict__ db, const u64* __re
 // slot is reused once its copy has finished.  The copy engine therefore always has several chunks queued while the next ones are read.
 // ---------------------------------------------------------------------------------------------------------------------------
 struct FileStager {
-    static constexpr size_t CHUNK = (size_t)4 << 20;
     static constexpr int MAXT = 32;
-    PinnedBuf ring; cudaEvent_t ev[2 * MAXT]; bool made = false, used[2 * MAXT] = {};
-    void release() { ring.release(); if (made) for (int i = 0; i < 2 * MAXT; i++) cudaEventDestroy(ev[i]); made = false; }
+    size_t CHUNK = (size_t)4 << 20; int SLOTS = 2;   // per thread: SLOTS pinned slots of CHUNK bytes (AG_STAGE_CHUNK_MB / AG_STAGE_SLOTS override, for tuning)
+    PinnedBuf ring; std::vector<cudaEvent_t> ev; std::vector<char> used;
+    FileStager() {
+        if (const char* e = getenv("AG_STAGE_CHUNK_MB")) { const long v = atol(e); if (v >= 1 && v <= 64) CHUNK = (size_t)v << 20; }
+        if (const char* e = getenv("AG_STAGE_SLOTS")) { const int v = atoi(e); if (v >= 2 && v <= 16) SLOTS = v; }
+    }
+    void release() { ring.release(); for (cudaEvent_t e : ev) cudaEventDestroy(e); ev.clear(); used.clear(); }
     // copies file bytes [off, off + len) to dst (device), asynchronously on `st` (every copy has been QUEUED when this returns)
     void run(int fd, size_t off, size_t len, char* dst, cudaStream_t st, int device) {
         if (!len) return;
-        if (!made) { for (int i = 0; i < 2 * MAXT; i++) CK(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming)); made = true; }
+        if (ev.empty()) { ev.resize((size_t)SLOTS * MAXT); used.assign((size_t)SLOTS * MAXT, 0); for (auto& e : ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); }
         const size_t n_chunks = (len + CHUNK - 1) / CHUNK;
-        const int T = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>((size_t)ag_team_size(), MAXT), n_chunks));
-        ring.ensure((size_t)2 * MAXT * CHUNK);
+        int tmax = MAXT; if (const char* e = getenv("AG_STAGE_THREADS")) { const int v = atoi(e); if (v >= 1 && v <= MAXT) tmax = v; }
+        const int T = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>((size_t)ag_team_size(), (size_t)tmax), n_chunks));
+        ring.ensure((size_t)SLOTS * MAXT * CHUNK);
         std::atomic<int> failed(0);
         static const bool no_read = getenv("AG_STAGE_NOREAD") != nullptr, no_copy = getenv("AG_STAGE_NOCOPY") != nullptr;   // diagnosis only: time the two halves apart
         ag_parallel_chunks(T, [&](int t) {
             cudaSetDevice(device);
             size_t j = 0;
             for (size_t k = (size_t)t; k < n_chunks; k += (size_t)T, j++) {
-                const int slot = 2 * t + (int)(j & 1);
-                if (used[slot]) cudaEventSynchronize(ev[slot]);   // the copy that last read this slot (this call's or an earlier one's) has finished
+                const int slot = SLOTS * t + (int)(j % (size_t)SLOTS);
+                if (used[(size_t)slot]) cudaEventSynchronize(ev[(size_t)slot]);   // the copy that last read this slot (this call's or an earlier one's) has finished
                 char* h = ring.p + (size_t)slot * CHUNK;
                 const size_t o = k * CHUNK, n = std::min(CHUNK, len - o);
                 size_t a = 0;
                 while (!no_read && a < n) { const ssize_t got = pread(fd, h + a, n - a, (off_t)(off + o + a)); if (got <= 0) { failed = 1; return; } a += (size_t)got; }
                 if (!no_copy && cudaMemcpyAsync(dst + o, h, n, cudaMemcpyHostToDevice, st) != cudaSuccess) { failed = 2; return; }
-                cudaEventRecord(ev[slot], st); used[slot] = true;
+                cudaEventRecord(ev[(size_t)slot], st); used[(size_t)slot] = 1;
             }
         });
         if (failed) throw AgError{failed == 1 ? "CANNOT OPEN FILE!" : "host->device copy of a staged chunk failed"};

@@ -298,7 +298,7 @@ def b200_arm(args):
 
     # ---- (1) `value`: inputs resident in HBM.  Per unit: text ingested + arrays uploaded once (untimed), then K timed steps of the device
     # pipeline + host post passes ending with the unit's FASTA text in host memory --------------------------------------------------------
-    ctx.load_reads_fasta(reads_fa)
+    ctx.load_reads_for_units(reads_fa, tmp, my_units)   # (only the reads this rank's units reference: the read file is shared by all units)
     W = max(args.warmup, 3); K = args.steps
     ms = 0.0
     stats = None

@@ -67,6 +67,7 @@ typedef struct ag_stats {
     uint64_t regrows; /* sweeps repeated with a larger node table / node overflow pool / edge overflow pool */
     uint64_t reads_windowed; /* read sets ingested for the id window of the job's SAM files only */
     float ms_stage, ms_build_kernel; /* inside ms_nodes: staging gather (k_stage) and the node sweep kernel (k_build_tma / k_build) */
+    float ms_select; /* emission filter + materialisation inputs on the device (fused extension path) */
 } ag_stats;
 
 int ag_create(const ag_params* params, ag_ctx** out);
@@ -86,6 +87,9 @@ int ag_set_reads_device(ag_ctx* ctx, const uint32_t* d_bases2, const uint32_t* d
 int ag_set_read_exceptions(ag_ctx* ctx, const uint64_t* keys, const char* chars, uint64_t n);
 /* parse tmp/_reads.fa (AG:361-404) and upload */
 int ag_load_reads_fasta(ag_ctx* ctx, const char* path);
+/* the same, but only the reads that the given units can reference are made resident: the pair-id window spanned by their SAM files
+ * (tmp/_reads_genome.N.bowtie), found in the read file by bisection (ids are the pair indices, AG:3455-3471); what ag_run_job_files does */
+int ag_load_reads_for_units(ag_ctx* ctx, const char* reads_fa, const char* tmp_dir, const int* units, int n_units);
 /* packed host copy held by the context (after ag_load_reads_fasta) — lets a launcher broadcast it */
 int ag_get_reads(ag_ctx* ctx, const uint32_t** bases2, const uint32_t** nmask, const uint16_t** pair_len, uint64_t* n_pairs, uint32_t* stride2, uint32_t* stridem);
 
@@ -167,7 +171,8 @@ int ag_remove_misassembly_file(ag_ctx* ctx, const char* file, const char* id, in
 /* tuning / test hooks: "reads_window" (0 = ag_run_job_files always makes the whole read set resident), "host_parse" (1 = SAM and reads text parsed by the host parsers instead of the device kernels), "node_cap" / "ovf_cap" /
  * "eovf_cap" / "key_cap" / "cand_cap" / "hwalk_cap" (initial capacities of the node table, the node overflow pool, the edge overflow pool, the
  * tile-key buffers, the start-candidate arrays and the host walk-record buffer; small values force the grow-and-redo path), "rank_rounds"
- * (global list-ranking rounds queued per step), "tma" (0 = node sweep with per-thread staging, k_build, instead of the bulk-async staged k_build_tma) */
+ * (global list-ranking rounds queued per step), "bases_cap" (initial capacity of the materialised-bases buffer), "fused_extend" (0 = emission filter on the host between walk and
+ * materialisation: two synchronisations per step), "tma" (0 = node sweep with per-thread staging, k_build, instead of the bulk-async staged k_build_tma) */
 int ag_set_option(ag_ctx* ctx, const char* name, long value);
 int ag_timer_start(ag_ctx* ctx);
 int ag_timer_stop(ag_ctx* ctx, float* ms);
