@@ -165,9 +165,10 @@ int ag_broadcast_reads(ag_ctx** ctxs, int n_ctx, ag_bcast_info* info) {
         if (!ctxs[0]->have_reads) throw AgHostError{"reads not set"};
         std::vector<AgDevice*> devs;
         for (int i = 0; i < n_ctx; i++) { if (!ctxs[i]) throw AgHostError{"null context"}; devs.push_back(ctxs[i]->dev); }
-        for (int i = 1; i < n_ctx; i++) { ctxs[i]->dev->unpin_all(); ctxs[i]->rp = ctxs[0]->rp; ctxs[i]->have_reads = true; ctxs[i]->reads_dirty = false; }
+        for (int i = 1; i < n_ctx; i++) { ctxs[i]->dev->unpin_all(); ctxs[i]->rp = ctxs[0]->rp; ctxs[i]->have_reads = true; ctxs[i]->reads_dirty = false; ctxs[i]->reads_path = ctxs[0]->reads_path; }
         double s = 0; size_t b = 0;
         const char* how = ag_device_broadcast_reads(devs.data(), n_ctx, &s, &b);
+        for (int i = 1; i < n_ctx; i++) ctxs[i]->dev->set_reads_window(ctxs[0]->rp->win_lo, ctxs[0]->rp->win_hi);
         if (info) { info->seconds = s; info->bytes = b; info->nccl = strcmp(how, "nccl") == 0; }
     });
 }

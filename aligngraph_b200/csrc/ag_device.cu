@@ -1876,6 +1876,7 @@ void AgDevice::verify_placements(const AgSeqSet& db, const AgSeqSet& qs, const s
     d_db.release(); d_q.release(); d_dbo.release(); d_qo.release(); d_c.release(); d_m.release();
 }
 bool AgDevice::sam_window_miss() const { return m_->window_miss; }
+void AgDevice::set_reads_window(u64 lo, u64 hi) { m_->win_lo = lo; m_->win_hi = hi; }
 u64 AgDevice::ingested_alignments() const { return m_->aln_ingested ? m_->n_aln : 0; }
 void AgDevice::fetch_alignments(std::vector<ag_aln>& aln, std::vector<ag_seg>& ext) {
     CK(cudaSetDevice(dev_));

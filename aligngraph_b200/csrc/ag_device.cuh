@@ -63,6 +63,7 @@ public:
     // the pair indices, AG:3455-3471) — ingest_sam then reports ids outside the window through sam_window_miss()
     bool ingest_reads(const std::string& path, struct AgReads& host, long long win_lo = -1, long long win_hi = -1);
     bool sam_window_miss() const;
+    void set_reads_window(u64 lo, u64 hi);   // pair-id window of the resident read set (a broadcast target inherits the source's)
     // tmp/_reads_genome.N.bowtie -> the unit's surviving alignment tuples, resident on the device in file order
     bool ingest_sam(const std::string& path);
     // removeMisassembly's coverage pile-up (AG:3938-3978) of tmp/_reads_<id>_contigs.bowtie over the chunks of tmp/_<id>_contigs.fa; false: the

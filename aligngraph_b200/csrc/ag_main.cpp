@@ -239,13 +239,8 @@ int main(int argc, char* argv[]) {
             if (ag_create(&p, &c) != 0) die(ag_create_error());
             ctxs.push_back(c);
         }
-        // reads are parsed once and shared by every unit (the reference re-reads tmp/_reads.fa per chromosome, AG:1880)
-        if (ag_load_reads_fasta(ctxs[0], "tmp/_reads.fa") != 0) die(ag_last_error(ctxs[0]));
-        if (ctxs.size() > 1) {   // ONE broadcast of the packed read buffer to the other GPUs; host copy incl. the exception list is shared
-            ag_bcast_info bi;
-            if (ag_broadcast_reads(ctxs.data(), (int)ctxs.size(), &bi) != 0) die(ag_last_error(ctxs[0]));
-            if (getenv("AG_STATS")) fprintf(stderr, "[ag] reads broadcast to %zu GPUs: %.1f MB in %.1f ms (%s)\n", ctxs.size() - 1, bi.bytes / 1e6, bi.seconds * 1e3, bi.nccl ? "ncclBroadcast" : "peer copy");
-        }
+        // the read set is loaded once per run, as part of the job (the reference re-reads tmp/_reads.fa per chromosome, AG:1880): raw text to the first
+        // GPU, parsed there, ONE broadcast of the packed buffers to the other GPUs — while the host already prepares the first units
         std::vector<string> errors((size_t)units);
         std::vector<char> done((size_t)units, 0);
         int printed = cp;
@@ -270,9 +265,11 @@ int main(int argc, char* argv[]) {
         };
         int prefetch = 4;
         if (const char* e = getenv("AG_PREFETCH")) prefetch = atoi(e);
-        ag_run_units_files(ctxs.data(), (int)ctxs.size(), "tmp", cp, units - cp, prefetch, on_done, &pg);
+        std::vector<int> todo; for (int u = cp; u < units; u++) todo.push_back(u);
+        const int job_rc = ag_run_job_files(ctxs.data(), (int)ctxs.size(), "tmp", "tmp/_reads.fa", todo.data(), (int)todo.size(), prefetch, on_done, &pg);
         flush_progress(pg);
         if (pg.failed >= 0) die(errors[(size_t)pg.failed]);   // the reference prints the message and exits at the failing chromosome (exit(-1))
+        if (job_rc != 0 && printed < units) die(ag_last_error(ctxs[0]));   // the read set could not be loaded
         if (getenv("AG_STATS")) {
             for (size_t g = 0; g < ctxs.size(); g++) {
                 ag_stats s; ag_get_stats(ctxs[g], &s);
