@@ -169,6 +169,17 @@ class Context:
         rc = self._lib.ag_run_job_files(arr, 1, os.fsencode(tmp_dir), os.fsencode(reads_fa) if reads_fa else None, ul, len(units), prefetch, None, None)
         self._ck(rc, "ag_run_job_files")
 
+    @staticmethod
+    def run_job_on(ctxs, tmp_dir, units, reads_fa=None, prefetch=2):
+        """ag_run_job_files over several contexts (one worker per context; contexts may share a GPU: a second context on the same device
+        overlaps its unit's text staging and host post passes with the first one's kernels).  The reads are loaded into ctxs[0] and copied."""
+        arr = (C.c_void_p * len(ctxs))(*[c._h for c in ctxs])
+        ul = (C.c_int * len(units))(*units)
+        rc = ctxs[0]._lib.ag_run_job_files(arr, len(ctxs), os.fsencode(tmp_dir), os.fsencode(reads_fa) if reads_fa else None, ul, len(units), prefetch, None, None)
+        if rc:
+            msgs = [c._lib.ag_last_error(c._h).decode() for c in ctxs]
+            raise AlignGraphError("ag_run_job_files: " + next((m for m in msgs if m), "failed"))
+
     def prepare_unit(self, tmp_dir, unit):
         self._ck(self._lib.ag_prepare_unit_files(self._h, os.fsencode(tmp_dir), unit), "ag_prepare_unit_files")
 

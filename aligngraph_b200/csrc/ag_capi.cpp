@@ -402,6 +402,10 @@ static int run_units_impl(ag_ctx** ctxs, int n_ctx, const char* tmp_dir, const s
         }
     };
     int first_rc = 0;
+    // AG_JOB_TIMING: wall-clock laps of the job's serial path on stderr (diagnosis)
+    const bool job_timing = getenv("AG_JOB_TIMING") != nullptr;
+    auto T_job = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) { if (job_timing) { auto t = std::chrono::steady_clock::now(); fprintf(stderr, "  [job] %-32s %7.2f ms\n", what, std::chrono::duration<double>(t - T_job).count() * 1e3); T_job = t; } };
     auto worker = [&](ag_ctx* ctx) {
         for (;;) {
             int i = next_run.fetch_add(1);
@@ -411,14 +415,19 @@ static int run_units_impl(ag_ctx** ctxs, int n_ctx, const char* tmp_dir, const s
             { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return ready.count(i) != 0 || stop.load(); }); if (!ready.count(i)) return; p = std::move(ready[i]); ready.erase(i); if (i + 1 > consumed) consumed = i + 1; }
             cv.notify_all();
             int rc = 0;
+            lap("wait for the prepared unit");
             if (!p->error.empty()) { ctx->err = p->error; rc = 1; }
             else {
                 ctx->dev->unpin_all();
                 ctx->unit = std::move(p->unit); ctx->res.reset(); ctx->res.initial_text = std::move(p->initial_text);
                 ctx->unit_id = u; ctx->uploaded = false; ctx->s_parse += p->s_parse;
+                lap("unit handed over");
                 if (!host_sam) rc = guard(ctx, [&] { auto t0 = std::chrono::steady_clock::now(); load_unit_sam(ctx, tmp, u); ctx->s_parse += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); });
+                lap("SAM text -> device tuples");
                 if (!rc) rc = ag_process(ctx);
+                lap("process");
                 if (!rc) rc = ag_write_unit_files(ctx, tmp_dir, u);
+                lap("write unit files");
             }
             std::lock_guard<std::mutex> lk(mu);
             if (rc && !first_rc) first_rc = rc;
@@ -437,7 +446,9 @@ static int run_units_impl(ag_ctx** ctxs, int n_ctx, const char* tmp_dir, const s
     int rc_reads = 0;
     if (reads_fa && host_sam) rc_reads = load_reads();                       // the host SAM parser needs the read lengths: reads first
     if (!rc_reads) for (int i = 0; i < n_prep && n_units; i++) th.emplace_back(preparer);
+    lap("start preparers");
     if (reads_fa && !host_sam) rc_reads = load_reads();                      // raw text -> GPU while the preparers parse the first units' genome / PSL
+    lap("reads text -> device");
     if (rc_reads) { stop = true; cv.notify_all(); for (auto& t : th) t.join(); return rc_reads; }
     for (int i = 1; i < n_ctx; i++) th.emplace_back(worker, ctxs[i]);
     worker(ctxs[0]);

@@ -22,6 +22,8 @@
 #include <dlfcn.h>
 #include <nccl.h>   // types only: the library is bound with dlopen (ag_device_broadcast_reads)
 #include <atomic>
+#include <memory>
+#include <thread>
 #include <fcntl.h>
 #include <unistd.h>
 #include <sys/stat.h>
@@ -125,12 +127,76 @@ __global__ void k_scan_apply(const u32* __restrict__ in, u32* __restrict__ out, 
     if (write_total && blockIdx.x == gridDim.x - 1 && threadIdx.x == SCAN_T - 1) out[n] = ex;
 }
 
+// Single-pass scan: every CTA scans its 2048 elements, publishes {epoch, flag, value} as ONE 64-bit word (flag 1 = the block's own sum,
+// 2 = inclusive prefix up to and including the block) and warp 0 looks back over its predecessors' words, 32 at a time, until it meets an inclusive
+// prefix (chained scan with decoupled look-back).  One launch and one read + one write of the data instead of three launches and two reads.  The
+// epoch (a per-call number from the host, 30 bits) makes words left by earlier calls read as "not ready", so the state array is never cleared.
+// CTAs are dispatched in blockIdx order, so every predecessor a CTA waits for is resident or finished.
+__device__ __forceinline__ u64 ld_state(const u64* p) { u64 v; asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_state(u64* p, u64 v) { asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
+__global__ void __launch_bounds__(SCAN_T) k_scan_onepass(const u32* in, u32* out, u64* __restrict__ state, size_t n, u32 epoch, int write_total) {
+    __shared__ u32 sm[33];
+    __shared__ u32 s_prefix;
+    const u32 b = blockIdx.x, lane = threadIdx.x & 31;
+    const size_t base = (size_t)b * SCAN_B + (size_t)threadIdx.x * SCAN_I;
+    u32 v[SCAN_I], s = 0;
+    if (base + SCAN_I <= n && (((size_t)in) & 15) == 0) {
+        const uint4 a = *(const uint4*)(in + base), c = *(const uint4*)(in + base + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+    } else {
+        for (int i = 0; i < SCAN_I; i++) v[i] = (base + i < n) ? in[base + i] : 0;
+    }
+    for (int i = 0; i < SCAN_I; i++) s += v[i];
+    u32 total; u32 ex = block_excl_scan(s, sm, total);
+    const u64 tag = (u64)epoch << 34;
+    if (threadIdx.x == 0) { s_prefix = 0; st_state(state + b, tag | ((u64)(b == 0 ? 2 : 1) << 32) | total); }
+    if (b > 0 && threadIdx.x < 32) {
+        u32 run = 0;
+        for (long long j = (long long)b - 1;; j -= 32) {
+            const long long idx = j - lane;                      // lane 0 = the nearest predecessor
+            u64 w; u32 flag;
+            do {
+                w = idx >= 0 ? ld_state(state + idx) : (tag | (2ull << 32));
+                flag = (w >> 34) == epoch ? (u32)(w >> 32) & 3u : 0u;
+            } while (__any_sync(0xFFFFFFFFu, flag == 0));
+            const u32 incl = __ballot_sync(0xFFFFFFFFu, flag == 2);
+            const u32 first = incl ? (u32)__ffs(incl) - 1 : 31u;
+            u32 x = lane <= first ? (u32)w : 0u;
+            for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, o);
+            run += x;
+            if (incl) break;
+        }
+        if (lane == 0) { s_prefix = run; st_state(state + b, tag | (2ull << 32) | (u32)(run + total)); }
+    }
+    __syncthreads();
+    ex += s_prefix;
+    if (base + SCAN_I <= n && (((size_t)out) & 15) == 0) {
+        uint4 a, c;
+        a.x = ex; ex += v[0]; a.y = ex; ex += v[1]; a.z = ex; ex += v[2]; a.w = ex; ex += v[3];
+        c.x = ex; ex += v[4]; c.y = ex; ex += v[5]; c.z = ex; ex += v[6]; c.w = ex; ex += v[7];
+        *(uint4*)(out + base) = a; *(uint4*)(out + base + 4) = c;
+    } else {
+        for (int i = 0; i < SCAN_I; i++) { if (base + i < n) out[base + i] = ex; ex += v[i]; }
+    }
+    if (write_total && b == gridDim.x - 1 && threadIdx.x == SCAN_T - 1) out[n] = ex;
+}
+
 struct Scanner {
     DBuf<u32> lvl[4];
+    DBuf<u64> state;
+    u32 epoch = 0;
+    bool one_pass = getenv("AG_SCAN_TWOPASS") == nullptr;   // (A/B switch for measurements)
     u64* launches = nullptr;
     void run(const u32* in, u32* out, size_t n, cudaStream_t st, int depth = 0, int write_total = 1) {
         if (n == 0) { if (write_total) CK(cudaMemsetAsync(out, 0, sizeof(u32), st)); return; }
         size_t nb = (n + SCAN_B - 1) / SCAN_B;
+        if (one_pass) {
+            if (nb > state.cap) { state.ensure(nb); CK(cudaMemsetAsync(state.p, 0, state.cap * sizeof(u64), st)); }
+            epoch = (epoch + 1) & 0x3FFFFFFFu; if (!epoch) epoch = 1;
+            k_scan_onepass<<<(unsigned)nb, SCAN_T, 0, st>>>(in, out, state.p, n, epoch, write_total);
+            if (launches) ++*launches;
+            return;
+        }
         if (nb == 1) { k_scan_apply<<<1, SCAN_T, 0, st>>>(in, out, nullptr, n, write_total); if (launches) ++*launches; return; }
         if (depth >= 4) throw AgError{"scan depth"};
         lvl[depth].ensure(nb + 1);
@@ -962,12 +1028,14 @@ __global__ void __launch_bounds__(1024) k_rank_local(ag_chain* recs, const u32* 
     sa[threadIdx.x] = c;
     __syncthreads();
     ag_chain *src = sa, *dst = sb;
-    for (int r = 0; r < 10; r++) {
+    for (int r = 0; r < 10; r++) {   // (2^10 = block size: enough for a chain through the whole block; most blocks are done after a few rounds)
         c = src[threadIdx.x];
-        if (c.jump != AG_NONE && c.jump - b0 < 1024u) { ag_chain j = src[c.jump - b0]; c.len += j.len; c.flg += j.flg; c.tail = j.tail; c.jump = j.jump; }
+        const bool open = c.jump != AG_NONE && c.jump - b0 < 1024u;
+        if (open) { ag_chain j = src[c.jump - b0]; c.len += j.len; c.flg += j.flg; c.tail = j.tail; c.jump = j.jump; }
         dst[threadIdx.x] = c;
-        __syncthreads();
+        const int any = __syncthreads_or(open ? 1 : 0);
         ag_chain* t = src; src = dst; dst = t;
+        if (!any) break;
     }
     if (v < n_nodes) recs[v] = src[threadIdx.x];
 }
@@ -1331,6 +1399,7 @@ AgDevice::~AgDevice() {
                         &m.eovf_target, &m.eovf_next, &m.walk_next, &m.parent, &m.cmin, &m.cmax, &m.walk_used, &m.sel_start, &m.sel_tails};
     for (auto* b : b32) b->release();
     for (int i = 0; i < 4; i++) m.scanner.lvl[i].release();
+    m.scanner.state.release();
     m.cm.release(); m.cthreads.release(); m.aln.release(); m.ext.release(); m.alnp.release(); m.fast.release(); m.pool_c.release(); m.pool_w.release(); m.ovf_node.release(); m.err.release();
     m.node_c.release(); m.node_w.release(); m.walks.release(); m.walks2.release(); m.cm1.release(); m.mat_detours.release(); m.tail_end.release(); m.pos_term.release(); m.cand_rank.release(); m.cand_node.release(); m.cand_label.release(); m.fprev.release(); m.msuf.release(); m.mnode.release(); m.indeg.release(); m.fnext.release(); m.chain_a.release(); m.chain_b.release(); m.hrec.release(); m.changed.release(); m.sel_off.release();
     m.contig_blob.release(); m.cdesc.release(); m.cruns.release(); m.raw.release(); m.exc_chr.release(); m.nl.release(); m.nl_blk.release(); m.rlen.release(); m.s_keep.release(); m.s_next.release(); m.s_aoff.release(); m.s_eoff.release(); m.s_lost.release(); m.ing.release(); m.exc_key.release(); m.srec.release(); m.stager.release();
@@ -1357,6 +1426,7 @@ void AgDevice::set_option(const std::string& name, long value) {
     else if (name == "tma") tma_off_ = value == 0;
     else if (name == "bases_cap") m.bases_cap = (u32)std::max<long>(value, 1);
     else if (name == "fused_extend") fused_off_ = value == 0;
+    else if (name == "scan_onepass") m_->scanner.one_pass = value != 0;
     else if (name == "rank_rounds") m.rank_rounds = (int)std::max<long>(value, 1);
     else if (name == "eovf_cap") m.eovf_cap_init = (u32)std::max<long>(value, 1);
     else if (name == "section_timing") section_timing_ = value != 0;
@@ -1955,10 +2025,10 @@ void AgDevice::enqueue_build() {
     if (m.unit_n_ref != n_ref || m.unit_n_aln != nA) {   // a new unit: capacities from its size (kept when the same unit is built again)
         m.unit_n_ref = n_ref; m.unit_n_aln = nA;
         if (!m.key_cap_hooked) m.key_cap = std::max<u32>(m.key_cap, 2 * nA + 4096);
-        m.node_cap = m.node_cap_hook ? m.node_cap_hook : std::max<u32>(m.node_cap, std::max<u32>(1u << 20, 3 * n_ref + (1u << 16)));
+        m.node_cap = m.node_cap_hook ? m.node_cap_hook : std::max<u32>(m.node_cap, std::max<u32>(1u << 20, n_ref / 4 * 9 + (1u << 16)));   // 2.25 nodes per position (1.6 measured at 50x); doubled on overflow
         if (m.ovf_cap_hook) m.ovf_cap = m.ovf_cap_hook;
     }
-    if (!m.node_cap) m.node_cap = std::max<u32>(1u << 20, 3 * n_ref + (1u << 16));
+    if (!m.node_cap) m.node_cap = std::max<u32>(1u << 20, n_ref / 4 * 9 + (1u << 16));
     if (!m.key_cap) m.key_cap = 2 * nA + 4096;
     if (!m.ovf_cap) m.ovf_cap = std::max<u32>(1u << 18, n_ref / 8);
     DevView& d = m.view;

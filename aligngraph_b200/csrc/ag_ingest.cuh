@@ -87,7 +87,9 @@ __global__ void k_rd_pairlen(const u32* __restrict__ rlen, u32 n_pairs, uint16_t
     if (a != b) atomicOr(bad, ING_PE_LEN);   // INCONSISTENT PE FILES!
     pair_len[p] = (uint16_t)a;
 }
-// one thread per (record, group of 32 bases): two 2-bit words + one mask word; characters other than upper-case ACGT are masked and listed
+// one thread per (record, group of 32 bases): two 2-bit words + one mask word; characters other than upper-case ACGT are masked and listed.
+// The 32 characters are fetched as aligned 32-bit words (funnel-shifted to the sequence's byte offset) and coded four at a time: for A C G T
+// ((x >> 1) ^ (x >> 2)) & 3 is the 2-bit code, and rebuilding the character from the code tells whether the byte was one of the four.
 __global__ void k_rd_pack(const char* __restrict__ text, const u32* __restrict__ nl, u32 n_rec, u32 stride2, u32 stridem, u64 read0,
                           u32* __restrict__ bases, u32* __restrict__ nmask, u64* __restrict__ exc_key, char* __restrict__ exc_chr, u32* exc_count, u32 exc_cap) {
     const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -99,16 +101,35 @@ __global__ void k_rd_pack(const char* __restrict__ text, const u32* __restrict__
     if (o0 < len) {
         const u32 cnt = min(32u, len - o0);
         const char* s = text + ss + o0;
-        for (u32 j = 0; j < cnt; j++) {
-            const char ch = s[j];
-            u32 c = ch == 'A' ? 0u : ch == 'C' ? 1u : ch == 'G' ? 2u : ch == 'T' ? 3u : 4u;
-            if (c == 4u) {
-                mk |= 1u << j;
-                const u32 e = atomicAdd(exc_count, 1u);
-                if (e < exc_cap) { exc_key[e] = (read0 + r) * 65536ull + (o0 + j); exc_chr[e] = ch; }
-                c = 0;
+        const unsigned long long addr = (unsigned long long)s;
+        const u32* wp = reinterpret_cast<const u32*>(addr & ~3ull);   // (the text buffer is 16-byte aligned and padded: the words around the sequence are readable)
+        const u32 sh = (u32)(addr & 3ull) * 8u;
+        u32 prev = wp[0];
+#pragma unroll
+        for (u32 k = 0; k < 8; k++) {
+            if (4 * k >= cnt) break;
+            const u32 next = wp[k + 1];
+            const u32 x = __funnelshift_r(prev, next, sh);   // characters 4k .. 4k+3
+            prev = next;
+            const u32 c = ((x >> 1) ^ (x >> 2)) & 0x03030303u;
+            const u32 c0 = c & 0x01010101u, c1 = (c >> 1) & 0x01010101u;
+            const u32 expect = 0x41414141u + c0 * 2u + c1 * 6u + (c0 & c1) * 0x0Bu;   // 'A' 'C' 'G' 'T' rebuilt from the code
+            u32 diff = x ^ expect;                                                     // non-zero byte = not one of the four
+            const u32 valid = min(4u, cnt - 4 * k);
+            if (valid < 4) diff &= (1u << (8 * valid)) - 1u;
+            u32 codes = c;
+            if (diff) {
+                for (u32 j = 0; j < valid; j++)
+                    if ((diff >> (8 * j)) & 0xFFu) {
+                        mk |= 1u << (4 * k + j);
+                        codes &= ~(3u << (8 * j));
+                        const u32 e = atomicAdd(exc_count, 1u);
+                        if (e < exc_cap) { exc_key[e] = (read0 + r) * 65536ull + (o0 + 4 * k + j); exc_chr[e] = (char)((x >> (8 * j)) & 0xFFu); }
+                    }
             }
-            if (j < 16) w0 |= c << (2 * j); else w1 |= c << (2 * (j - 16));
+            if (valid < 4) codes &= (1u << (8 * valid)) - 1u;
+            const u32 packed = (codes & 3u) | ((codes >> 6) & 0xCu) | ((codes >> 12) & 0x30u) | ((codes >> 18) & 0xC0u);   // four 2-bit codes -> one byte
+            if (k < 4) w0 |= packed << (8 * k); else w1 |= packed << (8 * (k - 4));
         }
     }
     const u64 rr = read0 + r;
@@ -282,43 +303,96 @@ __global__ void k_verify_placements(const char* __restrict__ db, const u64* __re
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
-// file -> device through page-locked staging chunks.  T host threads each own two pinned slots and take the file's chunks round-robin:
-// pread() into a slot (page cache -> pinned memory at memory speed), queue the slot's host->device copy, move on to the other slot; a
-// slot is reused once its copy has finished.  The copy engine therefore always has several chunks queued while the next ones are read.
+// file -> device through a ring of page-locked PIECES (256 KB; 256 MB ring).  Reader threads draw pieces in file order, pread() them into their ring slots
+// (page cache -> pinned memory) and raise the piece's ready flag; ONE submitter walks the pieces in order and queues a host->device copy for
+// every run of consecutive ready pieces (up to 8 MB, not across the ring's wrap), so the copy engine starts after the first piece, not
+// after every thread's first chunk, and the driver sees one caller and few, large copies.  Ring positions continue across calls (the reads
+// file and the SAM file follow each other without waiting for the earlier copies); a slot is reused once the copy batch that read it has
+// finished (one event per batch).
 // ---------------------------------------------------------------------------------------------------------------------------
 struct FileStager {
     static constexpr int MAXT = 32;
-    size_t CHUNK = (size_t)4 << 20; int SLOTS = 2;   // per thread: SLOTS pinned slots of CHUNK bytes (AG_STAGE_CHUNK_MB / AG_STAGE_SLOTS override, for tuning)
-    PinnedBuf ring; std::vector<cudaEvent_t> ev; std::vector<char> used;
+    size_t PIECE = (size_t)256 << 10, NP = 1024, MAXRUN = 32;   // AG_STAGE_PIECE_KB / AG_STAGE_RING_MB / AG_STAGE_RUN override (tuning)
+    PinnedBuf ring;
+    std::vector<cudaEvent_t> bev;              // event of batch b = bev[b % NP]
+    std::vector<unsigned long long> slot_batch;   // batch whose completion frees the slot (0 = never used)
+    unsigned long long seq = 0, batch = 0;       // global piece / batch counters (continue across calls)
     FileStager() {
-        if (const char* e = getenv("AG_STAGE_CHUNK_MB")) { const long v = atol(e); if (v >= 1 && v <= 64) CHUNK = (size_t)v << 20; }
-        if (const char* e = getenv("AG_STAGE_SLOTS")) { const int v = atoi(e); if (v >= 2 && v <= 16) SLOTS = v; }
+        if (const char* e = getenv("AG_STAGE_PIECE_KB")) { const long v = atol(e); if (v >= 64 && v <= 65536) PIECE = (size_t)v << 10; }
+        if (const char* e = getenv("AG_STAGE_RING_MB")) { const long v = atol(e); if (v >= 8 && v <= 4096) NP = std::max<size_t>(8, ((size_t)v << 20) / PIECE); }
+        if (const char* e = getenv("AG_STAGE_RUN")) { const long v = atol(e); if (v >= 1 && v <= 64) MAXRUN = (size_t)v; }
     }
-    void release() { ring.release(); for (cudaEvent_t e : ev) cudaEventDestroy(e); ev.clear(); used.clear(); }
+    void release() { ring.release(); for (cudaEvent_t e : bev) cudaEventDestroy(e); bev.clear(); slot_batch.clear(); seq = batch = 0; }
     // copies file bytes [off, off + len) to dst (device), asynchronously on `st` (every copy has been QUEUED when this returns)
     void run(int fd, size_t off, size_t len, char* dst, cudaStream_t st, int device) {
         if (!len) return;
-        if (ev.empty()) { ev.resize((size_t)SLOTS * MAXT); used.assign((size_t)SLOTS * MAXT, 0); for (auto& e : ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); }
-        const size_t n_chunks = (len + CHUNK - 1) / CHUNK;
+        if (bev.empty()) { bev.resize(NP); slot_batch.assign(NP, 0); for (auto& e : bev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); }
+        ring.ensure(NP * PIECE);
+        const size_t n_pieces = (len + PIECE - 1) / PIECE;
         int tmax = MAXT; if (const char* e = getenv("AG_STAGE_THREADS")) { const int v = atoi(e); if (v >= 1 && v <= MAXT) tmax = v; }
-        const int T = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>((size_t)ag_team_size(), (size_t)tmax), n_chunks));
-        ring.ensure((size_t)SLOTS * MAXT * CHUNK);
-        std::atomic<int> failed(0);
+        const int T = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>((size_t)ag_team_size(), (size_t)tmax), n_pieces + 1));
         static const bool no_read = getenv("AG_STAGE_NOREAD") != nullptr, no_copy = getenv("AG_STAGE_NOCOPY") != nullptr;   // diagnosis only: time the two halves apart
-        ag_parallel_chunks(T, [&](int t) {
-            cudaSetDevice(device);
-            size_t j = 0;
-            for (size_t k = (size_t)t; k < n_chunks; k += (size_t)T, j++) {
-                const int slot = SLOTS * t + (int)(j % (size_t)SLOTS);
-                if (used[(size_t)slot]) cudaEventSynchronize(ev[(size_t)slot]);   // the copy that last read this slot (this call's or an earlier one's) has finished
-                char* h = ring.p + (size_t)slot * CHUNK;
-                const size_t o = k * CHUNK, n = std::min(CHUNK, len - o);
-                size_t a = 0;
-                while (!no_read && a < n) { const ssize_t got = pread(fd, h + a, n - a, (off_t)(off + o + a)); if (got <= 0) { failed = 1; return; } a += (size_t)got; }
-                if (!no_copy && cudaMemcpyAsync(dst + o, h, n, cudaMemcpyHostToDevice, st) != cudaSuccess) { failed = 2; return; }
-                cudaEventRecord(ev[(size_t)slot], st); used[(size_t)slot] = 1;
-            }
-        });
+        const unsigned long long g0 = seq;
+        std::atomic<int> failed(0);
+        std::atomic<size_t> next_piece(0);
+        std::atomic<unsigned long long> submitted(g0);          // every piece with a global number below this has its copy queued and slot_batch set
+        std::unique_ptr<std::atomic<unsigned char>[]> ready(new std::atomic<unsigned char>[n_pieces]);
+        for (size_t i = 0; i < n_pieces; i++) ready[i].store(0, std::memory_order_relaxed);
+        auto relax = [](unsigned& spins) { if (++spins < 64) { __builtin_ia32_pause(); } else { std::this_thread::yield(); } };
+        // slot of global piece g is free once the copy of piece g - NP (its previous occupant) has finished
+        auto wait_slot = [&](unsigned long long g) -> bool {
+            const size_t slot = (size_t)(g % NP);
+            if (g >= NP) { unsigned spins = 0; while (submitted.load(std::memory_order_acquire) + NP <= g) { if (failed.load()) return false; relax(spins); } }
+            const unsigned long long b = slot_batch[slot];
+            if (b && cudaEventSynchronize(bev[(size_t)(b % NP)]) != cudaSuccess) return false;
+            return true;
+        };
+        auto read_piece = [&](size_t k) -> bool {
+            const unsigned long long g = g0 + k;
+            if (!wait_slot(g)) return false;
+            char* h = ring.p + (size_t)(g % NP) * PIECE;
+            const size_t o = k * PIECE, n = std::min(PIECE, len - o);
+            size_t a = 0;
+            while (!no_read && a < n) { const ssize_t got = pread(fd, h + a, n - a, (off_t)(off + o + a)); if (got <= 0) return false; a += (size_t)got; }
+            return true;
+        };
+        auto submit_run = [&](size_t k, size_t cnt) -> bool {     // pieces [k, k + cnt): consecutive in the file and in the ring
+            const unsigned long long g = g0 + k;
+            const size_t o = k * PIECE, n = std::min(cnt * PIECE, len - o);
+            if (!no_copy && cudaMemcpyAsync(dst + o, ring.p + (size_t)(g % NP) * PIECE, n, cudaMemcpyHostToDevice, st) != cudaSuccess) return false;
+            const unsigned long long b = ++batch;
+            if (cudaEventRecord(bev[(size_t)(b % NP)], st) != cudaSuccess) return false;
+            for (size_t i = 0; i < cnt; i++) slot_batch[(size_t)((g + i) % NP)] = b;
+            submitted.store(g + cnt, std::memory_order_release);
+            return true;
+        };
+        if (T == 1) {
+            for (size_t k = 0; k < n_pieces; k++) { if (!read_piece(k)) { failed = 1; break; } if (!submit_run(k, 1)) { failed = 2; break; } }
+        } else {
+            ag_parallel_chunks(T, [&](int t) {
+                cudaSetDevice(device);
+                if (t == 0) {                                       // the submitter
+                    size_t k = 0;
+                    while (k < n_pieces) {
+                        unsigned spins = 0;
+                        while (!ready[k].load(std::memory_order_acquire)) { if (failed.load()) return; relax(spins); }
+                        size_t cnt = 1;
+                        const size_t slot = (size_t)((g0 + k) % NP);
+                        while (cnt < MAXRUN && k + cnt < n_pieces && slot + cnt < NP && ready[k + cnt].load(std::memory_order_acquire)) cnt++;
+                        if (!submit_run(k, cnt)) { failed = 2; return; }
+                        k += cnt;
+                    }
+                    return;
+                }
+                for (;;) {                                          // readers
+                    const size_t k = next_piece.fetch_add(1);
+                    if (k >= n_pieces || failed.load()) return;
+                    if (!read_piece(k)) { failed = 1; return; }
+                    ready[k].store(1, std::memory_order_release);
+                }
+            });
+        }
+        seq = g0 + n_pieces;
         if (failed) throw AgError{failed == 1 ? "CANNOT OPEN FILE!" : "host->device copy of a staged chunk failed"};
     }
 };
