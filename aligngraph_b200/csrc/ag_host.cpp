@@ -7,6 +7,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <climits>
+#include <cerrno>
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -1466,18 +1467,25 @@ int ag_formalize_genome(const std::string& in_path, const std::string& tmp, int 
     return unit;
 }
 
-void ag_write_file(const std::string& path, const AgText& text) {
-    FILE* f = fopen(path.c_str(), "wb");
-    if (!f) throw AgHostError{"CANNOT OPEN FILE!"};
-    if (!text.empty()) fwrite(text.data(), 1, text.size(), f);
-    fclose(f);
+// One open / fallocate / write / close per output file.  Reserving the extent first (fallocate; ignored where the file system has no
+// support) lets ext4 allocate the blocks once instead of reserving them page by page on the buffered-write path: about twice as fast for
+// the 5 MB per-unit FASTA files here.  AG_WRITE_PLAIN=1 skips the reservation (measurements).
+static void write_file_bytes(const std::string& path, const char* data, size_t n) {
+    static const bool plain = getenv("AG_WRITE_PLAIN") != nullptr;
+    const int fd = open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
+    if (fd < 0) throw AgHostError{"CANNOT OPEN FILE!"};
+    if (n >= ((size_t)1 << 20) && !plain) (void)!fallocate(fd, 0, 0, (off_t)n);
+    size_t a = 0;
+    while (a < n) {
+        const ssize_t got = write(fd, data + a, n - a);
+        if (got < 0 && errno == EINTR) continue;
+        if (got <= 0) break;          // (disk full, ...: like the reference's unchecked ofstream, the file stays short)
+        a += (size_t)got;
+    }
+    close(fd);
 }
-void ag_write_file(const std::string& path, const std::string& text) {
-    FILE* f = fopen(path.c_str(), "wb");
-    if (!f) throw AgHostError{"CANNOT OPEN FILE!"};
-    if (!text.empty()) fwrite(text.data(), 1, text.size(), f);
-    fclose(f);
-}
+void ag_write_file(const std::string& path, const AgText& text) { write_file_bytes(path, text.data(), text.size()); }
+void ag_write_file(const std::string& path, const std::string& text) { write_file_bytes(path, text.data(), text.size()); }
 
 // =============================================================================================================================
 // CLI-side phases outside the hot path (kept byte-compatible with the reference so that the binary is a drop-in)
