@@ -1568,41 +1568,58 @@ const char* ag_device_broadcast_reads(AgDevice** devs, int n, double* seconds, s
     std::vector<AgDevice::ReadsView> dst((size_t)n);
     dst[0] = src;
     for (int i = 1; i < n; i++) dst[i] = devs[i]->reserve_reads(src.n_pairs, src.stride2, src.stridem);
-    bool distinct = true;
-    for (int i = 0; i < n; i++) for (int j = 0; j < i; j++) if (devs[i]->device() == devs[j]->device()) distinct = false;
+    // leaders = the first context of every distinct device: one collective among them, then device-local copies to the other contexts of a device
+    std::vector<int> leader((size_t)n, -1), leaders;
+    for (int i = 0; i < n; i++) {
+        for (int j = 0; j < i && leader[i] < 0; j++) if (devs[i]->device() == devs[j]->device()) leader[i] = leader[j] < 0 ? j : leader[j];
+        if (leader[i] < 0) leaders.push_back(i);
+    }
+    const int nl = (int)leaders.size();
     const auto t0 = std::chrono::steady_clock::now();
-    const char* how = "peer-copy";
-    bool done = false;
-    if (distinct && nccl().ok) {
-        std::vector<int> ids((size_t)n); for (int i = 0; i < n; i++) ids[i] = devs[i]->device();
-        std::vector<ncclComm_t> comm((size_t)n);
-        if (nccl().CommInitAll(comm.data(), n, ids.data()) == ncclSuccess) {
+    const char* how = nl > 1 ? "peer-copy" : "device-copy";
+    bool done = nl <= 1;
+    if (!done && nccl().ok) {
+        std::vector<int> ids((size_t)nl); for (int i = 0; i < nl; i++) ids[i] = devs[leaders[i]]->device();
+        std::vector<ncclComm_t> comm((size_t)nl);
+        if (nccl().CommInitAll(comm.data(), nl, ids.data()) == ncclSuccess) {
             bool ok = true;
             const void* sp[3] = {src.bases, src.nmask, src.len}; const size_t nb[3] = {src.bases_bytes, src.nmask_bytes, src.len_bytes};
             for (int b = 0; b < 3 && ok; b++) {
                 ok = nccl().GroupStart() == ncclSuccess;
-                for (int i = 0; i < n && ok; i++) {
-                    CK(cudaSetDevice(devs[i]->device()));
-                    void* rp = b == 0 ? (void*)dst[i].bases : b == 1 ? (void*)dst[i].nmask : (void*)dst[i].len;
-                    ok = nccl().Broadcast(sp[b], rp, nb[b], ncclUint8, 0, comm[i], (cudaStream_t)devs[i]->stream()) == ncclSuccess;
+                for (int i = 0; i < nl && ok; i++) {
+                    const int c = leaders[i];
+                    CK(cudaSetDevice(devs[c]->device()));
+                    void* rp = b == 0 ? (void*)dst[c].bases : b == 1 ? (void*)dst[c].nmask : (void*)dst[c].len;
+                    ok = nccl().Broadcast(sp[b], rp, nb[b], ncclUint8, 0, comm[i], (cudaStream_t)devs[c]->stream()) == ncclSuccess;
                 }
                 ok = nccl().GroupEnd() == ncclSuccess && ok;
             }
-            for (int i = 0; i < n; i++) devs[i]->sync();
-            for (int i = 0; i < n; i++) nccl().CommDestroy(comm[i]);
+            for (int i = 0; i < nl; i++) devs[leaders[i]]->sync();
+            for (int i = 0; i < nl; i++) nccl().CommDestroy(comm[i]);
             if (ok) { done = true; how = "nccl"; }
         }
     }
     if (!done) {
-        for (int i = 1; i < n; i++) {
-            CK(cudaSetDevice(devs[i]->device()));
-            cudaStream_t st = (cudaStream_t)devs[i]->stream();
-            CK(cudaMemcpyPeerAsync(dst[i].bases, devs[i]->device(), src.bases, devs[0]->device(), src.bases_bytes, st));
-            CK(cudaMemcpyPeerAsync(dst[i].nmask, devs[i]->device(), src.nmask, devs[0]->device(), src.nmask_bytes, st));
-            CK(cudaMemcpyPeerAsync(dst[i].len, devs[i]->device(), src.len, devs[0]->device(), src.len_bytes, st));
+        for (int i = 1; i < nl; i++) {
+            const int c = leaders[i];
+            CK(cudaSetDevice(devs[c]->device()));
+            cudaStream_t st = (cudaStream_t)devs[c]->stream();
+            CK(cudaMemcpyPeerAsync(dst[c].bases, devs[c]->device(), src.bases, devs[0]->device(), src.bases_bytes, st));
+            CK(cudaMemcpyPeerAsync(dst[c].nmask, devs[c]->device(), src.nmask, devs[0]->device(), src.nmask_bytes, st));
+            CK(cudaMemcpyPeerAsync(dst[c].len, devs[c]->device(), src.len, devs[0]->device(), src.len_bytes, st));
         }
-        for (int i = 1; i < n; i++) devs[i]->sync();
+        for (int i = 1; i < nl; i++) devs[leaders[i]]->sync();
     }
+    for (int i = 0; i < n; i++) {   // the other contexts of a device: copies inside its memory
+        if (leader[i] < 0) continue;
+        const int c = leader[i];
+        CK(cudaSetDevice(devs[i]->device()));
+        cudaStream_t st = (cudaStream_t)devs[i]->stream();
+        CK(cudaMemcpyAsync(dst[i].bases, dst[c].bases, src.bases_bytes, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(dst[i].nmask, dst[c].nmask, src.nmask_bytes, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(dst[i].len, dst[c].len, src.len_bytes, cudaMemcpyDeviceToDevice, st));
+    }
+    for (int i = 0; i < n; i++) if (leader[i] >= 0) devs[i]->sync();
     if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (bytes) *bytes = (src.bases_bytes + src.nmask_bytes + src.len_bytes) * (size_t)(n - 1);
     return how;

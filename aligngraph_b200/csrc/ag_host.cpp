@@ -1199,6 +1199,8 @@ static std::vector<size_t> byte_chunks(const std::vector<size_t>& off /* n + 1 p
 void ag_make_contigs_begin(const std::vector<ag_walk>& walks, const std::vector<u32>& sel, char* bases, const std::vector<u64>& offs,
                            std::vector<AgContig>& contigs, AgMakeState& st) {
     auto tp0 = std::chrono::steady_clock::now();
+    const bool probe = getenv("AG_POST_TIMING") != nullptr;
+    auto lap = [&](const char* what) { if (probe) { auto t = std::chrono::steady_clock::now(); fprintf(stderr, "  [make_contigs] . %s %.3f ms\n", what, std::chrono::duration<double>(t - tp0).count() * 1e3); } };
     contigs.clear(); contigs.resize(sel.size());
     // contig records + header strings + where every contig's text goes (nothing here reads the bases).  Headers are formatted by the thread
     // team into fixed slots, then packed.
@@ -1210,6 +1212,7 @@ void ag_make_contigs_begin(const std::vector<ag_walk>& walks, const std::vector<
     std::vector<unsigned char> hlen(sel.size());
     slots.resize(sel.size() * SLOT);
     char* const slot_base = slots.data();   // (the team's threads must not name the thread_local themselves: each would see its own, empty one)
+    lap("sized");
     const int nchunk = (int)std::min<size_t>((sel.size() + 511) / 512, (size_t)std::max(1, ag_team_size() * 2));
     const size_t per = nchunk ? (sel.size() + (size_t)nchunk - 1) / (size_t)nchunk : 0;
     ag_parallel_chunks(nchunk, [&](int ch) {
@@ -1239,6 +1242,7 @@ void ag_make_contigs_begin(const std::vector<ag_walk>& walks, const std::vector<
         }
       }
     });
+    lap("records");
     for (size_t i = 0; i < sel.size(); i++) { hoff[i + 1] = hoff[i] + hlen[i]; toff[i + 1] = toff[i] + hlen[i] + wrapped_len((size_t)(offs[i + 1] - offs[i])); }
     hdr.resize(hoff.back());
     ag_parallel_chunks(nchunk, [&](int ch) {

@@ -232,6 +232,11 @@ int main(int argc, char* argv[]) {
     if (const char* env = getenv("AG_DEVICES")) { std::stringstream ss(env); string t; while (std::getline(ss, t, ',')) if (!t.empty()) devices.push_back(atoi(t.c_str())); }
     if (devices.empty()) devices.push_back(0);
     if (cp < units) {
+        // more units than GPUs: two contexts per GPU, so that one unit's text staging and host post passes run under the other's kernels
+        // (AG_CONTEXTS_PER_DEVICE overrides; outputs do not depend on it)
+        int per_dev = (units - cp) > (int)devices.size() ? 2 : 1;
+        if (const char* e = getenv("AG_CONTEXTS_PER_DEVICE")) { const int v = atoi(e); if (v >= 1 && v <= 4) per_dev = v; }
+        { const std::vector<int> base = devices; for (int r = 1; r < per_dev; r++) devices.insert(devices.end(), base.begin(), base.end()); }
         std::vector<ag_ctx*> ctxs;
         for (int d : devices) {
             ag_params p; p.k = o.k; p.insert_variation = o.iv; p.coverage = o.cov; p.device = d;

@@ -196,3 +196,29 @@ def test_read_window_too_small_loads_the_whole_set(ag, harness, workdir):
     ctx.close()
     assert st["reads_windowed"] == 1 and st["reads_device"] == 2 and st["sam_host"] == 1, st
     assert harness.unit_outputs(gpu, 1) == harness.unit_outputs(ora, 1)
+
+
+def test_job_over_two_contexts_on_one_gpu(ag, harness, workdir):
+    """ag_run_job_files over two contexts that share a GPU (the second one's text staging and host post passes run under the first one's
+    kernels; the reads reach it by a device-local copy): same per-unit files as the reference, whichever context ran which unit."""
+    import cases
+    from conftest import golden_dir
+    harness.synth(workdir, **cases.GOLDEN["two_chr"])
+    harness.prepare_tmp(workdir)
+    tmp = os.path.join(workdir, "tmp")
+    p = harness.read_command(workdir)
+    ctxs = [ag.Context(k=p["kMer"], insert_variation=p["insertVariation"], coverage=p["coverage"]) for _ in range(2)]
+    g = golden_dir("two_chr")
+    for rep in range(3):
+        for u in (0, 1):
+            for pat in harness.UNIT_FILES:
+                if os.path.exists(os.path.join(tmp, pat.format(u))):
+                    os.remove(os.path.join(tmp, pat.format(u)))
+        ag.Context.run_job_on(ctxs, tmp, [0, 1], reads_fa=os.path.join(tmp, "_reads.fa"))
+        for u in (0, 1):
+            for pat in harness.UNIT_FILES:
+                assert open(os.path.join(tmp, pat.format(u)), "rb").read() == open(os.path.join(g, pat.format(u)), "rb").read(), (rep, pat, u)
+    st = [c.stats() for c in ctxs]
+    assert sum(s["sam_device"] for s in st) == 6 and sum(s["sam_host"] for s in st) == 0, st
+    for c in ctxs[::-1]:
+        c.close()

@@ -117,6 +117,10 @@ def test_fused_step_equals_staged_calls(ag, harness, workdir):
     ctx.set_option("fused_extend", 0)   # emission filter on the host between walk and materialisation (two synchronisations)
     ctx.process()
     assert (ctx.text(1), ctx.text(2)) == staged
+    ctx.set_option("fused_extend", 1)
+    ctx.set_option("scan_onepass", 0)   # prefix sums by the three-launch scan instead of the single-pass look-back kernel
+    ctx.process()
+    assert (ctx.text(1), ctx.text(2)) == staged
     g = os.path.join(os.path.dirname(__file__), "golden", "mix")
     assert staged[0] == open(os.path.join(g, "_pre_extended_contigs.0.fa"), "rb").read()
     ctx.close()
