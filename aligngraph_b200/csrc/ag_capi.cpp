@@ -561,7 +561,7 @@ int ag_set_option(ag_ctx* ctx, const char* name, long value) {
         const std::string n = name ? name : "";
         if (n == "host_parse") ctx->host_parse = value != 0;
         else if (n == "reads_window") ctx->reads_window = value != 0;
-        else if (n == "node_cap" || n == "ovf_cap" || n == "eovf_cap" || n == "key_cap" || n == "cand_cap" || n == "hwalk_cap" || n == "rank_rounds" || n == "tma" || n == "bases_cap" || n == "fused_extend") ctx->dev->set_option(n, value);
+        else if (n == "node_cap" || n == "ovf_cap" || n == "eovf_cap" || n == "key_cap" || n == "cand_cap" || n == "hwalk_cap" || n == "rank_rounds" || n == "tma" || n == "bases_cap" || n == "fused_extend" || n == "scan_onepass") ctx->dev->set_option(n, value);
         else throw AgHostError{"unknown option: " + n};
     });
 }

@@ -134,10 +134,15 @@ __global__ void k_scan_apply(const u32* __restrict__ in, u32* __restrict__ out, 
 // CTAs are dispatched in blockIdx order, so every predecessor a CTA waits for is resident or finished.
 __device__ __forceinline__ u64 ld_state(const u64* p) { u64 v; asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ void st_state(u64* p, u64 v) { asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
-__global__ void __launch_bounds__(SCAN_T) k_scan_onepass(const u32* in, u32* out, u64* __restrict__ state, size_t n, u32 epoch, int write_total) {
+// n_ptr (optional): the number of elements is only known on the device (at most n_cap, which sizes the grid): blocks behind it leave at once, the
+// total still goes to out[n_cap] and the entries between are not written.
+__global__ void __launch_bounds__(SCAN_T) k_scan_onepass(const u32* in, u32* out, u64* __restrict__ state, size_t n_cap, const u32* __restrict__ n_ptr, u32 epoch, int write_total) {
     __shared__ u32 sm[33];
     __shared__ u32 s_prefix;
     const u32 b = blockIdx.x, lane = threadIdx.x & 31;
+    const size_t n = n_ptr ? min((size_t)*n_ptr, n_cap) : n_cap;
+    const u32 last_b = n ? (u32)((n - 1) / SCAN_B) : 0u;
+    if (b > last_b) return;
     const size_t base = (size_t)b * SCAN_B + (size_t)threadIdx.x * SCAN_I;
     u32 v[SCAN_I], s = 0;
     if (base + SCAN_I <= n && (((size_t)in) & 15) == 0) {
@@ -178,7 +183,7 @@ __global__ void __launch_bounds__(SCAN_T) k_scan_onepass(const u32* in, u32* out
     } else {
         for (int i = 0; i < SCAN_I; i++) { if (base + i < n) out[base + i] = ex; ex += v[i]; }
     }
-    if (write_total && b == gridDim.x - 1 && threadIdx.x == SCAN_T - 1) out[n] = ex;
+    if (write_total && b == last_b && threadIdx.x == SCAN_T - 1) out[n_cap] = ex;
 }
 
 struct Scanner {
@@ -187,13 +192,14 @@ struct Scanner {
     u32 epoch = 0;
     bool one_pass = getenv("AG_SCAN_TWOPASS") == nullptr;   // (A/B switch for measurements)
     u64* launches = nullptr;
-    void run(const u32* in, u32* out, size_t n, cudaStream_t st, int depth = 0, int write_total = 1) {
+    // n_ptr (one-pass kernel only; callers check one_pass): device-side element count <= n
+    void run(const u32* in, u32* out, size_t n, cudaStream_t st, int depth = 0, int write_total = 1, const u32* n_ptr = nullptr) {
         if (n == 0) { if (write_total) CK(cudaMemsetAsync(out, 0, sizeof(u32), st)); return; }
         size_t nb = (n + SCAN_B - 1) / SCAN_B;
         if (one_pass) {
             if (nb > state.cap) { state.ensure(nb); CK(cudaMemsetAsync(state.p, 0, state.cap * sizeof(u64), st)); }
             epoch = (epoch + 1) & 0x3FFFFFFFu; if (!epoch) epoch = 1;
-            k_scan_onepass<<<(unsigned)nb, SCAN_T, 0, st>>>(in, out, state.p, n, epoch, write_total);
+            k_scan_onepass<<<(unsigned)nb, SCAN_T, 0, st>>>(in, out, state.p, n, n_ptr, epoch, write_total);
             if (launches) ++*launches;
             return;
         }
@@ -990,19 +996,11 @@ __global__ void k_indeg(DevView d) {
     if (w.misc & AG_NW_OVF) for (u32 o = d.eovf_head[v]; o != AG_NONE; o = d.eovf_next[o]) { u32 s = d.eovf_target[o]; if (!(d.node_w[s].misc & AG_NW_FILTERED)) atomicAdd(&d.indeg[s], 1u); }
     }
 }
-__global__ void k_links(DevView d) {
-    AG_BAIL(d);
-    AG_FOR_N(v, *d.nn_ptr) {
-    u32 w = ag_forced_succ(d.node_w, d.eovf_head, d.eovf_target, d.eovf_next, d.indeg, d.pos_term, d.node_pos, v);
-    d.fnext[v] = w;
-    if (w != AG_NONE) { atomicOr(&d.node_w[w].misc, AG_NW_INTERIOR); d.fprev[w] = v; }
-    ag_chain c; c.jump = w; c.tail = v; c.len = 1; c.flg = (d.node_w[v].misc & AG_NW_HASCONTIG) ? 1u : 0u;
-    d.chain_a[v] = c;
-    }
-}
 // one global pointer-jumping round (double-buffered); `last`: a record that is still open afterwards asks for more rounds (E_RANK_MORE:
 // the step is repeated with a larger round count, remembered by the context)
-__global__ void k_rank(const ag_chain* __restrict__ in, ag_chain* __restrict__ out, const u32* __restrict__ nn_ptr, int* err, int last) {
+// (cand_flag, last round only: 1 for the live nodes that are not chain-interior = the walk's start candidates, ready for the compaction scan)
+__global__ void k_rank(const ag_chain* __restrict__ in, ag_chain* __restrict__ out, const u32* __restrict__ nn_ptr, int* err, int last,
+                       const ag_nodew* __restrict__ nw, u32* __restrict__ cand_flag) {
     if (*(volatile int*)err & (E_FATAL & ~E_RANK_MORE)) return;
     AG_FOR_N(v, *nn_ptr) {
         ag_chain c = in[v];
@@ -1012,19 +1010,26 @@ __global__ void k_rank(const ag_chain* __restrict__ in, ag_chain* __restrict__ o
             if (last && c.jump != AG_NONE) atomicOr(err, E_RANK_MORE);
         }
         out[v] = c;
+        if (cand_flag) cand_flag[v] = (nw[v].misc & (AG_NW_FILTERED | AG_NW_INTERIOR)) ? 0u : 1u;
     }
 }
 
-// list ranking, step 1: pointer jumping inside blocks of 1024 consecutive nodes in shared memory.  Forced links point to higher node
-// indices and chains are short-range (the next node is the next position), so almost every chain is finished here; what remains are
-// links that leave the block, resolved by a few global k_rank rounds.
-__global__ void __launch_bounds__(1024) k_rank_local(ag_chain* recs, const u32* __restrict__ nn_ptr, const int* err) {
+// forced links + list ranking, step 1, in one kernel: a block of 1024 consecutive nodes derives its nodes' forced links (k_links' work: fnext,
+// fprev, the INTERIOR mark) straight into shared memory and runs the pointer jumping there.  Forced links point to higher node indices and
+// chains are short-range (the next node is the next position), so almost every chain is finished here; what remains are links that leave the
+// block, resolved by a few global k_rank rounds.  (The chain records never make the round trip through global memory in between.)
+__global__ void __launch_bounds__(1024) k_links_rank_local(DevView d, ag_chain* recs) {
     __shared__ ag_chain sa[1024], sb[1024];
-    const u32 n_nodes = *nn_ptr;
+    const u32 n_nodes = *d.nn_ptr;
     const u32 b0 = blockIdx.x * 1024u, v = b0 + threadIdx.x;
-    if (b0 >= n_nodes || (*(volatile const int*)err & E_FATAL)) return;
+    if (b0 >= n_nodes || (*(volatile const int*)d.err & E_FATAL)) return;
     ag_chain c; c.jump = AG_NONE; c.tail = v; c.len = 0; c.flg = 0;
-    if (v < n_nodes) c = recs[v];
+    if (v < n_nodes) {
+        const u32 w = ag_forced_succ(d.node_w, d.eovf_head, d.eovf_target, d.eovf_next, d.indeg, d.pos_term, d.node_pos, v);
+        d.fnext[v] = w;
+        if (w != AG_NONE) { atomicOr(&d.node_w[w].misc, AG_NW_INTERIOR); d.fprev[w] = v; }
+        c.jump = w; c.len = 1; c.flg = (d.node_w[v].misc & AG_NW_HASCONTIG) ? 1u : 0u;
+    }
     sa[threadIdx.x] = c;
     __syncthreads();
     ag_chain *src = sa, *dst = sb;
@@ -1134,7 +1139,8 @@ __global__ void k_walk_to_host(DevView d, const u32* __restrict__ rank) {
 // Walk records arrive compacted in scan order, i.e. by non-decreasing start position, so `contain(previous emitted, this)` (AG:2176, AG:1897-1902)
 // reduces to "this walk's end does not pass the furthest end seen so far": emitted[i] = (i == 0) || E[i] > max(E[0 .. i-1]), E = the end offset
 // with the tail adjustment of AG:2164-2173 in the reference's own unsigned arithmetic.
-__global__ void k_sel_prepare(DevView d, const u32* __restrict__ walk_rank, u32* __restrict__ E) {
+__global__ void k_sel_prepare(DevView d, const u32* __restrict__ walk_rank, u32* __restrict__ E, u32* __restrict__ info) {
+    if (blockIdx.x == 0 && threadIdx.x < 8) info[threadIdx.x] = 0;   // [0] emitted walks, [1] their bases, [2] > 100 kbp trigger (set by k_sel_flag / k_sel_fill, later in the stream)
     AG_BAIL(d);
     AG_FOR_N(i, min(walk_rank[d.cand_cap], d.hwalk_cap)) {
         const ag_walk r = d.walks_sorted[i];
@@ -1158,9 +1164,11 @@ __global__ void k_sel_flag(DevView d, const u32* __restrict__ walk_rank, const u
 }
 // compacted materialisation inputs of the emitted walks + their records for the host
 __global__ void k_sel_fill(DevView d, const u32* __restrict__ walk_rank, const u32* __restrict__ flag, const u32* __restrict__ srank, const u32* __restrict__ soff,
-                           u32* __restrict__ sel_start, u64* __restrict__ sel_off, u32* __restrict__ sel_tails, ag_walk* __restrict__ sel_walks, u32* __restrict__ sel_off32) {
+                           u32* __restrict__ sel_start, u64* __restrict__ sel_off, u32* __restrict__ sel_tails, ag_walk* __restrict__ sel_walks, u32* __restrict__ sel_off32,
+                           u32* __restrict__ info) {
     AG_BAIL(d);
     const u32 nw = min(walk_rank[d.cand_cap], d.hwalk_cap);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { info[0] = srank[d.hwalk_cap]; info[1] = soff[d.hwalk_cap]; }
     if (soff[d.hwalk_cap] > d.bases_cap) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(d.err, E_BASES_CAP); return; }
     AG_FOR_N(i, nw) {
         if (!flag[i]) continue;
@@ -2159,7 +2167,7 @@ void AgDevice::enqueue_build() {
 }
 
 // forced-link chains, start candidates, components, replay, compaction of the walk records into host memory — queued behind the build
-void AgDevice::enqueue_walk() {
+void AgDevice::enqueue_walk(bool records_to_host) {
     Impl& m = *m_; cudaStream_t st = m.st; DevView& d = m.view;
     const size_t nc = m.node_cap;
     if (!m.cand_cap) m.cand_cap = (u32)std::max<size_t>(1u << 16, nc / 16);
@@ -2173,11 +2181,11 @@ void AgDevice::enqueue_walk() {
         d.indeg = m.indeg.p; d.fnext = m.fnext.p; d.chain_a = m.chain_a.p; d.chain_b = m.chain_b.p;
         k_uf_init<<<GS_BLOCKS, GS_T, 0, st>>>(d); launches_++;
         k_indeg<<<GS_BLOCKS, GS_T, 0, st>>>(d); launches_++;
-        k_links<<<GS_BLOCKS, GS_T, 0, st>>>(d); launches_++;
         ag_chain *a = m.chain_a.p, *b = m.chain_b.p;
-        k_rank_local<<<(unsigned)((nc + 1023) / 1024), 1024, 0, st>>>(a, d.nn_ptr, m.err.p); launches_++;
+        k_links_rank_local<<<(unsigned)((nc + 1023) / 1024), 1024, 0, st>>>(d, a); launches_++;
         for (int round = 0; round < m.rank_rounds; round++) {  // links that leave a 1024-node block: a fixed number of global rounds, more on request (E_RANK_MORE)
-            k_rank<<<GS_BLOCKS, GS_T, 0, st>>>(a, b, d.nn_ptr, m.err.p, round + 1 == m.rank_rounds ? 1 : 0); launches_++;
+            const bool last = round + 1 == m.rank_rounds;
+            k_rank<<<GS_BLOCKS, GS_T, 0, st>>>(a, b, d.nn_ptr, m.err.p, last ? 1 : 0, d.node_w, last && m.scanner.one_pass ? m.indeg.p : nullptr); launches_++;
             std::swap(a, b);
         }
         d.chain = a;
@@ -2185,8 +2193,8 @@ void AgDevice::enqueue_walk() {
         m.cand_rank.ensure(nc + 2); m.cand_node.ensure((size_t)m.cand_cap + 1); m.cand_label.ensure((size_t)m.cand_cap + 1);
         d.cand_rank = m.cand_rank.p; d.cand_node = m.cand_node.p; d.cand_label = m.cand_label.p;
         d.ncand_ptr = m.cand_rank.p + nc; d.cand_cap = m.cand_cap;
-        k_cand_flag<<<GS_BLOCKS, GS_T, 0, st>>>(d, m.indeg.p); launches_++;
-        m.scanner.run(m.indeg.p, m.cand_rank.p, nc, st);
+        if (m.scanner.one_pass) m.scanner.run(m.indeg.p, m.cand_rank.p, nc, st, 0, 1, d.nn_ptr);   // flags written by the last ranking round; scan over the device-side node count
+        else { k_cand_flag<<<GS_BLOCKS, GS_T, 0, st>>>(d, m.indeg.p); launches_++; m.scanner.run(m.indeg.p, m.cand_rank.p, nc, st); }
         k_cand_scatter<<<GS_BLOCKS, GS_T, 0, st>>>(d, m.indeg.p); launches_++;
     }
     // every walk starts at a chain head, so the candidate count bounds the number of walk records
@@ -2212,7 +2220,7 @@ void AgDevice::enqueue_walk() {
         m.walk_rank.ensure((size_t)m.cand_cap + 2);
         m.scanner.run(m.walk_used.p, m.walk_rank.p, m.cand_cap, st);
         k_walk_compact<<<GS_BLOCKS / 4, GS_T, 0, st>>>(d, m.walk_rank.p); launches_++;
-        k_walk_to_host<<<GS_BLOCKS / 4, GS_T, 0, st>>>(d, m.walk_rank.p); launches_++;
+        if (records_to_host) { k_walk_to_host<<<GS_BLOCKS / 4, GS_T, 0, st>>>(d, m.walk_rank.p); launches_++; }   // (the fused extension only ships the emitted ones)
     }
     chains_valid_ = true;
     m.walk_queued = true;
@@ -2262,15 +2270,12 @@ void AgDevice::enqueue_select() {
     m.h_selw.ensure(wc * sizeof(ag_walk) + 64); m.h_selo.ensure((wc + 2) * sizeof(u32) + 64); m.h_bases.ensure((size_t)m.bases_cap + 16);
     {
         Section sec(m.sections, st, &t_.select);
-        CK(cudaMemsetAsync(m.sel_info.p, 0, 8 * sizeof(u32), st));
-        k_sel_prepare<<<GS_BLOCKS / 4, GS_T, 0, st>>>(d, m.walk_rank.p, m.sel_E.p); launches_++;
+        k_sel_prepare<<<GS_BLOCKS / 4, GS_T, 0, st>>>(d, m.walk_rank.p, m.sel_E.p, m.sel_info.p); launches_++;   // (also clears sel_info)
         k_excl_max_scan<<<1, 1024, 0, st>>>(m.sel_E.p, m.sel_M.p, m.walk_rank.p + m.cand_cap, m.hwalk_cap); launches_++;
         k_sel_flag<<<GS_BLOCKS / 4, GS_T, 0, st>>>(d, m.walk_rank.p, m.sel_E.p, m.sel_M.p, m.sel_flag.p, m.sel_len.p, m.sel_info.p + 2); launches_++;
         m.scanner.run(m.sel_flag.p, m.sel_rank.p, wc, st);    // sel_rank[wc] = emitted walks
         m.scanner.run(m.sel_len.p, m.sel_soff.p, wc, st);     // sel_soff[wc] = their bases
-        CK(cudaMemcpyAsync(m.sel_info.p + 0, m.sel_rank.p + wc, sizeof(u32), cudaMemcpyDeviceToDevice, st));
-        CK(cudaMemcpyAsync(m.sel_info.p + 1, m.sel_soff.p + wc, sizeof(u32), cudaMemcpyDeviceToDevice, st));
-        k_sel_fill<<<GS_BLOCKS / 4, GS_T, 0, st>>>(d, m.walk_rank.p, m.sel_flag.p, m.sel_rank.p, m.sel_soff.p, m.sel_start.p, m.sel_off.p, m.sel_tails.p, m.sel_walks.p, m.sel_off32.p); launches_++;
+        k_sel_fill<<<GS_BLOCKS / 4, GS_T, 0, st>>>(d, m.walk_rank.p, m.sel_flag.p, m.sel_rank.p, m.sel_soff.p, m.sel_start.p, m.sel_off.p, m.sel_tails.p, m.sel_walks.p, m.sel_off32.p, m.sel_info.p); launches_++;   // (sel_info[0..1] = emitted walks, their bases)
     }
     {
         Section sec(m.sections, st, &t_.materialize);
@@ -2299,7 +2304,7 @@ void AgDevice::extend_emitted(std::vector<ag_walk>& emitted, char*& bases, std::
     emitted.clear(); offs.assign(1, 0); bases = nullptr; n_walks = 0;
     if (!m.build_queued && !m.n_nodes) { occupancy_begin(); return; }
     for (;;) {
-        enqueue_walk();
+        enqueue_walk(false);
         enqueue_select();
         occupancy_begin();
         if (!finish()) break;

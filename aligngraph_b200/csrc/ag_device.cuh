@@ -132,7 +132,7 @@ private:
     bool tma_off_ = false, attr_tma_done_ = false, fused_off_ = false;
     bool chains_valid_ = false, attr_done_ = false, keep_counts_ = false, section_timing_ = false;
     void enqueue_build();
-    void enqueue_walk();
+    void enqueue_walk(bool records_to_host = true);
     void enqueue_select();
     bool finish();
     void walk_sequential();

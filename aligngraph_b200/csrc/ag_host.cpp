@@ -1213,7 +1213,7 @@ void ag_make_contigs_begin(const std::vector<ag_walk>& walks, const std::vector<
     slots.resize(sel.size() * SLOT);
     char* const slot_base = slots.data();   // (the team's threads must not name the thread_local themselves: each would see its own, empty one)
     lap("sized");
-    const int nchunk = (int)std::min<size_t>((sel.size() + 511) / 512, (size_t)std::max(1, ag_team_size() * 2));
+    const int nchunk = (int)std::min<size_t>((sel.size() + 63) / 64, (size_t)std::max(1, ag_team_size() * 2));
     const size_t per = nchunk ? (sel.size() + (size_t)nchunk - 1) / (size_t)nchunk : 0;
     ag_parallel_chunks(nchunk, [&](int ch) {
       for (size_t i = (size_t)ch * per; i < std::min(sel.size(), ((size_t)ch + 1) * per); i++) {
