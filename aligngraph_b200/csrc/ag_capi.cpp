@@ -247,12 +247,16 @@ int ag_process(ag_ctx* ctx) {
 static void extend_unit_fused(AgDevice& dev, const AgReads& reads, const std::string& ref, AgUnitResult& r, u64& n_walks, u64& n_emitted) {
     auto t0 = std::chrono::steady_clock::now();
     std::vector<ag_walk> em; char* bases = nullptr; std::vector<u64> offs;
-    dev.extend_emitted(em, bases, offs, n_walks);
-    auto t1 = std::chrono::steady_clock::now();
-    std::vector<u32> sel(em.size());
-    for (size_t i = 0; i < sel.size(); i++) sel[i] = (u32)i;
+    std::vector<u32> sel;
     std::vector<AgContig> contigs; AgMakeState ms;
-    ag_make_contigs_begin(em, sel, bases, offs, contigs, ms);
+    auto begin = [&] {   // contig records + headers: needs the emitted walk records and offsets, not the bases
+        sel.resize(em.size());
+        for (size_t i = 0; i < sel.size(); i++) sel[i] = (u32)i;
+        ag_make_contigs_begin(em, sel, bases, offs, contigs, ms);
+    };
+    const bool begun = dev.extend_emitted(em, bases, offs, n_walks, begin);   // (begin runs while the device is still producing the bases)
+    auto t1 = std::chrono::steady_clock::now();
+    if (!begun) begin();
     ag_make_contigs_finish(em, sel, bases, offs, reads, contigs, ms, r.pre_text);
     ag_dedup_join(contigs);
     std::vector<unsigned char> occ;

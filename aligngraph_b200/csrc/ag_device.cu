@@ -1195,6 +1195,14 @@ __global__ void k_status(DevView d, const u32* __restrict__ counters, const u32*
     out[7] = sel ? sel[0] : 0u; out[8] = sel ? sel[1] : 0u; out[9] = sel ? sel[2] : 0u;   // fused extension: emitted walks, their bases, >100 kbp trigger
 }
 
+// fused extension, early hand-off: {error word, emitted walks, their bases, > 100 kbp trigger} straight into page-locked host memory, queued
+// behind the copies of the emitted walk records and offsets and in front of the materialisation — the host formats records and headers
+// while the bases are still being produced
+__global__ void k_status_early(DevView d, const u32* __restrict__ sel, volatile u32* __restrict__ host) {
+    if (blockIdx.x || threadIdx.x) return;
+    host[0] = (u32)(*d.err | *d.err_load); host[1] = sel[0]; host[2] = sel[1]; host[3] = sel[2];
+}
+
 // exact sequential replay including the 1000-position skip (AG:2194-2202); used only when a >100 kbp contig was emitted
 __global__ void k_walk_sequential(DevView d) {
     if (blockIdx.x || threadIdx.x) return;
@@ -1373,6 +1381,7 @@ struct AgDevice::Impl {
     u32 node_cap = 0, ovf_cap = 0, eovf_cap = 0, eovf_cap_init = 0, walk_cap = 0;
     u32 key_cap = 0, cand_cap = 0, hwalk_cap = 0, n_walks = 0; int rank_rounds = 2;   // global list-ranking rounds queued per step (chains that leave their 1024-node block); more on request (E_RANK_MORE)
     u32 unit_n_ref = 0; u64 unit_n_aln = 0;   // the unit the capacities above were last derived for
+    cudaEvent_t ev_early = nullptr;          // fused extension: emitted walk records + offsets are in host memory (the bases follow)
     PinnedBuf h_wrec;                        // compacted walk records, written by k_walk_compact straight into host memory
     DBuf<u32> status, walk_rank; DBuf<int> err_load; SectionTimes sections;
     bool key_cap_hooked = false; u32 node_cap_hook = 0, ovf_cap_hook = 0;   // test hooks (set_option): initial capacities instead of the size-derived ones
@@ -1412,7 +1421,7 @@ AgDevice::~AgDevice() {
     m.node_c.release(); m.node_w.release(); m.walks.release(); m.walks2.release(); m.cm1.release(); m.mat_detours.release(); m.tail_end.release(); m.pos_term.release(); m.cand_rank.release(); m.cand_node.release(); m.cand_label.release(); m.fprev.release(); m.msuf.release(); m.mnode.release(); m.indeg.release(); m.fnext.release(); m.chain_a.release(); m.chain_b.release(); m.hrec.release(); m.changed.release(); m.sel_off.release();
     m.contig_blob.release(); m.cdesc.release(); m.cruns.release(); m.raw.release(); m.exc_chr.release(); m.nl.release(); m.nl_blk.release(); m.rlen.release(); m.s_keep.release(); m.s_next.release(); m.s_aoff.release(); m.s_eoff.release(); m.s_lost.release(); m.ing.release(); m.exc_key.release(); m.srec.release(); m.stager.release();
     m.sel_E.release(); m.sel_M.release(); m.sel_flag.release(); m.sel_len.release(); m.sel_rank.release(); m.sel_soff.release(); m.sel_info.release(); m.sel_off32.release(); m.sel_walks.release(); m.h_selw.release(); m.h_selo.release();
-    m.h_wrec.release(); m.walk_rank.release(); m.status.release(); m.err_load.release(); m.sections.release();
+    if (m.ev_early) { cudaEventDestroy(m.ev_early); m.ev_early = nullptr; } m.h_wrec.release(); m.walk_rank.release(); m.status.release(); m.err_load.release(); m.sections.release();
     m.h_walks.release(); m.h_bases.release(); m.h_occ.release(); m.h_sel.release(); m.h_s.release();
     if (ev_mat0_) { cudaEventDestroy((cudaEvent_t)ev_mat0_); cudaEventDestroy((cudaEvent_t)ev_mat1_); }
     if (st2_) { cudaStreamSynchronize((cudaStream_t)st2_); cudaStreamDestroy((cudaStream_t)st2_); cudaEventDestroy((cudaEvent_t)ev_main_); cudaEventDestroy((cudaEvent_t)ev_reads_); }
@@ -2277,6 +2286,16 @@ void AgDevice::enqueue_select() {
         m.scanner.run(m.sel_len.p, m.sel_soff.p, wc, st);     // sel_soff[wc] = their bases
         k_sel_fill<<<GS_BLOCKS / 4, GS_T, 0, st>>>(d, m.walk_rank.p, m.sel_flag.p, m.sel_rank.p, m.sel_soff.p, m.sel_start.p, m.sel_off.p, m.sel_tails.p, m.sel_walks.p, m.sel_off32.p, m.sel_info.p); launches_++;   // (sel_info[0..1] = emitted walks, their bases)
     }
+    {   // emitted walk records + their offsets to page-locked host memory, then the early status block and its event: the host starts on the
+        // contig records while the materialisation below is still running
+        Section sec(m.sections, st, &t_.select);
+        const u32* n_sel = m.sel_info.p + 0;
+        k_to_host16<<<GS_BLOCKS / 4, GS_T, 0, st>>>((const uint4*)m.sel_walks.p, (uint4*)m.h_selw.p, n_sel, (u32)sizeof(ag_walk), 0, m.err.p); launches_++;
+        k_to_host16<<<GS_BLOCKS / 4, GS_T, 0, st>>>((const uint4*)m.sel_off32.p, (uint4*)m.h_selo.p, n_sel, 4u, 1, m.err.p); launches_++;
+        k_status_early<<<1, 32, 0, st>>>(d, m.sel_info.p, (volatile u32*)m.h_s.p + 16); launches_++;
+        if (!m.ev_early) CK(cudaEventCreateWithFlags(&m.ev_early, cudaEventDisableTiming));
+        CK(cudaEventRecord(m.ev_early, st));
+    }
     {
         Section sec(m.sections, st, &t_.materialize);
         const u32* n_sel = m.sel_info.p + 0;
@@ -2288,9 +2307,7 @@ void AgDevice::enqueue_select() {
         k_mat_nodes<<<GS_BLOCKS, GS_T, 0, st>>>(d, 0, d.nn_ptr, m.tail_end.p, m.out_bases.p); launches_++;
         k_mat_detours<<<148u * 8u, 256, 0, st>>>(d, m.mat_detours.p, m.counters.p + 4, m.out_bases.p); launches_++;
         k_mat_tails<<<GS_BLOCKS / 8, 128, 0, st>>>(d, m.sel_tails.p, m.sel_off.p, 0, n_sel, m.out_bases.p); launches_++;
-        // results to page-locked host memory: emitted walk records, their offsets, the bases (counts known to the device only)
-        k_to_host16<<<GS_BLOCKS / 4, GS_T, 0, st>>>((const uint4*)m.sel_walks.p, (uint4*)m.h_selw.p, n_sel, (u32)sizeof(ag_walk), 0, m.err.p); launches_++;
-        k_to_host16<<<GS_BLOCKS / 4, GS_T, 0, st>>>((const uint4*)m.sel_off32.p, (uint4*)m.h_selo.p, n_sel, 4u, 1, m.err.p); launches_++;
+        // the bases to page-locked host memory (count known to the device only)
         k_to_host16<<<GS_BLOCKS, GS_T, 0, st>>>((const uint4*)m.out_bases.p, (uint4*)m.h_bases.p, m.sel_info.p + 1, 1u, 0, m.err.p); launches_++;
     }
     m.select_queued = true;
@@ -2298,15 +2315,33 @@ void AgDevice::enqueue_select() {
 
 // extendContigs1 up to the emitted contigs as ONE queued step: walk, emission filter, materialisation, copies — and one synchronisation.
 // `emitted` = the walk records that pass the emission filter, in scan order; contig i = bases[offs[i], offs[i + 1]).
-void AgDevice::extend_emitted(std::vector<ag_walk>& emitted, char*& bases, std::vector<u64>& offs, u64& n_walks) {
+bool AgDevice::extend_emitted(std::vector<ag_walk>& emitted, char*& bases, std::vector<u64>& offs, u64& n_walks, const std::function<void()>& on_records) {
     CK(cudaSetDevice(dev_));
     Impl& m = *m_;
     emitted.clear(); offs.assign(1, 0); bases = nullptr; n_walks = 0;
-    if (!m.build_queued && !m.n_nodes) { occupancy_begin(); return; }
+    if (!m.build_queued && !m.n_nodes) { occupancy_begin(); return false; }
+    bool early = false;
     for (;;) {
         enqueue_walk(false);
         enqueue_select();
         occupancy_begin();
+        early = false;
+        if (on_records) {   // records + offsets of the emitted walks are in host memory before the bases: let the caller work on them meanwhile
+            CK(cudaEventSynchronize(m.ev_early));
+            volatile u32* he = (volatile u32*)m.h_s.p + 16;
+            if (!(he[0] & E_FATAL) && !he[3]) {
+                const u32 ns = he[1];
+                emitted.resize(ns); offs.assign((size_t)ns + 1, 0);
+                if (ns) {
+                    memcpy(emitted.data(), m.h_selw.p, (size_t)ns * sizeof(ag_walk));
+                    const u32* o32 = (const u32*)m.h_selo.p;
+                    for (u32 i = 0; i <= ns; i++) offs[i] = o32[i];
+                }
+                bases = (char*)m.h_bases.p;
+                on_records();
+                early = true;
+            }
+        }
         if (!finish()) break;
         enqueue_build();
     }
@@ -2336,9 +2371,11 @@ void AgDevice::extend_emitted(std::vector<ag_walk>& emitted, char*& bases, std::
         emitted.resize(sel.size());
         for (size_t i = 0; i < sel.size(); i++) emitted[i] = walks[sel[i]];
         t_.d2h_bytes += (size_t)nw * sizeof(ag_walk);
-        return;
+        return false;
     }
     const u32 ns = m.n_sel;
+    t_.d2h_bytes += (size_t)ns * sizeof(ag_walk) + m.sel_bases;
+    if (early && emitted.size() == ns) return true;   // what on_records saw is what the finished step produced
     emitted.resize(ns); offs.assign((size_t)ns + 1, 0);
     if (ns) {
         memcpy(emitted.data(), m.h_selw.p, (size_t)ns * sizeof(ag_walk));
@@ -2346,7 +2383,7 @@ void AgDevice::extend_emitted(std::vector<ag_walk>& emitted, char*& bases, std::
         for (u32 i = 0; i <= ns; i++) offs[i] = o32[i];
     }
     bases = (char*)m.h_bases.p;
-    t_.d2h_bytes += (size_t)ns * sizeof(ag_walk) + m.sel_bases;
+    return false;
 }
 
 void AgDevice::walk_sequential() {

@@ -4,6 +4,7 @@
 #include "ag_types.h"
 #include <string>
 #include <vector>
+#include <functional>
 
 struct AgUnitInput {
     const char* ref;            // unit bases followed by the contig-insertion tail (AG:981-1036), n_pos bytes
@@ -92,7 +93,10 @@ public:
     // the walk records), materialisation and the copies to page-locked host memory; a single synchronisation.  `emitted` = the walk records that
     // pass the emission filter, in scan order; contig i = bases[offs[i], offs[i + 1]) (valid until the next call); the occupancy bitmap has been
     // queued as well (occupancy_wait)
-    void extend_emitted(std::vector<ag_walk>& emitted, char*& bases, std::vector<u64>& offs, u64& n_walks);
+    // on_records (optional) is called, possibly more than once (each call supersedes the earlier ones), as soon as `emitted` and `offs` are in host
+    // memory and `bases` points to where the bases WILL be: the caller may build records and headers while the materialisation runs.  Returns
+    // true when the last on_records call saw the final result (false: the caller starts from the returned arrays).
+    bool extend_emitted(std::vector<ag_walk>& emitted, char*& bases, std::vector<u64>& offs, u64& n_walks, const std::function<void()>& on_records = nullptr);
     bool fused_extend() const { return !fused_off_; }
     // materialise the selected walks' base strings (loop bases + tail); contig i occupies bases[offs[i], offs[i + 1]).  `bases` points into
     // a page-locked buffer owned by the device object (valid until the next call); the post passes patch and read it in place
