@@ -399,7 +399,15 @@ def b200_arm(args):
             "clocks": clock_info,
             "roofline": {"bound": "hbm", "kernel": "k_build_tma" if tma else "k_build", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                          "traffic": traffic, "alg_bytes_per_launch": int(alg), "ms_per_launch": round(nodes_ms, 4),
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"},
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+                         # SURVEY.md §8(d)'s per-pair figure for the bucketing kernel, B_K1 = 2*ceil(L/4) + 32 + 16*(L-k) (it assumes one materialised 16-byte event
+                         # per left-mate k-mer; this formulation never writes those, so `achieved` above uses the bytes it really moves): reported beside it
+                         "survey_b_k1": (lambda bk1, pairs, t_sweep, t_bucket: {
+                             "bytes_per_pair": bk1, "bytes_per_launch": int(bk1 * pairs),
+                             "frac_sweep_kernel": round(bk1 * pairs / t_sweep / 1e6 / peak, 4),
+                             "frac_prep_sort_stage_sweep": round(bk1 * pairs / t_bucket / 1e6 / peak, 4)})(
+                             2 * ((L + 3) // 4) + 32 + 16 * (L - cfg["kmer"]), stats["n_aln"] / n_launch, nodes_ms,
+                             (stats["ms_prep"] + stats["ms_sort"] + stats["ms_nodes"]) / n_launch)},
             "device_ms_per_step": {k[3:]: round(stats[k] / K, 4) for k in stats if k.startswith("ms_")},
             "counts": {"alignments": int(tot_aln / K), "nodes": int(tot_nodes), "tile_keys": int(tot_keys), "units": units},
             "host_s_per_step": {"device_section": round(stats["s_device_section"] / K, 4), "post_passes": round(stats["s_post"] / K, 4)},
