@@ -38,9 +38,12 @@ template <class T> static inline T ag_host_cas(T* p, T c, T v) { T o = *p; if (o
 // (lanes 0-30) and its lane 31 replays the NEXT position as a halo, so that the item an alignment resolves to at q + 1 reaches the
 // lane of q by one shuffle (the edge of the call that starts at q, AG:1590-1623, is then known inside the node sweep).  A tile owns
 // AG_TPOS positions and additionally needs every alignment that touches its halo position.
-#define AG_TILE 256
+#ifndef AG_TWARPS
+#define AG_TWARPS 8          // warps per tile (a compile-time knob for tuning builds only: tools/build_variants.py)
+#endif
+#define AG_TILE (32 * AG_TWARPS)
 #define AG_WPOS 31
-#define AG_TPOS (8 * AG_WPOS)
+#define AG_TPOS (AG_TWARPS * AG_WPOS)
 AG_HD void ag_tile_range(u32 lo, u32 hi, u32 n_tiles, u32& t0, u32& t1) {  // tiles that must see an alignment touching [lo, hi]
     t0 = lo ? (lo - 1) / AG_TPOS : 0u;
     t1 = hi / AG_TPOS;
@@ -618,6 +621,7 @@ struct ag_walkctx {
     u32* walk_next;           // per node: next node of the walk that marked it, or NONE
     const ag_chain* chain;    // forced-link chains
     const ag_hrec* hrec;      // per chain head: packed hop record (valid for live, non-interior nodes)
+    const ag_hdet* hdet;      // per chain head with hrec.tcm != NONE: where the contiMer detour of its tail lands (precomputed: the replay's longest dependent chain)
     // exact sequential replay (skip rule, AG:2194-2202): a chain can be entered at an interior node, so marks are kept as a marked SUFFIX
     // per chain, indexed by the chain's tail: msuf = nodes marked at the tail end, mnode = first marked node
     u32* msuf; u32* mnode; const u32* fprev;
@@ -690,12 +694,12 @@ AG_HD ag_walk ag_walk_from(const ag_walkctx& w, u32 start) {
         if (cnt == 1) { w.walk_next[t] = pick; v = pick; vmisc = pmisc; h = ph; continue; }
         if (h.tcm != AG_NONE) {
             // switch to the contiMer thread (AG:2047-2057), run to its terminal (AG:2064-2072), try to re-enter (AG:2093-2136)
-            const ag_cm m = w.cmt.cm[h.tcm];
-            len += m.term - m.chain; ext = 1;
+            const ag_hdet dt = w.hdet[v];   // (v heads the chain whose tail is t)
+            len += dt.len; ext = 1;
             w.nw[t].misc = tmisc | AG_NW_DETOUR;
-            const u32 z = w.chain_pos[m.term];
+            const u32 z = dt.z;
             u32 live = 0, item = AG_NONE; ag_nodew irec;
-            for (u32 x = w.pos_node[z]; x < w.pos_node[z + 1]; x++) { ag_nodew xr = w.nw[x]; if (!(xr.misc & AG_NW_TRAV)) { live++; item = x; irec = xr; } }
+            for (u32 x = dt.first; x < dt.first + dt.n; x++) { ag_nodew xr = w.nw[x]; if (!(xr.misc & AG_NW_TRAV)) { live++; item = x; irec = xr; } }
             u32 pick2 = AG_NONE, cnt2 = 0; ag_nodew prec2;
             if (live == 1) cnt2 = ag_live_succ(w, item, irec, pick2, prec2);
             if (cnt2 == 1) { w.walk_next[t] = pick2; v = pick2; vmisc = prec2.misc; h = w.hrec[pick2]; continue; }
@@ -717,6 +721,13 @@ AG_HD ag_hrec ag_make_hrec(const ag_chain& c, const ag_nodew& tail, const ag_cmt
     const u32 c0 = cmt.start[p];
     h.tcm = (cmt.start[p + 1] - c0 == 1 && cmt.cm[c0].chain != cmt.cm[c0].term) ? c0 : AG_NONE;
     return h;
+}
+
+// detour record of a chain head whose hop record has tcm != NONE (k_hrec)
+AG_HD ag_hdet ag_make_hdet(const ag_cmtab& cmt, const u32* chain_pos, const u32* pos_node, u32 tcm) {
+    const ag_cm m = cmt.cm[tcm];
+    ag_hdet dt; dt.z = chain_pos[m.term]; dt.first = pos_node[dt.z]; dt.n = pos_node[dt.z + 1] - dt.first; dt.len = m.term - m.chain;
+    return dt;
 }
 
 // ---- exact sequential replay with chains ----------------------------------------------------------------------------------

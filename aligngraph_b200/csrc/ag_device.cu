@@ -295,7 +295,7 @@ struct DevView {
     u32* eovf_head; u32* eovf_target; u32* eovf_next; u32* eovf_count; u32 eovf_cap;
     u32* walk_next; u32* parent; u32* cmin; u32* cmax;
     u32* cand_rank; u32* cand_node; u32* cand_label;
-    unsigned char* pos_term; u32* indeg; u32* fnext; u32* fprev; u32* msuf; u32* mnode; ag_chain* chain_a; ag_chain* chain_b; const ag_chain* chain; ag_hrec* hrec; int* changed;
+    unsigned char* pos_term; u32* indeg; u32* fnext; u32* fprev; u32* msuf; u32* mnode; ag_chain* chain_a; ag_chain* chain_b; const ag_chain* chain; ag_hrec* hrec; ag_hdet* hdet; int* changed;
     ag_walk* walks; ag_walk* walks_sorted; u32* walk_count; u32 walk_cap; u32* walk_used;
     int* err;
     int k, iv, coverage;
@@ -975,7 +975,7 @@ __global__ void k_uf_flatten(DevView d) {
 __device__ __forceinline__ ag_walkctx make_ctx(const DevView& d) {
     ag_walkctx w;
     w.nw = d.node_w; w.node_pos = d.node_pos; w.pos_node = d.pos_node; w.ovf_head = d.eovf_head; w.ovf_target = d.eovf_target;
-    w.ovf_next = d.eovf_next; w.cmt = d.cmt; w.chain_pos = d.chain_pos; w.walk_next = d.walk_next; w.chain = d.chain; w.hrec = d.hrec; w.msuf = d.msuf; w.mnode = d.mnode; w.fprev = d.fprev;
+    w.ovf_next = d.eovf_next; w.cmt = d.cmt; w.chain_pos = d.chain_pos; w.walk_next = d.walk_next; w.chain = d.chain; w.hrec = d.hrec; w.hdet = d.hdet; w.msuf = d.msuf; w.mnode = d.mnode; w.fprev = d.fprev;
     return w;
 }
 __device__ __forceinline__ void push_walk(const DevView& d, ag_walk r) {
@@ -1064,7 +1064,9 @@ __global__ void k_hrec(DevView d) {
     AG_FOR_N(i, *d.ncand_ptr) {
         const u32 v = d.cand_node[i];
         const ag_chain c = d.chain[v];
-        d.hrec[v] = ag_make_hrec(c, d.node_w[c.tail], d.cmt, d.node_pos[c.tail]);
+        const ag_hrec h = ag_make_hrec(c, d.node_w[c.tail], d.cmt, d.node_pos[c.tail]);
+        d.hrec[v] = h;
+        if (h.tcm != AG_NONE) d.hdet[v] = ag_make_hdet(d.cmt, d.chain_pos, d.pos_node, h.tcm);
     }
 }
 
@@ -1073,7 +1075,11 @@ __global__ void k_hrec(DevView d) {
 // largest component (a few hundred candidates, every one two or three dependent loads of never-touched lines).  So all 32 lanes first
 // pull the records the replay is going to read — walk record, hop record, position, founder string of every candidate, and the walk
 // records of the chain tails and of their successors — into L1/L2.
+#ifdef AG_WALK_TOUCH   // experiment: a real (unused) load instead of the prefetch hint
+__device__ __forceinline__ void prefetch_l1(const void* p) { unsigned t; asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(t) : "l"(p)); }
+#else
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
+#endif
 __global__ void k_walk_components(DevView d, u32* next_cand) {
     AG_BAIL(d);
     const u32 n_cand = *d.ncand_ptr;
@@ -1087,29 +1093,38 @@ __global__ void k_walk_components(DevView d, u32* next_cand) {
         const u32 r = d.chain[d.cand_node[i0]].tail;
         if (d.parent[r] != r) continue;
         const u32 lo = d.cmin[r], hi = d.cmax[r];
-        if (hi - lo >= 8) {
-            for (u32 i = lo + lane; i <= hi; i += 32) {
-                if (d.cand_label[i] != r) continue;
-                const u32 v = d.cand_node[i];
-                prefetch_l1(&d.node_w[v]); prefetch_l1(&d.node_pos[v]);
-                const ag_hrec h = d.hrec[v];
-                prefetch_l1(&d.node_w[h.tail]); prefetch_l1(&d.node_pos[h.tail]); prefetch_l1(&d.walk_next[h.tail]); prefetch_l1(&d.node_sref[2 * (size_t)h.tail]);
-                if (h.ts0 != AG_NONE) prefetch_l1(&d.node_w[h.ts0]);
-                if (h.ts1 != AG_NONE) prefetch_l1(&d.node_w[h.ts1]);
+        // A typical unit has a few hundred components of a few hundred candidates each (one per contig region) and thousands of tiny ones: the
+        // kernel's duration is the replay of ONE large component on one lane.  Pulling a whole component into L1 up front does not survive
+        // the other components replayed on the same SM, so the records are pulled one window of 32 candidates ahead of the replay.
+        auto pull = [&](u32 base) {
+            const u32 i = base + lane;
+            if (i > hi || d.cand_label[i] != r) return;
+            const u32 v = d.cand_node[i];
+            prefetch_l1(&d.node_w[v]); prefetch_l1(&d.node_pos[v]);
+            const ag_hrec h = d.hrec[v];
+            prefetch_l1(&d.node_w[h.tail]); prefetch_l1(&d.node_pos[h.tail]); prefetch_l1(&d.walk_next[h.tail]); prefetch_l1(&d.node_sref[2 * (size_t)h.tail]);
+            if (h.ts0 != AG_NONE) { prefetch_l1(&d.node_w[h.ts0]); prefetch_l1(&d.hrec[h.ts0]); }
+            if (h.ts1 != AG_NONE) { prefetch_l1(&d.node_w[h.ts1]); prefetch_l1(&d.hrec[h.ts1]); }
+            if (h.tcm != AG_NONE) { const ag_hdet dt = d.hdet[v]; if (dt.n) prefetch_l1(&d.node_w[dt.first]); }
+        };
+        const bool windowed = hi - lo >= 8;
+        if (windowed) { pull(lo); __syncwarp(); }
+        ag_walkctx w = make_ctx(d);
+        for (u32 base = lo; base <= hi; base += 32) {
+            if (windowed && base + 32 <= hi) pull(base + 32);
+            __syncwarp();
+            if (lane == 0) {
+                const u32 end = min(hi, base + 31u);
+                for (u32 i = base; i <= end; i++) {
+                    if (d.cand_label[i] != r) continue;
+                    const u32 v = d.cand_node[i];
+                    if (d.node_w[v].misc & AG_NW_TRAV) continue;
+                    d.walks[i] = ag_walk_from(w, v);   // slot = candidate index: no counter on the sequential path; k_walk_compact compacts the used slots in order
+                    d.walk_used[i] = 1;
+                }
             }
             __syncwarp();
         }
-        if (lane == 0) {
-            ag_walkctx w = make_ctx(d);
-            for (u32 i = lo; i <= hi; i++) {
-                if (d.cand_label[i] != r) continue;
-                u32 v = d.cand_node[i];
-                if (d.node_w[v].misc & AG_NW_TRAV) continue;
-                d.walks[i] = ag_walk_from(w, v);   // slot = candidate index: no counter on the sequential path; k_walk_compact compacts the used slots in order
-                d.walk_used[i] = 1;
-            }
-        }
-        __syncwarp();
       }
     }
 }
@@ -1364,7 +1379,7 @@ struct AgDevice::Impl {
     DBuf<u32> pos_node;
     DBuf<ag_nodec> node_c; DBuf<ag_nodew> node_w; DBuf<u32> node_sref, node_pos, node_cc;
     DBuf<u32> eovf_head, eovf_target, eovf_next;
-    DBuf<u32> walk_next, parent, cmin, cmax, walk_used; DBuf<ag_walk> walks, walks2; DBuf<ag_cm1> cm1; DBuf<MatItem> mat_detours; DBuf<u32> tail_end; u32 n_cand = 0; DBuf<unsigned char> pos_term; DBuf<u32> indeg, fnext, fprev, msuf, mnode, cand_rank, cand_node, cand_label; DBuf<ag_chain> chain_a, chain_b; DBuf<ag_hrec> hrec; DBuf<int> changed;
+    DBuf<u32> walk_next, parent, cmin, cmax, walk_used; DBuf<ag_walk> walks, walks2; DBuf<ag_cm1> cm1; DBuf<MatItem> mat_detours; DBuf<u32> tail_end; u32 n_cand = 0; DBuf<unsigned char> pos_term; DBuf<u32> indeg, fnext, fprev, msuf, mnode, cand_rank, cand_node, cand_label; DBuf<ag_chain> chain_a, chain_b; DBuf<ag_hrec> hrec; DBuf<ag_hdet> hdet; DBuf<int> changed;
     DBuf<unsigned char> out_bases, occ; DBuf<u32> sel_start, sel_tails; DBuf<u64> sel_off;
     PinnedBuf h_walks, h_bases, h_occ, h_sel, h_s;   // h_s: page-locked landing zone of the scalar read-backs (a pageable destination makes every copy a synchronous staged transfer)
     // text ingestion (ag_ingest.cuh)
@@ -1418,7 +1433,7 @@ AgDevice::~AgDevice() {
     for (int i = 0; i < 4; i++) m.scanner.lvl[i].release();
     m.scanner.state.release();
     m.cm.release(); m.cthreads.release(); m.aln.release(); m.ext.release(); m.alnp.release(); m.fast.release(); m.pool_c.release(); m.pool_w.release(); m.ovf_node.release(); m.err.release();
-    m.node_c.release(); m.node_w.release(); m.walks.release(); m.walks2.release(); m.cm1.release(); m.mat_detours.release(); m.tail_end.release(); m.pos_term.release(); m.cand_rank.release(); m.cand_node.release(); m.cand_label.release(); m.fprev.release(); m.msuf.release(); m.mnode.release(); m.indeg.release(); m.fnext.release(); m.chain_a.release(); m.chain_b.release(); m.hrec.release(); m.changed.release(); m.sel_off.release();
+    m.node_c.release(); m.node_w.release(); m.walks.release(); m.walks2.release(); m.cm1.release(); m.mat_detours.release(); m.tail_end.release(); m.pos_term.release(); m.cand_rank.release(); m.cand_node.release(); m.cand_label.release(); m.fprev.release(); m.msuf.release(); m.mnode.release(); m.indeg.release(); m.fnext.release(); m.chain_a.release(); m.chain_b.release(); m.hrec.release(); m.hdet.release(); m.changed.release(); m.sel_off.release();
     m.contig_blob.release(); m.cdesc.release(); m.cruns.release(); m.raw.release(); m.exc_chr.release(); m.nl.release(); m.nl_blk.release(); m.rlen.release(); m.s_keep.release(); m.s_next.release(); m.s_aoff.release(); m.s_eoff.release(); m.s_lost.release(); m.ing.release(); m.exc_key.release(); m.srec.release(); m.stager.release();
     m.sel_E.release(); m.sel_M.release(); m.sel_flag.release(); m.sel_len.release(); m.sel_rank.release(); m.sel_soff.release(); m.sel_info.release(); m.sel_off32.release(); m.sel_walks.release(); m.h_selw.release(); m.h_selo.release();
     if (m.ev_early) { cudaEventDestroy(m.ev_early); m.ev_early = nullptr; } m.h_wrec.release(); m.walk_rank.release(); m.status.release(); m.err_load.release(); m.sections.release();
@@ -2215,7 +2230,7 @@ void AgDevice::enqueue_walk(bool records_to_host) {
     CK(cudaMemsetAsync(m.walk_used.p, 0, ((size_t)m.cand_cap + 1) * sizeof(u32), st));
     {
         Section sec(m.sections, st, &t_.components);
-        m.hrec.ensure(nc + 1); d.hrec = m.hrec.p;
+        m.hrec.ensure(nc + 1); d.hrec = m.hrec.p; m.hdet.ensure(nc + 1); d.hdet = m.hdet.p;
         k_hrec<<<GS_BLOCKS / 4, GS_T, 0, st>>>(d); launches_++;
         k_uf_tails<<<GS_BLOCKS / 4, GS_T, 0, st>>>(d); launches_++;
         k_uf_flatten<<<GS_BLOCKS / 4, GS_T, 0, st>>>(d); launches_++;

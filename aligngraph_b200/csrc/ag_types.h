@@ -106,6 +106,7 @@ struct alignas(16) ag_chain { u32 jump, tail, len, flg; };  // flg = NUMBER of n
 // Everything a walk needs when it arrives at a chain head, in one 32-byte record: the chain's tail, length and contig flag, and the
 // tail's successors / static misc bits / mate offset / detour contiMer.  One load per chain hop instead of three dependent ones (chain -> tail -> successors).
 struct alignas(32) ag_hrec { u32 tail, len, flg, ts0, ts1, tmisc, tmoff, tcm; };   // tcm: index of the ONLY contiMer at the tail's position when it is not a terminal (the detour of AG:2047-2057 is possible), else NONE
+struct alignas(16) ag_hdet { u32 z, first, n, len; };   // per chain head whose tail can take the contiMer detour (hrec.tcm != NONE): terminal position z of the thread, its nodes [first, first + n), contiMers stepped over
 
 // bases a walk contributes to its contig: the loop's bases plus s[1..] of the last node when it ended in the k-mer graph (AG:2164-2168)
 AG_HD u32 ag_walk_tail_len(const ag_walk& r) { u32 slen = r.tail_soff_len >> 16; return (((r.flags >> 1) & 3) != 1 && slen > 1) ? slen - 1 : 0; }

@@ -25,7 +25,7 @@ public:
     std::vector<u32> pos_node, node_pos, node_sref, eovf_head, eovf_target, eovf_next, walk_next, parent;
     std::vector<ag_nodeb> nodeb;  // final order
     std::vector<ag_nodec> node_c; std::vector<ag_nodew> node_w; std::vector<ag_cm1> cm1;
-    std::vector<unsigned char> pos_term; std::vector<u32> indeg, fnext, fprev, msuf, mnode; std::vector<ag_chain> chain; std::vector<ag_hrec> hrec; bool use_chains = false;
+    std::vector<unsigned char> pos_term; std::vector<u32> indeg, fnext, fprev, msuf, mnode; std::vector<ag_chain> chain; std::vector<ag_hrec> hrec; std::vector<ag_hdet> hdet; bool use_chains = false;
     std::vector<ag_nodeb> ovf_node; std::vector<u32> ovf_next; u32 ovf_count = 0; int err = 0;
     u32 n_nodes = 0;
     bool fallback_used = false;
@@ -212,7 +212,7 @@ public:
 
     ag_walkctx ctx() {
         ag_walkctx w; w.nw = node_w.data(); w.node_pos = node_pos.data(); w.pos_node = pos_node.data(); w.ovf_head = eovf_head.data();
-        w.ovf_target = eovf_target.data(); w.ovf_next = eovf_next.data(); w.cmt = cmt(); w.chain_pos = in.chain_pos; w.walk_next = walk_next.data(); w.chain = chain.data(); w.hrec = hrec.data(); w.msuf = msuf.data(); w.mnode = mnode.data(); w.fprev = fprev.data();
+        w.ovf_target = eovf_target.data(); w.ovf_next = eovf_next.data(); w.cmt = cmt(); w.chain_pos = in.chain_pos; w.walk_next = walk_next.data(); w.chain = chain.data(); w.hrec = hrec.data(); w.hdet = hdet.data(); w.msuf = msuf.data(); w.mnode = mnode.data(); w.fprev = fprev.data();
         return w;
     }
     u32 find(u32 x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; }
@@ -255,7 +255,11 @@ public:
         for (u32 v = 0; v < n_nodes; v++) if (live(v)) { n_live++; if (!(node_w[v].misc & AG_NW_INTERIOR)) { cand.push_back(v); max_chain = std::max(max_chain, chain[v].len); } }
         n_heads = (u32)cand.size();
         hrec.assign(n_nodes, ag_hrec{});   // k_hrec
-        for (u32 h : cand) hrec[h] = ag_make_hrec(chain[h], node_w[chain[h].tail], ct, node_pos[chain[h].tail]);
+        hdet.assign(n_nodes, ag_hdet{});
+        for (u32 h : cand) {
+            hrec[h] = ag_make_hrec(chain[h], node_w[chain[h].tail], ct, node_pos[chain[h].tail]);
+            if (hrec[h].tcm != AG_NONE) hdet[h] = ag_make_hdet(ct, in.chain_pos, pos_node.data(), hrec[h].tcm);
+        }
         // components over chain tails (k_uf_tails, k_uf_flatten)
         for (u32 h : cand) {
             const u32 t = chain[h].tail;
