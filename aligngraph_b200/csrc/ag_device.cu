@@ -2,18 +2,23 @@
 // coverage filter (AG:1904-1918) and extension walk (AG:1954-2204).  Integer / indexing work, HBM- and latency-bound: no tensor
 // cores.  See DESIGN.md §3-§5 for the formulation, the HBM layout and the per-kernel algorithmic bytes.
 //
-//   k_cm_count / k_cm_fill / k_cm_sort / k_cm1   contiMer table (CSR + per-position summary) from the uploaded contig threads  (AG:884-1177)
-//   k_prep        1 thread / alignment   resolve left mate, touch range, tile count, clean-alignment bit      (AG:1657-1679)
+//   k_scan_onepass   every prefix sum of the step: chained scan with decoupled look-back, one launch
+//   k_chain_expand / k_cm_count / k_cm_fill / k_cm_sort / k_cm1   contig-thread descriptors -> chain arrays -> contiMer table (CSR + summary)  (AG:884-1177)
+//   k_prep        1 thread / alignment   resolve left mate, touch range, tile count, clean / linear bits                (AG:1657-1679)
 //   k_keys        1 thread / alignment   emit (tile, alignment) keys in alignment order
 //   k_rs_hist / k_rs_scatter   stable LSD radix sort, 5-bit digits: alignments bucketed by 248-position tile, order preserved
-//   k_build       1 CTA / tile, 1 thread / position (+ 1 halo lane per warp)   ordered first-compatible clustering (AG:1353-1587),
-//                 coverage filter + consensus base (AG:1904-1918, 1944-1952) and the common-case edges (AG:1590-1623) in one sweep
+//   k_stage       8 lanes / tile key     prepared header + oriented 4-bit codes of the left mate -> one contiguous record per key
+//   k_build_tma   1 CTA / tile, 1 thread / position (+ 1 halo lane per warp)   records staged by cp.async.bulk + mbarrier; ordered
+//                 first-compatible clustering (AG:1353-1587), coverage filter + consensus base (AG:1904-1918, 1944-1952) and the
+//                 common-case edges (AG:1590-1623) in one sweep   (k_build: the same sweep with per-thread staging, reads > ~500 bp)
 //   k_posfix / k_succ   tile blocks -> position order, successor-item bits -> node indices
 //   k_edges       generic edge sweep, flagged tiles only                                                          (AG:1590-1623)
-//   k_indeg / k_links / k_rank_local / k_rank / k_cand_* / k_hrec   forced-link chains, start candidates, hop records
+//   k_indeg / k_links_rank_local / k_rank / k_cand_scatter / k_hrec   forced-link chains, start candidates, hop + detour records
 //   k_uf_*        union-find over chain tails: independent walk components
 //   k_walk_components (1 warp / component) | k_walk_sequential (skip rule)   exact replay of the greedy walk    (AG:1972-2204)
-//   k_mat_*       base strings of the emitted walks; k_occupancy  bitmap for the scaffold gap test              (AG:2428)
+//   k_walk_compact, k_sel_*, k_excl_max_scan   walk records in scan order, emission filter (AG:2176-2189) as a prefix maximum
+//   k_mat_*       base strings of the emitted walks; k_to_host16 copies to page-locked memory; k_occupancy  bitmap for the scaffold gap test (AG:2428)
+//   ag_ingest.cuh: k_nl_*, k_rd_*, k_sam_*   text ingestion (reads FASTA, SAM), k_cov_marks, k_verify_placements
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cstdio>
@@ -134,8 +139,33 @@ __global__ void k_scan_apply(const u32* __restrict__ in, u32* __restrict__ out, 
 // CTAs are dispatched in blockIdx order, so every predecessor a CTA waits for is resident or finished.
 __device__ __forceinline__ u64 ld_state(const u64* p) { u64 v; asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ void st_state(u64* p, u64 v) { asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
+// the scan's operator: + (identity 0), or max over u32 (identity 0: the emission filter's prefix maximum)
+template <bool MAX> __device__ __forceinline__ u32 scan_op(u32 a, u32 b) { return MAX ? max(a, b) : a + b; }
+// exclusive block scan of one value per thread (SCAN_T threads), total = the block's reduction
+template <bool MAX> __device__ __forceinline__ u32 block_excl_scan_op(u32 v, u32* smem /* 33 */, u32& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    u32 x = v;   // inclusive inside the warp
+    for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= o) x = scan_op<MAX>(x, y); }
+    if (lane == 31) smem[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        const u32 w = lane < nw ? smem[lane] : 0u;
+        u32 sx = w;
+        for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(0xFFFFFFFFu, sx, o); if (lane >= o) sx = scan_op<MAX>(sx, y); }
+        const u32 up = __shfl_up_sync(0xFFFFFFFFu, sx, 1);
+        smem[lane] = lane ? up : 0u;   // exclusive over the warps
+        if (lane == 31) smem[32] = sx;
+    }
+    __syncthreads();
+    const u32 upx = __shfl_up_sync(0xFFFFFFFFu, x, 1);
+    const u32 r = scan_op<MAX>(smem[warp], lane ? upx : 0u);
+    total = smem[32];
+    __syncthreads();
+    return r;
+}
 // n_ptr (optional): the number of elements is only known on the device (at most n_cap, which sizes the grid): blocks behind it leave at once, the
 // total still goes to out[n_cap] and the entries between are not written.
+template <bool MAX>
 __global__ void __launch_bounds__(SCAN_T) k_scan_onepass(const u32* in, u32* out, u64* __restrict__ state, size_t n_cap, const u32* __restrict__ n_ptr, u32 epoch, int write_total) {
     __shared__ u32 sm[33];
     __shared__ u32 s_prefix;
@@ -151,8 +181,8 @@ __global__ void __launch_bounds__(SCAN_T) k_scan_onepass(const u32* in, u32* out
     } else {
         for (int i = 0; i < SCAN_I; i++) v[i] = (base + i < n) ? in[base + i] : 0;
     }
-    for (int i = 0; i < SCAN_I; i++) s += v[i];
-    u32 total; u32 ex = block_excl_scan(s, sm, total);
+    for (int i = 0; i < SCAN_I; i++) s = scan_op<MAX>(s, v[i]);
+    u32 total; u32 ex = block_excl_scan_op<MAX>(s, sm, total);
     const u64 tag = (u64)epoch << 34;
     if (threadIdx.x == 0) { s_prefix = 0; st_state(state + b, tag | ((u64)(b == 0 ? 2 : 1) << 32) | total); }
     if (b > 0 && threadIdx.x < 32) {
@@ -167,21 +197,21 @@ __global__ void __launch_bounds__(SCAN_T) k_scan_onepass(const u32* in, u32* out
             const u32 incl = __ballot_sync(0xFFFFFFFFu, flag == 2);
             const u32 first = incl ? (u32)__ffs(incl) - 1 : 31u;
             u32 x = lane <= first ? (u32)w : 0u;
-            for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, o);
-            run += x;
+            for (int o = 16; o; o >>= 1) x = scan_op<MAX>(x, __shfl_xor_sync(0xFFFFFFFFu, x, o));
+            run = scan_op<MAX>(run, x);
             if (incl) break;
         }
-        if (lane == 0) { s_prefix = run; st_state(state + b, tag | (2ull << 32) | (u32)(run + total)); }
+        if (lane == 0) { s_prefix = run; st_state(state + b, tag | (2ull << 32) | scan_op<MAX>(run, total)); }
     }
     __syncthreads();
-    ex += s_prefix;
+    ex = scan_op<MAX>(ex, s_prefix);
     if (base + SCAN_I <= n && (((size_t)out) & 15) == 0) {
         uint4 a, c;
-        a.x = ex; ex += v[0]; a.y = ex; ex += v[1]; a.z = ex; ex += v[2]; a.w = ex; ex += v[3];
-        c.x = ex; ex += v[4]; c.y = ex; ex += v[5]; c.z = ex; ex += v[6]; c.w = ex; ex += v[7];
+        a.x = ex; ex = scan_op<MAX>(ex, v[0]); a.y = ex; ex = scan_op<MAX>(ex, v[1]); a.z = ex; ex = scan_op<MAX>(ex, v[2]); a.w = ex; ex = scan_op<MAX>(ex, v[3]);
+        c.x = ex; ex = scan_op<MAX>(ex, v[4]); c.y = ex; ex = scan_op<MAX>(ex, v[5]); c.z = ex; ex = scan_op<MAX>(ex, v[6]); c.w = ex; ex = scan_op<MAX>(ex, v[7]);
         *(uint4*)(out + base) = a; *(uint4*)(out + base + 4) = c;
     } else {
-        for (int i = 0; i < SCAN_I; i++) { if (base + i < n) out[base + i] = ex; ex += v[i]; }
+        for (int i = 0; i < SCAN_I; i++) { if (base + i < n) out[base + i] = ex; ex = scan_op<MAX>(ex, v[i]); }
     }
     if (write_total && b == last_b && threadIdx.x == SCAN_T - 1) out[n_cap] = ex;
 }
@@ -193,13 +223,22 @@ struct Scanner {
     bool one_pass = getenv("AG_SCAN_TWOPASS") == nullptr;   // (A/B switch for measurements)
     u64* launches = nullptr;
     // n_ptr (one-pass kernel only; callers check one_pass): device-side element count <= n
+    // exclusive prefix MAXIMUM (identity 0) of in[0, min(*n_ptr, n)): out[i] = max(in[0 .. i-1]); one launch, any size
+    void run_max(const u32* in, u32* out, size_t n, const u32* n_ptr, cudaStream_t st) {
+        if (n == 0) return;
+        const size_t nb = (n + SCAN_B - 1) / SCAN_B;
+        if (nb > state.cap) { state.ensure(nb); CK(cudaMemsetAsync(state.p, 0, state.cap * sizeof(u64), st)); }
+        epoch = (epoch + 1) & 0x3FFFFFFFu; if (!epoch) epoch = 1;
+        k_scan_onepass<true><<<(unsigned)nb, SCAN_T, 0, st>>>(in, out, state.p, n, n_ptr, epoch, 0);
+        if (launches) ++*launches;
+    }
     void run(const u32* in, u32* out, size_t n, cudaStream_t st, int depth = 0, int write_total = 1, const u32* n_ptr = nullptr) {
         if (n == 0) { if (write_total) CK(cudaMemsetAsync(out, 0, sizeof(u32), st)); return; }
         size_t nb = (n + SCAN_B - 1) / SCAN_B;
         if (one_pass) {
             if (nb > state.cap) { state.ensure(nb); CK(cudaMemsetAsync(state.p, 0, state.cap * sizeof(u64), st)); }
             epoch = (epoch + 1) & 0x3FFFFFFFu; if (!epoch) epoch = 1;
-            k_scan_onepass<<<(unsigned)nb, SCAN_T, 0, st>>>(in, out, state.p, n, n_ptr, epoch, write_total);
+            k_scan_onepass<false><<<(unsigned)nb, SCAN_T, 0, st>>>(in, out, state.p, n, n_ptr, epoch, write_total);
             if (launches) ++*launches;
             return;
         }
@@ -1075,11 +1114,7 @@ __global__ void k_hrec(DevView d) {
 // largest component (a few hundred candidates, every one two or three dependent loads of never-touched lines).  So all 32 lanes first
 // pull the records the replay is going to read — walk record, hop record, position, founder string of every candidate, and the walk
 // records of the chain tails and of their successors — into L1/L2.
-#ifdef AG_WALK_TOUCH   // experiment: a real (unused) load instead of the prefetch hint
-__device__ __forceinline__ void prefetch_l1(const void* p) { unsigned t; asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(t) : "l"(p)); }
-#else
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
-#endif
 __global__ void k_walk_components(DevView d, u32* next_cand) {
     AG_BAIL(d);
     const u32 n_cand = *d.ncand_ptr;
@@ -2295,7 +2330,8 @@ void AgDevice::enqueue_select() {
     {
         Section sec(m.sections, st, &t_.select);
         k_sel_prepare<<<GS_BLOCKS / 4, GS_T, 0, st>>>(d, m.walk_rank.p, m.sel_E.p, m.sel_info.p); launches_++;   // (also clears sel_info)
-        k_excl_max_scan<<<1, 1024, 0, st>>>(m.sel_E.p, m.sel_M.p, m.walk_rank.p + m.cand_cap, m.hwalk_cap); launches_++;
+        if (m.scanner.one_pass) m.scanner.run_max(m.sel_E.p, m.sel_M.p, m.hwalk_cap, m.walk_rank.p + m.cand_cap, st);
+        else { k_excl_max_scan<<<1, 1024, 0, st>>>(m.sel_E.p, m.sel_M.p, m.walk_rank.p + m.cand_cap, m.hwalk_cap); launches_++; }
         k_sel_flag<<<GS_BLOCKS / 4, GS_T, 0, st>>>(d, m.walk_rank.p, m.sel_E.p, m.sel_M.p, m.sel_flag.p, m.sel_len.p, m.sel_info.p + 2); launches_++;
         m.scanner.run(m.sel_flag.p, m.sel_rank.p, wc, st);    // sel_rank[wc] = emitted walks
         m.scanner.run(m.sel_len.p, m.sel_soff.p, wc, st);     // sel_soff[wc] = their bases

@@ -9,7 +9,6 @@ sys.path.insert(0, ROOT)
 from aligngraph_b200 import build as b  # noqa: E402
 
 VARIANTS = {
-    "walk_touch": ["-DAG_WALK_TOUCH=1"],                         # replay records pulled with real loads instead of prefetch hints
     "tile7": ["-DAG_TWARPS=7"],                                  # 7-warp tiles (217 positions): 56 registers at 5 CTAs per SM
     "tma_minb5": ["-DAG_TMA_MINB=5"],                            # TMA-staged node sweep at 48 registers / 5 CTAs per SM
     "tma_minb4": ["-DAG_TMA_MINB=4"],                            # ... at 64 registers / 4 CTAs per SM
