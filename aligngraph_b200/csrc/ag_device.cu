@@ -350,10 +350,23 @@ struct DevView {
 // ---------------------------------------------------------------------------------------------------------------------------
 // k_prep / k_keys
 // ---------------------------------------------------------------------------------------------------------------------------
+// 16-byte vector copies of whole records (sizes are multiples of 16 and the arrays come from cudaMalloc): a 48-byte record leaves as three
+// 128-bit stores instead of twelve 32-bit ones
+template <class T> __device__ __forceinline__ void st_rec16(T* dst, const T& v) {
+    static_assert(sizeof(T) % 16 == 0, "record size");
+    uint4 t[sizeof(T) / 16]; memcpy(t, &v, sizeof(T));
+    for (unsigned k = 0; k < sizeof(T) / 16; k++) reinterpret_cast<uint4*>(dst)[k] = t[k];
+}
+template <class T> __device__ __forceinline__ T ld_rec16(const T* src) {
+    static_assert(sizeof(T) % 16 == 0, "record size");
+    uint4 t[sizeof(T) / 16];
+    for (unsigned k = 0; k < sizeof(T) / 16; k++) t[k] = reinterpret_cast<const uint4*>(src)[k];
+    T v; memcpy(&v, t, sizeof(T)); return v;
+}
 __global__ void k_prep(DevView d) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d.n_aln) return;
-    ag_aln a = d.aln[i];
+    ag_aln a = ld_rec16(d.aln + i);
     u32 len = d.reads.len[a.pair];
     ag_prep_out o = ag_prep(a, d.ext, len, (u32)d.k);
     // every aligned position of either mate must lie inside the unit (the reference indexes genome[0] with them, AG:1369)
@@ -365,7 +378,7 @@ __global__ void k_prep(DevView d) {
     if (bad) { atomicOr(d.err, E_BAD_ALN); o.any = 0; }
     ag_fast f = ag_fast_prep(o.p, o.lo, o.span, i);
     if (o.any) ag_fast_classify(f, o.p, d.many_prefix, d.lin_prefix, d.cm1);
-    d.alnp[i] = o.p; d.fast[i] = f;
+    st_rec16(d.alnp + i, o.p); st_rec16(d.fast + i, f);
     u32 nt = 0;
     if (o.any) { u32 t0, t1; ag_tile_range(o.lo, o.lo + o.span, d.n_tiles, t0, t1); nt = t1 - t0 + 1; }
     d.ntiles[i] = nt;
