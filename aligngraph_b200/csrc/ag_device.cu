@@ -1067,34 +1067,49 @@ __global__ void k_rank(const ag_chain* __restrict__ in, ag_chain* __restrict__ o
 }
 
 // forced links + list ranking, step 1, in one kernel: a block of 1024 consecutive nodes derives its nodes' forced links (k_links' work: fnext,
-// fprev, the INTERIOR mark) straight into shared memory and runs the pointer jumping there.  Forced links point to higher node indices and
-// chains are short-range (the next node is the next position), so almost every chain is finished here; what remains are links that leave the
-// block, resolved by a few global k_rank rounds.  (The chain records never make the round trip through global memory in between.)
+// fprev, the INTERIOR mark) and contracts the links that stay inside the block by pointer jumping in shared memory.  Forced links point to higher
+// node indices and chains are short-range (the next node is the next position), so almost every chain is finished here; what remains are links
+// that leave the block, resolved by a few global k_rank rounds.
+// The rounds are bound by shared-memory traffic, so the block-local record is ONE 64-bit word {jump: 11 bits (local index, 0x7FF = closed), tail: 10,
+// len: 11, flg: 11}; it is updated in place (read phase, barrier, write phase) and only by threads whose record is still open — the open
+// fraction of a chain of length L after r rounds is (L - 2^r) / L.  A link that leaves the block is kept per node (s_ext) and attached to
+// the finished records through their local tail.
 __global__ void __launch_bounds__(1024) k_links_rank_local(DevView d, ag_chain* recs) {
-    __shared__ ag_chain sa[1024], sb[1024];
+    __shared__ unsigned long long s_rec[1024];
+    __shared__ u32 s_ext[1024];
     const u32 n_nodes = *d.nn_ptr;
-    const u32 b0 = blockIdx.x * 1024u, v = b0 + threadIdx.x;
+    const u32 b0 = blockIdx.x * 1024u, t = threadIdx.x, v = b0 + t;
     if (b0 >= n_nodes || (*(volatile const int*)d.err & E_FATAL)) return;
-    ag_chain c; c.jump = AG_NONE; c.tail = v; c.len = 0; c.flg = 0;
+    constexpr u32 CLOSED = 0x7FFu;
+    auto pack = [](u32 jump, u32 tail, u32 len, u32 flg) { return (unsigned long long)jump | ((unsigned long long)tail << 11) | ((unsigned long long)len << 21) | ((unsigned long long)flg << 32); };
+    u32 ext = AG_NONE, jl = CLOSED, len = 0, flg = 0;
     if (v < n_nodes) {
         const u32 w = ag_forced_succ(d.node_w, d.eovf_head, d.eovf_target, d.eovf_next, d.indeg, d.pos_term, d.node_pos, v);
         d.fnext[v] = w;
         if (w != AG_NONE) { atomicOr(&d.node_w[w].misc, AG_NW_INTERIOR); d.fprev[w] = v; }
-        c.jump = w; c.len = 1; c.flg = (d.node_w[v].misc & AG_NW_HASCONTIG) ? 1u : 0u;
+        if (w != AG_NONE && w - b0 < 1024u) jl = w - b0; else ext = w;
+        len = 1; flg = (d.node_w[v].misc & AG_NW_HASCONTIG) ? 1u : 0u;
     }
-    sa[threadIdx.x] = c;
+    unsigned long long me = pack(jl, t, len, flg);
+    s_rec[t] = me; s_ext[t] = ext;
     __syncthreads();
-    ag_chain *src = sa, *dst = sb;
-    for (int r = 0; r < 10; r++) {   // (2^10 = block size: enough for a chain through the whole block; most blocks are done after a few rounds)
-        c = src[threadIdx.x];
-        const bool open = c.jump != AG_NONE && c.jump - b0 < 1024u;
-        if (open) { ag_chain j = src[c.jump - b0]; c.len += j.len; c.flg += j.flg; c.tail = j.tail; c.jump = j.jump; }
-        dst[threadIdx.x] = c;
-        const int any = __syncthreads_or(open ? 1 : 0);
-        ag_chain* t = src; src = dst; dst = t;
-        if (!any) break;
+    for (int r = 0; r < 10; r++) {   // (2^10 = block size: enough for a chain through the whole block)
+        const u32 j = (u32)me & 0x7FFu;
+        const bool open = j != CLOSED;
+        unsigned long long o = 0;
+        if (open) o = s_rec[j];
+        if (!__syncthreads_or(open ? 1 : 0)) break;          // every read of this round is done (and: nobody is open any more)
+        if (open) {   // me = me . o : jump and tail from o, lengths and contig flags add up (len, flg <= 1024: no carry between the fields)
+            me = ((me >> 21) + (o >> 21)) << 21 | (o & 0x1FFFFFull);
+            s_rec[t] = me;
+        }
+        __syncthreads();
     }
-    if (v < n_nodes) recs[v] = src[threadIdx.x];
+    if (v < n_nodes) {
+        const u32 tl = (u32)(me >> 11) & 0x3FFu;
+        ag_chain c; c.jump = s_ext[tl]; c.tail = b0 + tl; c.len = (u32)(me >> 21) & 0x7FFu; c.flg = (u32)(me >> 32) & 0x7FFu;
+        recs[v] = c;
+    }
 }
 
 // walk starts can only be live nodes that are not chain-interior: compact them (in node order) so that a component's replay does not
