@@ -998,21 +998,19 @@ __global__ void k_uf_init(DevView d) {
 // leave through a contiMer detour (interior nodes always see exactly one untraversed successor), so the relations a walk can follow are:
 // tail -> chains of its live successors (AG:2022-2032) and tail -> chains of the live nodes at its detour's terminal position
 // (AG:2093-2114).  One thread per start candidate (= chain head), ~1/66 of the nodes.
-__global__ void k_uf_tails(DevView d) {
+__global__ void k_uf_tails(DevView d) {   // (after k_hrec: the hop and detour records already hold the tail's successors and where its detour lands)
     AG_BAIL(d);
     AG_FOR_N(i, *d.ncand_ptr) {
-    const u32 t = d.chain[d.cand_node[i]].tail;
-    const ag_nodew w = d.node_w[t];
-    if (w.succ0 != AG_NONE && !(d.node_w[w.succ0].misc & AG_NW_FILTERED)) uf_unite(d.parent, t, d.chain[w.succ0].tail);
-    if (w.succ1 != AG_NONE && !(d.node_w[w.succ1].misc & AG_NW_FILTERED)) uf_unite(d.parent, t, d.chain[w.succ1].tail);
-    if (w.misc & AG_NW_OVF)
+    const u32 v = d.cand_node[i];
+    const ag_hrec h = d.hrec[v];
+    const u32 t = h.tail;
+    if (h.ts0 != AG_NONE && !(d.node_w[h.ts0].misc & AG_NW_FILTERED)) uf_unite(d.parent, t, d.chain[h.ts0].tail);
+    if (h.ts1 != AG_NONE && !(d.node_w[h.ts1].misc & AG_NW_FILTERED)) uf_unite(d.parent, t, d.chain[h.ts1].tail);
+    if (h.tmisc & AG_NW_OVF)
         for (u32 o = d.eovf_head[t]; o != AG_NONE; o = d.eovf_next[o]) { u32 s = d.eovf_target[o]; if (!(d.node_w[s].misc & AG_NW_FILTERED)) uf_unite(d.parent, t, d.chain[s].tail); }
-    const u32 p = d.node_pos[t], c0 = d.cmt.start[p];
-    if (d.cmt.start[p + 1] - c0 != 1) continue;
-    const ag_cm m = d.cmt.cm[c0];
-    if (m.chain == m.term) continue;
-    const u32 z = d.chain_pos[m.term];
-    for (u32 x = d.pos_node[z]; x < d.pos_node[z + 1]; x++) if (!(d.node_w[x].misc & AG_NW_FILTERED)) uf_unite(d.parent, t, d.chain[x].tail);
+    if (h.tcm == AG_NONE) continue;
+    const ag_hdet dt = d.hdet[v];
+    for (u32 x = dt.first; x < dt.first + dt.n; x++) if (!(d.node_w[x].misc & AG_NW_FILTERED)) uf_unite(d.parent, t, d.chain[x].tail);
     }
 }
 __global__ void k_uf_flatten(DevView d) {
